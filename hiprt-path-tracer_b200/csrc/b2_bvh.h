@@ -1,0 +1,313 @@
+/*
+ * b2_bvh.h -- the compressed 8-wide BVH ("CW8") the B200 path traverses, and its traversal.
+ *
+ * This replaces HIPRT's geometry object + hiprtGeomTraversalClosest/AnyHit
+ * (/root/reference/src/Device/includes/Intersect.h:38-69,212-215,284-293) and, for parity, must return what the
+ * reference's CPU octree returns (src/Renderer/BVH.h:132-223): the hit with the smallest t among triangles with
+ * t > 1e-7, t >= ray.minT, not rejected by the filter (self-hit, src/Device/functions/FilterFunction.h:22-35),
+ * computed with the reference's exact Moeller-Trumbore operation order (src/Renderer/Triangle.h:20-63).
+ *
+ * Layout in HBM (built on the host by b2_bvh_build.cpp, SAH binned BVH2 collapsed to 8-wide):
+ *   nodes      : 80-byte records = 5 x 16 B, fetched as five 128-bit loads
+ *     word 0-2 : float3 origin of the node's quantisation grid
+ *     word 3   : ex | ey<<8 | ez<<16 (biased exponents of the per-axis grid step) | imask<<24 (slots holding inner nodes)
+ *     word 4   : index of the first inner child (inner children are contiguous, in slot order)
+ *     word 5   : index of the first triangle referenced by this node's leaf slots
+ *     word 6-7 : meta[8]   per slot: 0 = empty; inner = 0b001_11sss (sss = slot); leaf = unary count (1,3,7)<<5 | offset
+ *     word 8-19: qlo_x[8] qlo_y[8] qlo_z[8] qhi_x[8] qhi_y[8] qhi_z[8]   child boxes, 8-bit, conservative
+ *   triangles  : 48-byte records = 3 x 16 B in leaf order: (A.xyz, prim id), (B-A, 0), (C-A, 0)
+ * Children are assigned to slots so that slot s is the nearest child for rays of octant s; the traversal order of
+ * a node's hit children is then a pure bit trick (slot ^ (7 - octant)), no per-node sorting.
+ * (Scheme after Ylitie, Karras, Laine: "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs",
+ * HPG 2017 -- restated from the paper; no code of the reference or of HIPRT is involved.)
+ *
+ * Algorithmic bytes per traversal step (DESIGN.md section "Roofline"): S_node = 80 B, S_tri = 48 B.
+ */
+#ifndef B2_BVH_H
+#define B2_BVH_H
+
+#include "b2_math.h"
+
+struct B2Node
+{
+    float ox, oy, oz;
+    uint32_t exyz_imask;
+    uint32_t child_base;
+    uint32_t tri_base;
+    uint8_t meta[8];
+    uint8_t qlo_x[8], qlo_y[8], qlo_z[8];
+    uint8_t qhi_x[8], qhi_y[8], qhi_z[8];
+};
+static_assert(sizeof(B2Node) == 80, "CW8 node must be 80 bytes");
+
+struct B2Tri
+{
+    float ax, ay, az;
+    int32_t prim;
+    float e1x, e1y, e1z, pad1;
+    float e2x, e2y, e2z, pad2;
+};
+static_assert(sizeof(B2Tri) == 48, "CW8 triangle must be 48 bytes");
+
+/* Device-side descriptor; `b2pt_bvh_device_handle()` returns a device pointer to one of these and that pointer
+ * is what goes into HIPRTRenderData::GPU_BVH. */
+struct B2BvhDevice
+{
+    const B2Node* nodes;
+    const B2Tri* tris;
+    uint32_t node_count;
+    uint32_t tri_count;
+};
+
+struct B2Hit
+{
+    float t;      /* -1 when no hit (reference: hiprtHit::t default) */
+    float u, v;   /* barycentric weights of vertices B and C */
+    int prim;     /* -1 when no hit */
+    /* un-normalised geometric normal = cross(B-A, C-A); the caller normalises (Triangle.h:53) */
+    V3 ng;
+};
+
+/* traversal statistics (instrumented variant only): "traversal steps per ray" of the north star */
+struct B2TraversalCounters
+{
+    unsigned long long rays, nodes, tris;
+};
+
+#define B2_STACK_ENTRIES 24
+
+/* Exact restatement of Triangle::intersect (Triangle.h:20-63) on precomputed edges: edge1 = B-A and edge2 = C-A are
+ * the same fp32 subtractions the reference performs per test, done once at build time. */
+B2_HD bool b2_intersect_triangle(V3 org, V3 dir, V3 a, V3 edge1, V3 edge2, float& out_t, float& out_u, float& out_v)
+{
+    const float EPSILON = 0.0000001f;
+    V3 h = cross(dir, edge2);
+    float det = dot(edge1, h);
+    if (det > -EPSILON && det < EPSILON)
+        return false;
+    float f = 1.0f / det;
+    V3 s = org - a;
+    float u = f * dot(s, h);
+    if (u < 0.0f || u > 1.0f)
+        return false;
+    V3 q = cross(s, edge1);
+    float v = f * dot(dir, q);
+    if (v < 0.0f || u + v > 1.0f)
+        return false;
+    float t = f * dot(edge2, q);
+    if (t > EPSILON)
+    {
+        out_t = t;
+        out_u = u;
+        out_v = v;
+        return true;
+    }
+    return false;
+}
+
+B2_HD uint32_t b2_bfind(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return 31u - (uint32_t)__clz((int)x);
+#else
+    return 31u - (uint32_t)__builtin_clz(x);
+#endif
+}
+B2_HD uint32_t b2_popc(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
+#if defined(__CUDA_ARCH__)
+struct B2NodeRaw { uint4 q0, q1, q2, q3, q4; };
+__device__ __forceinline__ B2NodeRaw b2_load_node(const B2Node* nodes, uint32_t index)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(nodes + index);
+    B2NodeRaw r;
+    r.q0 = __ldg(p + 0);
+    r.q1 = __ldg(p + 1);
+    r.q2 = __ldg(p + 2);
+    r.q3 = __ldg(p + 3);
+    r.q4 = __ldg(p + 4);
+    return r;
+}
+#endif
+
+/*
+ * One traversal. ANY_HIT = false: closest hit (ties: first found wins, as the reference's strict `<`).
+ * ANY_HIT = true: returns at the first triangle hit with t < t_max (shadow rays; for opaque scenes this is what the
+ * reference's closest-hit-then-compare loop decides, Intersect.h:295-322).
+ * `skip_prim` is the reference's last_hit_primitive_index self-intersection filter.
+ * `stack` points to B2_STACK_ENTRIES uint2-sized slots private to the calling thread (shared memory on the GPU).
+ */
+template <bool ANY_HIT>
+B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, B2TraversalCounters* counters)
+{
+    B2Hit best;
+    best.t = -1.0f;
+    best.u = best.v = 0.0f;
+    best.prim = -1;
+    best.ng = v3(0.0f);
+    if (bvh.node_count == 0)
+        return best;
+
+    float t_far = t_max;
+
+    /* direction reciprocal, guarded against 0 (the slab test may be conservative; the triangle test is exact) */
+    const float tiny = 1.0e-30f;
+    float idx = 1.0f / (fabsf(dir.x) > tiny ? dir.x : (dir.x < 0.0f ? -tiny : tiny));
+    float idy = 1.0f / (fabsf(dir.y) > tiny ? dir.y : (dir.y < 0.0f ? -tiny : tiny));
+    float idz = 1.0f / (fabsf(dir.z) > tiny ? dir.z : (dir.z < 0.0f ? -tiny : tiny));
+    const uint32_t octant = (dir.x < 0.0f ? 4u : 0u) | (dir.y < 0.0f ? 2u : 0u) | (dir.z < 0.0f ? 1u : 0u);
+    const uint32_t oct_inv = 7u - octant;
+
+    int sp = 0;
+    uint32_t group_base = 0;            /* node group: index of first child node */
+    uint32_t group_bits = 0x80000000u;  /* bits 24..31: pending inner children (by traversal priority); bits 0..7: imask */
+
+    unsigned long long n_nodes = 0, n_tris = 0;
+
+    while (true)
+    {
+        uint32_t tri_base = 0, tri_bits = 0;
+
+        if (group_bits > 0x00FFFFFFu)
+        {
+            const uint32_t child_bit = b2_bfind(group_bits);
+            const uint32_t slot = (child_bit - 24u) ^ oct_inv;
+            const uint32_t imask = group_bits & 0xFFu;
+            const uint32_t node_index = group_base + b2_popc(imask & ~(0xFFFFFFFFu << slot));
+            group_bits &= ~(1u << child_bit);
+            if (group_bits > 0x00FFFFFFu)
+            {
+                if (sp < B2_STACK_ENTRIES)
+                    stack[sp] = ((uint64_t)group_base << 32) | group_bits;
+                sp++; /* overflow is counted but dropped; the builder bounds the depth well below the stack size */
+            }
+
+            n_nodes++;
+#if defined(__CUDA_ARCH__)
+            const B2NodeRaw raw = b2_load_node(bvh.nodes, node_index);
+            const float nox = __uint_as_float(raw.q0.x), noy = __uint_as_float(raw.q0.y), noz = __uint_as_float(raw.q0.z);
+            const uint32_t exyz = raw.q0.w;
+            const uint32_t n_child_base = raw.q1.x, n_tri_base = raw.q1.y;
+            const uint32_t meta_lo = raw.q1.z, meta_hi = raw.q1.w;
+            const uint32_t qw[12] = { raw.q2.x, raw.q2.y, raw.q2.z, raw.q2.w, raw.q3.x, raw.q3.y, raw.q3.z, raw.q3.w, raw.q4.x, raw.q4.y, raw.q4.z, raw.q4.w };
+#else
+            const B2Node& nd = bvh.nodes[node_index];
+            const float nox = nd.ox, noy = nd.oy, noz = nd.oz;
+            const uint32_t exyz = nd.exyz_imask;
+            const uint32_t n_child_base = nd.child_base, n_tri_base = nd.tri_base;
+            uint32_t meta_lo, meta_hi, qw[12];
+            {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(nd.meta);
+                meta_lo = w[0];
+                meta_hi = w[1];
+                for (int k = 0; k < 12; k++)
+                    qw[k] = w[2 + k];
+            }
+#endif
+            /* grid step 2^(e-127) per axis, folded into the reciprocal direction */
+            const float sx = b2_uint_as_float((exyz & 0xFFu) << 23) * idx;
+            const float sy = b2_uint_as_float(((exyz >> 8) & 0xFFu) << 23) * idy;
+            const float sz = b2_uint_as_float(((exyz >> 16) & 0xFFu) << 23) * idz;
+            const float bx = (nox - org.x) * idx;
+            const float by = (noy - org.y) * idy;
+            const float bz = (noz - org.z) * idz;
+
+            uint32_t hit_bits = 0;
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+            {
+                const uint32_t meta = ((c < 4 ? meta_lo : meta_hi) >> ((c & 3) * 8)) & 0xFFu;
+                if (meta == 0)
+                    continue;
+                const int w = c >> 2, sh = (c & 3) * 8;
+                const float lox = (float)((qw[0 + w] >> sh) & 0xFFu), loy = (float)((qw[2 + w] >> sh) & 0xFFu), loz = (float)((qw[4 + w] >> sh) & 0xFFu);
+                const float hix = (float)((qw[6 + w] >> sh) & 0xFFu), hiy = (float)((qw[8 + w] >> sh) & 0xFFu), hiz = (float)((qw[10 + w] >> sh) & 0xFFu);
+                const float tx0 = (dir.x < 0.0f ? hix : lox) * sx + bx, tx1 = (dir.x < 0.0f ? lox : hix) * sx + bx;
+                const float ty0 = (dir.y < 0.0f ? hiy : loy) * sy + by, ty1 = (dir.y < 0.0f ? loy : hiy) * sy + by;
+                const float tz0 = (dir.z < 0.0f ? hiz : loz) * sz + bz, tz1 = (dir.z < 0.0f ? loz : hiz) * sz + bz;
+                /* widened by a few ulps so fp32 rounding in the slab arithmetic can never cull a box the exact
+                 * triangle test would hit */
+                const float t_enter = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f)) * 0.9999995f;
+                const float t_exit = fminf(fminf(tx1, ty1), fminf(tz1, t_far)) * 1.0000005f;
+                if (t_enter <= t_exit)
+                {
+                    const bool inner = (meta & 0x18u) == 0x18u && (meta >> 5) == 1u;
+                    const uint32_t bit_index = inner ? (24u + ((meta & 7u) ^ oct_inv)) : (meta & 0x1Fu);
+                    hit_bits |= (meta >> 5) << bit_index;
+                }
+            }
+            group_base = n_child_base;
+            group_bits = (hit_bits & 0xFF000000u) | (exyz >> 24);
+            tri_base = n_tri_base;
+            tri_bits = hit_bits & 0x00FFFFFFu;
+        }
+        else
+        {
+            group_bits = 0;
+        }
+
+        while (tri_bits != 0)
+        {
+            const uint32_t k = b2_bfind(tri_bits);
+            tri_bits &= ~(1u << k);
+            n_tris++;
+#if defined(__CUDA_ARCH__)
+            const float4* tp = reinterpret_cast<const float4*>(bvh.tris + tri_base + k);
+            const float4 ta = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+            const int prim = __float_as_int(ta.w);
+            const V3 a = v3(ta.x, ta.y, ta.z), e1 = v3(t1.x, t1.y, t1.z), e2 = v3(t2.x, t2.y, t2.z);
+#else
+            const B2Tri& tr = bvh.tris[tri_base + k];
+            const int prim = tr.prim;
+            const V3 a = v3(tr.ax, tr.ay, tr.az), e1 = v3(tr.e1x, tr.e1y, tr.e1z), e2 = v3(tr.e2x, tr.e2y, tr.e2z);
+#endif
+            if (prim == skip_prim)
+                continue;
+            float t, u, v;
+            if (!b2_intersect_triangle(org, dir, a, e1, e2, t, u, v))
+                continue;
+            if (ANY_HIT)
+            {
+                if (t < t_max)
+                {
+                    best.t = t; best.u = u; best.v = v; best.prim = prim; best.ng = cross(e1, e2);
+                    if (counters) { counters->rays += 1; counters->nodes += n_nodes; counters->tris += n_tris; }
+                    return best;
+                }
+            }
+            else if (t < t_far)
+            {
+                /* strictly closer. Equal-t candidates keep the first one found, like the reference's `<`; which
+                 * one is "first" depends on the acceleration structure (the documented "ties excepted"). */
+                best.t = t; best.u = u; best.v = v; best.prim = prim; best.ng = cross(e1, e2);
+                t_far = t;
+            }
+        }
+
+        if (group_bits <= 0x00FFFFFFu)
+        {
+            if (sp == 0)
+                break;
+            sp--;
+            if (sp < B2_STACK_ENTRIES)
+            {
+                const uint64_t e = stack[sp];
+                group_base = (uint32_t)(e >> 32);
+                group_bits = (uint32_t)e;
+            }
+            else
+                group_bits = 0;
+        }
+    }
+    if (counters) { counters->rays += 1; counters->nodes += n_nodes; counters->tris += n_tris; }
+    return best;
+}
+
+#endif

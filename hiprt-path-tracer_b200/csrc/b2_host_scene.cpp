@@ -1,0 +1,276 @@
+/* b2_host_scene.cpp -- see b2_host_scene.h for what this restates and why. */
+#include "b2_host_scene.h"
+
+#include "b2_material.h"
+#include "b2pt_alias_table.h"
+
+#include <chrono>
+#include <cmath>
+
+namespace
+{
+/* hippt::clamp on the host = fminf(max, fmaxf(min, v)) (HostDeviceCommon/Math.h:257-258) */
+inline float clamp01(float v) { return fminf(1.0f, fmaxf(0.0f, v)); }
+inline float clampf(float lo, float hi, float v) { return fminf(hi, fmaxf(lo, v)); }
+inline float maxf_ref(float a, float b) { return a > b ? a : b; }
+
+struct SafeMaterial
+{
+    float f[B2MAT_FLOAT_COUNT];
+    int dielectric_priority;
+};
+
+/* CPUMaterial::make_safe, MaterialCPU.h:156-215 */
+SafeMaterial make_safe(const float* rec)
+{
+    SafeMaterial m;
+    for (int i = 0; i < B2MAT_FLOAT_COUNT; i++)
+        m.f[i] = rec[i];
+    auto clamp_rgb01 = [&](int i) { for (int k = 0; k < 3; k++) m.f[i + k] = clamp01(m.f[i + k]); };
+
+    clamp_rgb01(B2MAT_base_color_r);
+    m.f[B2MAT_metallic] = clamp01(m.f[B2MAT_metallic]);
+    clamp_rgb01(B2MAT_metallic_F82_r);
+    clamp_rgb01(B2MAT_metallic_F90_r);
+    m.f[B2MAT_anisotropy] = clamp01(m.f[B2MAT_anisotropy]);
+    m.f[B2MAT_anisotropy_rotation] = clamp01(m.f[B2MAT_anisotropy_rotation]);
+    m.f[B2MAT_second_roughness_weight] = clamp01(m.f[B2MAT_second_roughness_weight]);
+    m.f[B2MAT_second_roughness] = clamp01(m.f[B2MAT_second_roughness]);
+
+    m.f[B2MAT_specular] = clamp01(m.f[B2MAT_specular]);
+    m.f[B2MAT_specular_tint] = clamp01(m.f[B2MAT_specular_tint]);
+    clamp_rgb01(B2MAT_specular_color_r);
+    m.f[B2MAT_specular_darkening] = clamp01(m.f[B2MAT_specular_darkening]);
+
+    m.f[B2MAT_coat] = clamp01(m.f[B2MAT_coat]);
+    clamp_rgb01(B2MAT_coat_medium_absorption_r);
+    m.f[B2MAT_coat_roughness] = clampf(B2_ROUGHNESS_CLAMP, 1.0f, m.f[B2MAT_coat_roughness]);
+    m.f[B2MAT_coat_roughening] = clamp01(m.f[B2MAT_coat_roughening]);
+    m.f[B2MAT_coat_darkening] = clamp01(m.f[B2MAT_coat_darkening]);
+    m.f[B2MAT_coat_anisotropy] = clamp01(m.f[B2MAT_coat_anisotropy]);
+    m.f[B2MAT_coat_anisotropy_rotation] = clamp01(m.f[B2MAT_coat_anisotropy_rotation]);
+
+    m.f[B2MAT_sheen] = clamp01(m.f[B2MAT_sheen]);
+    m.f[B2MAT_sheen_roughness] = clampf(B2_ROUGHNESS_CLAMP, 1.0f, m.f[B2MAT_sheen_roughness]);
+    clamp_rgb01(B2MAT_sheen_color_r);
+
+    m.f[B2MAT_specular_transmission] = clamp01(m.f[B2MAT_specular_transmission]);
+    m.f[B2MAT_absorption_at_distance] = maxf_ref(m.f[B2MAT_absorption_at_distance], 1.0e-4f);
+    for (int k = 0; k < 3; k++)
+        m.f[B2MAT_absorption_color_r + k] = clamp01(maxf_ref(m.f[B2MAT_absorption_color_r + k], 1.0f / 512.0f));
+
+    m.f[B2MAT_dispersion_abbe_number] = maxf_ref(1.0e-5f, m.f[B2MAT_dispersion_abbe_number]);
+    m.f[B2MAT_dispersion_scale] = clamp01(m.f[B2MAT_dispersion_scale]);
+
+    m.f[B2MAT_thin_film] = clamp01(m.f[B2MAT_thin_film]);
+    m.f[B2MAT_thin_film_hue_shift_degrees] = clampf(0.0f, 360.0f, m.f[B2MAT_thin_film_hue_shift_degrees]);
+    m.f[B2MAT_thin_film_ior] = maxf_ref(1.0005f, m.f[B2MAT_thin_film_ior]);
+
+    m.f[B2MAT_alpha_opacity] = clamp01(m.f[B2MAT_alpha_opacity]);
+
+    int priority = (int)m.f[B2MAT_dielectric_priority];
+    priority = std::min(15, std::max(0, priority));
+    for (int k = 0; k < 3; k++)
+        m.f[B2MAT_emission_r + k] = maxf_ref(0.0f, m.f[B2MAT_emission_r + k]);
+    if (m.f[B2MAT_specular_transmission] == 0.0f && m.f[B2MAT_diffuse_transmission] == 0.0f)
+        priority = (1 << 15) - 1;
+    m.dielectric_priority = priority;
+    return m;
+}
+
+inline Rgb rgb_at(const SafeMaterial& m, int i) { return rgb(m.f[i], m.f[i + 1], m.f[i + 2]); }
+
+/* CPUMaterial::pack_to_GPU, MaterialCPU.h:31-120 */
+B2PackedTexturedMaterial pack_to_gpu(const SafeMaterial& m)
+{
+    B2PackedTexturedMaterial out;
+    Mat u = mat_defaults();
+    Rgb e = rgb_at(m, B2MAT_emission_r) * m.f[B2MAT_emission_strength] * m.f[B2MAT_global_emissive_factor];
+    u.emission = e;
+    u.emissive_texture_used = false;
+    u.base_color = rgb_at(m, B2MAT_base_color_r);
+    u.roughness = m.f[B2MAT_roughness];
+    u.oren_nayar_sigma = m.f[B2MAT_oren_nayar_sigma];
+    u.metallic = m.f[B2MAT_metallic];
+    u.metallic_F90_falloff_exponent = m.f[B2MAT_metallic_F90_falloff_exponent];
+    u.metallic_F82 = rgb_at(m, B2MAT_metallic_F82_r);
+    u.metallic_F90 = rgb_at(m, B2MAT_metallic_F90_r);
+    u.anisotropy = m.f[B2MAT_anisotropy];
+    u.anisotropy_rotation = m.f[B2MAT_anisotropy_rotation];
+    u.second_roughness_weight = m.f[B2MAT_second_roughness_weight];
+    u.second_roughness = m.f[B2MAT_second_roughness];
+    u.do_metallic_energy_compensation = m.f[B2MAT_do_metallic_energy_compensation] != 0.0f;
+    u.specular = m.f[B2MAT_specular];
+    u.specular_tint = m.f[B2MAT_specular_tint];
+    u.specular_color = rgb_at(m, B2MAT_specular_color_r);
+    u.specular_darkening = m.f[B2MAT_specular_darkening];
+    u.do_specular_energy_compensation = m.f[B2MAT_do_specular_energy_compensation] != 0.0f;
+    u.coat = m.f[B2MAT_coat];
+    u.coat_medium_absorption = rgb_at(m, B2MAT_coat_medium_absorption_r);
+    u.coat_medium_thickness = m.f[B2MAT_coat_medium_thickness];
+    u.coat_roughness = m.f[B2MAT_coat_roughness];
+    u.coat_roughening = m.f[B2MAT_coat_roughening];
+    u.coat_darkening = m.f[B2MAT_coat_darkening];
+    u.coat_anisotropy = m.f[B2MAT_coat_anisotropy];
+    u.coat_anisotropy_rotation = m.f[B2MAT_coat_anisotropy_rotation];
+    u.coat_ior = m.f[B2MAT_coat_ior];
+    u.do_coat_energy_compensation = m.f[B2MAT_do_coat_energy_compensation] != 0.0f;
+    u.sheen = m.f[B2MAT_sheen];
+    u.sheen_roughness = m.f[B2MAT_sheen_roughness];
+    u.sheen_color = rgb_at(m, B2MAT_sheen_color_r);
+    u.ior = m.f[B2MAT_ior];
+    u.specular_transmission = m.f[B2MAT_specular_transmission];
+    u.diffuse_transmission = m.f[B2MAT_diffuse_transmission];
+    u.absorption_at_distance = m.f[B2MAT_absorption_at_distance];
+    u.absorption_color = rgb_at(m, B2MAT_absorption_color_r);
+    u.dispersion_scale = m.f[B2MAT_dispersion_scale];
+    u.dispersion_abbe_number = m.f[B2MAT_dispersion_abbe_number];
+    u.thin_walled = m.f[B2MAT_thin_walled] != 0.0f;
+    u.do_glass_energy_compensation = m.f[B2MAT_do_glass_energy_compensation] != 0.0f;
+    u.thin_film = m.f[B2MAT_thin_film];
+    u.thin_film_ior = m.f[B2MAT_thin_film_ior];
+    u.thin_film_thickness = m.f[B2MAT_thin_film_thickness];
+    u.thin_film_kappa_3 = m.f[B2MAT_thin_film_kappa_3];
+    u.thin_film_hue_shift_degrees = m.f[B2MAT_thin_film_hue_shift_degrees] / 360.0f;
+    u.thin_film_base_ior_override = m.f[B2MAT_thin_film_base_ior_override];
+    u.thin_film_do_ior_override = m.f[B2MAT_thin_film_do_ior_override] != 0.0f;
+    u.alpha_opacity = m.f[B2MAT_alpha_opacity];
+    /* set_dielectric_priority takes an unsigned char: 32767 becomes 255 */
+    u.dielectric_priority = (uint8_t)m.dielectric_priority;
+    /* pack_to_GPU never sets the strong-energy-conservation flag nor the sample count: packed defaults (0) */
+    u.enforce_strong_energy_conservation = false;
+    u.energy_preservation_monte_carlo_samples = 0;
+
+    PackedMat p = pack_material<0>(u);
+    for (int i = 0; i < 27; i++)
+        out.effective[i] = p.w[i];
+
+    /* texture indices: every slot NO_TEXTURE. The reference's setters for the anisotropic index write into the
+     * roughness/metallic word (MaterialPacked.h:717), which leaves the anisotropic half of word 3 at 0. */
+    const uint32_t none = 0xFFFFu;
+    out.texture_indices[0] = none | (none << 16); /* normal map | emission */
+    out.texture_indices[1] = none | (none << 16); /* base colour | roughness-metallic */
+    out.texture_indices[2] = none | (none << 16); /* roughness (then anisotropic, same slot) | metallic */
+    out.texture_indices[3] = none << 16;          /* (anisotropic: never written) | specular */
+    out.texture_indices[4] = none | (none << 16); /* coat | sheen */
+    out.texture_indices[5] = none;                /* specular transmission */
+    return out;
+}
+} // namespace
+
+bool b2_host_scene_prepare(B2HostScene& scene, std::string& error)
+{
+    const B2Scene& blob = scene.blob;
+    const size_t n_mat = blob.n_materials(), n_tri = blob.n_triangles(), n_vert = blob.n_vertices();
+    if (n_mat >= 0x03FFFFFFu)
+    {
+        error = "too many materials for the nested-dielectrics stack entries";
+        return false;
+    }
+    for (size_t t = 0; t < n_tri; t++)
+        if (blob.material_indices[t] < 0 || (size_t)blob.material_indices[t] >= n_mat)
+        {
+            error = "material index out of range";
+            return false;
+        }
+
+    std::vector<SafeMaterial> safe(n_mat);
+    scene.packed_materials.resize(n_mat);
+    scene.material_opaque.resize(n_mat);
+    for (size_t i = 0; i < n_mat; i++)
+    {
+        safe[i] = make_safe(blob.material(i));
+        if (safe[i].f[B2MAT_dispersion_scale] > 0.0f)
+        {
+            error = "dispersive media are not supported by the B200 path yet (SURVEY section 8: out of the configured scope)";
+            return false;
+        }
+        scene.packed_materials[i] = pack_to_gpu(safe[i]);
+        scene.material_opaque[i] = safe[i].f[B2MAT_alpha_opacity] == 1.0f;
+    }
+
+    /* AoS -> SoA */
+    B2MaterialSoAHost& s = scene.materials;
+    auto col = [&](std::vector<uint32_t>& dst, int word) { dst.resize(n_mat); for (size_t i = 0; i < n_mat; i++) dst[i] = scene.packed_materials[i].effective[word]; };
+    auto colf = [&](std::vector<float>& dst, int word) { dst.resize(n_mat); for (size_t i = 0; i < n_mat; i++) dst[i] = b2_uint_as_float(scene.packed_materials[i].effective[word]); };
+    auto coli = [&](std::vector<uint32_t>& dst, int word) { dst.resize(n_mat); for (size_t i = 0; i < n_mat; i++) dst[i] = scene.packed_materials[i].texture_indices[word]; };
+    s.flags.resize(n_mat);
+    s.emission.resize(3 * n_mat);
+    for (size_t i = 0; i < n_mat; i++)
+    {
+        s.flags[i] = (uint8_t)scene.packed_materials[i].effective[PM_FLAGS];
+        for (int k = 0; k < 3; k++)
+            s.emission[3 * i + k] = b2_uint_as_float(scene.packed_materials[i].effective[PM_EMISSION_R + k]);
+    }
+    col(s.base_color_roughness, PM_BASE_COLOR_ROUGHNESS);
+    colf(s.oren_nayar_sigma, PM_OREN_SIGMA);
+    col(s.metallic_F90_and_metallic, PM_METALLIC_F90_AND_METALLIC);
+    col(s.metallic_F82_packed_and_diffuse_transmission, PM_METALLIC_F82_AND_DIFFUSE_TRANSMISSION);
+    colf(s.metallic_F90_falloff_exponent, PM_METALLIC_F90_FALLOFF);
+    col(s.anisotropy_and_rotation_and_second_roughness, PM_ANISO_ROT_SECOND_ROUGHNESS);
+    col(s.specular_color_and_tint_factor, PM_SPECULAR_COLOR_TINT);
+    col(s.specular_and_darkening_and_coat_roughness, PM_SPECULAR_DARKENING_COAT_ROUGHNESS);
+    colf(s.coat_medium_thickness, PM_COAT_MEDIUM_THICKNESS);
+    col(s.coat_and_medium_absorption, PM_COAT_AND_MEDIUM_ABSORPTION);
+    col(s.coat_roughening_darkening_anisotropy_and_rotation, PM_COAT_ROUGHENING_DARKENING_ANISO);
+    colf(s.coat_ior, PM_COAT_IOR);
+    col(s.sheen_and_color, PM_SHEEN_AND_COLOR);
+    colf(s.ior, PM_IOR);
+    col(s.absorption_color_packed, PM_ABSORPTION_COLOR);
+    colf(s.absorption_at_distance, PM_ABSORPTION_DISTANCE);
+    col(s.sheen_roughness_transmission_dispersion_thin_film, PM_SHEEN_ROUGHNESS_TRANSMISSION_DISPERSION_THIN_FILM);
+    colf(s.dispersion_abbe_number, PM_DISPERSION_ABBE);
+    colf(s.thin_film_ior, PM_THIN_FILM_IOR);
+    colf(s.thin_film_thickness, PM_THIN_FILM_THICKNESS);
+    colf(s.thin_film_kappa_3, PM_THIN_FILM_KAPPA_3);
+    colf(s.thin_film_base_ior_override, PM_THIN_FILM_BASE_IOR_OVERRIDE);
+    col(s.alpha_thin_film_hue_dielectric_priority, PM_ALPHA_HUE_PRIORITY);
+    coli(s.normal_map_emission_index, 0);
+    coli(s.base_color_roughness_metallic_index, 1);
+    coli(s.roughness_and_metallic_index, 2);
+    coli(s.anisotropic_specular_index, 3);
+    coli(s.coat_sheen_index, 4);
+    coli(s.specular_transmission_index, 5);
+
+    /* triangle areas (ThreadFunctions.cpp:221-243) and the emissive list (:136-194) */
+    scene.triangle_areas.resize(n_tri);
+    scene.emissive_triangles.clear();
+    std::vector<uint8_t> mat_emissive(n_mat);
+    for (size_t i = 0; i < n_mat; i++)
+        mat_emissive[i] = !b2_is_zero(safe[i].f[B2MAT_emission_r]) || !b2_is_zero(safe[i].f[B2MAT_emission_g]) || !b2_is_zero(safe[i].f[B2MAT_emission_b]);
+    auto vertex = [&](int idx) { return v3(blob.positions[3 * (size_t)idx], blob.positions[3 * (size_t)idx + 1], blob.positions[3 * (size_t)idx + 2]); };
+    for (size_t t = 0; t < n_tri; t++)
+    {
+        V3 A = vertex(blob.indices[3 * t]), B = vertex(blob.indices[3 * t + 1]), C = vertex(blob.indices[3 * t + 2]);
+        V3 normal = cross(B - A, C - A);
+        scene.triangle_areas[t] = length(normal) * 0.5f;
+        if (mat_emissive[blob.material_indices[t]])
+            scene.emissive_triangles.push_back((int)t);
+    }
+
+    /* power-proportional alias table (CPURenderer.cpp:420-465): built for every scene, used by the POWER variants */
+    std::vector<float> power_list(scene.emissive_triangles.size());
+    float power_sum = 0.0f;
+    for (size_t i = 0; i < scene.emissive_triangles.size(); i++)
+    {
+        int t = scene.emissive_triangles[i];
+        V3 A = vertex(blob.indices[3 * (size_t)t]), B = vertex(blob.indices[3 * (size_t)t + 1]), C = vertex(blob.indices[3 * (size_t)t + 2]);
+        V3 normal = cross(B - A, C - A);
+        float triangle_area = 0.5f * length(normal);
+        const SafeMaterial& m = safe[blob.material_indices[t]];
+        float emission_luminance = luminance(rgb_at(m, B2MAT_emission_r)) * m.f[B2MAT_emission_strength] * m.f[B2MAT_global_emissive_factor];
+        float area_power = emission_luminance * triangle_area;
+        power_list[i] = area_power;
+        power_sum += area_power;
+    }
+    scene.power_alias_probas.clear();
+    scene.power_alias_alias.clear();
+    b2pt_build_alias_table(power_list, power_sum, scene.power_alias_probas, scene.power_alias_alias);
+    scene.power_sum = power_sum;
+
+    auto t0 = std::chrono::high_resolution_clock::now();
+    if (!b2_build_cw8(blob.indices.data(), n_tri, blob.positions.data(), n_vert, scene.bvh, error))
+        return false;
+    scene.bvh_build_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    return true;
+}

@@ -1,0 +1,566 @@
+/*
+ * b2_pathtrace.h -- the two per-pixel passes every configuration runs: G-buffer fill ("CameraRays") and the
+ * bounce loop ("MegaKernel"), written as per-pixel functions so the CUDA kernels (b2_kernels.cu) decide the
+ * thread <-> pixel mapping (persistent blocks, tile order) independently of the math.
+ *
+ * Restates /root/reference/src/Device/kernels/CameraRays.h:20-213, kernels/Megakernel.h:22-144,
+ * includes/PathTracing.h:18-217, RussianRoulette.h:20-55, AdaptiveSampling.h:18-102, SanityCheck.h:30-105,
+ * LightSampling/Lights.h:228-423 and HostDeviceCommon/HIPRTCamera.h:31-52.
+ */
+#ifndef B2_PATHTRACE_H
+#define B2_PATHTRACE_H
+
+#include "b2_envmap.h"
+#include "b2_principled.h"
+#include "b2_ris.h"
+#include "b2_restir_di_shading.h"
+
+#if defined(__CUDA_ARCH__)
+#define B2_ATOMIC_ADD_U32(ptr, v) atomicAdd((ptr), (v))
+#else
+#define B2_ATOMIC_ADD_U32(ptr, v) __atomic_fetch_add((ptr), (v), __ATOMIC_RELAXED)
+#endif
+
+B2_HD bool has_access_to_adaptive_sampling_buffers(const b2pt_render_settings& s)
+{
+    bool has_access = false;
+    has_access |= s.stop_pixel_noise_threshold > 0.0f;
+    has_access |= s.enable_adaptive_sampling != 0;
+    has_access &= s.accumulate != 0;
+    return has_access;
+}
+
+template <class V>
+B2_HD bool use_prev_frame_g_buffer(const b2pt_render_settings& s)
+{
+    return V::DIRECT == B2_LSS_RESTIR_DI && s.restir_di_settings.common_temporal_pass.do_temporal_reuse_pass;
+}
+
+B2_HD bool do_render_low_resolution(const b2pt_render_settings& s)
+{
+    return s.wants_render_low_resolution && s.allow_render_low_resolution && s.accumulate;
+}
+
+B2_HD void store_packed_material(void* buffer, uint32_t pixel_index, const PackedMat& p)
+{
+    uint32_t* dst = reinterpret_cast<uint32_t*>(buffer) + (size_t)pixel_index * PM_WORDS;
+#pragma unroll
+    for (int i = 0; i < PM_WORDS; i++)
+        dst[i] = p.w[i];
+}
+B2_HD PackedMat load_packed_material(const void* buffer, uint32_t pixel_index)
+{
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(buffer) + (size_t)pixel_index * PM_WORDS;
+    PackedMat p;
+#pragma unroll
+    for (int i = 0; i < PM_WORDS; i++)
+        p.w[i] = src[i];
+    return p;
+}
+
+/* CameraRays.h:20-59 */
+template <class V>
+B2_HD void reset_render(const b2pt_render_data& rd, uint32_t pixel_index)
+{
+    if (has_access_to_adaptive_sampling_buffers(rd.render_settings))
+    {
+        rd.aux_buffers.pixel_sample_count[pixel_index] = 0;
+        rd.aux_buffers.pixel_squared_luminance[pixel_index] = 0;
+        rd.aux_buffers.pixel_converged_sample_count[pixel_index] = -1;
+    }
+    const uint32_t zero_normal = pack_normal_oct24(v3(0.0f));
+    const PackedMat default_material = pack_material<V::BSDF_OVERRIDE>(mat_defaults());
+    rd.g_buffer.first_hit_prim_index[pixel_index] = -1;
+    rd.g_buffer.geometric_normals[pixel_index] = zero_normal;
+    rd.g_buffer.shading_normals[pixel_index] = zero_normal;
+    rd.g_buffer.primary_hit_position[pixel_index] = b2pt_float3{ 0.0f, 0.0f, 0.0f };
+    store_packed_material(rd.g_buffer.materials, pixel_index, default_material);
+    if (use_prev_frame_g_buffer<V>(rd.render_settings))
+    {
+        rd.g_buffer_prev_frame.first_hit_prim_index[pixel_index] = -1;
+        rd.g_buffer_prev_frame.geometric_normals[pixel_index] = zero_normal;
+        rd.g_buffer_prev_frame.shading_normals[pixel_index] = zero_normal;
+        rd.g_buffer_prev_frame.primary_hit_position[pixel_index] = b2pt_float3{ 0.0f, 0.0f, 0.0f };
+        store_packed_material(rd.g_buffer_prev_frame.materials, pixel_index, default_material);
+    }
+}
+
+/* AdaptiveSampling.h:18-102 */
+B2_HD float pixel_confidence_interval(const b2pt_render_data& rd, int pixel_index, int pixel_sample_count, float& average_luminance)
+{
+    float lum = luminance(load_rgb(rd.buffers.accumulated_ray_colors, pixel_index));
+    average_luminance = lum / (pixel_sample_count + 1);
+    float squared_luminance = rd.aux_buffers.pixel_squared_luminance[pixel_index];
+    float pixel_variance = (squared_luminance - lum * average_luminance) / (pixel_sample_count + 1);
+    return 1.96f * sqrtf(pixel_variance) / sqrtf((float)(pixel_sample_count + 1));
+}
+
+B2_HD bool adaptive_sampling(const b2pt_render_data& rd, int pixel_index, bool& pixel_converged)
+{
+    const b2pt_render_settings& s = rd.render_settings;
+    const b2pt_aux_buffers& aux = rd.aux_buffers;
+    if (!has_access_to_adaptive_sampling_buffers(s))
+        return true;
+
+    if (s.enable_adaptive_sampling)
+    {
+        if (aux.pixel_converged_sample_count[pixel_index] != -1)
+            return false;
+        int pixel_sample_count = aux.pixel_sample_count[pixel_index];
+        if (pixel_sample_count > s.adaptive_sampling_min_samples)
+        {
+            float average_luminance;
+            float confidence_interval = pixel_confidence_interval(rd, pixel_index, pixel_sample_count, average_luminance);
+            bool pixel_needs_sampling = confidence_interval > s.adaptive_sampling_noise_threshold * average_luminance;
+            if (!pixel_needs_sampling)
+            {
+                if (aux.pixel_converged_sample_count[pixel_index] == -1)
+                    aux.pixel_converged_sample_count[pixel_index] = pixel_sample_count;
+                return false;
+            }
+        }
+        return true;
+    }
+    else if (s.stop_pixel_noise_threshold > 0.0f && s.use_pixel_stop_noise_threshold)
+    {
+        int pixel_sample_count = aux.pixel_sample_count[pixel_index];
+        float average_luminance;
+        float confidence_interval = pixel_confidence_interval(rd, pixel_index, pixel_sample_count, average_luminance);
+        pixel_converged = (confidence_interval <= s.stop_pixel_noise_threshold * average_luminance) && (s.sample_number > 1);
+        int current_converged_count = aux.pixel_converged_sample_count[pixel_index];
+        if (pixel_converged && current_converged_count == -1)
+            aux.pixel_converged_sample_count[pixel_index] = pixel_sample_count;
+        else if (!pixel_converged)
+            aux.pixel_converged_sample_count[pixel_index] = -1;
+    }
+    return true;
+}
+
+/* HIPRTCamera::get_camera_ray, HIPRTCamera.h:31-52 */
+B2_HD void camera_ray(const b2pt_camera& cam, float x, float y, b2pt_int2 res, V3& origin, V3& direction)
+{
+    float x_ndc = x / res.x * 2 - 1;
+    float y_ndc = y / res.y * 2 - 1;
+    origin = mat4_mul_point(cam.inverse_view, v3(0.0f, 0.0f, 0.0f));
+    V3 point_view_space = mat4_mul_point(cam.inverse_projection, v3(x_ndc, y_ndc, -1.0f));
+    V3 point_world_space = mat4_mul_point(cam.inverse_view, point_view_space);
+    direction = normalize(point_world_space - origin);
+}
+
+B2_HD uint32_t pixel_seed(const b2pt_render_data& rd, uint32_t pixel_index)
+{
+    if (rd.render_settings.freeze_random)
+        return wang_hash(pixel_index + 1);
+    return wang_hash((pixel_index + 1) * (rd.render_settings.sample_number + 1) * rd.random_number);
+}
+
+/* rescale_samples, CameraRays.h:61-80 (GMoN part out of scope) */
+B2_HD void rescale_samples(const b2pt_render_data& rd, uint32_t pixel_index)
+{
+    float n = (float)rd.render_settings.sample_number;
+    Rgb c = load_rgb(rd.buffers.accumulated_ray_colors, pixel_index) / n * (float)(rd.render_settings.sample_number + 1);
+    rd.buffers.accumulated_ray_colors[pixel_index] = b2pt_rgb{ c.r, c.g, c.b };
+}
+
+/* The CameraRays pass for pixel (x, y): CameraRays.h:82-213 */
+template <class V>
+B2_HD void camera_rays_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    const b2pt_int2 res = rd.render_settings.render_resolution;
+    if (x >= (uint32_t)res.x || y >= (uint32_t)res.y)
+        return;
+    uint32_t pixel_index = x + y * res.x;
+
+    if (rd.render_settings.need_to_reset)
+        reset_render<V>(rd, pixel_index);
+
+    if (do_render_low_resolution(rd.render_settings))
+    {
+        int res_scaling = rd.render_settings.render_low_resolution_scaling;
+        if (x % res_scaling != 0 || y % res_scaling != 0)
+        {
+            rd.aux_buffers.pixel_active[pixel_index] = false;
+            return;
+        }
+        pixel_index /= res_scaling;
+    }
+
+    if (use_prev_frame_g_buffer<V>(rd.render_settings))
+    {
+        rd.g_buffer_prev_frame.geometric_normals[pixel_index] = rd.g_buffer.geometric_normals[pixel_index];
+        rd.g_buffer_prev_frame.shading_normals[pixel_index] = rd.g_buffer.shading_normals[pixel_index];
+        store_packed_material(rd.g_buffer_prev_frame.materials, pixel_index, load_packed_material(rd.g_buffer.materials, pixel_index));
+        rd.g_buffer_prev_frame.primary_hit_position[pixel_index] = rd.g_buffer.primary_hit_position[pixel_index];
+        rd.g_buffer_prev_frame.first_hit_prim_index[pixel_index] = rd.g_buffer.first_hit_prim_index[pixel_index];
+    }
+
+    bool pixel_converged = false;
+    bool sampling_needed = adaptive_sampling(rd, pixel_index, pixel_converged);
+    if (pixel_converged || !sampling_needed)
+    {
+        if (rd.render_settings.do_update_status_buffers)
+            B2_ATOMIC_ADD_U32(rd.aux_buffers.pixel_count_converged_so_far, 1u);
+    }
+
+    if (has_access_to_adaptive_sampling_buffers(rd.render_settings))
+    {
+        if (!sampling_needed)
+        {
+            rescale_samples(rd, pixel_index);
+            rd.aux_buffers.pixel_active[pixel_index] = false;
+            return;
+        }
+        else
+            rd.aux_buffers.pixel_sample_count[pixel_index]++;
+    }
+
+    Rng rng = make_rng(pixel_seed(rd, pixel_index));
+
+    float x_ray_point = (x + 0.5f);
+    float y_ray_point = (y + 0.5f);
+    if (rd.current_camera.do_jittering)
+    {
+        x_ray_point += rng.next_float() - 0.5f;
+        y_ray_point += rng.next_float() - 0.5f;
+    }
+
+    V3 origin, direction;
+    camera_ray(rd.current_camera, x_ray_point, y_ray_point, res, origin, direction);
+
+    Payload payload;
+    payload.init();
+    HitInfo hit = hit_info_defaults();
+    bool intersection_found = trace_main_path_ray<V>(ctx, origin, direction, payload, hit, -1, rng);
+
+    if (intersection_found)
+    {
+        rd.g_buffer.geometric_normals[pixel_index] = pack_normal_oct24(hit.geometric_normal);
+        rd.g_buffer.shading_normals[pixel_index] = pack_normal_oct24(hit.shading_normal);
+        store_packed_material(rd.g_buffer.materials, pixel_index, pack_material<V::BSDF_OVERRIDE>(payload.material));
+        rd.g_buffer.primary_hit_position[pixel_index] = b2pt_float3{ hit.inter_point.x, hit.inter_point.y, hit.inter_point.z };
+    }
+    else
+    {
+        V3 p = origin + direction;
+        rd.g_buffer.primary_hit_position[pixel_index] = b2pt_float3{ p.x, p.y, p.z };
+    }
+    rd.g_buffer.first_hit_prim_index[pixel_index] = intersection_found ? hit.primitive_index : -1;
+    rd.aux_buffers.pixel_active[pixel_index] = true;
+
+    if (rd.render_settings.do_update_status_buffers)
+        rd.aux_buffers.still_one_ray_active[0] = 1;
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+
+/* RussianRoulette.h:20-47 */
+B2_HD bool do_russian_roulette(const b2pt_render_settings& s, int bounce, Rgb& ray_throughput, Rgb current_weight, Rng& rng)
+{
+    if (bounce >= s.russian_roulette_min_depth && s.do_russian_roulette)
+    {
+        float survive_probability = 0.0f;
+        if (s.path_russian_roulette_method == 0)
+            survive_probability = max_component(ray_throughput);
+        else if (s.path_russian_roulette_method == 1)
+        {
+            survive_probability = max_component(ray_throughput * current_weight) / max_component(ray_throughput);
+            survive_probability = sqrtf(survive_probability);
+        }
+        survive_probability = b2_min(survive_probability, 1.0f);
+        if (rng.next_float() > survive_probability)
+            return false;
+        float throughput_scaling = 1.0f / survive_probability;
+        if (s.russian_roulette_throughput_clamp > 0.0f)
+            throughput_scaling = b2_min(throughput_scaling, s.russian_roulette_throughput_clamp);
+        ray_throughput *= throughput_scaling;
+    }
+    return true;
+}
+
+/* PathTracing.h:44-62; dispersive media are refused at scene upload, so get_dispersion_ray_color() == 1 */
+B2_HD Rgb update_ray_throughput(const b2pt_render_data& rd, Payload& payload, const HitInfo& hit, Rgb current_throughput, Rgb bsdf_color, V3 bounce_direction, float bsdf_pdf_value, Rng& rng)
+{
+    Rgb throughput_attenuation = bsdf_color * fabsf(dot(bounce_direction, hit.shading_normal)) / bsdf_pdf_value;
+    if (!do_russian_roulette(rd.render_settings, payload.bounce, current_throughput, throughput_attenuation, rng))
+        return rgb(0.0f);
+    current_throughput *= rgb(1.0f);
+    current_throughput *= throughput_attenuation;
+    current_throughput = rgb_max(current_throughput, rgb(1.0e-5f, 1.0e-5f, 1.0e-5f));
+    payload.next_ray_state = B2_RAY_BOUNCE;
+    return current_throughput;
+}
+
+/* PathTracing.h:24-39,81-101 */
+template <class V>
+B2_HD bool compute_next_indirect_bounce(const Ctx& ctx, Payload& payload, HitInfo& hit, V3 view_direction, V3& out_origin, V3& out_direction, Rng& rng)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    Rgb bsdf_color;
+    V3 bounce_direction;
+    float bsdf_pdf_value;
+    int sampled_light_info = B2_LOBE_NO_INFO;
+    BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, v3(0.0f), &sampled_light_info, &payload.volume_state, true,
+                                 &payload.material, payload.bounce, payload.accumulated_roughness);
+    bsdf_color = bsdf_sample<V>(rd, bctx, bounce_direction, bsdf_pdf_value, rng);
+    payload.accumulate_roughness(sampled_light_info);
+
+    if (bsdf_pdf_value <= 0.0f)
+        return false;
+
+    payload.throughput = update_ray_throughput(rd, payload, hit, payload.throughput, bsdf_color, bounce_direction, bsdf_pdf_value, rng);
+    if (is_black(payload.throughput))
+        return false;
+
+    out_origin = hit.inter_point;
+    out_direction = bounce_direction;
+    return true;
+}
+
+/* Lights.h:228-352: strategy dispatch for emissive geometry */
+template <class V>
+B2_HD Rgb sample_emissive_geometry(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, int x, int y)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    if (rd.buffers.emissive_triangles_count == 0 && !(rd.world_settings.ambient_light_type == 2 && V::DIRECT == B2_LSS_RESTIR_DI))
+        return rgb(0.0f);
+    if (rd.bsdfs_data.white_furnace_mode && rd.bsdfs_data.white_furnace_mode_turn_off_emissives)
+        return rgb(0.0f);
+
+    Rgb material_self_textured_emission = rgb(0.0f);
+    if (payload.material.emissive_texture_used)
+        material_self_textured_emission = payload.material.emission;
+
+    Rgb direct = rgb(0.0f);
+    /* DirectLightSamplingNEESampleCount = 1: "sum of one / 1" keeps the value bit-identical */
+    if constexpr (V::DIRECT == B2_LSS_ONE_LIGHT)
+        direct = sample_one_light_no_MIS<V>(ctx, payload, hit, view_direction, rng) / 1.0f;
+    else if constexpr (V::DIRECT == B2_LSS_BSDF)
+        direct = sample_one_light_bsdf<V>(ctx, payload, hit, view_direction, rng) / 1.0f;
+    else if constexpr (V::DIRECT == B2_LSS_MIS)
+        direct = sample_one_light_MIS<V>(ctx, payload, hit, view_direction, rng) / 1.0f;
+    else if constexpr (V::DIRECT == B2_LSS_RIS)
+        direct = sample_lights_RIS<V>(ctx, payload, hit, view_direction, rng) / 1.0f;
+    else if constexpr (V::DIRECT == B2_LSS_RESTIR_DI)
+    {
+        if (payload.bounce == 0)
+            direct = sample_light_ReSTIR_DI<V>(ctx, payload, hit, view_direction, rng, x, y);
+        else
+        {
+            if constexpr (V::LATER == B2_LATER_ONE_LIGHT)
+                direct = sample_one_light_no_MIS<V>(ctx, payload, hit, view_direction, rng);
+            else if constexpr (V::LATER == B2_LATER_BSDF)
+                direct = sample_one_light_bsdf<V>(ctx, payload, hit, view_direction, rng);
+            else if constexpr (V::LATER == B2_LATER_MIS)
+                direct = sample_one_light_MIS<V>(ctx, payload, hit, view_direction, rng);
+            else
+                direct = sample_lights_RIS<V>(ctx, payload, hit, view_direction, rng);
+            direct /= 1.0f;
+        }
+    }
+    return direct + material_self_textured_emission;
+}
+
+/* Lights.h:364-423 */
+template <class V>
+B2_HD Rgb estimate_direct_lighting(const Ctx& ctx, Payload& payload, HitInfo& hit, V3 view_direction, int x, int y, Rng& rng)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    Rgb total = rgb(0.0f);
+    Rgb emissive_contribution = sample_emissive_geometry<V>(ctx, payload, hit, view_direction, rng, x, y);
+    Rgb envmap_contribution = sample_environment_map<V>(ctx, payload, hit, view_direction, rng);
+
+    emissive_contribution = clamp_light_contribution(emissive_contribution, rd.render_settings.direct_contribution_clamp, payload.bounce == 0);
+    envmap_contribution = clamp_light_contribution(envmap_contribution, rd.render_settings.envmap_contribution_clamp, payload.bounce == 0);
+
+    if constexpr (V::DIRECT == B2_LSS_NONE)
+    {
+        Rgb hit_emission = clamp_light_contribution(payload.material.emission, rd.render_settings.indirect_contribution_clamp, payload.bounce > 0);
+        total += hit_emission * payload.throughput;
+    }
+    else
+    {
+        if (payload.bounce == 0)
+            total += payload.material.emission;
+        total += (emissive_contribution + envmap_contribution) * payload.throughput;
+    }
+    return clamp_light_contribution(total, rd.render_settings.indirect_contribution_clamp, payload.bounce > 0);
+}
+
+/* PathTracing.h:122-174 (denoiser AOVs are written by store_denoiser_aovs below) */
+B2_HD void store_denoiser_aovs(const b2pt_render_data& rd, uint32_t pixel_index, V3 shading_normal, Rgb base_color)
+{
+    const int counter = rd.render_settings.denoiser_AOV_accumulation_counter;
+    if (rd.render_settings.sample_number == 0)
+        rd.aux_buffers.denoiser_albedo[pixel_index] = b2pt_rgb{ base_color.r, base_color.g, base_color.b };
+    else
+    {
+        Rgb a = (load_rgb(rd.aux_buffers.denoiser_albedo, pixel_index) * (float)counter + base_color) / (counter + 1.0f);
+        rd.aux_buffers.denoiser_albedo[pixel_index] = b2pt_rgb{ a.r, a.g, a.b };
+    }
+    if (rd.render_settings.sample_number == 0)
+        rd.aux_buffers.denoiser_normals[pixel_index] = b2pt_float3{ shading_normal.x, shading_normal.y, shading_normal.z };
+    else
+    {
+        V3 acc = (load_v3(rd.aux_buffers.denoiser_normals, pixel_index) * (float)counter + shading_normal) / (counter + 1.0f);
+        float len = length(acc);
+        if (!b2_is_zero(len))
+        {
+            acc = acc / len;
+            rd.aux_buffers.denoiser_normals[pixel_index] = b2pt_float3{ acc.x, acc.y, acc.z };
+        }
+    }
+}
+
+template <class V>
+B2_HD Rgb miss_gather_envmap(const b2pt_render_data& rd, Rgb ray_throughput, V3 ray_direction, int bounce, uint32_t pixel_index)
+{
+    const b2pt_world_settings& ws = rd.world_settings;
+    Rgb skysphere_color = rgb(0.0f);
+    if (ws.ambient_light_type == 1 || rd.bsdfs_data.white_furnace_mode)
+        skysphere_color = rgb(ws.uniform_light_color.r, ws.uniform_light_color.g, ws.uniform_light_color.b);
+    else if (ws.ambient_light_type == 2 && ws.envmap_intensity == 0.0f)
+        return rgb(0.0f);
+    else if (ws.ambient_light_type == 2)
+    {
+        if (V::ENVMAP == B2_ESS_NONE || bounce == 0)
+        {
+            skysphere_color = eval_envmap_no_pdf(ws, ray_direction);
+            bool unscale = V::ENVMAP == B2_ESS_NONE ? (!ws.envmap_scale_background_intensity && bounce == 0) : !ws.envmap_scale_background_intensity;
+            if (unscale)
+                skysphere_color /= ws.envmap_intensity;
+        }
+    }
+    skysphere_color = clamp_light_contribution(skysphere_color, rd.render_settings.envmap_contribution_clamp, true);
+    Rgb contribution = skysphere_color * ray_throughput;
+    Rgb clamped = clamp_light_contribution(contribution, rd.render_settings.indirect_contribution_clamp, bounce > 0);
+    if (bounce == 0)
+        store_denoiser_aovs(rd, pixel_index, v3(0.0f, 0.0f, 0.0f), skysphere_color);
+    return clamped;
+}
+
+/* SanityCheck.h:78-105: returns false for NaN / Inf / negative samples. The reference's host build also runs this
+ * check after every direct-lighting estimate (sanity_check<true>), which is what the parity target does. */
+B2_HD bool sanity_check(const b2pt_render_data& rd, Rgb& color, int x, int y)
+{
+    bool invalid = (color.r < 0 || color.g < 0 || color.b < 0) || isnan(color.r) || isnan(color.g) || isnan(color.b) || isinf(color.r) || isinf(color.g) || isinf(color.b);
+    if (invalid)
+    {
+        if (rd.render_settings.display_NaNs)
+        {
+            Rgb pink = rgb(1.0e30f, 0.0f, 1.0e30f);
+            if (rd.render_settings.sample_number != 0)
+                pink = pink * (float)rd.render_settings.sample_number;
+            rd.buffers.accumulated_ray_colors[y * rd.render_settings.render_resolution.x + x] = b2pt_rgb{ pink.r, pink.g, pink.b };
+        }
+        else
+            color = rgb(0.0f);
+    }
+    return !invalid;
+}
+
+/* PathTracing.h:176-217 (GMoN sets out of scope) */
+B2_HD void accumulate_color(const b2pt_render_data& rd, Rgb ray_color, uint32_t pixel_index)
+{
+    if (has_access_to_adaptive_sampling_buffers(rd.render_settings))
+    {
+        float squared_luminance_of_samples = luminance(ray_color) * luminance(ray_color);
+        rd.aux_buffers.pixel_squared_luminance[pixel_index] += squared_luminance_of_samples;
+    }
+    if (rd.render_settings.sample_number == 0)
+        rd.buffers.accumulated_ray_colors[pixel_index] = b2pt_rgb{ ray_color.r, ray_color.g, ray_color.b };
+    else
+    {
+        Rgb c = load_rgb(rd.buffers.accumulated_ray_colors, pixel_index) + ray_color;
+        rd.buffers.accumulated_ray_colors[pixel_index] = b2pt_rgb{ c.r, c.g, c.b };
+    }
+}
+
+/* RayVolumeState::reconstruct_first_hit, RayVolumeState.h:29-58 */
+template <class V>
+B2_HD void reconstruct_first_hit(VolumeState& vs, const Mat& material, const int* material_indices, int primitive_index, Rng& rng)
+{
+    if (primitive_index == -1)
+        return;
+    int mat_index = material_indices[primitive_index];
+    vs.interior_stack.push(vs.incident_mat_index, vs.outgoing_mat_index, vs.inside_material, mat_index, effective_dielectric_priority<V>(material));
+    if (material.dispersion_scale > 0.0f && material.specular_transmission > 0.0f && vs.sampled_wavelength == 0.0f)
+        vs.sampled_wavelength = -sample_wavelength_uniformly(rng);
+}
+
+/* The MegaKernel pass for pixel (x, y): Megakernel.h:22-144 */
+template <class V>
+B2_HD void megakernel_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    const b2pt_int2 res = rd.render_settings.render_resolution;
+    if (x >= (uint32_t)res.x || y >= (uint32_t)res.y)
+        return;
+    uint32_t pixel_index = x + y * res.x;
+    if (!rd.aux_buffers.pixel_active[pixel_index])
+        return;
+
+    int nb_bounces = rd.render_settings.nb_bounces;
+    if (do_render_low_resolution(rd.render_settings))
+        nb_bounces = b2_min(3, nb_bounces);
+
+    Rng rng = make_rng(pixel_seed(rd, pixel_index));
+
+    HitInfo hit = hit_info_defaults();
+    hit.inter_point = load_v3(rd.g_buffer.primary_hit_position, pixel_index);
+    hit.geometric_normal = normalize(unpack_normal_oct24(rd.g_buffer.geometric_normals[pixel_index]));
+    hit.shading_normal = normalize(unpack_normal_oct24(rd.g_buffer.shading_normals[pixel_index]));
+    hit.primitive_index = rd.g_buffer.first_hit_prim_index[pixel_index];
+
+    V3 cam_pos = v3(rd.current_camera.position.x, rd.current_camera.position.y, rd.current_camera.position.z);
+    V3 ray_origin = v3(0.0f);
+    V3 ray_direction = normalize(-normalize(cam_pos - hit.inter_point));
+
+    Payload payload;
+    payload.init();
+    payload.material = unpack_material(load_packed_material(rd.g_buffer.materials, pixel_index));
+    reconstruct_first_hit<V>(payload.volume_state, payload.material, rd.buffers.material_indices, hit.primitive_index, rng);
+
+    bool intersection_found = hit.primitive_index != -1;
+
+    for (int& bounce = payload.bounce; bounce < nb_bounces + 1; bounce++)
+    {
+        if (payload.next_ray_state != B2_RAY_MISSED)
+        {
+            if (bounce > 0)
+                intersection_found = trace_main_path_ray<V>(ctx, ray_origin, ray_direction, payload, hit, hit.primitive_index, rng);
+
+            if (intersection_found)
+            {
+                if (bounce == 0)
+                    store_denoiser_aovs(rd, pixel_index, hit.shading_normal, payload.material.base_color);
+
+                if (bounce > 0 || rd.render_settings.enable_direct)
+                {
+                    payload.ray_color += estimate_direct_lighting<V>(ctx, payload, hit, -ray_direction, (int)x, (int)y, rng);
+                    sanity_check(rd, payload.ray_color, (int)x, (int)y);
+                }
+
+                bool valid_indirect_bounce = compute_next_indirect_bounce<V>(ctx, payload, hit, -ray_direction, ray_origin, ray_direction, rng);
+                if (!valid_indirect_bounce)
+                    break;
+            }
+            else
+            {
+                payload.ray_color += miss_gather_envmap<V>(rd, payload.throughput, ray_direction, payload.bounce, pixel_index);
+                payload.next_ray_state = B2_RAY_MISSED;
+                sanity_check(rd, payload.ray_color, (int)x, (int)y);
+            }
+        }
+        else
+            break;
+    }
+
+    if (!sanity_check(rd, payload.ray_color, (int)x, (int)y))
+        return;
+
+    rd.aux_buffers.still_one_ray_active[0] = 1;
+    accumulate_color(rd, payload.ray_color, pixel_index);
+}
+
+#endif

@@ -1,0 +1,325 @@
+/*
+ * oracle/port_harness.cpp -- TEST / DEBUG INFRASTRUCTURE ONLY ("port" oracle). Never part of the product path.
+ *
+ * Compiles the product's OWN per-pixel headers (hiprt-path-tracer_b200/csrc/b2_*.h -- the code the CUDA kernels
+ * instantiate) for the host and runs them pixel by pixel under OpenMP, with the same command line and the same
+ * dump files as oracle/ref_harness.cpp (the real reference). Purpose: (1) in a container without a GPU, diff the
+ * B200 shading / traversal code against the reference per pixel and per pass; (2) on the GPU box, tell apart
+ * "CUDA codegen / libdevice rounding" differences from logic differences (port vs CUDA must agree to the last
+ * transcendental ulp, port vs reference must agree within the parity tolerances).
+ * The authoritative oracle is oracle/_ref (reference sources); this one is only as good as its agreement with it,
+ * which tests/test_oracle_port.py checks.
+ */
+#include "b2_frame_loop.h"
+#include "b2_host_scene.h"
+#include "b2_kernels_body.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <omp.h>
+#include <string>
+
+struct Args
+{
+    std::string scene, luts, envmap, dump, variant = "c1";
+    int width = 512, height = 512, spp = 1, bounces = 3;
+    int win_x0 = 0, win_y0 = 0, win_x1 = -1, win_y1 = -1;
+    int threads = 0;
+    bool fused = true, dump_per_sample = false, no_jitter = false;
+    int spatial_passes = 1;
+    unsigned int seed = 42;
+};
+
+static Args parse_args(int argc, char** argv)
+{
+    Args a;
+    for (int i = 1; i < argc; i++)
+    {
+        std::string k = argv[i];
+        auto next = [&]() -> const char* { if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", k.c_str()); std::exit(2); } return argv[++i]; };
+        if (k == "--scene") a.scene = next();
+        else if (k == "--luts") a.luts = next();
+        else if (k == "--envmap") a.envmap = next();
+        else if (k == "--dump") a.dump = next();
+        else if (k == "--variant") a.variant = next();
+        else if (k == "--width") a.width = std::atoi(next());
+        else if (k == "--height") a.height = std::atoi(next());
+        else if (k == "--spp") a.spp = std::atoi(next());
+        else if (k == "--bounces") a.bounces = std::atoi(next());
+        else if (k == "--threads") a.threads = std::atoi(next());
+        else if (k == "--seed") a.seed = (unsigned)std::strtoul(next(), nullptr, 10);
+        else if (k == "--window") { a.win_x0 = std::atoi(next()); a.win_y0 = std::atoi(next()); a.win_x1 = std::atoi(next()); a.win_y1 = std::atoi(next()); }
+        else if (k == "--no-fused") a.fused = false;
+        else if (k == "--spatial-passes") a.spatial_passes = std::atoi(next());
+        else if (k == "--dump-per-sample") a.dump_per_sample = true;
+        else if (k == "--no-jitter") a.no_jitter = true;
+        else { std::fprintf(stderr, "unknown argument %s\n", k.c_str()); std::exit(2); }
+    }
+    if (a.win_x1 < 0) { a.win_x1 = a.width; a.win_y1 = a.height; }
+    return a;
+}
+
+template <typename T>
+static void dump_array(const std::string& prefix, const char* name, const T* data, size_t count)
+{
+    if (prefix.empty()) return;
+    std::string path = prefix + name + ".bin";
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) { std::fprintf(stderr, "cannot write %s\n", path.c_str()); std::exit(1); }
+    std::fwrite(data, sizeof(T), count, f);
+    std::fclose(f);
+}
+
+struct LutStore
+{
+    std::map<std::string, std::vector<float>> data;
+    std::map<std::string, b2pt_lut> luts;
+    bool load(const char* path)
+    {
+        FILE* f = std::fopen(path, "rb");
+        if (!f) return false;
+        char magic[8];
+        uint32_t count = 0;
+        if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "B2LUTS01", 8) != 0 || std::fread(&count, 4, 1, f) != 1) { std::fclose(f); return false; }
+        for (uint32_t i = 0; i < count; i++)
+        {
+            char name[32];
+            int32_t dims[3];
+            if (std::fread(name, 1, 32, f) != 32 || std::fread(dims, 4, 3, f) != 3) { std::fclose(f); return false; }
+            std::vector<float>& v = data[name];
+            v.resize((size_t)dims[0] * dims[1] * dims[2]);
+            if (std::fread(v.data(), 4, v.size(), f) != v.size()) { std::fclose(f); return false; }
+            luts[name] = b2pt_lut{ v.data(), dims[0], dims[1], dims[2], 1 };
+        }
+        std::fclose(f);
+        return true;
+    }
+};
+
+template <class V>
+static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice& bvh, const Args& a)
+{
+#pragma omp parallel
+    {
+        uint64_t stack[B2_STACK_ENTRIES];
+        Ctx ctx;
+        ctx.rd = &rd;
+        ctx.bvh = bvh;
+        ctx.stack = stack;
+        ctx.counters = nullptr;
+#pragma omp for schedule(dynamic)
+        for (int y = a.win_y0; y < a.win_y1; y++)
+            for (int x = a.win_x0; x < a.win_x1; x++)
+                b2_run_pass_pixel<V>(pass, ctx, (uint32_t)x, (uint32_t)y);
+    }
+}
+
+int main(int argc, char** argv)
+{
+    Args a = parse_args(argc, argv);
+    if (a.threads > 0)
+        omp_set_num_threads(a.threads);
+    if (a.scene.empty() || a.luts.empty())
+    {
+        std::fprintf(stderr, "usage: %s --variant c1|c2|c3|c4 --scene X.b2scene --luts L.b2luts --width W --height H --spp N --bounces B [--dump prefix]\n", argv[0]);
+        return 2;
+    }
+
+    B2HostScene scene;
+    std::string err = b2scene_read(a.scene.c_str(), scene.blob);
+    if (err.empty() && !b2_host_scene_prepare(scene, err) && err.empty())
+        err = "scene preparation failed";
+    if (!err.empty()) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
+
+    LutStore luts;
+    if (!luts.load(a.luts.c_str())) { std::fprintf(stderr, "cannot read LUT blob %s\n", a.luts.c_str()); return 1; }
+
+    const size_t n = (size_t)a.width * a.height;
+    B2FrameLoop loop;
+    b2pt_render_data& rd = loop.rd;
+    loop.host_rng = make_rng(a.seed);
+    rd.render_settings.render_resolution = b2pt_int2{ a.width, a.height };
+    rd.render_settings.nb_bounces = a.bounces;
+    rd.render_settings.samples_per_frame = a.spp;
+    rd.render_settings.output_debug_sample_N = a.spp - 1;
+    rd.render_settings.restir_di_settings.do_fused_spatiotemporal = a.fused;
+    rd.render_settings.restir_di_settings.common_spatial_pass.number_of_passes = a.spatial_passes;
+
+    /* camera */
+    std::memcpy(loop.camera.inverse_view, scene.blob.camera.inverse_view, 64);
+    std::memcpy(loop.camera.inverse_projection, scene.blob.camera.inverse_projection, 64);
+    std::memcpy(loop.camera.view_projection, scene.blob.camera.view_projection, 64);
+    loop.camera.position = b2pt_float3{ scene.blob.camera.position[0], scene.blob.camera.position[1], scene.blob.camera.position[2] };
+    loop.camera.vertical_fov = scene.blob.camera.vertical_fov;
+    loop.camera.sensor_width = a.width;
+    loop.camera.sensor_height = a.height;
+    loop.camera.do_jittering = !a.no_jitter;
+    rd.current_camera = loop.camera;
+
+    /* scene buffers */
+    std::vector<b2pt_rgb> framebuffer(n, b2pt_rgb{ 0, 0, 0 });
+    rd.buffers.accumulated_ray_colors = framebuffer.data();
+    rd.buffers.triangles_indices = scene.blob.indices.data();
+    rd.buffers.vertices_positions = reinterpret_cast<b2pt_float3*>(scene.blob.positions.data());
+    rd.buffers.has_vertex_normals = scene.blob.has_normals.data();
+    rd.buffers.vertex_normals = reinterpret_cast<b2pt_float3*>(scene.blob.normals.data());
+    rd.buffers.texcoords = reinterpret_cast<b2pt_float2*>(scene.blob.texcoords.data());
+    rd.buffers.triangles_areas = scene.triangle_areas.data();
+    rd.buffers.material_indices = scene.blob.material_indices.data();
+    rd.buffers.material_opaque = scene.material_opaque.data();
+    rd.buffers.emissive_triangles_count = (int)scene.emissive_triangles.size();
+    rd.buffers.emissive_triangles_primitive_indices = scene.emissive_triangles.data();
+    rd.buffers.emissive_triangles_primitive_indices_and_emissive_textures = scene.emissive_triangles.data();
+    rd.buffers.emissives_power_alias_table.alias_table_alias = scene.power_alias_alias.data();
+    rd.buffers.emissives_power_alias_table.alias_table_probas = scene.power_alias_probas.data();
+    rd.buffers.emissives_power_alias_table.sum_elements = scene.power_sum;
+    rd.buffers.emissives_power_alias_table.size = (unsigned)scene.emissive_triangles.size();
+    {
+        B2MaterialSoAHost& m = scene.materials;
+        b2pt_materials_soa& d = rd.buffers.materials_buffer;
+        d.flags = m.flags.data();
+        d.emission = reinterpret_cast<b2pt_rgb*>(m.emission.data());
+        d.base_color_roughness = m.base_color_roughness.data();
+        d.oren_nayar_sigma = m.oren_nayar_sigma.data();
+        d.metallic_F90_and_metallic = m.metallic_F90_and_metallic.data();
+        d.metallic_F82_packed_and_diffuse_transmission = m.metallic_F82_packed_and_diffuse_transmission.data();
+        d.metallic_F90_falloff_exponent = m.metallic_F90_falloff_exponent.data();
+        d.anisotropy_and_rotation_and_second_roughness = m.anisotropy_and_rotation_and_second_roughness.data();
+        d.specular_color_and_tint_factor = m.specular_color_and_tint_factor.data();
+        d.specular_and_darkening_and_coat_roughness = m.specular_and_darkening_and_coat_roughness.data();
+        d.coat_medium_thickness = m.coat_medium_thickness.data();
+        d.coat_and_medium_absorption = m.coat_and_medium_absorption.data();
+        d.coat_roughening_darkening_anisotropy_and_rotation = m.coat_roughening_darkening_anisotropy_and_rotation.data();
+        d.coat_ior = m.coat_ior.data();
+        d.sheen_and_color = m.sheen_and_color.data();
+        d.ior = m.ior.data();
+        d.absorption_color_packed = m.absorption_color_packed.data();
+        d.absorption_at_distance = m.absorption_at_distance.data();
+        d.sheen_roughness_transmission_dispersion_thin_film = m.sheen_roughness_transmission_dispersion_thin_film.data();
+        d.dispersion_abbe_number = m.dispersion_abbe_number.data();
+        d.thin_film_ior = m.thin_film_ior.data();
+        d.thin_film_thickness = m.thin_film_thickness.data();
+        d.thin_film_kappa_3 = m.thin_film_kappa_3.data();
+        d.thin_film_base_ior_override = m.thin_film_base_ior_override.data();
+        d.alpha_thin_film_hue_dielectric_priority = m.alpha_thin_film_hue_dielectric_priority.data();
+        d.normal_map_emission_index = m.normal_map_emission_index.data();
+        d.base_color_roughness_metallic_index = m.base_color_roughness_metallic_index.data();
+        d.roughness_and_metallic_index = m.roughness_and_metallic_index.data();
+        d.anisotropic_specular_index = m.anisotropic_specular_index.data();
+        d.coat_sheen_index = m.coat_sheen_index.data();
+        d.specular_transmission_index = m.specular_transmission_index.data();
+    }
+
+    rd.bsdfs_data.GGX_conductor_directional_albedo = &luts.luts["ggx_conductor"];
+    rd.bsdfs_data.glossy_dielectric_directional_albedo = &luts.luts["glossy_dielectric"];
+    rd.bsdfs_data.GGX_glass_directional_albedo = &luts.luts["ggx_glass"];
+    rd.bsdfs_data.GGX_glass_directional_albedo_inverse = &luts.luts["ggx_glass_inv"];
+    rd.bsdfs_data.GGX_thin_glass_directional_albedo = &luts.luts["ggx_thin_glass"];
+
+    /* aux + G-buffers */
+    std::vector<uint8_t> pixel_active(n, 0);
+    std::vector<b2pt_rgb> denoiser_albedo(n, b2pt_rgb{ 0, 0, 0 });
+    std::vector<b2pt_float3> denoiser_normals(n, b2pt_float3{ 0, 0, 0 });
+    std::vector<int> pixel_sample_count(n, 0), pixel_converged(n, 0);
+    std::vector<float> pixel_sq_lum(n, 0.0f);
+    uint8_t still_one_ray_active = 1;
+    unsigned int converged_count = 0;
+    rd.aux_buffers.pixel_active = pixel_active.data();
+    rd.aux_buffers.denoiser_albedo = denoiser_albedo.data();
+    rd.aux_buffers.denoiser_normals = denoiser_normals.data();
+    rd.aux_buffers.pixel_sample_count = pixel_sample_count.data();
+    rd.aux_buffers.pixel_converged_sample_count = pixel_converged.data();
+    rd.aux_buffers.pixel_squared_luminance = pixel_sq_lum.data();
+    rd.aux_buffers.still_one_ray_active = &still_one_ray_active;
+    rd.aux_buffers.pixel_count_converged_so_far = &converged_count;
+
+    struct GBufferHost { std::vector<uint32_t> materials, geo, shade; std::vector<b2pt_float3> pos; std::vector<int> prim; } g[2];
+    b2pt_gbuffer* gb[2] = { &rd.g_buffer, &rd.g_buffer_prev_frame };
+    for (int i = 0; i < 2; i++)
+    {
+        g[i].materials.assign(n * PM_WORDS, 0);
+        g[i].geo.assign(n, 0);
+        g[i].shade.assign(n, 0);
+        g[i].pos.assign(n, b2pt_float3{ 0, 0, 0 });
+        g[i].prim.assign(n, 0);
+        gb[i]->materials = g[i].materials.data();
+        gb[i]->geometric_normals = g[i].geo.data();
+        gb[i]->shading_normals = g[i].shade.data();
+        gb[i]->primary_hit_position = g[i].pos.data();
+        gb[i]->first_hit_prim_index = g[i].prim.data();
+    }
+
+    std::vector<uint32_t> reservoirs[3];
+    for (auto& r : reservoirs)
+        r.assign(n * 9, 0);
+    loop.initial_reservoirs = reservoirs[0].data();
+    loop.spatial_reservoirs_1 = reservoirs[1].data();
+    loop.spatial_reservoirs_2 = reservoirs[2].data();
+    rd.render_settings.restir_di_settings.restir_output_reservoirs = loop.spatial_reservoirs_1;
+
+    B2BvhDevice bvh;
+    bvh.nodes = scene.bvh.nodes.data();
+    bvh.tris = scene.bvh.tris.data();
+    bvh.node_count = (uint32_t)scene.bvh.nodes.size();
+    bvh.tri_count = (uint32_t)scene.bvh.tris.size();
+    rd.GPU_BVH = &bvh;
+
+    loop.restir_di = a.variant == "c4";
+
+    int frame = 0;
+    auto launch = [&](B2Pass pass) {
+        if (pass == B2_PASS_CAMERA_RAYS)
+        {
+            still_one_ray_active = 0;
+            converged_count = 0;
+        }
+        if (a.variant == "c1") run_pass<B2VariantC1>(pass, rd, bvh, a);
+#ifdef B2_PORT_HAVE_C2
+        else if (a.variant == "c2") run_pass<B2VariantC2>(pass, rd, bvh, a);
+#endif
+#ifdef B2_PORT_HAVE_C3
+        else if (a.variant == "c3") run_pass<B2VariantC3>(pass, rd, bvh, a);
+#endif
+#ifdef B2_PORT_HAVE_C4
+        else if (a.variant == "c4") run_pass<B2VariantC4>(pass, rd, bvh, a);
+#endif
+        else { std::fprintf(stderr, "unknown variant %s\n", a.variant.c_str()); std::exit(2); }
+        if (pass == B2_PASS_CAMERA_RAYS && frame == 1)
+        {
+            dump_array(a.dump, "gbuffer_prim", g[0].prim.data(), n);
+            dump_array(a.dump, "gbuffer_position", g[0].pos.data(), n);
+            dump_array(a.dump, "gbuffer_geometric_normal", g[0].geo.data(), n);
+            dump_array(a.dump, "gbuffer_shading_normal", g[0].shade.data(), n);
+            dump_array(a.dump, "gbuffer_material", g[0].materials.data(), n * PM_WORDS);
+        }
+    };
+
+    auto start = std::chrono::high_resolution_clock::now();
+    for (frame = 1; frame <= a.spp; frame++)
+    {
+        loop.render_one_sample(launch);
+        if (a.dump_per_sample)
+        {
+            std::string name = "framebuffer_s" + std::to_string(frame);
+            dump_array(a.dump, name.c_str(), framebuffer.data(), n);
+        }
+    }
+    double seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - start).count();
+
+    dump_array(a.dump, "framebuffer", framebuffer.data(), n);
+    dump_array(a.dump, "packed_materials", scene.packed_materials.data(), scene.packed_materials.size());
+    dump_array(a.dump, "triangle_areas", scene.triangle_areas.data(), scene.triangle_areas.size());
+    dump_array(a.dump, "emissive_prims", scene.emissive_triangles.data(), scene.emissive_triangles.size());
+    dump_array(a.dump, "power_alias", scene.power_alias_alias.data(), scene.power_alias_alias.size());
+    dump_array(a.dump, "power_probas", scene.power_alias_probas.data(), scene.power_alias_probas.size());
+
+    long long window_pixels = (long long)(a.win_x1 - a.win_x0) * (a.win_y1 - a.win_y0);
+    std::printf("{\"oracle\": \"port\", \"variant\": \"%s\", \"width\": %d, \"height\": %d, \"window_pixels\": %lld, \"spp\": %d, \"bounces\": %d, \"threads\": %d, "
+                "\"render_seconds\": %.6f, \"bvh_build_seconds\": %.3f, \"mpaths_per_s\": %.6f, \"bvh_nodes\": %zu, \"bvh_depth\": %d, \"triangles\": %zu, \"emissive_triangles\": %zu}\n",
+                a.variant.c_str(), a.width, a.height, window_pixels, a.spp, a.bounces, omp_get_max_threads(), seconds, scene.bvh_build_seconds,
+                (double)window_pixels * a.spp / seconds / 1.0e6, scene.bvh.nodes.size(), scene.bvh.stats.max_depth, scene.blob.n_triangles(), scene.emissive_triangles.size());
+    return 0;
+}
