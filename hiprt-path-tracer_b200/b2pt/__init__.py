@@ -1,0 +1,262 @@
+"""ctypes binding of libb2pt.so (C ABI: include/b2pt.h) -- the host-side mirror used by tests/ and bench.py.
+
+`Renderer` mirrors the reference's renderer front end (set_scene / set_envmap / render / get_framebuffer,
+/root/reference/src/Renderer/GPURenderer.h:61-346, CPURenderer.h:33-109). There is no CPU fallback: if the CUDA library
+is missing or no device is present, construction raises.
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent.parent
+LIB_PATH = PKG_DIR / "libb2pt.so"
+REPO_ROOT = PKG_DIR.parent
+
+PASS_NAMES = ["CameraRays", "ReSTIR_DI_LightsPresampling", "ReSTIR_DI_InitialCandidates", "ReSTIR_DI_TemporalReuse",
+              "ReSTIR_DI_SpatialReuse", "ReSTIR_DI_SpatiotemporalReuse", "MegaKernel"]
+
+
+class B2ptError(RuntimeError):
+    pass
+
+
+class DeviceProps(C.Structure):
+    _fields_ = [("name", C.c_char * 256), ("sm_count", C.c_int), ("compute_major", C.c_int), ("compute_minor", C.c_int),
+                ("total_memory_bytes", C.c_size_t), ("l2_bytes", C.c_size_t), ("shared_memory_per_block_optin", C.c_size_t),
+                ("clock_khz", C.c_int)]
+
+
+class BvhStats(C.Structure):
+    _fields_ = [("node_count", C.c_uint64), ("triangle_count", C.c_uint64), ("bytes", C.c_uint64), ("max_depth", C.c_int),
+                ("sah_cost", C.c_double), ("build_seconds", C.c_double)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("nodes", C.c_uint64), ("triangles", C.c_uint64)]
+
+
+class Option(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("value", C.c_int)]
+
+
+# Byte offsets inside b2pt_render_data of the settings tests and benches edit (checked against the reference's
+# HIPRTRenderData by oracle/layout_check.cpp through include/b2pt_render_data.h; see tests/test_layout.py).
+_RS = 728
+SETTINGS_OFFSETS = {
+    "nb_bounces": (_RS + 68, "i"),
+    "samples_per_frame": (_RS + 64, "i"),
+    "sample_number": (_RS + 56, "I"),
+    "need_to_reset": (_RS + 8, "B"),
+    "do_russian_roulette": (_RS + 72, "B"),
+    "russian_roulette_min_depth": (_RS + 76, "i"),
+    "freeze_random": (_RS + 88, "i"),
+    "accumulate": (_RS + 49, "B"),
+    "enable_direct": (_RS + 28, "B"),
+    "ris_number_of_light_candidates": (_RS + 152, "i"),
+    "ris_number_of_bsdf_candidates": (_RS + 156, "i"),
+    "restir_di_do_temporal_reuse_pass": (_RS + 160 + 0, "B"),
+    "restir_di_do_spatial_reuse_pass": (_RS + 160 + 24 + 0, "B"),
+    "restir_di_number_of_passes": (_RS + 160 + 24 + 8, "i"),
+    "restir_di_reuse_radius": (_RS + 160 + 24 + 12, "i"),
+    "restir_di_reuse_neighbor_count": (_RS + 160 + 24 + 20, "i"),
+    "restir_di_m_cap": (_RS + 160 + 180, "i"),
+    "restir_di_do_fused_spatiotemporal": (_RS + 160 + 272, "B"),
+    "current_camera_do_jittering": (2328 + 216, "B"),
+    "ambient_light_type": (2088 + 0, "i"),
+    "envmap_intensity": (2088 + 24, "f"),
+    "white_furnace_mode": (464 + 0, "B"),
+}
+_CT = {"i": C.c_int, "I": C.c_uint, "B": C.c_uint8, "f": C.c_float}
+
+
+def load_library():
+    if not LIB_PATH.exists():
+        raise B2ptError(f"{LIB_PATH} is missing: build it with `python hiprt-path-tracer_b200/build.py` "
+                        "(there is no CPU fallback for the B200 path)")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.b2pt_last_error_string.restype = C.c_char_p
+    lib.b2pt_version_string.restype = C.c_char_p
+    lib.b2pt_renderer_render_data.restype = C.c_void_p
+    lib.b2pt_bvh_device_handle.restype = C.c_void_p
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = load_library()
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise B2ptError(f"b2pt error {rc}: {lib().b2pt_last_error_string().decode()}")
+
+
+def declared_symbols():
+    """Names of every function include/b2pt.h declares (used by the CPU-side ABI test)."""
+    import re
+    text = (REPO_ROOT / "include" / "b2pt.h").read_text()
+    return sorted(set(re.findall(r"\b(b2pt_[a-z0-9_]+)\s*\(", text)))
+
+
+class Context:
+    def __init__(self, device=0):
+        self.handle = C.c_void_p()
+        check(lib().b2pt_ctx_create(C.c_int(device), C.byref(self.handle)))
+
+    def props(self):
+        p = DeviceProps()
+        check(lib().b2pt_ctx_device_props(self.handle, C.byref(p)))
+        return p
+
+    def counters_reset(self):
+        check(lib().b2pt_counters_reset(self.handle))
+
+    def counters_read(self):
+        c = Counters()
+        check(lib().b2pt_counters_read(self.handle, C.byref(c)))
+        return dict(rays=c.rays, nodes=c.nodes, triangles=c.triangles)
+
+    def close(self):
+        if self.handle:
+            lib().b2pt_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+class Renderer:
+    """Headless renderer: one instance = one (resolution, variant, flavour) on one GPU."""
+
+    def __init__(self, ctx, width, height, variant="c1", precise=True):
+        self.ctx, self.width, self.height, self.variant = ctx, width, height, variant
+        self.handle = C.c_void_p()
+        check(lib().b2pt_renderer_create(ctx.handle, width, height, variant.encode(), int(bool(precise)), C.byref(self.handle)))
+        self._rd = lib().b2pt_renderer_render_data(self.handle)
+
+    # -- scene ------------------------------------------------------------------------------------------------
+    def set_scene_file(self, path):
+        check(lib().b2pt_renderer_set_scene_file(self.handle, str(path).encode()))
+
+    def set_scene(self, scene):
+        """scene: dict as returned by tools/b2scene.read_scene (host numpy arrays)."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        pos, nrm, uv = f32(scene["positions"]), f32(scene["normals"]), f32(scene["texcoords"])
+        has = np.ascontiguousarray(scene["has_normals"], np.uint8)
+        idx = np.ascontiguousarray(scene["indices"], np.int32)
+        mid = np.ascontiguousarray(scene["material_indices"], np.int32)
+        mats = f32(scene["materials"])
+        cam = scene["camera"]
+        cam52 = np.concatenate([f32(cam["inverse_view"]).ravel(), f32(cam["inverse_projection"]).ravel(), f32(cam["view_projection"]).ravel(),
+                                f32(cam["position"]).ravel(), np.array([cam["vertical_fov"]], np.float32)])
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        check(lib().b2pt_renderer_set_scene_arrays(self.handle, p(pos, C.c_float), p(nrm, C.c_float), p(uv, C.c_float), p(has, C.c_uint8),
+                                                   len(has), p(idx, C.c_int), p(mid, C.c_int), len(mid), p(mats, C.c_float), len(mats),
+                                                   p(cam52, C.c_float)))
+
+    def set_luts_file(self, path):
+        check(lib().b2pt_renderer_set_luts_file(self.handle, str(path).encode()))
+
+    def set_envmap(self, rgba):
+        if rgba is None:
+            check(lib().b2pt_renderer_set_envmap(self.handle, None, 0, 0))
+            return
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        h, w, c = rgba.shape
+        assert c == 4
+        check(lib().b2pt_renderer_set_envmap(self.handle, rgba.ctypes.data_as(C.POINTER(C.c_float)), w, h))
+
+    # -- settings ---------------------------------------------------------------------------------------------
+    def set(self, **kw):
+        for k, v in kw.items():
+            off, t = SETTINGS_OFFSETS[k]
+            _CT[t].from_address(self._rd + off).value = v
+
+    def get(self, name):
+        off, t = SETTINGS_OFFSETS[name]
+        return _CT[t].from_address(self._rd + off).value
+
+    def set_host_seed(self, seed):
+        check(lib().b2pt_renderer_set_host_seed(self.handle, C.c_uint(seed)))
+
+    def set_counters(self, enabled):
+        check(lib().b2pt_renderer_set_counters(self.handle, int(enabled)))
+
+    def set_profile_passes(self, enabled):
+        check(lib().b2pt_renderer_set_profile_passes(self.handle, int(enabled)))
+
+    def reset(self):
+        check(lib().b2pt_renderer_reset(self.handle))
+
+    # -- rendering --------------------------------------------------------------------------------------------
+    def render(self, samples=1, sync=True):
+        check(lib().b2pt_renderer_render(self.handle, int(samples)))
+        if sync:
+            self.synchronize()
+
+    def synchronize(self):
+        check(lib().b2pt_renderer_synchronize(self.handle))
+
+    def last_render_ms(self):
+        ms = C.c_float()
+        check(lib().b2pt_renderer_last_render_ms(self.handle, C.byref(ms)))
+        return ms.value
+
+    def pass_times(self):
+        out = {}
+        for i, name in enumerate(PASS_NAMES):
+            ms, n = C.c_float(), C.c_uint64()
+            check(lib().b2pt_renderer_pass_ms(self.handle, i, C.byref(ms), C.byref(n)))
+            if n.value:
+                out[name] = dict(ms=ms.value, launches=n.value)
+        return out
+
+    def framebuffer(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 3), np.float32)
+        check(lib().b2pt_renderer_download_framebuffer(self.handle, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def gbuffer(self):
+        n = self.width * self.height
+        prim = np.empty(n, np.int32)
+        pos = np.empty((n, 3), np.float32)
+        geo, shade = np.empty(n, np.uint32), np.empty(n, np.uint32)
+        mat = np.empty((n, 27), np.uint32)
+        check(lib().b2pt_renderer_download_gbuffer(self.handle, prim.ctypes.data_as(C.POINTER(C.c_int)), pos.ctypes.data_as(C.POINTER(C.c_float)),
+                                                   geo.ctypes.data_as(C.POINTER(C.c_uint32)), shade.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                   mat.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return dict(prim=prim, position=pos, geometric_normal=geo, shading_normal=shade, material=mat)
+
+    def reservoirs(self, which=3):
+        """which: 0 initial, 1 spatial_1, 2 spatial_2, 3 current ReSTIR output. Returns (9, H*W) uint32 planes."""
+        out = np.empty((9, self.width * self.height), np.uint32)
+        check(lib().b2pt_renderer_download_reservoirs(self.handle, which, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def scene_info(self):
+        st, nt, ne = BvhStats(), C.c_int(), C.c_int()
+        check(lib().b2pt_renderer_scene_info(self.handle, C.byref(st), C.byref(nt), C.byref(ne)))
+        return dict(triangles=nt.value, emissive_triangles=ne.value, bvh_nodes=st.node_count, bvh_bytes=st.bytes,
+                    bvh_depth=st.max_depth, bvh_sah=st.sah_cost, bvh_build_seconds=st.build_seconds)
+
+    def derived(self, n_materials):
+        info = self.scene_info()
+        packed = np.empty((n_materials, 33), np.uint32)
+        areas = np.empty(info["triangles"], np.float32)
+        emissive = np.empty(info["emissive_triangles"], np.int32)
+        probas = np.empty(info["emissive_triangles"], np.float32)
+        alias = np.empty(info["emissive_triangles"], np.int32)
+        check(lib().b2pt_renderer_download_derived(self.handle, packed.ctypes.data_as(C.POINTER(C.c_uint32)), areas.ctypes.data_as(C.POINTER(C.c_float)),
+                                                   emissive.ctypes.data_as(C.POINTER(C.c_int)), probas.ctypes.data_as(C.POINTER(C.c_float)),
+                                                   alias.ctypes.data_as(C.POINTER(C.c_int))))
+        return dict(packed_materials=packed, triangle_areas=areas, emissive_triangles=emissive, alias_probas=probas, alias_alias=alias)
+
+    def close(self):
+        if self.handle:
+            lib().b2pt_renderer_destroy(self.handle)
+            self.handle = C.c_void_p()

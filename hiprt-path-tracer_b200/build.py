@@ -1,0 +1,101 @@
+#!/usr/bin/env python3
+"""Builds libb2pt.so (sm_100a) in-tree with nvcc. No GPU is needed to build (nvcc cross-compiles).
+
+    python hiprt-path-tracer_b200/build.py [--force] [--jobs N]
+
+The kernels translation unit is compiled twice:
+  * precise  : -fmad=false, IEEE division / sqrt  -> the flavour parity with the reference CPU path is asserted on
+  * fast     : FMA contraction + --use_fast_math   -> the throughput flavour
+Feature macros (B2_HAVE_*) mirror which strategy headers exist, so a partially built tree still links.
+"""
+import argparse
+import concurrent.futures
+import hashlib
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+OUT = PKG / "libb2pt.so"
+OBJ = PKG / "build"
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-fno-fast-math", f"-I{ROOT / 'include'}", f"-I{CSRC}",
+          "-diag-suppress", "821", "-Xptxas", "-v"]
+FEATURES = ["-DB2_HAVE_PRINCIPLED", "-DB2_HAVE_RIS", "-DB2_HAVE_RESTIR_DI"]
+
+UNITS = [
+    # (source, object name, extra flags)
+    ("b2_kernels.cu", "b2_kernels_precise.o", ["-DB2_FLAVOUR_PRECISE", "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]),
+    ("b2_kernels.cu", "b2_kernels_fast.o", ["-DB2_FLAVOUR_FAST", "--use_fast_math"]),
+    ("b2_capi.cu", "b2_capi.o", []),
+    ("b2_renderer.cpp", "b2_renderer.o", ["-x", "cu"]),
+    ("b2_host_scene.cpp", "b2_host_scene.o", ["-x", "cu"]),
+    ("b2_bvh_build.cpp", "b2_bvh_build.o", ["-x", "cu"]),
+]
+
+
+def enabled_features():
+    feats = []
+    text = {p.name: p.read_text() for p in CSRC.glob("*.h")}
+    if "principled_bsdf_eval(const b2pt_render_data& rd, BsdfCtx& ctx, float& pdf)\n{" in text.get("b2_principled.h", ""):
+        feats.append("-DB2_HAVE_PRINCIPLED")
+    if "placeholder" not in text.get("b2_ris.h", "placeholder"):
+        feats.append("-DB2_HAVE_RIS")
+    if "placeholder" not in text.get("b2_restir_di.h", "placeholder"):
+        feats.append("-DB2_HAVE_RESTIR_DI")
+    return feats
+
+
+def source_digest():
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*")) + list((ROOT / "include").glob("*.h")) + [Path(__file__)]):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()
+
+
+def compile_unit(unit, feats, log_dir):
+    src, obj, extra = unit
+    cmd = ["nvcc", *ARCH, *COMMON, *feats, *extra, "-c", str(CSRC / src), "-o", str(OBJ / obj)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    (log_dir / (obj + ".log")).write_text(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src} ({obj}):\n{res.stdout}\n{res.stderr}")
+    return obj
+
+
+def build(force=False, jobs=None, verbose=True):
+    OBJ.mkdir(exist_ok=True)
+    digest = source_digest()
+    stamp = OBJ / "digest.txt"
+    if not force and OUT.exists() and stamp.exists() and stamp.read_text() == digest:
+        if verbose:
+            print(f"{OUT} is up to date")
+        return OUT
+    feats = enabled_features()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=jobs or min(6, os.cpu_count() or 1)) as pool:
+        list(pool.map(lambda u: compile_unit(u, feats, OBJ), UNITS))
+    link = ["nvcc", *ARCH, "-shared", "-Xcompiler", "-fopenmp", "-o", str(OUT), *[str(OBJ / u[1]) for u in UNITS], "-lgomp"]
+    res = subprocess.run(link, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    stamp.write_text(digest)
+    if verbose:
+        print(f"built {OUT} with features {feats or ['(c1 only)']}")
+    return OUT
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--jobs", type=int, default=None)
+    a = ap.parse_args()
+    try:
+        build(a.force, a.jobs)
+    except RuntimeError as e:
+        print(e, file=sys.stderr)
+        sys.exit(1)

@@ -142,10 +142,11 @@ __device__ __forceinline__ B2NodeRaw b2_load_node(const B2Node* nodes, uint32_t 
  * ANY_HIT = true: returns at the first triangle hit with t < t_max (shadow rays; for opaque scenes this is what the
  * reference's closest-hit-then-compare loop decides, Intersect.h:295-322).
  * `skip_prim` is the reference's last_hit_primitive_index self-intersection filter.
- * `stack` points to B2_STACK_ENTRIES uint2-sized slots private to the calling thread (shared memory on the GPU).
+ * `stack` points to this thread's first of B2_STACK_ENTRIES 8-byte slots, `stack_stride` slots apart (on the GPU the
+ * slots live in shared memory, entry-major, so the 32 lanes of a warp touch 32 consecutive 8-byte words).
  */
 template <bool ANY_HIT>
-B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, B2TraversalCounters* counters)
+B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int stack_stride, B2TraversalCounters* counters)
 {
     B2Hit best;
     best.t = -1.0f;
@@ -185,7 +186,7 @@ B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int
             if (group_bits > 0x00FFFFFFu)
             {
                 if (sp < B2_STACK_ENTRIES)
-                    stack[sp] = ((uint64_t)group_base << 32) | group_bits;
+                    stack[sp * stack_stride] = ((uint64_t)group_base << 32) | group_bits;
                 sp++; /* overflow is counted but dropped; the builder bounds the depth well below the stack size */
             }
 
@@ -298,7 +299,7 @@ B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int
             sp--;
             if (sp < B2_STACK_ENTRIES)
             {
-                const uint64_t e = stack[sp];
+                const uint64_t e = stack[sp * stack_stride];
                 group_base = (uint32_t)(e >> 32);
                 group_bits = (uint32_t)e;
             }

@@ -1,0 +1,486 @@
+/*
+ * b2_capi.cu -- device layer of the C ABI (include/b2pt.h, group 1): context, memory, streams/events, LUTs,
+ * BVH build + upload, precompiled-kernel lookup and launch. Thin by design: it is what replaces
+ * src/HIPRT-Orochi and the JIT half of src/Compiler in the reference.
+ */
+#include "b2pt.h"
+
+#include "b2_bvh_build.h"
+#include "b2_kernel_table.h"
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_last_error;
+
+void b2_set_error(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+#define B2_CUDA(call)                                                                                  \
+    do                                                                                                 \
+    {                                                                                                  \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+        {                                                                                              \
+            b2_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            return B2PT_ERR_CUDA;                                                                      \
+        }                                                                                              \
+    } while (0)
+
+struct b2pt_ctx
+{
+    int device = 0;
+    cudaDeviceProp props;
+};
+
+struct b2pt_bvh
+{
+    B2Node* nodes = nullptr;
+    B2Tri* tris = nullptr;
+    B2BvhDevice* descriptor = nullptr;
+    b2pt_bvh_stats_t stats;
+};
+
+struct b2pt_kernel
+{
+    b2pt_ctx* ctx = nullptr;
+    const B2KernelEntry* entry = nullptr;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    bool timed = false;
+    uint64_t launches = 0;
+};
+
+extern "C" {
+
+const char* b2pt_last_error_string(void) { return g_last_error.c_str(); }
+const char* b2pt_version_string(void) { return "b2pt 0.1 (sm_100a)"; }
+
+int b2pt_ctx_create(int device_index, b2pt_ctx** out_ctx)
+{
+    if (!out_ctx)
+    {
+        b2_set_error("b2pt_ctx_create: null output");
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+    {
+        b2_set_error("no CUDA device available (%s); libb2pt has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return B2PT_ERR_NO_DEVICE;
+    }
+    if (device_index < 0 || device_index >= count)
+    {
+        b2_set_error("device index %d out of range (%d devices)", device_index, count);
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    B2_CUDA(cudaSetDevice(device_index));
+    b2pt_ctx* ctx = new b2pt_ctx();
+    ctx->device = device_index;
+    B2_CUDA(cudaGetDeviceProperties(&ctx->props, device_index));
+    *out_ctx = ctx;
+    return B2PT_OK;
+}
+
+int b2pt_ctx_destroy(b2pt_ctx* ctx)
+{
+    delete ctx;
+    return B2PT_OK;
+}
+
+int b2pt_ctx_make_current(b2pt_ctx* ctx)
+{
+    if (!ctx) { b2_set_error("null context"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_CUDA(cudaSetDevice(ctx->device));
+    return B2PT_OK;
+}
+
+int b2pt_ctx_device_props(b2pt_ctx* ctx, b2pt_device_props_t* out)
+{
+    if (!ctx || !out) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    std::memset(out, 0, sizeof(*out));
+    std::strncpy(out->name, ctx->props.name, sizeof(out->name) - 1);
+    out->sm_count = ctx->props.multiProcessorCount;
+    out->compute_major = ctx->props.major;
+    out->compute_minor = ctx->props.minor;
+    out->total_memory_bytes = ctx->props.totalGlobalMem;
+    out->l2_bytes = (size_t)ctx->props.l2CacheSize;
+    out->shared_memory_per_block_optin = ctx->props.sharedMemPerBlockOptin;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    out->clock_khz = khz;
+    return B2PT_OK;
+}
+
+int b2pt_malloc(b2pt_ctx* ctx, size_t bytes, void** out_device_ptr)
+{
+    if (!ctx || !out_device_ptr) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    *out_device_ptr = nullptr;
+    if (bytes == 0)
+        return B2PT_OK;
+    B2_CUDA(cudaMalloc(out_device_ptr, bytes));
+    return B2PT_OK;
+}
+
+int b2pt_free(b2pt_ctx*, void* device_ptr)
+{
+    if (device_ptr)
+        B2_CUDA(cudaFree(device_ptr));
+    return B2PT_OK;
+}
+
+int b2pt_memcpy_h2d(b2pt_ctx*, void* dst, const void* src, size_t bytes, b2pt_stream stream)
+{
+    if (bytes == 0) return B2PT_OK;
+    if (stream) B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    else B2_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return B2PT_OK;
+}
+
+int b2pt_memcpy_d2h(b2pt_ctx*, void* dst, const void* src, size_t bytes, b2pt_stream stream)
+{
+    if (bytes == 0) return B2PT_OK;
+    if (stream) B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    else B2_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return B2PT_OK;
+}
+
+int b2pt_memcpy_d2d(b2pt_ctx*, void* dst, const void* src, size_t bytes, b2pt_stream stream)
+{
+    if (bytes == 0) return B2PT_OK;
+    if (stream) B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    else B2_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+    return B2PT_OK;
+}
+
+int b2pt_memset(b2pt_ctx*, void* device_ptr, int byte_value, size_t bytes, b2pt_stream stream)
+{
+    if (bytes == 0) return B2PT_OK;
+    if (stream) B2_CUDA(cudaMemsetAsync(device_ptr, byte_value, bytes, (cudaStream_t)stream));
+    else B2_CUDA(cudaMemset(device_ptr, byte_value, bytes));
+    return B2PT_OK;
+}
+
+int b2pt_host_alloc_pinned(b2pt_ctx*, size_t bytes, void** out_host_ptr)
+{
+    if (!out_host_ptr) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_CUDA(cudaMallocHost(out_host_ptr, bytes));
+    return B2PT_OK;
+}
+
+int b2pt_host_free_pinned(b2pt_ctx*, void* host_ptr)
+{
+    if (host_ptr)
+        B2_CUDA(cudaFreeHost(host_ptr));
+    return B2PT_OK;
+}
+
+int b2pt_stream_create(b2pt_ctx*, b2pt_stream* out_stream)
+{
+    cudaStream_t s;
+    B2_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out_stream = s;
+    return B2PT_OK;
+}
+int b2pt_stream_destroy(b2pt_ctx*, b2pt_stream stream)
+{
+    if (stream) B2_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return B2PT_OK;
+}
+int b2pt_stream_synchronize(b2pt_ctx*, b2pt_stream stream)
+{
+    B2_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return B2PT_OK;
+}
+int b2pt_event_create(b2pt_ctx*, b2pt_event* out_event)
+{
+    cudaEvent_t e;
+    B2_CUDA(cudaEventCreate(&e));
+    *out_event = e;
+    return B2PT_OK;
+}
+int b2pt_event_destroy(b2pt_ctx*, b2pt_event event)
+{
+    if (event) B2_CUDA(cudaEventDestroy((cudaEvent_t)event));
+    return B2PT_OK;
+}
+int b2pt_event_record(b2pt_ctx*, b2pt_event event, b2pt_stream stream)
+{
+    B2_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return B2PT_OK;
+}
+int b2pt_event_synchronize(b2pt_ctx*, b2pt_event event)
+{
+    B2_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+    return B2PT_OK;
+}
+int b2pt_event_elapsed_ms(b2pt_ctx*, b2pt_event start, b2pt_event stop, float* out_ms)
+{
+    B2_CUDA(cudaEventElapsedTime(out_ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return B2PT_OK;
+}
+
+int b2pt_lut_create(b2pt_ctx* ctx, const float* texels, int width, int height, int depth, int channels, void** out_handle)
+{
+    if (!ctx || !texels || !out_handle || width <= 0 || height <= 0 || depth <= 0 || channels <= 0)
+    {
+        b2_set_error("b2pt_lut_create: invalid argument");
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    /* descriptor and texels share one allocation: [b2pt_lut (padded to 256 B)][texels] */
+    size_t texel_bytes = (size_t)width * height * depth * channels * sizeof(float);
+    char* block = nullptr;
+    B2_CUDA(cudaMalloc((void**)&block, 256 + texel_bytes));
+    b2pt_lut desc;
+    desc.texels = reinterpret_cast<const float*>(block + 256);
+    desc.width = width;
+    desc.height = height;
+    desc.depth = depth;
+    desc.channels = channels;
+    B2_CUDA(cudaMemcpy(block, &desc, sizeof(desc), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(block + 256, texels, texel_bytes, cudaMemcpyHostToDevice));
+    *out_handle = block;
+    return B2PT_OK;
+}
+
+int b2pt_lut_destroy(b2pt_ctx*, void* handle)
+{
+    if (handle) B2_CUDA(cudaFree(handle));
+    return B2PT_OK;
+}
+
+int b2pt_bvh_build(b2pt_ctx* ctx, const int* triangle_indices, int triangle_count, const float* vertex_positions, int vertex_count,
+                   uint32_t, b2pt_stream stream, b2pt_bvh** out_bvh)
+{
+    if (!ctx || !out_bvh || triangle_count < 0 || vertex_count < 0 || (triangle_count > 0 && (!triangle_indices || !vertex_positions)))
+    {
+        b2_set_error("b2pt_bvh_build: invalid argument");
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    auto t0 = std::chrono::high_resolution_clock::now();
+    B2BvhHost host;
+    std::string error;
+    if (!b2_build_cw8(triangle_indices, (size_t)triangle_count, vertex_positions, (size_t)vertex_count, host, error))
+    {
+        b2_set_error("b2pt_bvh_build: %s", error.c_str());
+        return B2PT_ERR_UNSUPPORTED_SCENE;
+    }
+    b2pt_bvh* bvh = new b2pt_bvh();
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!host.nodes.empty())
+    {
+        B2_CUDA(cudaMalloc((void**)&bvh->nodes, host.nodes.size() * sizeof(B2Node)));
+        B2_CUDA(cudaMemcpyAsync(bvh->nodes, host.nodes.data(), host.nodes.size() * sizeof(B2Node), cudaMemcpyHostToDevice, s));
+    }
+    if (!host.tris.empty())
+    {
+        B2_CUDA(cudaMalloc((void**)&bvh->tris, host.tris.size() * sizeof(B2Tri)));
+        B2_CUDA(cudaMemcpyAsync(bvh->tris, host.tris.data(), host.tris.size() * sizeof(B2Tri), cudaMemcpyHostToDevice, s));
+    }
+    B2BvhDevice desc;
+    desc.nodes = bvh->nodes;
+    desc.tris = bvh->tris;
+    desc.node_count = (uint32_t)host.nodes.size();
+    desc.tri_count = (uint32_t)host.tris.size();
+    B2_CUDA(cudaMalloc((void**)&bvh->descriptor, sizeof(B2BvhDevice)));
+    B2_CUDA(cudaMemcpyAsync(bvh->descriptor, &desc, sizeof(desc), cudaMemcpyHostToDevice, s));
+    B2_CUDA(cudaStreamSynchronize(s)); /* the host vectors die at return */
+    bvh->stats.node_count = host.stats.node_count;
+    bvh->stats.triangle_count = host.stats.triangle_count;
+    bvh->stats.bytes = host.stats.bytes;
+    bvh->stats.max_depth = host.stats.max_depth;
+    bvh->stats.sah_cost = host.stats.sah_cost;
+    bvh->stats.build_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    *out_bvh = bvh;
+    return B2PT_OK;
+}
+
+void* b2pt_bvh_device_handle(b2pt_bvh* bvh) { return bvh ? bvh->descriptor : nullptr; }
+
+int b2pt_bvh_stats(b2pt_bvh* bvh, b2pt_bvh_stats_t* out)
+{
+    if (!bvh || !out) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    *out = bvh->stats;
+    return B2PT_OK;
+}
+
+int b2pt_bvh_destroy(b2pt_ctx*, b2pt_bvh* bvh)
+{
+    if (!bvh) return B2PT_OK;
+    cudaFree(bvh->nodes);
+    cudaFree(bvh->tris);
+    cudaFree(bvh->descriptor);
+    delete bvh;
+    return B2PT_OK;
+}
+
+/* ---- kernels ---- */
+
+struct MacroDefault { const char* name; int value; };
+/* macros a caller may pass with their reference default; any other value has no variant */
+static const MacroDefault kFixedMacros[] = {
+    { "DirectLightSamplingNEESampleCount", 1 }, { "DirectLightSamplingDeltaDistributionOptimization", 1 },
+    { "DirectLightSamplingAllowBackfacingLights", 0 }, { "TrianglePointSamplingStrategy", 1 }, { "EnvmapSamplingDoBSDFMIS", 1 },
+    { "EnvmapSamplingDoBilinearFiltering", 0 }, { "PathSamplingStrategy", 0 }, { "RISUseVisiblityTargetFunction", 0 },
+    { "NestedDielectricsStackSize", 4 }, { "UseSharedStackBVHTraversal", 1 }, { "KernelBlockWidthHeight", 8 },
+    { "PrincipledBSDFDiffuseLobe", 0 }, { "PrincipledBSDFAnisotropicGGXSampleFunction", 0 }, { "PrincipledBSDFDoEnergyCompensation", 1 },
+    { "PrincipledBSDFDoGlassEnergyCompensation", 1 }, { "PrincipledBSDFDoClearcoatEnergyCompensation", 1 },
+    { "PrincipledBSDFDoMetallicEnergyCompensation", 1 }, { "PrincipledBSDFDoMetallicFresnelEnergyCompensation", 1 },
+    { "PrincipledBSDFDoSpecularEnergyCompensation", 1 }, { "PrincipledBSDFDeltaDistributionEvaluationOptimization", 1 },
+    { "PrincipledBSDFSampleGlossyBasedOnFresnel", 0 }, { "PrincipledBSDFSampleCoatBasedOnFresnel", 0 },
+    { "PrincipledBSDFDoMicrofacetRegularization", 1 }, { "PrincipledBSDFDoMicrofacetRegularizationConsistentParameterization", 1 },
+    { "PrincipledBSDFMicrofacetRegularizationDiffusionHeuristic", 1 }, { "ReSTIR_DI_InitialTargetFunctionVisibility", 0 },
+    { "ReSTIR_DI_SpatialTargetFunctionVisibility", 0 }, { "ReSTIR_DI_DoVisibilityReuse", 1 }, { "ReSTIR_DI_BiasCorrectionUseVisibility", 1 },
+    { "ReSTIR_DI_BiasCorrectionWeights", 4 }, { "ReSTIR_DI_DoLightPresampling", 0 }, { "ReSTIR_DI_DoOptimalVisibilitySampling", 0 },
+    { "DirectLightUseNEEPlusPlus", 0 }, { "SharedStackBVHTraversalSize", 16 },
+};
+
+static int pass_of_entry_name(const char* name)
+{
+    if (!std::strcmp(name, "CameraRays")) return B2_PASS_CAMERA_RAYS;
+    if (!std::strcmp(name, "MegaKernel")) return B2_PASS_MEGAKERNEL;
+    if (!std::strcmp(name, "ReSTIR_DI_InitialCandidates")) return B2_PASS_RESTIR_DI_INITIAL_CANDIDATES;
+    if (!std::strcmp(name, "ReSTIR_DI_TemporalReuse")) return B2_PASS_RESTIR_DI_TEMPORAL;
+    if (!std::strcmp(name, "ReSTIR_DI_SpatialReuse")) return B2_PASS_RESTIR_DI_SPATIAL;
+    if (!std::strcmp(name, "ReSTIR_DI_SpatiotemporalReuse")) return B2_PASS_RESTIR_DI_SPATIOTEMPORAL;
+    return -1;
+}
+
+int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* options, int option_count, b2pt_kernel** out_kernel)
+{
+    if (!ctx || !entry_name || !out_kernel || option_count < 0 || (option_count > 0 && !options))
+    {
+        b2_set_error("b2pt_kernel_get: invalid argument");
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    int pass = pass_of_entry_name(entry_name);
+    if (pass < 0)
+    {
+        b2_set_error("b2pt_kernel_get: unknown kernel entry '%s'", entry_name);
+        return B2PT_ERR_NO_VARIANT;
+    }
+    /* reference defaults */
+    int bsdf = 0, direct = 4, base = 1, later = 3, envmap = 2, precise = 1, counters = 0;
+    for (int i = 0; i < option_count; i++)
+    {
+        const char* n = options[i].name;
+        int v = options[i].value;
+        if (!n) { b2_set_error("b2pt_kernel_get: null option name"); return B2PT_ERR_INVALID_ARGUMENT; }
+        if (!std::strcmp(n, "BSDFOverride")) bsdf = (v == 3) ? 0 : v; /* BSDF_PRINCIPLED == BSDF_NONE in the dispatcher */
+        else if (!std::strcmp(n, "DirectLightSamplingStrategy")) direct = v;
+        else if (!std::strcmp(n, "DirectLightSamplingBaseStrategy")) base = v;
+        else if (!std::strcmp(n, "ReSTIR_DI_LaterBouncesSamplingStrategy")) later = v;
+        else if (!std::strcmp(n, "EnvmapSamplingStrategy")) envmap = v;
+        else if (!std::strcmp(n, "B2PT_PRECISE")) precise = v;
+        else if (!std::strcmp(n, "B2PT_COUNTERS")) counters = v;
+        else
+        {
+            bool known = false;
+            for (const MacroDefault& m : kFixedMacros)
+                if (!std::strcmp(n, m.name))
+                {
+                    known = true;
+                    if (m.value != v)
+                    {
+                        b2_set_error("no precompiled variant with %s=%d (only the reference default %d is built)", n, v, m.value);
+                        return B2PT_ERR_NO_VARIANT;
+                    }
+                }
+            if (!known)
+            {
+                b2_set_error("no precompiled variant knows the option '%s'", n);
+                return B2PT_ERR_NO_VARIANT;
+            }
+        }
+    }
+    int count = 0;
+    const B2KernelEntry* table = precise ? b2_kernel_table_precise(&count) : b2_kernel_table_fast(&count);
+    for (int i = 0; i < count; i++)
+    {
+        const B2KernelEntry& e = table[i];
+        bool later_matters = e.direct == 5; /* LSS_RESTIR_DI */
+        if (e.pass == pass && e.bsdf_override == bsdf && e.direct == direct && e.base == base && (!later_matters || e.later == later) && e.envmap == envmap && e.counters == (counters ? 1 : 0))
+        {
+            b2pt_kernel* k = new b2pt_kernel();
+            k->ctx = ctx;
+            k->entry = &e;
+            B2_CUDA(cudaEventCreate(&k->start));
+            B2_CUDA(cudaEventCreate(&k->stop));
+            *out_kernel = k;
+            return B2PT_OK;
+        }
+    }
+    b2_set_error("no precompiled variant for %s with BSDFOverride=%d DirectLightSamplingStrategy=%d DirectLightSamplingBaseStrategy=%d "
+                 "ReSTIR_DI_LaterBouncesSamplingStrategy=%d EnvmapSamplingStrategy=%d precise=%d counters=%d",
+                 entry_name, bsdf, direct, base, later, envmap, precise, counters);
+    return B2PT_ERR_NO_VARIANT;
+}
+
+int b2pt_kernel_launch(b2pt_kernel* kernel, int, int, int width, int height, void** args, b2pt_stream stream)
+{
+    if (!kernel || !args || !args[0] || width <= 0 || height <= 0)
+    {
+        b2_set_error("b2pt_kernel_launch: invalid argument");
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    const b2pt_render_data* rd = reinterpret_cast<const b2pt_render_data*>(args[0]);
+    cudaStream_t s = (cudaStream_t)stream;
+    B2_CUDA(cudaEventRecord(kernel->start, s));
+    B2_CUDA(kernel->entry->launch(rd, width, height, s));
+    B2_CUDA(cudaEventRecord(kernel->stop, s));
+    kernel->timed = true;
+    kernel->launches++;
+    return B2PT_OK;
+}
+
+int b2pt_kernel_last_ms(b2pt_kernel* kernel, float* out_ms)
+{
+    if (!kernel || !out_ms) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    *out_ms = 0.0f;
+    if (!kernel->timed)
+        return B2PT_OK;
+    B2_CUDA(cudaEventSynchronize(kernel->stop));
+    B2_CUDA(cudaEventElapsedTime(out_ms, kernel->start, kernel->stop));
+    return B2PT_OK;
+}
+
+int b2pt_kernel_launch_count(b2pt_kernel* kernel, uint64_t* out_count)
+{
+    if (!kernel || !out_count) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    *out_count = kernel->launches;
+    return B2PT_OK;
+}
+
+int b2pt_counters_reset(b2pt_ctx*)
+{
+    B2_CUDA(b2_counters_reset_precise());
+    B2_CUDA(b2_counters_reset_fast());
+    return B2PT_OK;
+}
+
+int b2pt_counters_read(b2pt_ctx*, b2pt_counters_t* out)
+{
+    if (!out) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    unsigned long long a[3], b[3];
+    B2_CUDA(cudaDeviceSynchronize());
+    B2_CUDA(b2_counters_read_precise(a));
+    B2_CUDA(b2_counters_read_fast(b));
+    out->rays = a[0] + b[0];
+    out->nodes = a[1] + b[1];
+    out->triangles = a[2] + b[2];
+    return B2PT_OK;
+}
+
+} /* extern "C" */

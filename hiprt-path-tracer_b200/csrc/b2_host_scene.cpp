@@ -158,7 +158,7 @@ B2PackedTexturedMaterial pack_to_gpu(const SafeMaterial& m)
 }
 } // namespace
 
-bool b2_host_scene_prepare(B2HostScene& scene, std::string& error)
+bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bvh)
 {
     const B2Scene& blob = scene.blob;
     const size_t n_mat = blob.n_materials(), n_tri = blob.n_triangles(), n_vert = blob.n_vertices();
@@ -268,6 +268,8 @@ bool b2_host_scene_prepare(B2HostScene& scene, std::string& error)
     b2pt_build_alias_table(power_list, power_sum, scene.power_alias_probas, scene.power_alias_alias);
     scene.power_sum = power_sum;
 
+    if (!build_bvh)
+        return true;
     auto t0 = std::chrono::high_resolution_clock::now();
     if (!b2_build_cw8(blob.indices.data(), n_tri, blob.positions.data(), n_vert, scene.bvh, error))
         return false;

@@ -80,6 +80,6 @@ struct B2HostScene
 
 /* Fills every derived array of `scene` from `scene.blob`. Returns false and sets `error` on unsupported input
  * (dispersive media, > 2^26 - 1 materials, invalid indices). */
-bool b2_host_scene_prepare(B2HostScene& scene, std::string& error);
+bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bvh = true);
 
 #endif

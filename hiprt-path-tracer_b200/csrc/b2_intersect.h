@@ -237,7 +237,8 @@ struct Ctx
 {
     const b2pt_render_data* rd;
     B2BvhDevice bvh;
-    uint64_t* stack;               /* B2_STACK_ENTRIES slots private to this thread */
+    uint64_t* stack;               /* first of B2_STACK_ENTRIES slots private to this thread */
+    int stack_stride;              /* distance between this thread's consecutive slots */
     B2TraversalCounters* counters; /* null unless the instrumented variant runs */
 };
 
@@ -304,7 +305,7 @@ B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload&
     bool skipping_volume_boundary = false;
     do
     {
-        hit = b2_traverse<false>(ctx.bvh, origin, direction, 3.0e38f, last_hit_primitive_index, ctx.stack, ctx.counters);
+        hit = b2_traverse<false>(ctx.bvh, origin, direction, 3.0e38f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters);
         if (hit.prim < 0)
             return false;
 
@@ -353,7 +354,7 @@ B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload&
 /* true when something lies strictly before t_max - 1e-4 (opaque scenes) */
 B2_HD bool shadow_ray_occluded(const Ctx& ctx, V3 origin, V3 direction, float t_max, int last_hit_primitive_index)
 {
-    B2Hit hit = b2_traverse<true>(ctx.bvh, origin, direction, t_max - 1.0e-4f, last_hit_primitive_index, ctx.stack, ctx.counters);
+    B2Hit hit = b2_traverse<true>(ctx.bvh, origin, direction, t_max - 1.0e-4f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters);
     return hit.prim >= 0;
 }
 
@@ -371,7 +372,7 @@ struct LightRayHit
 B2_HD bool bsdf_light_sample_ray(const Ctx& ctx, V3 origin, V3 direction, float t_max, LightRayHit& out, int last_hit_primitive_index)
 {
     const b2pt_render_data& rd = *ctx.rd;
-    B2Hit hit = b2_traverse<false>(ctx.bvh, origin, direction, 3.0e38f, last_hit_primitive_index, ctx.stack, ctx.counters);
+    B2Hit hit = b2_traverse<false>(ctx.bvh, origin, direction, 3.0e38f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters);
     if (hit.prim < 0)
         return false;
     if (!(hit.t < t_max - 1.0e-4f))

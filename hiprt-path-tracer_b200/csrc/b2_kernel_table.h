@@ -1,0 +1,29 @@
+/* b2_kernel_table.h -- registry of precompiled kernel variants (one table per codegen flavour). */
+#ifndef B2_KERNEL_TABLE_H
+#define B2_KERNEL_TABLE_H
+
+#include "b2_frame_loop.h"
+
+#include <cuda_runtime.h>
+
+struct B2KernelEntry
+{
+    int pass;          /* B2Pass */
+    int bsdf_override; /* variant key: the reference's macro values */
+    int direct;
+    int base;
+    int later;
+    int envmap;
+    int counters;
+    cudaError_t (*launch)(const b2pt_render_data* rd, int width, int height, cudaStream_t stream);
+};
+
+/* defined once per flavour by b2_kernels.cu (compiled twice: -fmad=false / fast) */
+const B2KernelEntry* b2_kernel_table_precise(int* count);
+const B2KernelEntry* b2_kernel_table_fast(int* count);
+cudaError_t b2_counters_reset_precise();
+cudaError_t b2_counters_reset_fast();
+cudaError_t b2_counters_read_precise(unsigned long long out[3]);
+cudaError_t b2_counters_read_fast(unsigned long long out[3]);
+
+#endif

@@ -1,0 +1,603 @@
+/*
+ * b2_renderer.cpp -- headless host mirror of the reference's renderer front end (include/b2pt.h, group 2).
+ *
+ * Mirrors GPURenderer's public surface (set_scene / set_camera / set_envmap / render / reset / get_render_data,
+ * /root/reference/src/Renderer/GPURenderer.h:61-346; set_scene uploads at GPURenderer.cpp:769-939) on top of the
+ * device layer of this library -- it only calls b2pt_* group-1 entry points, the same ones a maintainer would bind
+ * from the reference's own GPURenderer. Pass order and host RNG draws: B2FrameLoop (b2_frame_loop.h).
+ */
+#include "b2pt.h"
+
+#include "b2_frame_loop.h"
+#include "b2_host_scene.h"
+#include "b2_material.h"
+#include "b2pt_alias_table.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+void b2_set_error(const char* fmt, ...);
+
+#define B2_TRY(call)          \
+    do                        \
+    {                         \
+        int rc_ = (call);     \
+        if (rc_ != B2PT_OK)   \
+            return rc_;       \
+    } while (0)
+
+struct b2pt_renderer
+{
+    b2pt_ctx* ctx = nullptr;
+    int width = 0, height = 0;
+    std::string variant;
+    int precise = 1;
+    int counters = 0;
+    bool kernels_stale = true;
+    bool profile_passes = false;
+
+    B2FrameLoop loop;
+    B2HostScene scene;
+    bool has_scene = false;
+
+    b2pt_stream stream = nullptr;
+    b2pt_event ev_start = nullptr, ev_stop = nullptr;
+    bool timed = false;
+    std::vector<void*> frame_allocs, scene_allocs, lut_handles, envmap_allocs;
+    b2pt_bvh* bvh = nullptr;
+    b2pt_kernel* kernels[B2_PASS_COUNT] = {};
+    double pass_ms[B2_PASS_COUNT] = {};
+    uint64_t pass_launches[B2_PASS_COUNT] = {};
+    uint8_t* d_status = nullptr; /* [0] still_one_ray_active, [4..7] pixel_count_converged_so_far */
+    void* d_reservoirs[3] = {};
+
+    size_t pixels() const { return (size_t)width * height; }
+};
+
+namespace
+{
+int alloc_zero(b2pt_renderer* r, std::vector<void*>& owner, size_t bytes, void** out)
+{
+    B2_TRY(b2pt_malloc(r->ctx, bytes, out));
+    owner.push_back(*out);
+    return b2pt_memset(r->ctx, *out, 0, bytes, nullptr);
+}
+
+template <class T>
+int upload(b2pt_renderer* r, std::vector<void*>& owner, const std::vector<T>& host, T** out)
+{
+    *out = nullptr;
+    if (host.empty())
+        return B2PT_OK;
+    void* d = nullptr;
+    B2_TRY(b2pt_malloc(r->ctx, host.size() * sizeof(T), &d));
+    owner.push_back(d);
+    *out = reinterpret_cast<T*>(d);
+    return b2pt_memcpy_h2d(r->ctx, d, host.data(), host.size() * sizeof(T), nullptr);
+}
+
+void free_all(b2pt_renderer* r, std::vector<void*>& owner)
+{
+    for (void* p : owner)
+        b2pt_free(r->ctx, p);
+    owner.clear();
+}
+
+struct VariantKey { const char* name; int bsdf, direct, base, later; bool restir; };
+const VariantKey kVariants[] = {
+    { "c1", 1, 1, 0, 3, false },
+    { "c2", 0, 3, 1, 3, false },
+    { "c3", 0, 4, 1, 3, false },
+    { "c4", 0, 5, 1, 3, true },
+};
+
+const VariantKey* find_variant(const std::string& name)
+{
+    for (const VariantKey& v : kVariants)
+        if (name == v.name)
+            return &v;
+    return nullptr;
+}
+
+const char* entry_name_of_pass(int pass)
+{
+    switch (pass)
+    {
+    case B2_PASS_CAMERA_RAYS: return "CameraRays";
+    case B2_PASS_MEGAKERNEL: return "MegaKernel";
+    case B2_PASS_RESTIR_DI_INITIAL_CANDIDATES: return "ReSTIR_DI_InitialCandidates";
+    case B2_PASS_RESTIR_DI_TEMPORAL: return "ReSTIR_DI_TemporalReuse";
+    case B2_PASS_RESTIR_DI_SPATIAL: return "ReSTIR_DI_SpatialReuse";
+    case B2_PASS_RESTIR_DI_SPATIOTEMPORAL: return "ReSTIR_DI_SpatiotemporalReuse";
+    default: return nullptr;
+    }
+}
+
+int resolve_kernels(b2pt_renderer* r)
+{
+    if (!r->kernels_stale)
+        return B2PT_OK;
+    const VariantKey* v = find_variant(r->variant);
+    for (int pass = 0; pass < B2_PASS_COUNT; pass++)
+    {
+        r->kernels[pass] = nullptr; /* kernel objects are tiny; earlier ones are intentionally kept alive */
+        const char* entry = entry_name_of_pass(pass);
+        if (!entry)
+            continue;
+        bool restir_pass = pass != B2_PASS_CAMERA_RAYS && pass != B2_PASS_MEGAKERNEL;
+        if (restir_pass && !v->restir)
+            continue;
+        b2pt_option opts[] = {
+            { "BSDFOverride", v->bsdf }, { "DirectLightSamplingStrategy", v->direct }, { "DirectLightSamplingBaseStrategy", v->base },
+            { "ReSTIR_DI_LaterBouncesSamplingStrategy", v->later }, { "B2PT_PRECISE", r->precise }, { "B2PT_COUNTERS", r->counters },
+        };
+        B2_TRY(b2pt_kernel_get(r->ctx, entry, opts, (int)(sizeof(opts) / sizeof(opts[0])), &r->kernels[pass]));
+    }
+    r->kernels_stale = false;
+    return B2PT_OK;
+}
+
+int upload_scene(b2pt_renderer* r)
+{
+    free_all(r, r->scene_allocs);
+    if (r->bvh)
+    {
+        b2pt_bvh_destroy(r->ctx, r->bvh);
+        r->bvh = nullptr;
+    }
+    B2HostScene& s = r->scene;
+    std::string error;
+    if (!b2_host_scene_prepare(s, error, /* build_bvh = */ false))
+    {
+        b2_set_error("scene rejected: %s", error.c_str());
+        return B2PT_ERR_UNSUPPORTED_SCENE;
+    }
+
+    b2pt_render_data& rd = r->loop.rd;
+    b2pt_render_buffers& b = rd.buffers;
+    float* d_pos = nullptr;
+    float* d_nrm = nullptr;
+    float* d_uv = nullptr;
+    float* d_emission = nullptr;
+    B2_TRY(upload(r, r->scene_allocs, s.blob.indices, &b.triangles_indices));
+    B2_TRY(upload(r, r->scene_allocs, s.blob.positions, &d_pos));
+    B2_TRY(upload(r, r->scene_allocs, s.blob.normals, &d_nrm));
+    B2_TRY(upload(r, r->scene_allocs, s.blob.texcoords, &d_uv));
+    B2_TRY(upload(r, r->scene_allocs, s.blob.has_normals, &b.has_vertex_normals));
+    B2_TRY(upload(r, r->scene_allocs, s.triangle_areas, &b.triangles_areas));
+    B2_TRY(upload(r, r->scene_allocs, s.blob.material_indices, &b.material_indices));
+    B2_TRY(upload(r, r->scene_allocs, s.material_opaque, &b.material_opaque));
+    B2_TRY(upload(r, r->scene_allocs, s.emissive_triangles, &b.emissive_triangles_primitive_indices));
+    b.vertices_positions = reinterpret_cast<b2pt_float3*>(d_pos);
+    b.vertex_normals = reinterpret_cast<b2pt_float3*>(d_nrm);
+    b.texcoords = reinterpret_cast<b2pt_float2*>(d_uv);
+    b.emissive_triangles_count = (int)s.emissive_triangles.size();
+    b.emissive_triangles_primitive_indices_and_emissive_textures = b.emissive_triangles_primitive_indices;
+    B2_TRY(upload(r, r->scene_allocs, s.power_alias_alias, &b.emissives_power_alias_table.alias_table_alias));
+    B2_TRY(upload(r, r->scene_allocs, s.power_alias_probas, &b.emissives_power_alias_table.alias_table_probas));
+    b.emissives_power_alias_table.sum_elements = s.power_sum;
+    b.emissives_power_alias_table.size = (unsigned)s.emissive_triangles.size();
+    b.material_textures = nullptr;
+
+    B2MaterialSoAHost& m = s.materials;
+    b2pt_materials_soa& d = b.materials_buffer;
+    B2_TRY(upload(r, r->scene_allocs, m.flags, &d.flags));
+    B2_TRY(upload(r, r->scene_allocs, m.emission, &d_emission));
+    d.emission = reinterpret_cast<b2pt_rgb*>(d_emission);
+    B2_TRY(upload(r, r->scene_allocs, m.base_color_roughness, &d.base_color_roughness));
+    B2_TRY(upload(r, r->scene_allocs, m.oren_nayar_sigma, &d.oren_nayar_sigma));
+    B2_TRY(upload(r, r->scene_allocs, m.metallic_F90_and_metallic, &d.metallic_F90_and_metallic));
+    B2_TRY(upload(r, r->scene_allocs, m.metallic_F82_packed_and_diffuse_transmission, &d.metallic_F82_packed_and_diffuse_transmission));
+    B2_TRY(upload(r, r->scene_allocs, m.metallic_F90_falloff_exponent, &d.metallic_F90_falloff_exponent));
+    B2_TRY(upload(r, r->scene_allocs, m.anisotropy_and_rotation_and_second_roughness, &d.anisotropy_and_rotation_and_second_roughness));
+    B2_TRY(upload(r, r->scene_allocs, m.specular_color_and_tint_factor, &d.specular_color_and_tint_factor));
+    B2_TRY(upload(r, r->scene_allocs, m.specular_and_darkening_and_coat_roughness, &d.specular_and_darkening_and_coat_roughness));
+    B2_TRY(upload(r, r->scene_allocs, m.coat_medium_thickness, &d.coat_medium_thickness));
+    B2_TRY(upload(r, r->scene_allocs, m.coat_and_medium_absorption, &d.coat_and_medium_absorption));
+    B2_TRY(upload(r, r->scene_allocs, m.coat_roughening_darkening_anisotropy_and_rotation, &d.coat_roughening_darkening_anisotropy_and_rotation));
+    B2_TRY(upload(r, r->scene_allocs, m.coat_ior, &d.coat_ior));
+    B2_TRY(upload(r, r->scene_allocs, m.sheen_and_color, &d.sheen_and_color));
+    B2_TRY(upload(r, r->scene_allocs, m.ior, &d.ior));
+    B2_TRY(upload(r, r->scene_allocs, m.absorption_color_packed, &d.absorption_color_packed));
+    B2_TRY(upload(r, r->scene_allocs, m.absorption_at_distance, &d.absorption_at_distance));
+    B2_TRY(upload(r, r->scene_allocs, m.sheen_roughness_transmission_dispersion_thin_film, &d.sheen_roughness_transmission_dispersion_thin_film));
+    B2_TRY(upload(r, r->scene_allocs, m.dispersion_abbe_number, &d.dispersion_abbe_number));
+    B2_TRY(upload(r, r->scene_allocs, m.thin_film_ior, &d.thin_film_ior));
+    B2_TRY(upload(r, r->scene_allocs, m.thin_film_thickness, &d.thin_film_thickness));
+    B2_TRY(upload(r, r->scene_allocs, m.thin_film_kappa_3, &d.thin_film_kappa_3));
+    B2_TRY(upload(r, r->scene_allocs, m.thin_film_base_ior_override, &d.thin_film_base_ior_override));
+    B2_TRY(upload(r, r->scene_allocs, m.alpha_thin_film_hue_dielectric_priority, &d.alpha_thin_film_hue_dielectric_priority));
+    B2_TRY(upload(r, r->scene_allocs, m.normal_map_emission_index, &d.normal_map_emission_index));
+    B2_TRY(upload(r, r->scene_allocs, m.base_color_roughness_metallic_index, &d.base_color_roughness_metallic_index));
+    B2_TRY(upload(r, r->scene_allocs, m.roughness_and_metallic_index, &d.roughness_and_metallic_index));
+    B2_TRY(upload(r, r->scene_allocs, m.anisotropic_specular_index, &d.anisotropic_specular_index));
+    B2_TRY(upload(r, r->scene_allocs, m.coat_sheen_index, &d.coat_sheen_index));
+    B2_TRY(upload(r, r->scene_allocs, m.specular_transmission_index, &d.specular_transmission_index));
+
+    B2_TRY(b2pt_bvh_build(r->ctx, s.blob.indices.data(), (int)s.blob.n_triangles(), s.blob.positions.data(), (int)s.blob.n_vertices(), 0, nullptr, &r->bvh));
+    rd.GPU_BVH = b2pt_bvh_device_handle(r->bvh);
+    rd.light_GPU_BVH = nullptr;
+
+    /* camera (static): what Camera::to_hiprt hands over every sample */
+    b2pt_camera& cam = r->loop.camera;
+    std::memcpy(cam.inverse_view, s.blob.camera.inverse_view, 64);
+    std::memcpy(cam.inverse_projection, s.blob.camera.inverse_projection, 64);
+    std::memcpy(cam.view_projection, s.blob.camera.view_projection, 64);
+    cam.position = b2pt_float3{ s.blob.camera.position[0], s.blob.camera.position[1], s.blob.camera.position[2] };
+    cam.vertical_fov = s.blob.camera.vertical_fov;
+    cam.sensor_width = r->width;
+    cam.sensor_height = r->height;
+    cam.do_jittering = 1;
+    rd.current_camera = cam;
+    r->has_scene = true;
+    return B2PT_OK;
+}
+} // namespace
+
+extern "C" {
+
+int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* variant, int precise, b2pt_renderer** out_renderer)
+{
+    if (!ctx || !variant || !out_renderer || width <= 0 || height <= 0)
+    {
+        b2_set_error("b2pt_renderer_create: invalid argument");
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    if (!find_variant(variant))
+    {
+        b2_set_error("b2pt_renderer_create: unknown variant '%s' (c1, c2, c3, c4)", variant);
+        return B2PT_ERR_NO_VARIANT;
+    }
+    B2_TRY(b2pt_ctx_make_current(ctx));
+    b2pt_renderer* r = new b2pt_renderer();
+    r->ctx = ctx;
+    r->width = width;
+    r->height = height;
+    r->variant = variant;
+    r->precise = precise ? 1 : 0;
+    r->loop.restir_di = find_variant(variant)->restir;
+    B2_TRY(b2pt_stream_create(ctx, &r->stream));
+    B2_TRY(b2pt_event_create(ctx, &r->ev_start));
+    B2_TRY(b2pt_event_create(ctx, &r->ev_stop));
+
+    const size_t n = r->pixels();
+    b2pt_render_data& rd = r->loop.rd;
+    rd.render_settings.render_resolution = b2pt_int2{ width, height };
+    void* p = nullptr;
+    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_rgb), &p)); rd.buffers.accumulated_ray_colors = (b2pt_rgb*)p;
+    B2_TRY(alloc_zero(r, r->frame_allocs, n, &p)); rd.aux_buffers.pixel_active = (uint8_t*)p;
+    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_float3), &p)); rd.aux_buffers.denoiser_normals = (b2pt_float3*)p;
+    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_rgb), &p)); rd.aux_buffers.denoiser_albedo = (b2pt_rgb*)p;
+    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(int), &p)); rd.aux_buffers.pixel_sample_count = (int*)p;
+    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(float), &p)); rd.aux_buffers.pixel_squared_luminance = (float*)p;
+    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(int), &p)); rd.aux_buffers.pixel_converged_sample_count = (int*)p;
+    B2_TRY(alloc_zero(r, r->frame_allocs, 16, &p)); r->d_status = (uint8_t*)p;
+    rd.aux_buffers.still_one_ray_active = r->d_status;
+    rd.aux_buffers.pixel_count_converged_so_far = (unsigned int*)(r->d_status + 4);
+    b2pt_gbuffer* gb[2] = { &rd.g_buffer, &rd.g_buffer_prev_frame };
+    for (int i = 0; i < 2; i++)
+    {
+        B2_TRY(alloc_zero(r, r->frame_allocs, n * 108, &p)); gb[i]->materials = p;
+        B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(int), &p)); gb[i]->first_hit_prim_index = (int*)p;
+        B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_float3), &p)); gb[i]->primary_hit_position = (b2pt_float3*)p;
+        B2_TRY(alloc_zero(r, r->frame_allocs, n * 4, &p)); gb[i]->shading_normals = (uint32_t*)p;
+        B2_TRY(alloc_zero(r, r->frame_allocs, n * 4, &p)); gb[i]->geometric_normals = (uint32_t*)p;
+    }
+    for (int i = 0; i < 3; i++)
+        B2_TRY(alloc_zero(r, r->frame_allocs, n * 36, &r->d_reservoirs[i]));
+    r->loop.initial_reservoirs = r->d_reservoirs[0];
+    r->loop.spatial_reservoirs_1 = r->d_reservoirs[1];
+    r->loop.spatial_reservoirs_2 = r->d_reservoirs[2];
+    rd.render_settings.restir_di_settings.initial_candidates.output_reservoirs = r->d_reservoirs[0];
+    rd.render_settings.restir_di_settings.restir_output_reservoirs = r->d_reservoirs[1];
+    *out_renderer = r;
+    return B2PT_OK;
+}
+
+int b2pt_renderer_destroy(b2pt_renderer* r)
+{
+    if (!r) return B2PT_OK;
+    b2pt_stream_synchronize(r->ctx, r->stream);
+    free_all(r, r->frame_allocs);
+    free_all(r, r->scene_allocs);
+    free_all(r, r->envmap_allocs);
+    for (void* h : r->lut_handles)
+        b2pt_lut_destroy(r->ctx, h);
+    if (r->bvh) b2pt_bvh_destroy(r->ctx, r->bvh);
+    b2pt_event_destroy(r->ctx, r->ev_start);
+    b2pt_event_destroy(r->ctx, r->ev_stop);
+    b2pt_stream_destroy(r->ctx, r->stream);
+    delete r;
+    return B2PT_OK;
+}
+
+int b2pt_renderer_set_scene_file(b2pt_renderer* r, const char* scene_blob_path)
+{
+    if (!r || !scene_blob_path) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    std::string err = b2scene_read(scene_blob_path, r->scene.blob);
+    if (!err.empty())
+    {
+        b2_set_error("%s", err.c_str());
+        return B2PT_ERR_IO;
+    }
+    return upload_scene(r);
+}
+
+int b2pt_renderer_set_scene_arrays(b2pt_renderer* r, const float* positions, const float* normals, const float* texcoords,
+                                   const uint8_t* has_normals, int vertex_count, const int* indices, const int* material_indices,
+                                   int triangle_count, const float* materials, int material_count, const float* camera52)
+{
+    if (!r || !positions || !indices || !material_indices || !materials || !camera52 || vertex_count <= 0 || triangle_count <= 0 || material_count <= 0)
+    {
+        b2_set_error("b2pt_renderer_set_scene_arrays: invalid argument");
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    B2Scene& s = r->scene.blob;
+    s.positions.assign(positions, positions + 3 * (size_t)vertex_count);
+    if (normals) s.normals.assign(normals, normals + 3 * (size_t)vertex_count); else s.normals.assign(3 * (size_t)vertex_count, 0.0f);
+    if (texcoords) s.texcoords.assign(texcoords, texcoords + 2 * (size_t)vertex_count); else s.texcoords.assign(2 * (size_t)vertex_count, 0.0f);
+    if (has_normals) s.has_normals.assign(has_normals, has_normals + vertex_count); else s.has_normals.assign(vertex_count, normals ? 1 : 0);
+    s.indices.assign(indices, indices + 3 * (size_t)triangle_count);
+    s.material_indices.assign(material_indices, material_indices + triangle_count);
+    s.materials.assign(materials, materials + (size_t)material_count * B2MAT_FLOAT_COUNT);
+    std::memcpy(&s.camera, camera52, sizeof(B2SceneCamera));
+    return upload_scene(r);
+}
+
+int b2pt_renderer_set_luts_file(b2pt_renderer* r, const char* lut_blob_path)
+{
+    if (!r || !lut_blob_path) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    FILE* f = std::fopen(lut_blob_path, "rb");
+    char magic[8];
+    uint32_t count = 0;
+    if (!f || std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "B2LUTS01", 8) != 0 || std::fread(&count, 4, 1, f) != 1)
+    {
+        if (f) std::fclose(f);
+        b2_set_error("cannot read LUT container %s", lut_blob_path);
+        return B2PT_ERR_IO;
+    }
+    for (void* h : r->lut_handles)
+        b2pt_lut_destroy(r->ctx, h);
+    r->lut_handles.clear();
+    b2pt_bsdfs_data& b = r->loop.rd.bsdfs_data;
+    for (uint32_t i = 0; i < count; i++)
+    {
+        char name[32];
+        int32_t dims[3];
+        if (std::fread(name, 1, 32, f) != 32 || std::fread(dims, 4, 3, f) != 3)
+        {
+            std::fclose(f);
+            b2_set_error("truncated LUT container");
+            return B2PT_ERR_IO;
+        }
+        std::vector<float> texels((size_t)dims[0] * dims[1] * dims[2]);
+        if (std::fread(texels.data(), 4, texels.size(), f) != texels.size())
+        {
+            std::fclose(f);
+            b2_set_error("truncated LUT container");
+            return B2PT_ERR_IO;
+        }
+        void* handle = nullptr;
+        int rc = b2pt_lut_create(r->ctx, texels.data(), dims[0], dims[1], dims[2], 1, &handle);
+        if (rc != B2PT_OK)
+        {
+            std::fclose(f);
+            return rc;
+        }
+        r->lut_handles.push_back(handle);
+        if (!std::strcmp(name, "ggx_conductor")) b.GGX_conductor_directional_albedo = handle;
+        else if (!std::strcmp(name, "glossy_dielectric")) b.glossy_dielectric_directional_albedo = handle;
+        else if (!std::strcmp(name, "ggx_glass")) b.GGX_glass_directional_albedo = handle;
+        else if (!std::strcmp(name, "ggx_glass_inv")) b.GGX_glass_directional_albedo_inverse = handle;
+        else if (!std::strcmp(name, "ggx_thin_glass")) b.GGX_thin_glass_directional_albedo = handle;
+    }
+    std::fclose(f);
+    return B2PT_OK;
+}
+
+/* RendererEnvmap / CPURenderer::set_envmap (CPURenderer.cpp:467-508): luminance alias table (Image.cpp:536-545,
+ * 652-671) + RGBE9995 packing (EnvmapRGBE9995.h:21-46, Packing.h:443-468) */
+int b2pt_renderer_set_envmap(b2pt_renderer* r, const float* rgba, int width, int height)
+{
+    if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    free_all(r, r->envmap_allocs);
+    b2pt_world_settings& w = r->loop.rd.world_settings;
+    if (!rgba || width <= 0 || height <= 0)
+    {
+        w.ambient_light_type = 1;
+        w.envmap = nullptr;
+        return B2PT_OK;
+    }
+    const size_t n = (size_t)width * height;
+    std::vector<float> lum(n);
+    std::vector<uint32_t> packed(n);
+    float total = 0.0f;
+    const float weights[3] = { 0.3086f, 0.6094f, 0.0820f };
+    for (size_t i = 0; i < n; i++)
+    {
+        float l = 0.0f;
+        for (int c = 0; c < 3; c++)
+            l += rgba[4 * i + c] * weights[c];
+        total += l;
+        lum[i] = l;
+
+        const float k_max = b2_uint_as_float(0x477F8000u), k_min = b2_uint_as_float(0x37800000u);
+        float cr = fminf(k_max, fmaxf(0.0f, rgba[4 * i + 0])), cg = fminf(k_max, fmaxf(0.0f, rgba[4 * i + 1])), cb = fminf(k_max, fmaxf(0.0f, rgba[4 * i + 2]));
+        float max_channel = b2_max(b2_max(k_min, cr), b2_max(cg, cb));
+        float bias = b2_uint_as_float((b2_float_as_uint(max_channel) + 0x07804000u) & 0x7F800000u);
+        uint32_t R = b2_float_as_uint(cr + bias), G = b2_float_as_uint(cg + bias), B = b2_float_as_uint(cb + bias);
+        uint32_t E = (b2_float_as_uint(bias) << 4) + 0x10000000u;
+        packed[i] = E | B << 18 | G << 9 | (R & 0x1FFu);
+    }
+    std::vector<float> probas;
+    std::vector<int> alias;
+    b2pt_build_alias_table(lum, total, probas, alias);
+    B2_TRY(upload(r, r->envmap_allocs, packed, &w.envmap));
+    B2_TRY(upload(r, r->envmap_allocs, probas, &w.envmap_alias_table.alias_table_probas));
+    B2_TRY(upload(r, r->envmap_allocs, alias, &w.envmap_alias_table.alias_table_alias));
+    w.envmap_alias_table.sum_elements = total;
+    w.envmap_alias_table.size = (unsigned)n;
+    w.envmap_total_sum = total;
+    w.envmap_width = (unsigned)width;
+    w.envmap_height = (unsigned)height;
+    w.ambient_light_type = 2;
+    return B2PT_OK;
+}
+
+b2pt_render_data* b2pt_renderer_render_data(b2pt_renderer* r) { return r ? &r->loop.rd : nullptr; }
+
+int b2pt_renderer_set_host_seed(b2pt_renderer* r, unsigned int seed)
+{
+    if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    r->loop.host_rng = make_rng(seed);
+    return B2PT_OK;
+}
+
+int b2pt_renderer_set_counters(b2pt_renderer* r, int enabled)
+{
+    if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    r->counters = enabled ? 1 : 0;
+    r->kernels_stale = true;
+    return B2PT_OK;
+}
+
+int b2pt_renderer_set_profile_passes(b2pt_renderer* r, int enabled)
+{
+    if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    r->profile_passes = enabled != 0;
+    return B2PT_OK;
+}
+
+/* GPURenderer::reset (sample_number = 0, need_to_reset = true) */
+int b2pt_renderer_reset(b2pt_renderer* r)
+{
+    if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    r->loop.rd.render_settings.need_to_reset = 1;
+    r->loop.rd.render_settings.sample_number = 0;
+    return B2PT_OK;
+}
+
+int b2pt_renderer_render(b2pt_renderer* r, int samples)
+{
+    if (!r || samples < 0) { b2_set_error("invalid argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    if (!r->has_scene) { b2_set_error("b2pt_renderer_render: no scene set"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
+    B2_TRY(resolve_kernels(r));
+    r->loop.camera.sensor_width = r->width;
+    r->loop.camera.sensor_height = r->height;
+
+    int rc = B2PT_OK;
+    auto launch = [&](B2Pass pass) {
+        if (rc != B2PT_OK)
+            return;
+        if (pass == B2_PASS_CAMERA_RAYS)
+        {
+            /* pre_render_update: clear still_one_ray_active and the converged-pixel counter (CPURenderer.cpp:574-584) */
+            rc = b2pt_memset(r->ctx, r->d_status, 0, 16, r->stream);
+            if (rc != B2PT_OK)
+                return;
+        }
+        b2pt_kernel* k = r->kernels[pass];
+        if (!k)
+        {
+            b2_set_error("pass %d has no kernel in variant %s", (int)pass, r->variant.c_str());
+            rc = B2PT_ERR_NO_VARIANT;
+            return;
+        }
+        void* args[1] = { &r->loop.rd };
+        rc = b2pt_kernel_launch(k, 8, 8, r->width, r->height, args, r->stream);
+        r->pass_launches[pass]++;
+        if (rc == B2PT_OK && r->profile_passes)
+        {
+            float ms = 0.0f;
+            rc = b2pt_kernel_last_ms(k, &ms);
+            r->pass_ms[pass] += ms;
+        }
+    };
+
+    B2_TRY(b2pt_event_record(r->ctx, r->ev_start, r->stream));
+    for (int s = 0; s < samples && rc == B2PT_OK; s++)
+        r->loop.render_one_sample(launch);
+    B2_TRY(rc);
+    B2_TRY(b2pt_event_record(r->ctx, r->ev_stop, r->stream));
+    r->timed = true;
+    return B2PT_OK;
+}
+
+int b2pt_renderer_synchronize(b2pt_renderer* r)
+{
+    if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    return b2pt_stream_synchronize(r->ctx, r->stream);
+}
+
+int b2pt_renderer_last_render_ms(b2pt_renderer* r, float* out_ms)
+{
+    if (!r || !out_ms) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    *out_ms = 0.0f;
+    if (!r->timed)
+        return B2PT_OK;
+    B2_TRY(b2pt_event_synchronize(r->ctx, r->ev_stop));
+    return b2pt_event_elapsed_ms(r->ctx, r->ev_start, r->ev_stop, out_ms);
+}
+
+int b2pt_renderer_pass_ms(b2pt_renderer* r, int pass, float* out_ms, uint64_t* out_launches)
+{
+    if (!r || pass < 0 || pass >= B2_PASS_COUNT) { b2_set_error("invalid argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    if (out_ms) *out_ms = (float)r->pass_ms[pass];
+    if (out_launches) *out_launches = r->pass_launches[pass];
+    return B2PT_OK;
+}
+
+int b2pt_renderer_download_framebuffer(b2pt_renderer* r, float* out_rgb)
+{
+    if (!r || !out_rgb) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_memcpy_d2h(r->ctx, out_rgb, r->loop.rd.buffers.accumulated_ray_colors, r->pixels() * 12, r->stream));
+    return b2pt_stream_synchronize(r->ctx, r->stream);
+}
+
+int b2pt_renderer_download_gbuffer(b2pt_renderer* r, int* out_prim, float* out_position, uint32_t* out_geo, uint32_t* out_shade, uint32_t* out_material27)
+{
+    if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    const b2pt_gbuffer& g = r->loop.rd.g_buffer;
+    const size_t n = r->pixels();
+    B2_TRY(b2pt_stream_synchronize(r->ctx, r->stream));
+    if (out_prim) B2_TRY(b2pt_memcpy_d2h(r->ctx, out_prim, g.first_hit_prim_index, n * 4, nullptr));
+    if (out_position) B2_TRY(b2pt_memcpy_d2h(r->ctx, out_position, g.primary_hit_position, n * 12, nullptr));
+    if (out_geo) B2_TRY(b2pt_memcpy_d2h(r->ctx, out_geo, g.geometric_normals, n * 4, nullptr));
+    if (out_shade) B2_TRY(b2pt_memcpy_d2h(r->ctx, out_shade, g.shading_normals, n * 4, nullptr));
+    if (out_material27) B2_TRY(b2pt_memcpy_d2h(r->ctx, out_material27, g.materials, n * 108, nullptr));
+    return B2PT_OK;
+}
+
+int b2pt_renderer_download_reservoirs(b2pt_renderer* r, int which, uint32_t* out_words9)
+{
+    if (!r || !out_words9 || which < 0 || which > 3) { b2_set_error("invalid argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_stream_synchronize(r->ctx, r->stream));
+    const void* src = which < 3 ? r->d_reservoirs[which] : r->loop.rd.render_settings.restir_di_settings.restir_output_reservoirs;
+    return b2pt_memcpy_d2h(r->ctx, out_words9, src, r->pixels() * 36, nullptr);
+}
+
+int b2pt_renderer_scene_info(b2pt_renderer* r, b2pt_bvh_stats_t* out_bvh, int* out_triangles, int* out_emissive_triangles)
+{
+    if (!r || !r->has_scene) { b2_set_error("no scene"); return B2PT_ERR_INVALID_ARGUMENT; }
+    if (out_bvh) B2_TRY(b2pt_bvh_stats(r->bvh, out_bvh));
+    if (out_triangles) *out_triangles = (int)r->scene.blob.n_triangles();
+    if (out_emissive_triangles) *out_emissive_triangles = (int)r->scene.emissive_triangles.size();
+    return B2PT_OK;
+}
+
+int b2pt_renderer_download_derived(b2pt_renderer* r, uint32_t* out_packed33, float* out_areas, int* out_emissive, float* out_probas, int* out_alias)
+{
+    if (!r || !r->has_scene) { b2_set_error("no scene"); return B2PT_ERR_INVALID_ARGUMENT; }
+    const B2HostScene& s = r->scene;
+    if (out_packed33) std::memcpy(out_packed33, s.packed_materials.data(), s.packed_materials.size() * sizeof(B2PackedTexturedMaterial));
+    if (out_areas) std::memcpy(out_areas, s.triangle_areas.data(), s.triangle_areas.size() * 4);
+    if (out_emissive) std::memcpy(out_emissive, s.emissive_triangles.data(), s.emissive_triangles.size() * 4);
+    if (out_probas) std::memcpy(out_probas, s.power_alias_probas.data(), s.power_alias_probas.size() * 4);
+    if (out_alias) std::memcpy(out_alias, s.power_alias_alias.data(), s.power_alias_alias.size() * 4);
+    return B2PT_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,197 @@
+/*
+ * b2pt.h -- C ABI of libb2pt.so, the B200-native device layer of the path tracer.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) The DEVICE LAYER: what a maintainer binds in place of src/HIPRT-Orochi (+ the JIT half of src/Compiler) of
+ *      the reference. Each entry cites the reference interface it replaces. Plain pointers and sizes only; every
+ *      call returns 0 on success or a B2PT_ERR_* code, with a thread-local message in b2pt_last_error_string()
+ *      (the reference wraps every oro / hiprt call in OROCHI_CHECK_ERROR / HIPRT_CHECK_ERROR -> log + exit,
+ *      src/HIPRT-Orochi/HIPRTOrochiUtils.h:15-17; INTEGRATION.md shows the equivalent B2PT_CHECK macro).
+ *
+ *  (2) The HEADLESS RENDERER: a host-side mirror of the reference's GPURenderer frame / sample loop
+ *      (set_scene / set_camera / set_envmap / render / get_framebuffer, src/Renderer/GPURenderer.h:61-346) with the
+ *      CPURenderer's pass order and host RNG draws (src/Renderer/CPURenderer.cpp:534-604), driving group (1).
+ *      tests/ and bench.py go through this group with HOST buffers.
+ *
+ * There is no CPU fallback anywhere behind this header: without a CUDA device b2pt_ctx_create fails.
+ */
+#ifndef B2PT_H
+#define B2PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "b2pt_render_data.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2PT_OK 0
+#define B2PT_ERR_INVALID_ARGUMENT 1
+#define B2PT_ERR_CUDA 2
+#define B2PT_ERR_NO_DEVICE 3
+#define B2PT_ERR_NO_VARIANT 4 /* the requested macro combination is not among the precompiled variants */
+#define B2PT_ERR_UNSUPPORTED_SCENE 5
+#define B2PT_ERR_IO 6
+
+typedef struct b2pt_ctx b2pt_ctx;
+typedef struct b2pt_bvh b2pt_bvh;
+typedef struct b2pt_kernel b2pt_kernel;
+typedef struct b2pt_renderer b2pt_renderer;
+typedef void* b2pt_stream; /* cudaStream_t */
+typedef void* b2pt_event;  /* cudaEvent_t */
+
+const char* b2pt_last_error_string(void);
+const char* b2pt_version_string(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (1) device layer
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Context. Replaces HIPRTOrochiCtx::init (oroInitialize / oroInit / oroDeviceGet / oroCtxCreate /
+ * hiprtCreateContext, src/HIPRT-Orochi/HIPRTOrochiCtx.h:40-106) and oroCtxSetCurrent
+ * (src/Renderer/GPURenderer.cpp:245,444,854). One context per GPU. */
+typedef struct
+{
+    char name[256];
+    int sm_count;
+    int compute_major, compute_minor;
+    size_t total_memory_bytes;
+    size_t l2_bytes;
+    size_t shared_memory_per_block_optin;
+    int clock_khz;
+} b2pt_device_props_t;
+
+int b2pt_ctx_create(int device_index, b2pt_ctx** out_ctx);
+int b2pt_ctx_destroy(b2pt_ctx* ctx);
+int b2pt_ctx_make_current(b2pt_ctx* ctx);
+int b2pt_ctx_device_props(b2pt_ctx* ctx, b2pt_device_props_t* out);
+
+/* Memory. Replaces OrochiBuffer<T> (resize / free / upload_data / download_data / memset_whole_buffer /
+ * memcpy_from / resize_host_pinned_mem over oroMalloc / oroFree / oroMemcpy* / oroHostMalloc,
+ * src/HIPRT-Orochi/OrochiBuffer.h:20-122,175-360). Device pointers are plain CUDA device pointers and are stored
+ * verbatim in HIPRTRenderData; pointer identity is preserved (the host compares them, ReSTIRDIRenderPass.cpp:597). */
+int b2pt_malloc(b2pt_ctx* ctx, size_t bytes, void** out_device_ptr);
+int b2pt_free(b2pt_ctx* ctx, void* device_ptr);
+int b2pt_memcpy_h2d(b2pt_ctx* ctx, void* dst_device, const void* src_host, size_t bytes, b2pt_stream stream);
+int b2pt_memcpy_d2h(b2pt_ctx* ctx, void* dst_host, const void* src_device, size_t bytes, b2pt_stream stream);
+int b2pt_memcpy_d2d(b2pt_ctx* ctx, void* dst_device, const void* src_device, size_t bytes, b2pt_stream stream);
+int b2pt_memset(b2pt_ctx* ctx, void* device_ptr, int byte_value, size_t bytes, b2pt_stream stream);
+int b2pt_host_alloc_pinned(b2pt_ctx* ctx, size_t bytes, void** out_host_ptr);
+int b2pt_host_free_pinned(b2pt_ctx* ctx, void* host_ptr);
+
+/* Streams / events. Replaces oroStreamCreate / oroStreamSynchronize / oroEventCreate / Record / Synchronize /
+ * ElapsedTime (src/Renderer/GPURenderer.cpp:66,426; src/Compiler/GPUKernel.cpp:190-201,228-240). */
+int b2pt_stream_create(b2pt_ctx* ctx, b2pt_stream* out_stream);
+int b2pt_stream_destroy(b2pt_ctx* ctx, b2pt_stream stream);
+int b2pt_stream_synchronize(b2pt_ctx* ctx, b2pt_stream stream);
+int b2pt_event_create(b2pt_ctx* ctx, b2pt_event* out_event);
+int b2pt_event_destroy(b2pt_ctx* ctx, b2pt_event event);
+int b2pt_event_record(b2pt_ctx* ctx, b2pt_event event, b2pt_stream stream);
+int b2pt_event_synchronize(b2pt_ctx* ctx, b2pt_event event);
+int b2pt_event_elapsed_ms(b2pt_ctx* ctx, b2pt_event start, b2pt_event stop, float* out_ms);
+
+/* LUT "textures". Replaces OrochiTexture / OrochiTexture3D + get_device_texture()
+ * (src/HIPRT-Orochi/OrochiTexture.cpp, OrochiTexture3D.cpp; src/Renderer/GPURenderer.cpp:116-171). The returned
+ * handle (a device pointer to a b2pt_lut descriptor) goes into the BRDFsData fields of HIPRTRenderData. */
+int b2pt_lut_create(b2pt_ctx* ctx, const float* texels, int width, int height, int depth, int channels, void** out_handle);
+int b2pt_lut_destroy(b2pt_ctx* ctx, void* handle);
+
+/* Geometry / BVH. Replaces HIPRTGeometry::upload_triangle_indices / upload_vertices_positions / build_bvh
+ * (src/HIPRT-Orochi/HIPRTScene.h:37-72,87-150). The BVH is built on the HOST (binned SAH -> compressed 8-wide) and
+ * uploaded; `b2pt_bvh_device_handle` is what goes into HIPRTRenderData::GPU_BVH. `flags` is reserved (0). */
+typedef struct
+{
+    uint64_t node_count;
+    uint64_t triangle_count;
+    uint64_t bytes;
+    int max_depth;
+    double sah_cost;
+    double build_seconds;
+} b2pt_bvh_stats_t;
+
+int b2pt_bvh_build(b2pt_ctx* ctx, const int* triangle_indices, int triangle_count, const float* vertex_positions, int vertex_count,
+                   uint32_t flags, b2pt_stream stream, b2pt_bvh** out_bvh);
+void* b2pt_bvh_device_handle(b2pt_bvh* bvh);
+int b2pt_bvh_stats(b2pt_bvh* bvh, b2pt_bvh_stats_t* out);
+int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
+
+/* Kernels. Replaces GPUKernel::compile -> hiprtBuildTraceKernels (src/Compiler/GPUKernel.cpp:72-83,
+ * src/HIPRT-Orochi/HIPRTOrochiUtils.cpp:118-164) by a lookup in a table of PRECOMPILED sm_100a variants, and
+ * GPUKernel::launch_asynchronous -> oroModuleLaunchKernel (src/Compiler/GPUKernel.cpp:151-165).
+ * Entry names served: "CameraRays", "MegaKernel", "ReSTIR_DI_InitialCandidates", "ReSTIR_DI_TemporalReuse",
+ * "ReSTIR_DI_SpatialReuse", "ReSTIR_DI_SpatiotemporalReuse" (MegaKernelRenderPass.cpp:20,
+ * FillGBufferRenderPass.cpp:23, ReSTIRDIRenderPass.cpp:21-29).
+ * Options are the reference's macro names with integer values, e.g. {"DirectLightSamplingStrategy", 3}; macros not
+ * listed take the reference's defaults. Two extra options select the codegen flavour:
+ *   {"B2PT_PRECISE", 1}  (default) IEEE fp32 without FMA contraction: the flavour parity is asserted on;
+ *   {"B2PT_PRECISE", 0}  FMA contraction + fast intrinsics.
+ *   {"B2PT_COUNTERS", 1} traversal-step counters (rays / nodes / triangles) accumulated into b2pt_counters_read. */
+typedef struct
+{
+    const char* name;
+    int value;
+} b2pt_option;
+
+int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* options, int option_count, b2pt_kernel** out_kernel);
+/* args[0] must point to a host HIPRTRenderData / b2pt_render_data (2784 bytes, passed by value to the kernel).
+ * block_x / block_y are accepted for interface compatibility; the B200 kernels choose their own thread->pixel map. */
+int b2pt_kernel_launch(b2pt_kernel* kernel, int block_x, int block_y, int width, int height, void** args, b2pt_stream stream);
+int b2pt_kernel_last_ms(b2pt_kernel* kernel, float* out_ms);
+int b2pt_kernel_launch_count(b2pt_kernel* kernel, uint64_t* out_count);
+
+typedef struct
+{
+    uint64_t rays;      /* closest-hit + any-hit traversals started */
+    uint64_t nodes;     /* wide-BVH nodes fetched */
+    uint64_t triangles; /* triangles tested */
+} b2pt_counters_t;
+int b2pt_counters_reset(b2pt_ctx* ctx);
+int b2pt_counters_read(b2pt_ctx* ctx, b2pt_counters_t* out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (2) headless renderer (host mirror of GPURenderer, CPURenderer pass order)
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* variant: "c1" | "c2" | "c3" | "c4" (see b2_kernels_body.h); precise: 1 = parity flavour, 0 = fast flavour */
+int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* variant, int precise, b2pt_renderer** out_renderer);
+int b2pt_renderer_destroy(b2pt_renderer* renderer);
+/* Scene from a B2SCENE1 file (include/b2pt_scene_blob.h) or from host arrays laid out like the reference's Scene. */
+int b2pt_renderer_set_scene_file(b2pt_renderer* renderer, const char* scene_blob_path);
+int b2pt_renderer_set_scene_arrays(b2pt_renderer* renderer, const float* positions, const float* normals, const float* texcoords,
+                                   const uint8_t* has_normals, int vertex_count, const int* indices, const int* material_indices,
+                                   int triangle_count, const float* materials, int material_count, const float* camera52);
+int b2pt_renderer_set_luts_file(b2pt_renderer* renderer, const char* lut_blob_path);
+/* RGBA fp32 texels, row 0 first (what Image32Bit holds after read_image_hdr(path, 4, flipY=true)) */
+int b2pt_renderer_set_envmap(b2pt_renderer* renderer, const float* rgba_texels, int width, int height);
+/* Host copy of the render data; edit settings (nb_bounces, restir_di_settings, ...) before rendering. */
+b2pt_render_data* b2pt_renderer_render_data(b2pt_renderer* renderer);
+int b2pt_renderer_set_host_seed(b2pt_renderer* renderer, unsigned int seed);
+int b2pt_renderer_set_counters(b2pt_renderer* renderer, int enabled);
+/* When enabled, every pass launch is followed by an event wait and its time is added to b2pt_renderer_pass_ms
+ * (serialises host and device: for profiling runs only, never for the timed bench region). */
+int b2pt_renderer_set_profile_passes(b2pt_renderer* renderer, int enabled);
+int b2pt_renderer_reset(b2pt_renderer* renderer);
+/* Renders `samples` samples of every pixel (all passes), asynchronously on the renderer's stream. */
+int b2pt_renderer_render(b2pt_renderer* renderer, int samples);
+int b2pt_renderer_synchronize(b2pt_renderer* renderer);
+/* Device time of the last b2pt_renderer_render call (CUDA events on the renderer's stream), after synchronize. */
+int b2pt_renderer_last_render_ms(b2pt_renderer* renderer, float* out_ms);
+int b2pt_renderer_pass_ms(b2pt_renderer* renderer, int pass, float* out_ms, uint64_t* out_launches);
+/* Result buffers -> host. framebuffer: width*height*3 floats (sum of samples, like CPURenderer::get_framebuffer). */
+int b2pt_renderer_download_framebuffer(b2pt_renderer* renderer, float* out_rgb);
+int b2pt_renderer_download_gbuffer(b2pt_renderer* renderer, int* out_prim, float* out_position, uint32_t* out_geometric_normal,
+                                   uint32_t* out_shading_normal, uint32_t* out_material27);
+int b2pt_renderer_download_reservoirs(b2pt_renderer* renderer, int which, uint32_t* out_words9);
+int b2pt_renderer_scene_info(b2pt_renderer* renderer, b2pt_bvh_stats_t* out_bvh, int* out_triangles, int* out_emissive_triangles);
+/* Derived host arrays, for bit-exact comparison with the oracle (packed materials: 33 words each). */
+int b2pt_renderer_download_derived(b2pt_renderer* renderer, uint32_t* out_packed_materials33, float* out_triangle_areas,
+                                   int* out_emissive_triangles, float* out_alias_probas, int* out_alias_alias);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

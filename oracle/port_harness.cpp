@@ -109,6 +109,7 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
         ctx.rd = &rd;
         ctx.bvh = bvh;
         ctx.stack = stack;
+        ctx.stack_stride = 1;
         ctx.counters = nullptr;
 #pragma omp for schedule(dynamic)
         for (int y = a.win_y0; y < a.win_y1; y++)

@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz from the REFERENCE oracle (oracle/_ref, i.e. the reference's own CPU kernels compiled
+in place). Only runs where /root/reference was available to build oracle/_ref; the fixtures are committed."""
+import json
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+
+CASES = [
+    # name, variant, scene, w, h, spp, bounces, extra args
+    ("c1_128x72", "c1", "cornell_pbr_16x9", 128, 72, 1, 3, []),
+    ("c1_64x64_4spp", "c1", "cornell_pbr_1x1", 64, 64, 4, 5, []),
+    ("c2_128x72", "c2", "cornell_pbr_16x9", 128, 72, 2, 8, []),
+    ("c3_128x72", "c3", "cornell_pbr_16x9", 128, 72, 2, 8, []),
+    ("c4_96x54_fused", "c4", "cornell_pbr_16x9", 96, 54, 3, 4, []),
+    ("c4_96x54_split", "c4", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused"]),
+]
+
+
+def run_case(name, variant, scene, w, h, spp, bounces, extra):
+    exe = ROOT / "oracle" / "_ref" / f"ref_render_{variant}"
+    if not exe.exists():
+        print(f"skip {name}: {exe} not built")
+        return
+    with tempfile.TemporaryDirectory() as tmp:
+        prefix = str(Path(tmp) / "d_")
+        out = subprocess.run([str(exe), "--scene", str(ROOT / "data" / f"{scene}.b2scene"), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
+                              "--width", str(w), "--height", str(h), "--spp", str(spp), "--bounces", str(bounces), "--dump", prefix, *extra],
+                             check=True, capture_output=True, text=True)
+        meta = json.loads(out.stdout.strip().splitlines()[-1])
+        load = lambda n, dt: np.fromfile(prefix + n + ".bin", dt)
+        mat = load("gbuffer_material", np.uint32).reshape(-1, 27).copy()
+        mat[:, 0] &= 0xFF  # struct padding bytes are indeterminate in the reference
+        arrays = dict(
+            gbuffer_prim=load("gbuffer_prim", np.int32), gbuffer_position=load("gbuffer_position", np.float32),
+            gbuffer_geometric_normal=load("gbuffer_geometric_normal", np.uint32) & 0xFFFFFF,
+            gbuffer_shading_normal=load("gbuffer_shading_normal", np.uint32) & 0xFFFFFF,
+            gbuffer_material=mat, framebuffer=load("framebuffer", np.float32),
+            packed_materials=load("packed_materials", np.uint32), triangle_areas=load("triangle_areas", np.float32),
+            emissive_prims=load("emissive_prims", np.int32), power_alias=load("power_alias", np.int32), power_probas=load("power_probas", np.float32),
+            meta=np.frombuffer(json.dumps(dict(meta, name=name, scene=scene, extra=extra)).encode(), np.uint8))
+        np.savez_compressed(GOLD / f"{name}.npz", **arrays)
+        print(f"wrote {name}.npz ({(GOLD / (name + '.npz')).stat().st_size} bytes)")
+
+
+if __name__ == "__main__":
+    GOLD.mkdir(parents=True, exist_ok=True)
+    only = set(sys.argv[1:])
+    for case in CASES:
+        if not only or case[0] in only:
+            run_case(*case)
