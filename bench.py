@@ -1,0 +1,378 @@
+#!/usr/bin/env python3
+"""bench.py -- Mpaths/s of the per-pixel path-tracing hot path on N B200s (driver contract: one JSON line on rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the whole hot path (CameraRays -> [ReSTIR DI passes] -> MegaKernel, `spp` samples per pixel)
+over one full frame of the workload. The default workload is BASELINE.json configs[1]: Cornell box at 1920x1080,
+principled BSDF, 16 spp, NEE + BSDF MIS with power-proportional light sampling (variant "c2"), 8 bounces.
+
+ value      : W*H*spp*steps / device time (CUDA events on the renderer's stream, max over ranks), scene resident in HBM
+ e2e        : same metric through the C ABI with HOST buffers: per step the scene arrays are re-uploaded from pinned
+              host memory (geometry, materials, BVH blob: what GPURenderer::set_scene hands to the device layer), the
+              frame is rendered, and the fp32 framebuffer is read back to the host -- all inside the timed region
+ roofline   : MegaKernel's algorithmic bytes (B_path from measured traversal steps) / its CUDA-event time
+ cpu_baseline: the reference's own CPU path (oracle/_ref, compiled from /root/reference) on this box's host cores, on
+              a bounded pixel window of the same workload
+
+Multi-GPU (N > 1): the frame is partitioned into interleaved 64-row pixel bands (rank = band % N), scene replicated,
+no data-path collective inside a sample; the framebuffer bands are all-gathered with NCCL at the end of every step
+(inside the timed region). Total work is fixed => "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC = "Mpaths/s (pixels*spp/s) at 1080p"
+WORKLOADS = {
+    # name: variant, scene blob, width, height, spp per step, bounces, description
+    "c1": dict(variant="c1", scene="cornell_pbr_1x1", width=512, height=512, spp=1, bounces=3,
+               desc="Cornell 512x512 1spp 3 bounces Lambertian + uniform one-light NEE (BASELINE configs[0])"),
+    "c2": dict(variant="c2", scene="cornell_pbr_16x9", width=1920, height=1080, spp=16, bounces=8,
+               desc="Cornell 1080p principled BSDF 16spp NEE+BSDF MIS power-proportional light sampling (BASELINE configs[1])"),
+    "c3": dict(variant="c3", scene="cornell_pbr_16x9", width=1920, height=1080, spp=16, bounces=8,
+               desc="Cornell 1080p principled BSDF 16spp RIS 4+1 power (shipped defaults)"),
+    "c4": dict(variant="c4", scene="cornell_pbr_16x9", width=1920, height=1080, spp=16, bounces=8,
+               desc="Cornell 1080p principled BSDF ReSTIR DI fused spatiotemporal, 16 frames x 1spp"),
+}
+
+# bytes per traversal step and per shaded vertex / pixel
+S_NODE, S_TRI, S_HIT, S_LIGHT, S_PX = 80, 48, 164, 76, 288
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, sm_max, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                sm_max.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(sm_max)), power_w_max=float(max(power)), samples=len(sm), reasons=sorted(reasons))
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "fallback"
+
+
+def pick_workload(name, b2pt, ctx):
+    """The workload BASELINE.json's metric is quoted on is c2; fall back (loudly) only if that variant is not built."""
+    order = [name] if name else ["c2", "c1"]
+    for n in order:
+        w = WORKLOADS[n]
+        try:
+            r = b2pt.Renderer(ctx, 16, 16, w["variant"], precise=False)
+            r.set_scene_file(ROOT / "data" / f"{w['scene']}.b2scene")
+            r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
+            r.render(1)
+            r.close()
+            return n, w
+        except b2pt.B2ptError as e:
+            print(f"bench: workload {n} unavailable ({e})", file=sys.stderr)
+    raise SystemExit("bench: no workload can run")
+
+
+def reference_arm(a):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = a.workload or "c2"
+    w = dict(WORKLOADS[name])
+    exe = ROOT / "oracle" / "_ref" / f"ref_render_{w['variant']}"
+    if not exe.exists():
+        entry.build_oracles()
+    entry.ensure_data()
+    cores = host_cores()
+    # bounded sample: a centred window of the frame, 1 spp per step, sized for ~1-3 s per step
+    win_w, win_h = min(w["width"], 480), min(w["height"], 270)
+    x0, y0 = (w["width"] - win_w) // 2, (w["height"] - win_h) // 2
+    spp = 1
+    times = []
+    for i in range(a.warmup + a.steps):
+        out = subprocess.run([str(exe), "--scene", str(ROOT / "data" / f"{w['scene']}.b2scene"), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
+                              "--width", str(w["width"]), "--height", str(w["height"]), "--spp", str(spp), "--bounces", str(w["bounces"]),
+                              "--threads", str(cores), "--window", str(x0), str(y0), str(x0 + win_w), str(y0 + win_h)],
+                             check=True, capture_output=True, text=True)
+        meta = json.loads(out.stdout.strip().splitlines()[-1])
+        if i >= a.warmup:
+            times.append(meta["render_seconds"])
+    total = sum(times)
+    value = win_w * win_h * spp * len(times) / total / 1e6
+    sample = f"{win_w}x{win_h} centre window of the {w['width']}x{w['height']} frame, {spp} spp per step, {w['bounces']} bounces"
+    line = dict(metric=METRIC, value=value, unit="Mpaths/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=1e3 * total / len(times),
+                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=w["desc"], variant=w["variant"], width=w["width"], height=w["height"], spp=w["spp"], bounces=w["bounces"]),
+                cpu_baseline=dict(value=value, unit="Mpaths/s", cores=cores, kind="reference", sample=sample),
+                e2e=dict(value=value, unit="Mpaths/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def cpu_baseline(w, seconds_budget=20.0):
+    exe = ROOT / "oracle" / "_ref" / f"ref_render_{w['variant']}"
+    kind = "reference"
+    extra = []
+    if not exe.exists():
+        exe = ROOT / "oracle" / "_port" / "port_render"
+        kind = "port"
+        extra = ["--variant", w["variant"]]
+    if not exe.exists():
+        return dict(value=None, unit="Mpaths/s", cores=0, kind="unavailable", sample="oracle binaries not built")
+    cores = host_cores()
+    win_w, win_h = min(w["width"], 480), min(w["height"], 270)
+    x0, y0 = (w["width"] - win_w) // 2, (w["height"] - win_h) // 2
+    spp, total_s, total_paths = 1, 0.0, 0
+    t_start = time.time()
+    while True:
+        out = subprocess.run([str(exe), *extra, "--scene", str(ROOT / "data" / f"{w['scene']}.b2scene"), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
+                              "--width", str(w["width"]), "--height", str(w["height"]), "--spp", str(spp), "--bounces", str(w["bounces"]),
+                              "--threads", str(cores), "--window", str(x0), str(y0), str(x0 + win_w), str(y0 + win_h)],
+                             check=True, capture_output=True, text=True)
+        meta = json.loads(out.stdout.strip().splitlines()[-1])
+        total_s += meta["render_seconds"]
+        total_paths += win_w * win_h * spp
+        if time.time() - t_start > seconds_budget * 0.5 or total_s > seconds_budget:
+            break
+        spp = min(spp * 2, 16)
+    return dict(value=total_paths / total_s / 1e6, unit="Mpaths/s", cores=cores, kind=kind,
+                sample=f"{win_w}x{win_h} centre window of the {w['width']}x{w['height']} frame, {total_paths // (win_w * win_h)} spp total, {w['bounces']} bounces, {total_s:.1f} s of CPU render time")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS.keys()])
+    ap.add_argument("--precise", type=int, default=0, help="1 = time the parity flavour instead of the fast flavour")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spp", type=int, default=None)
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
+
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU reference arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    entry.ensure_data()
+    b2pt = entry.load_b2pt()
+    ctx = b2pt.Context(local_rank)
+    name, w = pick_workload(a.workload, b2pt, ctx)
+    w = dict(w)
+    if a.spp:
+        w["spp"] = a.spp
+    W, H, spp = w["width"], w["height"], w["spp"]
+
+    r = b2pt.Renderer(ctx, W, H, w["variant"], precise=bool(a.precise))
+    r.set_scene_file(ROOT / "data" / f"{w['scene']}.b2scene")
+    r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
+    r.set(nb_bounces=w["bounces"])
+    if world > 1:
+        r.set_partition(rank, world)
+    info = r.scene_info()
+
+    fb_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    fb_np = fb_host.numpy()
+    gather = None
+    if world > 1:
+        gather = r.make_gather(torch, dist)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(e2e):
+        r.reset()
+        r.set_host_seed(42)
+        if e2e:
+            r.reupload_scene()
+        r.render(spp, sync=False)
+        if gather is not None:
+            gather()
+        if e2e:
+            r.framebuffer(out=fb_np)
+
+    # ---- device-timed region (inputs resident in HBM) -------------------------------------------------------
+    for _ in range(a.warmup):
+        step(False)
+        r.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    launches_before = sum(v["launches"] for v in r.pass_times().values())
+    for _ in range(a.steps):
+        step(False)
+        r.synchronize()
+        dev_ms += r.last_render_ms()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = sum(v["launches"] for v in r.pass_times().values()) - launches_before
+    clocks = sampler.stop() if rank == 0 else None
+    # the renderer's own CUDA events bracket every step on its stream; the wall clock around the barrier pair is an upper bound
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+
+    # ---- end to end through the C ABI with host buffers -----------------------------------------------------
+    for _ in range(2):
+        step(True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step(True)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = r.scene_upload_bytes()
+    d2h = W * H * 12
+
+    paths_per_step = W * H * spp
+    value = paths_per_step * a.steps / (dev_ms * 1e-3) / 1e6
+    e2e_value = paths_per_step * a.steps / (e2e_ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (MegaKernel), rank 0, outside the timed region ---------------------------
+    roofline = None
+    extra = {}
+    if rank == 0:
+        r.reset()
+        r.set_host_seed(42)
+        r.set_profile_passes(True)
+        before = r.pass_times()
+        r.render(spp)
+        after = r.pass_times()
+        r.set_profile_passes(False)
+        pass_ms = {k: after[k]["ms"] - before.get(k, dict(ms=0.0))["ms"] for k in after}
+        n_launch = {k: after[k]["launches"] - before.get(k, dict(launches=0))["launches"] for k in after}
+        r.reset()
+        r.set_host_seed(42)
+        r.set_counters(True)
+        ctx.counters_reset()
+        r.render(spp)
+        c = ctx.counters_read()
+        r.set_counters(False)
+        mk_ms = pass_ms.get("MegaKernel", 0.0) / max(1, n_launch.get("MegaKernel", 1))
+        own = r.owned_pixels() if world > 1 else W * H
+        rays = c["rays"] / spp   # per launch (one launch = one sample of every pixel)
+        # B_path: traversal bytes + per-vertex hit reconstruction + light candidates + per-pixel G-buffer / framebuffer traffic.
+        # CameraRays' primary rays are part of `rays` but belong to its own launch: subtract one ray per pixel.
+        mk_rays = max(rays - own, 0.0)
+        frac_mk = mk_rays / max(rays, 1.0)
+        trav_bytes = frac_mk * (c["nodes"] * S_NODE + c["triangles"] * S_TRI) / spp
+        vertices = c.get("vertices", 0) / spp if c.get("vertices") else mk_rays / 3.0
+        lights = c.get("light_samples", 0) / spp if c.get("light_samples") else vertices
+        algo_bytes = trav_bytes + vertices * S_HIT + lights * S_LIGHT + own * S_PX
+        peak, which = measured_peak_gbs()
+        achieved = algo_bytes / (mk_ms * 1e-3) / 1e9 if mk_ms > 0 else 0.0
+        roofline = dict(bound="hbm", kernel="MegaKernel", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                        peak_source=which, algorithmic_bytes_per_launch=algo_bytes, launch_ms=mk_ms,
+                        note="Cornell (BVH+triangles < 1 MB) is L2-resident: issue rate, not HBM, binds; see DESIGN.md")
+        extra = dict(pass_ms_per_step=pass_ms, mrays_per_s=c["rays"] / (sum(pass_ms.values()) * 1e-3) / 1e6 if pass_ms else None,
+                     traversal=dict(rays_per_path=c["rays"] / (own * spp), nodes_per_ray=c["nodes"] / max(c["rays"], 1), triangles_per_ray=c["triangles"] / max(c["rays"], 1)),
+                     scene=info, wall_ms_timed_region=wall_ms)
+
+    if rank == 0:
+        cpu = dict(value=None, unit="Mpaths/s", cores=0, kind="skipped", sample="--no-cpu-baseline") if a.no_cpu_baseline or world > 1 else cpu_baseline(w)
+        line = dict(metric=METRIC, value=value, unit="Mpaths/s", n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=dev_ms / a.steps,
+                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=w["desc"], variant=w["variant"], width=W, height=H, spp=spp, bounces=w["bounces"],
+                                flavour="precise" if a.precise else "fast", partition="interleaved 64-row bands, scene replicated" if world > 1 else "single GPU",
+                                l2_policy="every step re-renders from reset: G-buffer + framebuffer + aux (> 126 MB at 1080p) are rewritten between timed iterations"),
+                    clocks=clocks,
+                    e2e=dict(value=e2e_value, unit="Mpaths/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / a.steps),
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, gpaths_bounce_per_s=value * (w["bounces"] + 1) / 1000.0, **extra)
+        print(json.dumps(line))
+
+    r.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

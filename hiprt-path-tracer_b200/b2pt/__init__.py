@@ -102,6 +102,7 @@ def declared_symbols():
     """Names of every function include/b2pt.h declares (used by the CPU-side ABI test)."""
     import re
     text = (REPO_ROOT / "include" / "b2pt.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(b2pt_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -157,6 +158,16 @@ class Renderer:
         check(lib().b2pt_renderer_set_scene_arrays(self.handle, p(pos, C.c_float), p(nrm, C.c_float), p(uv, C.c_float), p(has, C.c_uint8),
                                                    len(has), p(idx, C.c_int), p(mid, C.c_int), len(mid), p(mats, C.c_float), len(mats),
                                                    p(cam52, C.c_float)))
+
+    def reupload_scene(self):
+        """Async host->device re-send of all scene arrays + BVH blob on the renderer's stream; returns bytes copied."""
+        n = C.c_uint64()
+        check(lib().b2pt_renderer_reupload_scene(self.handle, C.byref(n)))
+        self._scene_upload_bytes = n.value
+        return n.value
+
+    def scene_upload_bytes(self):
+        return getattr(self, "_scene_upload_bytes", 0)
 
     def set_luts_file(self, path):
         check(lib().b2pt_renderer_set_luts_file(self.handle, str(path).encode()))

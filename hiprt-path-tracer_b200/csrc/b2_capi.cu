@@ -51,6 +51,7 @@ struct b2pt_bvh
     B2Tri* tris = nullptr;
     B2BvhDevice* descriptor = nullptr;
     b2pt_bvh_stats_t stats;
+    B2BvhHost host; /* kept for b2pt_bvh_reupload */
 };
 
 struct b2pt_kernel
@@ -270,14 +271,15 @@ int b2pt_bvh_build(b2pt_ctx* ctx, const int* triangle_indices, int triangle_coun
         return B2PT_ERR_INVALID_ARGUMENT;
     }
     auto t0 = std::chrono::high_resolution_clock::now();
-    B2BvhHost host;
+    b2pt_bvh* bvh = new b2pt_bvh();
+    B2BvhHost& host = bvh->host;
     std::string error;
     if (!b2_build_cw8(triangle_indices, (size_t)triangle_count, vertex_positions, (size_t)vertex_count, host, error))
     {
+        delete bvh;
         b2_set_error("b2pt_bvh_build: %s", error.c_str());
         return B2PT_ERR_UNSUPPORTED_SCENE;
     }
-    b2pt_bvh* bvh = new b2pt_bvh();
     cudaStream_t s = (cudaStream_t)stream;
     if (!host.nodes.empty())
     {
@@ -304,6 +306,18 @@ int b2pt_bvh_build(b2pt_ctx* ctx, const int* triangle_indices, int triangle_coun
     bvh->stats.sah_cost = host.stats.sah_cost;
     bvh->stats.build_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
     *out_bvh = bvh;
+    return B2PT_OK;
+}
+
+int b2pt_bvh_reupload(b2pt_ctx*, b2pt_bvh* bvh, b2pt_stream stream, uint64_t* out_bytes)
+{
+    if (!bvh) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!bvh->host.nodes.empty())
+        B2_CUDA(cudaMemcpyAsync(bvh->nodes, bvh->host.nodes.data(), bvh->host.nodes.size() * sizeof(B2Node), cudaMemcpyHostToDevice, s));
+    if (!bvh->host.tris.empty())
+        B2_CUDA(cudaMemcpyAsync(bvh->tris, bvh->host.tris.data(), bvh->host.tris.size() * sizeof(B2Tri), cudaMemcpyHostToDevice, s));
+    if (out_bytes) *out_bytes = bvh->host.nodes.size() * sizeof(B2Node) + bvh->host.tris.size() * sizeof(B2Tri);
     return B2PT_OK;
 }
 

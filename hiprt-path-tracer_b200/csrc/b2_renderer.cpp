@@ -46,6 +46,8 @@ struct b2pt_renderer
     b2pt_event ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
     std::vector<void*> frame_allocs, scene_allocs, lut_handles, envmap_allocs;
+    struct Upload { void* device; const void* host; size_t bytes; };
+    std::vector<Upload> scene_uploads; /* (device, host, bytes) of every scene array, for b2pt_renderer_reupload_scene */
     b2pt_bvh* bvh = nullptr;
     b2pt_kernel* kernels[B2_PASS_COUNT] = {};
     double pass_ms[B2_PASS_COUNT] = {};
@@ -75,6 +77,8 @@ int upload(b2pt_renderer* r, std::vector<void*>& owner, const std::vector<T>& ho
     B2_TRY(b2pt_malloc(r->ctx, host.size() * sizeof(T), &d));
     owner.push_back(d);
     *out = reinterpret_cast<T*>(d);
+    if (&owner == &r->scene_allocs)
+        r->scene_uploads.push_back({ d, host.data(), host.size() * sizeof(T) });
     return b2pt_memcpy_h2d(r->ctx, d, host.data(), host.size() * sizeof(T), nullptr);
 }
 
@@ -142,6 +146,7 @@ int resolve_kernels(b2pt_renderer* r)
 int upload_scene(b2pt_renderer* r)
 {
     free_all(r, r->scene_allocs);
+    r->scene_uploads.clear();
     if (r->bvh)
     {
         b2pt_bvh_destroy(r->ctx, r->bvh);
@@ -344,6 +349,25 @@ int b2pt_renderer_set_scene_arrays(b2pt_renderer* r, const float* positions, con
     s.materials.assign(materials, materials + (size_t)material_count * B2MAT_FLOAT_COUNT);
     std::memcpy(&s.camera, camera52, sizeof(B2SceneCamera));
     return upload_scene(r);
+}
+
+/* Re-sends every scene array (geometry, per-triangle data, material SoA, alias table, wide-BVH blob) from the host
+ * copies to their existing device allocations, asynchronously on the renderer's stream: the per-step host->device
+ * traffic of the end-to-end measurement (what GPURenderer::set_scene hands to the device layer, BVH build excluded). */
+int b2pt_renderer_reupload_scene(b2pt_renderer* r, uint64_t* out_bytes)
+{
+    if (!r || !r->has_scene) { b2_set_error("no scene"); return B2PT_ERR_INVALID_ARGUMENT; }
+    uint64_t total = 0;
+    for (const b2pt_renderer::Upload& u : r->scene_uploads)
+    {
+        B2_TRY(b2pt_memcpy_h2d(r->ctx, u.device, u.host, u.bytes, r->stream));
+        total += u.bytes;
+    }
+    uint64_t bvh_bytes = 0;
+    B2_TRY(b2pt_bvh_reupload(r->ctx, r->bvh, r->stream, &bvh_bytes));
+    total += bvh_bytes;
+    if (out_bytes) *out_bytes = total;
+    return B2PT_OK;
 }
 
 int b2pt_renderer_set_luts_file(b2pt_renderer* r, const char* lut_blob_path)

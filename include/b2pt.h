@@ -114,6 +114,9 @@ typedef struct
 
 int b2pt_bvh_build(b2pt_ctx* ctx, const int* triangle_indices, int triangle_count, const float* vertex_positions, int vertex_count,
                    uint32_t flags, b2pt_stream stream, b2pt_bvh** out_bvh);
+/* Re-sends the host-built node / triangle arrays to the existing device allocations (after a host-side refit, or to
+ * measure the upload): replaces the re-upload half of HIPRTGeometry::build_bvh on a geometry change. */
+int b2pt_bvh_reupload(b2pt_ctx* ctx, b2pt_bvh* bvh, b2pt_stream stream, uint64_t* out_bytes);
 void* b2pt_bvh_device_handle(b2pt_bvh* bvh);
 int b2pt_bvh_stats(b2pt_bvh* bvh, b2pt_bvh_stats_t* out);
 int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
@@ -163,6 +166,9 @@ int b2pt_renderer_set_scene_file(b2pt_renderer* renderer, const char* scene_blob
 int b2pt_renderer_set_scene_arrays(b2pt_renderer* renderer, const float* positions, const float* normals, const float* texcoords,
                                    const uint8_t* has_normals, int vertex_count, const int* indices, const int* material_indices,
                                    int triangle_count, const float* materials, int material_count, const float* camera52);
+/* Host -> device re-send of every scene array + the BVH blob on the renderer's stream (GPURenderer::set_scene's upload
+ * half, src/Renderer/GPURenderer.cpp:769-939, without the host BVH build). out_bytes: bytes copied. */
+int b2pt_renderer_reupload_scene(b2pt_renderer* renderer, uint64_t* out_bytes);
 int b2pt_renderer_set_luts_file(b2pt_renderer* renderer, const char* lut_blob_path);
 /* RGBA fp32 texels, row 0 first (what Image32Bit holds after read_image_hdr(path, 4, flipY=true)) */
 int b2pt_renderer_set_envmap(b2pt_renderer* renderer, const float* rgba_texels, int width, int height);

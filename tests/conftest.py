@@ -1,0 +1,88 @@
+"""Shared fixtures. `gpu` marks tests that need a CUDA device (run on the B200 box: `pytest -m gpu`); everything else
+runs on CPU (`pytest -m "not gpu"`): the oracles against the committed golden fixtures, host logic, and the C-ABI
+export check. The oracle (oracle/_ref = the reference's own CPU kernels compiled in place, oracle/_port = host build
+of the product's per-pixel headers) is TEST INFRASTRUCTURE: only tests/, smoke() and bench.py's cpu_baseline use it."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tools"))
+
+import __graft_entry__ as entry  # noqa: E402
+
+GOLDEN = ROOT / "tests" / "golden"
+DATA = ROOT / "data"
+REF_DIR = ROOT / "oracle" / "_ref"
+PORT_EXE = ROOT / "oracle" / "_port" / "port_render"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Library + oracles built (no GPU needed: nvcc cross-compiles)."""
+    lib = ROOT / "hiprt-path-tracer_b200" / "libb2pt.so"
+    if not lib.exists() or not PORT_EXE.exists() or not (REF_DIR / "ref_render_c1").exists():
+        entry.build()
+    entry.ensure_data()
+    return True
+
+
+@pytest.fixture(scope="session")
+def b2pt(built):
+    return entry.load_b2pt()
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx(b2pt):
+    ctx = b2pt.Context(0)  # raises if there is no device: there is no CPU fallback
+    yield ctx
+    ctx.close()
+
+
+def load_golden(name):
+    g = np.load(GOLDEN / f"{name}.npz")
+    meta = json.loads(bytes(g["meta"]).decode())
+    return g, meta
+
+
+def run_oracle(kind, variant, scene, width, height, spp, bounces, tmp_path, extra=(), threads=None):
+    """kind: 'ref' (reference sources compiled in place) or 'port' (host build of the product headers)."""
+    prefix = str(tmp_path / f"{kind}_")
+    if kind == "ref":
+        exe = REF_DIR / f"ref_render_{variant}"
+        cmd = [str(exe)]
+    else:
+        exe = PORT_EXE
+        cmd = [str(exe), "--variant", variant]
+    if not exe.exists():
+        pytest.skip(f"{exe} not built")
+    cmd += ["--scene", str(DATA / f"{scene}.b2scene"), "--luts", str(DATA / "brdf_luts.b2luts"), "--width", str(width), "--height", str(height),
+            "--spp", str(spp), "--bounces", str(bounces), "--dump", prefix, *extra]
+    if threads:
+        cmd += ["--threads", str(threads)]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True)
+    meta = json.loads(out.stdout.strip().splitlines()[-1])
+    n = width * height
+    load = lambda nm, dt: np.fromfile(prefix + nm + ".bin", dt)
+    mat = load("gbuffer_material", np.uint32).reshape(n, 27).copy()
+    mat[:, 0] &= 0xFF
+    return dict(meta=meta, prim=load("gbuffer_prim", np.int32), position=load("gbuffer_position", np.float32).reshape(n, 3),
+                geometric_normal=load("gbuffer_geometric_normal", np.uint32) & 0xFFFFFF, shading_normal=load("gbuffer_shading_normal", np.uint32) & 0xFFFFFF,
+                material=mat, framebuffer=load("framebuffer", np.float32).reshape(n, 3))
+
+
+def rel_error(a, b):
+    """Per-pixel max-over-channels relative error, |a-b| / max(|a|,|b|), 0 where both are ~0."""
+    a = np.asarray(a, np.float64).reshape(-1, 3)
+    b = np.asarray(b, np.float64).reshape(-1, 3)
+    denom = np.maximum(np.abs(a), np.abs(b))
+    return np.where(denom > 1e-6, np.abs(a - b) / np.maximum(denom, 1e-30), 0.0).max(axis=1)
