@@ -70,9 +70,9 @@ B2_HD Rgb lambertian_sample(const Mat& material, V3 shading_normal, V3& sampled_
 }
 
 /* defined in b2_principled.h */
-B2_HD Rgb principled_bsdf_eval(const b2pt_render_data& rd, BsdfCtx& ctx, float& pdf);
-B2_HD float principled_bsdf_pdf(const b2pt_render_data& rd, BsdfCtx& ctx);
-B2_HD Rgb principled_bsdf_sample(const b2pt_render_data& rd, BsdfCtx& ctx, V3& sampled_direction, float& pdf, Rng& rng);
+B2_HD_NOINLINE Rgb principled_bsdf_eval(const b2pt_render_data& rd, BsdfCtx& ctx, float& pdf);
+B2_HD_NOINLINE float principled_bsdf_pdf(const b2pt_render_data& rd, BsdfCtx& ctx);
+B2_HD_NOINLINE Rgb principled_bsdf_sample(const b2pt_render_data& rd, BsdfCtx& ctx, V3& sampled_direction, float& pdf, Rng& rng);
 
 template <class V>
 B2_HD Rgb bsdf_eval(const b2pt_render_data& rd, BsdfCtx& ctx, float& pdf)

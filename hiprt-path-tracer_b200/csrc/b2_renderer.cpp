@@ -404,7 +404,9 @@ int b2pt_renderer_set_luts_file(b2pt_renderer* r, const char* lut_blob_path)
             return B2PT_ERR_IO;
         }
         void* handle = nullptr;
-        int rc = b2pt_lut_create(r->ctx, texels.data(), dims[0], dims[1], dims[2], 1, &handle);
+        const bool is_sheen = !std::strcmp(name, "sheen_ltc"); /* stored as 96x32x1 floats = 32x32 RGB texels */
+        int rc = is_sheen ? b2pt_lut_create(r->ctx, texels.data(), dims[0] / 3, dims[1], dims[2], 3, &handle)
+                          : b2pt_lut_create(r->ctx, texels.data(), dims[0], dims[1], dims[2], 1, &handle);
         if (rc != B2PT_OK)
         {
             std::fclose(f);
@@ -416,6 +418,7 @@ int b2pt_renderer_set_luts_file(b2pt_renderer* r, const char* lut_blob_path)
         else if (!std::strcmp(name, "ggx_glass")) b.GGX_glass_directional_albedo = handle;
         else if (!std::strcmp(name, "ggx_glass_inv")) b.GGX_glass_directional_albedo_inverse = handle;
         else if (!std::strcmp(name, "ggx_thin_glass")) b.GGX_thin_glass_directional_albedo = handle;
+        else if (is_sheen) b.sheen_ltc_parameters_texture = handle;
     }
     std::fclose(f);
     return B2PT_OK;

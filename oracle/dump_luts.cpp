@@ -11,6 +11,7 @@
  * File names follow GPUBakerConstants (Renderer/Baker/GPUBakerConstants.h:43-100) for the default
  * HeightUncorrelated masking-shadowing flavour (HostDeviceCommon/BSDFsData.h:61).
  */
+#include "Device/includes/BSDFs/SheenLTCFittedParameters.h"
 #include "Image/Image.h"
 #include "Renderer/Baker/GPUBakerConstants.h"
 
@@ -42,7 +43,7 @@ int main(int argc, char** argv)
 
     FILE* f = std::fopen(argv[2], "wb");
     if (!f) { std::fprintf(stderr, "cannot write %s\n", argv[2]); return 1; }
-    uint32_t count = 5;
+    uint32_t count = 6;
     std::fwrite("B2LUTS01", 1, 8, f);
     std::fwrite(&count, 4, 1, f);
 
@@ -61,6 +62,18 @@ int main(int argc, char** argv)
     write_table(f, "ggx_glass", load_stack("/GGX/Glass/", GPUBakerConstants::get_GGX_glass_directional_albedo_texture_filename(flavor), GPUBakerConstants::GGX_GLASS_DIRECTIONAL_ALBEDO_TEXTURE_SIZE_IOR));
     write_table(f, "ggx_glass_inv", load_stack("/GGX/Glass/", GPUBakerConstants::get_GGX_glass_directional_albedo_inv_texture_filename(flavor), GPUBakerConstants::GGX_GLASS_DIRECTIONAL_ALBEDO_TEXTURE_SIZE_IOR));
     write_table(f, "ggx_thin_glass", load_stack("/GGX/Glass/", GPUBakerConstants::get_GGX_thin_glass_directional_albedo_texture_filename(flavor), GPUBakerConstants::GGX_THIN_GLASS_DIRECTIONAL_ALBEDO_TEXTURE_SIZE_IOR));
+    {
+        /* sheen LTC fit (Ai, Bi, Ri), 32x32 texels of 3 floats, compiled into the reference
+         * (Device/includes/BSDFs/SheenLTCFittedParameters.h; CPURenderer.cpp:157): stored as a 96x32x1 table whose
+         * rows are 32 RGB texels */
+        char padded[32] = { 0 };
+        std::strncpy(padded, "sheen_ltc", 31);
+        int32_t dims[3] = { 96, 32, 1 };
+        std::fwrite(padded, 1, 32, f);
+        std::fwrite(dims, 4, 3, f);
+        std::fwrite(reinterpret_cast<const float*>(ltc_parameters_table_approximation.data()), 4, 32 * 32 * 3, f);
+        std::printf("sheen_ltc: 32x32 rgb\n");
+    }
     std::fclose(f);
     return 0;
 }

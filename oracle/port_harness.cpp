@@ -92,7 +92,10 @@ struct LutStore
             std::vector<float>& v = data[name];
             v.resize((size_t)dims[0] * dims[1] * dims[2]);
             if (std::fread(v.data(), 4, v.size(), f) != v.size()) { std::fclose(f); return false; }
-            luts[name] = b2pt_lut{ v.data(), dims[0], dims[1], dims[2], 1 };
+            if (!std::strcmp(name, "sheen_ltc"))
+                luts[name] = b2pt_lut{ v.data(), dims[0] / 3, dims[1], dims[2], 3 };
+            else
+                luts[name] = b2pt_lut{ v.data(), dims[0], dims[1], dims[2], 1 };
         }
         std::fclose(f);
         return true;
@@ -219,6 +222,7 @@ int main(int argc, char** argv)
     rd.bsdfs_data.GGX_glass_directional_albedo = &luts.luts["ggx_glass"];
     rd.bsdfs_data.GGX_glass_directional_albedo_inverse = &luts.luts["ggx_glass_inv"];
     rd.bsdfs_data.GGX_thin_glass_directional_albedo = &luts.luts["ggx_thin_glass"];
+    rd.bsdfs_data.sheen_ltc_parameters_texture = &luts.luts["sheen_ltc"];
 
     /* aux + G-buffers */
     std::vector<uint8_t> pixel_active(n, 0);
