@@ -37,6 +37,10 @@ class Counters(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("nodes", C.c_uint64), ("triangles", C.c_uint64)]
 
 
+class Faults(C.Structure):
+    _fields_ = [("traversal_guard_trips", C.c_uint32), ("boundary_guard_trips", C.c_uint32), ("stack_overflows", C.c_uint32)]
+
+
 class Option(C.Structure):
     _fields_ = [("name", C.c_char_p), ("value", C.c_int)]
 
@@ -123,6 +127,11 @@ class Context:
         c = Counters()
         check(lib().b2pt_counters_read(self.handle, C.byref(c)))
         return dict(rays=c.rays, nodes=c.nodes, triangles=c.triangles)
+
+    def faults(self, reset=True):
+        f = Faults()
+        check(lib().b2pt_faults_read(self.handle, C.byref(f), int(reset)))
+        return dict(traversal_guard_trips=f.traversal_guard_trips, boundary_guard_trips=f.boundary_guard_trips, stack_overflows=f.stack_overflows)
 
     def close(self):
         if self.handle:

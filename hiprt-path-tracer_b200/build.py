@@ -52,7 +52,7 @@ def enabled_features():
 
 def source_digest():
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*")) + list((ROOT / "include").glob("*.h")) + [Path(__file__)]):
+    for p in sorted(list(CSRC.glob("*")) + list((ROOT / "include").glob("*.h")) + [Path(__file__), ROOT / "tools" / "traverse_selftest.cu"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     return h.hexdigest()
@@ -83,6 +83,11 @@ def build(force=False, jobs=None, verbose=True):
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    selftest = ["nvcc", *ARCH, "-O3", "-std=c++17", "-fmad=false", "-lineinfo", f"-I{ROOT / 'include'}", f"-I{CSRC}", "-diag-suppress", "821",
+                str(ROOT / "tools" / "traverse_selftest.cu"), str(CSRC / "b2_bvh_build.cpp"), "-Xcompiler", "-fopenmp", "-o", str(ROOT / "tools" / "traverse_selftest")]
+    res = subprocess.run(selftest, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"traverse_selftest build failed:\n{res.stdout}\n{res.stderr}")
     stamp.write_text(digest)
     if verbose:
         print(f"built {OUT} with features {feats or ['(c1 only)']}")

@@ -74,6 +74,23 @@ struct B2TraversalCounters
     unsigned long long rays, nodes, tris;
 };
 
+/* Defensive bounds: a corrupted BVH (or a bug) must never hang the GPU. A traversal that exceeds B2_TRAVERSAL_GUARD
+ * steps is abandoned and counted in the fault words (b2pt_counters_read reports them; tests assert they stay 0). */
+#define B2_TRAVERSAL_GUARD (1u << 20)
+#define B2_BOUNDARY_SKIP_GUARD 64
+enum { B2_FAULT_TRAVERSAL_GUARD = 0, B2_FAULT_BOUNDARY_GUARD = 1, B2_FAULT_STACK_OVERFLOW = 2, B2_FAULT_COUNT = 3 };
+
+B2_HD void b2_report_fault(unsigned int* faults, int which)
+{
+    if (!faults)
+        return;
+#if defined(__CUDA_ARCH__)
+    atomicAdd(faults + which, 1u);
+#else
+    __atomic_fetch_add(faults + which, 1u, __ATOMIC_RELAXED);
+#endif
+}
+
 #define B2_STACK_ENTRIES 24
 
 /* Exact restatement of Triangle::intersect (Triangle.h:20-63) on precomputed edges: edge1 = B-A and edge2 = C-A are
@@ -146,7 +163,8 @@ __device__ __forceinline__ B2NodeRaw b2_load_node(const B2Node* nodes, uint32_t 
  * slots live in shared memory, entry-major, so the 32 lanes of a warp touch 32 consecutive 8-byte words).
  */
 template <bool ANY_HIT>
-B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int stack_stride, B2TraversalCounters* counters)
+B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int stack_stride, B2TraversalCounters* counters,
+                        unsigned int* faults = nullptr)
 {
     B2Hit best;
     best.t = -1.0f;
@@ -166,14 +184,25 @@ B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int
     const uint32_t octant = (dir.x < 0.0f ? 4u : 0u) | (dir.y < 0.0f ? 2u : 0u) | (dir.z < 0.0f ? 1u : 0u);
     const uint32_t oct_inv = 7u - octant;
 
+    /* The stack is addressed through a moving pointer (`top`) plus a depth counter rather than stack[sp * stride]:
+     * ptxas 12.9 (sm_100a) mis-folds the `sp - 1` of the pop into the LDS immediate AFTER already decrementing the
+     * register (observed: "VIADD R22, R22, -1 ; IMAD R5, R22, 0x200, R37 ; LDS.64 [R5 + -0x200]"), which pops the entry
+     * below the top; tools/traverse_selftest.cu is the regression test for this. */
     int sp = 0;
+    uint64_t* top = stack;
     uint32_t group_base = 0;            /* node group: index of first child node */
     uint32_t group_bits = 0x80000000u;  /* bits 24..31: pending inner children (by traversal priority); bits 0..7: imask */
 
     unsigned long long n_nodes = 0, n_tris = 0;
+    unsigned int guard = 0;
 
     while (true)
     {
+        if (++guard > B2_TRAVERSAL_GUARD)
+        {
+            b2_report_fault(faults, B2_FAULT_TRAVERSAL_GUARD);
+            break;
+        }
         uint32_t tri_base = 0, tri_bits = 0;
 
         if (group_bits > 0x00FFFFFFu)
@@ -186,11 +215,19 @@ B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int
             if (group_bits > 0x00FFFFFFu)
             {
                 if (sp < B2_STACK_ENTRIES)
-                    stack[sp * stack_stride] = ((uint64_t)group_base << 32) | group_bits;
+                {
+                    *top = ((uint64_t)group_base << 32) | group_bits;
+                    top += stack_stride;
+                }
+                else
+                    b2_report_fault(faults, B2_FAULT_STACK_OVERFLOW);
                 sp++; /* overflow is counted but dropped; the builder bounds the depth well below the stack size */
             }
 
             n_nodes++;
+#ifdef B2_TRAVERSE_TRACE
+            B2_TRAVERSE_TRACE(guard, node_index, group_base, group_bits, sp);
+#endif
 #if defined(__CUDA_ARCH__)
             const B2NodeRaw raw = b2_load_node(bvh.nodes, node_index);
             const float nox = __uint_as_float(raw.q0.x), noy = __uint_as_float(raw.q0.y), noz = __uint_as_float(raw.q0.z);
@@ -299,7 +336,8 @@ B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int
             sp--;
             if (sp < B2_STACK_ENTRIES)
             {
-                const uint64_t e = stack[sp * stack_stride];
+                top -= stack_stride;
+                const uint64_t e = *top;
                 group_base = (uint32_t)(e >> 32);
                 group_bits = (uint32_t)e;
             }

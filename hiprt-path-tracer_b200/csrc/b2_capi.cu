@@ -191,7 +191,9 @@ int b2pt_host_free_pinned(b2pt_ctx*, void* host_ptr)
 int b2pt_stream_create(b2pt_ctx*, b2pt_stream* out_stream)
 {
     cudaStream_t s;
-    B2_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    /* a blocking stream, like oroStreamCreate (cuStreamCreate, flags 0): work on it is ordered after the synchronous
+     * uploads / memsets the host issues on the legacy default stream (GPURenderer relies on that ordering) */
+    B2_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamDefault));
     *out_stream = s;
     return B2PT_OK;
 }
@@ -494,6 +496,19 @@ int b2pt_counters_read(b2pt_ctx*, b2pt_counters_t* out)
     out->rays = a[0] + b[0];
     out->nodes = a[1] + b[1];
     out->triangles = a[2] + b[2];
+    return B2PT_OK;
+}
+
+int b2pt_faults_read(b2pt_ctx*, b2pt_faults_t* out, int reset)
+{
+    if (!out) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    unsigned int a[B2_FAULT_COUNT], b[B2_FAULT_COUNT];
+    B2_CUDA(cudaDeviceSynchronize());
+    B2_CUDA(b2_faults_read_precise(a, reset));
+    B2_CUDA(b2_faults_read_fast(b, reset));
+    out->traversal_guard_trips = a[B2_FAULT_TRAVERSAL_GUARD] + b[B2_FAULT_TRAVERSAL_GUARD];
+    out->boundary_guard_trips = a[B2_FAULT_BOUNDARY_GUARD] + b[B2_FAULT_BOUNDARY_GUARD];
+    out->stack_overflows = a[B2_FAULT_STACK_OVERFLOW] + b[B2_FAULT_STACK_OVERFLOW];
     return B2PT_OK;
 }
 

@@ -240,6 +240,7 @@ struct Ctx
     uint64_t* stack;               /* first of B2_STACK_ENTRIES slots private to this thread */
     int stack_stride;              /* distance between this thread's consecutive slots */
     B2TraversalCounters* counters; /* null unless the instrumented variant runs */
+    unsigned int* faults;          /* B2_FAULT_COUNT words (device global / host array) or null */
 };
 
 B2_HD V3 load_v3(const b2pt_float3* p, int i) { return v3(p[i].x, p[i].y, p[i].z); }
@@ -303,9 +304,15 @@ B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload&
     const b2pt_render_data& rd = *ctx.rd;
     B2Hit hit;
     bool skipping_volume_boundary = false;
+    int boundary_skips = 0;
     do
     {
-        hit = b2_traverse<false>(ctx.bvh, origin, direction, 3.0e38f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters);
+        if (++boundary_skips > B2_BOUNDARY_SKIP_GUARD)
+        {
+            b2_report_fault(ctx.faults, B2_FAULT_BOUNDARY_GUARD);
+            return false;
+        }
+        hit = b2_traverse<false>(ctx.bvh, origin, direction, 3.0e38f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults);
         if (hit.prim < 0)
             return false;
 
@@ -354,7 +361,7 @@ B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload&
 /* true when something lies strictly before t_max - 1e-4 (opaque scenes) */
 B2_HD bool shadow_ray_occluded(const Ctx& ctx, V3 origin, V3 direction, float t_max, int last_hit_primitive_index)
 {
-    B2Hit hit = b2_traverse<true>(ctx.bvh, origin, direction, t_max - 1.0e-4f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters);
+    B2Hit hit = b2_traverse<true>(ctx.bvh, origin, direction, t_max - 1.0e-4f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults);
     return hit.prim >= 0;
 }
 
@@ -372,7 +379,7 @@ struct LightRayHit
 B2_HD bool bsdf_light_sample_ray(const Ctx& ctx, V3 origin, V3 direction, float t_max, LightRayHit& out, int last_hit_primitive_index)
 {
     const b2pt_render_data& rd = *ctx.rd;
-    B2Hit hit = b2_traverse<false>(ctx.bvh, origin, direction, 3.0e38f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters);
+    B2Hit hit = b2_traverse<false>(ctx.bvh, origin, direction, 3.0e38f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults);
     if (hit.prim < 0)
         return false;
     if (!(hit.t < t_max - 1.0e-4f))

@@ -2,6 +2,7 @@
 #ifndef B2_KERNEL_TABLE_H
 #define B2_KERNEL_TABLE_H
 
+#include "b2_bvh.h"
 #include "b2_frame_loop.h"
 
 #include <cuda_runtime.h>
@@ -25,5 +26,7 @@ cudaError_t b2_counters_reset_precise();
 cudaError_t b2_counters_reset_fast();
 cudaError_t b2_counters_read_precise(unsigned long long out[3]);
 cudaError_t b2_counters_read_fast(unsigned long long out[3]);
+cudaError_t b2_faults_read_precise(unsigned int out[B2_FAULT_COUNT], int reset);
+cudaError_t b2_faults_read_fast(unsigned int out[B2_FAULT_COUNT], int reset);
 
 #endif

@@ -31,6 +31,7 @@
 namespace B2_NS
 {
 __device__ unsigned long long g_counters[3];
+__device__ unsigned int g_faults[B2_FAULT_COUNT];
 
 template <class V, int PASS>
 __global__ void __launch_bounds__(B2_BLOCK_THREADS) pass_kernel(const __grid_constant__ b2pt_render_data rd, int tiles_x)
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) pass_kernel(const __grid_con
     ctx.stack = stacks + threadIdx.x;
     ctx.stack_stride = B2_BLOCK_THREADS;
     ctx.counters = V::COUNTERS ? &local_counters : nullptr;
+    ctx.faults = g_faults;
 
     b2_run_pass_pixel<V>(PASS, ctx, x, y);
 
@@ -152,6 +154,14 @@ cudaError_t b2_counters_reset_precise()
     return cudaMemcpyToSymbol(b2_precise::g_counters, zero, sizeof(zero));
 }
 cudaError_t b2_counters_read_precise(unsigned long long out[3]) { return cudaMemcpyFromSymbol(out, b2_precise::g_counters, 3 * sizeof(unsigned long long)); }
+cudaError_t b2_faults_read_precise(unsigned int out[B2_FAULT_COUNT], int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, b2_precise::g_faults, B2_FAULT_COUNT * sizeof(unsigned int));
+    if (e != cudaSuccess || !reset)
+        return e;
+    unsigned int zero[B2_FAULT_COUNT] = {};
+    return cudaMemcpyToSymbol(b2_precise::g_faults, zero, sizeof(zero));
+}
 #else
 const B2KernelEntry* b2_kernel_table_fast(int* count) { return b2_fast::table(count); }
 cudaError_t b2_counters_reset_fast()
@@ -160,4 +170,12 @@ cudaError_t b2_counters_reset_fast()
     return cudaMemcpyToSymbol(b2_fast::g_counters, zero, sizeof(zero));
 }
 cudaError_t b2_counters_read_fast(unsigned long long out[3]) { return cudaMemcpyFromSymbol(out, b2_fast::g_counters, 3 * sizeof(unsigned long long)); }
+cudaError_t b2_faults_read_fast(unsigned int out[B2_FAULT_COUNT], int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, b2_fast::g_faults, B2_FAULT_COUNT * sizeof(unsigned int));
+    if (e != cudaSuccess || !reset)
+        return e;
+    unsigned int zero[B2_FAULT_COUNT] = {};
+    return cudaMemcpyToSymbol(b2_fast::g_faults, zero, sizeof(zero));
+}
 #endif

@@ -151,6 +151,15 @@ typedef struct
     uint64_t nodes;     /* wide-BVH nodes fetched */
     uint64_t triangles; /* triangles tested */
 } b2pt_counters_t;
+/* Defensive fault words: traversals abandoned by the step guard, boundary-skip loops abandoned, traversal-stack
+ * overflows. All three must stay 0 on a valid scene (asserted by tests/). */
+typedef struct
+{
+    uint32_t traversal_guard_trips;
+    uint32_t boundary_guard_trips;
+    uint32_t stack_overflows;
+} b2pt_faults_t;
+int b2pt_faults_read(b2pt_ctx* ctx, b2pt_faults_t* out, int reset);
 int b2pt_counters_reset(b2pt_ctx* ctx);
 int b2pt_counters_read(b2pt_ctx* ctx, b2pt_counters_t* out);
 

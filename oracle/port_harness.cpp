@@ -102,6 +102,8 @@ struct LutStore
     }
 };
 
+static unsigned int g_port_faults[B2_FAULT_COUNT] = { 0, 0, 0 };
+
 template <class V>
 static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice& bvh, const Args& a)
 {
@@ -114,6 +116,7 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
         ctx.stack = stack;
         ctx.stack_stride = 1;
         ctx.counters = nullptr;
+        ctx.faults = g_port_faults;
 #pragma omp for schedule(dynamic)
         for (int y = a.win_y0; y < a.win_y1; y++)
             for (int x = a.win_x0; x < a.win_x1; x++)
@@ -325,6 +328,6 @@ int main(int argc, char** argv)
     std::printf("{\"oracle\": \"port\", \"variant\": \"%s\", \"width\": %d, \"height\": %d, \"window_pixels\": %lld, \"spp\": %d, \"bounces\": %d, \"threads\": %d, "
                 "\"render_seconds\": %.6f, \"bvh_build_seconds\": %.3f, \"mpaths_per_s\": %.6f, \"bvh_nodes\": %zu, \"bvh_depth\": %d, \"triangles\": %zu, \"emissive_triangles\": %zu}\n",
                 a.variant.c_str(), a.width, a.height, window_pixels, a.spp, a.bounces, omp_get_max_threads(), seconds, scene.bvh_build_seconds,
-                (double)window_pixels * a.spp / seconds / 1.0e6, scene.bvh.nodes.size(), scene.bvh.stats.max_depth, scene.blob.n_triangles(), scene.emissive_triangles.size());
+                (double)window_pixels * a.spp / seconds / 1.0e6, scene.bvh.nodes.size(), scene.bvh.stats.max_depth, scene.blob.n_triangles(), scene.emissive_triangles.size(), g_port_faults[0], g_port_faults[1], g_port_faults[2]);
     return 0;
 }

@@ -29,8 +29,10 @@ def make_renderer(b2pt, ctx, meta, precise=True):
 def test_cuda_precise_matches_golden(b2pt, gpu_ctx, name):
     g, meta = load_golden(name)
     r = make_renderer(b2pt, gpu_ctx, meta, precise=True)
-    r.render(meta["spp"])
-    gb = r.gbuffer()
+    r.render(1)
+    gb = r.gbuffer()  # the fixtures hold the G-buffer of the FIRST sample (the oracle dumps it after frame 1)
+    if meta["spp"] > 1:
+        r.render(meta["spp"] - 1)
     fb = r.framebuffer()
     r.close()
     assert np.array_equal(gb["prim"], g["gbuffer_prim"]), "primary-hit primitive ids must match bit-exactly"
@@ -50,8 +52,10 @@ def test_cuda_fast_flavour_agrees_statistically(b2pt, gpu_ctx, name):
     G-buffer ids stay exact and the image mean stays within 1 %."""
     g, meta = load_golden(name)
     r = make_renderer(b2pt, gpu_ctx, meta, precise=False)
-    r.render(meta["spp"])
+    r.render(1)
     gb = r.gbuffer()
+    if meta["spp"] > 1:
+        r.render(meta["spp"] - 1)
     fb = r.framebuffer()
     r.close()
     assert (gb["prim"] != g["gbuffer_prim"]).mean() < 1e-3
@@ -97,5 +101,20 @@ def test_traversal_counters(b2pt, gpu_ctx):
     gpu_ctx.counters_reset()
     r.render(1)
     c = gpu_ctx.counters_read()
+    faults = gpu_ctx.faults()
     r.close()
     assert c["rays"] >= 256 * 256 and c["nodes"] > c["rays"] and c["triangles"] > 0
+    assert faults == dict(traversal_guard_trips=0, boundary_guard_trips=0, stack_overflows=0)
+
+
+def test_traversal_selftest_binary(built):
+    """GPU unit test of the CW8 traversal alone (tools/traverse_selftest.cu): device == host build of the same function,
+    bit for bit, for 256k rays, with the shared-memory stack and with a local stack; no guard trips. Regression test for
+    the ptxas stack-pop miscompile documented in b2_bvh.h."""
+    import subprocess
+    from conftest import ROOT
+    exe = ROOT / "tools" / "traverse_selftest"
+    if not exe.exists():
+        pytest.skip("tools/traverse_selftest not built")
+    out = subprocess.run([str(exe), str(DATA / "cornell_pbr_16x9.b2scene"), "262144"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "SELFTEST OK" in out.stdout, out.stdout[-2000:]

@@ -31,6 +31,27 @@ say("load library", b2pt.lib().b2pt_version_string())
 ctx = b2pt.Context(0)
 p = ctx.props()
 say("context", p.name.decode(), "SMs", p.sm_count)
+import ctypes as C  # noqa: E402
+
+# stage A: the two kernels one by one through the device-layer ABI (b2pt_kernel_get / b2pt_kernel_launch)
+r = b2pt.Renderer(ctx, w, h, variant, precise=True)
+r.set_scene_file(ROOT / "data" / "cornell_pbr_16x9.b2scene")
+r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
+r.set(nb_bounces=3)
+lib = b2pt.lib()
+vkey = dict(c1=(1, 1, 0), c2=(0, 3, 1), c3=(0, 4, 1), c4=(0, 5, 1))[variant]
+for entry_name in ("CameraRays", "MegaKernel"):
+    opts = (b2pt.Option * 4)((b"BSDFOverride", vkey[0]), (b"DirectLightSamplingStrategy", vkey[1]), (b"DirectLightSamplingBaseStrategy", vkey[2]), (b"B2PT_PRECISE", 1))
+    k = C.c_void_p()
+    b2pt.check(lib.b2pt_kernel_get(ctx.handle, entry_name.encode(), opts, 4, C.byref(k)))
+    args = (C.c_void_p * 1)(r._rd)
+    say("launch", entry_name)
+    b2pt.check(lib.b2pt_kernel_launch(k, 8, 8, w, h, args, None))
+    ms = C.c_float()
+    b2pt.check(lib.b2pt_kernel_last_ms(k, C.byref(ms)))
+    say(entry_name, "done", ms.value, "ms; faults", ctx.faults())
+r.close()
+
 for precise in (True, False):
     r = b2pt.Renderer(ctx, w, h, variant, precise=precise)
     say("renderer created precise=", precise)
@@ -46,7 +67,7 @@ for precise in (True, False):
     fb = r.framebuffer()
     say("framebuffer mean", float(fb.mean()), "max", float(fb.max()))
     g = r.gbuffer()
-    say("gbuffer hits", int((g["prim"] >= 0).sum()), "of", w * h)
+    say("gbuffer hits", int((g["prim"] >= 0).sum()), "of", w * h, "faults", ctx.faults())
     r.close()
 ctx.close()
 say("OK")
