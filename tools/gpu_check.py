@@ -72,8 +72,15 @@ def main():
             times.append(r.last_render_ms())
         report[f"{flavour}_ms"] = times[1:]
         report[f"{flavour}_mpaths_per_s"] = n * a.spp / (min(times[1:]) * 1e-3) / 1e6
+        # parity dump: the oracles dump the G-buffer of the FIRST sample, the framebuffer after the last one
+        r.reset()
+        r.set_host_seed(42)
+        r.render(1)
         g = r.gbuffer()
+        if a.spp > 1:
+            r.render(a.spp - 1)
         fb = r.framebuffer()
+        report[f"{flavour}_faults"] = ctx.faults()
         prefix = str(tmp / f"cuda_{flavour}_")
         g["prim"].tofile(prefix + "gbuffer_prim.bin")
         g["position"].tofile(prefix + "gbuffer_position.bin")
