@@ -243,6 +243,12 @@ struct Ctx
     unsigned int* faults;          /* B2_FAULT_COUNT words (device global / host array) or null */
 };
 
+/* HIPRTRenderSettings::do_render_low_resolution, RenderSettings.h */
+B2_HD bool do_render_low_resolution(const b2pt_render_settings& s)
+{
+    return s.wants_render_low_resolution && s.allow_render_low_resolution && s.accumulate;
+}
+
 B2_HD V3 load_v3(const b2pt_float3* p, int i) { return v3(p[i].x, p[i].y, p[i].z); }
 B2_HD Rgb load_rgb(const b2pt_rgb* p, int i) { return rgb(p[i].r, p[i].g, p[i].b); }
 

@@ -36,10 +36,6 @@ B2_HD bool use_prev_frame_g_buffer(const b2pt_render_settings& s)
     return V::DIRECT == B2_LSS_RESTIR_DI && s.restir_di_settings.common_temporal_pass.do_temporal_reuse_pass;
 }
 
-B2_HD bool do_render_low_resolution(const b2pt_render_settings& s)
-{
-    return s.wants_render_low_resolution && s.allow_render_low_resolution && s.accumulate;
-}
 
 B2_HD void store_packed_material(void* buffer, uint32_t pixel_index, const PackedMat& p)
 {

@@ -1,7 +1,998 @@
-/* b2_restir_di.h -- placeholder until ReSTIR DI lands (filled in by a later milestone of this round). */
+/*
+ * b2_restir_di.h -- the ReSTIR DI passes as per-pixel functions: initial candidates, temporal reuse, spatial reuse
+ * and the fused spatiotemporal reuse, with pairwise-MIS bias correction (confidence weights), visibility in the
+ * bias-correction target functions and visibility reuse -- the reference's default macro set.
+ *
+ * Restates /root/reference/src/Device/kernels/ReSTIR/DI/InitialCandidates.h:92-538, TemporalReuse.h:49-296,
+ * SpatialReuse.h:42-322, FusedSpatiotemporalReuse.h:43-564 and their helpers:
+ *   includes/ReSTIR/Utils.h:25-65                (visibility reuse: kill / mark-unoccluded)
+ *   includes/ReSTIR/UtilsTemporal.h:11-96        (reprojection, permutation sampling, neighbour search)
+ *   includes/ReSTIR/UtilsSpatial.h:17-339        (disk neighbours, directional masks, RNG replay, valid-neighbour count)
+ *   includes/ReSTIR/NeighborSimilarity.h:16-107  (plane distance / normal / roughness heuristics)
+ *   includes/ReSTIR/TemporalMISWeight.h:163-254, SpatialMISWeight.h:119-235, SpatiotemporalMISWeight.h:140-225
+ * The reference kernels take HIPRTRenderData BY VALUE and a few of them scribble per-pixel values into their private
+ * copy (spatial_neighbors_rng_seed, reuse_radius, reuse_neighbor_count, the directions mask); here the render data is a
+ * shared __grid_constant__, so those four live in `SpatialLocal`.
+ * Quirks kept on purpose (the oracle has them): the DI spatial kernel keys its seed on the ReSTIR *GI* setting
+ * `coalesced_spatial_reuse` (SpatialReuse.h:66); the fused kernel XORs instead of multiplying its seed (:173) and draws
+ * the neighbour seed twice (:177 then UtilsSpatial.h:22); similarity heuristics read the neighbour's normal from the
+ * CURRENT G-buffer even when comparing against the previous frame (NeighborSimilarity.h:100).
+ */
 #ifndef B2_RESTIR_DI_H
 #define B2_RESTIR_DI_H
+
 #include "b2_pathtrace.h"
+
+#define B2_LIGHT_DOESNT_CONTRIBUTE_ENOUGH -42.0f
+#define B2_DIRECTIONAL_REUSE_BIT_COUNT 64
+
+/* ReSTIR GI's common_spatial_pass.coalesced_spatial_reuse inside the opaque GI settings block: ReSTIRGISettings starts
+ * with the same ReSTIRCommonSettings prefix as ReSTIRDISettings (oracle/layout_check.cpp asserts the offset) */
+B2_HD bool restir_gi_coalesced_spatial_reuse(const b2pt_render_data& rd)
+{
+    const uint8_t* gi = reinterpret_cast<const uint8_t*>(rd.render_settings.restir_gi_settings_opaque);
+    const size_t offset = (size_t)(reinterpret_cast<const uint8_t*>(&rd.render_settings.restir_di_settings.common_spatial_pass.coalesced_spatial_reuse) -
+                                   reinterpret_cast<const uint8_t*>(&rd.render_settings.restir_di_settings));
+    return gi[offset] != 0;
+}
+
+struct SpatialLocal
+{
+    unsigned int rng_seed;
+    int reuse_radius;
+    int reuse_neighbor_count;
+    unsigned long long directions_mask;
+};
+
+B2_HD SpatialLocal spatial_local_from(const b2pt_render_data& rd)
+{
+    const b2pt_restir_spatial_common& s = rd.render_settings.restir_di_settings.common_spatial_pass;
+    SpatialLocal l;
+    l.rng_seed = s.spatial_neighbors_rng_seed;
+    l.reuse_radius = s.reuse_radius;
+    l.reuse_neighbor_count = s.reuse_neighbor_count;
+    l.directions_mask = s.current_pixel_directions_reuse_mask;
+    return l;
+}
+
+B2_HD bool do_adaptive_directional_spatial_reuse(const b2pt_render_data& rd)
+{
+    return rd.render_settings.restir_di_settings.common_spatial_pass.use_adaptive_directional_spatial_reuse && rd.render_settings.accumulate;
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* visibility reuse (ReSTIR/Utils.h:25-65) */
+B2_HD bool di_visibility_test_kill_reservoir(const Ctx& ctx, DiReservoir& reservoir, V3 shading_point, int last_primitive_hit_index)
+{
+    if (reservoir.UCW <= 0.0f && reservoir.weight_sum <= 0.0f)
+        return false;
+    else if (reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED)
+        return false;
+
+    float distance_to_light;
+    V3 sample_direction = di_light_sample_direction(*ctx.rd, reservoir.sample, shading_point, distance_to_light);
+    bool visible = !shadow_ray_occluded(ctx, shading_point, sample_direction, distance_to_light, last_primitive_hit_index);
+    if (!visible)
+    {
+        reservoir.UCW = -1.0f;
+        return true;
+    }
+    reservoir.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+    return false;
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* neighbour similarity (ReSTIR/NeighborSimilarity.h) */
+B2_HD bool check_neighbor_similarity_heuristics(const b2pt_render_data& rd, int neighbor_pixel_index, int center_pixel_index, V3 current_shading_point, V3 current_normal,
+                                                bool previous_frame)
+{
+    if (neighbor_pixel_index == center_pixel_index)
+        return true;
+    const b2pt_gbuffer& g = previous_frame ? rd.g_buffer_prev_frame : rd.g_buffer;
+    if (g.first_hit_prim_index[neighbor_pixel_index] == -1)
+        return false;
+
+    const b2pt_restir_neighbor_similarity& s = rd.render_settings.restir_di_settings.neighbor_similarity_settings;
+    V3 neighbor_world_space_point = v3(0.0f);
+    float neighbor_roughness = 0.0f;
+    float current_material_roughness = 0.0f;
+    if (previous_frame)
+    {
+        if (s.use_plane_distance_heuristic)
+            neighbor_world_space_point = load_v3(g.primary_hit_position, neighbor_pixel_index);
+        if (s.use_roughness_similarity_heuristic)
+            neighbor_roughness = unpack_hi8(reinterpret_cast<const uint32_t*>(g.materials)[(size_t)neighbor_pixel_index * PM_WORDS + PM_BASE_COLOR_ROUGHNESS]);
+    }
+    else
+    {
+        neighbor_world_space_point = load_v3(g.primary_hit_position, neighbor_pixel_index);
+        neighbor_roughness = unpack_hi8(reinterpret_cast<const uint32_t*>(g.materials)[(size_t)neighbor_pixel_index * PM_WORDS + PM_BASE_COLOR_ROUGHNESS]);
+    }
+    if (s.use_roughness_similarity_heuristic)
+        current_material_roughness = unpack_hi8(reinterpret_cast<const uint32_t*>(rd.g_buffer.materials)[(size_t)center_pixel_index * PM_WORDS + PM_BASE_COLOR_ROUGHNESS]);
+
+    V3 neighbor_normal = s.reject_using_geometric_normals ? unpack_normal_oct24(rd.g_buffer.geometric_normals[neighbor_pixel_index]) : unpack_normal_oct24(rd.g_buffer.shading_normals[neighbor_pixel_index]);
+
+    bool plane_distance_passed = true;
+    if (s.use_plane_distance_heuristic)
+    {
+        V3 direction_between_points = neighbor_world_space_point - current_shading_point;
+        float distance_to_plane = fabsf(dot(direction_between_points, current_normal));
+        plane_distance_passed = distance_to_plane < s.plane_distance_threshold;
+    }
+    bool normal_similarity_passed = true;
+    if (s.use_normal_similarity_heuristic)
+        normal_similarity_passed = dot(current_normal, neighbor_normal) > s.normal_similarity_angle_precomp;
+    bool roughness_similarity_passed = true;
+    if (s.use_roughness_similarity_heuristic)
+        roughness_similarity_passed = fabsf(neighbor_roughness - current_material_roughness) < s.roughness_similarity_threshold;
+    return plane_distance_passed && normal_similarity_passed && roughness_similarity_passed;
+}
+
+B2_HD V3 normal_for_rejection_heuristic(const b2pt_render_data& rd, const DiSurface& surface)
+{
+    return rd.render_settings.restir_di_settings.neighbor_similarity_settings.reject_using_geometric_normals ? surface.geometric_normal : surface.shading_normal;
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* temporal neighbour (ReSTIR/UtilsTemporal.h) */
+struct Int3 { int x, y, z; };
+
 template <class V>
-B2_HD void restir_di_pass_pixel(int pass, const Ctx& ctx, uint32_t x, uint32_t y);
+B2_HD Int3 find_temporal_neighbor_index(const b2pt_render_data& rd, V3 current_shading_point, V3 current_normal, int center_pixel_index, Rng& rng)
+{
+    const b2pt_int2 resolution = rd.render_settings.render_resolution;
+    if (rd.render_settings.accumulate)
+        return Int3{ center_pixel_index, center_pixel_index % resolution.x, center_pixel_index / resolution.x };
+
+    const b2pt_restir_temporal_common& t = rd.render_settings.restir_di_settings.common_temporal_pass;
+    V3 prev_xyz = mat4_mul_point(rd.prev_camera.view_projection, current_shading_point);
+    V2 prev_ss = v2(prev_xyz.x, prev_xyz.y);
+    prev_ss = prev_ss + v2(1.0f, 1.0f);
+    prev_ss = prev_ss * v2(0.5f, 0.5f);
+    V2 prev_pixel_float = v2(prev_ss.x * resolution.x, prev_ss.y * resolution.y);
+    prev_pixel_float = prev_pixel_float - v2(0.5f, 0.5f);
+
+    int temporal_neighbor_index = -1;
+    for (int i = 0; i < t.max_neighbor_search_count + 1; i++)
+    {
+        V2 offset = v2(0.0f, 0.0f);
+        if (i > 0)
+        {
+            /* make_float2(rng() - 0.5f, rng() - 0.5f): right-to-left argument evaluation under g++, see get_spatial_neighbor_pixel_index */
+            float oy = rng.next_float() - 0.5f;
+            float ox = rng.next_float() - 0.5f;
+            offset = v2(ox, oy) * (float)t.neighbor_search_radius;
+        }
+        int px = (int)roundf(prev_pixel_float.x + offset.x), py = (int)roundf(prev_pixel_float.y + offset.y);
+        if (t.use_permutation_sampling && i == 0)
+        {
+            int random_bits = t.permutation_sampling_random_bits;
+            int offx = random_bits & 3, offy = (random_bits >> 2) & 3;
+            px += offx;
+            py += offy;
+            px ^= 3;
+            py ^= 3;
+            px -= offx;
+            py -= offy;
+        }
+        if (px < 0 || px >= resolution.x || py < 0 || py >= resolution.y)
+            continue;
+        temporal_neighbor_index = px + py * resolution.x;
+        if (check_neighbor_similarity_heuristics(rd, temporal_neighbor_index, center_pixel_index, current_shading_point, current_normal, use_prev_frame_g_buffer<V>(rd.render_settings)))
+            break;
+        temporal_neighbor_index = -1;
+    }
+    return Int3{ temporal_neighbor_index, (int)roundf(prev_pixel_float.x), (int)roundf(prev_pixel_float.y) };
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* spatial neighbours (ReSTIR/UtilsSpatial.h) */
+B2_HD int b2_popcll(unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+
+B2_HD void setup_adaptive_directional_spatial_reuse(const b2pt_render_data& rd, SpatialLocal& local, unsigned int center_pixel_index, Rng& rng)
+{
+    const b2pt_restir_spatial_common& s = rd.render_settings.restir_di_settings.common_spatial_pass;
+    local.rng_seed = rng.next_u32();
+    if (do_adaptive_directional_spatial_reuse(rd))
+    {
+        local.reuse_radius = s.per_pixel_spatial_reuse_radius[center_pixel_index];
+        local.directions_mask = s.per_pixel_spatial_reuse_directions_mask_ull[center_pixel_index];
+        if (local.reuse_radius == 0)
+            local.reuse_neighbor_count = 0;
+    }
+}
+
+B2_HD V2 sample_spatial_neighbor_from_allowed_directions(const SpatialLocal& local, Rng& rng)
+{
+    unsigned long long directions_mask = local.directions_mask;
+    int number_of_allowed_sectors = b2_popcll(directions_mask);
+    unsigned char random_sector_index = (unsigned char)rng.next_index(number_of_allowed_sectors);
+    unsigned char count_left_to_go = (unsigned char)(random_sector_index + 1);
+    int sector_index = 0;
+    unsigned char bit_count_so_far = 0;
+    if (b2_popcll(directions_mask) == B2_DIRECTIONAL_REUSE_BIT_COUNT)
+        sector_index = random_sector_index;
+    else
+    {
+        while (count_left_to_go > 0)
+        {
+            unsigned char mask_length = count_left_to_go;
+            unsigned long long mask = ((1ull << mask_length) - 1ull) << bit_count_so_far;
+            int count_mask = b2_popcll(directions_mask & mask);
+            count_left_to_go = (unsigned char)(count_left_to_go - count_mask);
+            bit_count_so_far = (unsigned char)(bit_count_so_far + mask_length);
+        }
+        sector_index = --bit_count_so_far;
+    }
+    float theta_start = sector_index / (float)B2_DIRECTIONAL_REUSE_BIT_COUNT;
+    float random_theta = theta_start + rng.next_float() * (1.0f / (float)B2_DIRECTIONAL_REUSE_BIT_COUNT);
+    float second = rng.next_float();
+    return v2(random_theta, second);
+}
+
+B2_HD int get_spatial_neighbor_pixel_index(const b2pt_render_data& rd, const SpatialLocal& local, int neighbor_index, int cx, int cy, Rng& rng)
+{
+    const b2pt_restir_spatial_common& s = rd.render_settings.restir_di_settings.common_spatial_pass;
+    const b2pt_int2 res = rd.render_settings.render_resolution;
+    if (neighbor_index == local.reuse_neighbor_count)
+        return cx + cy * res.x;
+
+    V2 uv;
+    if (do_adaptive_directional_spatial_reuse(rd))
+        uv = sample_spatial_neighbor_from_allowed_directions(local, rng);
+    else
+    {
+        /* `make_float2(rng(), rng())` in the reference: the order of the two draws is unspecified in C++ and g++ (the
+         * compiler of the parity oracle) evaluates call arguments right to left, so .y gets the first draw */
+        float u1 = rng.next_float();
+        float u0 = rng.next_float();
+        uv = v2(u0, u1);
+    }
+    V2 neighbor_offset_in_disk = sample_in_disk_uv((float)local.reuse_radius, uv);
+    int ox = (int)roundf(neighbor_offset_in_disk.x), oy = (int)roundf(neighbor_offset_in_disk.y);
+
+    int nx, ny;
+    if (s.debug_neighbor_location)
+    {
+        int dx, dy;
+        if (s.debug_neighbor_location_direction == 0) { dx = local.reuse_radius; dy = 0; }
+        else if (s.debug_neighbor_location_direction == 1) { dx = 0; dy = local.reuse_radius; }
+        else { dx = local.reuse_radius; dy = local.reuse_radius; }
+        nx = cx + dx;
+        ny = cy + dy;
+    }
+    else
+    {
+        nx = cx + ox;
+        ny = cy + oy;
+    }
+    if (nx < 0 || nx >= res.x || ny < 0 || ny >= res.y)
+        return -1;
+
+    int neighbor_pixel_index = nx + ny * res.x;
+    if (rd.render_settings.enable_adaptive_sampling && rd.render_settings.sample_number >= (unsigned int)rd.render_settings.adaptive_sampling_min_samples)
+    {
+        if (s.allow_converged_neighbors_reuse)
+        {
+            Rng rng_converged = make_rng(rd.random_number);
+            if (rng_converged.next_float() > s.converged_neighbor_reuse_probability)
+                if (rd.aux_buffers.pixel_converged_sample_count[neighbor_pixel_index] != -1)
+                    return -1;
+        }
+        else if (rd.aux_buffers.pixel_converged_sample_count[neighbor_pixel_index] != -1)
+            return -1;
+    }
+    return neighbor_pixel_index;
+}
+
+B2_HD void spatial_neighbor_advance_rng(const b2pt_render_data& rd, Rng& rng)
+{
+    rng.next_u32();
+    rng.next_u32();
+    if (do_adaptive_directional_spatial_reuse(rd))
+        rng.next_u32();
+}
+
+/* count_valid_spatial_neighbors / count_valid_spatiotemporal_neighbors: replay the neighbour RNG, apply the
+ * heuristics, sum the neighbours' M and remember who passed in a bit cache */
+B2_HD void count_valid_neighbors(const b2pt_render_data& rd, const SpatialLocal& local, const DiSurface& center_pixel_surface, int center_pixel_index, int around_x, int around_y,
+                                 bool previous_frame, const void* input_reservoirs, int& out_valid_neighbor_count, int& out_valid_neighbor_M_sum, int& out_neighbor_heuristics_cache)
+{
+    out_valid_neighbor_count = 0;
+    Rng spatial_neighbors_rng = make_rng(local.rng_seed);
+    for (int neighbor_index = 0; neighbor_index < local.reuse_neighbor_count; neighbor_index++)
+    {
+        int neighbor_pixel_index = get_spatial_neighbor_pixel_index(rd, local, neighbor_index, around_x, around_y, spatial_neighbors_rng);
+        if (neighbor_pixel_index == -1)
+            continue;
+        if (!check_neighbor_similarity_heuristics(rd, neighbor_pixel_index, center_pixel_index, center_pixel_surface.shading_point, normal_for_rejection_heuristic(rd, center_pixel_surface), previous_frame))
+            continue;
+        out_valid_neighbor_M_sum += di_load_M(rd, input_reservoirs, neighbor_pixel_index);
+        out_valid_neighbor_count++;
+        out_neighbor_heuristics_cache |= (1 << neighbor_index);
+    }
+}
+
+B2_HD bool do_include_spatial_visibility_term(const b2pt_render_data& rd, const SpatialLocal& local, int current_neighbor_index)
+{
+    /* ReSTIR_DI_SpatialTargetFunctionVisibility = FALSE (reference default) makes the whole expression false */
+    (void)rd;
+    (void)local;
+    (void)current_neighbor_index;
+    return false;
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* pairwise MIS (confidence weights): shared arithmetic of SpatialMISWeight.h:119-235 and SpatiotemporalMISWeight.h:140-225 */
+struct PairwiseMis
+{
+    float mc;
+
+    template <class V>
+    B2_HD float weight(const Ctx& ctx, int reservoir_being_resampled_M, float reservoir_being_resampled_target_function, int center_pixel_reservoir_M,
+                       float center_pixel_reservoir_target_function, const DiSample& center_pixel_reservoir_sample, float target_function_at_center, int neighbor_pixel_index,
+                       bool neighbor_from_previous_frame, int valid_neighbors_count, int valid_neighbors_M_sum, bool update_mc, bool resampling_canonical, bool guard_zero_confidence, Rng& rng)
+    {
+        const b2pt_render_data& rd = *ctx.rd;
+        if (resampling_canonical)
+            return mc == 0.0f ? 1.0f : mc;
+
+        float target_function_at_neighbor = reservoir_being_resampled_target_function;
+        float target_function_center_sample_at_center = center_pixel_reservoir_target_function;
+        bool use_confidence_weights = rd.render_settings.restir_di_settings.use_confidence_weights != 0;
+        float reservoir_resampled_M = use_confidence_weights ? (float)reservoir_being_resampled_M : 1.0f;
+        float center_reservoir_M = use_confidence_weights ? (float)center_pixel_reservoir_M : 1.0f;
+        float neighbors_confidence_sum = use_confidence_weights ? (float)valid_neighbors_M_sum : 1.0f;
+        float valid_neighbor_division_term = use_confidence_weights ? 1.0f : (float)valid_neighbors_count;
+
+        float nume = target_function_at_neighbor * reservoir_resampled_M;
+        float denom = target_function_at_neighbor * neighbors_confidence_sum + target_function_at_center / valid_neighbor_division_term * center_reservoir_M;
+        float mi = denom == 0.0f ? 0.0f : (nume / denom);
+
+        if (update_mc)
+        {
+            DiSurface neighbor_pixel_surface = get_pixel_surface<V>(rd, neighbor_pixel_index, neighbor_from_previous_frame, rng);
+            float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, center_pixel_reservoir_sample, neighbor_pixel_surface);
+
+            float nume_mc = target_function_center_sample_at_center / valid_neighbor_division_term * center_reservoir_M;
+            float denom_mc = target_function_center_sample_at_neighbor * neighbors_confidence_sum + target_function_center_sample_at_center / valid_neighbor_division_term * center_reservoir_M;
+
+            float confidence_weights_multiplier;
+            if (use_confidence_weights)
+            {
+                if (guard_zero_confidence && neighbors_confidence_sum == 0.0f)
+                    confidence_weights_multiplier = 0.0f;
+                else
+                    confidence_weights_multiplier = reservoir_resampled_M / neighbors_confidence_sum;
+            }
+            else
+                confidence_weights_multiplier = 1.0f;
+
+            if (denom_mc != 0.0f)
+                mc += nume_mc / denom_mc / valid_neighbor_division_term * confidence_weights_multiplier;
+        }
+        return mi / valid_neighbor_division_term;
+    }
+};
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* initial candidates (InitialCandidates.h) */
+template <class V>
+B2_HD DiSample sample_fresh_light_candidate(const Ctx& ctx, float envmap_candidate_probability, const HitInfo& hit, Rgb& out_sample_radiance, float& out_sample_cosine_term,
+                                            float& out_sample_pdf, Rng& rng)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    DiSample light_sample = di_sample_defaults();
+    V3 evaluated_point = hit.inter_point;
+
+    if (rng.next_float() > envmap_candidate_probability)
+    {
+        LightSample light_sample_info = sample_one_emissive_triangle<V>(rd, rng);
+        light_sample.emissive_triangle_index = light_sample_info.emissive_triangle_index;
+        light_sample.point_on_light_source = light_sample_info.point_on_light;
+        out_sample_pdf = light_sample_info.area_measure_pdf;
+        if (out_sample_pdf > 0.0f)
+        {
+            V3 to_light_direction = light_sample.point_on_light_source - evaluated_point;
+            float distance_to_light = length(to_light_direction);
+            to_light_direction = to_light_direction / distance_to_light;
+            out_sample_cosine_term = b2_max(0.0f, dot(hit.shading_normal, to_light_direction));
+            bool contributes_enough = check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, light_sample_info.emission * out_sample_cosine_term / out_sample_pdf);
+            if (!contributes_enough)
+            {
+                light_sample.target_function = B2_LIGHT_DOESNT_CONTRIBUTE_ENOUGH;
+                return light_sample;
+            }
+            out_sample_pdf *= (1.0f - envmap_candidate_probability);
+            out_sample_radiance = light_sample_info.emission;
+        }
+    }
+    else
+    {
+        V3 envmap_sampled_direction = v3(0.0f, 1.0f, 0.0f);
+        out_sample_radiance = rd.world_settings.envmap ? envmap_sample<V>(rd.world_settings, envmap_sampled_direction, out_sample_pdf, rng) : rgb(0.0f);
+        out_sample_cosine_term = b2_max(0.0f, dot(envmap_sampled_direction, hit.shading_normal));
+        bool contributes_enough = check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, out_sample_radiance * out_sample_cosine_term / out_sample_pdf);
+        if (!contributes_enough)
+        {
+            light_sample.target_function = B2_LIGHT_DOESNT_CONTRIBUTE_ENOUGH;
+            return light_sample;
+        }
+        out_sample_pdf *= envmap_candidate_probability;
+        light_sample.emissive_triangle_index = -1;
+        light_sample.point_on_light_source = mat3_mul_vec(rd.world_settings.world_to_envmap_matrix, envmap_sampled_direction);
+        light_sample.or_flags(B2_DI_FLAGS_ENVMAP_SAMPLE);
+    }
+    return light_sample;
+}
+
+B2_HD DiSurface surface_from_hit(const HitInfo& hit, const Payload& payload, V3 view_direction)
+{
+    DiSurface surface;
+    surface.geometric_normal = hit.geometric_normal;
+    surface.primitive_index = hit.primitive_index;
+    surface.material = payload.material;
+    surface.ray_volume_state = payload.volume_state;
+    surface.shading_normal = hit.shading_normal;
+    surface.shading_point = hit.inter_point;
+    surface.view_direction = view_direction;
+    return surface;
+}
+
+template <class V>
+B2_HD DiReservoir sample_initial_candidates(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    int initial_nb_light_cand = di.initial_candidates.number_of_initial_light_candidates;
+    int initial_nb_bsdf_cand = di.initial_candidates.number_of_initial_bsdf_candidates;
+    const bool low_res = do_render_low_resolution(rd.render_settings);
+    int nb_light_candidates = low_res ? b2_min(1, initial_nb_light_cand) : initial_nb_light_cand;
+    int nb_bsdf_candidates = low_res ? b2_min(1, initial_nb_bsdf_cand) : initial_nb_bsdf_cand;
+    float envmap_candidate_probability = 0.0f;
+    if (rd.world_settings.ambient_light_type == 2)
+    {
+        if (rd.buffers.emissive_triangles_count == 0)
+            envmap_candidate_probability = 1.0f;
+        else
+            envmap_candidate_probability = di.initial_candidates.envmap_candidate_probability;
+    }
+
+    DiReservoir reservoir;
+    reservoir.init();
+
+    /* ---- light candidates ---- */
+    for (int i = 0; i < nb_light_candidates; i++)
+    {
+        Rgb sample_radiance = rgb(0.0f);
+        float sample_cosine_term = 0.0f;
+        float light_pdf_area_measure = 0.0f;
+        float distance_to_light = 0.0f;
+        V3 to_light_direction = v3(0.0f);
+
+        DiSample light_sample = sample_fresh_light_candidate<V>(ctx, envmap_candidate_probability, hit, sample_radiance, sample_cosine_term, light_pdf_area_measure, rng);
+        to_light_direction = di_light_sample_direction(rd, light_sample, hit.inter_point, distance_to_light);
+
+        if (light_sample.target_function == B2_LIGHT_DOESNT_CONTRIBUTE_ENOUGH)
+            continue;
+
+        float candidate_weight = 0.0f;
+        if (sample_cosine_term > 0.0f && light_pdf_area_measure > 0.0f)
+        {
+            float bsdf_pdf_solid_angle;
+            int incident_light_info = B2_LOBE_NO_INFO; /* uninitialised in the reference (InitialCandidates.h:226) */
+            BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, to_light_direction, &incident_light_info, &payload.volume_state, false, &payload.material,
+                                         payload.bounce, payload.accumulated_roughness);
+            (void)bsdf_eval<V>(rd, bctx, bsdf_pdf_solid_angle);
+
+            DiSurface surface = surface_from_hit(hit, payload, view_direction);
+            float target_function = di_target_function<V, false>(ctx, light_sample, surface);
+            if (bsdf_pdf_solid_angle <= 0.0f || !check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, target_function / light_pdf_area_measure / bsdf_pdf_solid_angle))
+                target_function = 0.0f;
+            else
+            {
+                float light_pdf_solid_angle;
+                if (light_sample.is_envmap_sample())
+                    light_pdf_solid_angle = light_pdf_area_measure;
+                else
+                {
+                    V3 light_normal = triangle_normal_not_normalized(rd, light_sample.emissive_triangle_index);
+                    float normal_length = length(light_normal);
+                    light_normal = light_normal / normal_length;
+                    light_pdf_solid_angle = area_to_solid_angle_pdf(light_pdf_area_measure / (1.0f - envmap_candidate_probability), distance_to_light,
+                                                                    cosine_term_at_light_source(light_normal, -to_light_direction));
+                    light_pdf_solid_angle *= (1.0f - envmap_candidate_probability);
+                }
+                float mis_weight = balance_heuristic(light_pdf_solid_angle, (float)nb_light_candidates, bsdf_pdf_solid_angle, (float)nb_bsdf_candidates);
+                candidate_weight = mis_weight * target_function / light_pdf_area_measure;
+                light_sample.target_function = target_function;
+            }
+        }
+        reservoir.add_one_candidate(light_sample, candidate_weight, rng);
+    }
+
+    /* ---- BSDF candidates ---- */
+    for (int i = 0; i < nb_bsdf_candidates; i++)
+    {
+        float bsdf_sample_pdf_solid_angle = 0.0f;
+        V3 bsdf_sampled_direction;
+        int sampled_lobe_info = B2_LOBE_NO_INFO;
+        BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, v3(0.0f), &sampled_lobe_info, &payload.volume_state, false, &payload.material, 0,
+                                     payload.accumulated_roughness);
+        (void)bsdf_sample<V>(rd, bctx, bsdf_sampled_direction, bsdf_sample_pdf_solid_angle, rng);
+
+        if (bsdf_sample_pdf_solid_angle > 0.0f)
+        {
+            LightRayHit light_hit;
+            bool hit_found = bsdf_light_sample_ray(ctx, hit.inter_point, bsdf_sampled_direction, 1.0e35f, light_hit, hit.primitive_index);
+            if (hit_found && !is_black(light_hit.emission))
+            {
+                DiSurface surface = surface_from_hit(hit, payload, view_direction);
+                DiSample bsdf_RIS_sample = di_sample_defaults();
+                bsdf_RIS_sample.emissive_triangle_index = light_hit.prim;
+                bsdf_RIS_sample.point_on_light_source = hit.inter_point + bsdf_sampled_direction * light_hit.distance;
+                bsdf_RIS_sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+                bsdf_RIS_sample.or_flags(sampled_lobe_info);
+                bsdf_RIS_sample.target_function = di_target_function<V, false>(ctx, bsdf_RIS_sample, surface);
+
+                float light_pdf_solid_angle = 0.0f;
+                bool refraction_sampled = dot(bsdf_sampled_direction, hit.shading_normal) < 0.0f;
+                if (!refraction_sampled)
+                    light_pdf_solid_angle = pdf_of_emissive_triangle_hit_solid_angle<V>(rd, light_hit, bsdf_sampled_direction);
+
+                float target_function = bsdf_RIS_sample.target_function;
+                if (bsdf_sample_pdf_solid_angle <= 0.0f || !check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, target_function / light_pdf_solid_angle / bsdf_sample_pdf_solid_angle))
+                    continue;
+
+                light_pdf_solid_angle *= (1.0f - envmap_candidate_probability);
+                float mis_weight = balance_heuristic(bsdf_sample_pdf_solid_angle, (float)nb_bsdf_candidates, light_pdf_solid_angle, (float)nb_light_candidates);
+
+                float bsdf_sample_pdf_area_measure = bsdf_sample_pdf_solid_angle;
+                bsdf_sample_pdf_area_measure /= (light_hit.distance * light_hit.distance);
+                bsdf_sample_pdf_area_measure *= cosine_term_at_light_source(light_hit.geometric_normal, -bsdf_sampled_direction);
+
+                float candidate_weight = mis_weight * target_function / bsdf_sample_pdf_area_measure;
+                reservoir.add_one_candidate(bsdf_RIS_sample, candidate_weight, rng);
+            }
+            else if (!hit_found && rd.world_settings.ambient_light_type == 2)
+            {
+                if (dot(hit.shading_normal, bsdf_sampled_direction) > 0.0f)
+                {
+                    float envmap_pdf;
+                    (void)envmap_eval<V>(rd.world_settings, bsdf_sampled_direction, envmap_pdf);
+
+                    DiSurface surface = surface_from_hit(hit, payload, view_direction);
+                    DiSample bsdf_RIS_sample = di_sample_defaults();
+                    bsdf_RIS_sample.emissive_triangle_index = -1;
+                    bsdf_RIS_sample.point_on_light_source = mat3_mul_vec(rd.world_settings.world_to_envmap_matrix, bsdf_sampled_direction);
+                    bsdf_RIS_sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+                    bsdf_RIS_sample.or_flags(B2_DI_FLAGS_ENVMAP_SAMPLE);
+                    bsdf_RIS_sample.or_flags(sampled_lobe_info);
+                    bsdf_RIS_sample.target_function = di_target_function<V, false>(ctx, bsdf_RIS_sample, surface);
+
+                    float target_function = bsdf_RIS_sample.target_function;
+                    if (bsdf_sample_pdf_solid_angle <= 0.0f || !check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, target_function / bsdf_sample_pdf_solid_angle))
+                        continue;
+
+                    envmap_pdf *= envmap_candidate_probability;
+                    float mis_weight = balance_heuristic(bsdf_sample_pdf_solid_angle, (float)nb_bsdf_candidates, envmap_pdf, (float)nb_light_candidates);
+                    float candidate_weight = mis_weight * target_function / bsdf_sample_pdf_solid_angle;
+                    reservoir.add_one_candidate(bsdf_RIS_sample, candidate_weight, rng);
+                }
+            }
+        }
+    }
+
+    reservoir.end();
+    reservoir.M = 1;
+    return reservoir;
+}
+
+template <class V>
+B2_HD bool restir_pass_prologue(const b2pt_render_data& rd, uint32_t x, uint32_t y, uint32_t& pixel_index)
+{
+    const b2pt_int2 res = rd.render_settings.render_resolution;
+    if (x >= (uint32_t)res.x || y >= (uint32_t)res.y)
+        return false;
+    pixel_index = x + y * res.x;
+    return true;
+}
+
+template <class V>
+B2_HD void restir_di_initial_candidates_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    if (rd.buffers.emissive_triangles_count == 0 && rd.world_settings.ambient_light_type != 2)
+        return;
+    uint32_t pixel_index;
+    if (!restir_pass_prologue<V>(rd, x, y, pixel_index))
+        return;
+
+    Rng rng = make_rng(pixel_seed(rd, pixel_index));
+    if (!rd.aux_buffers.pixel_active[pixel_index] || rd.g_buffer.first_hit_prim_index[pixel_index] == -1)
+        return;
+
+    HitInfo hit = hit_info_defaults();
+    hit.geometric_normal = unpack_normal_oct24(rd.g_buffer.geometric_normals[pixel_index]);
+    hit.shading_normal = unpack_normal_oct24(rd.g_buffer.shading_normals[pixel_index]);
+    hit.inter_point = load_v3(rd.g_buffer.primary_hit_position, pixel_index);
+    hit.primitive_index = rd.g_buffer.first_hit_prim_index[pixel_index];
+
+    Payload payload;
+    payload.init();
+    payload.material = unpack_material(load_packed_material(rd.g_buffer.materials, pixel_index));
+    reconstruct_first_hit<V>(payload.volume_state, payload.material, rd.buffers.material_indices, hit.primitive_index, rng);
+
+    V3 cam = v3(rd.current_camera.position.x, rd.current_camera.position.y, rd.current_camera.position.z);
+    V3 view_direction = normalize(cam - hit.inter_point);
+    DiReservoir initial_candidates_reservoir = sample_initial_candidates<V>(ctx, payload, hit, view_direction, rng);
+
+    di_visibility_test_kill_reservoir(ctx, initial_candidates_reservoir, hit.inter_point, hit.primitive_index);
+    di_store(rd, rd.render_settings.restir_di_settings.initial_candidates.output_reservoirs, (int)pixel_index, initial_candidates_reservoir);
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* temporal reuse (TemporalReuse.h) */
+template <class V>
+B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    uint32_t center_pixel_index;
+    if (!restir_pass_prologue<V>(rd, x, y, center_pixel_index))
+        return;
+    if (!rd.aux_buffers.pixel_active[center_pixel_index] || rd.g_buffer.first_hit_prim_index[center_pixel_index] == -1)
+        return;
+
+    Rng rng = make_rng(pixel_seed(rd, center_pixel_index));
+
+    if (di.common_temporal_pass.temporal_buffer_clear_requested)
+    {
+        DiReservoir empty;
+        empty.init();
+        di_store(rd, di.temporal_pass.input_reservoirs, (int)center_pixel_index, empty);
+    }
+
+    DiSurface center_pixel_surface = get_pixel_surface<V>(rd, (int)center_pixel_index, false, rng);
+    DiReservoir initial_candidates_reservoir = di_load(rd, di.initial_candidates.output_reservoirs, (int)center_pixel_index);
+
+    int temporal_neighbor_pixel_index = find_temporal_neighbor_index<V>(rd, load_v3(rd.g_buffer.primary_hit_position, center_pixel_index), center_pixel_surface.shading_normal,
+                                                                        (int)center_pixel_index, rng).x;
+    if (temporal_neighbor_pixel_index == -1 || rd.render_settings.freeze_random)
+    {
+        di_store(rd, di.temporal_pass.output_reservoirs, (int)center_pixel_index, initial_candidates_reservoir);
+        return;
+    }
+
+    DiReservoir temporal_neighbor_reservoir = di_load(rd, di.temporal_pass.input_reservoirs, temporal_neighbor_pixel_index);
+    if (temporal_neighbor_reservoir.M == 0)
+    {
+        di_store(rd, di.temporal_pass.output_reservoirs, (int)center_pixel_index, initial_candidates_reservoir);
+        return;
+    }
+
+    DiReservoir out;
+    out.init();
+    DiSurface temporal_neighbor_surface = get_pixel_surface<V>(rd, temporal_neighbor_pixel_index, use_prev_frame_g_buffer<V>(rd.render_settings), rng);
+    if (mat_is_emissive(temporal_neighbor_surface.material))
+    {
+        di_store(rd, di.temporal_pass.output_reservoirs, (int)center_pixel_index, initial_candidates_reservoir);
+        return;
+    }
+
+    /* pairwise MIS, TemporalMISWeight.h:163-254 */
+    float mc = 0.0f;
+    if (temporal_neighbor_reservoir.M > 0)
+    {
+        float target_function_at_center = 0.0f;
+        if (temporal_neighbor_reservoir.UCW > 0.0f)
+            target_function_at_center = di_target_function<V, true>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface);
+
+        float target_function_at_neighbor = temporal_neighbor_reservoir.sample.target_function;
+        bool use_confidence_weights = di.use_confidence_weights != 0;
+        float temporal_neighbor_M = use_confidence_weights ? (float)temporal_neighbor_reservoir.M : 1.0f;
+        float center_reservoir_M = use_confidence_weights ? (float)initial_candidates_reservoir.M : 1.0f;
+        float neighbors_confidence_sum = use_confidence_weights ? (float)temporal_neighbor_reservoir.M : 1.0f;
+
+        float nume = target_function_at_neighbor * temporal_neighbor_M;
+        float denom = target_function_at_neighbor * neighbors_confidence_sum + target_function_at_center * center_reservoir_M;
+        float mi = denom == 0.0f ? 0.0f : (nume / denom);
+
+        float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, initial_candidates_reservoir.sample, temporal_neighbor_surface);
+        float target_function_center_sample_at_center = initial_candidates_reservoir.sample.target_function;
+        float nume_mc = target_function_center_sample_at_center * center_reservoir_M;
+        float denom_mc = target_function_center_sample_at_neighbor * neighbors_confidence_sum + target_function_center_sample_at_center * center_reservoir_M;
+        float confidence_multiplier = 1.0f;
+        if (use_confidence_weights)
+            confidence_multiplier = temporal_neighbor_M / neighbors_confidence_sum;
+        if (denom_mc != 0.0f)
+            mc += nume_mc / denom_mc * confidence_multiplier;
+
+        if (out.combine_with(temporal_neighbor_reservoir, mi, target_function_at_center, 1.0f, rng))
+            out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+    }
+
+    float initial_candidates_mis_weight = mc == 0.0f ? 1.0f : mc;
+    if (out.combine_with(initial_candidates_reservoir, initial_candidates_mis_weight, initial_candidates_reservoir.sample.target_function, 1.0f, rng))
+        out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+
+    out.end_with_normalization(1.0f, 1.0f);
+    if (di.m_cap > 0)
+        out.M = b2_min(out.M, di.m_cap);
+    di_store(rd, di.temporal_pass.output_reservoirs, (int)center_pixel_index, out);
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* spatial reuse (SpatialReuse.h) */
+template <class V>
+B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    uint32_t center_pixel_index;
+    if (!restir_pass_prologue<V>(rd, x, y, center_pixel_index))
+        return;
+    if (!rd.aux_buffers.pixel_active[center_pixel_index] || rd.g_buffer.first_hit_prim_index[center_pixel_index] == -1)
+        return;
+
+    unsigned int seed;
+    if (rd.render_settings.freeze_random)
+        seed = wang_hash(center_pixel_index + 1);
+    else if (restir_gi_coalesced_spatial_reuse(rd))
+        seed = wang_hash((rd.render_settings.sample_number + 1) * rd.random_number);
+    else
+        seed = wang_hash(((center_pixel_index + 1) * (rd.render_settings.sample_number + 1)) * rd.random_number);
+    Rng rng = make_rng(seed);
+
+    const void* input_reservoir_buffer = di.spatial_pass.input_reservoirs;
+    DiReservoir out;
+    out.init();
+    SpatialLocal local = spatial_local_from(rd);
+
+    DiReservoir center_pixel_reservoir = di_load(rd, input_reservoir_buffer, (int)center_pixel_index);
+    if ((center_pixel_reservoir.M <= 1) && di.common_spatial_pass.do_disocclusion_reuse_boost)
+        local.reuse_neighbor_count = di.common_spatial_pass.disocclusion_reuse_count;
+
+    DiSurface center_pixel_surface = get_pixel_surface<V>(rd, (int)center_pixel_index, false, rng);
+    setup_adaptive_directional_spatial_reuse(rd, local, center_pixel_index, rng);
+
+    int neighbor_heuristics_cache = 0;
+    int valid_neighbors_count = 0;
+    int valid_neighbors_M_sum = 0;
+    count_valid_neighbors(rd, local, center_pixel_surface, (int)center_pixel_index, (int)x, (int)y, false, input_reservoir_buffer, valid_neighbors_count, valid_neighbors_M_sum,
+                          neighbor_heuristics_cache);
+
+    PairwiseMis mis;
+    mis.mc = 0.0f;
+    Rng spatial_neighbors_rng = make_rng(local.rng_seed);
+
+    int reused_neighbors_count = local.reuse_neighbor_count;
+    int start_index = 0;
+    if (valid_neighbors_M_sum == 0)
+        start_index = reused_neighbors_count;
+    for (int neighbor_index = start_index; neighbor_index < reused_neighbors_count + 1; neighbor_index++)
+    {
+        if (neighbor_index < reused_neighbors_count && reused_neighbors_count <= 32)
+        {
+            if ((neighbor_heuristics_cache & (1 << neighbor_index)) == 0)
+            {
+                spatial_neighbor_advance_rng(rd, spatial_neighbors_rng);
+                continue;
+            }
+        }
+        int neighbor_pixel_index = get_spatial_neighbor_pixel_index(rd, local, neighbor_index, (int)x, (int)y, spatial_neighbors_rng);
+        if (neighbor_pixel_index == -1)
+            continue;
+        if (neighbor_index < reused_neighbors_count && reused_neighbors_count > 32)
+            if (!check_neighbor_similarity_heuristics(rd, neighbor_pixel_index, (int)center_pixel_index, center_pixel_surface.shading_point, normal_for_rejection_heuristic(rd, center_pixel_surface), false))
+                continue;
+
+        DiReservoir neighbor_reservoir = di_load(rd, input_reservoir_buffer, neighbor_pixel_index);
+        float target_function_at_center = 0.0f;
+        bool do_neighbor_target_function_visibility = do_include_spatial_visibility_term(rd, local, neighbor_index);
+        if (neighbor_reservoir.UCW > 0.0f)
+        {
+            if (neighbor_index == reused_neighbors_count)
+                target_function_at_center = neighbor_reservoir.sample.target_function;
+            else
+                target_function_at_center = di_target_function<V, false>(ctx, neighbor_reservoir.sample, center_pixel_surface);
+        }
+
+        bool update_mc = center_pixel_reservoir.M > 0 && center_pixel_reservoir.UCW > 0.0f;
+        float mis_weight = mis.weight<V>(ctx, neighbor_reservoir.M, neighbor_reservoir.sample.target_function, center_pixel_reservoir.M, center_pixel_reservoir.sample.target_function,
+                                         center_pixel_reservoir.sample, target_function_at_center, neighbor_pixel_index, false, valid_neighbors_count, valid_neighbors_M_sum, update_mc,
+                                         neighbor_index == reused_neighbors_count, true, rng);
+
+        if (out.combine_with(neighbor_reservoir, mis_weight, target_function_at_center, 1.0f, rng))
+        {
+            if (do_neighbor_target_function_visibility)
+                out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+            else if (neighbor_index == reused_neighbors_count)
+                out.sample.or_flags((int)(neighbor_reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED));
+            else
+                out.sample.flags &= ~(uint32_t)B2_DI_FLAGS_UNOCCLUDED;
+        }
+    }
+
+    out.end_with_normalization(1.0f, 1.0f);
+
+    bool not_last_spatial_pass = di.common_spatial_pass.number_of_passes - 1 != di.common_spatial_pass.spatial_pass_index;
+    if (di.common_temporal_pass.do_temporal_reuse_pass || not_last_spatial_pass)
+        di_visibility_test_kill_reservoir(ctx, out, center_pixel_surface.shading_point, center_pixel_surface.primitive_index);
+
+    if (di.m_cap > 0)
+        out.M = b2_min(out.M, di.m_cap);
+    di_store(rd, di.spatial_pass.output_reservoirs, (int)center_pixel_index, out);
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* fused spatiotemporal reuse (FusedSpatiotemporalReuse.h) */
+template <class V>
+B2_HD void restir_di_spatiotemporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    uint32_t center_pixel_index;
+    if (!restir_pass_prologue<V>(rd, x, y, center_pixel_index))
+        return;
+    if (!rd.aux_buffers.pixel_active[center_pixel_index] || rd.g_buffer.first_hit_prim_index[center_pixel_index] == -1)
+        return;
+
+    unsigned int seed = rd.render_settings.freeze_random ? wang_hash(center_pixel_index + 1) : wang_hash(((center_pixel_index + 1) * (rd.render_settings.sample_number + 1)) ^ rd.random_number);
+    Rng rng = make_rng(seed);
+
+    SpatialLocal local = spatial_local_from(rd);
+    local.rng_seed = rng.next_u32();
+
+    if (di.common_temporal_pass.temporal_buffer_clear_requested)
+    {
+        DiReservoir empty;
+        empty.init();
+        di_store(rd, di.temporal_pass.input_reservoirs, (int)center_pixel_index, empty);
+    }
+
+    DiSurface center_pixel_surface = get_pixel_surface<V>(rd, (int)center_pixel_index, false, rng);
+    const bool prev_gbuffer = use_prev_frame_g_buffer<V>(rd.render_settings);
+
+    /* load_spatiotemporal_neighbor_data (:73-104) */
+    DiReservoir temporal_neighbor_reservoir;
+    temporal_neighbor_reservoir.init();
+    Int3 temporal = find_temporal_neighbor_index<V>(rd, load_v3(rd.g_buffer.primary_hit_position, center_pixel_index), center_pixel_surface.shading_normal, (int)center_pixel_index, rng);
+    if (!(temporal.x == -1 || rd.render_settings.freeze_random))
+    {
+        temporal_neighbor_reservoir = di_load(rd, di.temporal_pass.input_reservoirs, temporal.x);
+        if (temporal_neighbor_reservoir.M != 0)
+        {
+            /* the surface is only consumed by bias-correction modes other than pairwise MIS; its RNG side effect
+             * (wavelength draw for dispersive glass) cannot occur because dispersive scenes are refused */
+        }
+    }
+    if ((temporal.x == -1 || temporal_neighbor_reservoir.M <= 1) && di.common_spatial_pass.do_disocclusion_reuse_boost)
+        local.reuse_neighbor_count = di.common_spatial_pass.disocclusion_reuse_count;
+
+    setup_adaptive_directional_spatial_reuse(rd, local, center_pixel_index, rng);
+
+    int neighbor_heuristics_cache = 0;
+    int valid_neighbors_count = 0;
+    int valid_neighbors_M_sum = 0;
+    count_valid_neighbors(rd, local, center_pixel_surface, (int)center_pixel_index, temporal.y, temporal.z, prev_gbuffer, di.spatial_pass.input_reservoirs, valid_neighbors_count,
+                          valid_neighbors_M_sum, neighbor_heuristics_cache);
+    if (temporal.x != -1 && temporal_neighbor_reservoir.M > 0)
+    {
+        valid_neighbors_count++;
+        valid_neighbors_M_sum += temporal_neighbor_reservoir.M;
+    }
+
+    DiReservoir out;
+    out.init();
+    DiReservoir initial_candidates_reservoir = di_load(rd, di.initial_candidates.output_reservoirs, (int)center_pixel_index);
+    PairwiseMis mis;
+    mis.mc = 0.0f;
+    const bool update_mc = initial_candidates_reservoir.M > 0 && initial_candidates_reservoir.UCW > 0.0f;
+
+    if (temporal.x != -1)
+    {
+        if (temporal_neighbor_reservoir.M > 0)
+        {
+            float target_function_at_center = 0.0f;
+            if (temporal_neighbor_reservoir.UCW > 0.0f)
+                target_function_at_center = di_target_function<V, true>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface);
+
+            float w = mis.weight<V>(ctx, temporal_neighbor_reservoir.M, temporal_neighbor_reservoir.sample.target_function, initial_candidates_reservoir.M,
+                                    initial_candidates_reservoir.sample.target_function, initial_candidates_reservoir.sample, target_function_at_center, temporal.x, prev_gbuffer,
+                                    valid_neighbors_count, valid_neighbors_M_sum, update_mc, false, false, rng);
+            if (out.combine_with(temporal_neighbor_reservoir, w, target_function_at_center, 1.0f, rng))
+                out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+        }
+    }
+
+    const void* spatial_input_reservoir_buffer = di.spatial_pass.input_reservoirs;
+    Rng spatial_neighbors_rng = make_rng(local.rng_seed);
+    int reused_neighbors_count = local.reuse_neighbor_count;
+    int start_index = 0;
+    if (valid_neighbors_M_sum == 0)
+        start_index = reused_neighbors_count;
+    for (int spatial_neighbor_index = start_index; spatial_neighbor_index < reused_neighbors_count + 1; spatial_neighbor_index++)
+    {
+        if (spatial_neighbor_index < reused_neighbors_count && reused_neighbors_count <= 32)
+            if ((neighbor_heuristics_cache & (1 << spatial_neighbor_index)) == 0)
+            {
+                spatial_neighbor_advance_rng(rd, spatial_neighbors_rng);
+                continue;
+            }
+
+        int neighbor_pixel_index = -1;
+        if (spatial_neighbor_index == reused_neighbors_count)
+            neighbor_pixel_index = (int)center_pixel_index;
+        else
+            neighbor_pixel_index = get_spatial_neighbor_pixel_index(rd, local, spatial_neighbor_index, temporal.y, temporal.z, spatial_neighbors_rng);
+        if (neighbor_pixel_index == -1)
+            continue;
+
+        if (spatial_neighbor_index < reused_neighbors_count && reused_neighbors_count > 32)
+            if (!check_neighbor_similarity_heuristics(rd, neighbor_pixel_index, (int)center_pixel_index, center_pixel_surface.shading_point, normal_for_rejection_heuristic(rd, center_pixel_surface), prev_gbuffer))
+                continue;
+
+        DiReservoir neighbor_reservoir;
+        if (spatial_neighbor_index == reused_neighbors_count)
+            neighbor_reservoir = initial_candidates_reservoir;
+        else
+            neighbor_reservoir = di_load(rd, spatial_input_reservoir_buffer, neighbor_pixel_index);
+
+        float target_function_at_center = 0.0f;
+        bool do_neighbor_target_function_visibility = do_include_spatial_visibility_term(rd, local, spatial_neighbor_index);
+        if (neighbor_reservoir.UCW > 0.0f)
+        {
+            if (spatial_neighbor_index == reused_neighbors_count)
+                target_function_at_center = neighbor_reservoir.sample.target_function;
+            else
+                target_function_at_center = di_target_function<V, false>(ctx, neighbor_reservoir.sample, center_pixel_surface);
+        }
+
+        float mis_weight = mis.weight<V>(ctx, neighbor_reservoir.M, neighbor_reservoir.sample.target_function, initial_candidates_reservoir.M, initial_candidates_reservoir.sample.target_function,
+                                         initial_candidates_reservoir.sample, target_function_at_center, neighbor_pixel_index, prev_gbuffer, valid_neighbors_count, valid_neighbors_M_sum, update_mc,
+                                         spatial_neighbor_index == reused_neighbors_count, false, rng);
+
+        if (out.combine_with(neighbor_reservoir, mis_weight, target_function_at_center, 1.0f, rng))
+        {
+            if (do_neighbor_target_function_visibility)
+                out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+            else if (spatial_neighbor_index == reused_neighbors_count)
+                out.sample.or_flags((int)(neighbor_reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED));
+            else
+                out.sample.flags &= ~(uint32_t)B2_DI_FLAGS_UNOCCLUDED;
+        }
+    }
+
+    out.end_with_normalization(1.0f, 1.0f);
+
+    if (di.common_temporal_pass.do_temporal_reuse_pass || di.common_spatial_pass.number_of_passes - 1 != di.common_spatial_pass.spatial_pass_index)
+        di_visibility_test_kill_reservoir(ctx, out, center_pixel_surface.shading_point, center_pixel_surface.primitive_index);
+
+    if (di.m_cap > 0)
+        out.M = b2_min(out.M, di.m_cap);
+    di_store(rd, di.spatial_pass.output_reservoirs, (int)center_pixel_index, out);
+}
+
+template <class V>
+B2_HD void restir_di_pass_pixel(int pass, const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    switch (pass)
+    {
+    case B2_PASS_RESTIR_DI_INITIAL_CANDIDATES: restir_di_initial_candidates_pixel<V>(ctx, x, y); break;
+    case B2_PASS_RESTIR_DI_TEMPORAL: restir_di_temporal_pixel<V>(ctx, x, y); break;
+    case B2_PASS_RESTIR_DI_SPATIAL: restir_di_spatial_pixel<V>(ctx, x, y); break;
+    case B2_PASS_RESTIR_DI_SPATIOTEMPORAL: restir_di_spatiotemporal_pixel<V>(ctx, x, y); break;
+    default: break;
+    }
+}
+
 #endif

@@ -295,6 +295,23 @@ int main(int argc, char** argv)
         else if (a.variant == "c4") run_pass<B2VariantC4>(pass, rd, bvh, a);
 #endif
         else { std::fprintf(stderr, "unknown variant %s\n", a.variant.c_str()); std::exit(2); }
+        if (a.dump_per_sample && !a.dump.empty() && pass != B2_PASS_CAMERA_RAYS && pass != B2_PASS_MEGAKERNEL)
+        {
+            /* same files as oracle/ref_harness.cpp::dump_pass_reservoirs, transposed from the SoA planes to 36-byte records */
+            const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+            const char* name = nullptr;
+            const void* buffer = nullptr;
+            if (pass == B2_PASS_RESTIR_DI_INITIAL_CANDIDATES) { name = "initial"; buffer = di.initial_candidates.output_reservoirs; }
+            else if (pass == B2_PASS_RESTIR_DI_TEMPORAL) { name = "temporal"; buffer = di.temporal_pass.output_reservoirs; }
+            else { name = "output"; buffer = di.spatial_pass.output_reservoirs; }
+            std::vector<uint32_t> aos(n * 9);
+            const uint32_t* soa = reinterpret_cast<const uint32_t*>(buffer);
+            for (size_t i = 0; i < n; i++)
+                for (int p = 0; p < 9; p++)
+                    aos[i * 9 + p] = soa[p * n + i];
+            std::string file = std::string("restir_") + name + "_f" + std::to_string(frame);
+            dump_array(a.dump, file.c_str(), aos.data(), aos.size());
+        }
         if (pass == B2_PASS_CAMERA_RAYS && frame == 1)
         {
             dump_array(a.dump, "gbuffer_prim", g[0].prim.data(), n);
