@@ -808,6 +808,10 @@ B2_HD V3 sheen_ltc_sample(const b2pt_render_data& rd, const Mat& material, V3 lo
  * ------------------------------------------------------------------------------------------------------------ */
 B2_HD float medium_ior(const b2pt_render_data& rd, int material_index)
 {
+    /* material_index is -1 for a surface rebuilt from a G-buffer entry that holds no hit (ReSTIR neighbour whose
+     * previous-frame pixel missed): the reference then reads ior[-1] (undefined); the device treats it as air */
+    if (material_index < 0)
+        return 1.0f;
     return material_index == (int)B2_MAX_MATERIAL_INDEX ? 1.0f : rd.buffers.materials_buffer.ior[material_index];
 }
 

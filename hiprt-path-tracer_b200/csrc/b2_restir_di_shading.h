@@ -184,6 +184,12 @@ B2_HD DiSurface get_pixel_surface(const b2pt_render_data& rd, int pixel_index, b
 
 B2_HD V3 triangle_normal_not_normalized(const b2pt_render_data& rd, int triangle_index)
 {
+    /* A reservoir whose weights went NaN (0/0 candidate weight, see InitialCandidates.h:405-413 with a back-facing hit)
+     * keeps the default sample (triangle -1) but passes the `UCW <= 0` tests; the reference then reads
+     * triangles_indices[-3..-1] / material_indices[-1] (undefined, harmless on its host heap) and ends in a NaN ->
+     * pink pixel all the same. Never read out of bounds on the device: the NaN UCW still poisons the product. */
+    if (triangle_index < 0)
+        return v3(0.0f);
     V3 A = load_v3(rd.buffers.vertices_positions, rd.buffers.triangles_indices[triangle_index * 3 + 0]);
     V3 B = load_v3(rd.buffers.vertices_positions, rd.buffers.triangles_indices[triangle_index * 3 + 1]);
     V3 C = load_v3(rd.buffers.vertices_positions, rd.buffers.triangles_indices[triangle_index * 3 + 2]);
@@ -215,6 +221,8 @@ B2_HD Rgb di_light_sample_emission(const b2pt_render_data& rd, const DiSample& s
         float envmap_pdf;
         return envmap_eval<V>(rd.world_settings, sample_direction, envmap_pdf);
     }
+    if (sample.emissive_triangle_index < 0)
+        return rgb(0.0f); /* see triangle_normal_not_normalized */
     int material_index = rd.buffers.material_indices[sample.emissive_triangle_index];
     return load_rgb(rd.buffers.materials_buffer.emission, material_index);
 }

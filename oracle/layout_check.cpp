@@ -153,4 +153,10 @@ CAM(sensor_height); CAM(do_jittering);
 /* ReSTIR DI reservoir record: 36 bytes = 9 four-byte words (the SoA plane count used by the kernels) */
 static_assert(sizeof(ReSTIRDIReservoir) == 36 && offsetof(ReSTIRDIReservoir, sample) == 12 && offsetof(ReSTIRDISample, flags) == 20, "reservoir layout");
 
+/* b2_restir_di.h reads ReSTIR GI's common_spatial_pass.coalesced_spatial_reuse (the seed quirk of the DI spatial
+ * kernel) at the DI offset of the same field inside the opaque GI block: both structs start with ReSTIRCommonSettings */
+static_assert(offsetof(ReSTIRGISettings, common_spatial_pass) + offsetof(ReSTIRCommonSpatialPassSettings, coalesced_spatial_reuse) ==
+                  offsetof(b2pt_restir_di_settings, common_spatial_pass) + offsetof(b2pt_restir_spatial_common, coalesced_spatial_reuse),
+              "ReSTIR GI coalesced_spatial_reuse offset");
+
 int main() { return 0; }
