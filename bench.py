@@ -17,8 +17,9 @@ principled BSDF, 16 spp, NEE + BSDF MIS with power-proportional light sampling (
               a bounded pixel window of the same workload
 
 Multi-GPU (N > 1): the frame is partitioned into interleaved 64-row pixel bands (rank = band % N), scene replicated,
-no data-path collective inside a sample; the framebuffer bands are all-gathered with NCCL at the end of every step
-(inside the timed region). Total work is fixed => "scaling": "strong".
+no data-path collective inside a sample (ReSTIR DI variants all-gather the reservoir planes a reuse pass reads, once
+per frame); the framebuffer bands are all-gathered with NCCL at the end of every step (inside the timed region: the
+step's device time = the renderer's CUDA events + the all-gather's). Total work is fixed => "scaling": "strong".
 """
 import argparse
 import json
@@ -246,7 +247,7 @@ def main():
     r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
     r.set(nb_bounces=w["bounces"])
     if world > 1:
-        r.set_partition(rank, world)
+        r.set_partition(rank, world, torch, dist)
     info = r.scene_info()
 
     fb_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
@@ -261,20 +262,22 @@ def main():
         torch.cuda.synchronize()
 
     def step(e2e):
+        """Returns the device milliseconds of the step: the renderer's CUDA events on its stream (+ the all-gather's
+        events on torch's stream when N > 1; the two regions do not overlap)."""
         r.reset()
         r.set_host_seed(42)
         if e2e:
             r.reupload_scene()
         r.render(spp, sync=False)
-        if gather is not None:
-            gather()
+        gather_ms = gather() if gather is not None else 0.0
         if e2e:
             r.framebuffer(out=fb_np)
+        r.synchronize()
+        return r.last_render_ms() + gather_ms
 
     # ---- device-timed region (inputs resident in HBM) -------------------------------------------------------
     for _ in range(a.warmup):
         step(False)
-        r.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -283,9 +286,7 @@ def main():
     dev_ms = 0.0
     launches_before = sum(v["launches"] for v in r.pass_times().values())
     for _ in range(a.steps):
-        step(False)
-        r.synchronize()
-        dev_ms += r.last_render_ms()
+        dev_ms += step(False)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = sum(v["launches"] for v in r.pass_times().values()) - launches_before

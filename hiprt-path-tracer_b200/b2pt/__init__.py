@@ -72,10 +72,16 @@ SETTINGS_OFFSETS = {
     "envmap_intensity": (2088 + 24, "f"),
     "white_furnace_mode": (464 + 0, "B"),
 }
+FRAMEBUFFER_POINTER_OFFSET = None  # filled below from the C side (offsetof(b2pt_render_data, buffers.accumulated_ray_colors))
+_PTR = C.c_void_p
+EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64)
 _CT = {"i": C.c_int, "I": C.c_uint, "B": C.c_uint8, "f": C.c_float}
 
 
 def load_library():
+    global LIB_PATH
+    if os.environ.get("B2PT_LIB"):  # experiment builds (build.py: B2PT_BUILD_TAG)
+        LIB_PATH = Path(os.environ["B2PT_LIB"]).resolve()
     if not LIB_PATH.exists():
         raise B2ptError(f"{LIB_PATH} is missing: build it with `python hiprt-path-tracer_b200/build.py` "
                         "(there is no CPU fallback for the B200 path)")
@@ -84,6 +90,8 @@ def load_library():
     lib.b2pt_version_string.restype = C.c_char_p
     lib.b2pt_renderer_render_data.restype = C.c_void_p
     lib.b2pt_bvh_device_handle.restype = C.c_void_p
+    global FRAMEBUFFER_POINTER_OFFSET
+    FRAMEBUFFER_POINTER_OFFSET = lib.b2pt_render_data_framebuffer_offset()
     return lib
 
 
@@ -211,6 +219,54 @@ class Renderer:
 
     def reset(self):
         check(lib().b2pt_renderer_reset(self.handle))
+
+    # -- multi-GPU --------------------------------------------------------------------------------------------
+    def set_partition(self, rank, world, torch=None, dist=None):
+        """This renderer renders only rank's interleaved row bands (b2pt/partition.py). With ReSTIR DI (variant c4) the
+        reservoir planes a reuse pass reads are completed across ranks by an all-gather (torch.distributed) issued from
+        the C side's exchange callback right before that pass."""
+        from . import partition
+        self.rank, self.world = rank, world
+        self._exchange_cb = None
+        self.exchange_count = 0
+        cb = C.cast(None, EXCHANGE_FN)
+        if world > 1 and self.variant == "c4":
+            if torch is None or dist is None:
+                raise B2ptError("ReSTIR DI on several GPUs needs torch + torch.distributed for the reservoir exchange")
+
+            def exchange(user, ptr, nbytes):
+                planes = partition.device_tensor(torch, ptr, (9, self.height, self.width), "<i4")
+                partition.allgather_rows(planes, 1, rank, world, dist, torch)
+                torch.cuda.current_stream().synchronize()
+                self.exchange_count += 1
+
+            self._exchange_cb = cb = EXCHANGE_FN(exchange)
+        check(lib().b2pt_renderer_set_partition(self.handle, rank, world, cb, None))
+
+    def owned_pixels(self):
+        from . import partition
+        return len(partition.owned_rows(self.height, getattr(self, "rank", 0), getattr(self, "world", 1))) * self.width
+
+    def framebuffer_device_pointer(self):
+        return _PTR.from_address(self._rd + FRAMEBUFFER_POINTER_OFFSET).value
+
+    def make_gather(self, torch, dist):
+        """Returns gather(): all-gathers the framebuffer bands so every rank holds the whole frame (in place, in the
+        renderer's own framebuffer allocation). Waits for the renderer's stream first; returns the device ms it took."""
+        from . import partition
+        fb = partition.device_tensor(torch, self.framebuffer_device_pointer(), (self.height, self.width, 3), "<f4")
+        rank, world = self.rank, self.world
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def gather():
+            self.synchronize()
+            start.record()
+            partition.allgather_rows(fb, 0, rank, world, dist, torch)
+            stop.record()
+            stop.synchronize()
+            return start.elapsed_time(stop)
+
+        return gather
 
     # -- rendering --------------------------------------------------------------------------------------------
     def render(self, samples=1, sync=True):

@@ -1,0 +1,55 @@
+"""Multi-GPU partition of the frame: interleaved bands of BAND_ROWS pixel rows, band b -> rank b % world.
+
+Pure host logic over torch tensors (CPU or CUDA), so the same code runs under `gloo` on CPU in tests/ and under `nccl`
+on the B200 box. The reference has no multi-GPU path; the per-pixel passes are independent (CameraRays.h:95,
+Megakernel.h:35) and only the ReSTIR reuse passes read neighbouring pixels' reservoirs
+(kernels/ReSTIR/DI/SpatialReuse.h:142, FusedSpatiotemporalReuse.h:90,380,397), which is what `allgather_rows` completes.
+"""
+import numpy as np
+
+BAND_ROWS = 64  # == B2PT_BAND_ROWS in include/b2pt.h
+
+
+def owned_rows(height, rank, world):
+    """Row indices (ascending) of the bands rank owns."""
+    rows = np.arange(height)
+    return rows[(rows // BAND_ROWS) % world == rank]
+
+
+def allgather_rows(t, row_dim, rank, world, dist, torch, group=None):
+    """Completes `t` in place across ranks: every rank contributes the rows it owns along `row_dim` (size = frame
+    height) and receives everybody else's. Rows are packed to a contiguous send buffer (padded to the largest owner),
+    all-gathered, and scattered back -- one collective per call."""
+    if world == 1:
+        return t
+    height = t.shape[row_dim]
+    rows = [torch.as_tensor(owned_rows(height, k, world), device=t.device, dtype=torch.long) for k in range(world)]
+    max_rows = max(len(r) for r in rows)
+    if max_rows == 0:
+        return t
+    mine = t.index_select(row_dim, rows[rank])
+    pad_shape = list(mine.shape)
+    pad_shape[row_dim] = max_rows
+    send = torch.zeros(pad_shape, dtype=t.dtype, device=t.device)
+    send.narrow(row_dim, 0, len(rows[rank])).copy_(mine)
+    recv = torch.empty([world] + pad_shape, dtype=t.dtype, device=t.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(recv, send, group=group)
+    else:
+        parts = [recv[k] for k in range(world)]
+        dist.all_gather(parts, send, group=group)
+    for k in range(world):
+        if k != rank and len(rows[k]):
+            t.index_copy_(row_dim, rows[k], recv[k].narrow(row_dim, 0, len(rows[k])))
+    return t
+
+
+class _DevicePointer:
+    """Exposes a raw CUDA device pointer through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=3, strides=None)
+
+
+def device_tensor(torch, ptr, shape, typestr):
+    return torch.as_tensor(_DevicePointer(ptr, shape, typestr), device="cuda")

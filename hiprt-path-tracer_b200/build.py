@@ -19,8 +19,11 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
-OUT = PKG / "libb2pt.so"
-OBJ = PKG / "build"
+# Experiment builds: B2PT_BUILD_TAG=mb8 B2PT_EXTRA_DEFS="-DB2_MK_MIN_BLOCKS=8" -> libb2pt_mb8.so (load it with B2PT_LIB=...)
+TAG = os.environ.get("B2PT_BUILD_TAG", "")
+EXTRA_DEFS = os.environ.get("B2PT_EXTRA_DEFS", "").split()
+OUT = PKG / (f"libb2pt_{TAG}.so" if TAG else "libb2pt.so")
+OBJ = PKG / (f"build_{TAG}" if TAG else "build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-fno-fast-math", f"-I{ROOT / 'include'}", f"-I{CSRC}",
@@ -52,6 +55,7 @@ def enabled_features():
 
 def source_digest():
     h = hashlib.sha256()
+    h.update(" ".join(EXTRA_DEFS).encode())
     for p in sorted(list(CSRC.glob("*")) + list((ROOT / "include").glob("*.h")) + [Path(__file__), ROOT / "tools" / "traverse_selftest.cu"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
@@ -60,7 +64,7 @@ def source_digest():
 
 def compile_unit(unit, feats, log_dir):
     src, obj, extra = unit
-    cmd = ["nvcc", *ARCH, *COMMON, *feats, *extra, "-c", str(CSRC / src), "-o", str(OBJ / obj)]
+    cmd = ["nvcc", *ARCH, *COMMON, *feats, *EXTRA_DEFS, *extra, "-c", str(CSRC / src), "-o", str(OBJ / obj)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     (log_dir / (obj + ".log")).write_text(" ".join(cmd) + "\n" + res.stdout + res.stderr)
     if res.returncode != 0:
@@ -85,7 +89,7 @@ def build(force=False, jobs=None, verbose=True):
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     selftest = ["nvcc", *ARCH, "-O3", "-std=c++17", "-fmad=false", "-lineinfo", f"-I{ROOT / 'include'}", f"-I{CSRC}", "-diag-suppress", "821",
                 str(ROOT / "tools" / "traverse_selftest.cu"), str(CSRC / "b2_bvh_build.cpp"), "-Xcompiler", "-fopenmp", "-o", str(ROOT / "tools" / "traverse_selftest")]
-    res = subprocess.run(selftest, capture_output=True, text=True)
+    res = subprocess.run(selftest, capture_output=True, text=True) if not TAG else subprocess.CompletedProcess(selftest, 0)
     if res.returncode != 0:
         raise RuntimeError(f"traverse_selftest build failed:\n{res.stdout}\n{res.stderr}")
     stamp.write_text(digest)

@@ -162,9 +162,8 @@ __device__ __forceinline__ B2NodeRaw b2_load_node(const B2Node* nodes, uint32_t 
  * `stack` points to this thread's first of B2_STACK_ENTRIES 8-byte slots, `stack_stride` slots apart (on the GPU the
  * slots live in shared memory, entry-major, so the 32 lanes of a warp touch 32 consecutive 8-byte words).
  */
-template <bool ANY_HIT>
-B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int stack_stride, B2TraversalCounters* counters,
-                        unsigned int* faults = nullptr)
+B2_HD B2Hit b2_traverse_rt(const bool ANY_HIT, const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int stack_stride,
+                           B2TraversalCounters* counters, unsigned int* faults)
 {
     B2Hit best;
     best.t = -1.0f;
@@ -348,5 +347,31 @@ B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int
     if (counters) { counters->rays += 1; counters->nodes += n_nodes; counters->tris += n_tris; }
     return best;
 }
+
+template <bool ANY_HIT>
+B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int stack_stride, B2TraversalCounters* counters,
+                        unsigned int* faults = nullptr)
+{
+    return b2_traverse_rt(ANY_HIT, bvh, org, dir, t_max, skip_prim, stack, stack_stride, counters, faults);
+}
+
+#if defined(__CUDACC__)
+/* ONE out-of-line copy of the traversal per kernel (closest-hit and any-hit share it through a run-time flag): the
+ * per-pixel code calls the traversal from 5-7 places (main path, shadow rays of every NEE strategy, BSDF-sample rays)
+ * and inlining every one of them made the C2 MegaKernel 13.7k SASS instructions = 220 KB, far beyond the 32 KB L1.5
+ * instruction cache (ncu: `no_instruction` was the dominant stall, profiles/r01_ncu_c2_megakernel.md).
+ * Members are passed by value so the caller's context stays in registers. */
+static __device__ __noinline__ B2Hit b2_traverse_shared(bool any_hit, const B2Node* nodes, const B2Tri* tris, uint32_t node_count, float ox, float oy, float oz, float dx,
+                                                        float dy, float dz, float t_max, int skip_prim, uint64_t* stack, int stack_stride,
+                                                        B2TraversalCounters* counters, unsigned int* faults)
+{
+    B2BvhDevice bvh;
+    bvh.nodes = nodes;
+    bvh.tris = tris;
+    bvh.node_count = node_count;
+    bvh.tri_count = 0;
+    return b2_traverse_rt(any_hit, bvh, v3(ox, oy, oz), v3(dx, dy, dz), t_max, skip_prim, stack, stack_stride, counters, faults);
+}
+#endif
 
 #endif

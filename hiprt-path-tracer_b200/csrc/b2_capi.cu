@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -444,21 +445,44 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
     return B2PT_ERR_NO_VARIANT;
 }
 
-int b2pt_kernel_launch(b2pt_kernel* kernel, int, int, int width, int height, void** args, b2pt_stream stream)
+/* B2PT_MEGAKERNEL=tiles selects the one-thread-per-pixel MegaKernel (A/B measurements); default: persistent warps */
+static int megakernel_persistent_default()
 {
-    if (!kernel || !args || !args[0] || width <= 0 || height <= 0)
+    static int value = -1;
+    if (value < 0)
+    {
+        const char* e = std::getenv("B2PT_MEGAKERNEL");
+        value = (e && !std::strcmp(e, "tiles")) ? 0 : 1;
+    }
+    return value;
+}
+
+int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank, int world, void** args, b2pt_stream stream)
+{
+    if (!kernel || !args || !args[0] || width <= 0 || height <= 0 || world < 1 || rank < 0 || rank >= world)
     {
         b2_set_error("b2pt_kernel_launch: invalid argument");
         return B2PT_ERR_INVALID_ARGUMENT;
     }
     const b2pt_render_data* rd = reinterpret_cast<const b2pt_render_data*>(args[0]);
     cudaStream_t s = (cudaStream_t)stream;
+    B2LaunchGeom geom;
+    geom.width = width;
+    geom.height = height;
+    geom.rank = rank;
+    geom.world = world;
+    geom.persistent = megakernel_persistent_default();
     B2_CUDA(cudaEventRecord(kernel->start, s));
-    B2_CUDA(kernel->entry->launch(rd, width, height, s));
+    B2_CUDA(kernel->entry->launch(rd, &geom, s));
     B2_CUDA(cudaEventRecord(kernel->stop, s));
     kernel->timed = true;
     kernel->launches++;
     return B2PT_OK;
+}
+
+int b2pt_kernel_launch(b2pt_kernel* kernel, int, int, int width, int height, void** args, b2pt_stream stream)
+{
+    return b2pt_kernel_launch_rows(kernel, width, height, 0, 1, args, stream);
 }
 
 int b2pt_kernel_last_ms(b2pt_kernel* kernel, float* out_ms)

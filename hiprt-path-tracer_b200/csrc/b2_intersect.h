@@ -244,6 +244,17 @@ struct Ctx
 };
 
 /* HIPRTRenderSettings::do_render_low_resolution, RenderSettings.h */
+/* every ray of the per-pixel code goes through here: on the device one shared out-of-line traversal (b2_bvh.h) */
+B2_HD B2Hit b2_trace(const Ctx& ctx, bool any_hit, V3 origin, V3 direction, float t_max, int skip_prim)
+{
+#if defined(__CUDA_ARCH__) && !defined(B2_INLINE_TRAVERSAL)
+    return b2_traverse_shared(any_hit, ctx.bvh.nodes, ctx.bvh.tris, ctx.bvh.node_count, origin.x, origin.y, origin.z, direction.x, direction.y, direction.z, t_max,
+                              skip_prim, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults);
+#else
+    return b2_traverse_rt(any_hit, ctx.bvh, origin, direction, t_max, skip_prim, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults);
+#endif
+}
+
 B2_HD bool do_render_low_resolution(const b2pt_render_settings& s)
 {
     return s.wants_render_low_resolution && s.allow_render_low_resolution && s.accumulate;
@@ -318,7 +329,7 @@ B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload&
             b2_report_fault(ctx.faults, B2_FAULT_BOUNDARY_GUARD);
             return false;
         }
-        hit = b2_traverse<false>(ctx.bvh, origin, direction, 3.0e38f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults);
+        hit = b2_trace(ctx, false, origin, direction, 3.0e38f, last_hit_primitive_index);
         if (hit.prim < 0)
             return false;
 
@@ -367,7 +378,7 @@ B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload&
 /* true when something lies strictly before t_max - 1e-4 (opaque scenes) */
 B2_HD bool shadow_ray_occluded(const Ctx& ctx, V3 origin, V3 direction, float t_max, int last_hit_primitive_index)
 {
-    B2Hit hit = b2_traverse<true>(ctx.bvh, origin, direction, t_max - 1.0e-4f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults);
+    B2Hit hit = b2_trace(ctx, true, origin, direction, t_max - 1.0e-4f, last_hit_primitive_index);
     return hit.prim >= 0;
 }
 
@@ -385,7 +396,7 @@ struct LightRayHit
 B2_HD bool bsdf_light_sample_ray(const Ctx& ctx, V3 origin, V3 direction, float t_max, LightRayHit& out, int last_hit_primitive_index)
 {
     const b2pt_render_data& rd = *ctx.rd;
-    B2Hit hit = b2_traverse<false>(ctx.bvh, origin, direction, 3.0e38f, last_hit_primitive_index, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults);
+    B2Hit hit = b2_trace(ctx, false, origin, direction, 3.0e38f, last_hit_primitive_index);
     if (hit.prim < 0)
         return false;
     if (!(hit.t < t_max - 1.0e-4f))

@@ -2,10 +2,19 @@
 #ifndef B2_KERNEL_TABLE_H
 #define B2_KERNEL_TABLE_H
 
+#include "b2pt.h"
 #include "b2_bvh.h"
 #include "b2_frame_loop.h"
 
 #include <cuda_runtime.h>
+
+/* what a launch covers: the pixel rows of `rank`'s interleaved B2PT_BAND_ROWS-row bands of a width x height frame */
+struct B2LaunchGeom
+{
+    int width, height;
+    int rank, world;
+    int persistent; /* MegaKernel only: persistent warps with path regeneration (default) or one thread per pixel */
+};
 
 struct B2KernelEntry
 {
@@ -16,7 +25,7 @@ struct B2KernelEntry
     int later;
     int envmap;
     int counters;
-    cudaError_t (*launch)(const b2pt_render_data* rd, int width, int height, cudaStream_t stream);
+    cudaError_t (*launch)(const b2pt_render_data* rd, const B2LaunchGeom* geom, cudaStream_t stream);
 };
 
 /* defined once per flavour by b2_kernels.cu (compiled twice: -fmad=false / fast) */

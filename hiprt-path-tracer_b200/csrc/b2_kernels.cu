@@ -16,6 +16,9 @@
 #include "b2_kernel_table.h"
 #include "b2_kernels_body.h"
 
+#include <atomic>
+#include <mutex>
+
 #if defined(B2_FLAVOUR_PRECISE)
 #define B2_NS b2_precise
 #elif defined(B2_FLAVOUR_FAST)
@@ -27,27 +30,29 @@
 #define B2_TILE_W 8
 #define B2_TILE_H 8
 #define B2_BLOCK_THREADS (B2_TILE_W * B2_TILE_H)
+#define B2_BAND_ROWS B2PT_BAND_ROWS
+#define B2_WORK_COUNTER_SLOTS 256
+#define B2_MAX_DEVICES 64
+/* resident 64-thread blocks per SM the persistent MegaKernel is compiled for (caps registers at 65536 / (64 * N)) */
+#ifndef B2_MK_MIN_BLOCKS
+#define B2_MK_MIN_BLOCKS 6
+#endif
 
 namespace B2_NS
 {
 __device__ unsigned long long g_counters[3];
 __device__ unsigned int g_faults[B2_FAULT_COUNT];
 
-template <class V, int PASS>
-__global__ void __launch_bounds__(B2_BLOCK_THREADS) pass_kernel(const __grid_constant__ b2pt_render_data rd, int tiles_x)
+/* Pixel rows are partitioned across GPUs in interleaved bands of B2_BAND_ROWS rows (band b belongs to rank b % world);
+ * a launch covers the bands of one rank. `local_row` counts the rows of this rank's bands, top to bottom. */
+__device__ __forceinline__ uint32_t b2_global_row(uint32_t local_row, const B2LaunchGeom& g)
 {
-    __shared__ uint64_t stacks[B2_STACK_ENTRIES * B2_BLOCK_THREADS];
+    const uint32_t band_local = local_row / B2_BAND_ROWS;
+    return (band_local * (uint32_t)g.world + (uint32_t)g.rank) * B2_BAND_ROWS + local_row % B2_BAND_ROWS;
+}
 
-    const int tile = blockIdx.x;
-    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-    /* lane l of warp w: x = l & 7, y = 4 w + (l >> 3) */
-    const uint32_t x = tile_x * B2_TILE_W + (threadIdx.x & 7);
-    const uint32_t y = tile_y * B2_TILE_H + (threadIdx.x >> 3);
-
-    B2TraversalCounters local_counters;
-    local_counters.rays = local_counters.nodes = local_counters.tris = 0;
-
-    Ctx ctx;
+__device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd, uint64_t* stacks, B2TraversalCounters* counters, unsigned int* faults)
+{
     ctx.rd = &rd;
     if (rd.GPU_BVH != nullptr)
         ctx.bvh = *reinterpret_cast<const B2BvhDevice*>(rd.GPU_BVH);
@@ -59,35 +64,210 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) pass_kernel(const __grid_con
     }
     ctx.stack = stacks + threadIdx.x;
     ctx.stack_stride = B2_BLOCK_THREADS;
-    ctx.counters = V::COUNTERS ? &local_counters : nullptr;
-    ctx.faults = g_faults;
+    ctx.counters = counters;
+    ctx.faults = faults;
+}
+
+__device__ __forceinline__ void b2_flush_counters(const B2TraversalCounters& local_counters)
+{
+    unsigned long long r = local_counters.rays, n = local_counters.nodes, t = local_counters.tris;
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        r += __shfl_down_sync(0xFFFFFFFFu, r, off);
+        n += __shfl_down_sync(0xFFFFFFFFu, n, off);
+        t += __shfl_down_sync(0xFFFFFFFFu, t, off);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicAdd(&g_counters[0], r);
+        atomicAdd(&g_counters[1], n);
+        atomicAdd(&g_counters[2], t);
+    }
+}
+
+/* One thread per pixel, 8x8 tiles (CameraRays and the ReSTIR DI passes: a fixed, short amount of work per pixel). */
+template <class V, int PASS>
+__global__ void __launch_bounds__(B2_BLOCK_THREADS) pass_kernel(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x)
+{
+    __shared__ uint64_t stacks[B2_STACK_ENTRIES * B2_BLOCK_THREADS];
+
+    const int tile = blockIdx.x;
+    const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+    /* lane l of warp w: x = l & 7, y = 4 w + (l >> 3) */
+    const uint32_t x = tile_x * B2_TILE_W + (threadIdx.x & 7);
+    const uint32_t y = b2_global_row(tile_y * B2_TILE_H + (threadIdx.x >> 3), geom);
+
+    B2TraversalCounters local_counters;
+    local_counters.rays = local_counters.nodes = local_counters.tris = 0;
+
+    Ctx ctx;
+    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults);
 
     b2_run_pass_pixel<V>(PASS, ctx, x, y);
 
     if (V::COUNTERS)
+        b2_flush_counters(local_counters);
+}
+
+/*
+ * The MegaKernel as PERSISTENT warps with path regeneration. The grid is (SM count x resident blocks per SM). A warp
+ * fetches work one 8x4-pixel tile at a time from a global counter (one atomicAdd per tile): the tile's primary-miss
+ * pixels are finished on the spot by all of their lanes together (megakernel_primary_miss), its hit pixels go into a
+ * small per-warp queue in shared memory. A lane whose path ended -- Russian roulette, absorption, bounce limit, escape
+ * -- takes the next queued pixel at the top of the loop while the other lanes carry on with their bounce, so
+ * `megakernel_bounce` runs with (nearly) all 32 lanes holding a live surface hit until the work runs out. In the
+ * one-thread-per-pixel form the warp idled lanes until its longest path ended (6.2 of 32 lanes active on the C2
+ * Cornell frame, profiles/r01_ncu_c2_megakernel.md); handing out single pixels instead of tiles still spent a third of
+ * the bounce loop's lanes on primary misses (profiles/r01b_ncu_c2_megakernel.md).
+ * Per-pixel results do not depend on the schedule: every pixel owns its RNG stream and its framebuffer word.
+ */
+#define B2_QUEUE_SLOTS 64
+template <class V>
+__global__ void __launch_bounds__(B2_BLOCK_THREADS, B2_MK_MIN_BLOCKS) megakernel_persistent(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x,
+                                                                                             unsigned int total_tiles, unsigned int* work_counter)
+{
+    __shared__ uint64_t stacks[B2_STACK_ENTRIES * B2_BLOCK_THREADS];
+    __shared__ uint32_t queues[B2_BLOCK_THREADS / 32][B2_QUEUE_SLOTS];
+
+    B2TraversalCounters local_counters;
+    local_counters.rays = local_counters.nodes = local_counters.tris = 0;
+
+    Ctx ctx;
+    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults);
+
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int lanes_below = (1u << lane) - 1u;
+    uint32_t* queue = queues[threadIdx.x >> 5];
+    const int res_x = rd.render_settings.render_resolution.x, res_y = rd.render_settings.render_resolution.y;
+    PathState s;
+    bool alive = false;
+    /* warp-uniform */
+    bool exhausted = false;
+    unsigned int q_head = 0, q_count = 0;
+
+    while (true)
     {
-        unsigned long long r = local_counters.rays, n = local_counters.nodes, t = local_counters.tris;
-        for (int off = 16; off > 0; off >>= 1)
+        const unsigned int idle = __ballot_sync(0xFFFFFFFFu, !alive);
+        const unsigned int n_idle = __popc(idle);
+        while (q_count < n_idle && !exhausted)
         {
-            r += __shfl_down_sync(0xFFFFFFFFu, r, off);
-            n += __shfl_down_sync(0xFFFFFFFFu, n, off);
-            t += __shfl_down_sync(0xFFFFFFFFu, t, off);
+            unsigned int tile = 0;
+            if (lane == 0)
+                tile = atomicAdd(work_counter, 1u);
+            tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+            if (tile >= total_tiles)
+            {
+                exhausted = true;
+                break;
+            }
+            const uint32_t x = (tile % (unsigned int)tiles_x) * 8u + (lane & 7u);
+            const uint32_t y = b2_global_row((tile / (unsigned int)tiles_x) * 4u + (lane >> 3), geom);
+            bool is_hit = false;
+            if (x < (uint32_t)res_x && y < (uint32_t)res_y)
+            {
+                const uint32_t pixel_index = x + y * (uint32_t)res_x;
+                if (rd.aux_buffers.pixel_active[pixel_index])
+                {
+                    is_hit = rd.g_buffer.first_hit_prim_index[pixel_index] != -1;
+                    if (!is_hit)
+                        megakernel_primary_miss<V>(ctx, x, y, pixel_index);
+                }
+            }
+            const unsigned int hits = __ballot_sync(0xFFFFFFFFu, is_hit);
+            if (is_hit)
+                queue[(q_head + q_count + __popc(hits & lanes_below)) % B2_QUEUE_SLOTS] = x | (y << 16);
+            q_count += __popc(hits);
+            __syncwarp();
         }
-        if ((threadIdx.x & 31) == 0)
+        if (!alive)
         {
-            atomicAdd(&g_counters[0], r);
-            atomicAdd(&g_counters[1], n);
-            atomicAdd(&g_counters[2], t);
+            const unsigned int r = __popc(idle & lanes_below);
+            if (r < q_count)
+            {
+                const uint32_t packed = queue[(q_head + r) % B2_QUEUE_SLOTS];
+                alive = megakernel_begin<V>(ctx, packed & 0xFFFFu, packed >> 16, s);
+            }
+        }
+        {
+            const unsigned int taken = n_idle < q_count ? n_idle : q_count;
+            q_head = (q_head + taken) % B2_QUEUE_SLOTS;
+            q_count -= taken;
+        }
+        __syncwarp();
+        if (!__any_sync(0xFFFFFFFFu, alive))
+        {
+            if (exhausted && q_count == 0)
+                break;
+            continue;
+        }
+        if (alive)
+        {
+            if (!megakernel_bounce<V>(ctx, s))
+            {
+                megakernel_end(ctx, s);
+                alive = false;
+            }
         }
     }
+
+    if (V::COUNTERS)
+        b2_flush_counters(local_counters);
+}
+
+static int owned_rows(int height, const B2LaunchGeom& g)
+{
+    int rows = 0;
+    for (int band = g.rank; band * B2_BAND_ROWS < height; band += g.world)
+        rows += (height - band * B2_BAND_ROWS) < B2_BAND_ROWS ? (height - band * B2_BAND_ROWS) : B2_BAND_ROWS;
+    return rows;
 }
 
 template <class V, int PASS>
-cudaError_t launch_pass(const b2pt_render_data* rd, int width, int height, cudaStream_t stream)
+cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cudaStream_t stream)
 {
-    const int tiles_x = (width + B2_TILE_W - 1) / B2_TILE_W;
-    const int tiles_y = (height + B2_TILE_H - 1) / B2_TILE_H;
-    pass_kernel<V, PASS><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, tiles_x);
+    const B2LaunchGeom g = *geom;
+    const int rows = owned_rows(g.height, g);
+    if (rows == 0)
+        return cudaSuccess;
+    const int tiles_x = (g.width + B2_TILE_W - 1) / B2_TILE_W;
+    if (PASS == B2_PASS_MEGAKERNEL && g.persistent)
+    {
+        /* per instantiation and per device: resident blocks per SM, SM count, and a ring of work counters (a launch
+         * zeroes its own slot on its stream, so launches in flight on different streams never share a counter) */
+        struct PerDevice { int blocks_per_sm = 0, sm_count = 0; unsigned int* ring = nullptr; };
+        static PerDevice per_device[B2_MAX_DEVICES];
+        static std::mutex init_mutex;
+        static std::atomic<unsigned int> next_slot{ 0 };
+        int device = 0;
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess)
+            return e;
+        if (device < 0 || device >= B2_MAX_DEVICES)
+            return cudaErrorInvalidDevice;
+        PerDevice& pd = per_device[device];
+        {
+            std::lock_guard<std::mutex> lock(init_mutex);
+            if (!pd.ring)
+            {
+                e = cudaDeviceGetAttribute(&pd.sm_count, cudaDevAttrMultiProcessorCount, device);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pd.blocks_per_sm, megakernel_persistent<V>, B2_BLOCK_THREADS, 0);
+                if (e == cudaSuccess && pd.blocks_per_sm < 1) pd.blocks_per_sm = 1;
+                if (e == cudaSuccess) e = cudaMalloc(&pd.ring, B2_WORK_COUNTER_SLOTS * sizeof(unsigned int));
+                if (e != cudaSuccess)
+                    return e;
+            }
+        }
+        unsigned int* counter = pd.ring + (next_slot.fetch_add(1) % B2_WORK_COUNTER_SLOTS);
+        e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess)
+            return e;
+        const int sm_count = pd.sm_count, blocks_per_sm = pd.blocks_per_sm;
+        const unsigned int total_tiles = (unsigned int)tiles_x * (unsigned int)((rows + 3) / 4);
+        megakernel_persistent<V><<<sm_count * blocks_per_sm, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, total_tiles, counter);
+        return cudaGetLastError();
+    }
+    const int tiles_y = (rows + B2_TILE_H - 1) / B2_TILE_H;
+    pass_kernel<V, PASS><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x);
     return cudaGetLastError();
 }
 

@@ -484,79 +484,142 @@ B2_HD void reconstruct_first_hit(VolumeState& vs, const Mat& material, const int
         vs.sampled_wavelength = -sample_wavelength_uniformly(rng);
 }
 
-/* The MegaKernel pass for pixel (x, y): Megakernel.h:22-144 */
+/* The MegaKernel pass for pixel (x, y): Megakernel.h:22-144, cut into begin / one bounce / end so that the kernel can
+ * decide how threads and paths meet: the plain per-pixel loop (megakernel_pixel below: host port, tests) or the
+ * persistent warps of b2_kernels.cu that hand a finished lane the next pixel ("path regeneration") instead of idling
+ * it until the longest path of the warp ends. Per-pixel arithmetic and RNG order are identical either way. */
+struct PathState
+{
+    Payload payload;
+    HitInfo hit;
+    V3 ray_origin, ray_direction;
+    Rng rng;
+    uint32_t pixel_index;
+    int x, y;
+    int nb_bounces;
+    bool intersection_found;
+};
+
+/* Megakernel.h:33-79. Returns false when the pixel takes no sample (outside the frame / inactive). */
 template <class V>
-B2_HD void megakernel_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+B2_HD bool megakernel_begin(const Ctx& ctx, uint32_t x, uint32_t y, PathState& s)
 {
     const b2pt_render_data& rd = *ctx.rd;
     const b2pt_int2 res = rd.render_settings.render_resolution;
     if (x >= (uint32_t)res.x || y >= (uint32_t)res.y)
-        return;
+        return false;
     uint32_t pixel_index = x + y * res.x;
     if (!rd.aux_buffers.pixel_active[pixel_index])
-        return;
+        return false;
 
-    int nb_bounces = rd.render_settings.nb_bounces;
+    s.pixel_index = pixel_index;
+    s.x = (int)x;
+    s.y = (int)y;
+    s.nb_bounces = rd.render_settings.nb_bounces;
     if (do_render_low_resolution(rd.render_settings))
-        nb_bounces = b2_min(3, nb_bounces);
+        s.nb_bounces = b2_min(3, s.nb_bounces);
 
-    Rng rng = make_rng(pixel_seed(rd, pixel_index));
+    s.rng = make_rng(pixel_seed(rd, pixel_index));
 
-    HitInfo hit = hit_info_defaults();
-    hit.inter_point = load_v3(rd.g_buffer.primary_hit_position, pixel_index);
-    hit.geometric_normal = normalize(unpack_normal_oct24(rd.g_buffer.geometric_normals[pixel_index]));
-    hit.shading_normal = normalize(unpack_normal_oct24(rd.g_buffer.shading_normals[pixel_index]));
-    hit.primitive_index = rd.g_buffer.first_hit_prim_index[pixel_index];
+    s.hit = hit_info_defaults();
+    s.hit.inter_point = load_v3(rd.g_buffer.primary_hit_position, pixel_index);
+    s.hit.geometric_normal = normalize(unpack_normal_oct24(rd.g_buffer.geometric_normals[pixel_index]));
+    s.hit.shading_normal = normalize(unpack_normal_oct24(rd.g_buffer.shading_normals[pixel_index]));
+    s.hit.primitive_index = rd.g_buffer.first_hit_prim_index[pixel_index];
 
     V3 cam_pos = v3(rd.current_camera.position.x, rd.current_camera.position.y, rd.current_camera.position.z);
-    V3 ray_origin = v3(0.0f);
-    V3 ray_direction = normalize(-normalize(cam_pos - hit.inter_point));
+    s.ray_origin = v3(0.0f);
+    s.ray_direction = normalize(-normalize(cam_pos - s.hit.inter_point));
 
-    Payload payload;
-    payload.init();
-    payload.material = unpack_material(load_packed_material(rd.g_buffer.materials, pixel_index));
-    reconstruct_first_hit<V>(payload.volume_state, payload.material, rd.buffers.material_indices, hit.primitive_index, rng);
+    s.payload.init();
+    s.payload.material = unpack_material(load_packed_material(rd.g_buffer.materials, pixel_index));
+    reconstruct_first_hit<V>(s.payload.volume_state, s.payload.material, rd.buffers.material_indices, s.hit.primitive_index, s.rng);
 
-    bool intersection_found = hit.primitive_index != -1;
+    s.intersection_found = s.hit.primitive_index != -1;
+    return true;
+}
 
-    for (int& bounce = payload.bounce; bounce < nb_bounces + 1; bounce++)
+/* One iteration of the bounce loop (Megakernel.h:81-135). Returns true when the loop goes on to the next bounce. */
+template <class V>
+B2_HD bool megakernel_bounce(const Ctx& ctx, PathState& s)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    Payload& payload = s.payload;
+    HitInfo& hit = s.hit;
+    const int bounce = payload.bounce;
+    if (!(bounce < s.nb_bounces + 1))
+        return false;
+    if (payload.next_ray_state == B2_RAY_MISSED)
+        return false;
+
+    if (bounce > 0)
+        s.intersection_found = trace_main_path_ray<V>(ctx, s.ray_origin, s.ray_direction, payload, hit, hit.primitive_index, s.rng);
+
+    if (s.intersection_found)
     {
-        if (payload.next_ray_state != B2_RAY_MISSED)
+        if (bounce == 0)
+            store_denoiser_aovs(rd, s.pixel_index, hit.shading_normal, payload.material.base_color);
+
+        if (bounce > 0 || rd.render_settings.enable_direct)
         {
-            if (bounce > 0)
-                intersection_found = trace_main_path_ray<V>(ctx, ray_origin, ray_direction, payload, hit, hit.primitive_index, rng);
-
-            if (intersection_found)
-            {
-                if (bounce == 0)
-                    store_denoiser_aovs(rd, pixel_index, hit.shading_normal, payload.material.base_color);
-
-                if (bounce > 0 || rd.render_settings.enable_direct)
-                {
-                    payload.ray_color += estimate_direct_lighting<V>(ctx, payload, hit, -ray_direction, (int)x, (int)y, rng);
-                    sanity_check(rd, payload.ray_color, (int)x, (int)y);
-                }
-
-                bool valid_indirect_bounce = compute_next_indirect_bounce<V>(ctx, payload, hit, -ray_direction, ray_origin, ray_direction, rng);
-                if (!valid_indirect_bounce)
-                    break;
-            }
-            else
-            {
-                payload.ray_color += miss_gather_envmap<V>(rd, payload.throughput, ray_direction, payload.bounce, pixel_index);
-                payload.next_ray_state = B2_RAY_MISSED;
-                sanity_check(rd, payload.ray_color, (int)x, (int)y);
-            }
+            payload.ray_color += estimate_direct_lighting<V>(ctx, payload, hit, -s.ray_direction, s.x, s.y, s.rng);
+            sanity_check(rd, payload.ray_color, s.x, s.y);
         }
-        else
-            break;
+
+        bool valid_indirect_bounce = compute_next_indirect_bounce<V>(ctx, payload, hit, -s.ray_direction, s.ray_origin, s.ray_direction, s.rng);
+        if (!valid_indirect_bounce)
+            return false;
     }
+    else
+    {
+        payload.ray_color += miss_gather_envmap<V>(rd, payload.throughput, s.ray_direction, payload.bounce, s.pixel_index);
+        payload.next_ray_state = B2_RAY_MISSED;
+        sanity_check(rd, payload.ray_color, s.x, s.y);
+    }
+    payload.bounce++;
+    return true;
+}
 
-    if (!sanity_check(rd, payload.ray_color, (int)x, (int)y))
+/* Megakernel.h:137-144 */
+B2_HD void megakernel_end(const Ctx& ctx, PathState& s)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    if (!sanity_check(rd, s.payload.ray_color, s.x, s.y))
         return;
-
     rd.aux_buffers.still_one_ray_active[0] = 1;
-    accumulate_color(rd, payload.ray_color, pixel_index);
+    accumulate_color(rd, s.payload.ray_color, s.pixel_index);
+}
+
+/* What begin + bounce + end compute for an active pixel whose primary ray missed (first_hit_prim_index == -1): no RNG
+ * draw happens on that path (reconstruct_first_hit returns at once), the first loop iteration gathers the background
+ * with throughput 1 and the path ends. The persistent kernel runs this for the miss pixels of a freshly fetched tile
+ * with all of their lanes together instead of giving them a slot in the bounce loop. */
+template <class V>
+B2_HD void megakernel_primary_miss(const Ctx& ctx, uint32_t x, uint32_t y, uint32_t pixel_index)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    V3 inter_point = load_v3(rd.g_buffer.primary_hit_position, pixel_index);
+    V3 cam_pos = v3(rd.current_camera.position.x, rd.current_camera.position.y, rd.current_camera.position.z);
+    V3 ray_direction = normalize(-normalize(cam_pos - inter_point));
+    Rgb ray_color = rgb(0.0f);
+    ray_color += miss_gather_envmap<V>(rd, rgb(1.0f), ray_direction, 0, pixel_index);
+    sanity_check(rd, ray_color, (int)x, (int)y);
+    if (!sanity_check(rd, ray_color, (int)x, (int)y))
+        return;
+    rd.aux_buffers.still_one_ray_active[0] = 1;
+    accumulate_color(rd, ray_color, pixel_index);
+}
+
+template <class V>
+B2_HD void megakernel_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    PathState s;
+    if (!megakernel_begin<V>(ctx, x, y, s))
+        return;
+    while (megakernel_bounce<V>(ctx, s))
+    {
+    }
+    megakernel_end(ctx, s);
 }
 
 #endif

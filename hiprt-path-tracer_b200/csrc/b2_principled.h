@@ -583,12 +583,20 @@ B2_HD V3 microfacet_GGX_sample_reflection(float roughness, float anisotropy, V3 
 /* ------------------------------------------------------------------------------------------------------------
  * Glass energy compensation (MicrofacetEnergyCompensation.h:101-703)
  * ------------------------------------------------------------------------------------------------------------ */
+#if defined(__CUDACC__)
+static __device__ const B2ExponentCurve b2_glass_exponent_lower_device[B2_GLASS_EXPONENT_LOWER_COUNT] = B2_GLASS_EXPONENT_LOWER_INIT;
+static __device__ const B2ExponentCurve b2_glass_exponent_higher_device[B2_GLASS_EXPONENT_HIGHER_COUNT] = B2_GLASS_EXPONENT_HIGHER_INIT;
+#endif
+static const B2ExponentCurve b2_glass_exponent_lower_host[B2_GLASS_EXPONENT_LOWER_COUNT] = B2_GLASS_EXPONENT_LOWER_INIT;
+static const B2ExponentCurve b2_glass_exponent_higher_host[B2_GLASS_EXPONENT_HIGHER_COUNT] = B2_GLASS_EXPONENT_HIGHER_INIT;
+
 B2_HD float glass_exponent_curve(const B2ExponentCurve& curve, float roughness, float fallback)
 {
-    const float thresholds[11] = { 0.0f, 0.1f, 0.2f, 0.3f, 0.4f, 0.5f, 0.6f, 0.7f, 0.8f, 0.9f, 1.0f };
     for (int k = 0; k < 11; k++)
     {
-        if (roughness <= thresholds[k])
+        /* the reference's thresholds are the fp32 literals 0.0f, 0.1f, ... 1.0f */
+        const float threshold = k == 0 ? 0.0f : k == 1 ? 0.1f : k == 2 ? 0.2f : k == 3 ? 0.3f : k == 4 ? 0.4f : k == 5 ? 0.5f : k == 6 ? 0.6f : k == 7 ? 0.7f : k == 8 ? 0.8f : k == 9 ? 0.9f : 1.0f;
+        if (roughness <= threshold)
         {
             const B2ExponentSegment& s = curve.seg[k];
             if (!s.lerp)
@@ -604,8 +612,16 @@ B2_HD_NOINLINE float glass_energy_compensation_correction_exponent(float roughne
     if (b2_is_zero(roughness) || fabsf(1.0f - relative_eta) < 1.0e-3f)
         return 2.5f;
 
-    const B2ExponentCurve lower_curves[B2_GLASS_EXPONENT_LOWER_COUNT] = B2_GLASS_EXPONENT_LOWER_INIT;
-    const B2ExponentCurve higher_curves[B2_GLASS_EXPONENT_HIGHER_COUNT] = B2_GLASS_EXPONENT_HIGHER_INIT;
+    /* namespace-scope tables (global memory on the device, .rodata on the host): a function-local const array is
+     * re-materialised on the thread's local-memory stack at every call (3.4 KB of stores per call, measured as
+     * 1.4 GB of DRAM writes per C2 sample in profiles/r01_ncu_c2_megakernel.md) */
+#if defined(__CUDA_ARCH__)
+    const B2ExponentCurve* lower_curves = b2_glass_exponent_lower_device;
+    const B2ExponentCurve* higher_curves = b2_glass_exponent_higher_device;
+#else
+    const B2ExponentCurve* lower_curves = b2_glass_exponent_lower_host;
+    const B2ExponentCurve* higher_curves = b2_glass_exponent_higher_host;
+#endif
 
     /* lower chain: bracket (bound[i], bound[i + 1]] uses lower_curves[i]; outside every bracket the defaults stay */
     float lower_relative_eta_bound = 1.01f;

@@ -13,6 +13,7 @@
 #include "b2_material.h"
 #include "b2pt_alias_table.h"
 
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -52,6 +53,11 @@ struct b2pt_renderer
     b2pt_kernel* kernels[B2_PASS_COUNT] = {};
     double pass_ms[B2_PASS_COUNT] = {};
     uint64_t pass_launches[B2_PASS_COUNT] = {};
+    /* multi-GPU: this renderer owns the interleaved B2PT_BAND_ROWS-row bands `rank`, rank + world, ... of the frame */
+    int rank = 0, world = 1;
+    b2pt_exchange_fn exchange = nullptr;
+    void* exchange_user = nullptr;
+    uint64_t exchanges = 0;
     uint8_t* d_status = nullptr; /* [0] still_one_ray_active, [4..7] pixel_count_converged_so_far */
     void* d_reservoirs[3] = {};
 
@@ -533,8 +539,43 @@ int b2pt_renderer_render(b2pt_renderer* r, int samples)
             rc = B2PT_ERR_NO_VARIANT;
             return;
         }
+        int rank = r->rank, world = r->world;
+        if (world > 1 && r->loop.restir_di)
+        {
+            const b2pt_restir_di_settings& di = r->loop.rd.render_settings.restir_di_settings;
+            /* The reuse passes read reservoirs AND G-buffer entries of neighbouring pixels, which may belong to another
+             * GPU. G-buffer: every rank runs CameraRays over the whole frame (same seeds => same bytes; cheaper than
+             * exchanging 132 B/px). Reservoirs: the buffer a pass reads around a pixel is completed across ranks
+             * (all-gather of the owned rows, 36 B/px) right before that pass. */
+            if (pass == B2_PASS_CAMERA_RAYS)
+            {
+                rank = 0;
+                world = 1;
+            }
+            void* needs = nullptr;
+            if (pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL)
+                needs = di.temporal_pass.input_reservoirs;
+            else if (pass == B2_PASS_RESTIR_DI_SPATIAL)
+                needs = di.spatial_pass.input_reservoirs;
+            else if (pass == B2_PASS_RESTIR_DI_TEMPORAL && std::memcmp(&r->loop.rd.prev_camera, &r->loop.rd.current_camera, sizeof(b2pt_camera)) != 0)
+                needs = di.temporal_pass.input_reservoirs; /* reprojection reads other pixels only when the camera moved */
+            if (needs)
+            {
+                if (!r->exchange)
+                {
+                    b2_set_error("ReSTIR DI on %d GPUs needs the reservoir exchange callback (b2pt_renderer_set_partition)", world);
+                    rc = B2PT_ERR_INVALID_ARGUMENT;
+                    return;
+                }
+                rc = b2pt_stream_synchronize(r->ctx, r->stream);
+                if (rc != B2PT_OK)
+                    return;
+                r->exchange(r->exchange_user, needs, (uint64_t)r->pixels() * 36u);
+                r->exchanges++;
+            }
+        }
         void* args[1] = { &r->loop.rd };
-        rc = b2pt_kernel_launch(k, 8, 8, r->width, r->height, args, r->stream);
+        rc = b2pt_kernel_launch_rows(k, r->width, r->height, rank, world, args, r->stream);
         r->pass_launches[pass]++;
         if (rc == B2PT_OK && r->profile_passes)
         {
@@ -551,6 +592,22 @@ int b2pt_renderer_render(b2pt_renderer* r, int samples)
     B2_TRY(b2pt_event_record(r->ctx, r->ev_stop, r->stream));
     r->timed = true;
     return B2PT_OK;
+}
+
+/* Multi-GPU partition of the frame: interleaved row bands, scene replicated. */
+int b2pt_renderer_set_partition(b2pt_renderer* r, int rank, int world, b2pt_exchange_fn exchange, void* user)
+{
+    if (!r || world < 1 || rank < 0 || rank >= world) { b2_set_error("b2pt_renderer_set_partition: invalid argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    r->rank = rank;
+    r->world = world;
+    r->exchange = exchange;
+    r->exchange_user = user;
+    return B2PT_OK;
+}
+
+int b2pt_render_data_framebuffer_offset(void)
+{
+    return (int)offsetof(b2pt_render_data, buffers.accumulated_ray_colors);
 }
 
 int b2pt_renderer_synchronize(b2pt_renderer* r)

@@ -142,6 +142,11 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
 /* args[0] must point to a host HIPRTRenderData / b2pt_render_data (2784 bytes, passed by value to the kernel).
  * block_x / block_y are accepted for interface compatibility; the B200 kernels choose their own thread->pixel map. */
 int b2pt_kernel_launch(b2pt_kernel* kernel, int block_x, int block_y, int width, int height, void** args, b2pt_stream stream);
+/* Multi-GPU form: launches the kernel over the pixel rows of `rank`'s bands only. The frame is partitioned into
+ * interleaved bands of B2PT_BAND_ROWS rows; band b belongs to rank b % world (scene replicated on every GPU). The
+ * reference has no multi-GPU path; this is the one addition to its launch surface (BASELINE.json north_star). */
+#define B2PT_BAND_ROWS 64
+int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank, int world, void** args, b2pt_stream stream);
 int b2pt_kernel_last_ms(b2pt_kernel* kernel, float* out_ms);
 int b2pt_kernel_launch_count(b2pt_kernel* kernel, uint64_t* out_count);
 
@@ -191,6 +196,18 @@ int b2pt_renderer_set_profile_passes(b2pt_renderer* renderer, int enabled);
 int b2pt_renderer_reset(b2pt_renderer* renderer);
 /* Renders `samples` samples of every pixel (all passes), asynchronously on the renderer's stream. */
 int b2pt_renderer_render(b2pt_renderer* renderer, int samples);
+/* Multi-GPU (BASELINE.json north_star; the reference itself is single-GPU): this renderer renders only the pixel rows
+ * of its interleaved B2PT_BAND_ROWS-row bands (band b -> rank b % world); scene, BVH and LUTs are replicated by
+ * giving every rank the same scene. Without ReSTIR DI no pass reads another pixel and `exchange` may be null. With
+ * ReSTIR DI, CameraRays runs over the whole frame on every rank (deterministic, so neighbours' G-buffer entries are
+ * recomputed instead of exchanged) and `exchange(user, reservoir_planes, bytes)` is called on the host, with the
+ * renderer's stream idle, right before a pass that reads neighbouring pixels' reservoirs: it must complete the 9
+ * SoA planes (width*height 4-byte words each) across ranks, i.e. all-gather every rank's owned rows (NCCL). */
+typedef void (*b2pt_exchange_fn)(void* user, void* reservoir_planes, uint64_t bytes);
+int b2pt_renderer_set_partition(b2pt_renderer* renderer, int rank, int world, b2pt_exchange_fn exchange, void* user);
+/* offsetof(HIPRTRenderData, buffers.accumulated_ray_colors): where the framebuffer's device pointer sits in the host
+ * copy returned by b2pt_renderer_render_data (bindings that wrap the framebuffer without a copy) */
+int b2pt_render_data_framebuffer_offset(void);
 int b2pt_renderer_synchronize(b2pt_renderer* renderer);
 /* Device time of the last b2pt_renderer_render call (CUDA events on the renderer's stream), after synchronize. */
 int b2pt_renderer_last_render_ms(b2pt_renderer* renderer, float* out_ms);
