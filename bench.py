@@ -45,9 +45,56 @@ WORKLOADS = {
                desc="Cornell 1080p principled BSDF 16spp NEE+BSDF MIS power-proportional light sampling (BASELINE configs[1])"),
     "c3": dict(variant="c3", scene="cornell_pbr_16x9", width=1920, height=1080, spp=16, bounces=8,
                desc="Cornell 1080p principled BSDF 16spp RIS 4+1 power (shipped defaults)"),
-    "c4": dict(variant="c4", scene="cornell_pbr_16x9", width=1920, height=1080, spp=16, bounces=8,
+    "c4": dict(variant="c4", scene="cornell_pbr_16x9", width=1920, height=1080, spp=16, bounces=8, fused=1,
                desc="Cornell 1080p principled BSDF ReSTIR DI fused spatiotemporal, 16 frames x 1spp"),
+    # the synthetic many-light scene (tools/make_synthetic_scene.py, seed 0xB200: 10,000,000 triangles, 100,000 emissive) is
+    # generated on first use into gpurun_out/scenes/ (325 MB; deterministic), like the procedural HDR sky (tools/make_envmap.py)
+    "c3s": dict(variant="c3", scene="synthetic:10000000:100000", width=1920, height=1080, spp=4, bounces=8,
+                desc="synthetic 10M-triangle scene 1080p 8 bounces RIS 4+1 over 100k emissive triangles (BASELINE configs[2]), 4 spp per step"),
+    "c4s": dict(variant="c4", scene="synthetic:10000000:100000", envmap="sky:2048:1024", width=1920, height=1080, spp=4, bounces=8, fused=1,
+                desc="synthetic 10M-triangle scene 1080p ReSTIR DI fused spatiotemporal + HDR envmap alias table (BASELINE configs[3]), 4 frames x 1spp per step"),
+    "c5": dict(variant="c4", scene="synthetic:10000000:100000", envmap="sky:2048:1024", width=3840, height=2160, spp=4, bounces=8, fused=1,
+               desc="synthetic 10M-triangle scene 4K ReSTIR DI fused + envmap, tile-partitioned across GPUs (BASELINE configs[4]), 4 frames x 1spp per step"),
 }
+SCENE_CACHE = ROOT / "gpurun_out" / "scenes"
+
+
+def scene_file(w):
+    """Path of the workload's B2SCENE1 blob; synthetic scenes are generated (seeded, deterministic) on first use."""
+    name = w["scene"]
+    if not name.startswith("synthetic:"):
+        return ROOT / "data" / f"{name}.b2scene"
+    _, tris, emissive = name.split(":")
+    path = SCENE_CACHE / f"synthetic_{tris}_{emissive}_{w['width']}x{w['height']}.b2scene"
+    if not path.exists():
+        SCENE_CACHE.mkdir(parents=True, exist_ok=True)
+        tmp = path.with_suffix(f".tmp{os.getpid()}")
+        subprocess.run([sys.executable, str(ROOT / "tools" / "make_synthetic_scene.py"), str(tmp), "--triangles", tris, "--emissive", emissive,
+                        "--aspect", repr(w["width"] / w["height"])], check=True, stdout=subprocess.DEVNULL)
+        os.replace(tmp, path)
+    return path
+
+
+def envmap_file(w):
+    name = w.get("envmap")
+    if not name:
+        return None
+    _, ew, eh = name.split(":")
+    path = SCENE_CACHE / f"sky_{ew}x{eh}.b2env"
+    if not path.exists():
+        SCENE_CACHE.mkdir(parents=True, exist_ok=True)
+        tmp = path.with_suffix(f".tmp{os.getpid()}")
+        subprocess.run([sys.executable, str(ROOT / "tools" / "make_envmap.py"), str(tmp), "--width", ew, "--height", eh], check=True)
+        os.replace(tmp, path)
+    return path
+
+
+def oracle_args(w):
+    extra = ["--envmap", str(envmap_file(w))] if w.get("envmap") else []
+    if w["variant"] == "c4" and not w.get("fused", 0):
+        extra.append("--no-fused")
+    return extra
+
 
 # SURVEY.md section 8(d): bytes per traversal step and per shaded vertex / pixel
 S_NODE, S_TRI, S_HIT, S_LIGHT, S_PX = 80, 48, 164, 76, 288
@@ -123,12 +170,14 @@ def measured_peak_gbs():
 
 def pick_workload(name, b2pt, ctx):
     """The workload BASELINE.json's metric is quoted on is c2; fall back (loudly) only if that variant is not built."""
-    order = [name] if name else ["c2", "c1"]
+    if name:
+        return name, WORKLOADS[name]
+    order = ["c2", "c1"]
     for n in order:
         w = WORKLOADS[n]
         try:
             r = b2pt.Renderer(ctx, 16, 16, w["variant"], precise=False)
-            r.set_scene_file(ROOT / "data" / f"{w['scene']}.b2scene")
+            r.set_scene_file(scene_file(w))
             r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
             r.render(1)
             r.close()
@@ -151,14 +200,15 @@ def reference_arm(a):
     entry.ensure_data()
     cores = host_cores()
     # bounded sample: a centred window of the frame, 1 spp per step, sized for ~1-3 s per step
-    win_w, win_h = min(w["width"], 480), min(w["height"], 270)
+    big = w["scene"].startswith("synthetic:")  # the reference's octree build over 10M triangles takes ~12 s per run
+    win_w, win_h = (min(w["width"], 160), min(w["height"], 90)) if big else (min(w["width"], 480), min(w["height"], 270))
     x0, y0 = (w["width"] - win_w) // 2, (w["height"] - win_h) // 2
     spp = 1
     times = []
     for i in range(a.warmup + a.steps):
-        out = subprocess.run([str(exe), "--scene", str(ROOT / "data" / f"{w['scene']}.b2scene"), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
+        out = subprocess.run([str(exe), "--scene", str(scene_file(w)), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
                               "--width", str(w["width"]), "--height", str(w["height"]), "--spp", str(spp), "--bounces", str(w["bounces"]),
-                              "--threads", str(cores), "--window", str(x0), str(y0), str(x0 + win_w), str(y0 + win_h)],
+                              "--threads", str(cores), "--window", str(x0), str(y0), str(x0 + win_w), str(y0 + win_h), *oracle_args(w)],
                              check=True, capture_output=True, text=True)
         meta = json.loads(out.stdout.strip().splitlines()[-1])
         if i >= a.warmup:
@@ -185,19 +235,20 @@ def cpu_baseline(w, seconds_budget=20.0):
     if not exe.exists():
         return dict(value=None, unit="Mpaths/s", cores=0, kind="unavailable", sample="oracle binaries not built")
     cores = host_cores()
-    win_w, win_h = min(w["width"], 480), min(w["height"], 270)
+    big = w["scene"].startswith("synthetic:")
+    win_w, win_h = (min(w["width"], 160), min(w["height"], 90)) if big else (min(w["width"], 480), min(w["height"], 270))
     x0, y0 = (w["width"] - win_w) // 2, (w["height"] - win_h) // 2
-    spp, total_s, total_paths = 1, 0.0, 0
+    spp, total_s, total_paths = (2 if big else 1), 0.0, 0
     t_start = time.time()
     while True:
-        out = subprocess.run([str(exe), *extra, "--scene", str(ROOT / "data" / f"{w['scene']}.b2scene"), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
+        out = subprocess.run([str(exe), *extra, "--scene", str(scene_file(w)), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
                               "--width", str(w["width"]), "--height", str(w["height"]), "--spp", str(spp), "--bounces", str(w["bounces"]),
-                              "--threads", str(cores), "--window", str(x0), str(y0), str(x0 + win_w), str(y0 + win_h)],
+                              "--threads", str(cores), "--window", str(x0), str(y0), str(x0 + win_w), str(y0 + win_h), *oracle_args(w)],
                              check=True, capture_output=True, text=True)
         meta = json.loads(out.stdout.strip().splitlines()[-1])
         total_s += meta["render_seconds"]
         total_paths += win_w * win_h * spp
-        if time.time() - t_start > seconds_budget * 0.5 or total_s > seconds_budget:
+        if big or time.time() - t_start > seconds_budget * 0.5 or total_s > seconds_budget:
             break
         spp = min(spp * 2, 16)
     return dict(value=total_paths / total_s / 1e6, unit="Mpaths/s", cores=cores, kind=kind,
@@ -243,9 +294,17 @@ def main():
     W, H, spp = w["width"], w["height"], w["spp"]
 
     r = b2pt.Renderer(ctx, W, H, w["variant"], precise=bool(a.precise))
-    r.set_scene_file(ROOT / "data" / f"{w['scene']}.b2scene")
+    if rank == 0:
+        scene_file(w), envmap_file(w)   # generate once, before the other ranks look for the files
+    if world > 1:
+        dist.barrier()
+    r.set_scene_file(scene_file(w))
     r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
     r.set(nb_bounces=w["bounces"])
+    if w["variant"] == "c4":
+        r.set(restir_di_do_fused_spatiotemporal=int(w.get("fused", 0)))
+    if envmap_file(w):
+        r.set_envmap_file(envmap_file(w))
     if world > 1:
         r.set_partition(rank, world, torch, dist)
     info = r.scene_info()
@@ -352,7 +411,12 @@ def main():
         achieved = algo_bytes / (mk_ms * 1e-3) / 1e9 if mk_ms > 0 else 0.0
         roofline = dict(bound="hbm", kernel="MegaKernel", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
                         peak_source=which, algorithmic_bytes_per_launch=algo_bytes, launch_ms=mk_ms,
-                        note="Cornell (BVH+triangles < 1 MB) is L2-resident: issue rate, not HBM, binds; see DESIGN.md")
+                        note=("10M-triangle scene: 0.6 GB of nodes + triangles, random-sector HBM/L2 gathers bind" if w["scene"].startswith("synthetic:")
+                              else "Cornell (BVH+triangles < 1 MB) is L2-resident: issue rate, not HBM, binds; see DESIGN.md"))
+        # dram__bytes_read.sum + dram__bytes_write.sum of one MegaKernel launch from the committed `ncu --set full` capture
+        traffic_file = ROOT / "profiles" / "ncu_traffic.json"
+        if traffic_file.exists():
+            roofline["traffic"] = json.loads(traffic_file.read_text()).get(name, {}).get("dram_bytes_per_launch")
         extra = dict(pass_ms_per_step=pass_ms, mrays_per_s=c["rays"] / (sum(pass_ms.values()) * 1e-3) / 1e6 if pass_ms else None,
                      traversal=dict(rays_per_path=c["rays"] / (own * spp), nodes_per_ray=c["nodes"] / max(c["rays"], 1), triangles_per_ray=c["triangles"] / max(c["rays"], 1)),
                      scene=info, wall_ms_timed_region=wall_ms)

@@ -189,6 +189,9 @@ class Renderer:
     def set_luts_file(self, path):
         check(lib().b2pt_renderer_set_luts_file(self.handle, str(path).encode()))
 
+    def set_envmap_file(self, path):
+        check(lib().b2pt_renderer_set_envmap_file(self.handle, str(path).encode()))
+
     def set_envmap(self, rgba):
         if rgba is None:
             check(lib().b2pt_renderer_set_envmap(self.handle, None, 0, 0))

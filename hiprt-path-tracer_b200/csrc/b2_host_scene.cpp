@@ -276,3 +276,50 @@ bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bv
     scene.bvh_build_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
     return true;
 }
+
+void b2_host_envmap_prepare(B2HostEnvmap& out, const float* rgba, int width, int height)
+{
+    const size_t n = (size_t)width * height;
+    out.width = width;
+    out.height = height;
+    std::vector<float> lum(n);
+    out.packed.resize(n);
+    float total = 0.0f;
+    const float weights[3] = { 0.3086f, 0.6094f, 0.0820f };
+    for (size_t i = 0; i < n; i++)
+    {
+        float l = 0.0f;
+        for (int c = 0; c < 3; c++)
+            l += rgba[4 * i + c] * weights[c];
+        total += l;
+        lum[i] = l;
+
+        const float k_max = b2_uint_as_float(0x477F8000u), k_min = b2_uint_as_float(0x37800000u);
+        float cr = fminf(k_max, fmaxf(0.0f, rgba[4 * i + 0])), cg = fminf(k_max, fmaxf(0.0f, rgba[4 * i + 1])), cb = fminf(k_max, fmaxf(0.0f, rgba[4 * i + 2]));
+        float max_channel = b2_max(b2_max(k_min, cr), b2_max(cg, cb));
+        float bias = b2_uint_as_float((b2_float_as_uint(max_channel) + 0x07804000u) & 0x7F800000u);
+        uint32_t R = b2_float_as_uint(cr + bias), G = b2_float_as_uint(cg + bias), B = b2_float_as_uint(cb + bias);
+        uint32_t E = (b2_float_as_uint(bias) << 4) + 0x10000000u;
+        out.packed[i] = E | B << 18 | G << 9 | (R & 0x1FFu);
+    }
+    out.total_luminance = total;
+    b2pt_build_alias_table(lum, total, out.alias_probas, out.alias_alias);
+}
+
+bool b2_envmap_blob_read(const char* path, std::vector<float>& rgba, int& width, int& height)
+{
+    FILE* f = std::fopen(path, "rb");
+    char magic[8];
+    int32_t dims[2];
+    if (!f || std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "B2ENVMP1", 8) != 0 || std::fread(dims, 4, 2, f) != 2 || dims[0] <= 0 || dims[1] <= 0)
+    {
+        if (f) std::fclose(f);
+        return false;
+    }
+    rgba.resize((size_t)dims[0] * dims[1] * 4);
+    bool ok = std::fread(rgba.data(), 4, rgba.size(), f) == rgba.size();
+    std::fclose(f);
+    width = dims[0];
+    height = dims[1];
+    return ok;
+}

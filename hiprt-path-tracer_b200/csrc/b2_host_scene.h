@@ -78,6 +78,22 @@ struct B2HostScene
     double bvh_build_seconds = 0.0;
 };
 
+/* Environment map as the kernels read it: RGBE9995-packed texels + luminance alias table.
+ * CPURenderer::set_envmap (src/Renderer/CPURenderer.cpp:467-508, ESS_ALIAS_TABLE branch), Image32Bit::compute_alias_table
+ * (src/Image/Image.cpp:536-545,652-671), RGBE9995Packed::pack (src/HostDeviceCommon/Packing.h:443-468). */
+struct B2HostEnvmap
+{
+    int width = 0, height = 0;
+    std::vector<uint32_t> packed;
+    std::vector<float> alias_probas;
+    std::vector<int> alias_alias;
+    float total_luminance = 0.0f;
+};
+/* rgba: width*height*4 floats, row 0 first (what Image32Bit holds after read_image_hdr(path, 4, flipY = true)) */
+void b2_host_envmap_prepare(B2HostEnvmap& out, const float* rgba, int width, int height);
+/* "B2ENVMP1" blob: int32 width, height, then width*height*4 floats. Returns false when the file cannot be read. */
+bool b2_envmap_blob_read(const char* path, std::vector<float>& rgba, int& width, int& height);
+
 /* Fills every derived array of `scene` from `scene.blob`. Returns false and sets `error` on unsupported input
  * (dispersive media, > 2^26 - 1 materials, invalid indices). */
 bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bvh = true);

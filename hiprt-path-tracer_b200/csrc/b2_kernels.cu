@@ -35,7 +35,15 @@
 #define B2_MAX_DEVICES 64
 /* resident 64-thread blocks per SM the persistent MegaKernel is compiled for (caps registers at 65536 / (64 * N)) */
 #ifndef B2_MK_MIN_BLOCKS
-#define B2_MK_MIN_BLOCKS 6
+#define B2_MK_MIN_BLOCKS 12
+#endif
+/* threads per block of the persistent MegaKernel, and whether its warps meet at a block barrier at the top of every
+ * bounce iteration (keeps the warps of a block in the same code region: instruction-cache locality vs barrier waits) */
+#ifndef B2_MK_THREADS
+#define B2_MK_THREADS 64
+#endif
+#ifndef B2_MK_BLOCK_SYNC
+#define B2_MK_BLOCK_SYNC 0
 #endif
 
 namespace B2_NS
@@ -51,7 +59,7 @@ __device__ __forceinline__ uint32_t b2_global_row(uint32_t local_row, const B2La
     return (band_local * (uint32_t)g.world + (uint32_t)g.rank) * B2_BAND_ROWS + local_row % B2_BAND_ROWS;
 }
 
-__device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd, uint64_t* stacks, B2TraversalCounters* counters, unsigned int* faults)
+__device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd, uint64_t* stacks, B2TraversalCounters* counters, unsigned int* faults, int threads = B2_BLOCK_THREADS)
 {
     ctx.rd = &rd;
     if (rd.GPU_BVH != nullptr)
@@ -63,7 +71,7 @@ __device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd
         ctx.bvh.node_count = ctx.bvh.tri_count = 0;
     }
     ctx.stack = stacks + threadIdx.x;
-    ctx.stack_stride = B2_BLOCK_THREADS;
+    ctx.stack_stride = threads;
     ctx.counters = counters;
     ctx.faults = faults;
 }
@@ -123,17 +131,17 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) pass_kernel(const __grid_con
  */
 #define B2_QUEUE_SLOTS 64
 template <class V>
-__global__ void __launch_bounds__(B2_BLOCK_THREADS, B2_MK_MIN_BLOCKS) megakernel_persistent(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x,
+__global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_persistent(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x,
                                                                                              unsigned int total_tiles, unsigned int* work_counter)
 {
-    __shared__ uint64_t stacks[B2_STACK_ENTRIES * B2_BLOCK_THREADS];
-    __shared__ uint32_t queues[B2_BLOCK_THREADS / 32][B2_QUEUE_SLOTS];
+    __shared__ uint64_t stacks[B2_STACK_ENTRIES * B2_MK_THREADS];
+    __shared__ uint32_t queues[B2_MK_THREADS / 32][B2_QUEUE_SLOTS];
 
     B2TraversalCounters local_counters;
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
 
     Ctx ctx;
-    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults);
+    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_MK_THREADS);
 
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lanes_below = (1u << lane) - 1u;
@@ -194,12 +202,23 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS, B2_MK_MIN_BLOCKS) megakernel
             q_count -= taken;
         }
         __syncwarp();
+#if B2_MK_BLOCK_SYNC
+        if (!__syncthreads_or(alive ? 1 : 0))
+        {
+            /* no live path in the whole block: either every warp ran out of work, or (rarely) the freshly fetched tiles
+             * held no hit pixel -- in that case go round again (block-uniform decision) */
+            if (__syncthreads_and((exhausted && q_count == 0) ? 1 : 0))
+                break;
+            continue;
+        }
+#else
         if (!__any_sync(0xFFFFFFFFu, alive))
         {
             if (exhausted && q_count == 0)
                 break;
             continue;
         }
+#endif
         if (alive)
         {
             if (!megakernel_bounce<V>(ctx, s))
@@ -250,7 +269,7 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
             if (!pd.ring)
             {
                 e = cudaDeviceGetAttribute(&pd.sm_count, cudaDevAttrMultiProcessorCount, device);
-                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pd.blocks_per_sm, megakernel_persistent<V>, B2_BLOCK_THREADS, 0);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pd.blocks_per_sm, megakernel_persistent<V>, B2_MK_THREADS, 0);
                 if (e == cudaSuccess && pd.blocks_per_sm < 1) pd.blocks_per_sm = 1;
                 if (e == cudaSuccess) e = cudaMalloc(&pd.ring, B2_WORK_COUNTER_SLOTS * sizeof(unsigned int));
                 if (e != cudaSuccess)
@@ -263,7 +282,7 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
             return e;
         const int sm_count = pd.sm_count, blocks_per_sm = pd.blocks_per_sm;
         const unsigned int total_tiles = (unsigned int)tiles_x * (unsigned int)((rows + 3) / 4);
-        megakernel_persistent<V><<<sm_count * blocks_per_sm, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, total_tiles, counter);
+        megakernel_persistent<V><<<sm_count * blocks_per_sm, B2_MK_THREADS, 0, stream>>>(*rd, g, tiles_x, total_tiles, counter);
         return cudaGetLastError();
     }
     const int tiles_y = (rows + B2_TILE_H - 1) / B2_TILE_H;

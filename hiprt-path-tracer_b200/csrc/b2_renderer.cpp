@@ -432,6 +432,19 @@ int b2pt_renderer_set_luts_file(b2pt_renderer* r, const char* lut_blob_path)
 
 /* RendererEnvmap / CPURenderer::set_envmap (CPURenderer.cpp:467-508): luminance alias table (Image.cpp:536-545,
  * 652-671) + RGBE9995 packing (EnvmapRGBE9995.h:21-46, Packing.h:443-468) */
+int b2pt_renderer_set_envmap_file(b2pt_renderer* r, const char* envmap_blob_path)
+{
+    if (!r || !envmap_blob_path) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    std::vector<float> rgba;
+    int width = 0, height = 0;
+    if (!b2_envmap_blob_read(envmap_blob_path, rgba, width, height))
+    {
+        b2_set_error("cannot read envmap blob %s", envmap_blob_path);
+        return B2PT_ERR_IO;
+    }
+    return b2pt_renderer_set_envmap(r, rgba.data(), width, height);
+}
+
 int b2pt_renderer_set_envmap(b2pt_renderer* r, const float* rgba, int width, int height)
 {
     if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
@@ -443,36 +456,14 @@ int b2pt_renderer_set_envmap(b2pt_renderer* r, const float* rgba, int width, int
         w.envmap = nullptr;
         return B2PT_OK;
     }
-    const size_t n = (size_t)width * height;
-    std::vector<float> lum(n);
-    std::vector<uint32_t> packed(n);
-    float total = 0.0f;
-    const float weights[3] = { 0.3086f, 0.6094f, 0.0820f };
-    for (size_t i = 0; i < n; i++)
-    {
-        float l = 0.0f;
-        for (int c = 0; c < 3; c++)
-            l += rgba[4 * i + c] * weights[c];
-        total += l;
-        lum[i] = l;
-
-        const float k_max = b2_uint_as_float(0x477F8000u), k_min = b2_uint_as_float(0x37800000u);
-        float cr = fminf(k_max, fmaxf(0.0f, rgba[4 * i + 0])), cg = fminf(k_max, fmaxf(0.0f, rgba[4 * i + 1])), cb = fminf(k_max, fmaxf(0.0f, rgba[4 * i + 2]));
-        float max_channel = b2_max(b2_max(k_min, cr), b2_max(cg, cb));
-        float bias = b2_uint_as_float((b2_float_as_uint(max_channel) + 0x07804000u) & 0x7F800000u);
-        uint32_t R = b2_float_as_uint(cr + bias), G = b2_float_as_uint(cg + bias), B = b2_float_as_uint(cb + bias);
-        uint32_t E = (b2_float_as_uint(bias) << 4) + 0x10000000u;
-        packed[i] = E | B << 18 | G << 9 | (R & 0x1FFu);
-    }
-    std::vector<float> probas;
-    std::vector<int> alias;
-    b2pt_build_alias_table(lum, total, probas, alias);
-    B2_TRY(upload(r, r->envmap_allocs, packed, &w.envmap));
-    B2_TRY(upload(r, r->envmap_allocs, probas, &w.envmap_alias_table.alias_table_probas));
-    B2_TRY(upload(r, r->envmap_allocs, alias, &w.envmap_alias_table.alias_table_alias));
-    w.envmap_alias_table.sum_elements = total;
-    w.envmap_alias_table.size = (unsigned)n;
-    w.envmap_total_sum = total;
+    B2HostEnvmap env;
+    b2_host_envmap_prepare(env, rgba, width, height);
+    B2_TRY(upload(r, r->envmap_allocs, env.packed, &w.envmap));
+    B2_TRY(upload(r, r->envmap_allocs, env.alias_probas, &w.envmap_alias_table.alias_table_probas));
+    B2_TRY(upload(r, r->envmap_allocs, env.alias_alias, &w.envmap_alias_table.alias_table_alias));
+    w.envmap_alias_table.sum_elements = env.total_luminance;
+    w.envmap_alias_table.size = (unsigned)((size_t)width * height);
+    w.envmap_total_sum = env.total_luminance;
     w.envmap_width = (unsigned)width;
     w.envmap_height = (unsigned)height;
     w.ambient_light_type = 2;

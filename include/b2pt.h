@@ -186,6 +186,8 @@ int b2pt_renderer_reupload_scene(b2pt_renderer* renderer, uint64_t* out_bytes);
 int b2pt_renderer_set_luts_file(b2pt_renderer* renderer, const char* lut_blob_path);
 /* RGBA fp32 texels, row 0 first (what Image32Bit holds after read_image_hdr(path, 4, flipY=true)) */
 int b2pt_renderer_set_envmap(b2pt_renderer* renderer, const float* rgba_texels, int width, int height);
+/* same, from a "B2ENVMP1" blob (int32 width, height, then width*height*4 floats): the container tests and bench use */
+int b2pt_renderer_set_envmap_file(b2pt_renderer* renderer, const char* envmap_blob_path);
 /* Host copy of the render data; edit settings (nb_bounces, restir_di_settings, ...) before rendering. */
 b2pt_render_data* b2pt_renderer_render_data(b2pt_renderer* renderer);
 int b2pt_renderer_set_host_seed(b2pt_renderer* renderer, unsigned int seed);

@@ -227,6 +227,26 @@ int main(int argc, char** argv)
     rd.bsdfs_data.GGX_thin_glass_directional_albedo = &luts.luts["ggx_thin_glass"];
     rd.bsdfs_data.sheen_ltc_parameters_texture = &luts.luts["sheen_ltc"];
 
+    /* environment map (same host preparation the product's renderer uploads: b2_host_envmap_prepare) */
+    B2HostEnvmap env;
+    if (!a.envmap.empty())
+    {
+        std::vector<float> rgba;
+        int ew = 0, eh = 0;
+        if (!b2_envmap_blob_read(a.envmap.c_str(), rgba, ew, eh)) { std::fprintf(stderr, "cannot read envmap blob %s\n", a.envmap.c_str()); return 1; }
+        b2_host_envmap_prepare(env, rgba.data(), ew, eh);
+        b2pt_world_settings& w = rd.world_settings;
+        w.envmap = env.packed.data();
+        w.envmap_alias_table.alias_table_probas = env.alias_probas.data();
+        w.envmap_alias_table.alias_table_alias = env.alias_alias.data();
+        w.envmap_alias_table.sum_elements = env.total_luminance;
+        w.envmap_alias_table.size = (unsigned)((size_t)ew * eh);
+        w.envmap_total_sum = env.total_luminance;
+        w.envmap_width = (unsigned)ew;
+        w.envmap_height = (unsigned)eh;
+        w.ambient_light_type = 2;
+    }
+
     /* aux + G-buffers */
     std::vector<uint8_t> pixel_active(n, 0);
     std::vector<b2pt_rgb> denoiser_albedo(n, b2pt_rgb{ 0, 0, 0 });

@@ -69,7 +69,7 @@ def run_oracle(kind, variant, scene, width, height, spp, bounces, tmp_path, extr
             "--spp", str(spp), "--bounces", str(bounces), "--dump", prefix, *extra]
     if threads:
         cmd += ["--threads", str(threads)]
-    out = subprocess.run(cmd, check=True, capture_output=True, text=True)
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True, cwd=ROOT)  # envmap paths in `extra` are repo-relative
     meta = json.loads(out.stdout.strip().splitlines()[-1])
     n = width * height
     load = lambda nm, dt: np.fromfile(prefix + nm + ".bin", dt)
@@ -78,6 +78,12 @@ def run_oracle(kind, variant, scene, width, height, spp, bounces, tmp_path, extr
     return dict(meta=meta, prim=load("gbuffer_prim", np.int32), position=load("gbuffer_position", np.float32).reshape(n, 3),
                 geometric_normal=load("gbuffer_geometric_normal", np.uint32) & 0xFFFFFF, shading_normal=load("gbuffer_shading_normal", np.uint32) & 0xFFFFFF,
                 material=mat, framebuffer=load("framebuffer", np.float32).reshape(n, 3))
+
+
+def envmap_of(meta):
+    """Repo-relative envmap blob named in a fixture's extra args, or None."""
+    extra = list(meta.get("extra", []))
+    return ROOT / extra[extra.index("--envmap") + 1] if "--envmap" in extra else None
 
 
 def rel_error(a, b):

@@ -5,7 +5,7 @@ seed within 1e-3 relative (precise flavour)."""
 import numpy as np
 import pytest
 
-from conftest import DATA, GOLDEN, load_golden, rel_error, run_oracle
+from conftest import DATA, GOLDEN, envmap_of, load_golden, rel_error, run_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -22,6 +22,8 @@ def make_renderer(b2pt, ctx, meta, precise=True):
     r.set(nb_bounces=meta["bounces"])
     if variant == "c4":
         r.set(restir_di_do_fused_spatiotemporal=0 if "--no-fused" in meta.get("extra", []) else 1)
+    if envmap_of(meta):
+        r.set_envmap_file(envmap_of(meta))
     return r
 
 

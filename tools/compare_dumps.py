@@ -11,15 +11,22 @@ def load(prefix, name, dtype):
         return None
 
 
-def compare(pa, pb, width, height, rel_tol=1e-3, verbose=True):
+def compare(pa, pb, width, height, rel_tol=1e-3, verbose=True, window=None):
+    """window = (x0, y0, x1, y1): compare only those pixels (the oracle rendered a crop of the frame)."""
     out = {}
     n = width * height
+    sel = np.ones(n, bool)
+    if window is not None:
+        x0, y0, x1, y1 = window
+        m = np.zeros((height, width), bool)
+        m[y0:y1, x0:x1] = True
+        sel = m.ravel()
     prim_a, prim_b = load(pa, "gbuffer_prim", np.int32), load(pb, "gbuffer_prim", np.int32)
     if prim_a is not None and prim_b is not None:
-        out["prim_mismatch"] = int((prim_a != prim_b).sum())
+        out["prim_mismatch"] = int((prim_a != prim_b)[sel].sum())
         pos_a = load(pa, "gbuffer_position", np.float32).reshape(n, 3)
         pos_b = load(pb, "gbuffer_position", np.float32).reshape(n, 3)
-        same = prim_a == prim_b
+        same = (prim_a == prim_b) & sel
         out["position_bit_mismatch"] = int((pos_a[same].view(np.uint32) != pos_b[same].view(np.uint32)).any(axis=1).sum())
         for key in ("gbuffer_geometric_normal", "gbuffer_shading_normal"):
             a, b = load(pa, key, np.uint32), load(pb, key, np.uint32)
@@ -31,10 +38,10 @@ def compare(pa, pb, width, height, rel_tol=1e-3, verbose=True):
         out["material_mismatch"] = int((ma != mb).any(axis=1)[same].sum())
     fa, fb = load(pa, "framebuffer", np.float32), load(pb, "framebuffer", np.float32)
     if fa is not None and fb is not None:
-        fa, fb = fa.reshape(n, 3), fb.reshape(n, 3)
+        fa, fb = fa.reshape(n, 3)[sel], fb.reshape(n, 3)[sel]
         denom = np.maximum(np.abs(fa), np.abs(fb))
         rel = np.where(denom > 1e-6, np.abs(fa - fb) / np.maximum(denom, 1e-30), 0.0).max(axis=1)
-        out["pixels"] = n
+        out["pixels"] = int(sel.sum())
         out["pixels_over_tol"] = int((rel > rel_tol).sum())
         out["pixels_bit_exact"] = int((fa.view(np.uint32) == fb.view(np.uint32)).all(axis=1).sum())
         out["max_rel"] = float(rel.max())

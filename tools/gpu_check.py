@@ -21,8 +21,17 @@ import __graft_entry__ as entry  # noqa: E402
 from compare_dumps import compare  # noqa: E402
 
 
+def scene_path(a):
+    return Path(a.scene) if a.scene.endswith(".b2scene") else ROOT / "data" / f"{a.scene}.b2scene"
+
+
 def run_oracle(exe, a, prefix, extra=()):
-    cmd = [str(exe), "--scene", str(ROOT / "data" / f"{a.scene}.b2scene"), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
+    extra = list(extra)
+    if a.window:
+        extra += ["--window", *[str(v) for v in a.window]]
+    if a.envmap:
+        extra += ["--envmap", a.envmap]
+    cmd = [str(exe), "--scene", str(scene_path(a)), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
            "--width", str(a.width), "--height", str(a.height), "--spp", str(a.spp), "--bounces", str(a.bounces), "--dump", prefix, *extra]
     t0 = time.time()
     out = subprocess.run(cmd, check=True, capture_output=True, text=True)
@@ -40,6 +49,9 @@ def main():
     ap.add_argument("--no-oracle", action="store_true")
     ap.add_argument("--fused", type=int, default=1)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--window", type=int, nargs=4, default=None, help="x0 y0 x1 y1: the oracles render (and parity is checked on) this crop only")
+    ap.add_argument("--envmap", default=None, help="B2ENVMP1 blob")
+    ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
 
     entry.ensure_data()
@@ -52,7 +64,9 @@ def main():
 
     for flavour in ("precise", "fast"):
         r = b2pt.Renderer(ctx, a.width, a.height, a.variant, precise=(flavour == "precise"))
-        r.set_scene_file(ROOT / "data" / f"{a.scene}.b2scene")
+        r.set_scene_file(scene_path(a))
+        if a.envmap:
+            r.set_envmap_file(a.envmap)
         r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
         r.set(nb_bounces=a.bounces, restir_di_do_fused_spatiotemporal=a.fused)
         if flavour == "precise":
@@ -65,7 +79,7 @@ def main():
         r.set_counters(False)
         # timed passes: warm-up then 5 repeats of the whole spp loop from a reset state
         times = []
-        for rep in range(6):
+        for rep in range(a.reps + 1):
             r.reset()
             r.set_host_seed(42)
             r.render(a.spp)
@@ -96,10 +110,10 @@ def main():
         port_meta, _ = run_oracle(ROOT / "oracle" / "_port" / "port_render", a, str(tmp / "port_"), ["--variant", a.variant, *extra])
         report["ref_oracle"] = ref_meta
         report["port_oracle"] = port_meta
-        report["cuda_precise_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "cuda_precise_"), a.width, a.height, verbose=False)
-        report["cuda_fast_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "cuda_fast_"), a.width, a.height, verbose=False)
-        report["cuda_precise_vs_port"] = compare(str(tmp / "port_"), str(tmp / "cuda_precise_"), a.width, a.height, verbose=False)
-        report["port_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "port_"), a.width, a.height, verbose=False)
+        report["cuda_precise_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "cuda_precise_"), a.width, a.height, verbose=False, window=a.window)
+        report["cuda_fast_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "cuda_fast_"), a.width, a.height, verbose=False, window=a.window)
+        report["cuda_precise_vs_port"] = compare(str(tmp / "port_"), str(tmp / "cuda_precise_"), a.width, a.height, verbose=False, window=a.window)
+        report["port_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "port_"), a.width, a.height, verbose=False, window=a.window)
 
     out_dir = ROOT / "gpurun_out"
     out_dir.mkdir(exist_ok=True)
