@@ -162,190 +162,224 @@ __device__ __forceinline__ B2NodeRaw b2_load_node(const B2Node* nodes, uint32_t 
  * `stack` points to this thread's first of B2_STACK_ENTRIES 8-byte slots, `stack_stride` slots apart (on the GPU the
  * slots live in shared memory, entry-major, so the 32 lanes of a warp touch 32 consecutive 8-byte words).
  */
-B2_HD B2Hit b2_traverse_rt(const bool ANY_HIT, const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int stack_stride,
-                           B2TraversalCounters* counters, unsigned int* faults)
+/* The traversal as explicit state + one step, so that a kernel can interleave the steps of many rays in one converged
+ * loop (b2_kernels.cu: a lane that finishes its ray fetches the next one from the block's pool while the other lanes
+ * keep stepping). b2_traverse_rt below = begin; while (step); -- the same operations in the same order as before. */
+struct B2Traversal
 {
+    V3 org, dir;
+    float idx, idy, idz;
+    uint32_t oct_inv;
+    float t_max, t_far;
+    int skip_prim;
+    bool any_hit;
     B2Hit best;
-    best.t = -1.0f;
-    best.u = best.v = 0.0f;
-    best.prim = -1;
-    best.ng = v3(0.0f);
-    if (bvh.node_count == 0)
-        return best;
+    uint64_t* top; /* moving stack pointer: see the ptxas note below */
+    int sp;
+    uint32_t group_base, group_bits;
+    unsigned int guard;
+    unsigned int n_nodes, n_tris;
+};
 
-    float t_far = t_max;
-
+B2_HD void b2_traverse_begin(B2Traversal& t, bool any_hit, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack)
+{
+    t.org = org;
+    t.dir = dir;
+    t.any_hit = any_hit;
+    t.t_max = t_max;
+    t.t_far = t_max;
+    t.skip_prim = skip_prim;
+    t.best.t = -1.0f;
+    t.best.u = t.best.v = 0.0f;
+    t.best.prim = -1;
+    t.best.ng = v3(0.0f);
     /* direction reciprocal, guarded against 0 (the slab test may be conservative; the triangle test is exact) */
     const float tiny = 1.0e-30f;
-    float idx = 1.0f / (fabsf(dir.x) > tiny ? dir.x : (dir.x < 0.0f ? -tiny : tiny));
-    float idy = 1.0f / (fabsf(dir.y) > tiny ? dir.y : (dir.y < 0.0f ? -tiny : tiny));
-    float idz = 1.0f / (fabsf(dir.z) > tiny ? dir.z : (dir.z < 0.0f ? -tiny : tiny));
+    t.idx = 1.0f / (fabsf(dir.x) > tiny ? dir.x : (dir.x < 0.0f ? -tiny : tiny));
+    t.idy = 1.0f / (fabsf(dir.y) > tiny ? dir.y : (dir.y < 0.0f ? -tiny : tiny));
+    t.idz = 1.0f / (fabsf(dir.z) > tiny ? dir.z : (dir.z < 0.0f ? -tiny : tiny));
     const uint32_t octant = (dir.x < 0.0f ? 4u : 0u) | (dir.y < 0.0f ? 2u : 0u) | (dir.z < 0.0f ? 1u : 0u);
-    const uint32_t oct_inv = 7u - octant;
-
+    t.oct_inv = 7u - octant;
     /* The stack is addressed through a moving pointer (`top`) plus a depth counter rather than stack[sp * stride]:
      * ptxas 12.9 (sm_100a) mis-folds the `sp - 1` of the pop into the LDS immediate AFTER already decrementing the
      * register (observed: "VIADD R22, R22, -1 ; IMAD R5, R22, 0x200, R37 ; LDS.64 [R5 + -0x200]"), which pops the entry
      * below the top; tools/traverse_selftest.cu is the regression test for this. */
-    int sp = 0;
-    uint64_t* top = stack;
-    uint32_t group_base = 0;            /* node group: index of first child node */
-    uint32_t group_bits = 0x80000000u;  /* bits 24..31: pending inner children (by traversal priority); bits 0..7: imask */
+    t.sp = 0;
+    t.top = stack;
+    t.group_base = 0;            /* node group: index of first child node */
+    t.group_bits = 0x80000000u;  /* bits 24..31: pending inner children (by traversal priority); bits 0..7: imask */
+    t.guard = 0;
+    t.n_nodes = t.n_tris = 0;
+}
 
-    unsigned long long n_nodes = 0, n_tris = 0;
-    unsigned int guard = 0;
-
-    while (true)
+/* One step: at most one node (its 8 quantised child boxes) and the triangles of its hit leaf slots, then a pop if the
+ * current group is exhausted. Returns false when the traversal is over (t.best holds the result). */
+B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_stride, unsigned int* faults)
+{
+    const V3 org = t.org, dir = t.dir;
+    const uint32_t oct_inv = t.oct_inv;
+    if (++t.guard > B2_TRAVERSAL_GUARD)
     {
-        if (++guard > B2_TRAVERSAL_GUARD)
-        {
-            b2_report_fault(faults, B2_FAULT_TRAVERSAL_GUARD);
-            break;
-        }
-        uint32_t tri_base = 0, tri_bits = 0;
+        b2_report_fault(faults, B2_FAULT_TRAVERSAL_GUARD);
+        return false;
+    }
+    uint32_t tri_base = 0, tri_bits = 0;
 
-        if (group_bits > 0x00FFFFFFu)
+    if (t.group_bits > 0x00FFFFFFu)
+    {
+        const uint32_t child_bit = b2_bfind(t.group_bits);
+        const uint32_t slot = (child_bit - 24u) ^ oct_inv;
+        const uint32_t imask = t.group_bits & 0xFFu;
+        const uint32_t node_index = t.group_base + b2_popc(imask & ~(0xFFFFFFFFu << slot));
+        t.group_bits &= ~(1u << child_bit);
+        if (t.group_bits > 0x00FFFFFFu)
         {
-            const uint32_t child_bit = b2_bfind(group_bits);
-            const uint32_t slot = (child_bit - 24u) ^ oct_inv;
-            const uint32_t imask = group_bits & 0xFFu;
-            const uint32_t node_index = group_base + b2_popc(imask & ~(0xFFFFFFFFu << slot));
-            group_bits &= ~(1u << child_bit);
-            if (group_bits > 0x00FFFFFFu)
+            if (t.sp < B2_STACK_ENTRIES)
             {
-                if (sp < B2_STACK_ENTRIES)
-                {
-                    *top = ((uint64_t)group_base << 32) | group_bits;
-                    top += stack_stride;
-                }
-                else
-                    b2_report_fault(faults, B2_FAULT_STACK_OVERFLOW);
-                sp++; /* overflow is counted but dropped; the builder bounds the depth well below the stack size */
-            }
-
-            n_nodes++;
-#ifdef B2_TRAVERSE_TRACE
-            B2_TRAVERSE_TRACE(guard, node_index, group_base, group_bits, sp);
-#endif
-#if defined(__CUDA_ARCH__)
-            const B2NodeRaw raw = b2_load_node(bvh.nodes, node_index);
-            const float nox = __uint_as_float(raw.q0.x), noy = __uint_as_float(raw.q0.y), noz = __uint_as_float(raw.q0.z);
-            const uint32_t exyz = raw.q0.w;
-            const uint32_t n_child_base = raw.q1.x, n_tri_base = raw.q1.y;
-            const uint32_t meta_lo = raw.q1.z, meta_hi = raw.q1.w;
-            const uint32_t qw[12] = { raw.q2.x, raw.q2.y, raw.q2.z, raw.q2.w, raw.q3.x, raw.q3.y, raw.q3.z, raw.q3.w, raw.q4.x, raw.q4.y, raw.q4.z, raw.q4.w };
-#else
-            const B2Node& nd = bvh.nodes[node_index];
-            const float nox = nd.ox, noy = nd.oy, noz = nd.oz;
-            const uint32_t exyz = nd.exyz_imask;
-            const uint32_t n_child_base = nd.child_base, n_tri_base = nd.tri_base;
-            uint32_t meta_lo, meta_hi, qw[12];
-            {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(nd.meta);
-                meta_lo = w[0];
-                meta_hi = w[1];
-                for (int k = 0; k < 12; k++)
-                    qw[k] = w[2 + k];
-            }
-#endif
-            /* grid step 2^(e-127) per axis, folded into the reciprocal direction */
-            const float sx = b2_uint_as_float((exyz & 0xFFu) << 23) * idx;
-            const float sy = b2_uint_as_float(((exyz >> 8) & 0xFFu) << 23) * idy;
-            const float sz = b2_uint_as_float(((exyz >> 16) & 0xFFu) << 23) * idz;
-            const float bx = (nox - org.x) * idx;
-            const float by = (noy - org.y) * idy;
-            const float bz = (noz - org.z) * idz;
-
-            uint32_t hit_bits = 0;
-#pragma unroll
-            for (int c = 0; c < 8; c++)
-            {
-                const uint32_t meta = ((c < 4 ? meta_lo : meta_hi) >> ((c & 3) * 8)) & 0xFFu;
-                if (meta == 0)
-                    continue;
-                const int w = c >> 2, sh = (c & 3) * 8;
-                const float lox = (float)((qw[0 + w] >> sh) & 0xFFu), loy = (float)((qw[2 + w] >> sh) & 0xFFu), loz = (float)((qw[4 + w] >> sh) & 0xFFu);
-                const float hix = (float)((qw[6 + w] >> sh) & 0xFFu), hiy = (float)((qw[8 + w] >> sh) & 0xFFu), hiz = (float)((qw[10 + w] >> sh) & 0xFFu);
-                const float tx0 = (dir.x < 0.0f ? hix : lox) * sx + bx, tx1 = (dir.x < 0.0f ? lox : hix) * sx + bx;
-                const float ty0 = (dir.y < 0.0f ? hiy : loy) * sy + by, ty1 = (dir.y < 0.0f ? loy : hiy) * sy + by;
-                const float tz0 = (dir.z < 0.0f ? hiz : loz) * sz + bz, tz1 = (dir.z < 0.0f ? loz : hiz) * sz + bz;
-                /* widened by a few ulps so fp32 rounding in the slab arithmetic can never cull a box the exact
-                 * triangle test would hit */
-                const float t_enter = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f)) * 0.9999995f;
-                const float t_exit = fminf(fminf(tx1, ty1), fminf(tz1, t_far)) * 1.0000005f;
-                if (t_enter <= t_exit)
-                {
-                    const bool inner = (meta & 0x18u) == 0x18u && (meta >> 5) == 1u;
-                    const uint32_t bit_index = inner ? (24u + ((meta & 7u) ^ oct_inv)) : (meta & 0x1Fu);
-                    hit_bits |= (meta >> 5) << bit_index;
-                }
-            }
-            group_base = n_child_base;
-            group_bits = (hit_bits & 0xFF000000u) | (exyz >> 24);
-            tri_base = n_tri_base;
-            tri_bits = hit_bits & 0x00FFFFFFu;
-        }
-        else
-        {
-            group_bits = 0;
-        }
-
-        while (tri_bits != 0)
-        {
-            const uint32_t k = b2_bfind(tri_bits);
-            tri_bits &= ~(1u << k);
-            n_tris++;
-#if defined(__CUDA_ARCH__)
-            const float4* tp = reinterpret_cast<const float4*>(bvh.tris + tri_base + k);
-            const float4 ta = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-            const int prim = __float_as_int(ta.w);
-            const V3 a = v3(ta.x, ta.y, ta.z), e1 = v3(t1.x, t1.y, t1.z), e2 = v3(t2.x, t2.y, t2.z);
-#else
-            const B2Tri& tr = bvh.tris[tri_base + k];
-            const int prim = tr.prim;
-            const V3 a = v3(tr.ax, tr.ay, tr.az), e1 = v3(tr.e1x, tr.e1y, tr.e1z), e2 = v3(tr.e2x, tr.e2y, tr.e2z);
-#endif
-            if (prim == skip_prim)
-                continue;
-            float t, u, v;
-            if (!b2_intersect_triangle(org, dir, a, e1, e2, t, u, v))
-                continue;
-            if (ANY_HIT)
-            {
-                if (t < t_max)
-                {
-                    best.t = t; best.u = u; best.v = v; best.prim = prim; best.ng = cross(e1, e2);
-                    if (counters) { counters->rays += 1; counters->nodes += n_nodes; counters->tris += n_tris; }
-                    return best;
-                }
-            }
-            else if (t < t_far)
-            {
-                /* strictly closer. Equal-t candidates keep the first one found, like the reference's `<`; which
-                 * one is "first" depends on the acceleration structure (the documented "ties excepted"). */
-                best.t = t; best.u = u; best.v = v; best.prim = prim; best.ng = cross(e1, e2);
-                t_far = t;
-            }
-        }
-
-        if (group_bits <= 0x00FFFFFFu)
-        {
-            if (sp == 0)
-                break;
-            sp--;
-            if (sp < B2_STACK_ENTRIES)
-            {
-                top -= stack_stride;
-                const uint64_t e = *top;
-                group_base = (uint32_t)(e >> 32);
-                group_bits = (uint32_t)e;
+                *t.top = ((uint64_t)t.group_base << 32) | t.group_bits;
+                t.top += stack_stride;
             }
             else
-                group_bits = 0;
+                b2_report_fault(faults, B2_FAULT_STACK_OVERFLOW);
+            t.sp++; /* overflow is counted but dropped; the builder bounds the depth well below the stack size */
+        }
+
+        t.n_nodes++;
+#ifdef B2_TRAVERSE_TRACE
+        B2_TRAVERSE_TRACE(t.guard, node_index, t.group_base, t.group_bits, t.sp);
+#endif
+#if defined(__CUDA_ARCH__)
+        const B2NodeRaw raw = b2_load_node(bvh.nodes, node_index);
+        const float nox = __uint_as_float(raw.q0.x), noy = __uint_as_float(raw.q0.y), noz = __uint_as_float(raw.q0.z);
+        const uint32_t exyz = raw.q0.w;
+        const uint32_t n_child_base = raw.q1.x, n_tri_base = raw.q1.y;
+        const uint32_t meta_lo = raw.q1.z, meta_hi = raw.q1.w;
+        const uint32_t qw[12] = { raw.q2.x, raw.q2.y, raw.q2.z, raw.q2.w, raw.q3.x, raw.q3.y, raw.q3.z, raw.q3.w, raw.q4.x, raw.q4.y, raw.q4.z, raw.q4.w };
+#else
+        const B2Node& nd = bvh.nodes[node_index];
+        const float nox = nd.ox, noy = nd.oy, noz = nd.oz;
+        const uint32_t exyz = nd.exyz_imask;
+        const uint32_t n_child_base = nd.child_base, n_tri_base = nd.tri_base;
+        uint32_t meta_lo, meta_hi, qw[12];
+        {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(nd.meta);
+            meta_lo = w[0];
+            meta_hi = w[1];
+            for (int k = 0; k < 12; k++)
+                qw[k] = w[2 + k];
+        }
+#endif
+        /* grid step 2^(e-127) per axis, folded into the reciprocal direction */
+        const float sx = b2_uint_as_float((exyz & 0xFFu) << 23) * t.idx;
+        const float sy = b2_uint_as_float(((exyz >> 8) & 0xFFu) << 23) * t.idy;
+        const float sz = b2_uint_as_float(((exyz >> 16) & 0xFFu) << 23) * t.idz;
+        const float bx = (nox - org.x) * t.idx;
+        const float by = (noy - org.y) * t.idy;
+        const float bz = (noz - org.z) * t.idz;
+        const float t_far = t.t_far;
+
+        uint32_t hit_bits = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+        {
+            const uint32_t meta = ((c < 4 ? meta_lo : meta_hi) >> ((c & 3) * 8)) & 0xFFu;
+            if (meta == 0)
+                continue;
+            const int w = c >> 2, sh = (c & 3) * 8;
+            const float lox = (float)((qw[0 + w] >> sh) & 0xFFu), loy = (float)((qw[2 + w] >> sh) & 0xFFu), loz = (float)((qw[4 + w] >> sh) & 0xFFu);
+            const float hix = (float)((qw[6 + w] >> sh) & 0xFFu), hiy = (float)((qw[8 + w] >> sh) & 0xFFu), hiz = (float)((qw[10 + w] >> sh) & 0xFFu);
+            const float tx0 = (dir.x < 0.0f ? hix : lox) * sx + bx, tx1 = (dir.x < 0.0f ? lox : hix) * sx + bx;
+            const float ty0 = (dir.y < 0.0f ? hiy : loy) * sy + by, ty1 = (dir.y < 0.0f ? loy : hiy) * sy + by;
+            const float tz0 = (dir.z < 0.0f ? hiz : loz) * sz + bz, tz1 = (dir.z < 0.0f ? loz : hiz) * sz + bz;
+            /* widened by a few ulps so fp32 rounding in the slab arithmetic can never cull a box the exact
+             * triangle test would hit */
+            const float t_enter = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f)) * 0.9999995f;
+            const float t_exit = fminf(fminf(tx1, ty1), fminf(tz1, t_far)) * 1.0000005f;
+            if (t_enter <= t_exit)
+            {
+                const bool inner = (meta & 0x18u) == 0x18u && (meta >> 5) == 1u;
+                const uint32_t bit_index = inner ? (24u + ((meta & 7u) ^ oct_inv)) : (meta & 0x1Fu);
+                hit_bits |= (meta >> 5) << bit_index;
+            }
+        }
+        t.group_base = n_child_base;
+        t.group_bits = (hit_bits & 0xFF000000u) | (exyz >> 24);
+        tri_base = n_tri_base;
+        tri_bits = hit_bits & 0x00FFFFFFu;
+    }
+    else
+    {
+        t.group_bits = 0;
+    }
+
+    while (tri_bits != 0)
+    {
+        const uint32_t k = b2_bfind(tri_bits);
+        tri_bits &= ~(1u << k);
+        t.n_tris++;
+#if defined(__CUDA_ARCH__)
+        const float4* tp = reinterpret_cast<const float4*>(bvh.tris + tri_base + k);
+        const float4 ta = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+        const int prim = __float_as_int(ta.w);
+        const V3 a = v3(ta.x, ta.y, ta.z), e1 = v3(t1.x, t1.y, t1.z), e2 = v3(t2.x, t2.y, t2.z);
+#else
+        const B2Tri& tr = bvh.tris[tri_base + k];
+        const int prim = tr.prim;
+        const V3 a = v3(tr.ax, tr.ay, tr.az), e1 = v3(tr.e1x, tr.e1y, tr.e1z), e2 = v3(tr.e2x, tr.e2y, tr.e2z);
+#endif
+        if (prim == t.skip_prim)
+            continue;
+        float th, u, v;
+        if (!b2_intersect_triangle(org, dir, a, e1, e2, th, u, v))
+            continue;
+        if (t.any_hit)
+        {
+            if (th < t.t_max)
+            {
+                t.best.t = th; t.best.u = u; t.best.v = v; t.best.prim = prim; t.best.ng = cross(e1, e2);
+                return false;
+            }
+        }
+        else if (th < t.t_far)
+        {
+            /* strictly closer. Equal-t candidates keep the first one found, like the reference's `<`; which
+             * one is "first" depends on the acceleration structure (the documented "ties excepted"). */
+            t.best.t = th; t.best.u = u; t.best.v = v; t.best.prim = prim; t.best.ng = cross(e1, e2);
+            t.t_far = th;
         }
     }
-    if (counters) { counters->rays += 1; counters->nodes += n_nodes; counters->tris += n_tris; }
-    return best;
+
+    if (t.group_bits <= 0x00FFFFFFu)
+    {
+        if (t.sp == 0)
+            return false;
+        t.sp--;
+        if (t.sp < B2_STACK_ENTRIES)
+        {
+            t.top -= stack_stride;
+            const uint64_t e = *t.top;
+            t.group_base = (uint32_t)(e >> 32);
+            t.group_bits = (uint32_t)e;
+        }
+        else
+            t.group_bits = 0;
+    }
+    return true;
+}
+
+B2_HD B2Hit b2_traverse_rt(const bool ANY_HIT, const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int stack_stride,
+                           B2TraversalCounters* counters, unsigned int* faults)
+{
+    B2Traversal t;
+    b2_traverse_begin(t, ANY_HIT, org, dir, t_max, skip_prim, stack);
+    if (bvh.node_count != 0)
+    {
+        while (b2_traverse_step(t, bvh, stack_stride, faults))
+        {
+        }
+        if (counters) { counters->rays += 1; counters->nodes += t.n_nodes; counters->tris += t.n_tris; }
+    }
+    return t.best;
 }
 
 template <bool ANY_HIT>

@@ -445,16 +445,17 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
     return B2PT_ERR_NO_VARIANT;
 }
 
-/* B2PT_MEGAKERNEL=tiles selects the one-thread-per-pixel MegaKernel (A/B measurements); default: persistent warps */
-static int megakernel_persistent_default()
+/* B2PT_MEGAKERNEL selects the form of the MegaKernel (A/B measurements, tests): "phased" (default: persistent warps,
+ * bounce cut at its rays, block-pooled traversal), "persistent" (persistent warps, rays traced in place), "tiles" (one
+ * thread per pixel). Read at every launch so a test can switch between them. */
+static int megakernel_form()
 {
-    static int value = -1;
-    if (value < 0)
-    {
-        const char* e = std::getenv("B2PT_MEGAKERNEL");
-        value = (e && !std::strcmp(e, "tiles")) ? 0 : 1;
-    }
-    return value;
+    const char* e = std::getenv("B2PT_MEGAKERNEL");
+    if (e && !std::strcmp(e, "tiles"))
+        return 0;
+    if (e && !std::strcmp(e, "persistent"))
+        return 1;
+    return 2;
 }
 
 int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank, int world, void** args, b2pt_stream stream)
@@ -471,7 +472,7 @@ int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank
     geom.height = height;
     geom.rank = rank;
     geom.world = world;
-    geom.persistent = megakernel_persistent_default();
+    geom.persistent = megakernel_form();
     B2_CUDA(cudaEventRecord(kernel->start, s));
     B2_CUDA(kernel->entry->launch(rd, &geom, s));
     B2_CUDA(cudaEventRecord(kernel->stop, s));

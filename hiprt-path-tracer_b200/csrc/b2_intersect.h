@@ -315,8 +315,11 @@ B2_HD int effective_dielectric_priority(const Mat& m)
     return (V::BSDF_OVERRIDE == B2_BSDF_LAMBERTIAN || V::BSDF_OVERRIDE == B2_BSDF_OREN_NAYAR) ? 0 : (int)m.dielectric_priority;
 }
 
+/* `first`: the closest hit of (origin, direction) when the caller already traced it (the pooled tracer of the persistent
+ * MegaKernel); null = trace here. Re-traces after a skipped nested-dielectric boundary are always traced here. */
 template <class V>
-B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload& payload, HitInfo& out_hit, int last_hit_primitive_index, Rng& rng)
+B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload& payload, HitInfo& out_hit, int last_hit_primitive_index, Rng& rng,
+                               const B2Hit* first = nullptr)
 {
     const b2pt_render_data& rd = *ctx.rd;
     B2Hit hit;
@@ -329,7 +332,10 @@ B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload&
             b2_report_fault(ctx.faults, B2_FAULT_BOUNDARY_GUARD);
             return false;
         }
-        hit = b2_trace(ctx, false, origin, direction, 3.0e38f, last_hit_primitive_index);
+        if (first != nullptr && boundary_skips == 1)
+            hit = *first;
+        else
+            hit = b2_trace(ctx, false, origin, direction, 3.0e38f, last_hit_primitive_index);
         if (hit.prim < 0)
             return false;
 
@@ -393,10 +399,16 @@ struct LightRayHit
 };
 
 /* closest hit along a BSDF-sampled direction, returning what (emissive or not) was hit; t_max is 1e35 at every call site */
+B2_HD bool light_ray_hit_from(const b2pt_render_data& rd, const B2Hit& hit, float t_max, LightRayHit& out);
 B2_HD bool bsdf_light_sample_ray(const Ctx& ctx, V3 origin, V3 direction, float t_max, LightRayHit& out, int last_hit_primitive_index)
 {
-    const b2pt_render_data& rd = *ctx.rd;
     B2Hit hit = b2_trace(ctx, false, origin, direction, 3.0e38f, last_hit_primitive_index);
+    return light_ray_hit_from(*ctx.rd, hit, t_max, out);
+}
+
+/* what bsdf_light_sample_ray derives from the closest hit of its ray */
+B2_HD bool light_ray_hit_from(const b2pt_render_data& rd, const B2Hit& hit, float t_max, LightRayHit& out)
+{
     if (hit.prim < 0)
         return false;
     if (!(hit.t < t_max - 1.0e-4f))

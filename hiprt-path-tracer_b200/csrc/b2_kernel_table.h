@@ -13,7 +13,7 @@ struct B2LaunchGeom
 {
     int width, height;
     int rank, world;
-    int persistent; /* MegaKernel only: persistent warps with path regeneration (default) or one thread per pixel */
+    int persistent; /* MegaKernel only: 0 = one thread per pixel, 1 = persistent warps, 2 = persistent + phased (pooled rays) */
 };
 
 struct B2KernelEntry

@@ -1,0 +1,382 @@
+/*
+ * b2_nee.h -- next-event estimation cut at its rays, for the persistent MegaKernel of b2_kernels.cu.
+ *
+ * The reference's NEE strategies trace their rays in the middle of the shading code (sample_one_light_no_MIS /
+ * sample_one_light_MIS, /root/reference/src/Device/includes/LightSampling/Lights.h:25-226; sample_lights_RIS,
+ * RIS/RIS.h:18-262; evaluate_ReSTIR_DI_reservoir, ReSTIR/DI/FinalShading.h:16-101). Here each strategy is the same
+ * arithmetic and the same RNG draws in the same order, split into three parts around its (at most) two rays:
+ *     part1 -> ray #1 -> part2 -> ray #2 -> part3
+ * so that the kernel can trace the rays of a whole thread block together (one converged traversal loop fed from a
+ * shared ray pool) instead of every lane walking the BVH alone inside divergent shading code. The un-split functions
+ * (b2_lights.h, b2_ris.h, b2_restir_di_shading.h) stay the reference statement of the math: the host port and the
+ * one-thread-per-pixel kernels use them, and tests/ compare both forms against the same golden fixtures.
+ *
+ *   strategy            ray #1                                ray #2
+ *   ONE_LIGHT           shadow ray to the light sample        -
+ *   MIS                 shadow ray to the light sample        closest hit along the BSDF sample
+ *   RIS                 closest hit along BSDF candidate 0    shadow ray to the reservoir's survivor
+ *   ReSTIR DI, bounce 0 shadow ray to the reservoir's sample  -
+ *   (ReSTIR DI at later bounces = its later-bounces strategy, RIS by default)
+ * Envmap NEE (b2_envmap.h) and RIS BSDF candidates beyond the first keep tracing in place: rare, not pooled.
+ */
+#ifndef B2_NEE_H
+#define B2_NEE_H
+
+#include "b2_envmap.h"
+#include "b2_lights.h"
+#include "b2_restir_di_shading.h"
+#include "b2_ris.h"
+
+enum { B2_RAY_NONE = 0, B2_RAY_ANY_HIT = 1, B2_RAY_CLOSEST = 2 };
+
+struct RayRequest
+{
+    V3 origin, direction;
+    float t_max; /* as passed to the traversal: shadow rays carry (distance - 1e-4), closest-hit rays 3e38 */
+    int skip_prim;
+    int kind;
+};
+
+B2_HD void request_none(RayRequest& r) { r.kind = B2_RAY_NONE; }
+B2_HD void request_shadow(RayRequest& r, V3 origin, V3 direction, float distance, int skip_prim)
+{
+    /* shadow_ray_occluded, b2_intersect.h */
+    r.origin = origin;
+    r.direction = direction;
+    r.t_max = distance - 1.0e-4f;
+    r.skip_prim = skip_prim;
+    r.kind = B2_RAY_ANY_HIT;
+}
+B2_HD void request_closest(RayRequest& r, V3 origin, V3 direction, int skip_prim)
+{
+    /* bsdf_light_sample_ray, b2_intersect.h */
+    r.origin = origin;
+    r.direction = direction;
+    r.t_max = 3.0e38f;
+    r.skip_prim = skip_prim;
+    r.kind = B2_RAY_CLOSEST;
+}
+
+/* strategy used at this vertex (Lights.h:228-352) */
+template <class V>
+B2_HD int nee_strategy_at(int bounce)
+{
+    if (V::DIRECT != B2_LSS_RESTIR_DI || bounce == 0)
+        return V::DIRECT;
+    return V::LATER == B2_LATER_ONE_LIGHT ? B2_LSS_ONE_LIGHT : V::LATER == B2_LATER_BSDF ? B2_LSS_BSDF : V::LATER == B2_LATER_MIS ? B2_LSS_MIS : B2_LSS_RIS;
+}
+
+template <class V>
+struct Nee
+{
+    static constexpr bool HAS_ONE_LIGHT = V::DIRECT == B2_LSS_ONE_LIGHT || (V::DIRECT == B2_LSS_RESTIR_DI && V::LATER == B2_LATER_ONE_LIGHT);
+    static constexpr bool HAS_BSDF = V::DIRECT == B2_LSS_BSDF || (V::DIRECT == B2_LSS_RESTIR_DI && V::LATER == B2_LATER_BSDF);
+    static constexpr bool HAS_MIS = V::DIRECT == B2_LSS_MIS || (V::DIRECT == B2_LSS_RESTIR_DI && V::LATER == B2_LATER_MIS);
+    static constexpr bool HAS_RIS = V::DIRECT == B2_LSS_RIS || (V::DIRECT == B2_LSS_RESTIR_DI && V::LATER == B2_LATER_RIS);
+    static constexpr bool HAS_RESTIR = V::DIRECT == B2_LSS_RESTIR_DI;
+
+    int strategy;
+    bool active;              /* false: sample_emissive_geometry's early-outs (no emissives / white furnace) */
+    /* ONE_LIGHT, MIS */
+    LightSample light_sample;
+    V3 shadow_dir;
+    float distance_to_light;
+    float dot_light_source;
+    bool have_light_ray;
+    Rgb light_radiance;
+    /* BSDF, MIS */
+    Rgb bsdf_color;
+    V3 sampled_direction;
+    float bsdf_sample_pdf;
+    /* RIS */
+    RisReservoir reservoir;
+    int nb_light_candidates, nb_bsdf_candidates;
+    bool have_candidate_ray;
+    /* ReSTIR DI final shading */
+    DiReservoir di_reservoir;
+
+    /* ---- part 1: up to ray #1 ------------------------------------------------------------------------------- */
+    B2_HD void part1(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, int x, int y, RayRequest& ray)
+    {
+        const b2pt_render_data& rd = *ctx.rd;
+        request_none(ray);
+        strategy = nee_strategy_at<V>(payload.bounce);
+        active = true;
+        /* sample_emissive_geometry, Lights.h:313-352 */
+        if (rd.buffers.emissive_triangles_count == 0 && !(rd.world_settings.ambient_light_type == 2 && V::DIRECT == B2_LSS_RESTIR_DI))
+            active = false;
+        if (rd.bsdfs_data.white_furnace_mode && rd.bsdfs_data.white_furnace_mode_turn_off_emissives)
+            active = false;
+        if (!active)
+            return;
+
+        if (HAS_ONE_LIGHT && strategy == B2_LSS_ONE_LIGHT)
+        {
+            have_light_ray = false;
+            light_radiance = rgb(0.0f);
+            light_sample = sample_one_emissive_triangle<V>(rd, rng);
+            if (light_sample.area_measure_pdf <= 0.0f)
+                return;
+            V3 shadow_ray_direction = light_sample.point_on_light - hit.inter_point;
+            distance_to_light = length(shadow_ray_direction);
+            shadow_dir = shadow_ray_direction / distance_to_light;
+            dot_light_source = cosine_term_at_light_source(light_sample.light_source_normal, -shadow_dir);
+            if (dot_light_source > 0.0f)
+            {
+                have_light_ray = true;
+                request_shadow(ray, hit.inter_point, shadow_dir, distance_to_light, hit.primitive_index);
+            }
+        }
+        else if (HAS_MIS && strategy == B2_LSS_MIS)
+        {
+            have_light_ray = false;
+            light_radiance = rgb(0.0f);
+            light_sample = sample_one_emissive_triangle<V>(rd, rng);
+            if (light_sample.area_measure_pdf > 0.0f)
+            {
+                V3 shadow_ray_direction = light_sample.point_on_light - hit.inter_point;
+                distance_to_light = length(shadow_ray_direction);
+                shadow_dir = shadow_ray_direction / distance_to_light;
+                have_light_ray = true;
+                request_shadow(ray, hit.inter_point, shadow_dir, distance_to_light, hit.primitive_index);
+            }
+        }
+        else if (HAS_BSDF && strategy == B2_LSS_BSDF)
+        {
+            bsdf_part_sample(rd, payload, hit, view_direction, rng, B2_REGULARIZATION_CLASSIC, ray);
+        }
+        else if (HAS_RIS && strategy == B2_LSS_RIS)
+        {
+            ris_part1(ctx, payload, hit, view_direction, rng, ray);
+        }
+        else if (HAS_RESTIR && strategy == B2_LSS_RESTIR_DI)
+        {
+            /* sample_light_ReSTIR_DI + the head of evaluate_ReSTIR_DI_reservoir */
+            int pixel_index = x + y * rd.render_settings.render_resolution.x;
+            void* buffer = rd.render_settings.restir_di_settings.restir_output_reservoirs;
+            di_reservoir = di_load(rd, buffer, pixel_index);
+            if (di_reservoir.sample.is_envmap_sample() && rd.world_settings.ambient_light_type != 2)
+            {
+                di_reservoir.UCW = 0.0f;
+                reinterpret_cast<uint32_t*>(buffer)[DI_PLANE_UCW * di_plane_stride(rd) + pixel_index] = b2_float_as_uint(0.0f);
+            }
+            have_light_ray = false;
+            if (di_reservoir.UCW <= 0.0f)
+                return;
+            shadow_dir = di_light_sample_direction(rd, di_reservoir.sample, hit.inter_point, distance_to_light);
+            if (di_reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED)
+                return;
+            if (rd.render_settings.restir_di_settings.do_final_shading_visibility)
+            {
+                have_light_ray = true;
+                request_shadow(ray, hit.inter_point, shadow_dir, distance_to_light, hit.primitive_index);
+            }
+        }
+    }
+
+    /* ---- part 2: result of ray #1 -> up to ray #2 -------------------------------------------------------------- */
+    B2_HD void part2(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, const B2Hit& result1, RayRequest& ray)
+    {
+        const b2pt_render_data& rd = *ctx.rd;
+        request_none(ray);
+        if (!active)
+            return;
+        if (HAS_ONE_LIGHT && strategy == B2_LSS_ONE_LIGHT)
+        {
+            if (!have_light_ray)
+                return;
+            bool in_shadow = result1.prim >= 0;
+            if (!in_shadow)
+            {
+                float bsdf_pdf_value;
+                int incident_light_info = light_sample.incident_light_info;
+                BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, shadow_dir, &incident_light_info, &payload.volume_state, false,
+                                             &payload.material, payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_CLASSIC);
+                Rgb color = bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
+                if (bsdf_pdf_value != 0.0f)
+                {
+                    float light_sample_solid_angle_pdf = area_to_solid_angle_pdf(light_sample.area_measure_pdf, distance_to_light, dot_light_source);
+                    if (light_sample_solid_angle_pdf > 0.0f)
+                    {
+                        float cosine_term = fabsf(dot(hit.shading_normal, shadow_dir));
+                        light_radiance = light_sample.emission * cosine_term * color / light_sample_solid_angle_pdf / 1.0f;
+                    }
+                }
+            }
+        }
+        else if (HAS_MIS && strategy == B2_LSS_MIS)
+        {
+            if (have_light_ray)
+            {
+                bool in_shadow = result1.prim >= 0;
+                if (!in_shadow)
+                {
+                    float bsdf_pdf_value;
+                    int incident_light_info = B2_LOBE_NO_INFO;
+                    BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, shadow_dir, &incident_light_info, &payload.volume_state, false,
+                                                 &payload.material, payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
+                    Rgb color = bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
+                    if (bsdf_pdf_value > 0.0f)
+                    {
+                        float cos_theta_at_light_source = cosine_term_at_light_source(light_sample.light_source_normal, -shadow_dir);
+                        if (cos_theta_at_light_source > 1.0e-5f)
+                        {
+                            float light_sample_solid_angle_pdf = area_to_solid_angle_pdf(light_sample.area_measure_pdf, distance_to_light, cos_theta_at_light_source);
+                            float mis_weight = balance_heuristic(light_sample_solid_angle_pdf, bsdf_pdf_value);
+                            float cosine_term = fabsf(dot(hit.shading_normal, shadow_dir));
+                            light_radiance = color * cosine_term * light_sample.emission * mis_weight / light_sample_solid_angle_pdf / 1.0f;
+                        }
+                    }
+                }
+            }
+            bsdf_part_sample(rd, payload, hit, view_direction, rng, B2_REGULARIZATION_MIS, ray);
+        }
+        else if (HAS_RIS && strategy == B2_LSS_RIS)
+        {
+            ris_part2(ctx, payload, hit, view_direction, rng, result1, ray);
+        }
+        /* BSDF and ReSTIR DI final shading: no second ray */
+    }
+
+    /* ---- part 3: result of ray #2 (or of ray #1 for the strategies with a single ray) -> radiance ------------------------- */
+    B2_HD Rgb part3(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const B2Hit& result1, const B2Hit& result2)
+    {
+        const b2pt_render_data& rd = *ctx.rd;
+        if (!active)
+            return rgb(0.0f);
+        if (HAS_ONE_LIGHT && strategy == B2_LSS_ONE_LIGHT)
+            return light_radiance;
+        if (HAS_MIS && strategy == B2_LSS_MIS)
+            return light_radiance + bsdf_part_radiance(rd, hit, result2, true);
+        if (HAS_BSDF && strategy == B2_LSS_BSDF)
+            return bsdf_part_radiance(rd, hit, result1, false);
+        if (HAS_RIS && strategy == B2_LSS_RIS)
+            return ris_part3(ctx, payload, hit, view_direction, result2);
+        if (HAS_RESTIR && strategy == B2_LSS_RESTIR_DI)
+            return restir_part3(ctx, payload, hit, view_direction, result1);
+        return rgb(0.0f);
+    }
+
+    /* ---- BSDF-sample half of sample_one_light_bsdf / sample_one_light_MIS ------------------------------------------------ */
+    B2_HD void bsdf_part_sample(const b2pt_render_data& rd, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, int regularization, RayRequest& ray)
+    {
+        int incident_light_info = B2_LOBE_NO_INFO;
+        BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, v3(0.0f), &incident_light_info, &payload.volume_state, false,
+                                     &payload.material, payload.bounce, payload.accumulated_roughness, regularization);
+        bsdf_color = bsdf_sample<V>(rd, bctx, sampled_direction, bsdf_sample_pdf, rng);
+        if (bsdf_sample_pdf > 0.0f)
+            request_closest(ray, hit.inter_point, sampled_direction, hit.primitive_index);
+    }
+
+    B2_HD Rgb bsdf_part_radiance(const b2pt_render_data& rd, const HitInfo& hit, const B2Hit& result, bool with_mis)
+    {
+        Rgb radiance = rgb(0.0f);
+        if (bsdf_sample_pdf > 0.0f)
+        {
+            LightRayHit light_hit;
+            bool found = light_ray_hit_from(rd, result, 1.0e35f, light_hit);
+            if (found && !is_black(light_hit.emission) && cosine_term_at_light_source(light_hit.geometric_normal, -sampled_direction) > 0.0f)
+            {
+                if (with_mis)
+                {
+                    float light_pdf_solid_angle = pdf_of_emissive_triangle_hit_solid_angle<V>(rd, light_hit, sampled_direction);
+                    float mis_weight = balance_heuristic(bsdf_sample_pdf, light_pdf_solid_angle);
+                    float cosine_term = fabsf(dot(hit.shading_normal, sampled_direction));
+                    radiance = bsdf_color * cosine_term * light_hit.emission * mis_weight / bsdf_sample_pdf;
+                }
+                else
+                {
+                    float cosine_term = fabsf(dot(hit.shading_normal, sampled_direction));
+                    radiance = bsdf_color * cosine_term * light_hit.emission / bsdf_sample_pdf;
+                }
+            }
+        }
+        return radiance;
+    }
+
+    /* ---- RIS (RIS.h:83-262) ------------------------------------------------------------------------------------ */
+    /* the light-candidate loop, then the sampling half of BSDF candidate 0 */
+    B2_HD void ris_part1(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, RayRequest& ray)
+    {
+        const b2pt_render_data& rd = *ctx.rd;
+        const bool low_res = do_render_low_resolution(rd.render_settings);
+        nb_light_candidates = low_res ? 1 : rd.render_settings.ris_settings.number_of_light_candidates;
+        nb_bsdf_candidates = low_res ? 1 : rd.render_settings.ris_settings.number_of_bsdf_candidates;
+        if (!can_do_light_sampling(payload.material))
+            nb_light_candidates = 0;
+        have_candidate_ray = false;
+        reservoir.init();
+        /* sample_lights_RIS returns black before anything else when there is no emissive triangle: no candidates at all,
+         * reservoir.end() in part 2 then leaves UCW = 0 and nothing is traced or drawn from the RNG */
+        if (rd.buffers.emissive_triangles_count == 0)
+        {
+            nb_light_candidates = 0;
+            nb_bsdf_candidates = 0;
+            return;
+        }
+
+        for (int i = 0; i < nb_light_candidates; i++)
+            ris_light_candidate<V>(ctx, payload, hit, view_direction, rng, nb_light_candidates, nb_bsdf_candidates, reservoir);
+
+        if (nb_bsdf_candidates > 0)
+        {
+            int incident_light_info = B2_LOBE_NO_INFO;
+            BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, v3(0.0f), &incident_light_info, &payload.volume_state, false, &payload.material,
+                                         payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
+            bsdf_sample_pdf = 0.0f;
+            bsdf_color = bsdf_sample<V>(rd, bctx, sampled_direction, bsdf_sample_pdf, rng);
+            if (bsdf_sample_pdf > 0.0f)
+            {
+                have_candidate_ray = true;
+                request_closest(ray, hit.inter_point, sampled_direction, hit.primitive_index);
+            }
+        }
+    }
+
+    /* the rest of BSDF candidate 0, BSDF candidates 1.. (traced in place), reservoir.end(), head of the survivor's shading */
+    B2_HD void ris_part2(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, const B2Hit& result1, RayRequest& ray)
+    {
+        const b2pt_render_data& rd = *ctx.rd;
+        if (nb_bsdf_candidates > 0)
+        {
+            LightRayHit light_hit;
+            bool hit_found = have_candidate_ray && light_ray_hit_from(rd, result1, 1.0e35f, light_hit);
+            ris_bsdf_candidate_finish<V>(rd, hit, rng, nb_light_candidates, nb_bsdf_candidates, bsdf_color, sampled_direction, bsdf_sample_pdf, hit_found, light_hit, reservoir);
+            for (int i = 1; i < nb_bsdf_candidates; i++)
+                ris_bsdf_candidate<V>(ctx, payload, hit, view_direction, rng, nb_light_candidates, nb_bsdf_candidates, reservoir);
+        }
+        reservoir.end();
+
+        /* evaluate_ris_reservoir_sample up to its shadow ray */
+        have_light_ray = false;
+        if (reservoir.UCW <= 0.0f)
+            return;
+        V3 shadow_ray_direction = reservoir.sample.point_on_light_source - hit.inter_point;
+        distance_to_light = length(shadow_ray_direction);
+        shadow_dir = shadow_ray_direction / distance_to_light;
+        if (!reservoir.sample.is_bsdf_sample)
+        {
+            have_light_ray = true;
+            request_shadow(ray, hit.inter_point, shadow_dir, distance_to_light, hit.primitive_index);
+        }
+    }
+
+    B2_HD Rgb ris_part3(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const B2Hit& result2)
+    {
+        if (reservoir.UCW <= 0.0f)
+            return rgb(0.0f);
+        bool in_shadow = have_light_ray ? result2.prim >= 0 : false;
+        return ris_shade_survivor<V>(ctx, payload, hit, view_direction, reservoir, shadow_dir, in_shadow);
+    }
+
+    /* ---- ReSTIR DI final shading (FinalShading.h:16-101) after its shadow ray --------------------------------------------- */
+    B2_HD Rgb restir_part3(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const B2Hit& result1)
+    {
+        if (di_reservoir.UCW <= 0.0f)
+            return rgb(0.0f);
+        bool in_shadow = have_light_ray ? result1.prim >= 0 : false;
+        return restir_di_shade_sample<V>(ctx, payload, hit, view_direction, di_reservoir, shadow_dir, distance_to_light, in_shadow);
+    }
+};
+
+#endif

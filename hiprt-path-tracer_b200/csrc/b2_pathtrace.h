@@ -14,6 +14,7 @@
 #include "b2_principled.h"
 #include "b2_ris.h"
 #include "b2_restir_di_shading.h"
+#include "b2_nee.h"
 
 #if defined(__CUDA_ARCH__)
 #define B2_ATOMIC_ADD_U32(ptr, v) atomicAdd((ptr), (v))
@@ -359,11 +360,21 @@ B2_HD Rgb sample_emissive_geometry(const Ctx& ctx, Payload& payload, const HitIn
 
 /* Lights.h:364-423 */
 template <class V>
+B2_HD Rgb estimate_direct_lighting_from(const Ctx& ctx, Payload& payload, HitInfo& hit, V3 view_direction, Rng& rng, Rgb emissive_contribution);
+
+template <class V>
 B2_HD Rgb estimate_direct_lighting(const Ctx& ctx, Payload& payload, HitInfo& hit, V3 view_direction, int x, int y, Rng& rng)
+{
+    Rgb emissive_contribution = sample_emissive_geometry<V>(ctx, payload, hit, view_direction, rng, x, y);
+    return estimate_direct_lighting_from<V>(ctx, payload, hit, view_direction, rng, emissive_contribution);
+}
+
+/* everything of estimate_direct_lighting that follows the emissive-geometry sample */
+template <class V>
+B2_HD Rgb estimate_direct_lighting_from(const Ctx& ctx, Payload& payload, HitInfo& hit, V3 view_direction, Rng& rng, Rgb emissive_contribution)
 {
     const b2pt_render_data& rd = *ctx.rd;
     Rgb total = rgb(0.0f);
-    Rgb emissive_contribution = sample_emissive_geometry<V>(ctx, payload, hit, view_direction, rng, x, y);
     Rgb envmap_contribution = sample_environment_map<V>(ctx, payload, hit, view_direction, rng);
 
     emissive_contribution = clamp_light_contribution(emissive_contribution, rd.render_settings.direct_contribution_clamp, payload.bounce == 0);
@@ -608,6 +619,85 @@ B2_HD void megakernel_primary_miss(const Ctx& ctx, uint32_t x, uint32_t y, uint3
         return;
     rd.aux_buffers.still_one_ray_active[0] = 1;
     accumulate_color(rd, ray_color, pixel_index);
+}
+
+/* ---- the bounce cut at its rays (b2_nee.h) for the phased persistent kernel ------------------------------------------------
+ *   [main ray] stage A [ray #1] stage B [ray #2] stage C [next main ray] ...
+ * Same operations and RNG draws as megakernel_bounce, in the same order. */
+template <class V>
+struct BouncePhase
+{
+    Nee<V> nee;
+    bool nee_on;
+};
+
+/* Consumes the closest hit of the main ray (bounce > 0; `main_hit` may be null = trace here) or the G-buffer hit (bounce 0),
+ * then runs NEE up to its first ray. Returns false when the path ended here (escaped: background gathered). */
+template <class V>
+B2_HD bool megakernel_stage_a(const Ctx& ctx, PathState& s, const B2Hit* main_hit, BouncePhase<V>& ph, RayRequest& ray1)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    Payload& payload = s.payload;
+    HitInfo& hit = s.hit;
+    const int bounce = payload.bounce;
+    request_none(ray1);
+    ph.nee_on = false;
+
+    if (bounce > 0)
+        s.intersection_found = trace_main_path_ray<V>(ctx, s.ray_origin, s.ray_direction, payload, hit, hit.primitive_index, s.rng, main_hit);
+
+    if (!s.intersection_found)
+    {
+        payload.ray_color += miss_gather_envmap<V>(rd, payload.throughput, s.ray_direction, payload.bounce, s.pixel_index);
+        payload.next_ray_state = B2_RAY_MISSED;
+        sanity_check(rd, payload.ray_color, s.x, s.y);
+        return false;
+    }
+    if (bounce == 0)
+        store_denoiser_aovs(rd, s.pixel_index, hit.shading_normal, payload.material.base_color);
+    if (bounce > 0 || rd.render_settings.enable_direct)
+    {
+        ph.nee_on = true;
+        ph.nee.part1(ctx, payload, hit, -s.ray_direction, s.rng, s.x, s.y, ray1);
+    }
+    return true;
+}
+
+template <class V>
+B2_HD void megakernel_stage_b(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, const B2Hit& result1, RayRequest& ray2)
+{
+    request_none(ray2);
+    if (ph.nee_on)
+        ph.nee.part2(ctx, s.payload, s.hit, -s.ray_direction, s.rng, result1, ray2);
+}
+
+/* Finishes NEE, samples the next direction. Returns true when the path continues: (s.ray_origin, s.ray_direction) is the next
+ * main ray, to be traced as a closest-hit ray that skips s.hit.primitive_index. */
+template <class V>
+B2_HD bool megakernel_stage_c(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, const B2Hit& result1, const B2Hit& result2)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    Payload& payload = s.payload;
+    HitInfo& hit = s.hit;
+    if (ph.nee_on)
+    {
+        /* sample_emissive_geometry: strategy result + self-emission of emissive textures (textures are refused at upload) */
+        Rgb emissive_contribution = rgb(0.0f);
+        if (ph.nee.active)
+        {
+            Rgb material_self_textured_emission = rgb(0.0f);
+            if (payload.material.emissive_texture_used)
+                material_self_textured_emission = payload.material.emission;
+            emissive_contribution = ph.nee.part3(ctx, payload, hit, -s.ray_direction, result1, result2) / 1.0f + material_self_textured_emission;
+        }
+        payload.ray_color += estimate_direct_lighting_from<V>(ctx, payload, hit, -s.ray_direction, s.rng, emissive_contribution);
+        sanity_check(rd, payload.ray_color, s.x, s.y);
+    }
+    bool valid_indirect_bounce = compute_next_indirect_bounce<V>(ctx, payload, hit, -s.ray_direction, s.ray_origin, s.ray_direction, s.rng);
+    if (!valid_indirect_bounce)
+        return false;
+    payload.bounce++;
+    return payload.bounce < s.nb_bounces + 1;
 }
 
 template <class V>

@@ -269,25 +269,14 @@ B2_HD float di_target_function(const Ctx& ctx, const DiSample& sample, DiSurface
     return target_function;
 }
 
-/* evaluate_ReSTIR_DI_reservoir, DI/FinalShading.h:16-101 */
+/* evaluate_ReSTIR_DI_reservoir once the sample's visibility is known (DI/FinalShading.h:44-99) */
 template <class V>
-B2_HD Rgb evaluate_ReSTIR_DI_reservoir(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const DiReservoir& reservoir)
+B2_HD Rgb restir_di_shade_sample(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const DiReservoir& reservoir, V3 shadow_ray_direction, float distance_to_light,
+                                 bool in_shadow)
 {
     const b2pt_render_data& rd = *ctx.rd;
-    Rgb final_color = rgb(0.0f);
-    if (reservoir.UCW <= 0.0f)
-        return rgb(0.0f);
-
     const DiSample& sample = reservoir.sample;
-    float distance_to_light;
-    V3 shadow_ray_direction = di_light_sample_direction(rd, sample, hit.inter_point, distance_to_light);
-
-    bool in_shadow = false;
-    if (sample.flags & B2_DI_FLAGS_UNOCCLUDED)
-        in_shadow = false;
-    else if (rd.render_settings.restir_di_settings.do_final_shading_visibility)
-        in_shadow = shadow_ray_occluded(ctx, hit.inter_point, shadow_ray_direction, distance_to_light, hit.primitive_index);
-
+    Rgb final_color = rgb(0.0f);
     if (!in_shadow)
     {
         float bsdf_pdf_value;
@@ -316,6 +305,26 @@ B2_HD Rgb evaluate_ReSTIR_DI_reservoir(const Ctx& ctx, Payload& payload, const H
         }
     }
     return final_color;
+}
+
+/* evaluate_ReSTIR_DI_reservoir, DI/FinalShading.h:16-101 */
+template <class V>
+B2_HD Rgb evaluate_ReSTIR_DI_reservoir(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const DiReservoir& reservoir)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    if (reservoir.UCW <= 0.0f)
+        return rgb(0.0f);
+
+    const DiSample& sample = reservoir.sample;
+    float distance_to_light;
+    V3 shadow_ray_direction = di_light_sample_direction(rd, sample, hit.inter_point, distance_to_light);
+
+    bool in_shadow = false;
+    if (sample.flags & B2_DI_FLAGS_UNOCCLUDED)
+        in_shadow = false;
+    else if (rd.render_settings.restir_di_settings.do_final_shading_visibility)
+        in_shadow = shadow_ray_occluded(ctx, hit.inter_point, shadow_ray_direction, distance_to_light, hit.primitive_index);
+    return restir_di_shade_sample<V>(ctx, payload, hit, view_direction, reservoir, shadow_ray_direction, distance_to_light, in_shadow);
 }
 
 /* sample_light_ReSTIR_DI, DI/FinalShading.h:103-125 (validate_reservoir writes the killed UCW back, like the reference's

@@ -83,6 +83,111 @@ B2_HD bool check_minimum_light_contribution(float minimum_contribution, float co
     return true;
 }
 
+/* One light candidate of the RIS reservoir (RIS.h:103-163): sample, target function, MIS weight, stream into the reservoir. */
+template <class V>
+B2_HD void ris_light_candidate(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, int nb_light_candidates, int nb_bsdf_candidates,
+                               RisReservoir& reservoir)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    float target_function = 0.0f;
+    float candidate_weight = 0.0f;
+    LightSample light_sample = sample_one_emissive_triangle<V>(rd, rng);
+
+    if (light_sample.area_measure_pdf > 0.0f)
+    {
+        V3 to_light_direction = light_sample.point_on_light - hit.inter_point;
+        float distance_to_light = length(to_light_direction);
+        to_light_direction = to_light_direction / distance_to_light;
+        float cosine_at_light_source = cosine_term_at_light_source(light_sample.light_source_normal, -to_light_direction);
+        float cosine_at_evaluated_point = fabsf(dot(hit.shading_normal, to_light_direction));
+        if (cosine_at_evaluated_point > 0.0f && cosine_at_light_source > 1.0e-6f)
+        {
+            float bsdf_pdf_value = 0.0f;
+            bool contributes_enough = check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, light_sample.emission / light_sample.area_measure_pdf);
+            if (!contributes_enough)
+                target_function = 0.0f;
+            else
+            {
+                int incident_light_info = B2_LOBE_NO_INFO;
+                BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, to_light_direction, &incident_light_info, &payload.volume_state, false,
+                                             &payload.material, payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
+                Rgb bsdf_color = bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
+                Rgb light_contribution = bsdf_color * light_sample.emission * cosine_at_evaluated_point;
+                contributes_enough = check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, light_contribution / bsdf_pdf_value / light_sample.area_measure_pdf);
+                if (!contributes_enough)
+                    target_function = 0.0f;
+                else
+                    target_function = luminance(light_contribution);
+            }
+            float solid_angle_light_pdf = area_to_solid_angle_pdf(light_sample.area_measure_pdf, distance_to_light, cosine_at_light_source);
+            float mis_weight = balance_heuristic(solid_angle_light_pdf, (float)nb_light_candidates, bsdf_pdf_value, (float)nb_bsdf_candidates);
+            candidate_weight = mis_weight * target_function / solid_angle_light_pdf;
+        }
+    }
+
+    RisSample light_RIS_sample = ris_sample_defaults();
+    light_RIS_sample.is_bsdf_sample = false;
+    light_RIS_sample.point_on_light_source = light_sample.point_on_light;
+    light_RIS_sample.target_function = target_function;
+    light_RIS_sample.emission = light_sample.emission;
+    reservoir.add_one_candidate(light_RIS_sample, candidate_weight, rng);
+}
+
+/* The part of a BSDF candidate (RIS.h:165-243) that follows its ray: `hit_found` / `light_hit` are what
+ * bsdf_light_sample_ray returned for the sampled direction (hit_found is false when the sample's pdf was 0). */
+template <class V>
+B2_HD void ris_bsdf_candidate_finish(const b2pt_render_data& rd, const HitInfo& hit, Rng& rng, int nb_light_candidates, int nb_bsdf_candidates, Rgb bsdf_color,
+                                     V3 sampled_bsdf_direction, float bsdf_sample_pdf, bool hit_found, const LightRayHit& light_hit, RisReservoir& reservoir)
+{
+    float target_function = 0.0f;
+    float candidate_weight = 0.0f;
+    RisSample bsdf_RIS_sample = ris_sample_defaults();
+    if (bsdf_sample_pdf > 0.0f)
+    {
+        if (hit_found && !is_black(light_hit.emission) && cosine_term_at_light_source(light_hit.geometric_normal, -sampled_bsdf_direction) > 0.0f)
+        {
+            float cosine_at_evaluated_point = fabsf(dot(hit.shading_normal, sampled_bsdf_direction));
+            Rgb light_contribution = bsdf_color * light_hit.emission * cosine_at_evaluated_point;
+            target_function = luminance(light_contribution);
+
+            float light_pdf = pdf_of_emissive_triangle_hit_solid_angle<V>(rd, light_hit, sampled_bsdf_direction);
+            bool contributes_enough = bsdf_sample_pdf <= 0.0f || check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, light_contribution / light_pdf / bsdf_sample_pdf);
+            if (!contributes_enough)
+                target_function = 0.0f;
+
+            float mis_weight = balance_heuristic(bsdf_sample_pdf, (float)nb_bsdf_candidates, light_pdf, (float)nb_light_candidates);
+            candidate_weight = mis_weight * target_function / bsdf_sample_pdf;
+
+            bsdf_RIS_sample.emission = light_hit.emission;
+            bsdf_RIS_sample.point_on_light_source = hit.inter_point + sampled_bsdf_direction * light_hit.distance;
+            bsdf_RIS_sample.is_bsdf_sample = true;
+            bsdf_RIS_sample.bsdf_sample_contribution = bsdf_color;
+            bsdf_RIS_sample.bsdf_sample_cosine_term = cosine_at_evaluated_point;
+            bsdf_RIS_sample.target_function = target_function;
+        }
+    }
+    reservoir.add_one_candidate(bsdf_RIS_sample, candidate_weight, rng);
+}
+
+/* One whole BSDF candidate: sample, trace, finish. */
+template <class V>
+B2_HD void ris_bsdf_candidate(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, int nb_light_candidates, int nb_bsdf_candidates,
+                              RisReservoir& reservoir)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    float bsdf_sample_pdf = 0.0f;
+    V3 sampled_bsdf_direction;
+    int incident_light_info = B2_LOBE_NO_INFO;
+    BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, v3(0.0f), &incident_light_info, &payload.volume_state, false, &payload.material,
+                                 payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
+    Rgb bsdf_color = bsdf_sample<V>(rd, bctx, sampled_bsdf_direction, bsdf_sample_pdf, rng);
+    LightRayHit light_hit;
+    bool hit_found = false;
+    if (bsdf_sample_pdf > 0.0f)
+        hit_found = bsdf_light_sample_ray(ctx, hit.inter_point, sampled_bsdf_direction, 1.0e35f, light_hit, hit.primitive_index);
+    ris_bsdf_candidate_finish<V>(rd, hit, rng, nb_light_candidates, nb_bsdf_candidates, bsdf_color, sampled_bsdf_direction, bsdf_sample_pdf, hit_found, light_hit, reservoir);
+}
+
 template <class V>
 B2_HD RisReservoir sample_bsdf_and_lights_RIS_reservoir(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng)
 {
@@ -96,116 +201,20 @@ B2_HD RisReservoir sample_bsdf_and_lights_RIS_reservoir(const Ctx& ctx, Payload&
     RisReservoir reservoir;
     reservoir.init();
     for (int i = 0; i < nb_light_candidates; i++)
-    {
-        float target_function = 0.0f;
-        float candidate_weight = 0.0f;
-        LightSample light_sample = sample_one_emissive_triangle<V>(rd, rng);
-
-        if (light_sample.area_measure_pdf > 0.0f)
-        {
-            V3 to_light_direction = light_sample.point_on_light - hit.inter_point;
-            float distance_to_light = length(to_light_direction);
-            to_light_direction = to_light_direction / distance_to_light;
-            float cosine_at_light_source = cosine_term_at_light_source(light_sample.light_source_normal, -to_light_direction);
-            float cosine_at_evaluated_point = fabsf(dot(hit.shading_normal, to_light_direction));
-            if (cosine_at_evaluated_point > 0.0f && cosine_at_light_source > 1.0e-6f)
-            {
-                float bsdf_pdf_value = 0.0f;
-                bool contributes_enough = check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, light_sample.emission / light_sample.area_measure_pdf);
-                if (!contributes_enough)
-                    target_function = 0.0f;
-                else
-                {
-                    int incident_light_info = B2_LOBE_NO_INFO;
-                    BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, to_light_direction, &incident_light_info, &payload.volume_state, false,
-                                                 &payload.material, payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
-                    Rgb bsdf_color = bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
-                    Rgb light_contribution = bsdf_color * light_sample.emission * cosine_at_evaluated_point;
-                    contributes_enough = check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, light_contribution / bsdf_pdf_value / light_sample.area_measure_pdf);
-                    if (!contributes_enough)
-                        target_function = 0.0f;
-                    else
-                        target_function = luminance(light_contribution);
-                }
-                float solid_angle_light_pdf = area_to_solid_angle_pdf(light_sample.area_measure_pdf, distance_to_light, cosine_at_light_source);
-                float mis_weight = balance_heuristic(solid_angle_light_pdf, (float)nb_light_candidates, bsdf_pdf_value, (float)nb_bsdf_candidates);
-                candidate_weight = mis_weight * target_function / solid_angle_light_pdf;
-            }
-        }
-
-        RisSample light_RIS_sample = ris_sample_defaults();
-        light_RIS_sample.is_bsdf_sample = false;
-        light_RIS_sample.point_on_light_source = light_sample.point_on_light;
-        light_RIS_sample.target_function = target_function;
-        light_RIS_sample.emission = light_sample.emission;
-        reservoir.add_one_candidate(light_RIS_sample, candidate_weight, rng);
-    }
-
+        ris_light_candidate<V>(ctx, payload, hit, view_direction, rng, nb_light_candidates, nb_bsdf_candidates, reservoir);
     for (int i = 0; i < nb_bsdf_candidates; i++)
-    {
-        float bsdf_sample_pdf = 0.0f;
-        float target_function = 0.0f;
-        float candidate_weight = 0.0f;
-        V3 sampled_bsdf_direction;
-        int incident_light_info = B2_LOBE_NO_INFO;
-        BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, v3(0.0f), &incident_light_info, &payload.volume_state, false, &payload.material,
-                                     payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
-        Rgb bsdf_color = bsdf_sample<V>(rd, bctx, sampled_bsdf_direction, bsdf_sample_pdf, rng);
-
-        RisSample bsdf_RIS_sample = ris_sample_defaults();
-        if (bsdf_sample_pdf > 0.0f)
-        {
-            LightRayHit light_hit;
-            bool hit_found = bsdf_light_sample_ray(ctx, hit.inter_point, sampled_bsdf_direction, 1.0e35f, light_hit, hit.primitive_index);
-            if (hit_found && !is_black(light_hit.emission) && cosine_term_at_light_source(light_hit.geometric_normal, -sampled_bsdf_direction) > 0.0f)
-            {
-                float cosine_at_evaluated_point = fabsf(dot(hit.shading_normal, sampled_bsdf_direction));
-                Rgb light_contribution = bsdf_color * light_hit.emission * cosine_at_evaluated_point;
-                target_function = luminance(light_contribution);
-
-                float light_pdf = pdf_of_emissive_triangle_hit_solid_angle<V>(rd, light_hit, sampled_bsdf_direction);
-                bool contributes_enough = bsdf_sample_pdf <= 0.0f || check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, light_contribution / light_pdf / bsdf_sample_pdf);
-                if (!contributes_enough)
-                    target_function = 0.0f;
-
-                float mis_weight = balance_heuristic(bsdf_sample_pdf, (float)nb_bsdf_candidates, light_pdf, (float)nb_light_candidates);
-                candidate_weight = mis_weight * target_function / bsdf_sample_pdf;
-
-                bsdf_RIS_sample.emission = light_hit.emission;
-                bsdf_RIS_sample.point_on_light_source = hit.inter_point + sampled_bsdf_direction * light_hit.distance;
-                bsdf_RIS_sample.is_bsdf_sample = true;
-                bsdf_RIS_sample.bsdf_sample_contribution = bsdf_color;
-                bsdf_RIS_sample.bsdf_sample_cosine_term = cosine_at_evaluated_point;
-                bsdf_RIS_sample.target_function = target_function;
-            }
-        }
-        reservoir.add_one_candidate(bsdf_RIS_sample, candidate_weight, rng);
-    }
-
+        ris_bsdf_candidate<V>(ctx, payload, hit, view_direction, rng, nb_light_candidates, nb_bsdf_candidates, reservoir);
     reservoir.end();
     return reservoir;
 }
 
+/* The survivor's shading once its visibility is known (RIS.h:38-81); `direction` = normalised direction to the sample. */
 template <class V>
-B2_HD Rgb evaluate_ris_reservoir_sample(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const RisReservoir& reservoir)
+B2_HD Rgb ris_shade_survivor(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const RisReservoir& reservoir, V3 shadow_ray_direction_normalized, bool in_shadow)
 {
     const b2pt_render_data& rd = *ctx.rd;
-    Rgb final_color = rgb(0.0f);
-    if (reservoir.UCW <= 0.0f)
-        return rgb(0.0f);
-
     const RisSample& sample = reservoir.sample;
-    V3 evaluated_point = hit.inter_point;
-    V3 shadow_ray_direction = sample.point_on_light_source - evaluated_point;
-    float distance_to_light = length(shadow_ray_direction);
-    V3 shadow_ray_direction_normalized = shadow_ray_direction / distance_to_light;
-
-    bool in_shadow;
-    if (sample.is_bsdf_sample)
-        in_shadow = false;
-    else
-        in_shadow = shadow_ray_occluded(ctx, evaluated_point, shadow_ray_direction_normalized, distance_to_light, hit.primitive_index);
-
+    Rgb final_color = rgb(0.0f);
     if (!in_shadow)
     {
         float bsdf_pdf_value;
@@ -229,6 +238,26 @@ B2_HD Rgb evaluate_ris_reservoir_sample(const Ctx& ctx, Payload& payload, const 
             final_color /= 1.0f; /* NEE++ unoccluded probability (NEE++ off) */
     }
     return final_color;
+}
+
+template <class V>
+B2_HD Rgb evaluate_ris_reservoir_sample(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const RisReservoir& reservoir)
+{
+    if (reservoir.UCW <= 0.0f)
+        return rgb(0.0f);
+
+    const RisSample& sample = reservoir.sample;
+    V3 evaluated_point = hit.inter_point;
+    V3 shadow_ray_direction = sample.point_on_light_source - evaluated_point;
+    float distance_to_light = length(shadow_ray_direction);
+    V3 shadow_ray_direction_normalized = shadow_ray_direction / distance_to_light;
+
+    bool in_shadow;
+    if (sample.is_bsdf_sample)
+        in_shadow = false;
+    else
+        in_shadow = shadow_ray_occluded(ctx, evaluated_point, shadow_ray_direction_normalized, distance_to_light, hit.primitive_index);
+    return ris_shade_survivor<V>(ctx, payload, hit, view_direction, reservoir, shadow_ray_direction_normalized, in_shadow);
 }
 
 template <class V>
