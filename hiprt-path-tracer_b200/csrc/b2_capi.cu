@@ -445,9 +445,10 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
     return B2PT_ERR_NO_VARIANT;
 }
 
-/* B2PT_MEGAKERNEL selects the form of the MegaKernel (A/B measurements, tests): "phased" (default: persistent warps,
- * bounce cut at its rays, block-pooled traversal), "persistent" (persistent warps, rays traced in place), "tiles" (one
- * thread per pixel). Read at every launch so a test can switch between them. */
+/* Form of the MegaKernel: 2 = "phased" (default: persistent warps, bounce cut at its rays, block-pooled traversal; the
+ * fastest form on B200 for both the L2-resident Cornell box and the 10M-triangle scene, profiles/), 1 = "persistent"
+ * (persistent warps, rays traced in place), 0 = "tiles" (one thread per pixel). B2PT_MEGAKERNEL=phased|persistent|tiles
+ * forces one (A/B measurements, tests); it is read at every launch so a test can switch between them. */
 static int megakernel_form()
 {
     const char* e = std::getenv("B2PT_MEGAKERNEL");

@@ -35,10 +35,10 @@
 #define B2_MAX_DEVICES 64
 /* phased MegaKernel (default): threads per block and resident blocks per SM it is compiled for (register cap 65536 / (T * N)) */
 #ifndef B2_MK_THREADS
-#define B2_MK_THREADS 256
+#define B2_MK_THREADS 512
 #endif
 #ifndef B2_MK_MIN_BLOCKS
-#define B2_MK_MIN_BLOCKS 3
+#define B2_MK_MIN_BLOCKS 1
 #endif
 /* persistent MegaKernel without phases (kept for A/B measurements): 64-thread blocks, 12 resident per SM */
 #define B2_MKP_THREADS 64
@@ -234,54 +234,63 @@ __global__ void __launch_bounds__(B2_MKP_THREADS, B2_MKP_MIN_BLOCKS) megakernel_
 
 /*
  * The MegaKernel in PHASES (default). Same persistent warps, tile fetch and per-warp hit queue as megakernel_persistent
- * above, plus two things its ncu profile asked for (profiles/r01c_ncu_c2_megakernel.md: 6 of 32 lanes active inside the
- * traversal, `no_instruction` = 70 % of all stall samples because every warp of an SM sat in a different corner of a
- * 180 KB kernel while the L1.5 instruction cache holds 32 KB):
- *   1. the bounce is cut at its rays (b2_pathtrace.h: stage A / B / C, b2_nee.h) and the rays of the WHOLE BLOCK are traced
- *      together: every thread drops its ray into a shared-memory pool, then all threads drain the pool in one converged
- *      loop of traversal steps -- a lane whose ray is done takes the next ray from the pool while the other lanes keep
- *      stepping (warp-aggregated atomicAdd on the pool cursor), so the loop runs with full warps until the pool is empty
- *      no matter how many lanes asked for a ray or how long each ray is;
+ * above, plus what its ncu profile asked for (profiles/: 6 of 32 lanes active inside the traversal, `no_instruction` = 70 %
+ * of all stall samples because every warp of an SM sat in a different corner of a 180 KB kernel while the L1.5 instruction
+ * cache holds 32 KB):
+ *   1. the bounce is cut at its rays (b2_pathtrace.h: stage 1 / stage 2, b2_nee.h) and the rays of the WHOLE BLOCK are traced
+ *      together: every thread drops up to three rays (the next main ray and the previous vertex's deferred NEE rays) into a
+ *      shared-memory pool, then all threads drain the pool in one converged loop of traversal steps -- a lane whose ray is
+ *      done takes the next ray from the pool while the other lanes keep stepping (warp-aggregated atomicAdd on the pool
+ *      cursor), so the loop runs with full warps until the pool is empty, however many lanes asked for a ray and however
+ *      long each ray is;
  *   2. block barriers around every trace keep the block's warps in the same stage of the code, so a stage's instructions
  *      are fetched once and reused by all of its warps.
+ * One 512-thread block per SM (128 registers per thread: the path state stays in registers across the stages).
  * A path's arithmetic, RNG draws and results are the same as in the other two forms; tests/ run all three against the same
- * fixtures.
+ * fixtures and against each other (bit-identical frames).
  */
+#define B2_POOL_RAYS 3
 struct B2RayPool
 {
-    float4* ray_a;   /* origin.xyz, t_max                         [threads] */
-    float4* ray_b;   /* direction.xyz, skip_prim | any-hit flag   [threads] */
-    float4* hit_a;   /* t, u, v, prim                             [threads] */
-    float4* hit_b;   /* ng.xyz                                    [threads] */
-    int* list;       /* compacted slots of this phase's rays      [threads] */
+    float4* slot_a;  /* ray: origin.xyz, t_max            -> hit: t, u, v, prim      [B2_POOL_RAYS * threads] */
+    float4* slot_b;  /* ray: direction.xyz, skip | flags  -> hit: ng.xyz             [B2_POOL_RAYS * threads] */
+    int* list;       /* compacted slots of this phase's rays                        [B2_POOL_RAYS * threads] */
     int* count;      /* [2]: rays in the pool, by phase parity */
     int* next;       /* [2]: drain cursor, by phase parity */
 };
 
-/* All threads of the block call this the same number of times. `ray.kind == B2_RAY_NONE`: the thread has no ray this phase
- * but still helps draining. Returns this thread's result (prim = -1 when it had no ray). */
-__device__ __forceinline__ B2Hit b2_trace_pooled(const Ctx& ctx, const B2RayPool& pool, unsigned int& phase, const RayRequest& ray, B2TraversalCounters* counters)
+/* All threads of the block call this the same number of times. rays[k].kind == B2_RAY_NONE: no k-th ray from this thread
+ * (it still helps draining). results[k].prim = -1 for rays that were not asked for. */
+template <int N>
+__device__ __forceinline__ void b2_trace_pooled(const Ctx& ctx, const B2RayPool& pool, unsigned int& phase, const RayRequest (&rays)[N], B2Hit (&results)[N],
+                                                B2TraversalCounters* counters)
 {
+    static_assert(N <= B2_POOL_RAYS, "pool slots per thread");
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lanes_below = (1u << lane) - 1u;
     const int pc = (int)(phase & 1u);
     phase++;
 
-    /* deposit (warp-aggregated slot allocation) */
-    const bool have = ray.kind != B2_RAY_NONE && ctx.bvh.node_count != 0;
+    /* deposit (warp-aggregated slot allocation); skip_prim shares a word with the any-hit flag: prim ids are < 2^30 */
+    bool have[N];
+#pragma unroll
+    for (int k = 0; k < N; k++)
     {
-        const unsigned int havers = __ballot_sync(0xFFFFFFFFu, have);
+        have[k] = rays[k].kind != B2_RAY_NONE && ctx.bvh.node_count != 0;
+        const unsigned int havers = __ballot_sync(0xFFFFFFFFu, have[k]);
+        if (havers == 0u)
+            continue;
         int base = 0;
-        if (lane == 0 && havers != 0u)
+        if (lane == 0)
             base = atomicAdd(&pool.count[pc], __popc(havers));
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (have)
+        if (have[k])
         {
-            pool.list[base + __popc(havers & lanes_below)] = (int)threadIdx.x;
-            pool.ray_a[threadIdx.x] = make_float4(ray.origin.x, ray.origin.y, ray.origin.z, ray.t_max);
-            pool.ray_b[threadIdx.x] = make_float4(ray.direction.x, ray.direction.y, ray.direction.z,
-                                                  __int_as_float(ray.kind == B2_RAY_ANY_HIT ? 1 : 0));
-            pool.hit_b[threadIdx.x] = make_float4(__int_as_float(ray.skip_prim), 0.0f, 0.0f, 0.0f); /* skip_prim travels in hit_b.x until the hit overwrites it */
+            const int slot = k * (int)blockDim.x + (int)threadIdx.x;
+            pool.list[base + __popc(havers & lanes_below)] = slot;
+            pool.slot_a[slot] = make_float4(rays[k].origin.x, rays[k].origin.y, rays[k].origin.z, rays[k].t_max);
+            pool.slot_b[slot] = make_float4(rays[k].direction.x, rays[k].direction.y, rays[k].direction.z,
+                                            __int_as_float((rays[k].skip_prim << 1) | (rays[k].kind == B2_RAY_ANY_HIT ? 1 : 0)));
         }
     }
     if (threadIdx.x == 0)
@@ -314,9 +323,9 @@ __device__ __forceinline__ B2Hit b2_trace_pooled(const Ctx& ctx, const B2RayPool
                 if (i < count)
                 {
                     slot = pool.list[i];
-                    const float4 a = pool.ray_a[slot], b = pool.ray_b[slot];
-                    const int skip_prim = __float_as_int(pool.hit_b[slot].x);
-                    b2_traverse_begin(t, __float_as_int(b.w) != 0, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w, skip_prim, ctx.stack);
+                    const float4 a = pool.slot_a[slot], b = pool.slot_b[slot];
+                    const int packed = __float_as_int(b.w);
+                    b2_traverse_begin(t, (packed & 1) != 0, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), a.w, packed >> 1, ctx.stack);
                     busy = true;
                 }
             }
@@ -332,8 +341,8 @@ __device__ __forceinline__ B2Hit b2_trace_pooled(const Ctx& ctx, const B2RayPool
         {
             if (!b2_traverse_step(t, ctx.bvh, ctx.stack_stride, ctx.faults))
             {
-                pool.hit_a[slot] = make_float4(t.best.t, t.best.u, t.best.v, __int_as_float(t.best.prim));
-                pool.hit_b[slot] = make_float4(t.best.ng.x, t.best.ng.y, t.best.ng.z, 0.0f);
+                pool.slot_a[slot] = make_float4(t.best.t, t.best.u, t.best.v, __int_as_float(t.best.prim));
+                pool.slot_b[slot] = make_float4(t.best.ng.x, t.best.ng.y, t.best.ng.z, 0.0f);
                 if (counters)
                 {
                     counters->rays += 1;
@@ -346,24 +355,27 @@ __device__ __forceinline__ B2Hit b2_trace_pooled(const Ctx& ctx, const B2RayPool
     }
     __syncthreads();
 
-    B2Hit result;
-    result.t = -1.0f;
-    result.u = result.v = 0.0f;
-    result.prim = -1;
-    result.ng = v3(0.0f);
-    if (have)
+#pragma unroll
+    for (int k = 0; k < N; k++)
     {
-        const float4 a = pool.hit_a[threadIdx.x], b = pool.hit_b[threadIdx.x];
-        result.t = a.x;
-        result.u = a.y;
-        result.v = a.z;
-        result.prim = __float_as_int(a.w);
-        result.ng = v3(b.x, b.y, b.z);
+        results[k].t = -1.0f;
+        results[k].u = results[k].v = 0.0f;
+        results[k].prim = -1;
+        results[k].ng = v3(0.0f);
+        if (have[k])
+        {
+            const int own = k * (int)blockDim.x + (int)threadIdx.x;
+            const float4 a = pool.slot_a[own], b = pool.slot_b[own];
+            results[k].t = a.x;
+            results[k].u = a.y;
+            results[k].v = a.z;
+            results[k].prim = __float_as_int(a.w);
+            results[k].ng = v3(b.x, b.y, b.z);
+        }
     }
-    return result;
 }
 
-#define B2_PH_SMEM_BYTES (B2_STACK_ENTRIES * B2_MK_THREADS * 8 + (B2_MK_THREADS / 32) * B2_QUEUE_SLOTS * 4 + B2_MK_THREADS * (4 * 16 + 4) + 16)
+#define B2_PH_SMEM_BYTES (B2_STACK_ENTRIES * B2_MK_THREADS * 8 + (B2_MK_THREADS / 32) * B2_QUEUE_SLOTS * 4 + B2_POOL_RAYS * B2_MK_THREADS * (2 * 16 + 4) + 16)
 
 template <class V>
 __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_phased(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x,
@@ -372,12 +384,10 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
     extern __shared__ __align__(16) unsigned char smem[];
     uint64_t* stacks = reinterpret_cast<uint64_t*>(smem);
     B2RayPool pool;
-    pool.ray_a = reinterpret_cast<float4*>(smem + B2_STACK_ENTRIES * B2_MK_THREADS * 8);
-    pool.ray_b = pool.ray_a + B2_MK_THREADS;
-    pool.hit_a = pool.ray_b + B2_MK_THREADS;
-    pool.hit_b = pool.hit_a + B2_MK_THREADS;
-    pool.list = reinterpret_cast<int*>(pool.hit_b + B2_MK_THREADS);
-    uint32_t* queues = reinterpret_cast<uint32_t*>(pool.list + B2_MK_THREADS);
+    pool.slot_a = reinterpret_cast<float4*>(smem + B2_STACK_ENTRIES * B2_MK_THREADS * 8);
+    pool.slot_b = pool.slot_a + B2_POOL_RAYS * B2_MK_THREADS;
+    pool.list = reinterpret_cast<int*>(pool.slot_b + B2_POOL_RAYS * B2_MK_THREADS);
+    uint32_t* queues = reinterpret_cast<uint32_t*>(pool.list + B2_POOL_RAYS * B2_MK_THREADS);
     pool.count = reinterpret_cast<int*>(queues + (B2_MK_THREADS / 32) * B2_QUEUE_SLOTS);
     pool.next = pool.count + 2;
     if (threadIdx.x < 4)
@@ -397,8 +407,11 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
     const int res_x = rd.render_settings.render_resolution.x, res_y = rd.render_settings.render_resolution.y;
     PathState s;
     BouncePhase<V> ph;
-    RayRequest ray;
-    request_none(ray);
+    ph.reset();
+    RayRequest rays[3]; /* [0] next main ray, [1] deferred X, [2] deferred Y */
+    request_none(rays[0]);
+    request_none(rays[1]);
+    request_none(rays[2]);
     unsigned int phase = 0;
     bool alive = false;
     /* warp-uniform */
@@ -447,7 +460,11 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
             {
                 const uint32_t packed = queue[(q_head + r) % B2_QUEUE_SLOTS];
                 alive = megakernel_begin<V>(ctx, packed & 0xFFFFu, packed >> 16, s);
-                request_none(ray); /* bounce 0 starts from the G-buffer hit */
+                ph.reset();
+                /* bounce 0 starts from the G-buffer hit: no main ray, nothing deferred */
+                request_none(rays[0]);
+                request_none(rays[1]);
+                request_none(rays[2]);
             }
         }
         {
@@ -464,34 +481,56 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
             continue;
         }
 
-        /* main ray -> stage A -> ray #1 -> stage B -> ray #2 -> stage C */
-        if (!alive)
-            request_none(ray);
-        const B2Hit main_hit = b2_trace_pooled(ctx, pool, phase, ray, counters);
-        request_none(ray);
+        /* trace A: main ray + the previous vertex's deferred rays */
+        B2Hit results[3];
+        if (Nee<V>::HAS_DEFERRED_Y)
+            b2_trace_pooled<3>(ctx, pool, phase, rays, results, counters);
+        else
+        {
+            RayRequest two[2] = { rays[0], rays[1] };
+            B2Hit two_results[2];
+            b2_trace_pooled<2>(ctx, pool, phase, two, two_results, counters);
+            results[0] = two_results[0];
+            results[1] = two_results[1];
+            results[2].t = -1.0f;
+            results[2].u = results[2].v = 0.0f;
+            results[2].prim = -1;
+            results[2].ng = v3(0.0f);
+        }
+        request_none(rays[0]);
+        request_none(rays[1]);
+        request_none(rays[2]);
+
+        RayRequest sequential[1];
+        request_none(sequential[0]);
         if (alive)
         {
-            if (!megakernel_stage_a<V>(ctx, s, s.payload.bounce > 0 ? &main_hit : nullptr, ph, ray))
+            if (!megakernel_stage1<V>(ctx, s, ph, s.payload.bounce > 0 ? &results[0] : nullptr, results[1], results[2], sequential[0]))
             {
                 megakernel_end(ctx, s);
                 alive = false;
-                request_none(ray);
+                request_none(sequential[0]);
             }
         }
-        const B2Hit result1 = b2_trace_pooled(ctx, pool, phase, ray, counters);
-        request_none(ray);
-        if (alive)
-            megakernel_stage_b<V>(ctx, s, ph, result1, ray);
-        const B2Hit result2 = b2_trace_pooled(ctx, pool, phase, ray, counters);
-        request_none(ray);
+
+        /* trace B: the sequential ray (RIS: closest hit along BSDF candidate 0) */
+        B2Hit sequential_result[1];
+        sequential_result[0].t = -1.0f;
+        sequential_result[0].u = sequential_result[0].v = 0.0f;
+        sequential_result[0].prim = -1;
+        sequential_result[0].ng = v3(0.0f);
+        if (Nee<V>::HAS_SEQUENTIAL_RAY)
+            b2_trace_pooled<1>(ctx, pool, phase, sequential, sequential_result, counters);
+
         if (alive)
         {
-            if (megakernel_stage_c<V>(ctx, s, ph, result1, result2))
-                request_closest(ray, s.ray_origin, s.ray_direction, s.hit.primitive_index);
-            else
+            if (!megakernel_stage2<V>(ctx, s, ph, sequential_result[0], rays[0], rays[1], rays[2]))
             {
                 megakernel_end(ctx, s);
                 alive = false;
+                request_none(rays[0]);
+                request_none(rays[1]);
+                request_none(rays[2]);
             }
         }
     }

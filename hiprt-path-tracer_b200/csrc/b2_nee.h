@@ -1,21 +1,30 @@
 /*
- * b2_nee.h -- next-event estimation cut at its rays, for the persistent MegaKernel of b2_kernels.cu.
+ * b2_nee.h -- next-event estimation cut at its rays, for the phased MegaKernel of b2_kernels.cu.
  *
  * The reference's NEE strategies trace their rays in the middle of the shading code (sample_one_light_no_MIS /
  * sample_one_light_MIS, /root/reference/src/Device/includes/LightSampling/Lights.h:25-226; sample_lights_RIS,
  * RIS/RIS.h:18-262; evaluate_ReSTIR_DI_reservoir, ReSTIR/DI/FinalShading.h:16-101). Here each strategy is the same
- * arithmetic and the same RNG draws in the same order, split into three parts around its (at most) two rays:
- *     part1 -> ray #1 -> part2 -> ray #2 -> part3
- * so that the kernel can trace the rays of a whole thread block together (one converged traversal loop fed from a
- * shared ray pool) instead of every lane walking the BVH alone inside divergent shading code. The un-split functions
- * (b2_lights.h, b2_ris.h, b2_restir_di_shading.h) stay the reference statement of the math: the host port and the
- * one-thread-per-pixel kernels use them, and tests/ compare both forms against the same golden fixtures.
+ * arithmetic and the same RNG draws in the same order, reorganised around two kinds of rays:
+ *   - a SEQUENTIAL ray: its result decides what the strategy does next (RIS: the closest hit along BSDF candidate 0 is a
+ *     reservoir candidate; which sample survives decides where the shadow ray goes). It is traced between `begin` and
+ *     `finish_sampling`.
+ *   - DEFERRED rays: their results only switch already computed radiance on or off (shadow rays), or are looked up for an
+ *     emission that is then weighted by already computed factors (the BSDF-sample ray of MIS). No RNG draw and no later
+ *     decision of the path depends on them, so they are traced TOGETHER WITH THE NEXT MAIN RAY and `resolve` runs one trace
+ *     later. For that, the BSDF value of a light sample is evaluated before its visibility is known (the reference evaluates
+ *     it only when the sample is visible; bsdf_eval is pure, so the visible case computes the same bits and the occluded case
+ *     is discarded).
+ * The kernel can then trace the rays of a whole thread block together (one converged traversal loop fed from a shared ray
+ * pool of up to three rays per thread) instead of every lane walking the BVH alone inside divergent shading code. The
+ * un-split functions (b2_lights.h, b2_ris.h, b2_restir_di_shading.h) stay the reference statement of the math: the host
+ * port and the other kernel forms use them, and tests/ compare all forms against the same golden fixtures.
  *
- *   strategy            ray #1                                ray #2
- *   ONE_LIGHT           shadow ray to the light sample        -
- *   MIS                 shadow ray to the light sample        closest hit along the BSDF sample
- *   RIS                 closest hit along BSDF candidate 0    shadow ray to the reservoir's survivor
- *   ReSTIR DI, bounce 0 shadow ray to the reservoir's sample  -
+ *   strategy            sequential ray                        deferred X                          deferred Y
+ *   ONE_LIGHT           -                                     shadow ray to the light sample      -
+ *   BSDF                -                                     -                                   closest hit along the BSDF sample
+ *   MIS                 -                                     shadow ray to the light sample      closest hit along the BSDF sample
+ *   RIS                 closest hit along BSDF candidate 0    shadow ray to the survivor          -
+ *   ReSTIR DI, bounce 0 -                                     shadow ray to the reservoir sample  -
  *   (ReSTIR DI at later bounces = its later-bounces strategy, RIS by default)
  * Envmap NEE (b2_envmap.h) and RIS BSDF candidates beyond the first keep tracing in place: rare, not pooled.
  */
@@ -74,34 +83,33 @@ struct Nee
     static constexpr bool HAS_MIS = V::DIRECT == B2_LSS_MIS || (V::DIRECT == B2_LSS_RESTIR_DI && V::LATER == B2_LATER_MIS);
     static constexpr bool HAS_RIS = V::DIRECT == B2_LSS_RIS || (V::DIRECT == B2_LSS_RESTIR_DI && V::LATER == B2_LATER_RIS);
     static constexpr bool HAS_RESTIR = V::DIRECT == B2_LSS_RESTIR_DI;
+    /* compile-time shape of the trace schedule (see the table above) */
+    static constexpr bool HAS_SEQUENTIAL_RAY = HAS_RIS;
+    static constexpr bool HAS_DEFERRED_Y = HAS_MIS || HAS_BSDF;
 
     int strategy;
     bool active;              /* false: sample_emissive_geometry's early-outs (no emissives / white furnace) */
-    /* ONE_LIGHT, MIS */
-    LightSample light_sample;
-    V3 shadow_dir;
-    float distance_to_light;
-    float dot_light_source;
-    bool have_light_ray;
-    Rgb light_radiance;
-    /* BSDF, MIS */
-    Rgb bsdf_color;
+    /* carried from finish_sampling to resolve (one trace later) */
+    bool have_x;              /* deferred X was requested: light_radiance counts only if it came back unoccluded */
+    Rgb light_radiance;       /* radiance of the light-sampled part IF visible */
+    Rgb bsdf_color;           /* BSDF-sampled part (MIS / BSDF): weights of the emission the deferred Y ray finds */
     V3 sampled_direction;
     float bsdf_sample_pdf;
-    /* RIS */
+    /* RIS only, between begin and finish_sampling */
     RisReservoir reservoir;
     int nb_light_candidates, nb_bsdf_candidates;
     bool have_candidate_ray;
-    /* ReSTIR DI final shading */
-    DiReservoir di_reservoir;
 
-    /* ---- part 1: up to ray #1 ------------------------------------------------------------------------------- */
-    B2_HD void part1(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, int x, int y, RayRequest& ray)
+    /* ---- after the main hit: up to the sequential ray ------------------------------------------------------------------ */
+    B2_HD void begin(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, RayRequest& sequential_ray)
     {
         const b2pt_render_data& rd = *ctx.rd;
-        request_none(ray);
+        request_none(sequential_ray);
         strategy = nee_strategy_at<V>(payload.bounce);
         active = true;
+        have_x = false;
+        light_radiance = rgb(0.0f);
+        bsdf_sample_pdf = 0.0f;
         /* sample_emissive_geometry, Lights.h:313-352 */
         if (rd.buffers.emissive_triangles_count == 0 && !(rd.world_settings.ambient_light_type == 2 && V::DIRECT == B2_LSS_RESTIR_DI))
             active = false;
@@ -109,84 +117,30 @@ struct Nee
             active = false;
         if (!active)
             return;
-
-        if (HAS_ONE_LIGHT && strategy == B2_LSS_ONE_LIGHT)
-        {
-            have_light_ray = false;
-            light_radiance = rgb(0.0f);
-            light_sample = sample_one_emissive_triangle<V>(rd, rng);
-            if (light_sample.area_measure_pdf <= 0.0f)
-                return;
-            V3 shadow_ray_direction = light_sample.point_on_light - hit.inter_point;
-            distance_to_light = length(shadow_ray_direction);
-            shadow_dir = shadow_ray_direction / distance_to_light;
-            dot_light_source = cosine_term_at_light_source(light_sample.light_source_normal, -shadow_dir);
-            if (dot_light_source > 0.0f)
-            {
-                have_light_ray = true;
-                request_shadow(ray, hit.inter_point, shadow_dir, distance_to_light, hit.primitive_index);
-            }
-        }
-        else if (HAS_MIS && strategy == B2_LSS_MIS)
-        {
-            have_light_ray = false;
-            light_radiance = rgb(0.0f);
-            light_sample = sample_one_emissive_triangle<V>(rd, rng);
-            if (light_sample.area_measure_pdf > 0.0f)
-            {
-                V3 shadow_ray_direction = light_sample.point_on_light - hit.inter_point;
-                distance_to_light = length(shadow_ray_direction);
-                shadow_dir = shadow_ray_direction / distance_to_light;
-                have_light_ray = true;
-                request_shadow(ray, hit.inter_point, shadow_dir, distance_to_light, hit.primitive_index);
-            }
-        }
-        else if (HAS_BSDF && strategy == B2_LSS_BSDF)
-        {
-            bsdf_part_sample(rd, payload, hit, view_direction, rng, B2_REGULARIZATION_CLASSIC, ray);
-        }
-        else if (HAS_RIS && strategy == B2_LSS_RIS)
-        {
-            ris_part1(ctx, payload, hit, view_direction, rng, ray);
-        }
-        else if (HAS_RESTIR && strategy == B2_LSS_RESTIR_DI)
-        {
-            /* sample_light_ReSTIR_DI + the head of evaluate_ReSTIR_DI_reservoir */
-            int pixel_index = x + y * rd.render_settings.render_resolution.x;
-            void* buffer = rd.render_settings.restir_di_settings.restir_output_reservoirs;
-            di_reservoir = di_load(rd, buffer, pixel_index);
-            if (di_reservoir.sample.is_envmap_sample() && rd.world_settings.ambient_light_type != 2)
-            {
-                di_reservoir.UCW = 0.0f;
-                reinterpret_cast<uint32_t*>(buffer)[DI_PLANE_UCW * di_plane_stride(rd) + pixel_index] = b2_float_as_uint(0.0f);
-            }
-            have_light_ray = false;
-            if (di_reservoir.UCW <= 0.0f)
-                return;
-            shadow_dir = di_light_sample_direction(rd, di_reservoir.sample, hit.inter_point, distance_to_light);
-            if (di_reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED)
-                return;
-            if (rd.render_settings.restir_di_settings.do_final_shading_visibility)
-            {
-                have_light_ray = true;
-                request_shadow(ray, hit.inter_point, shadow_dir, distance_to_light, hit.primitive_index);
-            }
-        }
+        if (HAS_RIS && strategy == B2_LSS_RIS)
+            ris_begin(ctx, payload, hit, view_direction, rng, sequential_ray);
     }
 
-    /* ---- part 2: result of ray #1 -> up to ray #2 -------------------------------------------------------------- */
-    B2_HD void part2(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, const B2Hit& result1, RayRequest& ray)
+    /* ---- result of the sequential ray -> rest of the sampling; ends with the deferred rays -------------------------------------- */
+    B2_HD void finish_sampling(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, int x, int y, const B2Hit& sequential_result,
+                               RayRequest& deferred_x, RayRequest& deferred_y)
     {
         const b2pt_render_data& rd = *ctx.rd;
-        request_none(ray);
+        request_none(deferred_x);
+        request_none(deferred_y);
         if (!active)
             return;
         if (HAS_ONE_LIGHT && strategy == B2_LSS_ONE_LIGHT)
         {
-            if (!have_light_ray)
+            /* sample_one_light_no_MIS, Lights.h:25-87 */
+            LightSample light_sample = sample_one_emissive_triangle<V>(rd, rng);
+            if (light_sample.area_measure_pdf <= 0.0f)
                 return;
-            bool in_shadow = result1.prim >= 0;
-            if (!in_shadow)
+            V3 shadow_ray_direction = light_sample.point_on_light - hit.inter_point;
+            float distance_to_light = length(shadow_ray_direction);
+            V3 shadow_dir = shadow_ray_direction / distance_to_light;
+            float dot_light_source = cosine_term_at_light_source(light_sample.light_source_normal, -shadow_dir);
+            if (dot_light_source > 0.0f)
             {
                 float bsdf_pdf_value;
                 int incident_light_info = light_sample.incident_light_info;
@@ -202,59 +156,92 @@ struct Nee
                         light_radiance = light_sample.emission * cosine_term * color / light_sample_solid_angle_pdf / 1.0f;
                     }
                 }
+                request_visibility(deferred_x, hit, shadow_dir, distance_to_light);
             }
         }
         else if (HAS_MIS && strategy == B2_LSS_MIS)
         {
-            if (have_light_ray)
+            /* sample_one_light_MIS, Lights.h:123-226 */
+            LightSample light_sample = sample_one_emissive_triangle<V>(rd, rng);
+            if (light_sample.area_measure_pdf > 0.0f)
             {
-                bool in_shadow = result1.prim >= 0;
-                if (!in_shadow)
+                V3 shadow_ray_direction = light_sample.point_on_light - hit.inter_point;
+                float distance_to_light = length(shadow_ray_direction);
+                V3 shadow_dir = shadow_ray_direction / distance_to_light;
+                float bsdf_pdf_value;
+                int incident_light_info = B2_LOBE_NO_INFO;
+                BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, shadow_dir, &incident_light_info, &payload.volume_state, false,
+                                             &payload.material, payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
+                Rgb color = bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
+                if (bsdf_pdf_value > 0.0f)
                 {
-                    float bsdf_pdf_value;
-                    int incident_light_info = B2_LOBE_NO_INFO;
-                    BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, shadow_dir, &incident_light_info, &payload.volume_state, false,
-                                                 &payload.material, payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
-                    Rgb color = bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
-                    if (bsdf_pdf_value > 0.0f)
+                    float cos_theta_at_light_source = cosine_term_at_light_source(light_sample.light_source_normal, -shadow_dir);
+                    if (cos_theta_at_light_source > 1.0e-5f)
                     {
-                        float cos_theta_at_light_source = cosine_term_at_light_source(light_sample.light_source_normal, -shadow_dir);
-                        if (cos_theta_at_light_source > 1.0e-5f)
-                        {
-                            float light_sample_solid_angle_pdf = area_to_solid_angle_pdf(light_sample.area_measure_pdf, distance_to_light, cos_theta_at_light_source);
-                            float mis_weight = balance_heuristic(light_sample_solid_angle_pdf, bsdf_pdf_value);
-                            float cosine_term = fabsf(dot(hit.shading_normal, shadow_dir));
-                            light_radiance = color * cosine_term * light_sample.emission * mis_weight / light_sample_solid_angle_pdf / 1.0f;
-                        }
+                        float light_sample_solid_angle_pdf = area_to_solid_angle_pdf(light_sample.area_measure_pdf, distance_to_light, cos_theta_at_light_source);
+                        float mis_weight = balance_heuristic(light_sample_solid_angle_pdf, bsdf_pdf_value);
+                        float cosine_term = fabsf(dot(hit.shading_normal, shadow_dir));
+                        light_radiance = color * cosine_term * light_sample.emission * mis_weight / light_sample_solid_angle_pdf / 1.0f;
                     }
                 }
+                request_visibility(deferred_x, hit, shadow_dir, distance_to_light);
             }
-            bsdf_part_sample(rd, payload, hit, view_direction, rng, B2_REGULARIZATION_MIS, ray);
+            bsdf_part_sample(rd, payload, hit, view_direction, rng, B2_REGULARIZATION_MIS, deferred_y);
+        }
+        else if (HAS_BSDF && strategy == B2_LSS_BSDF)
+        {
+            bsdf_part_sample(rd, payload, hit, view_direction, rng, B2_REGULARIZATION_CLASSIC, deferred_y);
         }
         else if (HAS_RIS && strategy == B2_LSS_RIS)
         {
-            ris_part2(ctx, payload, hit, view_direction, rng, result1, ray);
+            ris_finish(ctx, payload, hit, view_direction, rng, sequential_result, deferred_x);
         }
-        /* BSDF and ReSTIR DI final shading: no second ray */
+        else if (HAS_RESTIR && strategy == B2_LSS_RESTIR_DI)
+        {
+            /* sample_light_ReSTIR_DI + evaluate_ReSTIR_DI_reservoir, FinalShading.h:16-125 */
+            int pixel_index = x + y * rd.render_settings.render_resolution.x;
+            void* buffer = rd.render_settings.restir_di_settings.restir_output_reservoirs;
+            DiReservoir di_reservoir = di_load(rd, buffer, pixel_index);
+            if (di_reservoir.sample.is_envmap_sample() && rd.world_settings.ambient_light_type != 2)
+            {
+                di_reservoir.UCW = 0.0f;
+                reinterpret_cast<uint32_t*>(buffer)[DI_PLANE_UCW * di_plane_stride(rd) + pixel_index] = b2_float_as_uint(0.0f);
+            }
+            if (di_reservoir.UCW <= 0.0f)
+                return;
+            float distance_to_light;
+            V3 shadow_dir = di_light_sample_direction(rd, di_reservoir.sample, hit.inter_point, distance_to_light);
+            light_radiance = restir_di_shade_sample<V>(ctx, payload, hit, view_direction, di_reservoir, shadow_dir, distance_to_light, false);
+            if (!(di_reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED) && rd.render_settings.restir_di_settings.do_final_shading_visibility)
+                request_visibility(deferred_x, hit, shadow_dir, distance_to_light);
+        }
     }
 
-    /* ---- part 3: result of ray #2 (or of ray #1 for the strategies with a single ray) -> radiance ------------------------- */
-    B2_HD Rgb part3(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const B2Hit& result1, const B2Hit& result2)
+    /* ---- one trace later: the strategy's radiance (what sample_one_light_* / sample_lights_RIS / sample_light_ReSTIR_DI return).
+     * `shading_normal` = the vertex's shading normal (the caller still holds the vertex's HitInfo at this point). */
+    B2_HD Rgb resolve(const b2pt_render_data& rd, V3 shading_normal, const B2Hit& result_x, const B2Hit& result_y) const
     {
-        const b2pt_render_data& rd = *ctx.rd;
         if (!active)
             return rgb(0.0f);
-        if (HAS_ONE_LIGHT && strategy == B2_LSS_ONE_LIGHT)
-            return light_radiance;
+        Rgb radiance = rgb(0.0f);
+        bool in_shadow = have_x && result_x.prim >= 0;
+        if (!in_shadow)
+            radiance = light_radiance;
         if (HAS_MIS && strategy == B2_LSS_MIS)
-            return light_radiance + bsdf_part_radiance(rd, hit, result2, true);
+            return radiance + bsdf_part_radiance(rd, shading_normal, result_y, true);
         if (HAS_BSDF && strategy == B2_LSS_BSDF)
-            return bsdf_part_radiance(rd, hit, result1, false);
-        if (HAS_RIS && strategy == B2_LSS_RIS)
-            return ris_part3(ctx, payload, hit, view_direction, result2);
-        if (HAS_RESTIR && strategy == B2_LSS_RESTIR_DI)
-            return restir_part3(ctx, payload, hit, view_direction, result1);
-        return rgb(0.0f);
+            return bsdf_part_radiance(rd, shading_normal, result_y, false);
+        return radiance;
+    }
+
+    /* a shadow ray is only worth tracing when something would be switched off by it */
+    B2_HD void request_visibility(RayRequest& ray, const HitInfo& hit, V3 shadow_dir, float distance_to_light)
+    {
+        /* exactly zero only: a NaN or negative value must still be discarded by an occluded ray, as in the reference */
+        if (light_radiance.r == 0.0f && light_radiance.g == 0.0f && light_radiance.b == 0.0f)
+            return;
+        have_x = true;
+        request_shadow(ray, hit.inter_point, shadow_dir, distance_to_light, hit.primitive_index);
     }
 
     /* ---- BSDF-sample half of sample_one_light_bsdf / sample_one_light_MIS ------------------------------------------------ */
@@ -268,7 +255,7 @@ struct Nee
             request_closest(ray, hit.inter_point, sampled_direction, hit.primitive_index);
     }
 
-    B2_HD Rgb bsdf_part_radiance(const b2pt_render_data& rd, const HitInfo& hit, const B2Hit& result, bool with_mis)
+    B2_HD Rgb bsdf_part_radiance(const b2pt_render_data& rd, V3 shading_normal, const B2Hit& result, bool with_mis) const
     {
         Rgb radiance = rgb(0.0f);
         if (bsdf_sample_pdf > 0.0f)
@@ -281,12 +268,12 @@ struct Nee
                 {
                     float light_pdf_solid_angle = pdf_of_emissive_triangle_hit_solid_angle<V>(rd, light_hit, sampled_direction);
                     float mis_weight = balance_heuristic(bsdf_sample_pdf, light_pdf_solid_angle);
-                    float cosine_term = fabsf(dot(hit.shading_normal, sampled_direction));
+                    float cosine_term = fabsf(dot(shading_normal, sampled_direction));
                     radiance = bsdf_color * cosine_term * light_hit.emission * mis_weight / bsdf_sample_pdf;
                 }
                 else
                 {
-                    float cosine_term = fabsf(dot(hit.shading_normal, sampled_direction));
+                    float cosine_term = fabsf(dot(shading_normal, sampled_direction));
                     radiance = bsdf_color * cosine_term * light_hit.emission / bsdf_sample_pdf;
                 }
             }
@@ -296,7 +283,7 @@ struct Nee
 
     /* ---- RIS (RIS.h:83-262) ------------------------------------------------------------------------------------ */
     /* the light-candidate loop, then the sampling half of BSDF candidate 0 */
-    B2_HD void ris_part1(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, RayRequest& ray)
+    B2_HD void ris_begin(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, RayRequest& ray)
     {
         const b2pt_render_data& rd = *ctx.rd;
         const bool low_res = do_render_low_resolution(rd.render_settings);
@@ -307,7 +294,7 @@ struct Nee
         have_candidate_ray = false;
         reservoir.init();
         /* sample_lights_RIS returns black before anything else when there is no emissive triangle: no candidates at all,
-         * reservoir.end() in part 2 then leaves UCW = 0 and nothing is traced or drawn from the RNG */
+         * reservoir.end() then leaves UCW = 0 and nothing is traced or drawn from the RNG */
         if (rd.buffers.emissive_triangles_count == 0)
         {
             nb_light_candidates = 0;
@@ -333,49 +320,30 @@ struct Nee
         }
     }
 
-    /* the rest of BSDF candidate 0, BSDF candidates 1.. (traced in place), reservoir.end(), head of the survivor's shading */
-    B2_HD void ris_part2(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, const B2Hit& result1, RayRequest& ray)
+    /* the rest of BSDF candidate 0, BSDF candidates 1.. (traced in place), reservoir.end(), the survivor's shading if visible */
+    B2_HD void ris_finish(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, const B2Hit& candidate_result, RayRequest& deferred_x)
     {
         const b2pt_render_data& rd = *ctx.rd;
         if (nb_bsdf_candidates > 0)
         {
             LightRayHit light_hit;
-            bool hit_found = have_candidate_ray && light_ray_hit_from(rd, result1, 1.0e35f, light_hit);
+            bool hit_found = have_candidate_ray && light_ray_hit_from(rd, candidate_result, 1.0e35f, light_hit);
             ris_bsdf_candidate_finish<V>(rd, hit, rng, nb_light_candidates, nb_bsdf_candidates, bsdf_color, sampled_direction, bsdf_sample_pdf, hit_found, light_hit, reservoir);
             for (int i = 1; i < nb_bsdf_candidates; i++)
                 ris_bsdf_candidate<V>(ctx, payload, hit, view_direction, rng, nb_light_candidates, nb_bsdf_candidates, reservoir);
         }
         reservoir.end();
+        bsdf_sample_pdf = 0.0f; /* not a MIS / BSDF strategy: resolve() looks at light_radiance only */
 
-        /* evaluate_ris_reservoir_sample up to its shadow ray */
-        have_light_ray = false;
+        /* evaluate_ris_reservoir_sample (RIS.h:18-81) */
         if (reservoir.UCW <= 0.0f)
             return;
         V3 shadow_ray_direction = reservoir.sample.point_on_light_source - hit.inter_point;
-        distance_to_light = length(shadow_ray_direction);
-        shadow_dir = shadow_ray_direction / distance_to_light;
+        float distance_to_light = length(shadow_ray_direction);
+        V3 shadow_dir = shadow_ray_direction / distance_to_light;
+        light_radiance = ris_shade_survivor<V>(ctx, payload, hit, view_direction, reservoir, shadow_dir, false);
         if (!reservoir.sample.is_bsdf_sample)
-        {
-            have_light_ray = true;
-            request_shadow(ray, hit.inter_point, shadow_dir, distance_to_light, hit.primitive_index);
-        }
-    }
-
-    B2_HD Rgb ris_part3(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const B2Hit& result2)
-    {
-        if (reservoir.UCW <= 0.0f)
-            return rgb(0.0f);
-        bool in_shadow = have_light_ray ? result2.prim >= 0 : false;
-        return ris_shade_survivor<V>(ctx, payload, hit, view_direction, reservoir, shadow_dir, in_shadow);
-    }
-
-    /* ---- ReSTIR DI final shading (FinalShading.h:16-101) after its shadow ray --------------------------------------------- */
-    B2_HD Rgb restir_part3(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, const B2Hit& result1)
-    {
-        if (di_reservoir.UCW <= 0.0f)
-            return rgb(0.0f);
-        bool in_shadow = have_light_ray ? result1.prim >= 0 : false;
-        return restir_di_shade_sample<V>(ctx, payload, hit, view_direction, di_reservoir, shadow_dir, distance_to_light, in_shadow);
+            request_visibility(deferred_x, hit, shadow_dir, distance_to_light);
     }
 };
 

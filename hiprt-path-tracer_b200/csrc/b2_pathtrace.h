@@ -369,29 +369,34 @@ B2_HD Rgb estimate_direct_lighting(const Ctx& ctx, Payload& payload, HitInfo& hi
     return estimate_direct_lighting_from<V>(ctx, payload, hit, view_direction, rng, emissive_contribution);
 }
 
+/* the arithmetic tail of estimate_direct_lighting (Lights.h:398-423), given both contributions and the vertex's state */
+template <class V>
+B2_HD Rgb direct_lighting_combine(const b2pt_render_data& rd, Rgb emissive_contribution, Rgb envmap_contribution, Rgb throughput, int bounce, Rgb material_emission)
+{
+    Rgb total = rgb(0.0f);
+    emissive_contribution = clamp_light_contribution(emissive_contribution, rd.render_settings.direct_contribution_clamp, bounce == 0);
+    envmap_contribution = clamp_light_contribution(envmap_contribution, rd.render_settings.envmap_contribution_clamp, bounce == 0);
+
+    if constexpr (V::DIRECT == B2_LSS_NONE)
+    {
+        Rgb hit_emission = clamp_light_contribution(material_emission, rd.render_settings.indirect_contribution_clamp, bounce > 0);
+        total += hit_emission * throughput;
+    }
+    else
+    {
+        if (bounce == 0)
+            total += material_emission;
+        total += (emissive_contribution + envmap_contribution) * throughput;
+    }
+    return clamp_light_contribution(total, rd.render_settings.indirect_contribution_clamp, bounce > 0);
+}
+
 /* everything of estimate_direct_lighting that follows the emissive-geometry sample */
 template <class V>
 B2_HD Rgb estimate_direct_lighting_from(const Ctx& ctx, Payload& payload, HitInfo& hit, V3 view_direction, Rng& rng, Rgb emissive_contribution)
 {
-    const b2pt_render_data& rd = *ctx.rd;
-    Rgb total = rgb(0.0f);
     Rgb envmap_contribution = sample_environment_map<V>(ctx, payload, hit, view_direction, rng);
-
-    emissive_contribution = clamp_light_contribution(emissive_contribution, rd.render_settings.direct_contribution_clamp, payload.bounce == 0);
-    envmap_contribution = clamp_light_contribution(envmap_contribution, rd.render_settings.envmap_contribution_clamp, payload.bounce == 0);
-
-    if constexpr (V::DIRECT == B2_LSS_NONE)
-    {
-        Rgb hit_emission = clamp_light_contribution(payload.material.emission, rd.render_settings.indirect_contribution_clamp, payload.bounce > 0);
-        total += hit_emission * payload.throughput;
-    }
-    else
-    {
-        if (payload.bounce == 0)
-            total += payload.material.emission;
-        total += (emissive_contribution + envmap_contribution) * payload.throughput;
-    }
-    return clamp_light_contribution(total, rd.render_settings.indirect_contribution_clamp, payload.bounce > 0);
+    return direct_lighting_combine<V>(*ctx.rd, emissive_contribution, envmap_contribution, payload.throughput, payload.bounce, payload.material.emission);
 }
 
 /* PathTracing.h:122-174 (denoiser AOVs are written by store_denoiser_aovs below) */
@@ -621,28 +626,59 @@ B2_HD void megakernel_primary_miss(const Ctx& ctx, uint32_t x, uint32_t y, uint3
     accumulate_color(rd, ray_color, pixel_index);
 }
 
-/* ---- the bounce cut at its rays (b2_nee.h) for the phased persistent kernel ------------------------------------------------
- *   [main ray] stage A [ray #1] stage B [ray #2] stage C [next main ray] ...
- * Same operations and RNG draws as megakernel_bounce, in the same order. */
+/* ---- the bounce cut at its rays (b2_nee.h) for the phased MegaKernel -----------------------------------------------------
+ * One iteration of a path:
+ *     trace A: [main ray, deferred X, deferred Y of the previous vertex]
+ *     stage 1: resolve the previous vertex's NEE; end the path if it has no main ray; take the main hit; NEE begin
+ *     trace B: [sequential ray]                       (only variants with RIS)
+ *     stage 2: rest of the NEE sampling -> deferred X / Y; envmap NEE; next direction -> main ray
+ * Same operations and RNG draws, in the same order, as megakernel_bounce; what moves is WHEN the NEE radiance of a vertex
+ * is added to the pixel (one trace later), which no RNG draw and no decision of the path depends on. */
 template <class V>
 struct BouncePhase
 {
     Nee<V> nee;
     bool nee_on;
+    /* a vertex whose NEE waits for its deferred rays */
+    bool pending;
+    Rgb pending_throughput, pending_envmap, pending_material_emission, pending_self_emission;
+    int pending_bounce;
+    /* the path has no next main ray: it ends as soon as its pending NEE is resolved */
+    bool ending;
+
+    B2_HD void reset()
+    {
+        nee_on = false;
+        pending = false;
+        ending = false;
+    }
 };
 
-/* Consumes the closest hit of the main ray (bounce > 0; `main_hit` may be null = trace here) or the G-buffer hit (bounce 0),
- * then runs NEE up to its first ray. Returns false when the path ended here (escaped: background gathered). */
+/* Returns false when the path ended here. `main_hit`: closest hit of the main ray when bounce > 0 (null = trace here). */
 template <class V>
-B2_HD bool megakernel_stage_a(const Ctx& ctx, PathState& s, const B2Hit* main_hit, BouncePhase<V>& ph, RayRequest& ray1)
+B2_HD bool megakernel_stage1(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, const B2Hit* main_hit, const B2Hit& result_x, const B2Hit& result_y, RayRequest& sequential_ray)
 {
     const b2pt_render_data& rd = *ctx.rd;
     Payload& payload = s.payload;
     HitInfo& hit = s.hit;
-    const int bounce = payload.bounce;
-    request_none(ray1);
-    ph.nee_on = false;
+    request_none(sequential_ray);
 
+    if (ph.pending)
+    {
+        /* sample_emissive_geometry's value for the previous vertex (s.hit still is that vertex), then the tail of
+         * estimate_direct_lighting and the sanity check that follows it in the bounce loop */
+        Rgb emissive_contribution = rgb(0.0f);
+        if (ph.nee.active)
+            emissive_contribution = ph.nee.resolve(rd, hit.shading_normal, result_x, result_y) / 1.0f + ph.pending_self_emission;
+        payload.ray_color += direct_lighting_combine<V>(rd, emissive_contribution, ph.pending_envmap, ph.pending_throughput, ph.pending_bounce, ph.pending_material_emission);
+        sanity_check(rd, payload.ray_color, s.x, s.y);
+        ph.pending = false;
+    }
+    if (ph.ending)
+        return false;
+
+    const int bounce = payload.bounce;
+    ph.nee_on = false;
     if (bounce > 0)
         s.intersection_found = trace_main_path_ray<V>(ctx, s.ray_origin, s.ray_direction, payload, hit, hit.primitive_index, s.rng, main_hit);
 
@@ -658,46 +694,41 @@ B2_HD bool megakernel_stage_a(const Ctx& ctx, PathState& s, const B2Hit* main_hi
     if (bounce > 0 || rd.render_settings.enable_direct)
     {
         ph.nee_on = true;
-        ph.nee.part1(ctx, payload, hit, -s.ray_direction, s.rng, s.x, s.y, ray1);
+        ph.nee.begin(ctx, payload, hit, -s.ray_direction, s.rng, sequential_ray);
     }
     return true;
 }
 
+/* Returns false when the path ended here (no next main ray and nothing pending). */
 template <class V>
-B2_HD void megakernel_stage_b(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, const B2Hit& result1, RayRequest& ray2)
+B2_HD bool megakernel_stage2(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, const B2Hit& sequential_result, RayRequest& main_ray, RayRequest& deferred_x, RayRequest& deferred_y)
 {
-    request_none(ray2);
-    if (ph.nee_on)
-        ph.nee.part2(ctx, s.payload, s.hit, -s.ray_direction, s.rng, result1, ray2);
-}
-
-/* Finishes NEE, samples the next direction. Returns true when the path continues: (s.ray_origin, s.ray_direction) is the next
- * main ray, to be traced as a closest-hit ray that skips s.hit.primitive_index. */
-template <class V>
-B2_HD bool megakernel_stage_c(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, const B2Hit& result1, const B2Hit& result2)
-{
-    const b2pt_render_data& rd = *ctx.rd;
     Payload& payload = s.payload;
     HitInfo& hit = s.hit;
+    request_none(main_ray);
+    request_none(deferred_x);
+    request_none(deferred_y);
     if (ph.nee_on)
     {
-        /* sample_emissive_geometry: strategy result + self-emission of emissive textures (textures are refused at upload) */
-        Rgb emissive_contribution = rgb(0.0f);
-        if (ph.nee.active)
-        {
-            Rgb material_self_textured_emission = rgb(0.0f);
-            if (payload.material.emissive_texture_used)
-                material_self_textured_emission = payload.material.emission;
-            emissive_contribution = ph.nee.part3(ctx, payload, hit, -s.ray_direction, result1, result2) / 1.0f + material_self_textured_emission;
-        }
-        payload.ray_color += estimate_direct_lighting_from<V>(ctx, payload, hit, -s.ray_direction, s.rng, emissive_contribution);
-        sanity_check(rd, payload.ray_color, s.x, s.y);
+        ph.nee.finish_sampling(ctx, payload, hit, -s.ray_direction, s.rng, s.x, s.y, sequential_result, deferred_x, deferred_y);
+        ph.pending_envmap = sample_environment_map<V>(ctx, payload, hit, -s.ray_direction, s.rng);
+        ph.pending_throughput = payload.throughput;
+        ph.pending_bounce = payload.bounce;
+        ph.pending_material_emission = payload.material.emission;
+        ph.pending_self_emission = payload.material.emissive_texture_used ? payload.material.emission : rgb(0.0f);
+        ph.pending = true;
     }
     bool valid_indirect_bounce = compute_next_indirect_bounce<V>(ctx, payload, hit, -s.ray_direction, s.ray_origin, s.ray_direction, s.rng);
-    if (!valid_indirect_bounce)
-        return false;
-    payload.bounce++;
-    return payload.bounce < s.nb_bounces + 1;
+    if (valid_indirect_bounce)
+    {
+        payload.bounce++;
+        valid_indirect_bounce = payload.bounce < s.nb_bounces + 1;
+    }
+    if (valid_indirect_bounce)
+        request_closest(main_ray, s.ray_origin, s.ray_direction, hit.primitive_index);
+    else
+        ph.ending = true;
+    return valid_indirect_bounce || ph.pending;
 }
 
 template <class V>

@@ -120,3 +120,48 @@ def test_traversal_selftest_binary(built):
         pytest.skip("tools/traverse_selftest not built")
     out = subprocess.run([str(exe), str(DATA / "cornell_pbr_16x9.b2scene"), "262144"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "SELFTEST OK" in out.stdout, out.stdout[-2000:]
+
+
+# ---- the three forms of the MegaKernel (B2PT_MEGAKERNEL: phased = default, persistent, tiles) ------------------------------
+@pytest.fixture
+def megakernel_form(monkeypatch):
+    def choose(form):
+        monkeypatch.setenv("B2PT_MEGAKERNEL", form)
+    return choose
+
+
+@pytest.mark.parametrize("form", ["persistent", "tiles"])
+@pytest.mark.parametrize("name", ["c1_128x72", "c2_128x72", "c3_syn_96x54", "c4_synenv_96x54_fused"])
+def test_other_megakernel_forms_match_golden(b2pt, gpu_ctx, megakernel_form, name, form):
+    """The fixtures above run through the default (phased) MegaKernel; the other two forms must meet the same bars."""
+    megakernel_form(form)
+    g, meta = load_golden(name)
+    r = make_renderer(b2pt, gpu_ctx, meta, precise=True)
+    r.render(meta["spp"])
+    fb = r.framebuffer()
+    r.close()
+    rel = rel_error(fb, g["framebuffer"])
+    assert (rel > REL_TOL).mean() <= OUTLIER_FRACTION, f"{(rel > REL_TOL).sum()} of {rel.size} pixels beyond {REL_TOL}"
+
+
+@pytest.mark.parametrize("variant,width,height,spp", [("c2", 1920, 1080, 2), ("c3", 1920, 1080, 1), ("c4", 1280, 720, 3)])
+def test_schedule_independence_at_full_size(b2pt, gpu_ctx, megakernel_form, variant, width, height, spp):
+    """Size-independent property at BASELINE.json's frame size: how paths are scheduled onto threads (one thread per pixel,
+    persistent warps with regeneration, phased with block-pooled rays) must not change a single bit of the frame -- every
+    pixel owns its RNG stream -- and no traversal may trip a guard."""
+    frames = {}
+    for form in ("phased", "persistent", "tiles"):
+        megakernel_form(form)
+        r = b2pt.Renderer(gpu_ctx, width, height, variant, precise=True)
+        r.set_scene_file(DATA / "cornell_pbr_16x9.b2scene")
+        r.set_luts_file(DATA / "brdf_luts.b2luts")
+        r.set(nb_bounces=8)
+        if variant == "c4":
+            r.set(restir_di_do_fused_spatiotemporal=1)
+        r.render(spp)
+        frames[form] = r.framebuffer().copy()
+        r.close()
+    assert gpu_ctx.faults() == dict(traversal_guard_trips=0, boundary_guard_trips=0, stack_overflows=0)
+    assert np.array_equal(frames["phased"].view(np.uint32), frames["tiles"].view(np.uint32))
+    assert np.array_equal(frames["persistent"].view(np.uint32), frames["tiles"].view(np.uint32))
+    assert np.isfinite(frames["phased"]).all() and frames["phased"].mean() > 0
