@@ -376,26 +376,27 @@ def main():
     value = paths_per_step * a.steps / (dev_ms * 1e-3) / 1e6
     e2e_value = paths_per_step * a.steps / (e2e_ms * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (MegaKernel), rank 0, outside the timed region ---------------------------
+    # ---- roofline of the dominant kernel (MegaKernel), outside the timed region. Every rank renders (the ReSTIR DI variants
+    # run collectives inside render()); rank 0 reports. ---------------------------------------------------------------
     roofline = None
     extra = {}
+    r.reset()
+    r.set_host_seed(42)
+    r.set_profile_passes(True)
+    before = r.pass_times()
+    r.render(spp)
+    after = r.pass_times()
+    r.set_profile_passes(False)
+    pass_ms = {k: after[k]["ms"] - before.get(k, dict(ms=0.0))["ms"] for k in after}
+    n_launch = {k: after[k]["launches"] - before.get(k, dict(launches=0))["launches"] for k in after}
+    r.reset()
+    r.set_host_seed(42)
+    r.set_counters(True)
+    ctx.counters_reset()
+    r.render(spp)
+    c = ctx.counters_read()
+    r.set_counters(False)
     if rank == 0:
-        r.reset()
-        r.set_host_seed(42)
-        r.set_profile_passes(True)
-        before = r.pass_times()
-        r.render(spp)
-        after = r.pass_times()
-        r.set_profile_passes(False)
-        pass_ms = {k: after[k]["ms"] - before.get(k, dict(ms=0.0))["ms"] for k in after}
-        n_launch = {k: after[k]["launches"] - before.get(k, dict(launches=0))["launches"] for k in after}
-        r.reset()
-        r.set_host_seed(42)
-        r.set_counters(True)
-        ctx.counters_reset()
-        r.render(spp)
-        c = ctx.counters_read()
-        r.set_counters(False)
         mk_ms = pass_ms.get("MegaKernel", 0.0) / max(1, n_launch.get("MegaKernel", 1))
         own = r.owned_pixels() if world > 1 else W * H
         rays = c["rays"] / spp   # per launch (one launch = one sample of every pixel)

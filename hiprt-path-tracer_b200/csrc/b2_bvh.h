@@ -278,29 +278,29 @@ B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_st
         const float bz = (noz - org.z) * t.idz;
         const float t_far = t.t_far;
 
+        /* near / far planes per axis are picked once per node on the packed words (12 selects) instead of per child (48) */
+        const bool neg_x = dir.x < 0.0f, neg_y = dir.y < 0.0f, neg_z = dir.z < 0.0f;
+        const uint32_t near_x[2] = { neg_x ? qw[6] : qw[0], neg_x ? qw[7] : qw[1] }, far_x[2] = { neg_x ? qw[0] : qw[6], neg_x ? qw[1] : qw[7] };
+        const uint32_t near_y[2] = { neg_y ? qw[8] : qw[2], neg_y ? qw[9] : qw[3] }, far_y[2] = { neg_y ? qw[2] : qw[8], neg_y ? qw[3] : qw[9] };
+        const uint32_t near_z[2] = { neg_z ? qw[10] : qw[4], neg_z ? qw[11] : qw[5] }, far_z[2] = { neg_z ? qw[4] : qw[10], neg_z ? qw[5] : qw[11] };
+
         uint32_t hit_bits = 0;
 #pragma unroll
         for (int c = 0; c < 8; c++)
         {
+            /* branch-free over the 8 slots: an empty slot has meta = 0 and contributes (0 >> 5) << x = no bit */
             const uint32_t meta = ((c < 4 ? meta_lo : meta_hi) >> ((c & 3) * 8)) & 0xFFu;
-            if (meta == 0)
-                continue;
             const int w = c >> 2, sh = (c & 3) * 8;
-            const float lox = (float)((qw[0 + w] >> sh) & 0xFFu), loy = (float)((qw[2 + w] >> sh) & 0xFFu), loz = (float)((qw[4 + w] >> sh) & 0xFFu);
-            const float hix = (float)((qw[6 + w] >> sh) & 0xFFu), hiy = (float)((qw[8 + w] >> sh) & 0xFFu), hiz = (float)((qw[10 + w] >> sh) & 0xFFu);
-            const float tx0 = (dir.x < 0.0f ? hix : lox) * sx + bx, tx1 = (dir.x < 0.0f ? lox : hix) * sx + bx;
-            const float ty0 = (dir.y < 0.0f ? hiy : loy) * sy + by, ty1 = (dir.y < 0.0f ? loy : hiy) * sy + by;
-            const float tz0 = (dir.z < 0.0f ? hiz : loz) * sz + bz, tz1 = (dir.z < 0.0f ? loz : hiz) * sz + bz;
+            const float tx0 = (float)((near_x[w] >> sh) & 0xFFu) * sx + bx, tx1 = (float)((far_x[w] >> sh) & 0xFFu) * sx + bx;
+            const float ty0 = (float)((near_y[w] >> sh) & 0xFFu) * sy + by, ty1 = (float)((far_y[w] >> sh) & 0xFFu) * sy + by;
+            const float tz0 = (float)((near_z[w] >> sh) & 0xFFu) * sz + bz, tz1 = (float)((far_z[w] >> sh) & 0xFFu) * sz + bz;
             /* widened by a few ulps so fp32 rounding in the slab arithmetic can never cull a box the exact
              * triangle test would hit */
             const float t_enter = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f)) * 0.9999995f;
             const float t_exit = fminf(fminf(tx1, ty1), fminf(tz1, t_far)) * 1.0000005f;
-            if (t_enter <= t_exit)
-            {
-                const bool inner = (meta & 0x18u) == 0x18u && (meta >> 5) == 1u;
-                const uint32_t bit_index = inner ? (24u + ((meta & 7u) ^ oct_inv)) : (meta & 0x1Fu);
-                hit_bits |= (meta >> 5) << bit_index;
-            }
+            const bool inner = (meta & 0x18u) == 0x18u && (meta >> 5) == 1u;
+            const uint32_t bit_index = inner ? (24u + ((meta & 7u) ^ oct_inv)) : (meta & 0x1Fu);
+            hit_bits |= (t_enter <= t_exit) ? ((meta >> 5) << bit_index) : 0u;
         }
         t.group_base = n_child_base;
         t.group_bits = (hit_bits & 0xFF000000u) | (exyz >> 24);

@@ -262,8 +262,8 @@ struct B2RayPool
 /* All threads of the block call this the same number of times. rays[k].kind == B2_RAY_NONE: no k-th ray from this thread
  * (it still helps draining). results[k].prim = -1 for rays that were not asked for. */
 template <int N>
-__device__ __forceinline__ void b2_trace_pooled(const Ctx& ctx, const B2RayPool& pool, unsigned int& phase, const RayRequest (&rays)[N], B2Hit (&results)[N],
-                                                B2TraversalCounters* counters)
+__device__ __forceinline__ int b2_trace_pooled(const Ctx& ctx, const B2RayPool& pool, unsigned int& phase, const RayRequest (&rays)[N], B2Hit (&results)[N],
+                                               B2TraversalCounters* counters, int vote = 0)
 {
     static_assert(N <= B2_POOL_RAYS, "pool slots per thread");
     const unsigned int lane = threadIdx.x & 31u;
@@ -299,7 +299,8 @@ __device__ __forceinline__ void b2_trace_pooled(const Ctx& ctx, const B2RayPool&
         pool.count[pc ^ 1] = 0;
         pool.next[pc ^ 1] = 0;
     }
-    __syncthreads();
+    /* the barrier between deposit and drain also carries the caller's block-wide vote (returned) */
+    const int block_vote = __syncthreads_or(vote);
 
     /* drain: one converged loop of traversal steps over all rays of the block */
     const int count = pool.count[pc];
@@ -373,6 +374,7 @@ __device__ __forceinline__ void b2_trace_pooled(const Ctx& ctx, const B2RayPool&
             results[k].ng = v3(b.x, b.y, b.z);
         }
     }
+    return block_vote;
 }
 
 #define B2_PH_SMEM_BYTES (B2_STACK_ENTRIES * B2_MK_THREADS * 8 + (B2_MK_THREADS / 32) * B2_QUEUE_SLOTS * 4 + B2_POOL_RAYS * B2_MK_THREADS * (2 * 16 + 4) + 16)
@@ -473,29 +475,30 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
             q_count -= taken;
         }
         __syncwarp();
-        if (!__syncthreads_or(alive ? 1 : 0))
-        {
-            /* no live path in the whole block: every warp ran out of work, or the fetched tiles held no hit pixel */
-            if (__syncthreads_and((exhausted && q_count == 0) ? 1 : 0))
-                break;
-            continue;
-        }
 
-        /* trace A: main ray + the previous vertex's deferred rays */
+        /* trace A: main ray + the previous vertex's deferred rays; its first barrier also votes "any live path in the block?" */
         B2Hit results[3];
+        int any_alive;
         if (Nee<V>::HAS_DEFERRED_Y)
-            b2_trace_pooled<3>(ctx, pool, phase, rays, results, counters);
+            any_alive = b2_trace_pooled<3>(ctx, pool, phase, rays, results, counters, alive ? 1 : 0);
         else
         {
             RayRequest two[2] = { rays[0], rays[1] };
             B2Hit two_results[2];
-            b2_trace_pooled<2>(ctx, pool, phase, two, two_results, counters);
+            any_alive = b2_trace_pooled<2>(ctx, pool, phase, two, two_results, counters, alive ? 1 : 0);
             results[0] = two_results[0];
             results[1] = two_results[1];
             results[2].t = -1.0f;
             results[2].u = results[2].v = 0.0f;
             results[2].prim = -1;
             results[2].ng = v3(0.0f);
+        }
+        if (!any_alive)
+        {
+            /* no live path in the whole block: every warp ran out of work, or the fetched tiles held no hit pixel */
+            if (__syncthreads_and((exhausted && q_count == 0) ? 1 : 0))
+                break;
+            continue;
         }
         request_none(rays[0]);
         request_none(rays[1]);

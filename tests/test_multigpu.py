@@ -27,7 +27,7 @@ def test_partitioned_render_is_bit_identical(built, variant, extra):
         pytest.skip("needs at least 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", "29517",
            str(ROOT / "tools" / "multigpu_check.py"), "--variant", variant, *extra]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert out.returncode == 0 and lines, out.stdout[-2000:] + out.stderr[-2000:]
     report = json.loads(lines[-1])
