@@ -250,6 +250,9 @@ __global__ void __launch_bounds__(B2_MKP_THREADS, B2_MKP_MIN_BLOCKS) megakernel_
  * fixtures and against each other (bit-identical frames).
  */
 #define B2_POOL_RAYS 3
+#ifndef B2_POOL_REFILL_MIN
+#define B2_POOL_REFILL_MIN 1
+#endif
 struct B2RayPool
 {
     float4* slot_a;  /* ray: origin.xyz, t_max            -> hit: t, u, v, prim      [B2_POOL_RAYS * threads] */
@@ -311,7 +314,9 @@ __device__ __forceinline__ int b2_trace_pooled(const Ctx& ctx, const B2RayPool& 
     while (true)
     {
         const unsigned int idle = __ballot_sync(0xFFFFFFFFu, !busy);
-        if (idle != 0u && !drained)
+        /* fetch when at least B2_POOL_REFILL_MIN lanes are idle (or none is busy): every fetch costs the whole warp a
+         * ballot, an atomic and a ray setup, so single stragglers wait for company */
+        if (idle != 0u && !drained && ((int)__popc(idle) >= B2_POOL_REFILL_MIN || idle == 0xFFFFFFFFu))
         {
             const int wanted = __popc(idle);
             int base = 0;
