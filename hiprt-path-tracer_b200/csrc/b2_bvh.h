@@ -393,7 +393,7 @@ B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int
 /* ONE out-of-line copy of the traversal per kernel (closest-hit and any-hit share it through a run-time flag): the
  * per-pixel code calls the traversal from 5-7 places (main path, shadow rays of every NEE strategy, BSDF-sample rays)
  * and inlining every one of them made the C2 MegaKernel 13.7k SASS instructions = 220 KB, far beyond the 32 KB L1.5
- * instruction cache (ncu: `no_instruction` was the dominant stall, profiles/r01_ncu_c2_megakernel.md).
+ * instruction cache (ncu: `no_instruction` was the dominant stall, profiles/r01_ncu_c2_megakernel_first.md).
  * Members are passed by value so the caller's context stays in registers. */
 static __device__ __noinline__ B2Hit b2_traverse_shared(bool any_hit, const B2Node* nodes, const B2Tri* tris, uint32_t node_count, float ox, float oy, float oz, float dx,
                                                         float dy, float dz, float t_max, int skip_prim, uint64_t* stack, int stack_stride,

@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) pass_kernel(const __grid_con
  * -- takes the next queued pixel at the top of the loop while the other lanes carry on with their bounce, so
  * `megakernel_bounce` runs with (nearly) all 32 lanes holding a live surface hit until the work runs out. In the
  * one-thread-per-pixel form the warp idled lanes until its longest path ended (6.2 of 32 lanes active on the C2
- * Cornell frame, profiles/r01_ncu_c2_megakernel.md); handing out single pixels instead of tiles still spent a third of
- * the bounce loop's lanes on primary misses (profiles/r01b_ncu_c2_megakernel.md).
+ * Cornell frame, profiles/r01_ncu_c2_megakernel_first.md); handing out single pixels instead of tiles still spent a third of
+ * the bounce loop's lanes on primary misses (profiles/r01_ncu_megakernel_history.md).
  * Per-pixel results do not depend on the schedule: every pixel owns its RNG stream and its framebuffer word.
  */
 #define B2_QUEUE_SLOTS 64

@@ -614,7 +614,7 @@ B2_HD_NOINLINE float glass_energy_compensation_correction_exponent(float roughne
 
     /* namespace-scope tables (global memory on the device, .rodata on the host): a function-local const array is
      * re-materialised on the thread's local-memory stack at every call (3.4 KB of stores per call, measured as
-     * 1.4 GB of DRAM writes per C2 sample in profiles/r01_ncu_c2_megakernel.md) */
+     * 1.4 GB of DRAM writes per C2 sample in profiles/r01_ncu_c2_megakernel_first.md) */
 #if defined(__CUDA_ARCH__)
     const B2ExponentCurve* lower_curves = b2_glass_exponent_lower_device;
     const B2ExponentCurve* higher_curves = b2_glass_exponent_higher_device;
