@@ -494,12 +494,24 @@ int b2pt_renderer_set_profile_passes(b2pt_renderer* r, int enabled)
     return B2PT_OK;
 }
 
-/* GPURenderer::reset (sample_number = 0, need_to_reset = true) */
+/* GPURenderer::reset (sample_number = 0, need_to_reset = true) + every render pass's reset(): ReSTIRDIRenderPass::reset
+ * empties the three reservoir buffers and restarts the ping-pong (src/Renderer/RenderPasses/ReSTIRDIRenderPass.cpp:319-341),
+ * so the first frame after a reset has no temporal / spatial history, exactly like the first frame ever. */
 int b2pt_renderer_reset(b2pt_renderer* r)
 {
     if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
     r->loop.rd.render_settings.need_to_reset = 1;
     r->loop.rd.render_settings.sample_number = 0;
+    if (r->loop.restir_di)
+    {
+        B2_TRY(b2pt_ctx_make_current(r->ctx));
+        for (int i = 0; i < 3; i++)
+            if (r->d_reservoirs[i])
+                B2_TRY(b2pt_memset(r->ctx, r->d_reservoirs[i], 0, r->pixels() * 36, r->stream));
+        r->loop.odd_frame = false;
+        r->loop.rd.render_settings.restir_di_settings.initial_candidates.output_reservoirs = r->d_reservoirs[0];
+        r->loop.rd.render_settings.restir_di_settings.restir_output_reservoirs = r->d_reservoirs[1];
+    }
     return B2PT_OK;
 }
 

@@ -80,11 +80,16 @@ def test_c1_512_against_reference_oracle_on_host(b2pt, gpu_ctx, tmp_path):
     assert (rel > REL_TOL).mean() <= OUTLIER_FRACTION
 
 
-def test_determinism_and_reset(b2pt, gpu_ctx):
-    """Same host seed => identical bytes; reset() restarts accumulation (idempotence property, any size)."""
-    r = b2pt.Renderer(gpu_ctx, 320, 200, "c1", precise=True)
+@pytest.mark.parametrize("variant", ["c1", "c4"])
+def test_determinism_and_reset(b2pt, gpu_ctx, variant):
+    """Same host seed => identical bytes; reset() restarts accumulation AND the ReSTIR DI history (reservoir buffers emptied,
+    ping-pong restarted: ReSTIRDIRenderPass::reset) -- idempotence property, any size."""
+    r = b2pt.Renderer(gpu_ctx, 320, 200, variant, precise=True)
     r.set_scene_file(DATA / "cornell_pbr_16x9.b2scene")
+    r.set_luts_file(DATA / "brdf_luts.b2luts")
     r.set(nb_bounces=3)
+    if variant == "c4":
+        r.set(restir_di_do_fused_spatiotemporal=1)
     r.render(2)
     a = r.framebuffer().copy()
     r.reset()

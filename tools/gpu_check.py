@@ -51,6 +51,8 @@ def main():
     ap.add_argument("--tag", default="")
     ap.add_argument("--window", type=int, nargs=4, default=None, help="x0 y0 x1 y1: the oracles render (and parity is checked on) this crop only")
     ap.add_argument("--envmap", default=None, help="B2ENVMP1 blob")
+    ap.add_argument("--margin", type=int, default=0, help="compare only the window shrunk by this many pixels: ReSTIR reuse reads neighbours (radius 16 per frame) "
+                    "that a windowed oracle run does not have outside its window")
     ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
 
@@ -104,16 +106,19 @@ def main():
         fb.tofile(prefix + "framebuffer.bin")
         r.close()
 
+    cmp_window = a.window
+    if a.window and a.margin:
+        cmp_window = [a.window[0] + a.margin, a.window[1] + a.margin, a.window[2] - a.margin, a.window[3] - a.margin]
     if not a.no_oracle:
         extra = [] if a.fused else ["--no-fused"]
         ref_meta, _ = run_oracle(ROOT / "oracle" / "_ref" / f"ref_render_{a.variant}", a, str(tmp / "ref_"), extra)
         port_meta, _ = run_oracle(ROOT / "oracle" / "_port" / "port_render", a, str(tmp / "port_"), ["--variant", a.variant, *extra])
         report["ref_oracle"] = ref_meta
         report["port_oracle"] = port_meta
-        report["cuda_precise_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "cuda_precise_"), a.width, a.height, verbose=False, window=a.window)
-        report["cuda_fast_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "cuda_fast_"), a.width, a.height, verbose=False, window=a.window)
-        report["cuda_precise_vs_port"] = compare(str(tmp / "port_"), str(tmp / "cuda_precise_"), a.width, a.height, verbose=False, window=a.window)
-        report["port_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "port_"), a.width, a.height, verbose=False, window=a.window)
+        report["cuda_precise_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "cuda_precise_"), a.width, a.height, verbose=False, window=cmp_window)
+        report["cuda_fast_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "cuda_fast_"), a.width, a.height, verbose=False, window=cmp_window)
+        report["cuda_precise_vs_port"] = compare(str(tmp / "port_"), str(tmp / "cuda_precise_"), a.width, a.height, verbose=False, window=cmp_window)
+        report["port_vs_ref"] = compare(str(tmp / "ref_"), str(tmp / "port_"), a.width, a.height, verbose=False, window=cmp_window)
 
     out_dir = ROOT / "gpurun_out"
     out_dir.mkdir(exist_ok=True)
