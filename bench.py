@@ -16,7 +16,7 @@ principled BSDF, 16 spp, NEE + BSDF MIS with power-proportional light sampling (
  cpu_baseline: the reference's own CPU path (oracle/_ref, compiled from /root/reference) on this box's host cores, on
               a bounded pixel window of the same workload
 
-Multi-GPU (N > 1): the frame is partitioned into interleaved 64-row pixel bands (rank = band % N), scene replicated,
+Multi-GPU (N > 1): the frame is partitioned into interleaved 16-row pixel bands (rank = band % N), scene replicated,
 no data-path collective inside a sample (ReSTIR DI variants all-gather the reservoir planes a reuse pass reads, once
 per frame); the framebuffer bands are all-gathered with NCCL at the end of every step (inside the timed region: the
 step's device time = the renderer's CUDA events + the all-gather's). Total work is fixed => "scaling": "strong".
@@ -427,7 +427,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit="Mpaths/s", n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=dev_ms / a.steps,
                     higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=w["desc"], variant=w["variant"], width=W, height=H, spp=spp, bounces=w["bounces"],
-                                flavour="precise" if a.precise else "fast", partition="interleaved 64-row bands, scene replicated" if world > 1 else "single GPU",
+                                flavour="precise" if a.precise else "fast", partition="interleaved 16-row bands, scene replicated" if world > 1 else "single GPU",
                                 l2_policy="every step re-renders from reset: G-buffer + framebuffer + aux (> 126 MB at 1080p) are rewritten between timed iterations"),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit="Mpaths/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / a.steps),

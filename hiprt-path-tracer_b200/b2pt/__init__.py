@@ -237,9 +237,13 @@ class Renderer:
             if torch is None or dist is None:
                 raise B2ptError("ReSTIR DI on several GPUs needs torch + torch.distributed for the reservoir exchange")
 
+            gatherers = {}  # one per reservoir buffer (the render loop ping-pongs between three)
+
             def exchange(user, ptr, nbytes):
-                planes = partition.device_tensor(torch, ptr, (9, self.height, self.width), "<i4")
-                partition.allgather_rows(planes, 1, rank, world, dist, torch)
+                if ptr not in gatherers:
+                    planes = partition.device_tensor(torch, ptr, (9, self.height, self.width), "<i4")
+                    gatherers[ptr] = partition.RowGatherer(planes, 1, rank, world, dist, torch)
+                gatherers[ptr]()
                 torch.cuda.current_stream().synchronize()
                 self.exchange_count += 1
 
@@ -261,10 +265,12 @@ class Renderer:
         rank, world = self.rank, self.world
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+        gatherer = partition.RowGatherer(fb, 0, rank, world, dist, torch)
+
         def gather():
             self.synchronize()
             start.record()
-            partition.allgather_rows(fb, 0, rank, world, dist, torch)
+            gatherer()
             stop.record()
             stop.synchronize()
             return start.elapsed_time(stop)

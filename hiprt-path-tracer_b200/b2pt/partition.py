@@ -7,7 +7,7 @@ Megakernel.h:35) and only the ReSTIR reuse passes read neighbouring pixels' rese
 """
 import numpy as np
 
-BAND_ROWS = 64  # == B2PT_BAND_ROWS in include/b2pt.h
+BAND_ROWS = 16  # == B2PT_BAND_ROWS in include/b2pt.h (fine bands: 1080 rows / 16 = 67.5 bands keep 8 ranks within 7 % of each other)
 
 
 def owned_rows(height, rank, world):
@@ -42,6 +42,39 @@ def allgather_rows(t, row_dim, rank, world, dist, torch, group=None):
         if k != rank and len(rows[k]):
             t.index_copy_(row_dim, rows[k], recv[k].narrow(row_dim, 0, len(rows[k])))
     return t
+
+
+class RowGatherer:
+    """allgather_rows with everything that does not change between calls prepared once: row index tensors, the padded
+    send buffer and the receive buffer. One gather = index_select into the send buffer, ONE all-gather, world-1 index_copy_."""
+
+    def __init__(self, t, row_dim, rank, world, dist, torch, group=None):
+        self.t, self.row_dim, self.rank, self.world, self.dist, self.torch, self.group = t, row_dim, rank, world, dist, torch, group
+        height = t.shape[row_dim]
+        self.rows = [torch.as_tensor(owned_rows(height, k, world), device=t.device, dtype=torch.long) for k in range(world)]
+        self.max_rows = max(len(r) for r in self.rows) if world > 1 else 0
+        if world > 1 and self.max_rows:
+            pad_shape = list(t.shape)
+            pad_shape[row_dim] = self.max_rows
+            self.send = torch.zeros(pad_shape, dtype=t.dtype, device=t.device)
+            self.recv = torch.empty([world] + pad_shape, dtype=t.dtype, device=t.device)
+            self.nccl = dist.get_backend(group) == "nccl"
+
+    def __call__(self):
+        if self.world == 1 or not self.max_rows:
+            return self.t
+        torch, rd = self.torch, self.row_dim
+        mine = self.rows[self.rank]
+        if len(mine):
+            torch.index_select(self.t, rd, mine, out=self.send.narrow(rd, 0, len(mine)))
+        if self.nccl:
+            self.dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        else:
+            self.dist.all_gather([self.recv[k] for k in range(self.world)], self.send, group=self.group)
+        for k in range(self.world):
+            if k != self.rank and len(self.rows[k]):
+                self.t.index_copy_(rd, self.rows[k], self.recv[k].narrow(rd, 0, len(self.rows[k])))
+        return self.t
 
 
 class _DevicePointer:

@@ -145,7 +145,7 @@ int b2pt_kernel_launch(b2pt_kernel* kernel, int block_x, int block_y, int width,
 /* Multi-GPU form: launches the kernel over the pixel rows of `rank`'s bands only. The frame is partitioned into
  * interleaved bands of B2PT_BAND_ROWS rows; band b belongs to rank b % world (scene replicated on every GPU). The
  * reference has no multi-GPU path; this is the one addition to its launch surface (BASELINE.json north_star). */
-#define B2PT_BAND_ROWS 64
+#define B2PT_BAND_ROWS 16
 int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank, int world, void** args, b2pt_stream stream);
 int b2pt_kernel_last_ms(b2pt_kernel* kernel, float* out_ms);
 int b2pt_kernel_launch_count(b2pt_kernel* kernel, uint64_t* out_count);

@@ -33,9 +33,9 @@ def test_band_ownership_covers_every_row_once():
             assert np.array_equal(allrows, np.arange(height))
             for r in range(world):
                 assert np.all((rows[r] // p.BAND_ROWS) % world == r)
-    # 1080p on 8 GPUs: 17 bands -> rank 0 owns 3 bands (one of them the 56-row tail band? no: band 16 -> rank 0)
-    assert len(p.owned_rows(1080, 0, 8)) == 64 + 64 + 56
-    assert len(p.owned_rows(1080, 1, 8)) == 128
+    # 1080p on 8 GPUs: 67 full bands + an 8-row tail band -> ranks own 8 or 9 bands, within 7 % of each other
+    counts = [len(p.owned_rows(1080, r, 8)) for r in range(8)]
+    assert sum(counts) == 1080 and max(counts) <= 144 and min(counts) >= 128
 
 
 def _worker(rank, world, port, height, width, out_dir):
@@ -54,12 +54,19 @@ def _worker(rank, world, port, height, width, out_dir):
     p.allgather_rows(fb, 0, rank, world, dist, torch)
     p.allgather_rows(planes, 1, rank, world, dist, torch)
     ok = torch.equal(fb, full_fb) and torch.equal(planes, full_planes)
+    # the prepared form used by bench.py / the reservoir exchange: same result, and reusable (second call = no-op change)
+    fb2 = torch.full_like(full_fb, float("nan"))
+    fb2[rows] = full_fb[rows]
+    gatherer = p.RowGatherer(fb2, 0, rank, world, dist, torch)
+    gatherer()
+    gatherer()
+    ok = ok and torch.equal(fb2, full_fb)
     with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
         f.write("ok" if ok else "mismatch")
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,height", [(2, 200), (3, 130), (2, 40)])
+@pytest.mark.parametrize("world,height", [(2, 200), (3, 130), (2, 40), (3, 20)])
 def test_allgather_rows_gloo(world, height, tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

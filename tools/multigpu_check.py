@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Run under torchrun with N ranks (one per GPU): renders a frame partitioned across the ranks (interleaved 64-row bands,
+"""Run under torchrun with N ranks (one per GPU): renders a frame partitioned across the ranks (interleaved 16-row bands,
 ReSTIR DI reservoir exchange, framebuffer all-gather) and checks on every rank that the gathered frame is BIT-IDENTICAL to
 the same frame rendered by that rank alone -- results must not depend on the number of GPUs.
 
