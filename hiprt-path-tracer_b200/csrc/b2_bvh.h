@@ -91,7 +91,9 @@ B2_HD void b2_report_fault(unsigned int* faults, int which)
 #endif
 }
 
+#ifndef B2_STACK_ENTRIES
 #define B2_STACK_ENTRIES 24
+#endif
 
 /* Exact restatement of Triangle::intersect (Triangle.h:20-63) on precomputed edges: edge1 = B-A and edge2 = C-A are
  * the same fp32 subtractions the reference performs per test, done once at build time. */
