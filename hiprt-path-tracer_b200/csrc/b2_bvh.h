@@ -216,7 +216,7 @@ B2_HD void b2_traverse_begin(B2Traversal& t, bool any_hit, V3 org, V3 dir, float
 
 /* One step: at most one node (its 8 quantised child boxes) and the triangles of its hit leaf slots, then a pop if the
  * current group is exhausted. Returns false when the traversal is over (t.best holds the result). */
-B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_stride, unsigned int* faults)
+B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_stride, unsigned int* faults, int stack_entries = B2_STACK_ENTRIES)
 {
     const V3 org = t.org, dir = t.dir;
     const uint32_t oct_inv = t.oct_inv;
@@ -236,7 +236,7 @@ B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_st
         t.group_bits &= ~(1u << child_bit);
         if (t.group_bits > 0x00FFFFFFu)
         {
-            if (t.sp < B2_STACK_ENTRIES)
+            if (t.sp < stack_entries)
             {
                 *t.top = ((uint64_t)t.group_base << 32) | t.group_bits;
                 t.top += stack_stride;
@@ -356,7 +356,7 @@ B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_st
         if (t.sp == 0)
             return false;
         t.sp--;
-        if (t.sp < B2_STACK_ENTRIES)
+        if (t.sp < stack_entries)
         {
             t.top -= stack_stride;
             const uint64_t e = *t.top;

@@ -8,6 +8,7 @@
 #include "b2_bvh_build.h"
 #include "b2_kernel_table.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -15,6 +16,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 static thread_local std::string g_last_error;
@@ -54,6 +56,10 @@ struct b2pt_bvh
     b2pt_bvh_stats_t stats;
     B2BvhHost host; /* kept for b2pt_bvh_reupload */
 };
+
+/* device descriptor -> depth of the tree, so a launch can size the traversal stack (b2pt_kernel_launch only sees the render data) */
+static std::mutex g_bvh_depth_mutex;
+static std::unordered_map<const void*, int> g_bvh_depth;
 
 struct b2pt_kernel
 {
@@ -308,6 +314,10 @@ int b2pt_bvh_build(b2pt_ctx* ctx, const int* triangle_indices, int triangle_coun
     bvh->stats.max_depth = host.stats.max_depth;
     bvh->stats.sah_cost = host.stats.sah_cost;
     bvh->stats.build_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    {
+        std::lock_guard<std::mutex> lock(g_bvh_depth_mutex);
+        g_bvh_depth[bvh->descriptor] = bvh->stats.max_depth;
+    }
     *out_bvh = bvh;
     return B2PT_OK;
 }
@@ -336,6 +346,10 @@ int b2pt_bvh_stats(b2pt_bvh* bvh, b2pt_bvh_stats_t* out)
 int b2pt_bvh_destroy(b2pt_ctx*, b2pt_bvh* bvh)
 {
     if (!bvh) return B2PT_OK;
+    {
+        std::lock_guard<std::mutex> lock(g_bvh_depth_mutex);
+        g_bvh_depth.erase(bvh->descriptor);
+    }
     cudaFree(bvh->nodes);
     cudaFree(bvh->tris);
     cudaFree(bvh->descriptor);
@@ -474,6 +488,14 @@ int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank
     geom.rank = rank;
     geom.world = world;
     geom.persistent = megakernel_form();
+    geom.stack_entries = B2_STACK_ENTRIES;
+    {
+        /* a traversal pushes at most one entry per level: depth + 1 entries are enough for this tree */
+        std::lock_guard<std::mutex> lock(g_bvh_depth_mutex);
+        auto it = g_bvh_depth.find(rd->GPU_BVH);
+        if (it != g_bvh_depth.end())
+            geom.stack_entries = std::max(4, std::min(B2_STACK_ENTRIES, it->second + 1));
+    }
     B2_CUDA(cudaEventRecord(kernel->start, s));
     B2_CUDA(kernel->entry->launch(rd, &geom, s));
     B2_CUDA(cudaEventRecord(kernel->stop, s));

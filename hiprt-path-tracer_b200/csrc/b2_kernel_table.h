@@ -13,6 +13,7 @@ struct B2LaunchGeom
 {
     int width, height;
     int rank, world;
+    int stack_entries; /* phased MegaKernel: traversal-stack entries per thread (BVH depth + 1 when known, else B2_STACK_ENTRIES) */
     int persistent; /* MegaKernel only: 0 = one thread per pixel, 1 = persistent warps, 2 = persistent + phased (pooled rays) */
 };
 

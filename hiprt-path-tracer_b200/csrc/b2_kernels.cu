@@ -266,7 +266,7 @@ struct B2RayPool
  * (it still helps draining). results[k].prim = -1 for rays that were not asked for. */
 template <int N>
 __device__ __forceinline__ int b2_trace_pooled(const Ctx& ctx, const B2RayPool& pool, unsigned int& phase, const RayRequest (&rays)[N], B2Hit (&results)[N],
-                                               B2TraversalCounters* counters, int vote = 0)
+                                               B2TraversalCounters* counters, int stack_entries, int vote = 0)
 {
     static_assert(N <= B2_POOL_RAYS, "pool slots per thread");
     const unsigned int lane = threadIdx.x & 31u;
@@ -345,7 +345,7 @@ __device__ __forceinline__ int b2_trace_pooled(const Ctx& ctx, const B2RayPool& 
         }
         if (busy)
         {
-            if (!b2_traverse_step(t, ctx.bvh, ctx.stack_stride, ctx.faults))
+            if (!b2_traverse_step(t, ctx.bvh, ctx.stack_stride, ctx.faults, stack_entries))
             {
                 pool.slot_a[slot] = make_float4(t.best.t, t.best.u, t.best.v, __int_as_float(t.best.prim));
                 pool.slot_b[slot] = make_float4(t.best.ng.x, t.best.ng.y, t.best.ng.z, 0.0f);
@@ -382,7 +382,11 @@ __device__ __forceinline__ int b2_trace_pooled(const Ctx& ctx, const B2RayPool& 
     return block_vote;
 }
 
-#define B2_PH_SMEM_BYTES (B2_STACK_ENTRIES * B2_MK_THREADS * 8 + (B2_MK_THREADS / 32) * B2_QUEUE_SLOTS * 4 + B2_POOL_RAYS * B2_MK_THREADS * (2 * 16 + 4) + 16)
+/* shared memory of a phased block for a traversal stack of `entries` entries per thread: the stack is sized by the depth of the
+ * BVH at hand (Cornell: 9 entries = 36 KB instead of 96 KB), which leaves more of the SM's 256 KB to the L1 that backs the
+ * path state in local memory */
+#define B2_PH_SMEM_BYTES_FOR(entries) ((entries) * B2_MK_THREADS * 8 + (B2_MK_THREADS / 32) * B2_QUEUE_SLOTS * 4 + B2_POOL_RAYS * B2_MK_THREADS * (2 * 16 + 4) + 16)
+#define B2_PH_SMEM_BYTES B2_PH_SMEM_BYTES_FOR(B2_STACK_ENTRIES)
 
 template <class V>
 __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_phased(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x,
@@ -391,7 +395,8 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
     extern __shared__ __align__(16) unsigned char smem[];
     uint64_t* stacks = reinterpret_cast<uint64_t*>(smem);
     B2RayPool pool;
-    pool.slot_a = reinterpret_cast<float4*>(smem + B2_STACK_ENTRIES * B2_MK_THREADS * 8);
+    const int stack_entries = geom.stack_entries;
+    pool.slot_a = reinterpret_cast<float4*>(smem + stack_entries * B2_MK_THREADS * 8);
     pool.slot_b = pool.slot_a + B2_POOL_RAYS * B2_MK_THREADS;
     pool.list = reinterpret_cast<int*>(pool.slot_b + B2_POOL_RAYS * B2_MK_THREADS);
     uint32_t* queues = reinterpret_cast<uint32_t*>(pool.list + B2_POOL_RAYS * B2_MK_THREADS);
@@ -485,12 +490,12 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
         B2Hit results[3];
         int any_alive;
         if (Nee<V>::HAS_DEFERRED_Y)
-            any_alive = b2_trace_pooled<3>(ctx, pool, phase, rays, results, counters, alive ? 1 : 0);
+            any_alive = b2_trace_pooled<3>(ctx, pool, phase, rays, results, counters, stack_entries, alive ? 1 : 0);
         else
         {
             RayRequest two[2] = { rays[0], rays[1] };
             B2Hit two_results[2];
-            any_alive = b2_trace_pooled<2>(ctx, pool, phase, two, two_results, counters, alive ? 1 : 0);
+            any_alive = b2_trace_pooled<2>(ctx, pool, phase, two, two_results, counters, stack_entries, alive ? 1 : 0);
             results[0] = two_results[0];
             results[1] = two_results[1];
             results[2].t = -1.0f;
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
         sequential_result[0].prim = -1;
         sequential_result[0].ng = v3(0.0f);
         if (Nee<V>::HAS_SEQUENTIAL_RAY)
-            b2_trace_pooled<1>(ctx, pool, phase, sequential, sequential_result, counters);
+            b2_trace_pooled<1>(ctx, pool, phase, sequential, sequential_result, counters, stack_entries);
 
         if (alive)
         {
@@ -599,7 +604,7 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
             return e;
         const unsigned int total_tiles = (unsigned int)tiles_x * (unsigned int)((rows + 3) / 4);
         if (g.persistent == 2)
-            megakernel_phased<V><<<pd.sm_count * pd.blocks_per_sm[1], B2_MK_THREADS, B2_PH_SMEM_BYTES, stream>>>(*rd, g, tiles_x, total_tiles, counter);
+            megakernel_phased<V><<<pd.sm_count * pd.blocks_per_sm[1], B2_MK_THREADS, B2_PH_SMEM_BYTES_FOR(g.stack_entries), stream>>>(*rd, g, tiles_x, total_tiles, counter);
         else
             megakernel_persistent<V><<<pd.sm_count * pd.blocks_per_sm[0], B2_MKP_THREADS, 0, stream>>>(*rd, g, tiles_x, total_tiles, counter);
         return cudaGetLastError();
