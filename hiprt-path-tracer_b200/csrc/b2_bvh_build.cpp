@@ -3,7 +3,7 @@
  *
  * Replaces `HIPRTGeometry::build_bvh` (/root/reference/src/HIPRT-Orochi/HIPRTScene.h:87-150), which hands the
  * mesh to HIPRT's GPU LBVH/PLOC/SBVH builders. Per the north star the B200 build does this on the host:
- *   1. binned-SAH binary BVH over triangle boxes (16 bins, leaves of <= 3 triangles), subtrees built in parallel;
+ *   1. binned-SAH binary BVH over triangle boxes (64 bins; leaves of <= 2 triangles, 1 on scenes of a million triangles and more), subtrees built in parallel;
  *   2. collapse to 8-wide nodes by repeatedly opening the child with the largest surface area;
  *   3. octant-ordered slot assignment, 8-bit quantisation of child boxes on a power-of-two grid anchored at the
  *      node's min corner (floor / ceil, i.e. conservative), breadth-first emission so inner children are contiguous.
@@ -42,8 +42,13 @@ struct Bin2Node
     int first = 0, count = 0;  /* range in the permuted primitive array (leaf) */
 };
 
-constexpr int kBins = 16;
-constexpr int kMaxLeaf = 3;
+/* 64 bins: measured on the 10M-triangle scene, nodes visited per ray 28.7 (16 bins) -> 25.0 (32) -> 24.2 (64) -> 23.9 (128) */
+constexpr int kBins = 64;
+/* Triangles per leaf slot (<= 3, the CW8 leaf encoding). The traversal tests a leaf's triangles one after the other while
+ * the lanes whose node had no leaf hit wait, so on big scenes smaller leaves pay although they make more nodes. Measured on
+ * B200 (profiles/r01_ncu_megakernel_history.md): 10M triangles 3 / 2 / 1 per leaf = 25.2 / 27.3 / 28.9 Mpaths/s (nodes per
+ * ray 24.2 / 24.7 / 25.6, triangles per ray 9.9 / 7.8 / 5.9); Cornell (8k triangles) 342.9 / 344.2 / 328.1. */
+constexpr size_t kSmallLeafTriangleCount = 1u << 20;
 
 struct Builder
 {
@@ -53,7 +58,9 @@ struct Builder
     std::vector<Bin2Node> nodes;
     std::atomic<int> next_node{ 0 };
 
-    Builder(const std::vector<Box>& b, const std::vector<float>& c, std::vector<int>& o) : prim_box(b), centroid(c), order(o) { nodes.resize(std::max<size_t>(1, 2 * o.size())); }
+    int max_leaf;
+
+    Builder(const std::vector<Box>& b, const std::vector<float>& c, std::vector<int>& o, int leaf) : prim_box(b), centroid(c), order(o), max_leaf(leaf) { nodes.resize(std::max<size_t>(1, 2 * o.size())); }
 
     int alloc() { return next_node.fetch_add(1); }
 
@@ -68,7 +75,7 @@ struct Builder
             n.box.grow(prim_box[order[i]]);
             cbox.grow(&centroid[3 * (size_t)order[i]]);
         }
-        if (count <= kMaxLeaf)
+        if (count <= max_leaf)
         {
             n.first = first;
             n.count = count;
@@ -168,8 +175,11 @@ int grid_exponent(float extent)
 }
 } // namespace
 
-bool b2_build_cw8(const int* indices, size_t n_tri, const float* positions, size_t n_vert, B2BvhHost& out, std::string& error)
+bool b2_build_cw8(const int* indices, size_t n_tri, const float* positions, size_t n_vert, B2BvhHost& out, std::string& error, int max_leaf)
 {
+    if (max_leaf <= 0)
+        max_leaf = n_tri >= kSmallLeafTriangleCount ? 1 : 2;
+    max_leaf = std::min(max_leaf, 3);
     out.nodes.clear();
     out.tris.clear();
     out.stats = B2BvhStats();
@@ -204,7 +214,7 @@ bool b2_build_cw8(const int* indices, size_t n_tri, const float* positions, size
             centroid[3 * t + a] = 0.5f * (b.lo[a] + b.hi[a]);
     }
 
-    Builder builder(prim_box, centroid, order);
+    Builder builder(prim_box, centroid, order, max_leaf);
     int root = builder.alloc();
 #pragma omp parallel
 #pragma omp single

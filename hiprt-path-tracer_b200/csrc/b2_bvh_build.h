@@ -25,6 +25,7 @@ struct B2BvhHost
 };
 
 /* indices: 3 per triangle; positions: 3 floats per vertex. Returns false and fills `error` on invalid input. */
-bool b2_build_cw8(const int* indices, size_t n_tri, const float* positions, size_t n_vert, B2BvhHost& out, std::string& error);
+/* max_leaf: triangles per leaf slot, 1..3; 0 = chosen from the scene size (see b2_bvh_build.cpp) */
+bool b2_build_cw8(const int* indices, size_t n_tri, const float* positions, size_t n_vert, B2BvhHost& out, std::string& error, int max_leaf = 0);
 
 #endif

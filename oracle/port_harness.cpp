@@ -103,6 +103,7 @@ struct LutStore
 };
 
 static unsigned int g_port_faults[B2_FAULT_COUNT] = { 0, 0, 0 };
+static unsigned long long g_port_counters[3] = { 0, 0, 0 }; /* rays, nodes, triangles: traversal steps per ray of the CW8 BVH */
 
 template <class V>
 static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice& bvh, const Args& a)
@@ -115,12 +116,20 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
         ctx.bvh = bvh;
         ctx.stack = stack;
         ctx.stack_stride = 1;
-        ctx.counters = nullptr;
+        B2TraversalCounters local;
+        local.rays = local.nodes = local.tris = 0;
+        ctx.counters = &local;
         ctx.faults = g_port_faults;
 #pragma omp for schedule(dynamic)
         for (int y = a.win_y0; y < a.win_y1; y++)
             for (int x = a.win_x0; x < a.win_x1; x++)
                 b2_run_pass_pixel<V>(pass, ctx, (uint32_t)x, (uint32_t)y);
+#pragma omp critical
+        {
+            g_port_counters[0] += local.rays;
+            g_port_counters[1] += local.nodes;
+            g_port_counters[2] += local.tris;
+        }
     }
 }
 
@@ -363,8 +372,9 @@ int main(int argc, char** argv)
 
     long long window_pixels = (long long)(a.win_x1 - a.win_x0) * (a.win_y1 - a.win_y0);
     std::printf("{\"oracle\": \"port\", \"variant\": \"%s\", \"width\": %d, \"height\": %d, \"window_pixels\": %lld, \"spp\": %d, \"bounces\": %d, \"threads\": %d, "
-                "\"render_seconds\": %.6f, \"bvh_build_seconds\": %.3f, \"mpaths_per_s\": %.6f, \"bvh_nodes\": %zu, \"bvh_depth\": %d, \"triangles\": %zu, \"emissive_triangles\": %zu}\n",
+                "\"render_seconds\": %.6f, \"bvh_build_seconds\": %.3f, \"mpaths_per_s\": %.6f, \"bvh_nodes\": %zu, \"bvh_depth\": %d, \"triangles\": %zu, \"emissive_triangles\": %zu, \"rays\": %llu, \"nodes_per_ray\": %.3f, \"triangles_per_ray\": %.3f}\n",
                 a.variant.c_str(), a.width, a.height, window_pixels, a.spp, a.bounces, omp_get_max_threads(), seconds, scene.bvh_build_seconds,
-                (double)window_pixels * a.spp / seconds / 1.0e6, scene.bvh.nodes.size(), scene.bvh.stats.max_depth, scene.blob.n_triangles(), scene.emissive_triangles.size(), g_port_faults[0], g_port_faults[1], g_port_faults[2]);
+                (double)window_pixels * a.spp / seconds / 1.0e6, scene.bvh.nodes.size(), scene.bvh.stats.max_depth, scene.blob.n_triangles(), scene.emissive_triangles.size(), g_port_counters[0], (double)g_port_counters[1] / (double)(g_port_counters[0] ? g_port_counters[0] : 1),
+                (double)g_port_counters[2] / (double)(g_port_counters[0] ? g_port_counters[0] : 1));
     return 0;
 }
