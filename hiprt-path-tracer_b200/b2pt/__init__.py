@@ -233,7 +233,7 @@ class Renderer:
         self._exchange_cb = None
         self.exchange_count = 0
         cb = C.cast(None, EXCHANGE_FN)
-        if world > 1 and self.variant == "c4":
+        if world > 1 and self.variant.startswith("c4"):
             if torch is None or dist is None:
                 raise B2ptError("ReSTIR DI on several GPUs needs torch + torch.distributed for the reservoir exchange")
 

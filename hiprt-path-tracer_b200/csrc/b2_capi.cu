@@ -68,6 +68,7 @@ struct b2pt_kernel
     cudaEvent_t start = nullptr, stop = nullptr;
     bool timed = false;
     uint64_t launches = 0;
+    int light_presampling = 0; /* ReSTIR_DI_DoLightPresampling the kernel was asked for */
 };
 
 extern "C" {
@@ -374,7 +375,7 @@ static const MacroDefault kFixedMacros[] = {
     { "PrincipledBSDFDoMicrofacetRegularization", 1 }, { "PrincipledBSDFDoMicrofacetRegularizationConsistentParameterization", 1 },
     { "PrincipledBSDFMicrofacetRegularizationDiffusionHeuristic", 1 }, { "ReSTIR_DI_InitialTargetFunctionVisibility", 0 },
     { "ReSTIR_DI_SpatialTargetFunctionVisibility", 0 }, { "ReSTIR_DI_DoVisibilityReuse", 1 }, { "ReSTIR_DI_BiasCorrectionUseVisibility", 1 },
-    { "ReSTIR_DI_BiasCorrectionWeights", 4 }, { "ReSTIR_DI_DoLightPresampling", 0 }, { "ReSTIR_DI_DoOptimalVisibilitySampling", 0 },
+    { "ReSTIR_DI_BiasCorrectionWeights", 4 }, { "ReSTIR_DI_DoOptimalVisibilitySampling", 0 },
     { "DirectLightUseNEEPlusPlus", 0 }, { "SharedStackBVHTraversalSize", 16 },
 };
 
@@ -382,6 +383,7 @@ static int pass_of_entry_name(const char* name)
 {
     if (!std::strcmp(name, "CameraRays")) return B2_PASS_CAMERA_RAYS;
     if (!std::strcmp(name, "MegaKernel")) return B2_PASS_MEGAKERNEL;
+    if (!std::strcmp(name, "ReSTIR_DI_LightsPresampling")) return B2_PASS_RESTIR_DI_PRESAMPLING;
     if (!std::strcmp(name, "ReSTIR_DI_InitialCandidates")) return B2_PASS_RESTIR_DI_INITIAL_CANDIDATES;
     if (!std::strcmp(name, "ReSTIR_DI_TemporalReuse")) return B2_PASS_RESTIR_DI_TEMPORAL;
     if (!std::strcmp(name, "ReSTIR_DI_SpatialReuse")) return B2_PASS_RESTIR_DI_SPATIAL;
@@ -403,7 +405,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
         return B2PT_ERR_NO_VARIANT;
     }
     /* reference defaults */
-    int bsdf = 0, direct = 4, base = 1, later = 3, envmap = 2, precise = 1, counters = 0;
+    int bsdf = 0, direct = 4, base = 1, later = 3, envmap = 2, precise = 1, counters = 0, light_presampling = 0;
     for (int i = 0; i < option_count; i++)
     {
         const char* n = options[i].name;
@@ -414,6 +416,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
         else if (!std::strcmp(n, "DirectLightSamplingBaseStrategy")) base = v;
         else if (!std::strcmp(n, "ReSTIR_DI_LaterBouncesSamplingStrategy")) later = v;
         else if (!std::strcmp(n, "EnvmapSamplingStrategy")) envmap = v;
+        else if (!std::strcmp(n, "ReSTIR_DI_DoLightPresampling")) light_presampling = v != 0; /* launch-time switch of the same kernels */
         else if (!std::strcmp(n, "B2PT_PRECISE")) precise = v;
         else if (!std::strcmp(n, "B2PT_COUNTERS")) counters = v;
         else
@@ -447,6 +450,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
             b2pt_kernel* k = new b2pt_kernel();
             k->ctx = ctx;
             k->entry = &e;
+            k->light_presampling = light_presampling;
             B2_CUDA(cudaEventCreate(&k->start));
             B2_CUDA(cudaEventCreate(&k->stop));
             *out_kernel = k;
@@ -480,13 +484,23 @@ int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank
         b2_set_error("b2pt_kernel_launch: invalid argument");
         return B2PT_ERR_INVALID_ARGUMENT;
     }
-    const b2pt_render_data* rd = reinterpret_cast<const b2pt_render_data*>(args[0]);
+    /* ReSTIR_DI_LightsPresampling takes (LightPresamplingParameters, HIPRTRenderData) like the reference's kernel
+     * (ReSTIRDIRenderPass.cpp:441-444); every other entry takes the render data alone */
+    const bool presampling_pass = kernel->entry->pass == B2_PASS_RESTIR_DI_PRESAMPLING;
+    if (presampling_pass && !args[1])
+    {
+        b2_set_error("ReSTIR_DI_LightsPresampling: args = { &LightPresamplingParameters, &render_data }");
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    const b2pt_render_data* rd = reinterpret_cast<const b2pt_render_data*>(presampling_pass ? args[1] : args[0]);
     cudaStream_t s = (cudaStream_t)stream;
     B2LaunchGeom geom;
     geom.width = width;
     geom.height = height;
     geom.rank = rank;
     geom.world = world;
+    geom.light_presampling = kernel->light_presampling;
+    geom.presampling_parameters = presampling_pass ? args[0] : nullptr;
     geom.persistent = megakernel_form();
     geom.stack_entries = B2_STACK_ENTRIES;
     {

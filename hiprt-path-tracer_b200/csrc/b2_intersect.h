@@ -241,6 +241,7 @@ struct Ctx
     int stack_stride;              /* distance between this thread's consecutive slots */
     B2TraversalCounters* counters; /* null unless the instrumented variant runs */
     unsigned int* faults;          /* B2_FAULT_COUNT words (device global / host array) or null */
+    bool light_presampling;        /* ReSTIR_DI_DoLightPresampling: initial candidates come from the presampled light buffer */
 };
 
 /* HIPRTRenderSettings::do_render_low_resolution, RenderSettings.h */

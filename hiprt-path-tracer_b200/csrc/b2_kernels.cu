@@ -73,6 +73,7 @@ __device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd
     ctx.stack_stride = threads;
     ctx.counters = counters;
     ctx.faults = faults;
+    ctx.light_presampling = false;
 }
 
 __device__ __forceinline__ void b2_flush_counters(const B2TraversalCounters& local_counters)
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) pass_kernel(const __grid_con
 
     Ctx ctx;
     b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults);
+    ctx.light_presampling = geom.light_presampling != 0;
 
     b2_run_pass_pixel<V>(PASS, ctx, x, y);
 
@@ -552,6 +554,14 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
         b2_flush_counters(local_counters);
 }
 
+/* ReSTIR_DI_LightsPresampling: one thread per presampled light (kernels/ReSTIR/DI/LightsPresampling.h:78-110); arguments in the
+ * reference's order (LightPresamplingParameters, HIPRTRenderData) */
+template <class V>
+__global__ void __launch_bounds__(128) lights_presampling_kernel(const B2LightPresamplingParameters params, const __grid_constant__ b2pt_render_data rd)
+{
+    restir_di_presample_light<V>(rd, params, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 static int owned_rows(int height, const B2LaunchGeom& g)
 {
     int rows = 0;
@@ -564,6 +574,21 @@ template <class V, int PASS>
 cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cudaStream_t stream)
 {
     const B2LaunchGeom g = *geom;
+    if (PASS == B2_PASS_RESTIR_DI_PRESAMPLING)
+    {
+        if constexpr (V::DIRECT == B2_LSS_RESTIR_DI)
+        {
+            if (!g.presampling_parameters)
+                return cudaErrorInvalidValue;
+            const B2LightPresamplingParameters params = *reinterpret_cast<const B2LightPresamplingParameters*>(g.presampling_parameters);
+            const int count = params.number_of_subsets * params.subset_size;
+            if (count <= 0)
+                return cudaSuccess;
+            lights_presampling_kernel<V><<<(count + 127) / 128, 128, 0, stream>>>(params, *rd);
+            return cudaGetLastError();
+        }
+        return cudaErrorInvalidValue;
+    }
     const int rows = owned_rows(g.height, g);
     if (rows == 0)
         return cudaSuccess;
@@ -639,6 +664,7 @@ struct Reg
     Reg<BSDF, DIRECT, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_MEGAKERNEL>()
 
 #define B2_REG_RESTIR(BSDF, BASE, COUNTERS)                                                                                       \
+    Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_PRESAMPLING>(),        \
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_INITIAL_CANDIDATES>(), \
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_TEMPORAL>(),           \
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_SPATIAL>(),            \

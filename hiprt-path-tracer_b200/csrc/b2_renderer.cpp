@@ -95,12 +95,13 @@ void free_all(b2pt_renderer* r, std::vector<void*>& owner)
     owner.clear();
 }
 
-struct VariantKey { const char* name; int bsdf, direct, base, later; bool restir; };
+struct VariantKey { const char* name; int bsdf, direct, base, later; bool restir; bool presampling; };
 const VariantKey kVariants[] = {
-    { "c1", 1, 1, 0, 3, false },
-    { "c2", 0, 3, 1, 3, false },
-    { "c3", 0, 4, 1, 3, false },
-    { "c4", 0, 5, 1, 3, true },
+    { "c1", 1, 1, 0, 3, false, false },
+    { "c2", 0, 3, 1, 3, false, false },
+    { "c3", 0, 4, 1, 3, false, false },
+    { "c4", 0, 5, 1, 3, true, false },
+    { "c4p", 0, 5, 1, 3, true, true }, /* c4 with ReSTIR_DI_DoLightPresampling */
 };
 
 const VariantKey* find_variant(const std::string& name)
@@ -117,6 +118,7 @@ const char* entry_name_of_pass(int pass)
     {
     case B2_PASS_CAMERA_RAYS: return "CameraRays";
     case B2_PASS_MEGAKERNEL: return "MegaKernel";
+    case B2_PASS_RESTIR_DI_PRESAMPLING: return "ReSTIR_DI_LightsPresampling";
     case B2_PASS_RESTIR_DI_INITIAL_CANDIDATES: return "ReSTIR_DI_InitialCandidates";
     case B2_PASS_RESTIR_DI_TEMPORAL: return "ReSTIR_DI_TemporalReuse";
     case B2_PASS_RESTIR_DI_SPATIAL: return "ReSTIR_DI_SpatialReuse";
@@ -139,9 +141,12 @@ int resolve_kernels(b2pt_renderer* r)
         bool restir_pass = pass != B2_PASS_CAMERA_RAYS && pass != B2_PASS_MEGAKERNEL;
         if (restir_pass && !v->restir)
             continue;
+        if (pass == B2_PASS_RESTIR_DI_PRESAMPLING && !v->presampling)
+            continue;
         b2pt_option opts[] = {
             { "BSDFOverride", v->bsdf }, { "DirectLightSamplingStrategy", v->direct }, { "DirectLightSamplingBaseStrategy", v->base },
-            { "ReSTIR_DI_LaterBouncesSamplingStrategy", v->later }, { "B2PT_PRECISE", r->precise }, { "B2PT_COUNTERS", r->counters },
+            { "ReSTIR_DI_LaterBouncesSamplingStrategy", v->later }, { "ReSTIR_DI_DoLightPresampling", v->presampling ? 1 : 0 },
+            { "B2PT_PRECISE", r->precise }, { "B2PT_COUNTERS", r->counters },
         };
         B2_TRY(b2pt_kernel_get(r->ctx, entry, opts, (int)(sizeof(opts) / sizeof(opts[0])), &r->kernels[pass]));
     }
@@ -269,6 +274,7 @@ int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* varia
     r->variant = variant;
     r->precise = precise ? 1 : 0;
     r->loop.restir_di = find_variant(variant)->restir;
+    r->loop.restir_di_presampling = find_variant(variant)->presampling;
     B2_TRY(b2pt_stream_create(ctx, &r->stream));
     B2_TRY(b2pt_event_create(ctx, &r->ev_start));
     B2_TRY(b2pt_event_create(ctx, &r->ev_stop));
@@ -298,6 +304,13 @@ int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* varia
     }
     for (int i = 0; i < 3; i++)
         B2_TRY(alloc_zero(r, r->frame_allocs, n * 36, &r->d_reservoirs[i]));
+    if (r->loop.restir_di_presampling)
+    {
+        /* ReSTIRDIRenderPass allocates number_of_subsets * subset_size presampled lights of 48 bytes (defaults 128 x 1024) */
+        const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+        B2_TRY(alloc_zero(r, r->frame_allocs, (size_t)di.light_presampling.number_of_subsets * di.light_presampling.subset_size * 48, &p));
+        rd.render_settings.restir_di_settings.light_presampling.light_samples = p;
+    }
     r->loop.initial_reservoirs = r->d_reservoirs[0];
     r->loop.spatial_reservoirs_1 = r->d_reservoirs[1];
     r->loop.spatial_reservoirs_2 = r->d_reservoirs[2];
@@ -577,7 +590,19 @@ int b2pt_renderer_render(b2pt_renderer* r, int samples)
                 r->exchanges++;
             }
         }
-        void* args[1] = { &r->loop.rd };
+        /* LightPresamplingParameters as the reference's pass fills it (ReSTIRDIRenderPass.cpp:417-444) */
+        struct { int number_of_subsets, subset_size; void* out_light_samples; float envmap_sampling_probability; } presampling;
+        const b2pt_restir_di_settings& di_settings = r->loop.rd.render_settings.restir_di_settings;
+        presampling.number_of_subsets = di_settings.light_presampling.number_of_subsets;
+        presampling.subset_size = di_settings.light_presampling.subset_size;
+        presampling.out_light_samples = di_settings.light_presampling.light_samples;
+        presampling.envmap_sampling_probability = di_settings.initial_candidates.envmap_candidate_probability;
+        void* args[2] = { &r->loop.rd, nullptr };
+        if (pass == B2_PASS_RESTIR_DI_PRESAMPLING)
+        {
+            args[0] = &presampling;
+            args[1] = &r->loop.rd;
+        }
         rc = b2pt_kernel_launch_rows(k, r->width, r->height, rank, world, args, r->stream);
         r->pass_launches[pass]++;
         if (rc == B2PT_OK && r->profile_passes)

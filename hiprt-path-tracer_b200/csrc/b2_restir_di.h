@@ -385,6 +385,112 @@ struct PairwiseMis
 
 /* ---------------------------------------------------------------------------------------------------------- */
 /* initial candidates (InitialCandidates.h) */
+/* ---- light presampling (kernels/ReSTIR/DI/LightsPresampling.h, includes/ReSTIR/DI/PresampledLight.h) ----------------------------
+ * ReSTIRDIPresampledLight is 48 bytes in the reference: tri index, point (envmap samples: direction in envmap space), light
+ * normal, radiance, pdf, one flags byte + 3 bytes of padding (written here as one word, flags in the low byte). */
+struct B2PresampledLight
+{
+    int emissive_triangle_index;
+    float px, py, pz;
+    float nx, ny, nz;
+    float r, g, b;
+    float pdf;
+    uint32_t flags;
+};
+static_assert(sizeof(B2PresampledLight) == 48, "ReSTIRDIPresampledLight is 48 bytes");
+
+/* LightPresamplingParameters (Device/kernel_parameters/ReSTIR/DI/LightPresamplingParameters.h): first kernel argument of
+ * ReSTIR_DI_LightsPresampling */
+struct B2LightPresamplingParameters
+{
+    int number_of_subsets;
+    int subset_size;
+    B2PresampledLight* out_light_samples;
+    float envmap_sampling_probability;
+};
+static_assert(sizeof(B2LightPresamplingParameters) == 24, "LightPresamplingParameters is 24 bytes");
+
+/* One thread per presampled light: LightsPresampling.h:78-110 (presample_envmap :27-41, presample_emissive_triangle :43-64) */
+template <class V>
+B2_HD void restir_di_presample_light(const b2pt_render_data& rd, const B2LightPresamplingParameters& params, uint32_t x)
+{
+    if (rd.buffers.emissive_triangles_count == 0 && rd.world_settings.ambient_light_type != 2)
+        return;
+    if (x >= (uint32_t)(params.subset_size * params.number_of_subsets))
+        return;
+    uint32_t seed = rd.render_settings.freeze_random ? wang_hash(x + 1) : wang_hash((x + 1) * (rd.render_settings.sample_number + 1) * rd.random_number);
+    Rng rng = make_rng(seed);
+
+    float envmap_candidate_probability = 0.0f;
+    if (rd.world_settings.ambient_light_type == 2)
+        envmap_candidate_probability = rd.buffers.emissive_triangles_count == 0 ? 1.0f : params.envmap_sampling_probability;
+
+    B2PresampledLight light;
+    light.emissive_triangle_index = -1;
+    light.px = light.py = light.pz = 0.0f;
+    light.nx = light.ny = light.nz = 0.0f;
+    light.r = light.g = light.b = 0.0f;
+    light.pdf = 0.0f;
+    light.flags = B2_DI_FLAGS_NONE;
+    if (rng.next_float() < envmap_candidate_probability)
+    {
+        light.flags |= B2_DI_FLAGS_ENVMAP_SAMPLE;
+        V3 direction = v3(0.0f, 1.0f, 0.0f);
+        float pdf = 0.0f;
+        Rgb radiance = rd.world_settings.envmap ? envmap_sample<V>(rd.world_settings, direction, pdf, rng) : rgb(0.0f);
+        V3 envmap_space = mat3_mul_vec(rd.world_settings.world_to_envmap_matrix, direction);
+        light.px = envmap_space.x; light.py = envmap_space.y; light.pz = envmap_space.z;
+        light.r = radiance.r; light.g = radiance.g; light.b = radiance.b;
+        light.pdf = pdf * envmap_candidate_probability;
+    }
+    else
+    {
+        LightSample sample = sample_one_emissive_triangle<V>(rd, rng);
+        if (sample.area_measure_pdf > 0.0f)
+        {
+            light.px = sample.point_on_light.x; light.py = sample.point_on_light.y; light.pz = sample.point_on_light.z;
+            light.nx = sample.light_source_normal.x; light.ny = sample.light_source_normal.y; light.nz = sample.light_source_normal.z;
+            light.emissive_triangle_index = sample.emissive_triangle_index;
+            light.pdf = sample.area_measure_pdf * (1.0f - envmap_candidate_probability);
+            light.r = sample.emission.r; light.g = sample.emission.g; light.b = sample.emission.b;
+        }
+    }
+    params.out_light_samples[x] = light;
+}
+
+/* use_presampled_light_candidate, InitialCandidates.h:33-90: every pixel of a tile_size x tile_size tile draws from the same
+ * random subset of the presampled lights */
+B2_HD DiSample use_presampled_light_candidate(const b2pt_render_data& rd, int px, int py, V3 evaluated_point, V3 shading_normal, Rgb& out_sample_radiance,
+                                              float& out_sample_cosine_term, float& out_sample_pdf, Rng& rng)
+{
+    const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    const int tx = px / di.light_presampling.tile_size, ty = py / di.light_presampling.tile_size;
+    const int tile_index_seed = (tx + ty + 1) * (tx + ty) / 2 + ty; /* cantor_pairing_function */
+    Rng subset_rng = make_rng(rd.random_number * (uint32_t)(tile_index_seed + 1));
+    int random_subset_index = subset_rng.next_index(di.light_presampling.number_of_subsets);
+    int random_light_index_in_subset = rng.next_index(di.light_presampling.subset_size);
+    int light_sample_index = random_subset_index * di.light_presampling.subset_size + random_light_index_in_subset;
+    const B2PresampledLight presampled = reinterpret_cast<const B2PresampledLight*>(di.light_presampling.light_samples)[light_sample_index];
+
+    DiSample light_sample = di_sample_defaults();
+    light_sample.emissive_triangle_index = presampled.emissive_triangle_index;
+    light_sample.point_on_light_source = v3(presampled.px, presampled.py, presampled.pz);
+    light_sample.flags = presampled.flags & 0xFFu;
+    out_sample_radiance = rgb(presampled.r, presampled.g, presampled.b);
+    out_sample_pdf = presampled.pdf;
+
+    float distance_to_light;
+    V3 to_light_direction = di_light_sample_direction(rd, light_sample, evaluated_point, distance_to_light);
+    out_sample_cosine_term = dot(shading_normal, to_light_direction);
+    if (!light_sample.is_envmap_sample())
+    {
+        bool contributes_enough = check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, out_sample_radiance * out_sample_cosine_term / out_sample_pdf);
+        if (!contributes_enough)
+            light_sample.target_function = B2_LIGHT_DOESNT_CONTRIBUTE_ENOUGH;
+    }
+    return light_sample;
+}
+
 template <class V>
 B2_HD DiSample sample_fresh_light_candidate(const Ctx& ctx, float envmap_candidate_probability, const HitInfo& hit, Rgb& out_sample_radiance, float& out_sample_cosine_term,
                                             float& out_sample_pdf, Rng& rng)
@@ -448,7 +554,7 @@ B2_HD DiSurface surface_from_hit(const HitInfo& hit, const Payload& payload, V3 
 }
 
 template <class V>
-B2_HD DiReservoir sample_initial_candidates(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng)
+B2_HD DiReservoir sample_initial_candidates(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, int pixel_x, int pixel_y)
 {
     const b2pt_render_data& rd = *ctx.rd;
     const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
@@ -478,7 +584,10 @@ B2_HD DiReservoir sample_initial_candidates(const Ctx& ctx, Payload& payload, co
         float distance_to_light = 0.0f;
         V3 to_light_direction = v3(0.0f);
 
-        DiSample light_sample = sample_fresh_light_candidate<V>(ctx, envmap_candidate_probability, hit, sample_radiance, sample_cosine_term, light_pdf_area_measure, rng);
+        /* ReSTIR_DI_DoLightPresampling (a -D macro in the reference, InitialCandidates.h:192-211) is a launch-time switch here */
+        DiSample light_sample = ctx.light_presampling
+                                    ? use_presampled_light_candidate(rd, pixel_x, pixel_y, hit.inter_point, hit.shading_normal, sample_radiance, sample_cosine_term, light_pdf_area_measure, rng)
+                                    : sample_fresh_light_candidate<V>(ctx, envmap_candidate_probability, hit, sample_radiance, sample_cosine_term, light_pdf_area_measure, rng);
         to_light_direction = di_light_sample_direction(rd, light_sample, hit.inter_point, distance_to_light);
 
         if (light_sample.target_function == B2_LIGHT_DOESNT_CONTRIBUTE_ENOUGH)
@@ -633,7 +742,7 @@ B2_HD void restir_di_initial_candidates_pixel(const Ctx& ctx, uint32_t x, uint32
 
     V3 cam = v3(rd.current_camera.position.x, rd.current_camera.position.y, rd.current_camera.position.z);
     V3 view_direction = normalize(cam - hit.inter_point);
-    DiReservoir initial_candidates_reservoir = sample_initial_candidates<V>(ctx, payload, hit, view_direction, rng);
+    DiReservoir initial_candidates_reservoir = sample_initial_candidates<V>(ctx, payload, hit, view_direction, rng, (int)x, (int)y);
 
     di_visibility_test_kill_reservoir(ctx, initial_candidates_reservoir, hit.inter_point, hit.primitive_index);
     di_store(rd, rd.render_settings.restir_di_settings.initial_candidates.output_reservoirs, (int)pixel_index, initial_candidates_reservoir);

@@ -124,9 +124,11 @@ int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
 /* Kernels. Replaces GPUKernel::compile -> hiprtBuildTraceKernels (src/Compiler/GPUKernel.cpp:72-83,
  * src/HIPRT-Orochi/HIPRTOrochiUtils.cpp:118-164) by a lookup in a table of PRECOMPILED sm_100a variants, and
  * GPUKernel::launch_asynchronous -> oroModuleLaunchKernel (src/Compiler/GPUKernel.cpp:151-165).
- * Entry names served: "CameraRays", "MegaKernel", "ReSTIR_DI_InitialCandidates", "ReSTIR_DI_TemporalReuse",
- * "ReSTIR_DI_SpatialReuse", "ReSTIR_DI_SpatiotemporalReuse" (MegaKernelRenderPass.cpp:20,
- * FillGBufferRenderPass.cpp:23, ReSTIRDIRenderPass.cpp:21-29).
+ * Entry names served: "CameraRays", "MegaKernel", "ReSTIR_DI_LightsPresampling", "ReSTIR_DI_InitialCandidates",
+ * "ReSTIR_DI_TemporalReuse", "ReSTIR_DI_SpatialReuse", "ReSTIR_DI_SpatiotemporalReuse" (MegaKernelRenderPass.cpp:20,
+ * FillGBufferRenderPass.cpp:23, ReSTIRDIRenderPass.cpp:21-29). "ReSTIR_DI_LightsPresampling" takes the reference's two
+ * arguments, args = { &LightPresamplingParameters, &render_data } (ReSTIRDIRenderPass.cpp:441-444); kernels obtained with
+ * {"ReSTIR_DI_DoLightPresampling", 1} draw their initial light candidates from render_data's presampled-light buffer.
  * Options are the reference's macro names with integer values, e.g. {"DirectLightSamplingStrategy", 3}; macros not
  * listed take the reference's defaults. Two extra options select the codegen flavour:
  *   {"B2PT_PRECISE", 1}  (default) IEEE fp32 without FMA contraction: the flavour parity is asserted on;
@@ -172,7 +174,7 @@ int b2pt_counters_read(b2pt_ctx* ctx, b2pt_counters_t* out);
  * (2) headless renderer (host mirror of GPURenderer, CPURenderer pass order)
  * ------------------------------------------------------------------------------------------------------------ */
 
-/* variant: "c1" | "c2" | "c3" | "c4" (see b2_kernels_body.h); precise: 1 = parity flavour, 0 = fast flavour */
+/* variant: "c1" | "c2" | "c3" | "c4" | "c4p" (= c4 + ReSTIR DI light presampling) (see b2_kernels_body.h); precise: 1 = parity flavour, 0 = fast flavour */
 int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* variant, int precise, b2pt_renderer** out_renderer);
 int b2pt_renderer_destroy(b2pt_renderer* renderer);
 /* Scene from a B2SCENE1 file (include/b2pt_scene_blob.h) or from host arrays laid out like the reference's Scene. */

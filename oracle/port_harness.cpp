@@ -120,6 +120,7 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
         local.rays = local.nodes = local.tris = 0;
         ctx.counters = &local;
         ctx.faults = g_port_faults;
+        ctx.light_presampling = a.variant == "c4p";
 #pragma omp for schedule(dynamic)
         for (int y = a.win_y0; y < a.win_y1; y++)
             for (int x = a.win_x0; x < a.win_x1; x++)
@@ -304,7 +305,16 @@ int main(int argc, char** argv)
     bvh.tri_count = (uint32_t)scene.bvh.tris.size();
     rd.GPU_BVH = &bvh;
 
-    loop.restir_di = a.variant == "c4";
+    loop.restir_di = a.variant == "c4" || a.variant == "c4p";
+    loop.restir_di_presampling = a.variant == "c4p";
+    std::vector<B2PresampledLight> presampled_lights;
+    if (loop.restir_di_presampling)
+    {
+        const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+        presampled_lights.resize((size_t)di.light_presampling.number_of_subsets * di.light_presampling.subset_size);
+        std::memset(presampled_lights.data(), 0, presampled_lights.size() * sizeof(B2PresampledLight));
+        rd.render_settings.restir_di_settings.light_presampling.light_samples = presampled_lights.data();
+    }
 
     int frame = 0;
     auto launch = [&](B2Pass pass) {
@@ -321,7 +331,20 @@ int main(int argc, char** argv)
         else if (a.variant == "c3") run_pass<B2VariantC3>(pass, rd, bvh, a);
 #endif
 #ifdef B2_PORT_HAVE_C4
-        else if (a.variant == "c4") run_pass<B2VariantC4>(pass, rd, bvh, a);
+        else if (pass == B2_PASS_RESTIR_DI_PRESAMPLING)
+        {
+            /* ReSTIR_DI_LightsPresampling: one "thread" per presampled light, whole buffer (not windowed) */
+            const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+            B2LightPresamplingParameters params;
+            params.number_of_subsets = di.light_presampling.number_of_subsets;
+            params.subset_size = di.light_presampling.subset_size;
+            params.out_light_samples = presampled_lights.data();
+            params.envmap_sampling_probability = di.initial_candidates.envmap_candidate_probability;
+#pragma omp parallel for schedule(static)
+            for (int index = 0; index < params.number_of_subsets * params.subset_size; index++)
+                restir_di_presample_light<B2VariantC4>(rd, params, (uint32_t)index);
+        }
+        else if (a.variant == "c4" || a.variant == "c4p") run_pass<B2VariantC4>(pass, rd, bvh, a);
 #endif
         else { std::fprintf(stderr, "unknown variant %s\n", a.variant.c_str()); std::exit(2); }
         if (a.dump_per_sample && !a.dump.empty() && pass != B2_PASS_CAMERA_RAYS && pass != B2_PASS_MEGAKERNEL)

@@ -20,7 +20,7 @@ def make_renderer(b2pt, ctx, meta, precise=True):
     r.set_scene_file(DATA / f"{meta['scene']}.b2scene")
     r.set_luts_file(DATA / "brdf_luts.b2luts")
     r.set(nb_bounces=meta["bounces"])
-    if variant == "c4":
+    if variant.startswith("c4"):
         r.set(restir_di_do_fused_spatiotemporal=0 if "--no-fused" in meta.get("extra", []) else 1)
     if envmap_of(meta):
         r.set_envmap_file(envmap_of(meta))

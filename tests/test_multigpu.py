@@ -20,7 +20,8 @@ def _gpu_count():
 
 
 @pytest.mark.parametrize("variant,extra", [("c2", []), ("c4", ["--fused", "1"]), ("c4", ["--fused", "0"]),
-                                           ("c4", ["--fused", "1", "--scene", "synthetic_20k", "--envmap", "data/sky_128x64.b2env"])])
+                                           ("c4", ["--fused", "1", "--scene", "synthetic_20k", "--envmap", "data/sky_128x64.b2env"]),
+                                           ("c4p", ["--fused", "1", "--scene", "synthetic_20k", "--envmap", "data/sky_128x64.b2env"])])
 def test_partitioned_render_is_bit_identical(built, variant, extra):
     n = min(_gpu_count(), 4)
     if n < 2:
@@ -32,5 +33,5 @@ def test_partitioned_render_is_bit_identical(built, variant, extra):
     assert out.returncode == 0 and lines, out.stdout[-2000:] + out.stderr[-2000:]
     report = json.loads(lines[-1])
     assert report["bit_identical_on_all_ranks"], report
-    if variant == "c4":
+    if variant.startswith("c4"):
         assert report["reservoir_exchanges"] > 0

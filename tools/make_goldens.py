@@ -30,6 +30,9 @@ CASES = [
     # (Cornell + envmap + split temporal/spatial passes is not a usable case: at the 2nd frame the REFERENCE produces a NaN
     #  reservoir at pixel [54, 47], indexes emissive_triangles[-1] and segfaults; the fused variant below is fine)
     ("c4_env_96x54_fused", "c4", "cornell_pbr_16x9", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
+    # ReSTIR_DI_DoLightPresampling: the ReSTIR_DI_LightsPresampling kernel + presampled initial light candidates (variant "c4p")
+    ("c4p_synenv_96x54_fused", "c4p", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
+    ("c4p_cornell_96x54_split", "c4p", "cornell_pbr_16x9", 96, 54, 2, 4, ["--no-fused"]),
 ]
 
 

@@ -45,7 +45,7 @@ def main():
         r.set_scene_file(ROOT / "data" / f"{a.scene}.b2scene")
         r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
         r.set(nb_bounces=a.bounces)
-        if a.variant == "c4":
+        if a.variant.startswith("c4"):
             r.set(restir_di_do_fused_spatiotemporal=a.fused)
         if a.envmap:
             r.set_envmap_file(ROOT / a.envmap)
@@ -54,7 +54,7 @@ def main():
     whole = make()
     whole.render(a.spp)
     ref = whole.framebuffer().copy()
-    ref_res = whole.reservoirs(3).copy() if a.variant == "c4" else None
+    ref_res = whole.reservoirs(3).copy() if a.variant.startswith("c4") else None
     whole.close()
 
     part = make()
