@@ -384,6 +384,7 @@ static int pass_of_entry_name(const char* name)
     if (!std::strcmp(name, "CameraRays")) return B2_PASS_CAMERA_RAYS;
     if (!std::strcmp(name, "MegaKernel")) return B2_PASS_MEGAKERNEL;
     if (!std::strcmp(name, "ReSTIR_DI_LightsPresampling")) return B2_PASS_RESTIR_DI_PRESAMPLING;
+    if (!std::strcmp(name, "ReSTIR_Directional_Reuse_Compute")) return B2_PASS_RESTIR_DIRECTIONAL_REUSE;
     if (!std::strcmp(name, "ReSTIR_DI_InitialCandidates")) return B2_PASS_RESTIR_DI_INITIAL_CANDIDATES;
     if (!std::strcmp(name, "ReSTIR_DI_TemporalReuse")) return B2_PASS_RESTIR_DI_TEMPORAL;
     if (!std::strcmp(name, "ReSTIR_DI_SpatialReuse")) return B2_PASS_RESTIR_DI_SPATIAL;
@@ -501,6 +502,19 @@ int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank
     geom.world = world;
     geom.light_presampling = kernel->light_presampling;
     geom.presampling_parameters = presampling_pass ? args[0] : nullptr;
+    geom.directional_masks_ull = nullptr;
+    geom.directional_radius = nullptr;
+    if (kernel->entry->pass == B2_PASS_RESTIR_DIRECTIONAL_REUSE)
+    {
+        /* args = { &render_data, &masks_u, &masks_ull, &radius } (ReSTIRDIRenderPass.cpp:409-411) */
+        if (!args[1] || !args[2] || !args[3])
+        {
+            b2_set_error("ReSTIR_Directional_Reuse_Compute: args = { &render_data, &masks_u, &masks_ull, &radius }");
+            return B2PT_ERR_INVALID_ARGUMENT;
+        }
+        geom.directional_masks_ull = *reinterpret_cast<void**>(args[2]);
+        geom.directional_radius = *reinterpret_cast<void**>(args[3]);
+    }
     geom.persistent = megakernel_form();
     geom.stack_entries = B2_STACK_ENTRIES;
     {

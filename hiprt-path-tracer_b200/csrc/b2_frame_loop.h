@@ -24,6 +24,7 @@ enum B2Pass
 {
     B2_PASS_CAMERA_RAYS = 0,
     B2_PASS_RESTIR_DI_PRESAMPLING,
+    B2_PASS_RESTIR_DIRECTIONAL_REUSE,
     B2_PASS_RESTIR_DI_INITIAL_CANDIDATES,
     B2_PASS_RESTIR_DI_TEMPORAL,
     B2_PASS_RESTIR_DI_SPATIAL,
@@ -188,6 +189,13 @@ struct B2FrameLoop
             rd.random_number = host_rng.next_u32();
             launch(B2_PASS_RESTIR_DI_PRESAMPLING);
         }
+
+        /* ReSTIRDIRenderPass::compute_optimal_spatial_reuse_radii (ReSTIRDIRenderPass.cpp:391-415): a prepass at sample 0 of an
+         * accumulating, non-interactive render; no host RNG draw. (The CPURenderer defines the equivalent function but never
+         * calls it for ReSTIR DI, CPURenderer.cpp:797-818,863-872; the test oracle calls it at this point on request.) */
+        if (di.common_spatial_pass.use_adaptive_directional_spatial_reuse && rd.render_settings.accumulate && rd.render_settings.sample_number == 0 &&
+            !rd.render_settings.wants_render_low_resolution)
+            launch(B2_PASS_RESTIR_DIRECTIONAL_REUSE);
 
         rd.random_number = host_rng.next_u32();
         di.initial_candidates.output_reservoirs = initial_reservoirs;

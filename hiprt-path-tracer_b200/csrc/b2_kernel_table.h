@@ -16,6 +16,8 @@ struct B2LaunchGeom
     int stack_entries; /* phased MegaKernel: traversal-stack entries per thread (BVH depth + 1 when known, else B2_STACK_ENTRIES) */
     int light_presampling; /* ReSTIR DI initial candidates: take light candidates from the presampled buffer */
     const void* presampling_parameters; /* ReSTIR_DI_LightsPresampling only: host pointer to its LightPresamplingParameters argument */
+    void* directional_masks_ull; /* ReSTIR_Directional_Reuse_Compute only: its two output buffers (device pointers) */
+    void* directional_radius;
     int persistent; /* MegaKernel only: 0 = one thread per pixel, 1 = persistent warps, 2 = persistent + phased (pooled rays) */
 };
 

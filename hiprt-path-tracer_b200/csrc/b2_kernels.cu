@@ -562,6 +562,14 @@ __global__ void __launch_bounds__(128) lights_presampling_kernel(const B2LightPr
     restir_di_presample_light<V>(rd, params, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+/* ReSTIR_Directional_Reuse_Compute: one thread per pixel, 8x8 tiles; arguments in the reference's order (render data, 32-bit masks
+ * [unused: the DI instantiation keeps 64 direction bits], 64-bit masks, radii) */
+__global__ void __launch_bounds__(B2_BLOCK_THREADS) directional_reuse_kernel(const __grid_constant__ b2pt_render_data rd, unsigned int*, unsigned long long* masks_ull, uint8_t* radius, int tiles_x)
+{
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    restir_directional_reuse_compute_pixel(rd, tile_x * B2_TILE_W + (threadIdx.x & 7), tile_y * B2_TILE_H + (threadIdx.x >> 3), masks_ull, radius);
+}
+
 static int owned_rows(int height, const B2LaunchGeom& g)
 {
     int rows = 0;
@@ -574,6 +582,14 @@ template <class V, int PASS>
 cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cudaStream_t stream)
 {
     const B2LaunchGeom g = *geom;
+    if (PASS == B2_PASS_RESTIR_DIRECTIONAL_REUSE)
+    {
+        if (!g.directional_masks_ull || !g.directional_radius)
+            return cudaErrorInvalidValue;
+        const int tx = (g.width + B2_TILE_W - 1) / B2_TILE_W, ty = (g.height + B2_TILE_H - 1) / B2_TILE_H;
+        directional_reuse_kernel<<<tx * ty, B2_BLOCK_THREADS, 0, stream>>>(*rd, nullptr, (unsigned long long*)g.directional_masks_ull, (uint8_t*)g.directional_radius, tx);
+        return cudaGetLastError();
+    }
     if (PASS == B2_PASS_RESTIR_DI_PRESAMPLING)
     {
         if constexpr (V::DIRECT == B2_LSS_RESTIR_DI)
@@ -665,6 +681,7 @@ struct Reg
 
 #define B2_REG_RESTIR(BSDF, BASE, COUNTERS)                                                                                       \
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_PRESAMPLING>(),        \
+    Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DIRECTIONAL_REUSE>(),     \
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_INITIAL_CANDIDATES>(), \
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_TEMPORAL>(),           \
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_SPATIAL>(),            \

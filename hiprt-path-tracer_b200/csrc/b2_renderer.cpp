@@ -119,6 +119,7 @@ const char* entry_name_of_pass(int pass)
     case B2_PASS_CAMERA_RAYS: return "CameraRays";
     case B2_PASS_MEGAKERNEL: return "MegaKernel";
     case B2_PASS_RESTIR_DI_PRESAMPLING: return "ReSTIR_DI_LightsPresampling";
+    case B2_PASS_RESTIR_DIRECTIONAL_REUSE: return "ReSTIR_Directional_Reuse_Compute";
     case B2_PASS_RESTIR_DI_INITIAL_CANDIDATES: return "ReSTIR_DI_InitialCandidates";
     case B2_PASS_RESTIR_DI_TEMPORAL: return "ReSTIR_DI_TemporalReuse";
     case B2_PASS_RESTIR_DI_SPATIAL: return "ReSTIR_DI_SpatialReuse";
@@ -304,6 +305,14 @@ int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* varia
     }
     for (int i = 0; i < 3; i++)
         B2_TRY(alloc_zero(r, r->frame_allocs, n * 36, &r->d_reservoirs[i]));
+    if (r->loop.restir_di)
+    {
+        /* per-pixel radius + 64-bit direction mask of the adaptive-directional spatial reuse (ReSTIRDIRenderPass.h) */
+        B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(unsigned long long), &p));
+        rd.render_settings.restir_di_settings.common_spatial_pass.per_pixel_spatial_reuse_directions_mask_ull = (unsigned long long*)p;
+        B2_TRY(alloc_zero(r, r->frame_allocs, n, &p));
+        rd.render_settings.restir_di_settings.common_spatial_pass.per_pixel_spatial_reuse_radius = (uint8_t*)p;
+    }
     if (r->loop.restir_di_presampling)
     {
         /* ReSTIRDIRenderPass allocates number_of_subsets * subset_size presampled lights of 48 bytes (defaults 128 x 1024) */
@@ -597,11 +606,20 @@ int b2pt_renderer_render(b2pt_renderer* r, int samples)
         presampling.subset_size = di_settings.light_presampling.subset_size;
         presampling.out_light_samples = di_settings.light_presampling.light_samples;
         presampling.envmap_sampling_probability = di_settings.initial_candidates.envmap_candidate_probability;
-        void* args[2] = { &r->loop.rd, nullptr };
+        void* args[4] = { &r->loop.rd, nullptr, nullptr, nullptr };
+        unsigned int* masks_u = nullptr;
+        unsigned long long* masks_ull = r->loop.rd.render_settings.restir_di_settings.common_spatial_pass.per_pixel_spatial_reuse_directions_mask_ull;
+        uint8_t* radius = r->loop.rd.render_settings.restir_di_settings.common_spatial_pass.per_pixel_spatial_reuse_radius;
         if (pass == B2_PASS_RESTIR_DI_PRESAMPLING)
         {
             args[0] = &presampling;
             args[1] = &r->loop.rd;
+        }
+        else if (pass == B2_PASS_RESTIR_DIRECTIONAL_REUSE)
+        {
+            args[1] = &masks_u;
+            args[2] = &masks_ull;
+            args[3] = &radius;
         }
         rc = b2pt_kernel_launch_rows(k, r->width, r->height, rank, world, args, r->stream);
         r->pass_launches[pass]++;

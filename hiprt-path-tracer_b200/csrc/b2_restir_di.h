@@ -384,6 +384,69 @@ struct PairwiseMis
 };
 
 /* ---------------------------------------------------------------------------------------------------------- */
+/* ReSTIR_Directional_Reuse_Compute (kernels/ReSTIR/DirectionalReuseCompute.h:30-155, DI instantiation: 64 direction bits):
+ * for 32 radii between the minimum and the configured reuse radius, test 64 directions ON the circle of that radius with
+ * the neighbour-similarity heuristics (a direction must have passed at the previous radius); keep the radius whose valid arc
+ * covers the largest area and the mask of its valid directions. The RNG the reference constructs is never drawn from. */
+B2_HD void restir_directional_reuse_compute_pixel(const b2pt_render_data& rd, uint32_t x, uint32_t y, unsigned long long* out_masks_ull, uint8_t* out_radius)
+{
+    const b2pt_int2 res = rd.render_settings.render_resolution;
+    if (x >= (uint32_t)res.x || y >= (uint32_t)res.y)
+        return;
+    const uint32_t center_pixel_index = x + y * res.x;
+    if (!rd.aux_buffers.pixel_active[center_pixel_index])
+        return;
+    out_masks_ull[center_pixel_index] = 0;
+    out_radius[center_pixel_index] = 0;
+
+    const b2pt_restir_spatial_common& sp = rd.render_settings.restir_di_settings.common_spatial_pass;
+    V3 center_shading_point = load_v3(rd.g_buffer.primary_hit_position, center_pixel_index);
+    V3 center_normal = rd.render_settings.restir_di_settings.neighbor_similarity_settings.reject_using_geometric_normals
+                           ? unpack_normal_oct24(rd.g_buffer.geometric_normals[center_pixel_index])
+                           : unpack_normal_oct24(rd.g_buffer.shading_normals[center_pixel_index]);
+    const int NB_RADIUS = 32, NB_SAMPLES_PER_RADIUS = 64;
+    float best_area = 0.0f;
+    int best_radius_index = 0;
+    unsigned long long best_mask = 0, previous_mask = 0;
+    for (int radius_index = 0; radius_index < NB_RADIUS; radius_index++)
+    {
+        float current_radius = sp.minimum_per_pixel_reuse_radius + (radius_index / (float)NB_RADIUS) * (sp.reuse_radius - sp.minimum_per_pixel_reuse_radius);
+        float current_radius_circle_area = B2_PI * current_radius * current_radius;
+        float area_at_current_radius = 0.0f;
+        unsigned long long mask = 0;
+        for (int sample_index = 0; sample_index < NB_SAMPLES_PER_RADIUS; sample_index++)
+        {
+            if (radius_index > 0 && !(previous_mask & (1ull << sample_index)))
+                continue;
+            float theta = sample_index / (float)NB_SAMPLES_PER_RADIUS * B2_TWO_PI;
+            float x_circle = current_radius * cosf(theta);
+            float y_circle = current_radius * sinf(theta);
+            int nx = (int)x + (int)roundf(x_circle), ny = (int)y + (int)roundf(y_circle);
+            if (nx < 0 || nx >= res.x || ny < 0 || ny >= res.y)
+                continue;
+            int neighbor_index = nx + ny * res.x;
+            if (!check_neighbor_similarity_heuristics(rd, neighbor_index, (int)center_pixel_index, center_shading_point, center_normal, false))
+                continue;
+            mask |= 1ull << sample_index;
+            area_at_current_radius += current_radius_circle_area * (1.0f / NB_SAMPLES_PER_RADIUS);
+        }
+        if (best_area < area_at_current_radius)
+        {
+            best_area = area_at_current_radius;
+            best_radius_index = radius_index;
+            best_mask = mask;
+        }
+        previous_mask = mask;
+    }
+    float best_radius = sp.minimum_per_pixel_reuse_radius + (best_radius_index / (float)NB_RADIUS) * (sp.reuse_radius - sp.minimum_per_pixel_reuse_radius);
+    if (best_area == 0.0f)
+        best_radius = 0.0f;
+    out_radius[center_pixel_index] = (uint8_t)best_radius;
+    /* = valid_samples_per_radius[best_radius_index]; when no radius has a valid direction that is index 0, an empty mask */
+    out_masks_ull[center_pixel_index] = best_mask;
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
 /* initial candidates (InitialCandidates.h) */
 /* ---- light presampling (kernels/ReSTIR/DI/LightsPresampling.h, includes/ReSTIR/DI/PresampledLight.h) ----------------------------
  * ReSTIRDIPresampledLight is 48 bytes in the reference: tri index, point (envmap samples: direction in envmap space), light

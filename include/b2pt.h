@@ -124,7 +124,8 @@ int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
 /* Kernels. Replaces GPUKernel::compile -> hiprtBuildTraceKernels (src/Compiler/GPUKernel.cpp:72-83,
  * src/HIPRT-Orochi/HIPRTOrochiUtils.cpp:118-164) by a lookup in a table of PRECOMPILED sm_100a variants, and
  * GPUKernel::launch_asynchronous -> oroModuleLaunchKernel (src/Compiler/GPUKernel.cpp:151-165).
- * Entry names served: "CameraRays", "MegaKernel", "ReSTIR_DI_LightsPresampling", "ReSTIR_DI_InitialCandidates",
+ * Entry names served: "CameraRays", "MegaKernel", "ReSTIR_DI_LightsPresampling", "ReSTIR_Directional_Reuse_Compute"
+ * (args = { &render_data, &masks_u, &masks_ull, &radius }, ReSTIRDIRenderPass.cpp:409-411), "ReSTIR_DI_InitialCandidates",
  * "ReSTIR_DI_TemporalReuse", "ReSTIR_DI_SpatialReuse", "ReSTIR_DI_SpatiotemporalReuse" (MegaKernelRenderPass.cpp:20,
  * FillGBufferRenderPass.cpp:23, ReSTIRDIRenderPass.cpp:21-29). "ReSTIR_DI_LightsPresampling" takes the reference's two
  * arguments, args = { &LightPresamplingParameters, &render_data } (ReSTIRDIRenderPass.cpp:441-444); kernels obtained with

@@ -28,7 +28,7 @@ struct Args
     int width = 512, height = 512, spp = 1, bounces = 3;
     int win_x0 = 0, win_y0 = 0, win_x1 = -1, win_y1 = -1;
     int threads = 0;
-    bool fused = true, dump_per_sample = false, no_jitter = false;
+    bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false;
     int spatial_passes = 1;
     unsigned int seed = 42;
 };
@@ -56,6 +56,7 @@ static Args parse_args(int argc, char** argv)
         else if (k == "--spatial-passes") a.spatial_passes = std::atoi(next());
         else if (k == "--dump-per-sample") a.dump_per_sample = true;
         else if (k == "--no-jitter") a.no_jitter = true;
+        else if (k == "--directional-reuse") a.directional_reuse = true; /* use_adaptive_directional_spatial_reuse + the prepass */
         else { std::fprintf(stderr, "unknown argument %s\n", k.c_str()); std::exit(2); }
     }
     if (a.win_x1 < 0) { a.win_x1 = a.width; a.win_y1 = a.height; }
@@ -163,6 +164,7 @@ int main(int argc, char** argv)
     rd.render_settings.samples_per_frame = a.spp;
     rd.render_settings.output_debug_sample_N = a.spp - 1;
     rd.render_settings.restir_di_settings.do_fused_spatiotemporal = a.fused;
+    rd.render_settings.restir_di_settings.common_spatial_pass.use_adaptive_directional_spatial_reuse = a.directional_reuse ? 1 : 0;
     rd.render_settings.restir_di_settings.common_spatial_pass.number_of_passes = a.spatial_passes;
 
     /* camera */
@@ -307,6 +309,10 @@ int main(int argc, char** argv)
 
     loop.restir_di = a.variant == "c4" || a.variant == "c4p";
     loop.restir_di_presampling = a.variant == "c4p";
+    std::vector<unsigned long long> directional_masks((size_t)a.width * a.height, 0ull);
+    std::vector<uint8_t> directional_radius((size_t)a.width * a.height, 0);
+    rd.render_settings.restir_di_settings.common_spatial_pass.per_pixel_spatial_reuse_directions_mask_ull = directional_masks.data();
+    rd.render_settings.restir_di_settings.common_spatial_pass.per_pixel_spatial_reuse_radius = directional_radius.data();
     std::vector<B2PresampledLight> presampled_lights;
     if (loop.restir_di_presampling)
     {
@@ -331,6 +337,14 @@ int main(int argc, char** argv)
         else if (a.variant == "c3") run_pass<B2VariantC3>(pass, rd, bvh, a);
 #endif
 #ifdef B2_PORT_HAVE_C4
+        else if (pass == B2_PASS_RESTIR_DIRECTIONAL_REUSE)
+        {
+            b2pt_restir_spatial_common& sp = rd.render_settings.restir_di_settings.common_spatial_pass;
+#pragma omp parallel for schedule(dynamic)
+            for (int y = a.win_y0; y < a.win_y1; y++)
+                for (int x = a.win_x0; x < a.win_x1; x++)
+                    restir_directional_reuse_compute_pixel(rd, (uint32_t)x, (uint32_t)y, sp.per_pixel_spatial_reuse_directions_mask_ull, sp.per_pixel_spatial_reuse_radius);
+        }
         else if (pass == B2_PASS_RESTIR_DI_PRESAMPLING)
         {
             /* ReSTIR_DI_LightsPresampling: one "thread" per presampled light, whole buffer (not windowed) */

@@ -22,6 +22,8 @@ def make_renderer(b2pt, ctx, meta, precise=True):
     r.set(nb_bounces=meta["bounces"])
     if variant.startswith("c4"):
         r.set(restir_di_do_fused_spatiotemporal=0 if "--no-fused" in meta.get("extra", []) else 1)
+    if "--directional-reuse" in meta.get("extra", []):
+        r.set(restir_di_use_adaptive_directional_spatial_reuse=1)
     if envmap_of(meta):
         r.set_envmap_file(envmap_of(meta))
     return r

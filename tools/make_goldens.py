@@ -33,6 +33,10 @@ CASES = [
     # ReSTIR_DI_DoLightPresampling: the ReSTIR_DI_LightsPresampling kernel + presampled initial light candidates (variant "c4p")
     ("c4p_synenv_96x54_fused", "c4p", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
     ("c4p_cornell_96x54_split", "c4p", "cornell_pbr_16x9", 96, 54, 2, 4, ["--no-fused"]),
+    # adaptive-directional spatial reuse: the ReSTIR_Directional_Reuse_Compute prepass (per-pixel radius + 64-bit direction
+    # mask) and the spatial neighbour sampling restricted to the allowed directions
+    ("c4_syn_96x54_directional_fused", "c4", "synthetic_20k", 96, 54, 3, 4, ["--directional-reuse"]),
+    ("c4_syn_96x54_directional_split", "c4", "synthetic_20k", 96, 54, 2, 4, ["--directional-reuse", "--no-fused"]),
 ]
 
 
