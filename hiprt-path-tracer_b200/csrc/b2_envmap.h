@@ -26,8 +26,8 @@ B2_HD Rgb envmap_texel(const b2pt_world_settings& ws, V2 uv)
 B2_HD Rgb eval_envmap_no_pdf(const b2pt_world_settings& ws, V3 direction)
 {
     V3 rotated = mat3_mul_vec(ws.world_to_envmap_matrix, direction);
-    float u = 0.5f + atan2f(rotated.z, rotated.x) * B2_INV_2_PI;
-    float v = 0.5f + asinf(rotated.y) * B2_INV_PI;
+    float u = (float)((b2w)0.5f + b2w_atan2(rotated.z, rotated.x) * (b2w)B2_INV_2_PI);
+    float v = (float)((b2w)0.5f + b2w_asin(rotated.y) * (b2w)B2_INV_PI);
     return envmap_texel(ws, v2(u, v));
 }
 
@@ -48,9 +48,9 @@ B2_HD Rgb envmap_sample(const b2pt_world_settings& ws, V3& sampled_direction, fl
     float v = (float)y / (float)ws.envmap_height;
     float phi = u * B2_TWO_PI;
     float theta = b2_max(1.0e-5f, v * B2_PI);
-    float cos_theta = cosf(theta);
-    float sin_theta = sinf(theta);
-    sampled_direction = v3(-sin_theta * cosf(phi), -cos_theta, -sin_theta * sinf(phi));
+    float cos_theta = (float)b2w_cos(theta);
+    float sin_theta = (float)b2w_sin(theta);
+    sampled_direction = v3((float)((b2w)(-sin_theta) * b2w_cos(phi)), -cos_theta, (float)((b2w)(-sin_theta) * b2w_sin(phi)));
     sampled_direction = mat3_mul_vec(ws.envmap_to_world_matrix, sampled_direction);
 
     Rgb radiance = envmap_texel(ws, v2(u, v));
@@ -69,8 +69,8 @@ B2_HD Rgb envmap_eval(const b2pt_world_settings& ws, V3 direction, float& pdf)
         return rgb(0.0f);
     }
     Rgb radiance = eval_envmap_no_pdf(ws, direction);
-    float theta_bsdf_dir = acosf(-direction.y);
-    float sin_theta = sinf(theta_bsdf_dir);
+    float theta_bsdf_dir = (float)b2w_acos(-direction.y);
+    float sin_theta = (float)b2w_sin(theta_bsdf_dir);
     pdf = luminance(radiance) / (ws.envmap_total_sum * ws.envmap_intensity);
     pdf *= (float)(ws.envmap_width * ws.envmap_height);
     pdf /= (B2_TWO_PI_SQUARED * sin_theta);

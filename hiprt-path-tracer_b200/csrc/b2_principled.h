@@ -111,13 +111,13 @@ B2_HD float full_fresnel_dielectric(float cos_theta_i, float eta_i, float eta_t)
 /* Hoffman 2023 / Adobe Standard Material F82-tint conductor Fresnel */
 B2_HD Rgb adobe_f82_tint_fresnel(Rgb F0, Rgb F82, Rgb F90, float F90_falloff_exponent, float cos_theta)
 {
-    Rgb base_term = F0 + (F90 - F0) * powf(1.0f - cos_theta, F90_falloff_exponent);
+    Rgb base_term = F0 + (F90 - F0) * (float)b2w_pow(1.0f - cos_theta, F90_falloff_exponent);
     if (max_component(base_term) < 1.0e-8f)
         return rgb(0.0f);
     float lazanyi_correction = cos_theta * b2_pow_6(1.0f - cos_theta);
     const float cos_theta_max = 1.0f / 7.0f;
     const float denom_a = cos_theta_max * b2_pow_6(1.0f - cos_theta_max);
-    Rgb nume_a = (F0 + (F90 - F0) * powf(1.0f - cos_theta_max, F90_falloff_exponent)) * (rgb(1.0f) - F82);
+    Rgb nume_a = (F0 + (F90 - F0) * (float)b2w_pow(1.0f - cos_theta_max, F90_falloff_exponent)) * (rgb(1.0f) - F82);
     Rgb a = nume_a / denom_a;
     Rgb F = base_term - a * lazanyi_correction;
     return rgb_clamp(F, 0.0f, 1.0f);
@@ -278,7 +278,8 @@ B2_HD_NOINLINE Rgb thin_film_fresnel(const Mat& material, float ambient_IOR, flo
  * ------------------------------------------------------------------------------------------------------------ */
 B2_HD float regularization_consistent_tau(float tau_0, int sample_number)
 {
-    return 1.0f / (2.0f * B2_PI * (1.0f - cosf(atanf(powf((float)(sample_number + 1), -1.0f / 6.0f) * sqrtf(B2_FOUR_PI * tau_0 - 1.0f) / (B2_TWO_PI * tau_0 - 1.0f)))));
+    /* powf(...) * sqrt(...) / (...): the unqualified sqrt makes the product and the quotient double (MicrofacetRegularization.h:160) */
+    return 1.0f / (2.0f * B2_PI * (1.0f - cosf(atanf((float)((b2w)powf((float)(sample_number + 1), -1.0f / 6.0f) * b2w_sqrt(B2_FOUR_PI * tau_0 - 1.0f) / (b2w)(B2_TWO_PI * tau_0 - 1.0f))))));
 }
 
 B2_HD float regularize_reflection(const b2pt_render_data& rd, int mode, float initial_roughness, float accumulated_path_roughness)
@@ -323,7 +324,7 @@ B2_HD float thin_walled_roughness(bool thin_walled, float base_roughness, float 
 {
     if (!thin_walled)
         return base_roughness;
-    float remapped = base_roughness * sqrtf(3.7f * (relative_eta - 1.0f) * b2_square(relative_eta - 0.5f) / b2_pow_3(relative_eta));
+    float remapped = (float)((b2w)base_roughness * b2w_sqrt(3.7f * (relative_eta - 1.0f) * b2_square(relative_eta - 0.5f) / b2_pow_3(relative_eta)));
     return b2_clamp(0.0f, 1.0f, remapped / 1.39f);
 }
 
@@ -373,7 +374,7 @@ B2_HD float G1_Smith_lambda(float alpha_x, float alpha_y, V3 d)
 {
     float ax = d.x * alpha_x;
     float ay = d.y * alpha_y;
-    return (-1.0f + sqrtf(1.0f + (ax * ax + ay * ay) / (d.z * d.z))) * 0.5f;
+    return (float)(((b2w)-1.0f + b2w_sqrt(1.0f + (ax * ax + ay * ay) / (d.z * d.z))) * (b2w)0.5f);
 }
 
 B2_HD float G1_Smith(float alpha_x, float alpha_y, V3 d) { return 1.0f / (1.0f + G1_Smith_lambda(alpha_x, alpha_y, d)); }
@@ -554,10 +555,10 @@ B2_HD V3 GGX_VNDF_sample(V3 local_view_direction, float alpha_x, float alpha_y, 
 
     float r = sqrtf(r1);
     float phi = B2_TWO_PI * r2;
-    float t1 = r * cosf(phi);
-    float t2 = r * sinf(phi);
+    float t1 = (float)((b2w)r * b2w_cos(phi));
+    float t2 = (float)((b2w)r * b2w_sin(phi));
     float s = 0.5f * (1.0f + Vh.z);
-    t2 = (1.0f - s) * sqrtf(1.0f - t1 * t1) + s * t2;
+    t2 = (float)((b2w)(1.0f - s) * b2w_sqrt(1.0f - t1 * t1) + (b2w)(s * t2));
 
     V3 Nh = t1 * T1 + t2 * T2 + sqrtf(b2_max(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
     return normalize(v3(alpha_x * Nh.x, alpha_y * Nh.y, b2_max(0.0f, Nh.z)));
@@ -674,7 +675,7 @@ B2_HD float ggx_energy_compensation_dielectrics(const b2pt_render_data& rd, cons
 
         float view_direction_tex_fetch = powf(b2_max(1.0e-3f, NoV), 1.0f / exponent_correction);
         float F0 = F0_from_eta(eta_t, eta_i);
-        float F0_remapped = sqrtf(sqrtf(F0));
+        float F0_remapped = (float)b2w_sqrt(b2w_sqrt(F0));
 
         const void* texture;
         if (material.thin_walled)
@@ -716,8 +717,8 @@ B2_HD float energy_compensation_glossy_base(const b2pt_render_data& rd, const Ma
     if (fabsf(relative_ior - 1.0f) < 1.0e-3f)
         relative_ior += 1.0e-3f;
 
-    float view_dir_remapped = powf(NoV, 1.0f / 2.5f);
-    float F0_remapped = sqrtf(sqrtf(F0_from_eta_t_and_relative_ior(ior, relative_ior)));
+    float view_dir_remapped = (float)b2w_pow(NoV, 1.0f / 2.5f);
+    float F0_remapped = (float)b2w_sqrt(b2w_sqrt(F0_from_eta_t_and_relative_ior(ior, relative_ior)));
     float multiple_scattering_compensation = lut_fetch_3d(rd.bsdfs_data.glossy_dielectric_directional_albedo, view_dir_remapped, material.roughness, F0_remapped);
 
     float ms_compensation = b2_lerp(1.0f, multiple_scattering_compensation, material.specular);
@@ -737,8 +738,8 @@ B2_HD float energy_compensation_clearcoat_lobe(const b2pt_render_data& rd, const
     if (fabsf(material.coat_ior / incident_medium_ior - 1.0f) < 1.0e-3f)
         incident_medium_ior += 1.0e-3f;
 
-    float view_dir_remapped = powf(NoV, 1.0f / 2.5f);
-    float F0_remapped = sqrtf(sqrtf(F0_from_eta(material.coat_ior, incident_medium_ior)));
+    float view_dir_remapped = (float)b2w_pow(NoV, 1.0f / 2.5f);
+    float F0_remapped = (float)b2w_sqrt(b2w_sqrt(F0_from_eta(material.coat_ior, incident_medium_ior)));
     float multiple_scattering_compensation = lut_fetch_3d(rd.bsdfs_data.glossy_dielectric_directional_albedo, view_dir_remapped, material.coat_roughness, F0_remapped);
 
     float ms_compensation = b2_lerp(1.0f, multiple_scattering_compensation, material.coat * (1.0f - material.specular_transmission));
@@ -766,7 +767,7 @@ B2_HD V3 sheen_read_LTC_parameters(const b2pt_render_data& rd, float roughness, 
 
 B2_HD float sheen_get_phi(V3 direction)
 {
-    float p = atan2f(direction.y, direction.x);
+    float p = (float)b2w_atan2(direction.y, direction.x);
     if (p < 0.0f)
         p += B2_TWO_PI;
     return p;
@@ -774,8 +775,8 @@ B2_HD float sheen_get_phi(V3 direction)
 
 B2_HD V3 sheen_rotate_vector(V3 vec, V3 axis, float angle)
 {
-    float sin_angle = sinf(angle);
-    float cos_angle = cosf(angle);
+    float sin_angle = (float)b2w_sin(angle);
+    float cos_angle = (float)b2w_cos(angle);
     return vec * cos_angle + axis * dot(vec, axis) * (1.0f - cos_angle) + sin_angle * cross(axis, vec);
 }
 

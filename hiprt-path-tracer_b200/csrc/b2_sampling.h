@@ -19,8 +19,8 @@ B2_HD float balance_heuristic(float pdf_a, float pdf_b) { return balance_heurist
 B2_HD V2 sample_in_disk_uv(float radius, V2 uv)
 {
     float r_sqrt_v = radius * sqrtf(uv.y);
-    float x = r_sqrt_v * cosf(B2_TWO_PI * uv.x);
-    float y = r_sqrt_v * sinf(B2_TWO_PI * uv.x);
+    float x = (float)((b2w)r_sqrt_v * b2w_cos(B2_TWO_PI * uv.x));
+    float y = (float)((b2w)r_sqrt_v * b2w_sin(B2_TWO_PI * uv.x));
     return v2(x, y);
 }
 
@@ -44,7 +44,7 @@ B2_HD V3 cosine_weighted_sample_around_normal_world_space(V3 normal, Rng& rng)
     }
     float theta = B2_TWO_PI * rand_1;
     float s = sqrtf(1.0f - rand_2 * rand_2);
-    V3 sphere_point = v3(s * cosf(theta), s * sinf(theta), rand_2);
+    V3 sphere_point = v3(s * (float)b2w_cos(theta), s * (float)b2w_sin(theta), rand_2);
     return normalize(normal + sphere_point);
 }
 
@@ -55,7 +55,7 @@ B2_HD V3 cosine_weighted_sample_z_up_frame(Rng& rng)
     float phi = B2_TWO_PI * r1;
     float cos_theta = sqrtf(r2);
     float sin_theta = sqrtf(1 - cos_theta * cos_theta);
-    return normalize(v3(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta));
+    return normalize(v3((float)(b2w_cos(phi) * (b2w)sin_theta), (float)(b2w_sin(phi) * (b2w)sin_theta), cos_theta));
 }
 
 /* Duff et al. style branchless basis, ONB.h:18-30 */
@@ -76,7 +76,7 @@ B2_HD void build_rotated_ONB(V3 N, V3& T, V3& B, float basis_rotation)
 {
     V3 up = fabsf(N.z) < 0.9999999f ? v3(0.0f, 0.0f, 1.0f) : v3(1.0f, 0.0f, 0.0f);
     T = normalize(cross(up, N));
-    T = T * cosf(basis_rotation) + cross(N, T) * sinf(basis_rotation) + N * dot(N, T) * (1.0f - cosf(basis_rotation));
+    T = T * (float)b2w_cos(basis_rotation) + cross(N, T) * (float)b2w_sin(basis_rotation) + N * dot(N, T) * (float)((b2w)1.0f - b2w_cos(basis_rotation));
     B = cross(N, T);
 }
 

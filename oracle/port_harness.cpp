@@ -28,7 +28,7 @@ struct Args
     int width = 512, height = 512, spp = 1, bounces = 3;
     int win_x0 = 0, win_y0 = 0, win_x1 = -1, win_y1 = -1;
     int threads = 0;
-    bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false;
+    bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false, kat = false;
     int spatial_passes = 1;
     unsigned int seed = 42;
 };
@@ -56,6 +56,7 @@ static Args parse_args(int argc, char** argv)
         else if (k == "--spatial-passes") a.spatial_passes = std::atoi(next());
         else if (k == "--dump-per-sample") a.dump_per_sample = true;
         else if (k == "--no-jitter") a.no_jitter = true;
+        else if (k == "--kat") a.kat = true; /* function-level known-answer dump instead of a render (see run_bsdf_kat) */
         else if (k == "--directional-reuse") a.directional_reuse = true; /* use_adaptive_directional_spatial_reuse + the prepass */
         else { std::fprintf(stderr, "unknown argument %s\n", k.c_str()); std::exit(2); }
     }
@@ -134,6 +135,60 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
         }
     }
 }
+
+/* Function-level known-answer vectors: same inputs and record layout as run_bsdf_kat in ref_harness.cpp, computed with the
+ * product's bsdf_eval / bsdf_sample (variant c2: principled BSDF). */
+static void kat_directions(unsigned int index, V3& normal, V3& view, V3& light, unsigned int& seed)
+{
+    Rng g = make_rng(wang_hash(index + 1u));
+    auto unit = [&]() {
+        float z = 2.0f * g.next_float() - 1.0f, phi = 6.2831853f * g.next_float(), r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+        return v3(r * cosf(phi), r * sinf(phi), z);
+    };
+    normal = unit();
+    view = unit();
+    if (dot(view, normal) < 0.0f) view = view * -1.0f;
+    light = unit();
+    seed = g.next_u32() | 1u;
+}
+
+#ifdef B2_PORT_HAVE_C2
+static void run_bsdf_kat(const b2pt_render_data& rd, const Args& a, int n_materials)
+{
+    const int per_material = 64;
+    std::vector<float> eval_out((size_t)n_materials * per_material * 4), sample_out((size_t)n_materials * per_material * 7);
+    for (int m = 0; m < n_materials; m++)
+        for (int k = 0; k < per_material; k++)
+        {
+            V3 normal, view, light;
+            unsigned int seed;
+            kat_directions((unsigned int)(m * per_material + k), normal, view, light, seed);
+            Mat material = load_scene_material(rd.buffers.materials_buffer, m, rd.bsdfs_data.white_furnace_mode != 0);
+            VolumeState volume_state;
+            Rng rng = make_rng(seed);
+            {
+                int info = B2_LOBE_NO_INFO;
+                BsdfCtx ctx = make_bsdf_ctx(view, normal, normal, light, &info, &volume_state, false, &material, 1, 0.0f);
+                float pdf = 0.0f;
+                Rgb c = bsdf_eval<B2VariantC2>(rd, ctx, pdf);
+                float* out = &eval_out[((size_t)m * per_material + k) * 4];
+                out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = pdf;
+            }
+            {
+                int info = B2_LOBE_NO_INFO;
+                BsdfCtx ctx = make_bsdf_ctx(view, normal, normal, v3(0.0f), &info, &volume_state, false, &material, 1, 0.0f);
+                float pdf = 0.0f;
+                V3 dir = v3(0.0f);
+                Rgb c = bsdf_sample<B2VariantC2>(rd, ctx, dir, pdf, rng);
+                float* out = &sample_out[((size_t)m * per_material + k) * 7];
+                out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = pdf; out[4] = dir.x; out[5] = dir.y; out[6] = dir.z;
+            }
+        }
+    dump_array(a.dump, "kat_bsdf_eval", eval_out.data(), eval_out.size());
+    dump_array(a.dump, "kat_bsdf_sample", sample_out.data(), sample_out.size());
+    std::printf("{\"oracle\": \"port\", \"kat\": \"bsdf\", \"materials\": %d, \"per_material\": %d}\n", n_materials, per_material);
+}
+#endif
 
 int main(int argc, char** argv)
 {
@@ -307,6 +362,13 @@ int main(int argc, char** argv)
     bvh.tri_count = (uint32_t)scene.bvh.tris.size();
     rd.GPU_BVH = &bvh;
 
+#ifdef B2_PORT_HAVE_C2
+    if (a.kat)
+    {
+        run_bsdf_kat(rd, a, (int)scene.blob.n_materials());
+        return 0;
+    }
+#endif
     loop.restir_di = a.variant == "c4" || a.variant == "c4p";
     loop.restir_di_presampling = a.variant == "c4p";
     std::vector<unsigned long long> directional_masks((size_t)a.width * a.height, 0ull);
