@@ -86,6 +86,13 @@ def envmap_of(meta):
     return ROOT / extra[extra.index("--envmap") + 1] if "--envmap" in extra else None
 
 
+def pixels_not_bit_identical(a, b):
+    """Number of pixels whose float32 RGB differs in any bit."""
+    a = np.ascontiguousarray(np.asarray(a, np.float32).reshape(-1, 3)).view(np.uint32)
+    b = np.ascontiguousarray(np.asarray(b, np.float32).reshape(-1, 3)).view(np.uint32)
+    return int((a != b).any(axis=1).sum())
+
+
 def rel_error(a, b):
     """Per-pixel max-over-channels relative error, |a-b| / max(|a|,|b|), 0 where both are ~0."""
     a = np.asarray(a, np.float64).reshape(-1, 3)

@@ -5,13 +5,17 @@ seed within 1e-3 relative (precise flavour)."""
 import numpy as np
 import pytest
 
-from conftest import DATA, GOLDEN, envmap_of, load_golden, rel_error, run_oracle
+from conftest import DATA, GOLDEN, envmap_of, load_golden, pixels_not_bit_identical, rel_error, run_oracle
 
 pytestmark = pytest.mark.gpu
 
 CASES = sorted(p.stem for p in GOLDEN.glob("*.npz"))
 REL_TOL = 1e-3
 OUTLIER_FRACTION = 2e-3
+# The precise flavour evaluates every expression the way the reference's host build does and is
+# bit-identical to it at full size on C1-C3; the slack covers the reference's own reads of uninitialised memory in
+# ReSTIR DI (a handful of pixels per 100k).
+BIT_EXACT_SLACK = 1e-3
 
 
 def make_renderer(b2pt, ctx, meta, precise=True):
@@ -48,6 +52,8 @@ def test_cuda_precise_matches_golden(b2pt, gpu_ctx, name):
     assert np.array_equal(mat, g["gbuffer_material"])
     rel = rel_error(fb, g["framebuffer"])
     assert (rel > REL_TOL).mean() <= OUTLIER_FRACTION, f"{(rel > REL_TOL).sum()} of {rel.size} pixels beyond {REL_TOL}"
+    differing = pixels_not_bit_identical(fb, g["framebuffer"])
+    assert differing <= max(2, BIT_EXACT_SLACK * rel.size), f"{differing} of {rel.size} pixels are not bit-identical to the reference"
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -80,6 +86,7 @@ def test_c1_512_against_reference_oracle_on_host(b2pt, gpu_ctx, tmp_path):
     assert np.array_equal(gb["position"].view(np.uint32), ref["position"].view(np.uint32))
     rel = rel_error(fb, ref["framebuffer"])
     assert (rel > REL_TOL).mean() <= OUTLIER_FRACTION
+    assert pixels_not_bit_identical(fb, ref["framebuffer"]) <= 26  # observed: 0 of 262144
 
 
 @pytest.mark.parametrize("variant", ["c1", "c4"])
@@ -149,6 +156,8 @@ def test_other_megakernel_forms_match_golden(b2pt, gpu_ctx, megakernel_form, nam
     r.close()
     rel = rel_error(fb, g["framebuffer"])
     assert (rel > REL_TOL).mean() <= OUTLIER_FRACTION, f"{(rel > REL_TOL).sum()} of {rel.size} pixels beyond {REL_TOL}"
+    differing = pixels_not_bit_identical(fb, g["framebuffer"])
+    assert differing <= max(2, BIT_EXACT_SLACK * rel.size), f"{differing} of {rel.size} pixels are not bit-identical to the reference"
 
 
 @pytest.mark.parametrize("variant,width,height,spp", [("c2", 1920, 1080, 2), ("c3", 1920, 1080, 1), ("c4", 1280, 720, 3)])
