@@ -397,7 +397,9 @@ def main():
     c = ctx.counters_read()
     r.set_counters(False)
     if rank == 0:
-        mk_ms = pass_ms.get("MegaKernel", 0.0) / max(1, n_launch.get("MegaKernel", 1))
+        if n_launch.get("MegaKernel", 0) <= 0 or pass_ms.get("MegaKernel", 0.0) <= 0.0:
+            raise RuntimeError(f"no MegaKernel launch was timed by the profiled render (passes seen: {sorted(pass_ms)}): the roofline would be empty")
+        mk_ms = pass_ms["MegaKernel"] / n_launch["MegaKernel"]
         own = r.owned_pixels() if world > 1 else W * H
         rays = c["rays"] / spp   # per launch (one launch = one sample of every pixel)
         # B_path: traversal bytes + per-vertex hit reconstruction + light candidates + per-pixel G-buffer / framebuffer traffic.

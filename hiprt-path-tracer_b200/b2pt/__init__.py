@@ -14,8 +14,9 @@ PKG_DIR = Path(__file__).resolve().parent.parent
 LIB_PATH = PKG_DIR / "libb2pt.so"
 REPO_ROOT = PKG_DIR.parent
 
-PASS_NAMES = ["CameraRays", "ReSTIR_DI_LightsPresampling", "ReSTIR_DI_InitialCandidates", "ReSTIR_DI_TemporalReuse",
-              "ReSTIR_DI_SpatialReuse", "ReSTIR_DI_SpatiotemporalReuse", "MegaKernel"]
+# index = the B2_PASS_* enumerator of csrc/b2_frame_loop.h (tests/test_abi.py keeps the two in step)
+PASS_NAMES = ["CameraRays", "ReSTIR_DI_LightsPresampling", "ReSTIR_Directional_Reuse_Compute", "ReSTIR_DI_InitialCandidates",
+              "ReSTIR_DI_TemporalReuse", "ReSTIR_DI_SpatialReuse", "ReSTIR_DI_SpatiotemporalReuse", "MegaKernel"]
 
 
 class B2ptError(RuntimeError):

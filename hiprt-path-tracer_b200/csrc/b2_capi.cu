@@ -215,6 +215,12 @@ int b2pt_stream_synchronize(b2pt_ctx*, b2pt_stream stream)
     B2_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return B2PT_OK;
 }
+int b2pt_stream_launch_host_func(b2pt_ctx*, b2pt_stream stream, b2pt_host_fn fn, void* user)
+{
+    if (!fn) { b2_set_error("b2pt_stream_launch_host_func: null function"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_CUDA(cudaLaunchHostFunc((cudaStream_t)stream, fn, user));
+    return B2PT_OK;
+}
 int b2pt_event_create(b2pt_ctx*, b2pt_event* out_event)
 {
     cudaEvent_t e;

@@ -92,6 +92,10 @@ int b2pt_event_destroy(b2pt_ctx* ctx, b2pt_event event);
 int b2pt_event_record(b2pt_ctx* ctx, b2pt_event event, b2pt_stream stream);
 int b2pt_event_synchronize(b2pt_ctx* ctx, b2pt_event event);
 int b2pt_event_elapsed_ms(b2pt_ctx* ctx, b2pt_event start, b2pt_event stop, float* out_ms);
+/* Runs fn(user) on a driver thread once everything queued on `stream` before it has finished. Replaces oroLaunchHostFunc
+ * (src/Renderer/GPURendererThread.cpp:285,345: the "frame rendered" callbacks). fn must not call back into this library. */
+typedef void (*b2pt_host_fn)(void* user);
+int b2pt_stream_launch_host_func(b2pt_ctx* ctx, b2pt_stream stream, b2pt_host_fn fn, void* user);
 
 /* LUT "textures". Replaces OrochiTexture / OrochiTexture3D + get_device_texture()
  * (src/HIPRT-Orochi/OrochiTexture.cpp, OrochiTexture3D.cpp; src/Renderer/GPURenderer.cpp:116-171). The returned

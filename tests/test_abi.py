@@ -46,3 +46,19 @@ def test_no_cpu_fallback_without_device(b2pt):
     assert lib.b2pt_last_error_string()
     with pytest.raises(b2pt.B2ptError):
         b2pt.Context(0)
+
+
+def test_pass_names_follow_the_pass_enumeration(b2pt):
+    """b2pt_renderer_pass_ms takes a B2_PASS_* index; the binding's name table must list them in enumeration order
+    (a pass added to the enum but not to the table shifted every later name -- and zeroed bench.py's roofline)."""
+    text = (ROOT / "hiprt-path-tracer_b200" / "csrc" / "b2_frame_loop.h").read_text()
+    body = re.search(r"enum\s*\w*\s*\{([^}]*B2_PASS_COUNT[^}]*)\}", text).group(1)
+    enumerators = [e.split("=")[0].strip() for e in re.sub(r"/\*.*?\*/", "", body, flags=re.S).split(",") if e.strip()]
+    enumerators = [e for e in enumerators if e != "B2_PASS_COUNT"]
+    assert len(enumerators) == len(b2pt.PASS_NAMES)
+    assert enumerators[0] == "B2_PASS_CAMERA_RAYS" and b2pt.PASS_NAMES[0] == "CameraRays"
+    assert enumerators[-1] == "B2_PASS_MEGAKERNEL" and b2pt.PASS_NAMES[-1] == "MegaKernel"
+    key = lambda s: re.sub(r"[^a-z]", "", s.lower())
+    for enumerator, name in zip(enumerators, b2pt.PASS_NAMES):
+        stem = key(enumerator.replace("B2_PASS_", "")).replace("restirdi", "").replace("restir", "")
+        assert stem[:6] in key(name), (enumerator, name)

@@ -21,6 +21,8 @@ def render(b2pt, ctx, variant, scene, width, height, spp, bounces, envmap=None):
     if envmap:
         r.set_envmap_file(envmap)
     r.set(nb_bounces=bounces)
+    if variant.startswith("c4"):
+        r.set(restir_di_do_fused_spatiotemporal=1)  # what the oracle harness runs unless given --no-fused
     r.render(1)
     gb = r.gbuffer()
     if spp > 1:
