@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--bounces", type=int, default=3)
     ap.add_argument("--no-oracle", action="store_true")
     ap.add_argument("--fused", type=int, default=1)
+    ap.add_argument("--directional", action="store_true", help="ReSTIR DI adaptive directional spatial reuse (+ its prepass)")
     ap.add_argument("--tag", default="")
     ap.add_argument("--window", type=int, nargs=4, default=None, help="x0 y0 x1 y1: the oracles render (and parity is checked on) this crop only")
     ap.add_argument("--envmap", default=None, help="B2ENVMP1 blob")
@@ -71,6 +72,8 @@ def main():
             r.set_envmap_file(a.envmap)
         r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
         r.set(nb_bounces=a.bounces, restir_di_do_fused_spatiotemporal=a.fused)
+        if a.directional:
+            r.set(restir_di_use_adaptive_directional_spatial_reuse=1)
         if flavour == "precise":
             report["scene"] = r.scene_info()
         # counters pass (separate instrumented kernels)
@@ -111,6 +114,8 @@ def main():
         cmp_window = [a.window[0] + a.margin, a.window[1] + a.margin, a.window[2] - a.margin, a.window[3] - a.margin]
     if not a.no_oracle:
         extra = [] if a.fused else ["--no-fused"]
+        if a.directional:
+            extra.append("--directional-reuse")
         ref_meta, _ = run_oracle(ROOT / "oracle" / "_ref" / f"ref_render_{a.variant}", a, str(tmp / "ref_"), extra)
         port_meta, _ = run_oracle(ROOT / "oracle" / "_port" / "port_render", a, str(tmp / "port_"), ["--variant", a.variant, *extra])
         report["ref_oracle"] = ref_meta
