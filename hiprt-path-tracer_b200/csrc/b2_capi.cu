@@ -55,6 +55,7 @@ struct b2pt_bvh
     B2BvhDevice* descriptor = nullptr;
     b2pt_bvh_stats_t stats;
     B2BvhHost host; /* kept for b2pt_bvh_reupload */
+    bool host_pinned = false; /* page-locked on the first re-upload */
 };
 
 /* device descriptor -> depth of the tree, so a launch can size the traversal stack (b2pt_kernel_launch only sees the render data) */
@@ -196,6 +197,20 @@ int b2pt_host_free_pinned(b2pt_ctx*, void* host_ptr)
     return B2PT_OK;
 }
 
+int b2pt_host_register(b2pt_ctx*, const void* host_ptr, size_t bytes)
+{
+    if (!host_ptr || !bytes) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_CUDA(cudaHostRegister(const_cast<void*>(host_ptr), bytes, cudaHostRegisterDefault));
+    return B2PT_OK;
+}
+
+int b2pt_host_unregister(b2pt_ctx*, const void* host_ptr)
+{
+    if (host_ptr)
+        B2_CUDA(cudaHostUnregister(const_cast<void*>(host_ptr)));
+    return B2PT_OK;
+}
+
 int b2pt_stream_create(b2pt_ctx*, b2pt_stream* out_stream)
 {
     cudaStream_t s;
@@ -333,6 +348,22 @@ int b2pt_bvh_reupload(b2pt_ctx*, b2pt_bvh* bvh, b2pt_stream stream, uint64_t* ou
 {
     if (!bvh) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
     cudaStream_t s = (cudaStream_t)stream;
+    if (!bvh->host_pinned)
+    {
+        /* best effort: a range that cannot be page-locked is still copied, just through the driver's staging buffer */
+        bool ok = true;
+        if (!bvh->host.nodes.empty())
+            ok = cudaHostRegister(bvh->host.nodes.data(), bvh->host.nodes.size() * sizeof(B2Node), cudaHostRegisterDefault) == cudaSuccess;
+        if (ok && !bvh->host.tris.empty() && cudaHostRegister(bvh->host.tris.data(), bvh->host.tris.size() * sizeof(B2Tri), cudaHostRegisterDefault) != cudaSuccess)
+        {
+            ok = false;
+            if (!bvh->host.nodes.empty())
+                cudaHostUnregister(bvh->host.nodes.data());
+        }
+        if (!ok)
+            (void)cudaGetLastError();
+        bvh->host_pinned = ok;
+    }
     if (!bvh->host.nodes.empty())
         B2_CUDA(cudaMemcpyAsync(bvh->nodes, bvh->host.nodes.data(), bvh->host.nodes.size() * sizeof(B2Node), cudaMemcpyHostToDevice, s));
     if (!bvh->host.tris.empty())
@@ -356,6 +387,11 @@ int b2pt_bvh_destroy(b2pt_ctx*, b2pt_bvh* bvh)
     {
         std::lock_guard<std::mutex> lock(g_bvh_depth_mutex);
         g_bvh_depth.erase(bvh->descriptor);
+    }
+    if (bvh->host_pinned)
+    {
+        if (!bvh->host.nodes.empty()) cudaHostUnregister(bvh->host.nodes.data());
+        if (!bvh->host.tris.empty()) cudaHostUnregister(bvh->host.tris.data());
     }
     cudaFree(bvh->nodes);
     cudaFree(bvh->tris);

@@ -47,7 +47,8 @@ struct b2pt_renderer
     b2pt_event ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
     std::vector<void*> frame_allocs, scene_allocs, lut_handles, envmap_allocs;
-    struct Upload { void* device; const void* host; size_t bytes; };
+    struct Upload { void* device; const void* host; size_t bytes; bool pinned; };
+    bool scene_pin_attempted = false; /* the host copies are page-locked on the first b2pt_renderer_reupload_scene */
     std::vector<Upload> scene_uploads; /* (device, host, bytes) of every scene array, for b2pt_renderer_reupload_scene */
     b2pt_bvh* bvh = nullptr;
     b2pt_kernel* kernels[B2_PASS_COUNT] = {};
@@ -84,8 +85,21 @@ int upload(b2pt_renderer* r, std::vector<void*>& owner, const std::vector<T>& ho
     owner.push_back(d);
     *out = reinterpret_cast<T*>(d);
     if (&owner == &r->scene_allocs)
-        r->scene_uploads.push_back({ d, host.data(), host.size() * sizeof(T) });
+        r->scene_uploads.push_back({ d, host.data(), host.size() * sizeof(T), false });
     return b2pt_memcpy_h2d(r->ctx, d, host.data(), host.size() * sizeof(T), nullptr);
+}
+
+/* Releases the page locks on the host copies of the scene arrays; must run before those vectors are resized or freed. */
+void unpin_scene(b2pt_renderer* r)
+{
+    b2pt_stream_synchronize(r->ctx, r->stream);
+    for (b2pt_renderer::Upload& u : r->scene_uploads)
+        if (u.pinned)
+        {
+            b2pt_host_unregister(r->ctx, u.host);
+            u.pinned = false;
+        }
+    r->scene_pin_attempted = false;
 }
 
 void free_all(b2pt_renderer* r, std::vector<void*>& owner)
@@ -157,6 +171,7 @@ int resolve_kernels(b2pt_renderer* r)
 
 int upload_scene(b2pt_renderer* r)
 {
+    unpin_scene(r); /* normally already done by the caller, before it touched r->scene */
     free_all(r, r->scene_allocs);
     r->scene_uploads.clear();
     if (r->bvh)
@@ -332,7 +347,7 @@ int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* varia
 int b2pt_renderer_destroy(b2pt_renderer* r)
 {
     if (!r) return B2PT_OK;
-    b2pt_stream_synchronize(r->ctx, r->stream);
+    unpin_scene(r);
     free_all(r, r->frame_allocs);
     free_all(r, r->scene_allocs);
     free_all(r, r->envmap_allocs);
@@ -349,6 +364,7 @@ int b2pt_renderer_destroy(b2pt_renderer* r)
 int b2pt_renderer_set_scene_file(b2pt_renderer* r, const char* scene_blob_path)
 {
     if (!r || !scene_blob_path) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    unpin_scene(r);
     std::string err = b2scene_read(scene_blob_path, r->scene.blob);
     if (!err.empty())
     {
@@ -367,6 +383,7 @@ int b2pt_renderer_set_scene_arrays(b2pt_renderer* r, const float* positions, con
         b2_set_error("b2pt_renderer_set_scene_arrays: invalid argument");
         return B2PT_ERR_INVALID_ARGUMENT;
     }
+    unpin_scene(r);
     B2Scene& s = r->scene.blob;
     s.positions.assign(positions, positions + 3 * (size_t)vertex_count);
     if (normals) s.normals.assign(normals, normals + 3 * (size_t)vertex_count); else s.normals.assign(3 * (size_t)vertex_count, 0.0f);
@@ -386,6 +403,13 @@ int b2pt_renderer_reupload_scene(b2pt_renderer* r, uint64_t* out_bytes)
 {
     if (!r || !r->has_scene) { b2_set_error("no scene"); return B2PT_ERR_INVALID_ARGUMENT; }
     uint64_t total = 0;
+    if (!r->scene_pin_attempted)
+    {
+        /* best effort, once per scene: a range that cannot be page-locked is still copied (through the driver's staging buffer) */
+        r->scene_pin_attempted = true;
+        for (b2pt_renderer::Upload& u : r->scene_uploads)
+            u.pinned = u.bytes >= 65536 && b2pt_host_register(r->ctx, u.host, u.bytes) == B2PT_OK;
+    }
     for (const b2pt_renderer::Upload& u : r->scene_uploads)
     {
         B2_TRY(b2pt_memcpy_h2d(r->ctx, u.device, u.host, u.bytes, r->stream));

@@ -81,6 +81,11 @@ int b2pt_memcpy_d2d(b2pt_ctx* ctx, void* dst_device, const void* src_device, siz
 int b2pt_memset(b2pt_ctx* ctx, void* device_ptr, int byte_value, size_t bytes, b2pt_stream stream);
 int b2pt_host_alloc_pinned(b2pt_ctx* ctx, size_t bytes, void** out_host_ptr);
 int b2pt_host_free_pinned(b2pt_ctx* ctx, void* host_ptr);
+/* Page-locks / releases a host range the caller already owns, so that asynchronous copies from it run at full PCIe / C2C rate
+ * (the renderer does this once for the host copies of the scene arrays it re-sends every step). No reference counterpart:
+ * OrochiBuffer::upload_data copies from pageable std::vector storage (OrochiBuffer.h:263-289). */
+int b2pt_host_register(b2pt_ctx* ctx, const void* host_ptr, size_t bytes);
+int b2pt_host_unregister(b2pt_ctx* ctx, const void* host_ptr);
 
 /* Streams / events. Replaces oroStreamCreate / oroStreamSynchronize / oroEventCreate / Record / Synchronize /
  * ElapsedTime (src/Renderer/GPURenderer.cpp:66,426; src/Compiler/GPUKernel.cpp:190-201,228-240). */
