@@ -424,6 +424,30 @@ def main():
                      traversal=dict(rays_per_path=c["rays"] / (own * spp), nodes_per_ray=c["nodes"] / max(c["rays"], 1), triangles_per_ray=c["triangles"] / max(c["rays"], 1)),
                      scene=info, wall_ms_timed_region=wall_ms)
 
+    # ---- the same frame with the OTHER codegen flavour, one step, N=1 only: `value` is the fast flavour (FMA contraction + fast
+    # intrinsics; statistically equal to the reference), the parity flavour (no contraction, IEEE div/sqrt, C-library calls evaluated
+    # in double like the reference's host build) is the one that is bit-identical to it -- both numbers belong next to each other.
+    other = None
+    if world == 1 and not a.no_cpu_baseline:
+        r2 = b2pt.Renderer(ctx, W, H, w["variant"], precise=not bool(a.precise))
+        r2.set_scene_file(scene_file(w))
+        r2.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
+        r2.set(nb_bounces=w["bounces"])
+        if w["variant"] == "c4":
+            r2.set(restir_di_do_fused_spatiotemporal=int(w.get("fused", 0)))
+        if envmap_file(w):
+            r2.set_envmap_file(envmap_file(w))
+        ms2 = []
+        for i in range(3):
+            r2.reset()
+            r2.set_host_seed(42)
+            r2.render(spp, sync=False)
+            r2.synchronize()
+            ms2.append(r2.last_render_ms())
+        r2.close()
+        other = dict(flavour="fast" if a.precise else "precise", value=paths_per_step / (min(ms2[1:]) * 1e-3) / 1e6, unit="Mpaths/s", ms_per_step=min(ms2[1:]),
+                     note="one warm-up + best of two steps; the precise flavour is the one asserted bit-identical to the reference (DESIGN.md section 3)")
+
     if rank == 0:
         cpu = dict(value=None, unit="Mpaths/s", cores=0, kind="skipped", sample="--no-cpu-baseline") if a.no_cpu_baseline or world > 1 else cpu_baseline(w)
         line = dict(metric=METRIC, value=value, unit="Mpaths/s", n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=dev_ms / a.steps,
@@ -433,7 +457,7 @@ def main():
                                 l2_policy="every step re-renders from reset: G-buffer + framebuffer + aux (> 126 MB at 1080p) are rewritten between timed iterations"),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit="Mpaths/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / a.steps),
-                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, gpaths_bounce_per_s=value * (w["bounces"] + 1) / 1000.0, **extra)
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, gpaths_bounce_per_s=value * (w["bounces"] + 1) / 1000.0, other_flavour=other, **extra)
         print(json.dumps(line))
 
     r.close()
