@@ -116,8 +116,30 @@ class ClockSampler:
         self.device_index = device_index
         self.proc = None
         self.lines = []
+        self.nvml_samples = []  # (sm MHz, max sm MHz, W, reasons bitmask) every 5 ms through NVML: short timed regions (N = 8:
+        self.nvml_stop = None   # ~60 ms) end before nvidia-smi's first line arrives
+        self.nvml_thread = None
+
+    def _nvml_pump(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device_index)
+            sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.nvml_stop.is_set():
+                self.nvml_samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), float(sm_max),
+                                          pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                self.nvml_stop.wait(0.005)
+        except Exception:  # no NVML / no permission: the nvidia-smi lines remain
+            pass
 
     def start(self):
+        try:
+            self.nvml_stop = threading.Event()
+            self.nvml_thread = threading.Thread(target=self._nvml_pump, daemon=True)
+            self.nvml_thread.start()
+        except Exception:
+            self.nvml_thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -130,9 +152,23 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def _nvml_summary(self):
+        if not self.nvml_samples:
+            return None
+        bits = dict(hw_slowdown=0x8, sw_thermal_slowdown=0x20, hw_thermal_slowdown=0x40, sw_power_cap=0x4)  # nvmlClocksEventReason*
+        seen = 0
+        for s_ in self.nvml_samples:
+            seen |= s_[3]
+        return dict(sm_mhz=float(np.median([s_[0] for s_ in self.nvml_samples])), sm_max_mhz=float(max(s_[1] for s_ in self.nvml_samples)),
+                    power_w_max=float(max(s_[2] for s_ in self.nvml_samples)), samples=len(self.nvml_samples), source="nvml, 5 ms period",
+                    reasons=sorted(n for n, b in bits.items() if seen & b))
+
     def stop(self):
+        if self.nvml_thread is not None:
+            self.nvml_stop.set()
+            self.nvml_thread.join(timeout=2)
         if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+            return self._nvml_summary() or dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -154,7 +190,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+            return self._nvml_summary() or dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(sm_max)), power_w_max=float(max(power)), samples=len(sm), reasons=sorted(reasons))
 
 
