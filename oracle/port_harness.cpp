@@ -188,6 +188,52 @@ static void run_bsdf_kat(const b2pt_render_data& rd, const Args& a, int n_materi
     dump_array(a.dump, "kat_bsdf_sample", sample_out.data(), sample_out.size());
     std::printf("{\"oracle\": \"port\", \"kat\": \"bsdf\", \"materials\": %d, \"per_material\": %d}\n", n_materials, per_material);
 }
+
+/* same records as run_light_kat in ref_harness.cpp, from the product's samplers (c1 = uniform base strategy, c2 = power) */
+static void run_light_kat(const b2pt_render_data& rd, const Args& a)
+{
+    const int n = 4096;
+    std::vector<float> uniform_out((size_t)n * 12), power_out((size_t)n * 12), env_sample_out, env_eval_out;
+    auto put = [](float* out, const LightSample& s) {
+        std::memcpy(&out[0], &s.emissive_triangle_index, 4);
+        out[1] = s.point_on_light.x; out[2] = s.point_on_light.y; out[3] = s.point_on_light.z;
+        out[4] = s.light_source_normal.x; out[5] = s.light_source_normal.y; out[6] = s.light_source_normal.z;
+        out[7] = s.light_area; out[8] = s.emission.r; out[9] = s.emission.g; out[10] = s.emission.b; out[11] = s.area_measure_pdf;
+    };
+    for (int i = 0; i < n; i++)
+    {
+        Rng ra = make_rng(wang_hash(7919u * (unsigned)i + 1u) | 1u), rb = make_rng(wang_hash(7919u * (unsigned)i + 1u) | 1u);
+        put(&uniform_out[(size_t)i * 12], sample_one_emissive_triangle<B2VariantC1>(rd, ra));
+        put(&power_out[(size_t)i * 12], sample_one_emissive_triangle<B2VariantC2>(rd, rb));
+    }
+    dump_array(a.dump, "kat_light_uniform", uniform_out.data(), uniform_out.size());
+    dump_array(a.dump, "kat_light_power", power_out.data(), power_out.size());
+    if (!a.envmap.empty())
+    {
+        env_sample_out.resize((size_t)n * 7);
+        env_eval_out.resize((size_t)n * 4);
+        for (int i = 0; i < n; i++)
+        {
+            Rng rng = make_rng(wang_hash(104729u * (unsigned)i + 3u) | 1u);
+            V3 dir = v3(0.0f, 1.0f, 0.0f);
+            float pdf = 0.0f;
+            Rgb c = envmap_sample<B2VariantC2>(rd.world_settings, dir, pdf, rng);
+            float* out = &env_sample_out[(size_t)i * 7];
+            out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = pdf; out[4] = dir.x; out[5] = dir.y; out[6] = dir.z;
+
+            V3 normal, view, light;
+            unsigned int seed;
+            kat_directions(100000u + (unsigned)i, normal, view, light, seed);
+            float eval_pdf = 0.0f;
+            Rgb e = envmap_eval<B2VariantC2>(rd.world_settings, light, eval_pdf);
+            float* eo = &env_eval_out[(size_t)i * 4];
+            eo[0] = e.r; eo[1] = e.g; eo[2] = e.b; eo[3] = eval_pdf;
+        }
+        dump_array(a.dump, "kat_envmap_sample", env_sample_out.data(), env_sample_out.size());
+        dump_array(a.dump, "kat_envmap_eval", env_eval_out.data(), env_eval_out.size());
+    }
+    std::printf("{\"oracle\": \"port\", \"kat\": \"lights\", \"records\": %d, \"envmap\": %d}\n", n, a.envmap.empty() ? 0 : 1);
+}
 #endif
 
 int main(int argc, char** argv)
@@ -366,6 +412,7 @@ int main(int argc, char** argv)
     if (a.kat)
     {
         run_bsdf_kat(rd, a, (int)scene.blob.n_materials());
+        run_light_kat(rd, a);
         return 0;
     }
 #endif
