@@ -74,6 +74,16 @@ int alloc_zero(b2pt_renderer* r, std::vector<void*>& owner, size_t bytes, void**
     return b2pt_memset(r->ctx, *out, 0, bytes, nullptr);
 }
 
+/* Every reservoir of a buffer = a default-constructed ReSTIRDIReservoir (Reservoir.h:22-50): all words zero except the
+ * emissive triangle index, which is -1. The buffer is 9 SoA planes of one 32-bit word per pixel; the index is plane 6
+ * (DI_PLANE_TRIANGLE, b2_restir_di_shading.h). */
+int clear_reservoirs(b2pt_renderer* r, void* buffer, b2pt_stream stream)
+{
+    const size_t plane_bytes = r->pixels() * 4;
+    B2_TRY(b2pt_memset(r->ctx, buffer, 0, plane_bytes * 9, stream));
+    return b2pt_memset(r->ctx, static_cast<char*>(buffer) + 6 * plane_bytes, 0xFF, plane_bytes, stream);
+}
+
 template <class T>
 int upload(b2pt_renderer* r, std::vector<void*>& owner, const std::vector<T>& host, T** out)
 {
@@ -319,7 +329,10 @@ int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* varia
         B2_TRY(alloc_zero(r, r->frame_allocs, n * 4, &p)); gb[i]->geometric_normals = (uint32_t*)p;
     }
     for (int i = 0; i < 3; i++)
+    {
         B2_TRY(alloc_zero(r, r->frame_allocs, n * 36, &r->d_reservoirs[i]));
+        B2_TRY(clear_reservoirs(r, r->d_reservoirs[i], nullptr));
+    }
     if (r->loop.restir_di)
     {
         /* per-pixel radius + 64-bit direction mask of the adaptive-directional spatial reuse (ReSTIRDIRenderPass.h) */
@@ -553,7 +566,7 @@ int b2pt_renderer_reset(b2pt_renderer* r)
         B2_TRY(b2pt_ctx_make_current(r->ctx));
         for (int i = 0; i < 3; i++)
             if (r->d_reservoirs[i])
-                B2_TRY(b2pt_memset(r->ctx, r->d_reservoirs[i], 0, r->pixels() * 36, r->stream));
+                B2_TRY(clear_reservoirs(r, r->d_reservoirs[i], r->stream));
         r->loop.odd_frame = false;
         r->loop.rd.render_settings.restir_di_settings.initial_candidates.output_reservoirs = r->d_reservoirs[0];
         r->loop.rd.render_settings.restir_di_settings.restir_output_reservoirs = r->d_reservoirs[1];

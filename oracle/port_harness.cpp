@@ -395,7 +395,10 @@ int main(int argc, char** argv)
 
     std::vector<uint32_t> reservoirs[3];
     for (auto& r : reservoirs)
+    {
         r.assign(n * 9, 0);
+        std::fill(r.begin() + (size_t)DI_PLANE_TRIANGLE * n, r.begin() + (size_t)(DI_PLANE_TRIANGLE + 1) * n, 0xFFFFFFFFu); /* a default ReSTIRDISample: triangle -1 */
+    }
     loop.initial_reservoirs = reservoirs[0].data();
     loop.spatial_reservoirs_1 = reservoirs[1].data();
     loop.spatial_reservoirs_2 = reservoirs[2].data();
