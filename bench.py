@@ -1,25 +1,31 @@
 #!/usr/bin/env python3
 """bench.py -- Mpaths/s of the per-pixel path-tracing hot path on N B200s (driver contract: one JSON line on rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3s|c4s|c5|...] [--precise 0|1]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A "step" is one pass of the whole hot path (CameraRays -> [ReSTIR DI passes] -> MegaKernel, `spp` samples per pixel)
-over one full frame of the workload. The default workload is BASELINE.json configs[1]: Cornell box at 1920x1080,
-principled BSDF, 16 spp, NEE + BSDF MIS with power-proportional light sampling (variant "c2"), 8 bounces.
+A "step" is one pass of the whole hot path (CameraRays -> [ReSTIR DI passes] -> MegaKernel, `spp` samples per pixel) over one
+full frame of the workload. Default workload = the north-star target: N = 1 -> "c4s" (BASELINE.json configs[3]: the synthetic
+10M-triangle scene at 1080p, ReSTIR DI fused spatiotemporal reuse + HDR envmap alias table, RIS at later bounces, 8 bounces,
+4 frames x 1 spp per step); N > 1 -> "c5" (configs[4]: the same scene at 4K, partitioned across the GPUs). The timed kernels
+are the PRECISE flavour -- the one tests/ assert bit-identical to the reference CPURenderer; `other_flavour` carries the
+fast-math build of the same frame, `workloads` the c2 / c3s lines (configs[1], configs[2]).
 
  value      : W*H*spp*steps / device time (CUDA events on the renderer's stream, max over ranks), scene resident in HBM
- e2e        : same metric through the C ABI with HOST buffers: per step the scene arrays are re-uploaded from pinned
-              host memory (geometry, materials, BVH blob: what GPURenderer::set_scene hands to the device layer), the
-              frame is rendered, and the fp32 framebuffer is read back to the host -- all inside the timed region
+ e2e        : same metric through the C ABI with HOST buffers: per step the scene arrays + BVH blob are re-uploaded from pinned
+              host memory (what GPURenderer::set_scene hands to the device layer), the frame is rendered, and the fp32
+              framebuffer is read back to the host -- all inside the timed region (wall clock, max over ranks)
  roofline   : MegaKernel's algorithmic bytes (B_path from measured traversal steps) / its CUDA-event time
- cpu_baseline: the reference's own CPU path (oracle/_ref, compiled from /root/reference) on this box's host cores, on
-              a bounded pixel window of the same workload
+ cpu_baseline: the reference's own CPU path (oracle/_ref, compiled from /root/reference) on this box's host cores, on a bounded
+              pixel window of the same workload, several renders in ONE process (one octree build)
+ --impl reference: the same thing as the driver's reference arm: K timed + W warm-up renders of the window in one process
 
-Multi-GPU (N > 1): the frame is partitioned into interleaved 16-row pixel bands (rank = band % N), scene replicated,
-no data-path collective inside a sample (ReSTIR DI variants all-gather the reservoir planes a reuse pass reads, once
-per frame); the framebuffer bands are all-gathered with NCCL at the end of every step (inside the timed region: the
-step's device time = the renderer's CUDA events + the all-gather's). Total work is fixed => "scaling": "strong".
+Multi-GPU (N > 1): the frame is partitioned into interleaved pixel-row bands (rank = band % N), scene replicated. No
+data-path collective inside a sample except for ReSTIR DI, whose reuse passes read neighbouring pixels: the reservoir rows next
+to a rank's bands (halo) are exchanged with NCCL send/recv issued from C on the renderer's stream, and CameraRays also covers
+the halo rows. The framebuffer bands are all-gathered (ncclAllGather from C, same stream) at the end of every step, inside the
+timed region. Total work is fixed => "scaling": "strong". Rank 0 also renders the same frame alone once, outside the timed
+region: `single_gpu_same_workload` (the efficiency denominator on the SAME workload) and `multi_gpu_bit_identical`.
 """
 import argparse
 import json
@@ -204,23 +210,48 @@ def measured_peak_gbs():
     return 6650.0, "fallback"
 
 
-def pick_workload(name, b2pt, ctx):
-    """The workload BASELINE.json's metric is quoted on is c2; fall back (loudly) only if that variant is not built."""
-    if name:
-        return name, WORKLOADS[name]
-    order = ["c2", "c1"]
-    for n in order:
-        w = WORKLOADS[n]
-        try:
-            r = b2pt.Renderer(ctx, 16, 16, w["variant"], precise=False)
-            r.set_scene_file(scene_file(w))
-            r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
-            r.render(1)
-            r.close()
-            return n, w
-        except b2pt.B2ptError as e:
-            print(f"bench: workload {n} unavailable ({e})", file=sys.stderr)
-    raise SystemExit("bench: no workload can run")
+def default_workload(n_gpus):
+    """The north-star target workloads (BASELINE.json configs[3] on one GPU, configs[4] across GPUs)."""
+    return "c4s" if n_gpus <= 1 else "c5"
+
+
+def workload_config(w):
+    """`config` of the JSON line: names the workload only, identical for both arms."""
+    return dict(workload=w["desc"], variant=w["variant"], width=w["width"], height=w["height"], spp=w["spp"], bounces=w["bounces"],
+                scene=w["scene"], envmap=w.get("envmap"))
+
+
+def cpu_window(w):
+    """Bounded sample of the workload the CPU arm renders per step: the whole frame at 1 spp on the Cornell scenes (~0.6 s on 16
+    cores), a centred 256x144 window at 1 spp on the 10M-triangle scene (~2 s)."""
+    big = w["scene"].startswith("synthetic:")
+    win_w, win_h = (min(w["width"], 256), min(w["height"], 144)) if big else (w["width"], w["height"])
+    x0, y0 = (w["width"] - win_w) // 2, (w["height"] - win_h) // 2
+    return x0, y0, win_w, win_h
+
+
+def run_reference(w, repeats, cores):
+    """Renders the workload's CPU window `repeats` times in ONE process of oracle/_ref/ref_extras_<variant> (the reference's own
+    kernels + octree, compiled from /root/reference; one scene load + BVH build). Returns (seconds per repeat, kind, sample)."""
+    exe = ROOT / "oracle" / "_ref" / f"ref_extras_{w['variant']}"
+    if not exe.exists() and (Path("/root/reference") / "src").exists():
+        entry.build_oracles()
+    if not exe.exists():
+        return None, "unavailable", "oracle/_ref binaries not built"
+    x0, y0, win_w, win_h = cpu_window(w)
+    out = subprocess.run([str(exe), "--scene", str(scene_file(w)), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
+                          "--width", str(w["width"]), "--height", str(w["height"]), "--spp", "1", "--bounces", str(w["bounces"]),
+                          "--threads", str(cores), "--window", str(x0), str(y0), str(x0 + win_w), str(y0 + win_h), "--repeat", str(repeats), *oracle_args(w)],
+                         check=True, capture_output=True, text=True)
+    seconds = None
+    for line in out.stdout.splitlines():
+        if line.startswith('{"render_seconds_per_repeat"'):
+            seconds = json.loads(line)["render_seconds_per_repeat"]
+    if not seconds:
+        raise RuntimeError("reference oracle printed no timings: " + out.stdout[-500:] + out.stderr[-500:])
+    sample = (f"{win_w}x{win_h} {'centre window' if (win_w, win_h) != (w['width'], w['height']) else 'full frame'} of the {w['width']}x{w['height']} frame, "
+              f"1 spp per step, {w['bounces']} bounces, {repeats} renders in one process")
+    return seconds, "reference", sample
 
 
 def reference_arm(a):
@@ -228,67 +259,63 @@ def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    name = a.workload or "c2"
+    name = a.workload or default_workload(a.gpus)
     w = dict(WORKLOADS[name])
-    exe = ROOT / "oracle" / "_ref" / f"ref_render_{w['variant']}"
-    if not exe.exists():
-        entry.build_oracles()
     entry.ensure_data()
     cores = host_cores()
-    # bounded sample: a centred window of the frame, 1 spp per step, sized for ~1-3 s per step
-    big = w["scene"].startswith("synthetic:")  # the reference's octree build over 10M triangles takes ~12 s per run
-    win_w, win_h = (min(w["width"], 160), min(w["height"], 90)) if big else (min(w["width"], 480), min(w["height"], 270))
-    x0, y0 = (w["width"] - win_w) // 2, (w["height"] - win_h) // 2
-    spp = 1
-    times = []
-    for i in range(a.warmup + a.steps):
-        out = subprocess.run([str(exe), "--scene", str(scene_file(w)), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
-                              "--width", str(w["width"]), "--height", str(w["height"]), "--spp", str(spp), "--bounces", str(w["bounces"]),
-                              "--threads", str(cores), "--window", str(x0), str(y0), str(x0 + win_w), str(y0 + win_h), *oracle_args(w)],
-                             check=True, capture_output=True, text=True)
-        meta = json.loads(out.stdout.strip().splitlines()[-1])
-        if i >= a.warmup:
-            times.append(meta["render_seconds"])
-    total = sum(times)
-    value = win_w * win_h * spp * len(times) / total / 1e6
-    sample = f"{win_w}x{win_h} centre window of the {w['width']}x{w['height']} frame, {spp} spp per step, {w['bounces']} bounces"
-    line = dict(metric=METRIC, value=value, unit="Mpaths/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=1e3 * total / len(times),
+    seconds, kind, sample = run_reference(w, a.warmup + a.steps, cores)
+    if seconds is None:
+        print(json.dumps(dict(impl="reference", unavailable=sample)))
+        return
+    timed = seconds[a.warmup:]
+    _, _, win_w, win_h = cpu_window(w)
+    total = sum(timed)
+    value = win_w * win_h * len(timed) / total / 1e6
+    line = dict(metric=METRIC, value=value, unit="Mpaths/s", n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=1e3 * total / len(timed),
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload=w["desc"], variant=w["variant"], width=w["width"], height=w["height"], spp=w["spp"], bounces=w["bounces"]),
-                cpu_baseline=dict(value=value, unit="Mpaths/s", cores=cores, kind="reference", sample=sample),
+                config=workload_config(w),
+                cpu_baseline=dict(value=value, unit="Mpaths/s", cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="Mpaths/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
 
-def cpu_baseline(w, seconds_budget=20.0):
-    exe = ROOT / "oracle" / "_ref" / f"ref_render_{w['variant']}"
-    kind = "reference"
-    extra = []
-    if not exe.exists():
-        exe = ROOT / "oracle" / "_port" / "port_render"
-        kind = "port"
-        extra = ["--variant", w["variant"]]
-    if not exe.exists():
-        return dict(value=None, unit="Mpaths/s", cores=0, kind="unavailable", sample="oracle binaries not built")
+def cpu_baseline(w, repeats=6):
     cores = host_cores()
-    big = w["scene"].startswith("synthetic:")
-    win_w, win_h = (min(w["width"], 160), min(w["height"], 90)) if big else (min(w["width"], 480), min(w["height"], 270))
-    x0, y0 = (w["width"] - win_w) // 2, (w["height"] - win_h) // 2
-    spp, total_s, total_paths = (2 if big else 1), 0.0, 0
-    t_start = time.time()
-    while True:
-        out = subprocess.run([str(exe), *extra, "--scene", str(scene_file(w)), "--luts", str(ROOT / "data" / "brdf_luts.b2luts"),
-                              "--width", str(w["width"]), "--height", str(w["height"]), "--spp", str(spp), "--bounces", str(w["bounces"]),
-                              "--threads", str(cores), "--window", str(x0), str(y0), str(x0 + win_w), str(y0 + win_h), *oracle_args(w)],
-                             check=True, capture_output=True, text=True)
-        meta = json.loads(out.stdout.strip().splitlines()[-1])
-        total_s += meta["render_seconds"]
-        total_paths += win_w * win_h * spp
-        if big or time.time() - t_start > seconds_budget * 0.5 or total_s > seconds_budget:
-            break
-        spp = min(spp * 2, 16)
-    return dict(value=total_paths / total_s / 1e6, unit="Mpaths/s", cores=cores, kind=kind,
-                sample=f"{win_w}x{win_h} centre window of the {w['width']}x{w['height']} frame, {total_paths // (win_w * win_h)} spp total, {w['bounces']} bounces, {total_s:.1f} s of CPU render time")
+    seconds, kind, sample = run_reference(w, repeats + 1, cores)
+    if seconds is None:
+        return dict(value=None, unit="Mpaths/s", cores=0, kind=kind, sample=sample)
+    _, _, win_w, win_h = cpu_window(w)
+    timed = seconds[1:]
+    return dict(value=win_w * win_h * len(timed) / sum(timed) / 1e6, unit="Mpaths/s", cores=cores, kind=kind,
+                sample=sample + f" (first one untimed), {sum(timed):.1f} s of CPU render time")
+
+
+def make_renderer(b2pt, ctx, w, precise):
+    r = b2pt.Renderer(ctx, w["width"], w["height"], w["variant"], precise=precise)
+    r.set_scene_file(scene_file(w))
+    r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
+    r.set(nb_bounces=w["bounces"])
+    if w["variant"].startswith("c4"):
+        r.set(restir_di_do_fused_spatiotemporal=int(w.get("fused", 0)))
+    if envmap_file(w):
+        r.set_envmap_file(envmap_file(w))
+    return r
+
+
+def quick_line(b2pt, ctx, w, precise, steps=2):
+    """One warm-up + `steps` timed steps of a workload on this GPU, scene resident: a sub-line of the main JSON line."""
+    r = make_renderer(b2pt, ctx, w, precise)
+    ms = []
+    for i in range(steps + 1):
+        r.reset()
+        r.set_host_seed(42)
+        r.render(w["spp"], sync=False)
+        r.synchronize()
+        ms.append(r.last_render_ms())
+    r.close()
+    best = min(ms[1:])
+    return dict(value=w["width"] * w["height"] * w["spp"] / (best * 1e-3) / 1e6, unit="Mpaths/s", ms_per_step=best, flavour="precise" if precise else "fast",
+                config=workload_config(w), note=f"one warm-up + best of {steps} steps, scene resident")
 
 
 def main():
@@ -298,8 +325,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=None, choices=[None, *WORKLOADS.keys()])
-    ap.add_argument("--precise", type=int, default=0, help="1 = time the parity flavour instead of the fast flavour")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precise", type=int, default=1, help="1 (default) = the parity flavour, bit-identical to the reference; 0 = the fast-math A/B flavour")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline, the other-flavour line and the c2 / c3s sub-lines")
     ap.add_argument("--spp", type=int, default=None)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
@@ -323,24 +350,18 @@ def main():
     entry.ensure_data()
     b2pt = entry.load_b2pt()
     ctx = b2pt.Context(local_rank)
-    name, w = pick_workload(a.workload, b2pt, ctx)
-    w = dict(w)
+    name = a.workload or default_workload(world)
+    w = dict(WORKLOADS[name])
     if a.spp:
         w["spp"] = a.spp
     W, H, spp = w["width"], w["height"], w["spp"]
+    precise = bool(a.precise)
 
-    r = b2pt.Renderer(ctx, W, H, w["variant"], precise=bool(a.precise))
     if rank == 0:
         scene_file(w), envmap_file(w)   # generate once, before the other ranks look for the files
     if world > 1:
         dist.barrier()
-    r.set_scene_file(scene_file(w))
-    r.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
-    r.set(nb_bounces=w["bounces"])
-    if w["variant"] == "c4":
-        r.set(restir_di_do_fused_spatiotemporal=int(w.get("fused", 0)))
-    if envmap_file(w):
-        r.set_envmap_file(envmap_file(w))
+    r = make_renderer(b2pt, ctx, w, precise)
     if world > 1:
         r.set_partition(rank, world, torch, dist)
     info = r.scene_info()
@@ -357,8 +378,8 @@ def main():
         torch.cuda.synchronize()
 
     def step(e2e):
-        """Returns the device milliseconds of the step: the renderer's CUDA events on its stream (+ the all-gather's
-        events on torch's stream when N > 1; the two regions do not overlap)."""
+        """Returns the device milliseconds of the step: the renderer's CUDA events on its stream (they bracket the framebuffer
+        all-gather too when it is issued from C on that stream; a torch-side gather adds its own events)."""
         r.reset()
         r.set_host_seed(42)
         if e2e:
@@ -393,11 +414,12 @@ def main():
     dev_ms = float(t.item())
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------------------
+    e2e_steps = a.steps if a.steps <= 5 else max(5, a.steps // 2)   # a bounded share of the run on the heavy workloads
     for _ in range(2):
         step(True)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
+    for _ in range(e2e_steps):
         step(True)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
@@ -410,7 +432,7 @@ def main():
 
     paths_per_step = W * H * spp
     value = paths_per_step * a.steps / (dev_ms * 1e-3) / 1e6
-    e2e_value = paths_per_step * a.steps / (e2e_ms * 1e-3) / 1e6
+    e2e_value = paths_per_step * e2e_steps / (e2e_ms * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (MegaKernel), outside the timed region. Every rank renders (the ReSTIR DI variants
     # run collectives inside render()); rank 0 reports. ---------------------------------------------------------------
@@ -432,71 +454,100 @@ def main():
     r.render(spp)
     c = ctx.counters_read()
     r.set_counters(False)
+    # whole-job ray / node / triangle counts: every rank counted its own pixels
+    c_all = torch.tensor([c["rays"], c["nodes"], c["triangles"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(c_all, op=dist.ReduceOp.SUM)
+    rays_all, nodes_all, tris_all = (float(v) for v in c_all.tolist())
     if rank == 0:
         if n_launch.get("MegaKernel", 0) <= 0 or pass_ms.get("MegaKernel", 0.0) <= 0.0:
             raise RuntimeError(f"no MegaKernel launch was timed by the profiled render (passes seen: {sorted(pass_ms)}): the roofline would be empty")
         mk_ms = pass_ms["MegaKernel"] / n_launch["MegaKernel"]
         own = r.owned_pixels() if world > 1 else W * H
-        rays = c["rays"] / spp   # per launch (one launch = one sample of every pixel)
+        rays = c["rays"] / spp   # rank 0's, per launch (one launch = one sample of every owned pixel)
         # B_path: traversal bytes + per-vertex hit reconstruction + light candidates + per-pixel G-buffer / framebuffer traffic.
-        # CameraRays' primary rays are part of `rays` but belong to its own launch: subtract one ray per pixel.
-        mk_rays = max(rays - own, 0.0)
+        # Rays of the other passes (CameraRays' primary rays, the ReSTIR passes' candidate / shadow rays) are part of `rays` but belong
+        # to their own launches: one primary ray per rendered CameraRays pixel is subtracted; the rest is attributed pro rata.
+        camera_pixels = own if not (world > 1 and w["variant"].startswith("c4")) else r.camera_rays_pixels()
+        mk_rays = max(rays - camera_pixels, 0.0)
         frac_mk = mk_rays / max(rays, 1.0)
         trav_bytes = frac_mk * (c["nodes"] * S_NODE + c["triangles"] * S_TRI) / spp
-        vertices = c.get("vertices", 0) / spp if c.get("vertices") else mk_rays / 3.0
-        lights = c.get("light_samples", 0) / spp if c.get("light_samples") else vertices
+        vertices = mk_rays / 3.0
+        lights = vertices * (4.0 if w["variant"] in ("c3", "c4", "c4p") else 1.0)   # RIS: 4 light candidates per vertex
         algo_bytes = trav_bytes + vertices * S_HIT + lights * S_LIGHT + own * S_PX
         peak, which = measured_peak_gbs()
         achieved = algo_bytes / (mk_ms * 1e-3) / 1e9 if mk_ms > 0 else 0.0
         roofline = dict(bound="hbm", kernel="MegaKernel", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
                         peak_source=which, algorithmic_bytes_per_launch=algo_bytes, launch_ms=mk_ms,
-                        note=("10M-triangle scene: 0.6 GB of nodes + triangles, random-sector HBM/L2 gathers bind" if w["scene"].startswith("synthetic:")
+                        note=("10M-triangle scene: 0.72 GB of nodes + triangles, random-sector HBM/L2 gathers (dependent node fetches) bind" if w["scene"].startswith("synthetic:")
                               else "Cornell (BVH+triangles < 1 MB) is L2-resident: issue rate, not HBM, binds; see DESIGN.md"))
         # dram__bytes_read.sum + dram__bytes_write.sum of one MegaKernel launch from the committed `ncu --set full` capture
         traffic_file = ROOT / "profiles" / "ncu_traffic.json"
         if traffic_file.exists():
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get(name, {}).get("dram_bytes_per_launch")
-        extra = dict(pass_ms_per_step=pass_ms, mrays_per_s=c["rays"] / (sum(pass_ms.values()) * 1e-3) / 1e6 if pass_ms else None,
-                     traversal=dict(rays_per_path=c["rays"] / (own * spp), nodes_per_ray=c["nodes"] / max(c["rays"], 1), triangles_per_ray=c["triangles"] / max(c["rays"], 1)),
+            key = {"c5": "c4s"}.get(name, name) + ("" if precise else "_fast")
+            roofline["traffic"] = json.loads(traffic_file.read_text()).get(key, {}).get("dram_bytes_per_launch")
+        total_pass_ms = sum(pass_ms.values())
+        extra = dict(pass_ms_per_step=pass_ms, mrays_per_s=rays_all / (total_pass_ms * 1e-3) / 1e6 if total_pass_ms else None,
+                     traversal=dict(rays_per_path=rays_all / (W * H * spp), nodes_per_ray=nodes_all / max(rays_all, 1), triangles_per_ray=tris_all / max(rays_all, 1)),
                      scene=info, wall_ms_timed_region=wall_ms)
 
-    # ---- the same frame with the OTHER codegen flavour, one step, N=1 only: `value` is the fast flavour (FMA contraction + fast
-    # intrinsics; statistically equal to the reference), the parity flavour (no contraction, IEEE div/sqrt, C-library calls evaluated
-    # in double like the reference's host build) is the one that is bit-identical to it -- both numbers belong next to each other.
+    # ---- N > 1: rank 0 renders the SAME frame alone (unpartitioned), outside the timed region: the single-GPU rate on this very
+    # workload and the bit-identity of the partitioned render (every rank's gathered framebuffer vs rank 0's own). ---------------
+    single = None
+    identical = None
+    if world > 1:
+        r.reset()
+        r.set_host_seed(42)
+        r.render(spp, sync=False)
+        gather()
+        r.synchronize()
+        multi_fb = r.framebuffer().copy()
+        if rank == 0:
+            r.set_partition(0, 1, torch, dist)
+            ms1 = []
+            for i in range(2):
+                r.reset()
+                r.set_host_seed(42)
+                r.render(spp, sync=False)
+                r.synchronize()
+                ms1.append(r.last_render_ms())
+            single_fb = r.framebuffer()
+            single = dict(value=paths_per_step / (ms1[-1] * 1e-3) / 1e6, unit="Mpaths/s", ms_per_step=ms1[-1], note="rank 0 alone, whole frame, second of two steps")
+            ref_fb = torch.from_numpy(single_fb.view(np.int32).copy()).cuda()
+        else:
+            ref_fb = torch.empty((H, W, 3), dtype=torch.int32, device="cuda")
+        dist.broadcast(ref_fb, src=0)
+        same = torch.tensor([int(bool((torch.from_numpy(multi_fb.view(np.int32).copy()).cuda() == ref_fb).all().item()))], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        identical = bool(same.item())
+
+    # ---- sub-lines, N = 1 only: the other codegen flavour on this workload, and the lighter BASELINE configs ----------------------
     other = None
+    sublines = {}
     if world == 1 and not a.no_cpu_baseline:
-        r2 = b2pt.Renderer(ctx, W, H, w["variant"], precise=not bool(a.precise))
-        r2.set_scene_file(scene_file(w))
-        r2.set_luts_file(ROOT / "data" / "brdf_luts.b2luts")
-        r2.set(nb_bounces=w["bounces"])
-        if w["variant"] == "c4":
-            r2.set(restir_di_do_fused_spatiotemporal=int(w.get("fused", 0)))
-        if envmap_file(w):
-            r2.set_envmap_file(envmap_file(w))
-        ms2 = []
-        for i in range(3):
-            r2.reset()
-            r2.set_host_seed(42)
-            r2.render(spp, sync=False)
-            r2.synchronize()
-            ms2.append(r2.last_render_ms())
-        r2.close()
-        other = dict(flavour="fast" if a.precise else "precise", value=paths_per_step / (min(ms2[1:]) * 1e-3) / 1e6, unit="Mpaths/s", ms_per_step=min(ms2[1:]),
-                     note="one warm-up + best of two steps; the precise flavour is the one asserted bit-identical to the reference (DESIGN.md section 3)")
+        r.close()
+        r = None
+        other = quick_line(b2pt, ctx, w, not precise)
+        for sub in ("c2", "c3s"):
+            if sub != name:
+                sublines[sub] = quick_line(b2pt, ctx, dict(WORKLOADS[sub]), precise, steps=2)
 
     if rank == 0:
-        cpu = dict(value=None, unit="Mpaths/s", cores=0, kind="skipped", sample="--no-cpu-baseline") if a.no_cpu_baseline or world > 1 else cpu_baseline(w)
+        cpu = dict(value=None, unit="Mpaths/s", cores=0, kind="skipped", sample="--no-cpu-baseline / N > 1") if a.no_cpu_baseline or world > 1 else cpu_baseline(w)
         line = dict(metric=METRIC, value=value, unit="Mpaths/s", n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=dev_ms / a.steps,
                     higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=w["desc"], variant=w["variant"], width=W, height=H, spp=spp, bounces=w["bounces"],
-                                flavour="precise" if a.precise else "fast", partition="interleaved 16-row bands, scene replicated" if world > 1 else "single GPU",
-                                l2_policy="every step re-renders from reset: G-buffer + framebuffer + aux (> 126 MB at 1080p) are rewritten between timed iterations"),
+                    config=workload_config(w),
+                    impl_detail=dict(flavour="precise (bit-identical to the reference CPURenderer, tests/)" if precise else "fast (--use_fast_math A/B build)",
+                                     partition=r.partition_description() if world > 1 else "single GPU",
+                                     l2_policy="every step re-renders from reset: G-buffer + framebuffer + reservoirs (> 126 MB) are rewritten between timed iterations; the scene (0.72 GB BVH) exceeds L2"),
                     clocks=clocks,
-                    e2e=dict(value=e2e_value, unit="Mpaths/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / a.steps),
-                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, gpaths_bounce_per_s=value * (w["bounces"] + 1) / 1000.0, other_flavour=other, **extra)
+                    e2e=dict(value=e2e_value, unit="Mpaths/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps),
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, gpaths_bounce_per_s=value * (w["bounces"] + 1) / 1000.0,
+                    other_flavour=other, workloads=sublines, single_gpu_same_workload=single, multi_gpu_bit_identical=identical, **extra)
         print(json.dumps(line))
 
-    r.close()
+    if r is not None:
+        r.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -10,6 +10,8 @@ from pathlib import Path
 
 import numpy as np
 
+from . import partition
+
 PKG_DIR = Path(__file__).resolve().parent.parent
 LIB_PATH = PKG_DIR / "libb2pt.so"
 REPO_ROOT = PKG_DIR.parent
@@ -255,6 +257,13 @@ class Renderer:
     def owned_pixels(self):
         from . import partition
         return len(partition.owned_rows(self.height, getattr(self, "rank", 0), getattr(self, "world", 1))) * self.width
+
+    def camera_rays_pixels(self):
+        """Pixels CameraRays covers on this rank (ReSTIR DI partitions also fill the halo rows its reuse passes read)."""
+        return self.width * self.height
+
+    def partition_description(self):
+        return f"interleaved {partition.BAND_ROWS}-row bands, scene replicated" if getattr(self, "world", 1) > 1 else "single GPU"
 
     def framebuffer_device_pointer(self):
         return _PTR.from_address(self._rd + FRAMEBUFFER_POINTER_OFFSET).value

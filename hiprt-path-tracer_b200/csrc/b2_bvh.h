@@ -124,6 +124,28 @@ B2_HD bool b2_intersect_triangle(V3 org, V3 dir, V3 a, V3 edge1, V3 edge2, float
     return false;
 }
 
+/* The slab test only culls: it is conservative by construction (boxes widened by 8-bit quantisation and by the 0.5e-6 margins
+ * below), so its arithmetic need not be the reference's -- one FMA per plane and an approximate reciprocal direction in both
+ * codegen flavours. The triangle test, which decides t / u / v / prim, stays exact. */
+B2_HD float b2_slab_fma(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return a * b + c;
+#endif
+}
+B2_HD float b2_slab_rcp(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
+
 B2_HD uint32_t b2_bfind(uint32_t x)
 {
 #if defined(__CUDA_ARCH__)
@@ -197,9 +219,9 @@ B2_HD void b2_traverse_begin(B2Traversal& t, bool any_hit, V3 org, V3 dir, float
     t.best.ng = v3(0.0f);
     /* direction reciprocal, guarded against 0 (the slab test may be conservative; the triangle test is exact) */
     const float tiny = 1.0e-30f;
-    t.idx = 1.0f / (fabsf(dir.x) > tiny ? dir.x : (dir.x < 0.0f ? -tiny : tiny));
-    t.idy = 1.0f / (fabsf(dir.y) > tiny ? dir.y : (dir.y < 0.0f ? -tiny : tiny));
-    t.idz = 1.0f / (fabsf(dir.z) > tiny ? dir.z : (dir.z < 0.0f ? -tiny : tiny));
+    t.idx = b2_slab_rcp(fabsf(dir.x) > tiny ? dir.x : (dir.x < 0.0f ? -tiny : tiny));
+    t.idy = b2_slab_rcp(fabsf(dir.y) > tiny ? dir.y : (dir.y < 0.0f ? -tiny : tiny));
+    t.idz = b2_slab_rcp(fabsf(dir.z) > tiny ? dir.z : (dir.z < 0.0f ? -tiny : tiny));
     const uint32_t octant = (dir.x < 0.0f ? 4u : 0u) | (dir.y < 0.0f ? 2u : 0u) | (dir.z < 0.0f ? 1u : 0u);
     t.oct_inv = 7u - octant;
     /* The stack is addressed through a moving pointer (`top`) plus a depth counter rather than stack[sp * stride]:
@@ -293,9 +315,9 @@ B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_st
             /* branch-free over the 8 slots: an empty slot has meta = 0 and contributes (0 >> 5) << x = no bit */
             const uint32_t meta = ((c < 4 ? meta_lo : meta_hi) >> ((c & 3) * 8)) & 0xFFu;
             const int w = c >> 2, sh = (c & 3) * 8;
-            const float tx0 = (float)((near_x[w] >> sh) & 0xFFu) * sx + bx, tx1 = (float)((far_x[w] >> sh) & 0xFFu) * sx + bx;
-            const float ty0 = (float)((near_y[w] >> sh) & 0xFFu) * sy + by, ty1 = (float)((far_y[w] >> sh) & 0xFFu) * sy + by;
-            const float tz0 = (float)((near_z[w] >> sh) & 0xFFu) * sz + bz, tz1 = (float)((far_z[w] >> sh) & 0xFFu) * sz + bz;
+            const float tx0 = b2_slab_fma((float)((near_x[w] >> sh) & 0xFFu), sx, bx), tx1 = b2_slab_fma((float)((far_x[w] >> sh) & 0xFFu), sx, bx);
+            const float ty0 = b2_slab_fma((float)((near_y[w] >> sh) & 0xFFu), sy, by), ty1 = b2_slab_fma((float)((far_y[w] >> sh) & 0xFFu), sy, by);
+            const float tz0 = b2_slab_fma((float)((near_z[w] >> sh) & 0xFFu), sz, bz), tz1 = b2_slab_fma((float)((far_z[w] >> sh) & 0xFFu), sz, bz);
             /* widened by a few ulps so fp32 rounding in the slab arithmetic can never cull a box the exact
              * triangle test would hit */
             const float t_enter = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, 0.0f)) * 0.9999995f;

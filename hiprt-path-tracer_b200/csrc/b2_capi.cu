@@ -48,6 +48,15 @@ struct b2pt_ctx
     cudaDeviceProp props;
 };
 
+/* every entry that allocates, copies or launches runs on the context's own device, whichever device another context of the
+ * process made current last */
+#define B2_SELECT_DEVICE(ctx)                     \
+    do                                            \
+    {                                             \
+        if (ctx)                                  \
+            B2_CUDA(cudaSetDevice((ctx)->device)); \
+    } while (0)
+
 struct b2pt_bvh
 {
     B2Node* nodes = nullptr;
@@ -61,6 +70,14 @@ struct b2pt_bvh
 /* device descriptor -> depth of the tree, so a launch can size the traversal stack (b2pt_kernel_launch only sees the render data) */
 static std::mutex g_bvh_depth_mutex;
 static std::unordered_map<const void*, int> g_bvh_depth;
+
+/* kernel units (objects of b2_kernels.cu) register here from their static initialisers */
+static std::vector<B2KernelUnit>& kernel_units()
+{
+    static std::vector<B2KernelUnit> units;
+    return units;
+}
+void b2_register_kernel_unit(const B2KernelUnit* unit) { kernel_units().push_back(*unit); }
 
 struct b2pt_kernel
 {
@@ -136,6 +153,7 @@ int b2pt_ctx_device_props(b2pt_ctx* ctx, b2pt_device_props_t* out)
 
 int b2pt_malloc(b2pt_ctx* ctx, size_t bytes, void** out_device_ptr)
 {
+    B2_SELECT_DEVICE(ctx);
     if (!ctx || !out_device_ptr) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
     *out_device_ptr = nullptr;
     if (bytes == 0)
@@ -144,75 +162,85 @@ int b2pt_malloc(b2pt_ctx* ctx, size_t bytes, void** out_device_ptr)
     return B2PT_OK;
 }
 
-int b2pt_free(b2pt_ctx*, void* device_ptr)
+int b2pt_free(b2pt_ctx* ctx, void* device_ptr)
 {
+    B2_SELECT_DEVICE(ctx);
     if (device_ptr)
         B2_CUDA(cudaFree(device_ptr));
     return B2PT_OK;
 }
 
-int b2pt_memcpy_h2d(b2pt_ctx*, void* dst, const void* src, size_t bytes, b2pt_stream stream)
+int b2pt_memcpy_h2d(b2pt_ctx* ctx, void* dst, const void* src, size_t bytes, b2pt_stream stream)
 {
+    B2_SELECT_DEVICE(ctx);
     if (bytes == 0) return B2PT_OK;
     if (stream) B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     else B2_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
     return B2PT_OK;
 }
 
-int b2pt_memcpy_d2h(b2pt_ctx*, void* dst, const void* src, size_t bytes, b2pt_stream stream)
+int b2pt_memcpy_d2h(b2pt_ctx* ctx, void* dst, const void* src, size_t bytes, b2pt_stream stream)
 {
+    B2_SELECT_DEVICE(ctx);
     if (bytes == 0) return B2PT_OK;
     if (stream) B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     else B2_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     return B2PT_OK;
 }
 
-int b2pt_memcpy_d2d(b2pt_ctx*, void* dst, const void* src, size_t bytes, b2pt_stream stream)
+int b2pt_memcpy_d2d(b2pt_ctx* ctx, void* dst, const void* src, size_t bytes, b2pt_stream stream)
 {
+    B2_SELECT_DEVICE(ctx);
     if (bytes == 0) return B2PT_OK;
     if (stream) B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     else B2_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
     return B2PT_OK;
 }
 
-int b2pt_memset(b2pt_ctx*, void* device_ptr, int byte_value, size_t bytes, b2pt_stream stream)
+int b2pt_memset(b2pt_ctx* ctx, void* device_ptr, int byte_value, size_t bytes, b2pt_stream stream)
 {
+    B2_SELECT_DEVICE(ctx);
     if (bytes == 0) return B2PT_OK;
     if (stream) B2_CUDA(cudaMemsetAsync(device_ptr, byte_value, bytes, (cudaStream_t)stream));
     else B2_CUDA(cudaMemset(device_ptr, byte_value, bytes));
     return B2PT_OK;
 }
 
-int b2pt_host_alloc_pinned(b2pt_ctx*, size_t bytes, void** out_host_ptr)
+int b2pt_host_alloc_pinned(b2pt_ctx* ctx, size_t bytes, void** out_host_ptr)
 {
+    B2_SELECT_DEVICE(ctx);
     if (!out_host_ptr) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
     B2_CUDA(cudaMallocHost(out_host_ptr, bytes));
     return B2PT_OK;
 }
 
-int b2pt_host_free_pinned(b2pt_ctx*, void* host_ptr)
+int b2pt_host_free_pinned(b2pt_ctx* ctx, void* host_ptr)
 {
+    B2_SELECT_DEVICE(ctx);
     if (host_ptr)
         B2_CUDA(cudaFreeHost(host_ptr));
     return B2PT_OK;
 }
 
-int b2pt_host_register(b2pt_ctx*, const void* host_ptr, size_t bytes)
+int b2pt_host_register(b2pt_ctx* ctx, const void* host_ptr, size_t bytes)
 {
+    B2_SELECT_DEVICE(ctx);
     if (!host_ptr || !bytes) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
     B2_CUDA(cudaHostRegister(const_cast<void*>(host_ptr), bytes, cudaHostRegisterDefault));
     return B2PT_OK;
 }
 
-int b2pt_host_unregister(b2pt_ctx*, const void* host_ptr)
+int b2pt_host_unregister(b2pt_ctx* ctx, const void* host_ptr)
 {
+    B2_SELECT_DEVICE(ctx);
     if (host_ptr)
         B2_CUDA(cudaHostUnregister(const_cast<void*>(host_ptr)));
     return B2PT_OK;
 }
 
-int b2pt_stream_create(b2pt_ctx*, b2pt_stream* out_stream)
+int b2pt_stream_create(b2pt_ctx* ctx, b2pt_stream* out_stream)
 {
+    B2_SELECT_DEVICE(ctx);
     cudaStream_t s;
     /* a blocking stream, like oroStreamCreate (cuStreamCreate, flags 0): work on it is ordered after the synchronous
      * uploads / memsets the host issues on the legacy default stream (GPURenderer relies on that ordering) */
@@ -236,8 +264,9 @@ int b2pt_stream_launch_host_func(b2pt_ctx*, b2pt_stream stream, b2pt_host_fn fn,
     B2_CUDA(cudaLaunchHostFunc((cudaStream_t)stream, fn, user));
     return B2PT_OK;
 }
-int b2pt_event_create(b2pt_ctx*, b2pt_event* out_event)
+int b2pt_event_create(b2pt_ctx* ctx, b2pt_event* out_event)
 {
+    B2_SELECT_DEVICE(ctx);
     cudaEvent_t e;
     B2_CUDA(cudaEventCreate(&e));
     *out_event = e;
@@ -266,6 +295,7 @@ int b2pt_event_elapsed_ms(b2pt_ctx*, b2pt_event start, b2pt_event stop, float* o
 
 int b2pt_lut_create(b2pt_ctx* ctx, const float* texels, int width, int height, int depth, int channels, void** out_handle)
 {
+    B2_SELECT_DEVICE(ctx);
     if (!ctx || !texels || !out_handle || width <= 0 || height <= 0 || depth <= 0 || channels <= 0)
     {
         b2_set_error("b2pt_lut_create: invalid argument");
@@ -287,8 +317,9 @@ int b2pt_lut_create(b2pt_ctx* ctx, const float* texels, int width, int height, i
     return B2PT_OK;
 }
 
-int b2pt_lut_destroy(b2pt_ctx*, void* handle)
+int b2pt_lut_destroy(b2pt_ctx* ctx, void* handle)
 {
+    B2_SELECT_DEVICE(ctx);
     if (handle) B2_CUDA(cudaFree(handle));
     return B2PT_OK;
 }
@@ -296,6 +327,7 @@ int b2pt_lut_destroy(b2pt_ctx*, void* handle)
 int b2pt_bvh_build(b2pt_ctx* ctx, const int* triangle_indices, int triangle_count, const float* vertex_positions, int vertex_count,
                    uint32_t, b2pt_stream stream, b2pt_bvh** out_bvh)
 {
+    B2_SELECT_DEVICE(ctx);
     if (!ctx || !out_bvh || triangle_count < 0 || vertex_count < 0 || (triangle_count > 0 && (!triangle_indices || !vertex_positions)))
     {
         b2_set_error("b2pt_bvh_build: invalid argument");
@@ -305,7 +337,16 @@ int b2pt_bvh_build(b2pt_ctx* ctx, const int* triangle_indices, int triangle_coun
     b2pt_bvh* bvh = new b2pt_bvh();
     B2BvhHost& host = bvh->host;
     std::string error;
-    if (!b2_build_cw8(triangle_indices, (size_t)triangle_count, vertex_positions, (size_t)vertex_count, host, error))
+    bool built = false;
+    try
+    {
+        built = b2_build_cw8(triangle_indices, (size_t)triangle_count, vertex_positions, (size_t)vertex_count, host, error);
+    }
+    catch (const std::exception& e)
+    {
+        error = std::string("host exception: ") + e.what();
+    }
+    if (!built)
     {
         delete bvh;
         b2_set_error("b2pt_bvh_build: %s", error.c_str());
@@ -344,8 +385,9 @@ int b2pt_bvh_build(b2pt_ctx* ctx, const int* triangle_indices, int triangle_coun
     return B2PT_OK;
 }
 
-int b2pt_bvh_reupload(b2pt_ctx*, b2pt_bvh* bvh, b2pt_stream stream, uint64_t* out_bytes)
+int b2pt_bvh_reupload(b2pt_ctx* ctx, b2pt_bvh* bvh, b2pt_stream stream, uint64_t* out_bytes)
 {
+    B2_SELECT_DEVICE(ctx);
     if (!bvh) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
     cudaStream_t s = (cudaStream_t)stream;
     if (!bvh->host_pinned)
@@ -381,8 +423,9 @@ int b2pt_bvh_stats(b2pt_bvh* bvh, b2pt_bvh_stats_t* out)
     return B2PT_OK;
 }
 
-int b2pt_bvh_destroy(b2pt_ctx*, b2pt_bvh* bvh)
+int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh)
 {
+    B2_SELECT_DEVICE(ctx);
     if (!bvh) return B2PT_OK;
     {
         std::lock_guard<std::mutex> lock(g_bvh_depth_mutex);
@@ -482,22 +525,25 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
             }
         }
     }
-    int count = 0;
-    const B2KernelEntry* table = precise ? b2_kernel_table_precise(&count) : b2_kernel_table_fast(&count);
-    for (int i = 0; i < count; i++)
+    for (const B2KernelUnit& unit : kernel_units())
     {
-        const B2KernelEntry& e = table[i];
-        bool later_matters = e.direct == 5; /* LSS_RESTIR_DI */
-        if (e.pass == pass && e.bsdf_override == bsdf && e.direct == direct && e.base == base && (!later_matters || e.later == later) && e.envmap == envmap && e.counters == (counters ? 1 : 0))
+        if ((unit.precise != 0) != (precise != 0))
+            continue;
+        for (int i = 0; i < unit.count; i++)
         {
-            b2pt_kernel* k = new b2pt_kernel();
-            k->ctx = ctx;
-            k->entry = &e;
-            k->light_presampling = light_presampling;
-            B2_CUDA(cudaEventCreate(&k->start));
-            B2_CUDA(cudaEventCreate(&k->stop));
-            *out_kernel = k;
-            return B2PT_OK;
+            const B2KernelEntry& e = unit.entries[i];
+            bool later_matters = e.direct == 5; /* LSS_RESTIR_DI */
+            if (e.pass == pass && e.bsdf_override == bsdf && e.direct == direct && e.base == base && (!later_matters || e.later == later) && e.envmap == envmap && e.counters == (counters ? 1 : 0))
+            {
+                b2pt_kernel* k = new b2pt_kernel();
+                k->ctx = ctx;
+                k->entry = &e;
+                k->light_presampling = light_presampling;
+                B2_CUDA(cudaEventCreate(&k->start));
+                B2_CUDA(cudaEventCreate(&k->stop));
+                *out_kernel = k;
+                return B2PT_OK;
+            }
         }
     }
     b2_set_error("no precompiled variant for %s with BSDFOverride=%d DirectLightSamplingStrategy=%d DirectLightSamplingBaseStrategy=%d "
@@ -537,6 +583,7 @@ int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank
     }
     const b2pt_render_data* rd = reinterpret_cast<const b2pt_render_data*>(presampling_pass ? args[1] : args[0]);
     cudaStream_t s = (cudaStream_t)stream;
+    B2_SELECT_DEVICE(kernel->ctx);
     B2LaunchGeom geom;
     geom.width = width;
     geom.height = height;
@@ -579,6 +626,16 @@ int b2pt_kernel_launch(b2pt_kernel* kernel, int, int, int width, int height, voi
     return b2pt_kernel_launch_rows(kernel, width, height, 0, 1, args, stream);
 }
 
+int b2pt_kernel_destroy(b2pt_kernel* kernel)
+{
+    if (!kernel) return B2PT_OK;
+    if (kernel->ctx) cudaSetDevice(kernel->ctx->device);
+    if (kernel->start) cudaEventDestroy(kernel->start);
+    if (kernel->stop) cudaEventDestroy(kernel->stop);
+    delete kernel;
+    return B2PT_OK;
+}
+
 int b2pt_kernel_last_ms(b2pt_kernel* kernel, float* out_ms)
 {
     if (!kernel || !out_ms) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
@@ -597,36 +654,45 @@ int b2pt_kernel_launch_count(b2pt_kernel* kernel, uint64_t* out_count)
     return B2PT_OK;
 }
 
-int b2pt_counters_reset(b2pt_ctx*)
+int b2pt_counters_reset(b2pt_ctx* ctx)
 {
-    B2_CUDA(b2_counters_reset_precise());
-    B2_CUDA(b2_counters_reset_fast());
+    B2_SELECT_DEVICE(ctx);
+    for (const B2KernelUnit& unit : kernel_units())
+        B2_CUDA(unit.counters_reset());
     return B2PT_OK;
 }
 
-int b2pt_counters_read(b2pt_ctx*, b2pt_counters_t* out)
+int b2pt_counters_read(b2pt_ctx* ctx, b2pt_counters_t* out)
 {
+    B2_SELECT_DEVICE(ctx);
     if (!out) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
-    unsigned long long a[3], b[3];
     B2_CUDA(cudaDeviceSynchronize());
-    B2_CUDA(b2_counters_read_precise(a));
-    B2_CUDA(b2_counters_read_fast(b));
-    out->rays = a[0] + b[0];
-    out->nodes = a[1] + b[1];
-    out->triangles = a[2] + b[2];
+    out->rays = out->nodes = out->triangles = 0;
+    for (const B2KernelUnit& unit : kernel_units())
+    {
+        unsigned long long a[3];
+        B2_CUDA(unit.counters_read(a));
+        out->rays += a[0];
+        out->nodes += a[1];
+        out->triangles += a[2];
+    }
     return B2PT_OK;
 }
 
-int b2pt_faults_read(b2pt_ctx*, b2pt_faults_t* out, int reset)
+int b2pt_faults_read(b2pt_ctx* ctx, b2pt_faults_t* out, int reset)
 {
+    B2_SELECT_DEVICE(ctx);
     if (!out) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
-    unsigned int a[B2_FAULT_COUNT], b[B2_FAULT_COUNT];
     B2_CUDA(cudaDeviceSynchronize());
-    B2_CUDA(b2_faults_read_precise(a, reset));
-    B2_CUDA(b2_faults_read_fast(b, reset));
-    out->traversal_guard_trips = a[B2_FAULT_TRAVERSAL_GUARD] + b[B2_FAULT_TRAVERSAL_GUARD];
-    out->boundary_guard_trips = a[B2_FAULT_BOUNDARY_GUARD] + b[B2_FAULT_BOUNDARY_GUARD];
-    out->stack_overflows = a[B2_FAULT_STACK_OVERFLOW] + b[B2_FAULT_STACK_OVERFLOW];
+    out->traversal_guard_trips = out->boundary_guard_trips = out->stack_overflows = 0;
+    for (const B2KernelUnit& unit : kernel_units())
+    {
+        unsigned int a[B2_FAULT_COUNT];
+        B2_CUDA(unit.faults_read(a, reset));
+        out->traversal_guard_trips += a[B2_FAULT_TRAVERSAL_GUARD];
+        out->boundary_guard_trips += a[B2_FAULT_BOUNDARY_GUARD];
+        out->stack_overflows += a[B2_FAULT_STACK_OVERFLOW];
+    }
     return B2PT_OK;
 }
 

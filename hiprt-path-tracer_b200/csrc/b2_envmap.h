@@ -48,9 +48,12 @@ B2_HD Rgb envmap_sample(const b2pt_world_settings& ws, V3& sampled_direction, fl
     float v = (float)y / (float)ws.envmap_height;
     float phi = u * B2_TWO_PI;
     float theta = b2_max(1.0e-5f, v * B2_PI);
-    float cos_theta = (float)b2w_cos(theta);
-    float sin_theta = (float)b2w_sin(theta);
-    sampled_direction = v3((float)((b2w)(-sin_theta) * b2w_cos(phi)), -cos_theta, (float)((b2w)(-sin_theta) * b2w_sin(phi)));
+    b2w sin_theta_w, cos_theta_w, sin_phi_w, cos_phi_w;
+    b2w_sincos(theta, sin_theta_w, cos_theta_w);
+    b2w_sincos(phi, sin_phi_w, cos_phi_w);
+    float cos_theta = (float)cos_theta_w;
+    float sin_theta = (float)sin_theta_w;
+    sampled_direction = v3((float)((b2w)(-sin_theta) * cos_phi_w), -cos_theta, (float)((b2w)(-sin_theta) * sin_phi_w));
     sampled_direction = mat3_mul_vec(ws.envmap_to_world_matrix, sampled_direction);
 
     Rgb radiance = envmap_texel(ws, v2(u, v));

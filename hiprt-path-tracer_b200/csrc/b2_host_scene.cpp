@@ -173,6 +173,18 @@ bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bv
             error = "material index out of range";
             return false;
         }
+    /* vertex indices are dereferenced below (triangle areas, emissive power) before the BVH builder would look at them */
+    if (blob.indices.size() != 3 * n_tri || blob.positions.size() != 3 * n_vert || blob.normals.size() != 3 * n_vert || blob.texcoords.size() != 2 * n_vert)
+    {
+        error = "scene arrays have inconsistent sizes";
+        return false;
+    }
+    for (size_t i = 0; i < 3 * n_tri; i++)
+        if (blob.indices[i] < 0 || (size_t)blob.indices[i] >= n_vert)
+        {
+            error = "vertex index out of range";
+            return false;
+        }
 
     std::vector<SafeMaterial> safe(n_mat);
     scene.packed_materials.resize(n_mat);

@@ -33,14 +33,17 @@ struct B2KernelEntry
     cudaError_t (*launch)(const b2pt_render_data* rd, const B2LaunchGeom* geom, cudaStream_t stream);
 };
 
-/* defined once per flavour by b2_kernels.cu (compiled twice: -fmad=false / fast) */
-const B2KernelEntry* b2_kernel_table_precise(int* count);
-const B2KernelEntry* b2_kernel_table_fast(int* count);
-cudaError_t b2_counters_reset_precise();
-cudaError_t b2_counters_reset_fast();
-cudaError_t b2_counters_read_precise(unsigned long long out[3]);
-cudaError_t b2_counters_read_fast(unsigned long long out[3]);
-cudaError_t b2_faults_read_precise(unsigned int out[B2_FAULT_COUNT], int reset);
-cudaError_t b2_faults_read_fast(unsigned int out[B2_FAULT_COUNT], int reset);
+/* One object of b2_kernels.cu (a flavour x a group of variants, build.py) = one unit; units register themselves with
+ * b2_capi.cu when the library is loaded. Each unit owns a private copy of the traversal counters and the fault words. */
+struct B2KernelUnit
+{
+    const B2KernelEntry* entries;
+    int count;
+    int precise;
+    cudaError_t (*counters_reset)();
+    cudaError_t (*counters_read)(unsigned long long out[3]);
+    cudaError_t (*faults_read)(unsigned int out[B2_FAULT_COUNT], int reset);
+};
+void b2_register_kernel_unit(const B2KernelUnit* unit);
 
 #endif

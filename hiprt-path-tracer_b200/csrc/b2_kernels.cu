@@ -45,10 +45,12 @@
 #define B2_MKP_MIN_BLOCKS 12
 #define B2_MKP_BLOCK_SYNC 0
 
+namespace
+{
 namespace B2_NS
 {
-__device__ unsigned long long g_counters[3];
-__device__ unsigned int g_faults[B2_FAULT_COUNT];
+static __device__ unsigned long long g_counters[3];
+static __device__ unsigned int g_faults[B2_FAULT_COUNT];
 
 /* Pixel rows are partitioned across GPUs in interleaved bands of B2_BAND_ROWS rows (band b belongs to rank b % world);
  * a launch covers the bands of one rank. `local_row` counts the rows of this rank's bands, top to bottom. */
@@ -98,6 +100,7 @@ template <class V, int PASS>
 __global__ void __launch_bounds__(B2_BLOCK_THREADS) pass_kernel(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x)
 {
     __shared__ uint64_t stacks[B2_STACK_ENTRIES * B2_BLOCK_THREADS];
+    b2_block_constants_init(rd);
 
     const int tile = blockIdx.x;
     const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -137,6 +140,7 @@ __global__ void __launch_bounds__(B2_MKP_THREADS, B2_MKP_MIN_BLOCKS) megakernel_
 {
     __shared__ uint64_t stacks[B2_STACK_ENTRIES * B2_MKP_THREADS];
     __shared__ uint32_t queues[B2_MKP_THREADS / 32][B2_QUEUE_SLOTS];
+    b2_block_constants_init(rd);
 
     B2TraversalCounters local_counters;
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
     pool.next = pool.count + 2;
     if (threadIdx.x < 4)
         pool.count[threadIdx.x] = 0; /* count[0..1], next[0..1] */
-    __syncthreads();
+    b2_block_constants_init(rd); /* ends with the block barrier */
 
     B2TraversalCounters local_counters;
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
@@ -687,61 +691,69 @@ struct Reg
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_SPATIAL>(),            \
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_SPATIOTEMPORAL>()
 
+/* This translation unit is compiled once per (flavour, B2_UNIT, B2_UNIT_COUNTERS) -- build.py -- so that the variants build in
+ * parallel; every object registers its entries (and its own copy of the counter / fault words) with b2_capi.cu at load time. */
+#ifndef B2_UNIT
+#error "define B2_UNIT (1 = c1, 2 = c2, 3 = c3, 4 = c4 MegaKernel + CameraRays, 5 = c4 ReSTIR DI passes)"
+#endif
+#ifndef B2_UNIT_COUNTERS
+#define B2_UNIT_COUNTERS 0
+#endif
+#define B2_UC (B2_UNIT_COUNTERS != 0)
+
 static const B2KernelEntry* table(int* count)
 {
     static const B2KernelEntry entries[] = {
-        B2_REG_BASIC(B2_BSDF_LAMBERTIAN, B2_LSS_ONE_LIGHT, B2_BASE_UNIFORM, false),
-        B2_REG_BASIC(B2_BSDF_LAMBERTIAN, B2_LSS_ONE_LIGHT, B2_BASE_UNIFORM, true),
-#ifdef B2_HAVE_PRINCIPLED
-        B2_REG_BASIC(B2_BSDF_NONE, B2_LSS_MIS, B2_BASE_POWER, false),
-        B2_REG_BASIC(B2_BSDF_NONE, B2_LSS_MIS, B2_BASE_POWER, true),
-#endif
-#ifdef B2_HAVE_RIS
-        B2_REG_BASIC(B2_BSDF_NONE, B2_LSS_RIS, B2_BASE_POWER, false),
-        B2_REG_BASIC(B2_BSDF_NONE, B2_LSS_RIS, B2_BASE_POWER, true),
-#endif
-#ifdef B2_HAVE_RESTIR_DI
-        B2_REG_BASIC(B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, false),
-        B2_REG_RESTIR(B2_BSDF_NONE, B2_BASE_POWER, false),
-        B2_REG_BASIC(B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, true),
-        B2_REG_RESTIR(B2_BSDF_NONE, B2_BASE_POWER, true),
+#if B2_UNIT == 1
+        B2_REG_BASIC(B2_BSDF_LAMBERTIAN, B2_LSS_ONE_LIGHT, B2_BASE_UNIFORM, B2_UC),
+#elif B2_UNIT == 2
+        B2_REG_BASIC(B2_BSDF_NONE, B2_LSS_MIS, B2_BASE_POWER, B2_UC),
+#elif B2_UNIT == 3
+        B2_REG_BASIC(B2_BSDF_NONE, B2_LSS_RIS, B2_BASE_POWER, B2_UC),
+#elif B2_UNIT == 4
+        B2_REG_BASIC(B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_UC),
+#elif B2_UNIT == 5
+        B2_REG_RESTIR(B2_BSDF_NONE, B2_BASE_POWER, B2_UC),
+#else
+#error "unknown B2_UNIT"
 #endif
     };
     *count = (int)(sizeof(entries) / sizeof(entries[0]));
     return entries;
 }
-} // namespace B2_NS
 
+static cudaError_t unit_counters_reset()
+{
+    unsigned long long zero[3] = { 0, 0, 0 };
+    return cudaMemcpyToSymbol(g_counters, zero, sizeof(zero));
+}
+static cudaError_t unit_counters_read(unsigned long long out[3]) { return cudaMemcpyFromSymbol(out, g_counters, 3 * sizeof(unsigned long long)); }
+static cudaError_t unit_faults_read(unsigned int out[B2_FAULT_COUNT], int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_faults, B2_FAULT_COUNT * sizeof(unsigned int));
+    if (e != cudaSuccess || !reset)
+        return e;
+    unsigned int zero[B2_FAULT_COUNT] = {};
+    return cudaMemcpyToSymbol(g_faults, zero, sizeof(zero));
+}
+
+struct Registrar
+{
+    Registrar()
+    {
+        B2KernelUnit u;
+        u.entries = table(&u.count);
 #if defined(B2_FLAVOUR_PRECISE)
-const B2KernelEntry* b2_kernel_table_precise(int* count) { return b2_precise::table(count); }
-cudaError_t b2_counters_reset_precise()
-{
-    unsigned long long zero[3] = { 0, 0, 0 };
-    return cudaMemcpyToSymbol(b2_precise::g_counters, zero, sizeof(zero));
-}
-cudaError_t b2_counters_read_precise(unsigned long long out[3]) { return cudaMemcpyFromSymbol(out, b2_precise::g_counters, 3 * sizeof(unsigned long long)); }
-cudaError_t b2_faults_read_precise(unsigned int out[B2_FAULT_COUNT], int reset)
-{
-    cudaError_t e = cudaMemcpyFromSymbol(out, b2_precise::g_faults, B2_FAULT_COUNT * sizeof(unsigned int));
-    if (e != cudaSuccess || !reset)
-        return e;
-    unsigned int zero[B2_FAULT_COUNT] = {};
-    return cudaMemcpyToSymbol(b2_precise::g_faults, zero, sizeof(zero));
-}
+        u.precise = 1;
 #else
-const B2KernelEntry* b2_kernel_table_fast(int* count) { return b2_fast::table(count); }
-cudaError_t b2_counters_reset_fast()
-{
-    unsigned long long zero[3] = { 0, 0, 0 };
-    return cudaMemcpyToSymbol(b2_fast::g_counters, zero, sizeof(zero));
-}
-cudaError_t b2_counters_read_fast(unsigned long long out[3]) { return cudaMemcpyFromSymbol(out, b2_fast::g_counters, 3 * sizeof(unsigned long long)); }
-cudaError_t b2_faults_read_fast(unsigned int out[B2_FAULT_COUNT], int reset)
-{
-    cudaError_t e = cudaMemcpyFromSymbol(out, b2_fast::g_faults, B2_FAULT_COUNT * sizeof(unsigned int));
-    if (e != cudaSuccess || !reset)
-        return e;
-    unsigned int zero[B2_FAULT_COUNT] = {};
-    return cudaMemcpyToSymbol(b2_fast::g_faults, zero, sizeof(zero));
-}
+        u.precise = 0;
 #endif
+        u.counters_reset = &unit_counters_reset;
+        u.counters_read = &unit_counters_read;
+        u.faults_read = &unit_faults_read;
+        b2_register_kernel_unit(&u);
+    }
+};
+static Registrar g_registrar;
+} // namespace B2_NS
+} // anonymous namespace: every object of this file keeps its symbols to itself

@@ -126,7 +126,7 @@ B2_HD Rgb adobe_f82_tint_fresnel(Rgb F0, Rgb F82, Rgb F90, float F90_falloff_exp
 /* d'Eon, "A Hitchhiker's Guide to Multiple Scattering", eq. 11.15 fit */
 B2_HD float fresnel_hemispherical_albedo_fit(float relative_eta)
 {
-    return logf((10893.0f * relative_eta - 1438.2f) / (-774.4f * b2_square(relative_eta) + 10212.0f * relative_eta + 1.0f));
+    return b2f_log((10893.0f * relative_eta - 1438.2f) / (-774.4f * b2_square(relative_eta) + 10212.0f * relative_eta + 1.0f));
 }
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -140,11 +140,11 @@ B2_HD Rgb thin_film_eval_sensitivity(float opd, float shift)
     V3 var = v3(4.3278e+09f, 9.3046e+09f, 6.6121e+09f);
     V3 sq = v3(sqrtf((2.0f * B2_PI * var).x), sqrtf((2.0f * B2_PI * var).y), sqrtf((2.0f * B2_PI * var).z));
     V3 arg = pos * phase + v3(shift);
-    V3 cs = v3(cosf(arg.x), cosf(arg.y), cosf(arg.z));
+    V3 cs = v3(b2f_cos(arg.x), b2f_cos(arg.y), b2f_cos(arg.z));
     V3 ea = -1.0f * var * phase * phase;
-    V3 ex = v3(expf(ea.x), expf(ea.y), expf(ea.z));
+    V3 ex = v3(b2f_exp(ea.x), b2f_exp(ea.y), b2f_exp(ea.z));
     V3 xyz = val * sq * cs * ex;
-    xyz.x += 9.7470e-14f * sqrtf(2.0f * B2_PI * 4.5282e+09f) * cosf(2.2399e+06f * phase + shift) * expf(-4.5282e+09f * phase * phase);
+    xyz.x += 9.7470e-14f * sqrtf(2.0f * B2_PI * 4.5282e+09f) * b2f_cos(2.2399e+06f * phase + shift) * b2f_exp(-4.5282e+09f * phase * phase);
     V3 r = xyz / 1.0685e-7f;
     return rgb(r.x, r.y, r.z);
 }
@@ -158,10 +158,10 @@ B2_HD void thin_film_fresnel_phase(float cos_theta_i, float eta1, float eta2, fl
     float V = sqrtf((B - A) * 0.5f);
     float phi_perp_y = 2.0f * eta1 * V * cos_theta_i;
     float phi_perp_x = b2_square(U) + b2_square(V) - b2_square(eta1 * cos_theta_i);
-    phi_perp = atan2f(phi_perp_y, phi_perp_x);
+    phi_perp = b2f_atan2(phi_perp_y, phi_perp_x);
     float phi_par_y = 2.0f * eta1 * b2_square(eta2) * cos_theta_i * (2.0f * kappa2 * U - (1.0f - b2_square(kappa2)) * V);
     float phi_par_x = b2_square(b2_square(eta2) * (1.0f + b2_square(kappa2)) * cos_theta_i) - b2_square(eta1) * (b2_square(U) + b2_square(V));
-    phi_par = atan2f(phi_par_y, phi_par_x);
+    phi_par = b2f_atan2(phi_par_y, phi_par_x);
 }
 
 B2_HD void thin_film_fresnel_conductor(float cos_theta_i, float eta, float k, float& Rp2, float& Rs2)
@@ -185,8 +185,8 @@ B2_HD Rgb rgb_hue_shift(Rgb color, float hue_shift_degrees)
 {
     if (hue_shift_degrees == 0.0f)
         return color;
-    float cosA = cosf(hue_shift_degrees / 180.0f * B2_PI);
-    float sinA = sinf(hue_shift_degrees / 180.0f * B2_PI);
+    float cosA = b2f_cos(hue_shift_degrees / 180.0f * B2_PI);
+    float sinA = b2f_sin(hue_shift_degrees / 180.0f * B2_PI);
     const float sqrt_1_3 = 0.57735026918962576451f;
     const float one_over_3 = 1.0f / 3.0f;
     float m00 = cosA + (1.0f - cosA) / 3.0f;
@@ -276,17 +276,39 @@ B2_HD_NOINLINE Rgb thin_film_fresnel(const Mat& material, float ambient_IOR, flo
 /* ------------------------------------------------------------------------------------------------------------
  * Microfacet regularization (Jendersie & Grosch 2019; MicrofacetRegularization.h)
  * ------------------------------------------------------------------------------------------------------------ */
-B2_HD float regularization_consistent_tau(float tau_0, int sample_number)
+B2_HD float regularization_consistent_tau_compute(float tau_0, int sample_number)
 {
     /* powf(...) * sqrt(...) / (...): the unqualified sqrt makes the product and the quotient double (MicrofacetRegularization.h:160) */
-    return 1.0f / (2.0f * B2_PI * (1.0f - cosf(atanf((float)((b2w)powf((float)(sample_number + 1), -1.0f / 6.0f) * b2w_sqrt(B2_FOUR_PI * tau_0 - 1.0f) / (b2w)(B2_TWO_PI * tau_0 - 1.0f))))));
+    return 1.0f / (2.0f * B2_PI * (1.0f - b2f_cos(b2f_atan((float)((b2w)b2f_pow((float)(sample_number + 1), -1.0f / 6.0f) * b2w_sqrt(B2_FOUR_PI * tau_0 - 1.0f) / (b2w)(B2_TWO_PI * tau_0 - 1.0f))))));
+}
+
+/* The value depends on two launch-uniform inputs only (tau_0 and the sample number; the call sites ask for sample_number and
+ * sample_number + 1), yet the reference evaluates its powf / sqrt / atanf / cosf chain at every regularised lobe: ~300
+ * instructions per call and, inlined at ten sites, 12 % of the precise MegaKernel's code. On the device every block computes the two
+ * values once (b2_block_constants_init, first thing in every pixel kernel) and the call sites read them from shared memory. */
+#if defined(__CUDACC__)
+__shared__ float b2_s_consistent_tau[2];
+__device__ __forceinline__ void b2_block_constants_init(const b2pt_render_data& rd)
+{
+    if (threadIdx.x < 2)
+        b2_s_consistent_tau[threadIdx.x] = regularization_consistent_tau_compute(rd.bsdfs_data.microfacet_regularization_tau_0, (int)rd.render_settings.sample_number + (int)threadIdx.x);
+    __syncthreads();
+}
+#endif
+B2_HD float regularization_consistent_tau(const b2pt_render_data& rd, int sample_offset)
+{
+#if defined(__CUDA_ARCH__)
+    return b2_s_consistent_tau[sample_offset];
+#else
+    return regularization_consistent_tau_compute(rd.bsdfs_data.microfacet_regularization_tau_0, (int)rd.render_settings.sample_number + sample_offset);
+#endif
 }
 
 B2_HD float regularize_reflection(const b2pt_render_data& rd, int mode, float initial_roughness, float accumulated_path_roughness)
 {
     if (mode == B2_REGULARIZATION_NONE)
         return initial_roughness;
-    float consistent_tau = regularization_consistent_tau(rd.bsdfs_data.microfacet_regularization_tau_0, (int)rd.render_settings.sample_number);
+    float consistent_tau = regularization_consistent_tau(rd, 0);
     float final_tau = consistent_tau / b2_max(b2_square(accumulated_path_roughness), 1.0e-8f);
     float regularized_roughness = sqrtf(sqrtf(1.0f / (final_tau * B2_PI)));
     return b2_max(rd.bsdfs_data.microfacet_regularization_min_roughness, b2_max(initial_roughness, regularized_roughness));
@@ -297,7 +319,7 @@ B2_HD float regularize_refraction(const b2pt_render_data& rd, int mode, float in
     if (mode == B2_REGULARIZATION_NONE)
         return initial_roughness;
     /* the reference passes sample_number + 1 here and only here (MicrofacetRegularization.h:70) */
-    float consistent_tau = regularization_consistent_tau(rd.bsdfs_data.microfacet_regularization_tau_0, (int)rd.render_settings.sample_number + 1);
+    float consistent_tau = regularization_consistent_tau(rd, 1);
     float final_tau = consistent_tau / b2_max(b2_square(accumulated_path_roughness), 1.0e-8f);
     float regularized_roughness = sqrtf(sqrtf(1.0f / (final_tau * B2_PI * b2_square(eta_i - eta_t) / (4.0f * b2_square(b2_max(eta_i, eta_t))))));
     return b2_max(rd.bsdfs_data.microfacet_regularization_min_roughness, b2_max(initial_roughness, regularized_roughness));
@@ -307,7 +329,7 @@ B2_HD float regularize_mix_reflection_refraction(const b2pt_render_data& rd, int
 {
     if (mode == B2_REGULARIZATION_NONE)
         return initial_roughness;
-    float consistent_tau = regularization_consistent_tau(rd.bsdfs_data.microfacet_regularization_tau_0, (int)rd.render_settings.sample_number);
+    float consistent_tau = regularization_consistent_tau(rd, 0);
     float final_tau = consistent_tau / b2_max(b2_square(accumulated_path_roughness), 1.0e-8f);
     float regularized_roughness_reflection = sqrtf(sqrtf(1.0f / (final_tau * B2_PI)));
     if (eta_i == eta_t)
@@ -555,8 +577,10 @@ B2_HD V3 GGX_VNDF_sample(V3 local_view_direction, float alpha_x, float alpha_y, 
 
     float r = sqrtf(r1);
     float phi = B2_TWO_PI * r2;
-    float t1 = (float)((b2w)r * b2w_cos(phi));
-    float t2 = (float)((b2w)r * b2w_sin(phi));
+    b2w sin_phi_w, cos_phi_w;
+    b2w_sincos(phi, sin_phi_w, cos_phi_w);
+    float t1 = (float)((b2w)r * cos_phi_w);
+    float t2 = (float)((b2w)r * sin_phi_w);
     float s = 0.5f * (1.0f + Vh.z);
     t2 = (float)((b2w)(1.0f - s) * b2w_sqrt(1.0f - t1 * t1) + (b2w)(s * t2));
 
@@ -591,21 +615,38 @@ static __device__ const B2ExponentCurve b2_glass_exponent_higher_device[B2_GLASS
 static const B2ExponentCurve b2_glass_exponent_lower_host[B2_GLASS_EXPONENT_LOWER_COUNT] = B2_GLASS_EXPONENT_LOWER_INIT;
 static const B2ExponentCurve b2_glass_exponent_higher_host[B2_GLASS_EXPONENT_HIGHER_COUNT] = B2_GLASS_EXPONENT_HIGHER_INIT;
 
-B2_HD float glass_exponent_curve(const B2ExponentCurve& curve, float roughness, float fallback)
+/* compile-time copies of the curves' eta bounds (b2_glass_exponent_table.h; tests/test_abi.py keeps them in step): the bracket
+ * searches below unroll into compare chains on immediates; only the one segment a thread ends up with is fetched from the table */
+#define B2_GLASS_LOWER_BOUND(i) ((i) == 0 ? 1.01f : (i) == 1 ? 1.02f : (i) == 2 ? 1.03f : (i) == 3 ? 1.1f : (i) == 4 ? 1.2f : (i) == 5 ? 1.4f : (i) == 6 ? 1.5f : (i) == 7 ? 2.0f : 2.4f)
+#define B2_GLASS_HIGHER_BOUND(i) ((i) == 0 ? 1.01f : (i) == 1 ? 1.02f : (i) == 2 ? 1.03f : (i) == 3 ? 1.1f : (i) == 4 ? 1.2f : (i) == 5 ? 1.4f : (i) == 6 ? 1.5f : (i) == 7 ? 2.0f : (i) == 8 ? 2.4f : 3.0f)
+
+/* index of the roughness segment: the first k with roughness <= k * 0.1f (the reference's thresholds are the fp32 literals
+ * 0.0f, 0.1f, ... 1.0f); 11 = none (roughness > 1: the reference's chains leave the initial value untouched) */
+B2_HD int glass_exponent_segment(float roughness)
 {
-    for (int k = 0; k < 11; k++)
-    {
-        /* the reference's thresholds are the fp32 literals 0.0f, 0.1f, ... 1.0f */
-        const float threshold = k == 0 ? 0.0f : k == 1 ? 0.1f : k == 2 ? 0.2f : k == 3 ? 0.3f : k == 4 ? 0.4f : k == 5 ? 0.5f : k == 6 ? 0.6f : k == 7 ? 0.7f : k == 8 ? 0.8f : k == 9 ? 0.9f : 1.0f;
-        if (roughness <= threshold)
-        {
-            const B2ExponentSegment& s = curve.seg[k];
-            if (!s.lerp)
-                return s.a;
-            return b2_lerp(s.a, s.b, (roughness - s.x0) / 0.1f);
-        }
-    }
-    return fallback; /* roughness > 1: the reference's chains leave the initial value untouched */
+    int k = 11;
+    k = roughness <= 1.0f ? 10 : k;
+    k = roughness <= 0.9f ? 9 : k;
+    k = roughness <= 0.8f ? 8 : k;
+    k = roughness <= 0.7f ? 7 : k;
+    k = roughness <= 0.6f ? 6 : k;
+    k = roughness <= 0.5f ? 5 : k;
+    k = roughness <= 0.4f ? 4 : k;
+    k = roughness <= 0.3f ? 3 : k;
+    k = roughness <= 0.2f ? 2 : k;
+    k = roughness <= 0.1f ? 1 : k;
+    k = roughness <= 0.0f ? 0 : k;
+    return k;
+}
+
+B2_HD float glass_exponent_curve(const B2ExponentCurve& curve, int k, float roughness, float fallback)
+{
+    if (k > 10)
+        return fallback;
+    const B2ExponentSegment s = curve.seg[k];
+    if (!s.lerp)
+        return s.a;
+    return b2_lerp(s.a, s.b, (roughness - s.x0) / 0.1f);
 }
 
 B2_HD_NOINLINE float glass_energy_compensation_correction_exponent(float roughness, float relative_eta)
@@ -623,34 +664,37 @@ B2_HD_NOINLINE float glass_energy_compensation_correction_exponent(float roughne
     const B2ExponentCurve* lower_curves = b2_glass_exponent_lower_host;
     const B2ExponentCurve* higher_curves = b2_glass_exponent_higher_host;
 #endif
+    const int k = glass_exponent_segment(roughness);
 
-    /* lower chain: bracket (bound[i], bound[i + 1]] uses lower_curves[i]; outside every bracket the defaults stay */
+    /* lower chain: bracket (bound[i], bound[i + 1]] uses lower_curves[i]; outside every bracket the defaults stay.
+     * The brackets are tested from the last to the first so that the first match of the reference's chain wins. */
+    int lower_index = -1;
     float lower_relative_eta_bound = 1.01f;
-    float lower_correction = 2.5f;
-    for (int i = 0; i < B2_GLASS_EXPONENT_LOWER_COUNT; i++)
+#pragma unroll
+    for (int i = B2_GLASS_EXPONENT_LOWER_COUNT - 1; i >= 0; i--)
     {
-        float lo = lower_curves[i].eta_bound;
-        float hi = higher_curves[i + 1].eta_bound;
-        if (relative_eta > lo && relative_eta <= hi)
-        {
-            lower_relative_eta_bound = lo;
-            lower_correction = glass_exponent_curve(lower_curves[i], roughness, 2.5f);
-            break;
-        }
+        const float lo = B2_GLASS_LOWER_BOUND(i);
+        const float hi = B2_GLASS_HIGHER_BOUND(i + 1);
+        const bool inside = relative_eta > lo && relative_eta <= hi;
+        lower_index = inside ? i : lower_index;
+        lower_relative_eta_bound = inside ? lo : lower_relative_eta_bound;
     }
+    float lower_correction = 2.5f;
+    if (lower_index >= 0)
+        lower_correction = glass_exponent_curve(lower_curves[lower_index], k, roughness, 2.5f);
 
     /* higher chain: the first bound >= relative_eta, the last curve beyond all bounds */
     int j = B2_GLASS_EXPONENT_HIGHER_COUNT - 1;
-    for (int i = 0; i < B2_GLASS_EXPONENT_HIGHER_COUNT - 1; i++)
+    float higher_relative_eta_bound = B2_GLASS_HIGHER_BOUND(B2_GLASS_EXPONENT_HIGHER_COUNT - 1);
+#pragma unroll
+    for (int i = B2_GLASS_EXPONENT_HIGHER_COUNT - 2; i >= 0; i--)
     {
-        if (relative_eta <= higher_curves[i].eta_bound)
-        {
-            j = i;
-            break;
-        }
+        const float bound = B2_GLASS_HIGHER_BOUND(i);
+        const bool below = relative_eta <= bound;
+        j = below ? i : j;
+        higher_relative_eta_bound = below ? bound : higher_relative_eta_bound;
     }
-    float higher_relative_eta_bound = higher_curves[j].eta_bound;
-    float higher_correction = glass_exponent_curve(higher_curves[j], roughness, 2.5f);
+    float higher_correction = glass_exponent_curve(higher_curves[j], k, roughness, 2.5f);
 
     if (higher_relative_eta_bound == lower_relative_eta_bound)
         return lower_correction;
@@ -673,7 +717,7 @@ B2_HD float ggx_energy_compensation_dielectrics(const b2pt_render_data& rd, cons
         if (!material.thin_walled)
             exponent_correction = glass_energy_compensation_correction_exponent(custom_roughness, relative_eta_for_correction);
 
-        float view_direction_tex_fetch = powf(b2_max(1.0e-3f, NoV), 1.0f / exponent_correction);
+        float view_direction_tex_fetch = b2f_pow(b2_max(1.0e-3f, NoV), 1.0f / exponent_correction);
         float F0 = F0_from_eta(eta_t, eta_i);
         float F0_remapped = (float)b2w_sqrt(b2w_sqrt(F0));
 
@@ -775,8 +819,10 @@ B2_HD float sheen_get_phi(V3 direction)
 
 B2_HD V3 sheen_rotate_vector(V3 vec, V3 axis, float angle)
 {
-    float sin_angle = (float)b2w_sin(angle);
-    float cos_angle = (float)b2w_cos(angle);
+    b2w sin_angle_w, cos_angle_w;
+    b2w_sincos(angle, sin_angle_w, cos_angle_w);
+    float sin_angle = (float)sin_angle_w;
+    float cos_angle = (float)cos_angle_w;
     return vec * cos_angle + axis * dot(vec, axis) * (1.0f - cos_angle) + sin_angle * cross(axis, vec);
 }
 

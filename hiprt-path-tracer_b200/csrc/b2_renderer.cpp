@@ -16,6 +16,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -28,6 +29,35 @@ void b2_set_error(const char* fmt, ...);
         if (rc_ != B2PT_OK)   \
             return rc_;       \
     } while (0)
+
+/* inside b2pt_renderer_create: a failure releases everything allocated so far */
+#define B2_TRY_R(call)                  \
+    do                                  \
+    {                                   \
+        int rc_ = (call);               \
+        if (rc_ != B2PT_OK)             \
+        {                               \
+            b2pt_renderer_destroy(r);   \
+            return rc_;                 \
+        }                               \
+    } while (0)
+
+/* C ABI boundary: no C++ exception may cross it */
+#define B2_GUARDED(...)                                                    \
+    try                                                                    \
+    {                                                                      \
+        __VA_ARGS__                                                            \
+    }                                                                      \
+    catch (const std::bad_alloc&)                                          \
+    {                                                                      \
+        b2_set_error("out of host memory");                                \
+        return B2PT_ERR_IO;                                                \
+    }                                                                      \
+    catch (const std::exception& e)                                        \
+    {                                                                      \
+        b2_set_error("unexpected exception: %s", e.what());                \
+        return B2PT_ERR_INVALID_ARGUMENT;                                  \
+    }
 
 struct b2pt_renderer
 {
@@ -159,7 +189,11 @@ int resolve_kernels(b2pt_renderer* r)
     const VariantKey* v = find_variant(r->variant);
     for (int pass = 0; pass < B2_PASS_COUNT; pass++)
     {
-        r->kernels[pass] = nullptr; /* kernel objects are tiny; earlier ones are intentionally kept alive */
+        if (r->kernels[pass])
+        {
+            b2pt_kernel_destroy(r->kernels[pass]);
+            r->kernels[pass] = nullptr;
+        }
         const char* entry = entry_name_of_pass(pass);
         if (!entry)
             continue;
@@ -179,16 +213,31 @@ int resolve_kernels(b2pt_renderer* r)
     return B2PT_OK;
 }
 
-int upload_scene(b2pt_renderer* r)
+/* Forgets the current scene: after this no device pointer of the render data refers to scene memory, so a failed
+ * upload leaves the renderer in the "no scene set" state (render / reupload return an error) instead of pointing at
+ * freed allocations. */
+void invalidate_scene(b2pt_renderer* r)
 {
-    unpin_scene(r); /* normally already done by the caller, before it touched r->scene */
-    free_all(r, r->scene_allocs);
+    unpin_scene(r);
+    r->has_scene = false;
     r->scene_uploads.clear();
+    b2pt_render_data& rd = r->loop.rd;
+    b2pt_rgb* framebuffer = rd.buffers.accumulated_ray_colors;
+    std::memset(&rd.buffers, 0, sizeof(rd.buffers));
+    rd.buffers.accumulated_ray_colors = framebuffer;
+    rd.GPU_BVH = nullptr;
+    rd.light_GPU_BVH = nullptr;
+    free_all(r, r->scene_allocs);
     if (r->bvh)
     {
         b2pt_bvh_destroy(r->ctx, r->bvh);
         r->bvh = nullptr;
     }
+}
+
+int upload_scene(b2pt_renderer* r)
+{
+    invalidate_scene(r);
     B2HostScene& s = r->scene;
     std::string error;
     if (!b2_host_scene_prepare(s, error, /* build_bvh = */ false))
@@ -293,7 +342,8 @@ int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* varia
         return B2PT_ERR_NO_VARIANT;
     }
     B2_TRY(b2pt_ctx_make_current(ctx));
-    b2pt_renderer* r = new b2pt_renderer();
+    b2pt_renderer* r = new (std::nothrow) b2pt_renderer();
+    if (!r) { b2_set_error("out of host memory"); return B2PT_ERR_INVALID_ARGUMENT; }
     r->ctx = ctx;
     r->width = width;
     r->height = height;
@@ -301,51 +351,52 @@ int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* varia
     r->precise = precise ? 1 : 0;
     r->loop.restir_di = find_variant(variant)->restir;
     r->loop.restir_di_presampling = find_variant(variant)->presampling;
-    B2_TRY(b2pt_stream_create(ctx, &r->stream));
-    B2_TRY(b2pt_event_create(ctx, &r->ev_start));
-    B2_TRY(b2pt_event_create(ctx, &r->ev_stop));
+    B2_TRY_R(b2pt_stream_create(ctx, &r->stream));
+    B2_TRY_R(b2pt_event_create(ctx, &r->ev_start));
+    B2_TRY_R(b2pt_event_create(ctx, &r->ev_stop));
 
     const size_t n = r->pixels();
     b2pt_render_data& rd = r->loop.rd;
     rd.render_settings.render_resolution = b2pt_int2{ width, height };
     void* p = nullptr;
-    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_rgb), &p)); rd.buffers.accumulated_ray_colors = (b2pt_rgb*)p;
-    B2_TRY(alloc_zero(r, r->frame_allocs, n, &p)); rd.aux_buffers.pixel_active = (uint8_t*)p;
-    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_float3), &p)); rd.aux_buffers.denoiser_normals = (b2pt_float3*)p;
-    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_rgb), &p)); rd.aux_buffers.denoiser_albedo = (b2pt_rgb*)p;
-    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(int), &p)); rd.aux_buffers.pixel_sample_count = (int*)p;
-    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(float), &p)); rd.aux_buffers.pixel_squared_luminance = (float*)p;
-    B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(int), &p)); rd.aux_buffers.pixel_converged_sample_count = (int*)p;
-    B2_TRY(alloc_zero(r, r->frame_allocs, 16, &p)); r->d_status = (uint8_t*)p;
+    B2_TRY_R(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_rgb), &p)); rd.buffers.accumulated_ray_colors = (b2pt_rgb*)p;
+    B2_TRY_R(alloc_zero(r, r->frame_allocs, n, &p)); rd.aux_buffers.pixel_active = (uint8_t*)p;
+    B2_TRY_R(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_float3), &p)); rd.aux_buffers.denoiser_normals = (b2pt_float3*)p;
+    B2_TRY_R(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_rgb), &p)); rd.aux_buffers.denoiser_albedo = (b2pt_rgb*)p;
+    B2_TRY_R(alloc_zero(r, r->frame_allocs, n * sizeof(int), &p)); rd.aux_buffers.pixel_sample_count = (int*)p;
+    B2_TRY_R(alloc_zero(r, r->frame_allocs, n * sizeof(float), &p)); rd.aux_buffers.pixel_squared_luminance = (float*)p;
+    B2_TRY_R(alloc_zero(r, r->frame_allocs, n * sizeof(int), &p)); rd.aux_buffers.pixel_converged_sample_count = (int*)p;
+    B2_TRY_R(alloc_zero(r, r->frame_allocs, 16, &p)); r->d_status = (uint8_t*)p;
     rd.aux_buffers.still_one_ray_active = r->d_status;
     rd.aux_buffers.pixel_count_converged_so_far = (unsigned int*)(r->d_status + 4);
     b2pt_gbuffer* gb[2] = { &rd.g_buffer, &rd.g_buffer_prev_frame };
-    for (int i = 0; i < 2; i++)
+    /* the previous-frame G-buffer and the reservoir buffers exist only for the ReSTIR DI variants (use_prev_frame_g_buffer) */
+    for (int i = 0; i < (r->loop.restir_di ? 2 : 1); i++)
     {
-        B2_TRY(alloc_zero(r, r->frame_allocs, n * 108, &p)); gb[i]->materials = p;
-        B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(int), &p)); gb[i]->first_hit_prim_index = (int*)p;
-        B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_float3), &p)); gb[i]->primary_hit_position = (b2pt_float3*)p;
-        B2_TRY(alloc_zero(r, r->frame_allocs, n * 4, &p)); gb[i]->shading_normals = (uint32_t*)p;
-        B2_TRY(alloc_zero(r, r->frame_allocs, n * 4, &p)); gb[i]->geometric_normals = (uint32_t*)p;
+        B2_TRY_R(alloc_zero(r, r->frame_allocs, n * 108, &p)); gb[i]->materials = p;
+        B2_TRY_R(alloc_zero(r, r->frame_allocs, n * sizeof(int), &p)); gb[i]->first_hit_prim_index = (int*)p;
+        B2_TRY_R(alloc_zero(r, r->frame_allocs, n * sizeof(b2pt_float3), &p)); gb[i]->primary_hit_position = (b2pt_float3*)p;
+        B2_TRY_R(alloc_zero(r, r->frame_allocs, n * 4, &p)); gb[i]->shading_normals = (uint32_t*)p;
+        B2_TRY_R(alloc_zero(r, r->frame_allocs, n * 4, &p)); gb[i]->geometric_normals = (uint32_t*)p;
     }
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < (r->loop.restir_di ? 3 : 0); i++)
     {
-        B2_TRY(alloc_zero(r, r->frame_allocs, n * 36, &r->d_reservoirs[i]));
-        B2_TRY(clear_reservoirs(r, r->d_reservoirs[i], nullptr));
+        B2_TRY_R(alloc_zero(r, r->frame_allocs, n * 36, &r->d_reservoirs[i]));
+        B2_TRY_R(clear_reservoirs(r, r->d_reservoirs[i], nullptr));
     }
     if (r->loop.restir_di)
     {
         /* per-pixel radius + 64-bit direction mask of the adaptive-directional spatial reuse (ReSTIRDIRenderPass.h) */
-        B2_TRY(alloc_zero(r, r->frame_allocs, n * sizeof(unsigned long long), &p));
+        B2_TRY_R(alloc_zero(r, r->frame_allocs, n * sizeof(unsigned long long), &p));
         rd.render_settings.restir_di_settings.common_spatial_pass.per_pixel_spatial_reuse_directions_mask_ull = (unsigned long long*)p;
-        B2_TRY(alloc_zero(r, r->frame_allocs, n, &p));
+        B2_TRY_R(alloc_zero(r, r->frame_allocs, n, &p));
         rd.render_settings.restir_di_settings.common_spatial_pass.per_pixel_spatial_reuse_radius = (uint8_t*)p;
     }
     if (r->loop.restir_di_presampling)
     {
         /* ReSTIRDIRenderPass allocates number_of_subsets * subset_size presampled lights of 48 bytes (defaults 128 x 1024) */
         const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
-        B2_TRY(alloc_zero(r, r->frame_allocs, (size_t)di.light_presampling.number_of_subsets * di.light_presampling.subset_size * 48, &p));
+        B2_TRY_R(alloc_zero(r, r->frame_allocs, (size_t)di.light_presampling.number_of_subsets * di.light_presampling.subset_size * 48, &p));
         rd.render_settings.restir_di_settings.light_presampling.light_samples = p;
     }
     r->loop.initial_reservoirs = r->d_reservoirs[0];
@@ -360,7 +411,12 @@ int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* varia
 int b2pt_renderer_destroy(b2pt_renderer* r)
 {
     if (!r) return B2PT_OK;
-    unpin_scene(r);
+    b2pt_ctx_make_current(r->ctx);
+    if (r->stream)
+        unpin_scene(r);
+    for (int pass = 0; pass < B2_PASS_COUNT; pass++)
+        if (r->kernels[pass])
+            b2pt_kernel_destroy(r->kernels[pass]);
     free_all(r, r->frame_allocs);
     free_all(r, r->scene_allocs);
     free_all(r, r->envmap_allocs);
@@ -377,14 +433,20 @@ int b2pt_renderer_destroy(b2pt_renderer* r)
 int b2pt_renderer_set_scene_file(b2pt_renderer* r, const char* scene_blob_path)
 {
     if (!r || !scene_blob_path) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
-    unpin_scene(r);
-    std::string err = b2scene_read(scene_blob_path, r->scene.blob);
-    if (!err.empty())
-    {
-        b2_set_error("%s", err.c_str());
-        return B2PT_ERR_IO;
-    }
-    return upload_scene(r);
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
+    B2_GUARDED(
+        /* parsed into a temporary: a file that cannot be read leaves the current scene untouched and valid */
+        B2Scene incoming;
+        std::string err = b2scene_read(scene_blob_path, incoming);
+        if (!err.empty())
+        {
+            b2_set_error("%s", err.c_str());
+            return B2PT_ERR_IO;
+        }
+        invalidate_scene(r);
+        r->scene.blob = std::move(incoming);
+        return upload_scene(r);
+    )
 }
 
 int b2pt_renderer_set_scene_arrays(b2pt_renderer* r, const float* positions, const float* normals, const float* texcoords,
@@ -396,7 +458,9 @@ int b2pt_renderer_set_scene_arrays(b2pt_renderer* r, const float* positions, con
         b2_set_error("b2pt_renderer_set_scene_arrays: invalid argument");
         return B2PT_ERR_INVALID_ARGUMENT;
     }
-    unpin_scene(r);
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
+    B2_GUARDED(
+    invalidate_scene(r);
     B2Scene& s = r->scene.blob;
     s.positions.assign(positions, positions + 3 * (size_t)vertex_count);
     if (normals) s.normals.assign(normals, normals + 3 * (size_t)vertex_count); else s.normals.assign(3 * (size_t)vertex_count, 0.0f);
@@ -407,6 +471,7 @@ int b2pt_renderer_set_scene_arrays(b2pt_renderer* r, const float* positions, con
     s.materials.assign(materials, materials + (size_t)material_count * B2MAT_FLOAT_COUNT);
     std::memcpy(&s.camera, camera52, sizeof(B2SceneCamera));
     return upload_scene(r);
+    )
 }
 
 /* Re-sends every scene array (geometry, per-triangle data, material SoA, alias table, wide-BVH blob) from the host
@@ -415,6 +480,7 @@ int b2pt_renderer_set_scene_arrays(b2pt_renderer* r, const float* positions, con
 int b2pt_renderer_reupload_scene(b2pt_renderer* r, uint64_t* out_bytes)
 {
     if (!r || !r->has_scene) { b2_set_error("no scene"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
     uint64_t total = 0;
     if (!r->scene_pin_attempted)
     {
@@ -438,7 +504,16 @@ int b2pt_renderer_reupload_scene(b2pt_renderer* r, uint64_t* out_bytes)
 int b2pt_renderer_set_luts_file(b2pt_renderer* r, const char* lut_blob_path)
 {
     if (!r || !lut_blob_path) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
+    B2_GUARDED(
     FILE* f = std::fopen(lut_blob_path, "rb");
+    long file_bytes = 0;
+    if (f)
+    {
+        std::fseek(f, 0, SEEK_END);
+        file_bytes = std::ftell(f);
+        std::fseek(f, 0, SEEK_SET);
+    }
     char magic[8];
     uint32_t count = 0;
     if (!f || std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "B2LUTS01", 8) != 0 || std::fread(&count, 4, 1, f) != 1)
@@ -459,6 +534,12 @@ int b2pt_renderer_set_luts_file(b2pt_renderer* r, const char* lut_blob_path)
         {
             std::fclose(f);
             b2_set_error("truncated LUT container");
+            return B2PT_ERR_IO;
+        }
+        if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || (unsigned long long)dims[0] * dims[1] * dims[2] * 4ull > (unsigned long long)file_bytes)
+        {
+            std::fclose(f);
+            b2_set_error("LUT container: dimensions of '%.32s' exceed the file size", name);
             return B2PT_ERR_IO;
         }
         std::vector<float> texels((size_t)dims[0] * dims[1] * dims[2]);
@@ -487,6 +568,7 @@ int b2pt_renderer_set_luts_file(b2pt_renderer* r, const char* lut_blob_path)
     }
     std::fclose(f);
     return B2PT_OK;
+    )
 }
 
 /* RendererEnvmap / CPURenderer::set_envmap (CPURenderer.cpp:467-508): luminance alias table (Image.cpp:536-545,
@@ -494,6 +576,7 @@ int b2pt_renderer_set_luts_file(b2pt_renderer* r, const char* lut_blob_path)
 int b2pt_renderer_set_envmap_file(b2pt_renderer* r, const char* envmap_blob_path)
 {
     if (!r || !envmap_blob_path) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_GUARDED(
     std::vector<float> rgba;
     int width = 0, height = 0;
     if (!b2_envmap_blob_read(envmap_blob_path, rgba, width, height))
@@ -502,11 +585,14 @@ int b2pt_renderer_set_envmap_file(b2pt_renderer* r, const char* envmap_blob_path
         return B2PT_ERR_IO;
     }
     return b2pt_renderer_set_envmap(r, rgba.data(), width, height);
+    )
 }
 
 int b2pt_renderer_set_envmap(b2pt_renderer* r, const float* rgba, int width, int height)
 {
     if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
+    B2_GUARDED(
     free_all(r, r->envmap_allocs);
     b2pt_world_settings& w = r->loop.rd.world_settings;
     if (!rgba || width <= 0 || height <= 0)
@@ -527,6 +613,7 @@ int b2pt_renderer_set_envmap(b2pt_renderer* r, const float* rgba, int width, int
     w.envmap_height = (unsigned)height;
     w.ambient_light_type = 2;
     return B2PT_OK;
+    )
 }
 
 b2pt_render_data* b2pt_renderer_render_data(b2pt_renderer* r) { return r ? &r->loop.rd : nullptr; }
@@ -696,6 +783,7 @@ int b2pt_render_data_framebuffer_offset(void)
 int b2pt_renderer_synchronize(b2pt_renderer* r)
 {
     if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
     return b2pt_stream_synchronize(r->ctx, r->stream);
 }
 
@@ -720,6 +808,7 @@ int b2pt_renderer_pass_ms(b2pt_renderer* r, int pass, float* out_ms, uint64_t* o
 int b2pt_renderer_download_framebuffer(b2pt_renderer* r, float* out_rgb)
 {
     if (!r || !out_rgb) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
     B2_TRY(b2pt_memcpy_d2h(r->ctx, out_rgb, r->loop.rd.buffers.accumulated_ray_colors, r->pixels() * 12, r->stream));
     return b2pt_stream_synchronize(r->ctx, r->stream);
 }
@@ -727,6 +816,7 @@ int b2pt_renderer_download_framebuffer(b2pt_renderer* r, float* out_rgb)
 int b2pt_renderer_download_gbuffer(b2pt_renderer* r, int* out_prim, float* out_position, uint32_t* out_geo, uint32_t* out_shade, uint32_t* out_material27)
 {
     if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
     const b2pt_gbuffer& g = r->loop.rd.g_buffer;
     const size_t n = r->pixels();
     B2_TRY(b2pt_stream_synchronize(r->ctx, r->stream));
@@ -741,6 +831,8 @@ int b2pt_renderer_download_gbuffer(b2pt_renderer* r, int* out_prim, float* out_p
 int b2pt_renderer_download_reservoirs(b2pt_renderer* r, int which, uint32_t* out_words9)
 {
     if (!r || !out_words9 || which < 0 || which > 3) { b2_set_error("invalid argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    if (!r->loop.restir_di) { b2_set_error("variant %s has no ReSTIR DI reservoirs", r->variant.c_str()); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
     B2_TRY(b2pt_stream_synchronize(r->ctx, r->stream));
     const void* src = which < 3 ? r->d_reservoirs[which] : r->loop.rd.render_settings.restir_di_settings.restir_output_reservoirs;
     return b2pt_memcpy_d2h(r->ctx, out_words9, src, r->pixels() * 36, nullptr);

@@ -419,8 +419,8 @@ B2_HD void restir_directional_reuse_compute_pixel(const b2pt_render_data& rd, ui
             if (radius_index > 0 && !(previous_mask & (1ull << sample_index)))
                 continue;
             float theta = sample_index / (float)NB_SAMPLES_PER_RADIUS * B2_TWO_PI;
-            float x_circle = current_radius * cosf(theta);
-            float y_circle = current_radius * sinf(theta);
+            float x_circle = current_radius * b2f_cos(theta);
+            float y_circle = current_radius * b2f_sin(theta);
             int nx = (int)x + (int)roundf(x_circle), ny = (int)y + (int)roundf(y_circle);
             if (nx < 0 || nx >= res.x || ny < 0 || ny >= res.y)
                 continue;

@@ -19,8 +19,10 @@ B2_HD float balance_heuristic(float pdf_a, float pdf_b) { return balance_heurist
 B2_HD V2 sample_in_disk_uv(float radius, V2 uv)
 {
     float r_sqrt_v = radius * sqrtf(uv.y);
-    float x = (float)((b2w)r_sqrt_v * b2w_cos(B2_TWO_PI * uv.x));
-    float y = (float)((b2w)r_sqrt_v * b2w_sin(B2_TWO_PI * uv.x));
+    b2w sin_w, cos_w;
+    b2w_sincos(B2_TWO_PI * uv.x, sin_w, cos_w);
+    float x = (float)((b2w)r_sqrt_v * cos_w);
+    float y = (float)((b2w)r_sqrt_v * sin_w);
     return v2(x, y);
 }
 
@@ -44,7 +46,9 @@ B2_HD V3 cosine_weighted_sample_around_normal_world_space(V3 normal, Rng& rng)
     }
     float theta = B2_TWO_PI * rand_1;
     float s = sqrtf(1.0f - rand_2 * rand_2);
-    V3 sphere_point = v3(s * (float)b2w_cos(theta), s * (float)b2w_sin(theta), rand_2);
+    b2w sin_w, cos_w;
+    b2w_sincos(theta, sin_w, cos_w);
+    V3 sphere_point = v3(s * (float)cos_w, s * (float)sin_w, rand_2);
     return normalize(normal + sphere_point);
 }
 
@@ -55,7 +59,9 @@ B2_HD V3 cosine_weighted_sample_z_up_frame(Rng& rng)
     float phi = B2_TWO_PI * r1;
     float cos_theta = sqrtf(r2);
     float sin_theta = sqrtf(1 - cos_theta * cos_theta);
-    return normalize(v3((float)(b2w_cos(phi) * (b2w)sin_theta), (float)(b2w_sin(phi) * (b2w)sin_theta), cos_theta));
+    b2w sin_w, cos_w;
+    b2w_sincos(phi, sin_w, cos_w);
+    return normalize(v3((float)(cos_w * (b2w)sin_theta), (float)(sin_w * (b2w)sin_theta), cos_theta));
 }
 
 /* Duff et al. style branchless basis, ONB.h:18-30 */
@@ -76,7 +82,9 @@ B2_HD void build_rotated_ONB(V3 N, V3& T, V3& B, float basis_rotation)
 {
     V3 up = fabsf(N.z) < 0.9999999f ? v3(0.0f, 0.0f, 1.0f) : v3(1.0f, 0.0f, 0.0f);
     T = normalize(cross(up, N));
-    T = T * (float)b2w_cos(basis_rotation) + cross(N, T) * (float)b2w_sin(basis_rotation) + N * dot(N, T) * (float)((b2w)1.0f - b2w_cos(basis_rotation));
+    b2w sin_w, cos_w;
+    b2w_sincos(basis_rotation, sin_w, cos_w);
+    T = T * (float)cos_w + cross(N, T) * (float)sin_w + N * dot(N, T) * (float)((b2w)1.0f - cos_w);
     B = cross(N, T);
 }
 

@@ -159,6 +159,8 @@ int b2pt_kernel_launch(b2pt_kernel* kernel, int block_x, int block_y, int width,
  * reference has no multi-GPU path; this is the one addition to its launch surface (BASELINE.json north_star). */
 #define B2PT_BAND_ROWS 16
 int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank, int world, void** args, b2pt_stream stream);
+/* GPUKernel's destructor (src/Compiler/GPUKernel.h): releases the kernel object and its two timing events */
+int b2pt_kernel_destroy(b2pt_kernel* kernel);
 int b2pt_kernel_last_ms(b2pt_kernel* kernel, float* out_ms);
 int b2pt_kernel_launch_count(b2pt_kernel* kernel, uint64_t* out_count);
 

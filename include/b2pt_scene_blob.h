@@ -117,6 +117,19 @@ inline std::string b2scene_read(const char* path, B2Scene& out)
         return "scene blob material record size mismatch";
     }
 
+    {
+        /* a bad header must not size the vectors: every count is bounded by what the file can hold */
+        long here = std::ftell(f);
+        std::fseek(f, 0, SEEK_END);
+        const unsigned long long file_bytes = (unsigned long long)std::ftell(f);
+        std::fseek(f, here, SEEK_SET);
+        const unsigned long long need = sizeof(h) + 33ull * h.n_vertices + ((4 - (h.n_vertices & 3)) & 3) + 16ull * h.n_triangles + 4ull * h.n_materials * B2MAT_FLOAT_COUNT;
+        if (need > file_bytes)
+        {
+            std::fclose(f);
+            return std::string("scene blob header counts exceed the file size: ") + path;
+        }
+    }
     out.camera = h.camera;
     out.positions.resize(3ull * h.n_vertices);
     out.normals.resize(3ull * h.n_vertices);
