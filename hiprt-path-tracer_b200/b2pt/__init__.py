@@ -78,7 +78,6 @@ SETTINGS_OFFSETS = {
 }
 FRAMEBUFFER_POINTER_OFFSET = None  # filled below from the C side (offsetof(b2pt_render_data, buffers.accumulated_ray_colors))
 _PTR = C.c_void_p
-EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64)
 _CT = {"i": C.c_int, "I": C.c_uint, "B": C.c_uint8, "f": C.c_float}
 
 
@@ -149,6 +148,40 @@ class Context:
         if self.handle:
             lib().b2pt_ctx_destroy(self.handle)
             self.handle = C.c_void_p()
+
+
+class Communicator:
+    """NCCL communicator of the C layer (b2pt_comm): rank 0 draws the unique id, torch.distributed broadcasts it."""
+
+    def __init__(self, ctx, rank, world, torch, dist):
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(lib().b2pt_comm_unique_id(ident))
+        device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=device)
+        dist.broadcast(t, src=0)
+        ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self.handle = C.c_void_p()
+        check(lib().b2pt_comm_create(ctx.handle, ident, rank, world, C.byref(self.handle)))
+        self.rank, self.world = rank, world
+
+    def stats(self):
+        e, g, b = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().b2pt_comm_stats(self.handle, C.byref(e), C.byref(g), C.byref(b)))
+        return dict(exchanges=e.value, gathers=g.value, bytes_sent=b.value)
+
+    def close(self):
+        if self.handle:
+            lib().b2pt_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+def partition_rows(height, rank, world, band_rows, halo=0):
+    """b2pt_partition_rows (host logic of the C layer): rows within `halo` of rank's bands."""
+    rows = (C.c_int * height)()
+    n = C.c_int()
+    check(lib().b2pt_partition_rows(height, rank, world, band_rows, halo, rows, C.byref(n)))
+    return np.array(rows[:n.value], dtype=np.int64)
 
 
 class Renderer:
@@ -228,65 +261,60 @@ class Renderer:
         check(lib().b2pt_renderer_reset(self.handle))
 
     # -- multi-GPU --------------------------------------------------------------------------------------------
-    def set_partition(self, rank, world, torch=None, dist=None):
-        """This renderer renders only rank's interleaved row bands (b2pt/partition.py). With ReSTIR DI (variant c4) the
-        reservoir planes a reuse pass reads are completed across ranks by an all-gather (torch.distributed) issued from
-        the C side's exchange callback right before that pass."""
-        from . import partition
+    def set_partition(self, rank, world, torch=None, dist=None, dynamic_camera=False):
+        """This renderer renders only rank's interleaved row bands. The exchanges (ReSTIR DI reservoir halos, framebuffer
+        all-gather) are NCCL calls issued from C on the renderer's stream (csrc/b2_comm.cu); torch.distributed only carries the
+        128-byte ncclUniqueId from rank 0 to the other ranks once."""
         self.rank, self.world = rank, world
-        self._exchange_cb = None
-        self.exchange_count = 0
-        cb = C.cast(None, EXCHANGE_FN)
-        if world > 1 and self.variant.startswith("c4"):
+        if world > 1 and getattr(self, "_comm", None) is None:
             if torch is None or dist is None:
-                raise B2ptError("ReSTIR DI on several GPUs needs torch + torch.distributed for the reservoir exchange")
+                raise B2ptError("a partition over several GPUs needs torch + torch.distributed to bootstrap the NCCL communicator")
+            self._comm = Communicator(self.ctx, rank, world, torch, dist)
+        comm = self._comm.handle if world > 1 else None
+        check(lib().b2pt_renderer_set_partition(self.handle, rank, world, comm, int(bool(dynamic_camera))))
 
-            gatherers = {}  # one per reservoir buffer (the render loop ping-pongs between three)
+    @property
+    def exchange_count(self):
+        return self._comm.stats()["exchanges"] if getattr(self, "_comm", None) else 0
 
-            def exchange(user, ptr, nbytes):
-                if ptr not in gatherers:
-                    planes = partition.device_tensor(torch, ptr, (9, self.height, self.width), "<i4")
-                    gatherers[ptr] = partition.RowGatherer(planes, 1, rank, world, dist, torch)
-                gatherers[ptr]()
-                torch.cuda.current_stream().synchronize()
-                self.exchange_count += 1
-
-            self._exchange_cb = cb = EXCHANGE_FN(exchange)
-        check(lib().b2pt_renderer_set_partition(self.handle, rank, world, cb, None))
+    def partition_info(self):
+        cam, own, band, halo = C.c_uint64(), C.c_uint64(), C.c_int(), C.c_int()
+        check(lib().b2pt_renderer_partition_info(self.handle, C.byref(cam), C.byref(own), C.byref(band), C.byref(halo)))
+        return dict(camera_pixels=cam.value, owned_pixels=own.value, band_rows=band.value, halo_rows=halo.value)
 
     def owned_pixels(self):
-        from . import partition
-        return len(partition.owned_rows(self.height, getattr(self, "rank", 0), getattr(self, "world", 1))) * self.width
+        return self.partition_info()["owned_pixels"]
 
     def camera_rays_pixels(self):
         """Pixels CameraRays covers on this rank (ReSTIR DI partitions also fill the halo rows its reuse passes read)."""
-        return self.width * self.height
+        return self.partition_info()["camera_pixels"]
 
     def partition_description(self):
-        return f"interleaved {partition.BAND_ROWS}-row bands, scene replicated" if getattr(self, "world", 1) > 1 else "single GPU"
+        if getattr(self, "world", 1) <= 1:
+            return "single GPU"
+        info = self.partition_info()
+        halo = f", ReSTIR DI halo {info['halo_rows']} rows (CameraRays recomputed, reservoirs by NCCL send/recv)" if info["halo_rows"] else ""
+        return f"interleaved {info['band_rows']}-row bands, scene replicated{halo}, framebuffer ncclAllGather per step, all on the renderer's stream"
 
     def framebuffer_device_pointer(self):
         return _PTR.from_address(self._rd + FRAMEBUFFER_POINTER_OFFSET).value
 
-    def make_gather(self, torch, dist):
-        """Returns gather(): all-gathers the framebuffer bands so every rank holds the whole frame (in place, in the
-        renderer's own framebuffer allocation). Waits for the renderer's stream first; returns the device ms it took."""
-        from . import partition
-        fb = partition.device_tensor(torch, self.framebuffer_device_pointer(), (self.height, self.width, 3), "<f4")
-        rank, world = self.rank, self.world
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def gather_framebuffer(self):
+        check(lib().b2pt_renderer_gather_framebuffer(self.handle))
 
-        gatherer = partition.RowGatherer(fb, 0, rank, world, dist, torch)
-
+    def make_gather(self, torch=None, dist=None):
+        """Returns gather(): all-gathers the framebuffer bands so every rank holds the whole frame (in place). The collective is
+        issued from C on the renderer's stream and counted by last_render_ms(), hence the 0.0 extra milliseconds."""
         def gather():
-            self.synchronize()
-            start.record()
-            gatherer()
-            stop.record()
-            stop.synchronize()
-            return start.elapsed_time(stop)
+            self.gather_framebuffer()
+            return 0.0
 
         return gather
+
+    def set_camera(self, camera52):
+        cam = np.ascontiguousarray(camera52, np.float32)
+        assert cam.size == 52
+        check(lib().b2pt_renderer_set_camera(self.handle, cam.ctypes.data_as(C.POINTER(C.c_float))))
 
     # -- rendering --------------------------------------------------------------------------------------------
     def render(self, samples=1, sync=True):
@@ -356,3 +384,6 @@ class Renderer:
         if self.handle:
             lib().b2pt_renderer_destroy(self.handle)
             self.handle = C.c_void_p()
+        if getattr(self, "_comm", None) is not None:
+            self._comm.close()
+            self._comm = None

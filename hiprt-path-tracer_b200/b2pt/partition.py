@@ -10,10 +10,62 @@ import numpy as np
 BAND_ROWS = 16  # == B2PT_BAND_ROWS in include/b2pt.h (fine bands: 1080 rows / 16 = 67.5 bands keep 8 ranks within 7 % of each other)
 
 
-def owned_rows(height, rank, world):
+RESTIR_BAND_ROWS = 32  # ReSTIR DI partitions: a band is at least as tall as the reuse halo (reuse_radius 16 + search radius 4 + 2)
+
+
+def owned_rows(height, rank, world, band_rows=BAND_ROWS):
     """Row indices (ascending) of the bands rank owns."""
     rows = np.arange(height)
-    return rows[(rows // BAND_ROWS) % world == rank]
+    return rows[(rows // band_rows) % world == rank]
+
+
+def needed_rows(height, rank, world, band_rows, halo):
+    """Rows within `halo` rows of a row rank owns (what CameraRays covers and what the reuse passes may read under a ReSTIR DI
+    partition). Mirrors b2pt_partition_rows of the C layer (csrc/b2_comm.cu); tests/test_partition.py keeps the two in step."""
+    own = np.zeros(height, bool)
+    own[owned_rows(height, rank, world, band_rows)] = True
+    reach = np.zeros(height, bool)
+    for d in range(-halo, halo + 1):
+        lo, hi = max(0, d), min(height, height + d)
+        if lo < hi:
+            reach[lo - d:hi - d] |= own[lo:hi]
+    return np.nonzero(reach)[0]
+
+
+def halo_plan(height, rank, world, band_rows, halo):
+    """{peer: (rows rank sends to peer, rows rank receives from peer)}, ascending -- the halo exchange of csrc/b2_comm.cu."""
+    plan = {}
+    mine = needed_rows(height, rank, world, band_rows, halo)
+    for q in range(world):
+        if q == rank:
+            continue
+        theirs = needed_rows(height, q, world, band_rows, halo)
+        send = theirs[(theirs // band_rows) % world == rank]
+        recv = mine[(mine // band_rows) % world == q]
+        if len(send) or len(recv):
+            plan[q] = (send, recv)
+    return plan
+
+
+def exchange_halo(t, row_dim, rank, world, band_rows, halo, dist, torch):
+    """Completes the halo rows of `t` in place: point-to-point sends / receives between the ranks whose bands touch (the host-logic
+    twin of b2pt_comm_exchange_halo, run under gloo in tests)."""
+    ops, recvs = [], []
+    for q, (send, recv) in sorted(halo_plan(t.shape[row_dim], rank, world, band_rows, halo).items()):
+        if len(send):
+            ops.append(dist.P2POp(dist.isend, t.index_select(row_dim, torch.as_tensor(send, dtype=torch.long)).contiguous(), q))
+        if len(recv):
+            shape = list(t.shape)
+            shape[row_dim] = len(recv)
+            buf = torch.empty(shape, dtype=t.dtype)
+            ops.append(dist.P2POp(dist.irecv, buf, q))
+            recvs.append((recv, buf))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for recv, buf in recvs:
+        t.index_copy_(row_dim, torch.as_tensor(recv, dtype=torch.long), buf)
+    return t
 
 
 def allgather_rows(t, row_dim, rank, world, dist, torch, group=None):

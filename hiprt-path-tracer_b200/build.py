@@ -58,6 +58,7 @@ def kernel_units(feats):
 HOST_UNITS = [
     # (source, object name, extra flags)
     ("b2_capi.cu", "b2_capi.o", []),
+    ("b2_comm.cu", "b2_comm.o", []),
     ("b2_renderer.cpp", "b2_renderer.o", ["-x", "cu"]),
     ("b2_host_scene.cpp", "b2_host_scene.o", ["-x", "cu"]),
     ("b2_bvh_build.cpp", "b2_bvh_build.o", ["-x", "cu"]),
@@ -107,7 +108,7 @@ def build(force=False, jobs=None, verbose=True):
     UNITS = kernel_units(feats) + HOST_UNITS
     with concurrent.futures.ThreadPoolExecutor(max_workers=jobs or min(8, os.cpu_count() or 1)) as pool:
         list(pool.map(lambda u: compile_unit(u, feats, OBJ), UNITS))
-    link = ["nvcc", *ARCH, "-shared", "-Xcompiler", "-fopenmp", "-o", str(OUT), *[str(OBJ / u[1]) for u in UNITS], "-lgomp"]
+    link = ["nvcc", *ARCH, "-shared", "-Xcompiler", "-fopenmp", "-o", str(OUT), *[str(OBJ / u[1]) for u in UNITS], "-lgomp", "-ldl"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

@@ -89,6 +89,8 @@ struct b2pt_kernel
     int light_presampling = 0; /* ReSTIR_DI_DoLightPresampling the kernel was asked for */
 };
 
+int b2_ctx_device(b2pt_ctx* ctx) { return ctx ? ctx->device : 0; }
+
 extern "C" {
 
 const char* b2pt_last_error_string(void) { return g_last_error.c_str(); }
@@ -568,7 +570,13 @@ static int megakernel_form()
 
 int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank, int world, void** args, b2pt_stream stream)
 {
-    if (!kernel || !args || !args[0] || width <= 0 || height <= 0 || world < 1 || rank < 0 || rank >= world)
+    return b2pt_kernel_launch_partition(kernel, width, height, rank, world, B2PT_BAND_ROWS, nullptr, 0, args, stream);
+}
+
+int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int rank, int world, int band_rows, const int* device_rows, int n_rows, void** args,
+                                 b2pt_stream stream)
+{
+    if (!kernel || !args || !args[0] || width <= 0 || height <= 0 || world < 1 || rank < 0 || rank >= world || band_rows < 1 || n_rows < 0 || (device_rows && n_rows > height))
     {
         b2_set_error("b2pt_kernel_launch: invalid argument");
         return B2PT_ERR_INVALID_ARGUMENT;
@@ -589,6 +597,9 @@ int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank
     geom.height = height;
     geom.rank = rank;
     geom.world = world;
+    geom.band_rows = band_rows;
+    geom.row_map = device_rows;
+    geom.row_count = device_rows ? n_rows : 0;
     geom.light_presampling = kernel->light_presampling;
     geom.presampling_parameters = presampling_pass ? args[0] : nullptr;
     geom.directional_masks_ull = nullptr;
@@ -605,13 +616,22 @@ int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank
         geom.directional_radius = *reinterpret_cast<void**>(args[3]);
     }
     geom.persistent = megakernel_form();
+    geom.pool_rays = (rd->world_settings.ambient_light_type == 2 && rd->world_settings.envmap_intensity > 0.0f) ? 5 : 3;
     geom.stack_entries = B2_STACK_ENTRIES;
     {
         /* a traversal pushes at most one entry per level: depth + 1 entries are enough for this tree */
         std::lock_guard<std::mutex> lock(g_bvh_depth_mutex);
         auto it = g_bvh_depth.find(rd->GPU_BVH);
         if (it != g_bvh_depth.end())
+        {
+            if (it->second + 1 > B2_STACK_ENTRIES)
+            {
+                /* a deeper tree would overflow the per-thread traversal stack and silently lose subtrees: refuse the launch */
+                b2_set_error("the BVH is %d levels deep; the traversal stack holds %d entries (B2_STACK_ENTRIES)", it->second, B2_STACK_ENTRIES);
+                return B2PT_ERR_UNSUPPORTED_SCENE;
+            }
             geom.stack_entries = std::max(4, std::min(B2_STACK_ENTRIES, it->second + 1));
+        }
     }
     B2_CUDA(cudaEventRecord(kernel->start, s));
     B2_CUDA(kernel->entry->launch(rd, &geom, s));

@@ -13,6 +13,10 @@ struct B2LaunchGeom
 {
     int width, height;
     int rank, world;
+    int band_rows;      /* interleaved bands of this many rows: band b belongs to rank b % world */
+    const int* row_map; /* device array of row_count frame rows (ascending) this launch covers instead of rank's bands, or null */
+    int row_count;
+    int pool_rays;      /* phased MegaKernel: ray-pool slots per thread (3; 5 when the world has an envmap: its two MIS shadow rays) */
     int stack_entries; /* phased MegaKernel: traversal-stack entries per thread (BVH depth + 1 when known, else B2_STACK_ENTRIES) */
     int light_presampling; /* ReSTIR DI initial candidates: take light candidates from the presampled buffer */
     const void* presampling_parameters; /* ReSTIR_DI_LightsPresampling only: host pointer to its LightPresamplingParameters argument */

@@ -30,7 +30,6 @@
 #define B2_TILE_W 8
 #define B2_TILE_H 8
 #define B2_BLOCK_THREADS (B2_TILE_W * B2_TILE_H)
-#define B2_BAND_ROWS B2PT_BAND_ROWS
 #define B2_WORK_COUNTER_SLOTS 256
 #define B2_MAX_DEVICES 64
 /* phased MegaKernel (default): threads per block and resident blocks per SM it is compiled for (register cap 65536 / (T * N)) */
@@ -56,8 +55,11 @@ static __device__ unsigned int g_faults[B2_FAULT_COUNT];
  * a launch covers the bands of one rank. `local_row` counts the rows of this rank's bands, top to bottom. */
 __device__ __forceinline__ uint32_t b2_global_row(uint32_t local_row, const B2LaunchGeom& g)
 {
-    const uint32_t band_local = local_row / B2_BAND_ROWS;
-    return (band_local * (uint32_t)g.world + (uint32_t)g.rank) * B2_BAND_ROWS + local_row % B2_BAND_ROWS;
+    if (g.row_map != nullptr) /* an explicit list of frame rows (own bands + halo rows): local rows beyond it map outside the frame */
+        return local_row < (uint32_t)g.row_count ? (uint32_t)g.row_map[local_row] : 0xFFFFu;
+    const uint32_t band_rows = (uint32_t)g.band_rows;
+    const uint32_t band_local = local_row / band_rows;
+    return (band_local * (uint32_t)g.world + (uint32_t)g.rank) * band_rows + local_row % band_rows;
 }
 
 __device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd, uint64_t* stacks, B2TraversalCounters* counters, unsigned int* faults, int threads = B2_BLOCK_THREADS)
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(B2_MKP_THREADS, B2_MKP_MIN_BLOCKS) megakernel_
  * A path's arithmetic, RNG draws and results are the same as in the other two forms; tests/ run all three against the same
  * fixtures and against each other (bit-identical frames).
  */
-#define B2_POOL_RAYS 3
+#define B2_POOL_RAYS 5 /* main, deferred X, deferred Y, envmap light ray, envmap BSDF ray */
 #ifndef B2_POOL_REFILL_MIN
 #define B2_POOL_REFILL_MIN 1
 #endif
@@ -268,50 +270,66 @@ struct B2RayPool
     int* next;       /* [2]: drain cursor, by phase parity */
 };
 
-/* All threads of the block call this the same number of times. rays[k].kind == B2_RAY_NONE: no k-th ray from this thread
- * (it still helps draining). results[k].prim = -1 for rays that were not asked for. */
-template <int N>
-__device__ __forceinline__ int b2_trace_pooled(const Ctx& ctx, const B2RayPool& pool, unsigned int& phase, const RayRequest (&rays)[N], B2Hit (&results)[N],
-                                               B2TraversalCounters* counters, int stack_entries, int vote = 0)
+/* A trace of the block's pooled rays is three steps, each called by ALL threads of the block the same number of times:
+ *   b2_pool_deposit : every thread drops its rays of this phase into the pool (warp-aggregated slot allocation)
+ *   b2_pool_drain   : barrier (which also carries the caller's block-wide vote), then one converged loop of traversal steps
+ *                     over all rays of the block, barrier
+ *   b2_pool_results : every thread reads the hits of the rays it deposited (prim = -1 for rays it did not ask for)
+ * Deposit and drain are separate so that the rays a bounce ends with go straight from the shading code into shared memory
+ * instead of living in registers across the top of the path loop (5 rays = 45 registers of a 128-register budget). `phase`
+ * counts traces; its parity picks one of two counter pairs so that a deposit can reset the other pair without a barrier. */
+__device__ __forceinline__ unsigned int b2_pool_deposit_one(const Ctx& ctx, const B2RayPool& pool, int pc, int k, const RayRequest& ray)
 {
-    static_assert(N <= B2_POOL_RAYS, "pool slots per thread");
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lanes_below = (1u << lane) - 1u;
-    const int pc = (int)(phase & 1u);
-    phase++;
+    /* skip_prim shares a word with the any-hit flag: prim ids are < 2^30 */
+    const bool have = ray.kind != B2_RAY_NONE && ctx.bvh.node_count != 0;
+    const unsigned int havers = __ballot_sync(0xFFFFFFFFu, have);
+    if (havers == 0u)
+        return 0u;
+    int base = 0;
+    if (lane == 0)
+        base = atomicAdd(&pool.count[pc], __popc(havers));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (have)
+    {
+        const int slot = k * (int)blockDim.x + (int)threadIdx.x;
+        pool.list[base + __popc(havers & lanes_below)] = slot;
+        pool.slot_a[slot] = make_float4(ray.origin.x, ray.origin.y, ray.origin.z, ray.t_max);
+        pool.slot_b[slot] = make_float4(ray.direction.x, ray.direction.y, ray.direction.z, __int_as_float((ray.skip_prim << 1) | (ray.kind == B2_RAY_ANY_HIT ? 1 : 0)));
+    }
+    return have ? (1u << k) : 0u;
+}
 
-    /* deposit (warp-aggregated slot allocation); skip_prim shares a word with the any-hit flag: prim ids are < 2^30 */
-    bool have[N];
+/* `active_rays` (block-uniform): rays[k] with k >= active_rays are never requested in this launch (no envmap in the world) */
+template <int N>
+__device__ __forceinline__ unsigned int b2_pool_deposit(const Ctx& ctx, const B2RayPool& pool, unsigned int phase, const RayRequest (&rays)[N], int active_rays = N)
+{
+    static_assert(N <= B2_POOL_RAYS, "pool slots per thread");
+    const int pc = (int)(phase & 1u);
+    unsigned int have_mask = 0u;
 #pragma unroll
     for (int k = 0; k < N; k++)
-    {
-        have[k] = rays[k].kind != B2_RAY_NONE && ctx.bvh.node_count != 0;
-        const unsigned int havers = __ballot_sync(0xFFFFFFFFu, have[k]);
-        if (havers == 0u)
-            continue;
-        int base = 0;
-        if (lane == 0)
-            base = atomicAdd(&pool.count[pc], __popc(havers));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (have[k])
-        {
-            const int slot = k * (int)blockDim.x + (int)threadIdx.x;
-            pool.list[base + __popc(havers & lanes_below)] = slot;
-            pool.slot_a[slot] = make_float4(rays[k].origin.x, rays[k].origin.y, rays[k].origin.z, rays[k].t_max);
-            pool.slot_b[slot] = make_float4(rays[k].direction.x, rays[k].direction.y, rays[k].direction.z,
-                                            __int_as_float((rays[k].skip_prim << 1) | (rays[k].kind == B2_RAY_ANY_HIT ? 1 : 0)));
-        }
-    }
+        if (k < active_rays)
+            have_mask |= b2_pool_deposit_one(ctx, pool, pc, k, rays[k]);
     if (threadIdx.x == 0)
     {
         /* the other parity's counters are idle during this phase: reset them for the next one */
         pool.count[pc ^ 1] = 0;
         pool.next[pc ^ 1] = 0;
     }
+    return have_mask;
+}
+
+__device__ __forceinline__ int b2_pool_drain(const Ctx& ctx, const B2RayPool& pool, unsigned int phase, B2TraversalCounters* counters, int stack_entries, int vote = 0)
+{
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int lanes_below = (1u << lane) - 1u;
+    const int pc = (int)(phase & 1u);
     /* the barrier between deposit and drain also carries the caller's block-wide vote (returned) */
     const int block_vote = __syncthreads_or(vote);
 
-    /* drain: one converged loop of traversal steps over all rays of the block */
+    /* one converged loop of traversal steps over all rays of the block */
     const int count = pool.count[pc];
     B2Traversal t;
     bool busy = false;
@@ -366,7 +384,12 @@ __device__ __forceinline__ int b2_trace_pooled(const Ctx& ctx, const B2RayPool& 
         }
     }
     __syncthreads();
+    return block_vote;
+}
 
+template <int N>
+__device__ __forceinline__ void b2_pool_results(const B2RayPool& pool, unsigned int have_mask, B2Hit (&results)[N])
+{
 #pragma unroll
     for (int k = 0; k < N; k++)
     {
@@ -374,7 +397,7 @@ __device__ __forceinline__ int b2_trace_pooled(const Ctx& ctx, const B2RayPool& 
         results[k].u = results[k].v = 0.0f;
         results[k].prim = -1;
         results[k].ng = v3(0.0f);
-        if (have[k])
+        if (have_mask & (1u << k))
         {
             const int own = k * (int)blockDim.x + (int)threadIdx.x;
             const float4 a = pool.slot_a[own], b = pool.slot_b[own];
@@ -385,14 +408,13 @@ __device__ __forceinline__ int b2_trace_pooled(const Ctx& ctx, const B2RayPool& 
             results[k].ng = v3(b.x, b.y, b.z);
         }
     }
-    return block_vote;
 }
 
 /* shared memory of a phased block for a traversal stack of `entries` entries per thread: the stack is sized by the depth of the
  * BVH at hand (Cornell: 9 entries = 36 KB instead of 96 KB), which leaves more of the SM's 256 KB to the L1 that backs the
  * path state in local memory */
-#define B2_PH_SMEM_BYTES_FOR(entries) ((entries) * B2_MK_THREADS * 8 + (B2_MK_THREADS / 32) * B2_QUEUE_SLOTS * 4 + B2_POOL_RAYS * B2_MK_THREADS * (2 * 16 + 4) + 16)
-#define B2_PH_SMEM_BYTES B2_PH_SMEM_BYTES_FOR(B2_STACK_ENTRIES)
+#define B2_PH_SMEM_BYTES_FOR(entries, pool_rays) ((entries) * B2_MK_THREADS * 8 + (B2_MK_THREADS / 32) * B2_QUEUE_SLOTS * 4 + (pool_rays) * B2_MK_THREADS * (2 * 16 + 4) + 16)
+#define B2_PH_SMEM_BYTES B2_PH_SMEM_BYTES_FOR(B2_STACK_ENTRIES, B2_POOL_RAYS)
 
 template <class V>
 __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_phased(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x,
@@ -402,10 +424,12 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
     uint64_t* stacks = reinterpret_cast<uint64_t*>(smem);
     B2RayPool pool;
     const int stack_entries = geom.stack_entries;
+    /* rays per thread of a trace: 3 (main + the two NEE rays), 5 when the world has an envmap (its two MIS shadow rays) */
+    const int pool_rays = geom.pool_rays;
     pool.slot_a = reinterpret_cast<float4*>(smem + stack_entries * B2_MK_THREADS * 8);
-    pool.slot_b = pool.slot_a + B2_POOL_RAYS * B2_MK_THREADS;
-    pool.list = reinterpret_cast<int*>(pool.slot_b + B2_POOL_RAYS * B2_MK_THREADS);
-    uint32_t* queues = reinterpret_cast<uint32_t*>(pool.list + B2_POOL_RAYS * B2_MK_THREADS);
+    pool.slot_b = pool.slot_a + pool_rays * B2_MK_THREADS;
+    pool.list = reinterpret_cast<int*>(pool.slot_b + pool_rays * B2_MK_THREADS);
+    uint32_t* queues = reinterpret_cast<uint32_t*>(pool.list + pool_rays * B2_MK_THREADS);
     pool.count = reinterpret_cast<int*>(queues + (B2_MK_THREADS / 32) * B2_QUEUE_SLOTS);
     pool.next = pool.count + 2;
     if (threadIdx.x < 4)
@@ -426,10 +450,9 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
     PathState s;
     BouncePhase<V> ph;
     ph.reset();
-    RayRequest rays[3]; /* [0] next main ray, [1] deferred X, [2] deferred Y */
-    request_none(rays[0]);
-    request_none(rays[1]);
-    request_none(rays[2]);
+    /* rays of the NEXT trace A this thread has in the pool: bit 0 next main ray, 1 deferred X, 2 deferred Y, 3 envmap light ray,
+     * 4 envmap BSDF ray (deposited at the end of the previous iteration, straight from stage 2) */
+    unsigned int have_a = 0u;
     unsigned int phase = 0;
     bool alive = false;
     /* warp-uniform */
@@ -479,10 +502,9 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
                 const uint32_t packed = queue[(q_head + r) % B2_QUEUE_SLOTS];
                 alive = megakernel_begin<V>(ctx, packed & 0xFFFFu, packed >> 16, s);
                 ph.reset();
-                /* bounce 0 starts from the G-buffer hit: no main ray, nothing deferred */
-                request_none(rays[0]);
-                request_none(rays[1]);
-                request_none(rays[2]);
+                /* bounce 0 starts from the G-buffer hit: no main ray, nothing deferred (a lane is only refilled after its previous
+                 * path ended, and a path never ends with rays in the pool) */
+                have_a = 0u;
             }
         }
         {
@@ -492,39 +514,30 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
         }
         __syncwarp();
 
-        /* trace A: main ray + the previous vertex's deferred rays; its first barrier also votes "any live path in the block?" */
-        B2Hit results[3];
-        int any_alive;
-        if (Nee<V>::HAS_DEFERRED_Y)
-            any_alive = b2_trace_pooled<3>(ctx, pool, phase, rays, results, counters, stack_entries, alive ? 1 : 0);
-        else
-        {
-            RayRequest two[2] = { rays[0], rays[1] };
-            B2Hit two_results[2];
-            any_alive = b2_trace_pooled<2>(ctx, pool, phase, two, two_results, counters, stack_entries, alive ? 1 : 0);
-            results[0] = two_results[0];
-            results[1] = two_results[1];
-            results[2].t = -1.0f;
-            results[2].u = results[2].v = 0.0f;
-            results[2].prim = -1;
-            results[2].ng = v3(0.0f);
-        }
+        /* trace A: main ray + the previous vertex's deferred rays (already in the pool); its first barrier also votes "any live
+         * path in the block?" */
+        B2Hit results[5];
+        const int any_alive = b2_pool_drain(ctx, pool, phase, counters, stack_entries, alive ? 1 : 0);
+        phase++;
         if (!any_alive)
         {
-            /* no live path in the whole block: every warp ran out of work, or the fetched tiles held no hit pixel */
+            /* no live path in the whole block (so the pool was empty): every warp ran out of work, or the fetched tiles held no hit
+             * pixel. The deposit that would have reset the other parity's counters is replayed empty. */
+            RayRequest none[1];
+            request_none(none[0]);
             if (__syncthreads_and((exhausted && q_count == 0) ? 1 : 0))
                 break;
+            b2_pool_deposit<1>(ctx, pool, phase, none);
             continue;
         }
-        request_none(rays[0]);
-        request_none(rays[1]);
-        request_none(rays[2]);
+        b2_pool_results<5>(pool, have_a, results);
+        have_a = 0u;
 
         RayRequest sequential[1];
         request_none(sequential[0]);
         if (alive)
         {
-            if (!megakernel_stage1<V>(ctx, s, ph, s.payload.bounce > 0 ? &results[0] : nullptr, results[1], results[2], sequential[0]))
+            if (!megakernel_stage1<V>(ctx, s, ph, s.payload.bounce > 0 ? &results[0] : nullptr, results[1], results[2], results[3], results[4], sequential[0]))
             {
                 megakernel_end(ctx, s);
                 alive = false;
@@ -539,19 +552,32 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
         sequential_result[0].prim = -1;
         sequential_result[0].ng = v3(0.0f);
         if (Nee<V>::HAS_SEQUENTIAL_RAY)
-            b2_trace_pooled<1>(ctx, pool, phase, sequential, sequential_result, counters, stack_entries);
+        {
+            const unsigned int have_b = b2_pool_deposit<1>(ctx, pool, phase, sequential);
+            b2_pool_drain(ctx, pool, phase, counters, stack_entries);
+            phase++;
+            b2_pool_results<1>(pool, have_b, sequential_result);
+        }
 
+        /* stage 2 ends with the rays of the next trace A: they go straight into the pool */
+        RayRequest rays[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+            request_none(rays[k]);
         if (alive)
         {
-            if (!megakernel_stage2<V>(ctx, s, ph, sequential_result[0], rays[0], rays[1], rays[2]))
+            if (!megakernel_stage2<V>(ctx, s, ph, sequential_result[0], rays[0], rays[1], rays[2], rays[3], rays[4]))
             {
                 megakernel_end(ctx, s);
                 alive = false;
-                request_none(rays[0]);
-                request_none(rays[1]);
-                request_none(rays[2]);
+#pragma unroll
+                for (int k = 0; k < 5; k++)
+                    request_none(rays[k]);
             }
         }
+        if (!Nee<V>::HAS_DEFERRED_Y)
+            request_none(rays[2]);
+        have_a = b2_pool_deposit<5>(ctx, pool, phase, rays, pool_rays);
     }
 
     if (V::COUNTERS)
@@ -576,9 +602,11 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) directional_reuse_kernel(con
 
 static int owned_rows(int height, const B2LaunchGeom& g)
 {
+    if (g.row_map != nullptr)
+        return g.row_count;
     int rows = 0;
-    for (int band = g.rank; band * B2_BAND_ROWS < height; band += g.world)
-        rows += (height - band * B2_BAND_ROWS) < B2_BAND_ROWS ? (height - band * B2_BAND_ROWS) : B2_BAND_ROWS;
+    for (int band = g.rank; band * g.band_rows < height; band += g.world)
+        rows += (height - band * g.band_rows) < g.band_rows ? (height - band * g.band_rows) : g.band_rows;
     return rows;
 }
 
@@ -649,7 +677,7 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
             return e;
         const unsigned int total_tiles = (unsigned int)tiles_x * (unsigned int)((rows + 3) / 4);
         if (g.persistent == 2)
-            megakernel_phased<V><<<pd.sm_count * pd.blocks_per_sm[1], B2_MK_THREADS, B2_PH_SMEM_BYTES_FOR(g.stack_entries), stream>>>(*rd, g, tiles_x, total_tiles, counter);
+            megakernel_phased<V><<<pd.sm_count * pd.blocks_per_sm[1], B2_MK_THREADS, B2_PH_SMEM_BYTES_FOR(g.stack_entries, g.pool_rays), stream>>>(*rd, g, tiles_x, total_tiles, counter);
         else
             megakernel_persistent<V><<<pd.sm_count * pd.blocks_per_sm[0], B2_MKP_THREADS, 0, stream>>>(*rd, g, tiles_x, total_tiles, counter);
         return cudaGetLastError();

@@ -347,4 +347,99 @@ struct Nee
     }
 };
 
+/* ---- envmap NEE cut at its rays (sample_environment_map, b2_envmap.h / Envmap.h:170-274) -------------------------------------
+ * The reference traces two shadow rays in the middle of the envmap MIS estimator: one towards the envmap sample, one along a
+ * BSDF sample; each only decides whether an already determined contribution counts. Here both contributions are computed as if
+ * visible (bsdf_eval is pure; the reference skips it when the sample is occluded, and the occluded value is discarded here),
+ * the two rays are handed back as deferred any-hit rays that ride with the next main ray in the block's ray pool, and
+ * EnvmapNee::resolve adds what turned out visible one trace later -- same arithmetic, same RNG draws in the same order.
+ * (In round 1 these two rays were traced in place by every lane on its own: on the 10M-triangle ReSTIR DI + envmap workload
+ * that was the larger part of the MegaKernel, profiles/r02_ncu_c4s.md.) */
+struct EnvmapNee
+{
+    Rgb light_part, bsdf_part; /* envmap_mis_contribution / bsdf_mis_contribution IF their rays come back unoccluded */
+    bool have_light_ray, have_bsdf_ray;
+
+    B2_HD void reset()
+    {
+        light_part = bsdf_part = rgb(0.0f);
+        have_light_ray = have_bsdf_ray = false;
+    }
+
+    template <class V>
+    B2_HD void sample(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, RayRequest& light_ray, RayRequest& bsdf_ray)
+    {
+        reset();
+        request_none(light_ray);
+        request_none(bsdf_ray);
+        const b2pt_render_data& rd = *ctx.rd;
+        const b2pt_world_settings& ws = rd.world_settings;
+        /* sample_environment_map's early-outs */
+        if (ws.ambient_light_type != 2 || rd.bsdfs_data.white_furnace_mode)
+            return;
+        if (ws.envmap_intensity <= 0.0f)
+            return;
+        if (payload.bounce == 0 && V::DIRECT == B2_LSS_RESTIR_DI)
+            return;
+        if constexpr (V::ENVMAP != B2_ESS_NONE)
+        {
+            /* sample_environment_map_with_mis */
+            float envmap_pdf;
+            V3 sampled_direction;
+            Rgb envmap_color = envmap_sample<V>(ws, sampled_direction, envmap_pdf, rng);
+            if (can_do_light_sampling(payload.material))
+            {
+                float cosine_term = dot(hit.shading_normal, sampled_direction);
+                if (envmap_pdf > 0.0f && cosine_term > 0.0f)
+                {
+                    float bsdf_pdf_value;
+                    int incident_light_info = B2_LOBE_NO_INFO;
+                    BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, sampled_direction, &incident_light_info, &payload.volume_state,
+                                                 false, &payload.material, payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
+                    Rgb bsdf_color = bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
+                    float mis_weight = balance_heuristic(envmap_pdf, bsdf_pdf_value);
+                    light_part = bsdf_color * cosine_term * mis_weight * envmap_color / envmap_pdf / 1.0f;
+                    /* exactly zero only: anything else (NaN included) must still be switched off by an occluded ray */
+                    if (!(light_part.r == 0.0f && light_part.g == 0.0f && light_part.b == 0.0f))
+                    {
+                        have_light_ray = true;
+                        request_shadow(light_ray, hit.inter_point, sampled_direction, 1.0e35f, hit.primitive_index);
+                    }
+                }
+            }
+
+            float bsdf_sample_pdf;
+            V3 bsdf_sampled_dir;
+            int incident_light_info = B2_LOBE_NO_INFO;
+            BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, v3(0.0f), &incident_light_info, &payload.volume_state, false,
+                                         &payload.material, payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
+            Rgb bsdf_color = bsdf_sample<V>(rd, bctx, bsdf_sampled_dir, bsdf_sample_pdf, rng);
+            float cosine_term = fabsf(dot(hit.shading_normal, bsdf_sampled_dir));
+            if (bsdf_sample_pdf > 0.0f)
+            {
+                float envmap_eval_pdf;
+                Rgb envmap_radiance = envmap_eval<V>(ws, bsdf_sampled_dir, envmap_eval_pdf);
+                if (envmap_eval_pdf > 0.0f)
+                {
+                    float mis_weight = balance_heuristic(bsdf_sample_pdf, envmap_eval_pdf);
+                    bsdf_part = envmap_radiance * mis_weight * cosine_term * bsdf_color / bsdf_sample_pdf;
+                    if (!(bsdf_part.r == 0.0f && bsdf_part.g == 0.0f && bsdf_part.b == 0.0f))
+                    {
+                        have_bsdf_ray = true;
+                        request_shadow(bsdf_ray, hit.inter_point, bsdf_sampled_dir, 1.0e35f, hit.primitive_index);
+                    }
+                }
+            }
+        }
+    }
+
+    /* sample_environment_map's value: bsdf_mis_contribution + envmap_mis_contribution */
+    B2_HD Rgb resolve(const B2Hit& light_result, const B2Hit& bsdf_result) const
+    {
+        Rgb envmap_mis_contribution = (have_light_ray && light_result.prim >= 0) ? rgb(0.0f) : light_part;
+        Rgb bsdf_mis_contribution = (have_bsdf_ray && bsdf_result.prim >= 0) ? rgb(0.0f) : bsdf_part;
+        return bsdf_mis_contribution + envmap_mis_contribution;
+    }
+};
+
 #endif

@@ -628,7 +628,7 @@ B2_HD void megakernel_primary_miss(const Ctx& ctx, uint32_t x, uint32_t y, uint3
 
 /* ---- the bounce cut at its rays (b2_nee.h) for the phased MegaKernel -----------------------------------------------------
  * One iteration of a path:
- *     trace A: [main ray, deferred X, deferred Y of the previous vertex]
+ *     trace A: [main ray, deferred X, deferred Y, envmap light ray, envmap BSDF ray of the previous vertex]
  *     stage 1: resolve the previous vertex's NEE; end the path if it has no main ray; take the main hit; NEE begin
  *     trace B: [sequential ray]                       (only variants with RIS)
  *     stage 2: rest of the NEE sampling -> deferred X / Y; envmap NEE; next direction -> main ray
@@ -641,7 +641,8 @@ struct BouncePhase
     bool nee_on;
     /* a vertex whose NEE waits for its deferred rays */
     bool pending;
-    Rgb pending_throughput, pending_envmap, pending_material_emission, pending_self_emission;
+    Rgb pending_throughput, pending_material_emission, pending_self_emission;
+    EnvmapNee envmap; /* the vertex's envmap NEE, waiting for its two deferred shadow rays like `nee` for its own */
     int pending_bounce;
     /* the path has no next main ray: it ends as soon as its pending NEE is resolved */
     bool ending;
@@ -656,7 +657,8 @@ struct BouncePhase
 
 /* Returns false when the path ended here. `main_hit`: closest hit of the main ray when bounce > 0 (null = trace here). */
 template <class V>
-B2_HD bool megakernel_stage1(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, const B2Hit* main_hit, const B2Hit& result_x, const B2Hit& result_y, RayRequest& sequential_ray)
+B2_HD bool megakernel_stage1(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, const B2Hit* main_hit, const B2Hit& result_x, const B2Hit& result_y, const B2Hit& result_env_light,
+                             const B2Hit& result_env_bsdf, RayRequest& sequential_ray)
 {
     const b2pt_render_data& rd = *ctx.rd;
     Payload& payload = s.payload;
@@ -670,7 +672,8 @@ B2_HD bool megakernel_stage1(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, c
         Rgb emissive_contribution = rgb(0.0f);
         if (ph.nee.active)
             emissive_contribution = ph.nee.resolve(rd, hit.shading_normal, result_x, result_y) / 1.0f + ph.pending_self_emission;
-        payload.ray_color += direct_lighting_combine<V>(rd, emissive_contribution, ph.pending_envmap, ph.pending_throughput, ph.pending_bounce, ph.pending_material_emission);
+        payload.ray_color += direct_lighting_combine<V>(rd, emissive_contribution, ph.envmap.resolve(result_env_light, result_env_bsdf), ph.pending_throughput, ph.pending_bounce,
+                                                        ph.pending_material_emission);
         sanity_check(rd, payload.ray_color, s.x, s.y);
         ph.pending = false;
     }
@@ -701,17 +704,20 @@ B2_HD bool megakernel_stage1(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, c
 
 /* Returns false when the path ended here (no next main ray and nothing pending). */
 template <class V>
-B2_HD bool megakernel_stage2(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, const B2Hit& sequential_result, RayRequest& main_ray, RayRequest& deferred_x, RayRequest& deferred_y)
+B2_HD bool megakernel_stage2(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, const B2Hit& sequential_result, RayRequest& main_ray, RayRequest& deferred_x, RayRequest& deferred_y,
+                             RayRequest& env_light_ray, RayRequest& env_bsdf_ray)
 {
     Payload& payload = s.payload;
     HitInfo& hit = s.hit;
     request_none(main_ray);
     request_none(deferred_x);
     request_none(deferred_y);
+    request_none(env_light_ray);
+    request_none(env_bsdf_ray);
     if (ph.nee_on)
     {
         ph.nee.finish_sampling(ctx, payload, hit, -s.ray_direction, s.rng, s.x, s.y, sequential_result, deferred_x, deferred_y);
-        ph.pending_envmap = sample_environment_map<V>(ctx, payload, hit, -s.ray_direction, s.rng);
+        ph.envmap.template sample<V>(ctx, payload, hit, -s.ray_direction, s.rng, env_light_ray, env_bsdf_ray);
         ph.pending_throughput = payload.throughput;
         ph.pending_bounce = payload.bounce;
         ph.pending_material_emission = payload.material.emission;

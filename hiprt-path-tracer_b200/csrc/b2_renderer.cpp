@@ -8,6 +8,7 @@
  */
 #include "b2pt.h"
 
+#include "b2_comm.h"
 #include "b2_frame_loop.h"
 #include "b2_host_scene.h"
 #include "b2_material.h"
@@ -86,9 +87,13 @@ struct b2pt_renderer
     uint64_t pass_launches[B2_PASS_COUNT] = {};
     /* multi-GPU: this renderer owns the interleaved B2PT_BAND_ROWS-row bands `rank`, rank + world, ... of the frame */
     int rank = 0, world = 1;
-    b2pt_exchange_fn exchange = nullptr;
-    void* exchange_user = nullptr;
-    uint64_t exchanges = 0;
+    b2pt_comm* comm = nullptr;      /* not owned */
+    int band_rows = B2PT_BAND_ROWS; /* 32 for the ReSTIR DI variants: a band must be at least as tall as the halo */
+    bool dynamic_camera = false;
+    int halo_rows = 0;              /* halo the camera-row list below was built for */
+    int* d_camera_rows = nullptr;   /* own bands + halo rows (ReSTIR DI partitions): what CameraRays covers */
+    int camera_row_count = 0;
+    int owned_row_count = 0;
     uint8_t* d_status = nullptr; /* [0] still_one_ray_active, [4..7] pixel_count_converged_so_far */
     void* d_reservoirs[3] = {};
 
@@ -233,6 +238,37 @@ void invalidate_scene(b2pt_renderer* r)
         b2pt_bvh_destroy(r->ctx, r->bvh);
         r->bvh = nullptr;
     }
+}
+
+/* (Re)builds the list of rows CameraRays covers under a ReSTIR DI partition: this rank's bands plus `halo` rows around them,
+ * halo = how far a reuse pass looks (fused pass: spatial neighbours around the temporal neighbour). */
+int update_partition_rows(b2pt_renderer* r)
+{
+    const b2pt_restir_di_settings& di = r->loop.rd.render_settings.restir_di_settings;
+    int halo = di.common_spatial_pass.reuse_radius + di.common_temporal_pass.neighbor_search_radius + 2;
+    if (r->dynamic_camera)
+        halo = r->height; /* a reprojected temporal neighbour can be anywhere */
+    if (halo > r->band_rows && halo < r->height)
+    {
+        b2_set_error("ReSTIR DI partition: reuse radius %d needs a halo of %d rows, more than the %d-row bands", di.common_spatial_pass.reuse_radius, halo, r->band_rows);
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    if (r->d_camera_rows && halo == r->halo_rows)
+        return B2PT_OK;
+    const std::vector<int> rows = b2_partition_rows(r->height, r->rank, r->world, r->band_rows, halo);
+    if (r->d_camera_rows)
+    {
+        B2_TRY(b2pt_stream_synchronize(r->ctx, r->stream));
+        b2pt_free(r->ctx, r->d_camera_rows);
+        r->d_camera_rows = nullptr;
+    }
+    void* d = nullptr;
+    B2_TRY(b2pt_malloc(r->ctx, rows.size() * sizeof(int), &d));
+    B2_TRY(b2pt_memcpy_h2d(r->ctx, d, rows.data(), rows.size() * sizeof(int), nullptr));
+    r->d_camera_rows = (int*)d;
+    r->camera_row_count = (int)rows.size();
+    r->halo_rows = halo;
+    return B2PT_OK;
 }
 
 int upload_scene(b2pt_renderer* r)
@@ -417,6 +453,8 @@ int b2pt_renderer_destroy(b2pt_renderer* r)
     for (int pass = 0; pass < B2_PASS_COUNT; pass++)
         if (r->kernels[pass])
             b2pt_kernel_destroy(r->kernels[pass]);
+    if (r->d_camera_rows)
+        b2pt_free(r->ctx, r->d_camera_rows);
     free_all(r, r->frame_allocs);
     free_all(r, r->scene_allocs);
     free_all(r, r->envmap_allocs);
@@ -688,39 +726,39 @@ int b2pt_renderer_render(b2pt_renderer* r, int samples)
             rc = B2PT_ERR_NO_VARIANT;
             return;
         }
-        int rank = r->rank, world = r->world;
-        if (world > 1 && r->loop.restir_di)
+        const int* launch_rows = nullptr;
+        int launch_row_count = 0;
+        if (r->world > 1 && r->loop.restir_di)
         {
             const b2pt_restir_di_settings& di = r->loop.rd.render_settings.restir_di_settings;
-            /* The reuse passes read reservoirs AND G-buffer entries of neighbouring pixels, which may belong to another
-             * GPU. G-buffer: every rank runs CameraRays over the whole frame (same seeds => same bytes; cheaper than
-             * exchanging 132 B/px). Reservoirs: the buffer a pass reads around a pixel is completed across ranks
-             * (all-gather of the owned rows, 36 B/px) right before that pass. */
+            /* The reuse passes read reservoirs AND G-buffer entries of neighbouring pixels, which may belong to another GPU.
+             * G-buffer: CameraRays also renders the halo rows around this rank's bands (same seeds => same bytes as on their
+             * owner; cheaper than exchanging 132 B/px). Reservoirs: the halo rows of the buffer a pass reads around a pixel are
+             * fetched from their owners (36 B/px, NCCL send / recv on this stream) right before that pass. */
+            rc = update_partition_rows(r);
+            if (rc != B2PT_OK)
+                return;
             if (pass == B2_PASS_CAMERA_RAYS)
             {
-                rank = 0;
-                world = 1;
+                launch_rows = r->d_camera_rows;
+                launch_row_count = r->camera_row_count;
             }
             void* needs = nullptr;
-            if (pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL)
-                needs = di.temporal_pass.input_reservoirs;
+            if (pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL || pass == B2_PASS_RESTIR_DI_TEMPORAL)
+                needs = di.temporal_pass.input_reservoirs; /* reprojection + its neighbour search, and the fused pass's spatial neighbours */
             else if (pass == B2_PASS_RESTIR_DI_SPATIAL)
                 needs = di.spatial_pass.input_reservoirs;
-            else if (pass == B2_PASS_RESTIR_DI_TEMPORAL && std::memcmp(&r->loop.rd.prev_camera, &r->loop.rd.current_camera, sizeof(b2pt_camera)) != 0)
-                needs = di.temporal_pass.input_reservoirs; /* reprojection reads other pixels only when the camera moved */
             if (needs)
             {
-                if (!r->exchange)
+                if (!r->comm)
                 {
-                    b2_set_error("ReSTIR DI on %d GPUs needs the reservoir exchange callback (b2pt_renderer_set_partition)", world);
+                    b2_set_error("ReSTIR DI on %d GPUs needs a communicator (b2pt_renderer_set_partition)", r->world);
                     rc = B2PT_ERR_INVALID_ARGUMENT;
                     return;
                 }
-                rc = b2pt_stream_synchronize(r->ctx, r->stream);
+                rc = b2pt_comm_exchange_halo(r->comm, needs, 9, r->pixels() * 4, (size_t)r->width * 4, r->height, r->band_rows, r->halo_rows, r->stream);
                 if (rc != B2PT_OK)
                     return;
-                r->exchange(r->exchange_user, needs, (uint64_t)r->pixels() * 36u);
-                r->exchanges++;
             }
         }
         /* LightPresamplingParameters as the reference's pass fills it (ReSTIRDIRenderPass.cpp:417-444) */
@@ -745,7 +783,7 @@ int b2pt_renderer_render(b2pt_renderer* r, int samples)
             args[2] = &masks_ull;
             args[3] = &radius;
         }
-        rc = b2pt_kernel_launch_rows(k, r->width, r->height, rank, world, args, r->stream);
+        rc = b2pt_kernel_launch_partition(k, r->width, r->height, r->rank, r->world, r->band_rows, launch_rows, launch_row_count, args, r->stream);
         r->pass_launches[pass]++;
         if (rc == B2PT_OK && r->profile_passes)
         {
@@ -765,13 +803,69 @@ int b2pt_renderer_render(b2pt_renderer* r, int samples)
 }
 
 /* Multi-GPU partition of the frame: interleaved row bands, scene replicated. */
-int b2pt_renderer_set_partition(b2pt_renderer* r, int rank, int world, b2pt_exchange_fn exchange, void* user)
+int b2pt_renderer_set_partition(b2pt_renderer* r, int rank, int world, b2pt_comm* comm, int dynamic_camera)
 {
     if (!r || world < 1 || rank < 0 || rank >= world) { b2_set_error("b2pt_renderer_set_partition: invalid argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    if (comm && (b2_comm_rank(comm) != rank || b2_comm_world(comm) != world))
+    {
+        b2_set_error("b2pt_renderer_set_partition: the communicator is rank %d of %d, not %d of %d", b2_comm_rank(comm), b2_comm_world(comm), rank, world);
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
+    B2_TRY(b2pt_stream_synchronize(r->ctx, r->stream));
     r->rank = rank;
     r->world = world;
-    r->exchange = exchange;
-    r->exchange_user = user;
+    r->comm = comm;
+    r->dynamic_camera = dynamic_camera != 0;
+    r->band_rows = r->loop.restir_di ? 32 : B2PT_BAND_ROWS;
+    if (r->d_camera_rows)
+    {
+        b2pt_free(r->ctx, r->d_camera_rows);
+        r->d_camera_rows = nullptr;
+    }
+    r->camera_row_count = 0;
+    r->halo_rows = 0;
+    r->owned_row_count = (int)b2_partition_rows(r->height, rank, world, r->band_rows, 0).size();
+    return B2PT_OK;
+}
+
+int b2pt_renderer_gather_framebuffer(b2pt_renderer* r)
+{
+    if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    if (r->world == 1)
+        return B2PT_OK;
+    if (!r->comm) { b2_set_error("b2pt_renderer_gather_framebuffer: no communicator (b2pt_renderer_set_partition)"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
+    B2_TRY(b2pt_comm_allgather_rows(r->comm, r->loop.rd.buffers.accumulated_ray_colors, 1, r->pixels() * 12, (size_t)r->width * 12, r->height, r->band_rows, r->stream));
+    /* the step's device time = render + gather: the stop event moves behind the gather */
+    return b2pt_event_record(r->ctx, r->ev_stop, r->stream);
+}
+
+int b2pt_renderer_partition_info(b2pt_renderer* r, uint64_t* out_camera_pixels, uint64_t* out_owned_pixels, int* out_band_rows, int* out_halo_rows)
+{
+    if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    const bool halo_partition = r->world > 1 && r->loop.restir_di;
+    if (halo_partition)
+        B2_TRY(update_partition_rows(r));
+    const int owned = r->world > 1 ? r->owned_row_count : r->height;
+    if (out_owned_pixels) *out_owned_pixels = (uint64_t)owned * r->width;
+    if (out_camera_pixels) *out_camera_pixels = (uint64_t)(halo_partition ? r->camera_row_count : owned) * r->width;
+    if (out_band_rows) *out_band_rows = r->band_rows;
+    if (out_halo_rows) *out_halo_rows = halo_partition ? r->halo_rows : 0;
+    return B2PT_OK;
+}
+
+int b2pt_renderer_set_camera(b2pt_renderer* r, const float* camera52)
+{
+    if (!r || !camera52) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2SceneCamera c;
+    std::memcpy(&c, camera52, sizeof(c));
+    b2pt_camera& cam = r->loop.camera;
+    std::memcpy(cam.inverse_view, c.inverse_view, 64);
+    std::memcpy(cam.inverse_projection, c.inverse_projection, 64);
+    std::memcpy(cam.view_projection, c.view_projection, 64);
+    cam.position = b2pt_float3{ c.position[0], c.position[1], c.position[2] };
+    cam.vertical_fov = c.vertical_fov;
     return B2PT_OK;
 }
 

@@ -183,6 +183,31 @@ int b2pt_counters_reset(b2pt_ctx* ctx);
 int b2pt_counters_read(b2pt_ctx* ctx, b2pt_counters_t* out);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * (1b) multi-GPU: frame partition + NCCL exchanges issued from C on the caller's stream (csrc/b2_comm.cu). No counterpart
+ * in the reference, which drives one GPU; the launch surface stays GPUKernel::launch's plus a row selection.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct b2pt_comm b2pt_comm;
+#define B2PT_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+/* Host logic: the frame rows (ascending) within `halo` rows of a band of `band_rows` rows that rank owns (band b -> rank
+ * b % world); halo 0 = the owned rows. out_rows may be null (count only); it needs room for `height` ints. */
+int b2pt_partition_rows(int height, int rank, int world, int band_rows, int halo, int* out_rows, int* out_count);
+/* ncclGetUniqueId on one rank, handed to the others by the host's own bootstrap (torch.distributed in bench.py / tests),
+ * then ncclCommInitRank on every rank. NCCL is loaded at run time (the libnccl.so.2 already in the process, else the system's). */
+int b2pt_comm_unique_id(unsigned char out_id[B2PT_COMM_ID_BYTES]);
+int b2pt_comm_create(b2pt_ctx* ctx, const unsigned char id[B2PT_COMM_ID_BYTES], int rank, int world, b2pt_comm** out_comm);
+int b2pt_comm_destroy(b2pt_comm* comm);
+int b2pt_comm_stats(b2pt_comm* comm, uint64_t* out_exchanges, uint64_t* out_gathers, uint64_t* out_bytes_sent);
+/* `base` = `planes` planes, plane_stride_bytes apart, of `height` rows of row_bytes bytes. Halo exchange: every rank receives the
+ * rows within `halo` of its bands from their owners and sends its own rows to the ranks that want them (pack kernel, one NCCL
+ * group of send / recv, unpack kernel -- all on `stream`). All-gather: every rank's owned rows to every rank. */
+int b2pt_comm_exchange_halo(b2pt_comm* comm, void* base, int planes, size_t plane_stride_bytes, size_t row_bytes, int height, int band_rows, int halo, b2pt_stream stream);
+int b2pt_comm_allgather_rows(b2pt_comm* comm, void* base, int planes, size_t plane_stride_bytes, size_t row_bytes, int height, int band_rows, b2pt_stream stream);
+/* b2pt_kernel_launch_rows with the band height chosen by the caller, or over an explicit ascending list of frame rows
+ * (device_rows != null: a device array of n_rows rows, e.g. a rank's bands plus their halo rows). */
+int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int rank, int world, int band_rows, const int* device_rows, int n_rows, void** args,
+                                 b2pt_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * (2) headless renderer (host mirror of GPURenderer, CPURenderer pass order)
  * ------------------------------------------------------------------------------------------------------------ */
 
@@ -212,15 +237,24 @@ int b2pt_renderer_set_profile_passes(b2pt_renderer* renderer, int enabled);
 int b2pt_renderer_reset(b2pt_renderer* renderer);
 /* Renders `samples` samples of every pixel (all passes), asynchronously on the renderer's stream. */
 int b2pt_renderer_render(b2pt_renderer* renderer, int samples);
-/* Multi-GPU (BASELINE.json north_star; the reference itself is single-GPU): this renderer renders only the pixel rows
- * of its interleaved B2PT_BAND_ROWS-row bands (band b -> rank b % world); scene, BVH and LUTs are replicated by
- * giving every rank the same scene. Without ReSTIR DI no pass reads another pixel and `exchange` may be null. With
- * ReSTIR DI, CameraRays runs over the whole frame on every rank (deterministic, so neighbours' G-buffer entries are
- * recomputed instead of exchanged) and `exchange(user, reservoir_planes, bytes)` is called on the host, with the
- * renderer's stream idle, right before a pass that reads neighbouring pixels' reservoirs: it must complete the 9
- * SoA planes (width*height 4-byte words each) across ranks, i.e. all-gather every rank's owned rows (NCCL). */
-typedef void (*b2pt_exchange_fn)(void* user, void* reservoir_planes, uint64_t bytes);
-int b2pt_renderer_set_partition(b2pt_renderer* renderer, int rank, int world, b2pt_exchange_fn exchange, void* user);
+/* Multi-GPU (BASELINE.json north_star; the reference itself is single-GPU): this renderer renders only the pixel rows of its
+ * interleaved bands (band b -> rank b % world; 16-row bands, 32-row bands for the ReSTIR DI variants); scene, BVH and LUTs are
+ * replicated by giving every rank the same scene. Without ReSTIR DI no pass reads another pixel. With ReSTIR DI the reuse passes
+ * read reservoirs and G-buffer entries up to reuse_radius + neighbor_search_radius pixels away: CameraRays also covers those
+ * halo rows (deterministic, so neighbours' G-buffer entries are recomputed instead of exchanged) and the reservoir rows of the
+ * halo are exchanged with the ranks that own them (b2pt_comm_exchange_halo: ncclSend / ncclRecv on the renderer's stream) right
+ * before every pass that reads neighbours. `dynamic_camera` != 0: the camera may move between frames, so a temporal neighbour can
+ * be anywhere: the halo becomes the whole frame. comm may be null when world == 1. */
+int b2pt_renderer_set_partition(b2pt_renderer* renderer, int rank, int world, b2pt_comm* comm, int dynamic_camera);
+/* All-gathers the framebuffer rows of every rank (ncclAllGather on the renderer's stream) so that each rank holds the whole
+ * frame; counted in b2pt_renderer_last_render_ms. */
+int b2pt_renderer_gather_framebuffer(b2pt_renderer* renderer);
+/* (pixels CameraRays covers on this rank, pixels this rank owns, rows per band, halo rows) of the current partition */
+int b2pt_renderer_partition_info(b2pt_renderer* renderer, uint64_t* out_camera_pixels, uint64_t* out_owned_pixels, int* out_band_rows, int* out_halo_rows);
+/* GPURenderer::set_camera (src/Renderer/GPURenderer.h): the camera of the next frames as 52 floats (B2SceneCamera: inverse view,
+ * inverse projection, view-projection, position, vertical fov). The previous camera becomes prev_camera at the next sample, as
+ * in update_render_data (CPURenderer.cpp:600-604). */
+int b2pt_renderer_set_camera(b2pt_renderer* renderer, const float* camera52);
 /* offsetof(HIPRTRenderData, buffers.accumulated_ray_colors): where the framebuffer's device pointer sits in the host
  * copy returned by b2pt_renderer_render_data (bindings that wrap the framebuffer without a copy) */
 int b2pt_render_data_framebuffer_offset(void);

@@ -55,22 +55,24 @@ def load_golden(name):
 
 
 def run_oracle(kind, variant, scene, width, height, spp, bounces, tmp_path, extra=(), threads=None):
-    """kind: 'ref' (reference sources compiled in place) or 'port' (host build of the product headers)."""
+    """kind: 'ref' (reference sources compiled in place), 'extras' (the same harness + --cameras / --repeat, a separate binary)
+    or 'port' (host build of the product headers). scene: a name under data/ or the path of a .b2scene blob."""
     prefix = str(tmp_path / f"{kind}_")
-    if kind == "ref":
-        exe = REF_DIR / f"ref_render_{variant}"
+    if kind in ("ref", "extras"):
+        exe = REF_DIR / f"ref_{'render' if kind == 'ref' else 'extras'}_{variant}"
         cmd = [str(exe)]
     else:
         exe = PORT_EXE
         cmd = [str(exe), "--variant", variant]
     if not exe.exists():
         pytest.skip(f"{exe} not built")
-    cmd += ["--scene", str(DATA / f"{scene}.b2scene"), "--luts", str(DATA / "brdf_luts.b2luts"), "--width", str(width), "--height", str(height),
+    scene_path = Path(scene) if str(scene).endswith(".b2scene") else DATA / f"{scene}.b2scene"
+    cmd += ["--scene", str(scene_path), "--luts", str(DATA / "brdf_luts.b2luts"), "--width", str(width), "--height", str(height),
             "--spp", str(spp), "--bounces", str(bounces), "--dump", prefix, *extra]
     if threads:
         cmd += ["--threads", str(threads)]
     out = subprocess.run(cmd, check=True, capture_output=True, text=True, cwd=ROOT)  # envmap paths in `extra` are repo-relative
-    meta = json.loads(out.stdout.strip().splitlines()[-1])
+    meta = json.loads([l for l in out.stdout.splitlines() if l.startswith('{"oracle"')][-1])
     n = width * height
     load = lambda nm, dt: np.fromfile(prefix + nm + ".bin", dt)
     mat = load("gbuffer_material", np.uint32).reshape(n, 27).copy()
@@ -99,3 +101,24 @@ def rel_error(a, b):
     b = np.asarray(b, np.float64).reshape(-1, 3)
     denom = np.maximum(np.abs(a), np.abs(b))
     return np.where(denom > 1e-6, np.abs(a - b) / np.maximum(denom, 1e-30), 0.0).max(axis=1)
+
+
+def window_mask(width, height, window, margin=0):
+    """Boolean per-pixel mask of the window [x0, y0, x1, y1) shrunk by `margin` pixels."""
+    x0, y0, x1, y1 = window
+    m = np.zeros((height, width), bool)
+    m[y0 + margin:y1 - margin, x0 + margin:x1 - margin] = True
+    return m.ravel()
+
+
+def moved_camera(camera, offset):
+    """The scene camera (dict of tools/b2scene.read_scene) translated by `offset` in world space, as the 52 floats of a
+    B2SceneCamera: inverse_view gets the translation, view_projection = VP * T(-offset), all in float32."""
+    d = np.asarray(offset, np.float32)
+    inv_view = np.array(camera["inverse_view"], np.float32).reshape(4, 4).copy()
+    vp = np.array(camera["view_projection"], np.float32).reshape(4, 4).copy()
+    inv_view[:3, 3] = inv_view[:3, 3] + d
+    vp[:, 3] = vp[:, 3] - (vp[:, 0] * d[0] + vp[:, 1] * d[1] + vp[:, 2] * d[2])
+    position = np.array(camera["position"], np.float32) + d
+    return np.concatenate([inv_view.ravel(), np.array(camera["inverse_projection"], np.float32).ravel(), vp.ravel(), position,
+                           np.array([camera["vertical_fov"]], np.float32)]).astype(np.float32)

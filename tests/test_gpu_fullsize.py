@@ -1,0 +1,139 @@
+"""Parity at BASELINE.json's FULL sizes, inside `pytest -m gpu`: the CUDA path (precise flavour, through the C ABI) against the
+reference oracle (oracle/_ref: the reference's own CPU kernels compiled in place) run on the box's host cores in the same test.
+Cornell configs: every pixel of the 1080p frame. 10M-triangle configs: a pixel window (the reference CPU path needs ~40 s per
+Mpath there); ReSTIR DI windows are compared on their interior only, because a windowed oracle run has no reservoirs outside
+its window (reuse radius 16 + neighbour search 4, per frame of history). Also: a MOVING camera through the temporal
+reprojection path (UtilsTemporal.h:33-96) and the previous-frame G-buffer, which no static fixture exercises."""
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import DATA, ROOT, moved_camera, pixels_not_bit_identical, rel_error, run_oracle, window_mask
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-3
+
+
+def render_cuda(b2pt, ctx, variant, scene, width, height, spp, bounces, envmap=None, fused=1, cameras=None):
+    r = b2pt.Renderer(ctx, width, height, variant, precise=True)
+    r.set_scene_file(scene if str(scene).endswith(".b2scene") else DATA / f"{scene}.b2scene")
+    r.set_luts_file(DATA / "brdf_luts.b2luts")
+    r.set(nb_bounces=bounces)
+    if variant.startswith("c4"):
+        r.set(restir_di_do_fused_spatiotemporal=fused)
+    if envmap:
+        r.set_envmap_file(envmap)
+    gb = None
+    for frame in range(spp):
+        if cameras is not None:
+            r.set_camera(cameras[min(frame, len(cameras) - 1)])
+        r.render(1)
+        if frame == 0:
+            gb = r.gbuffer()
+    fb = r.framebuffer().reshape(-1, 3)
+    faults = ctx.faults()
+    r.close()
+    assert faults == dict(traversal_guard_trips=0, boundary_guard_trips=0, stack_overflows=0)
+    return gb, fb
+
+
+def assert_gbuffer_equal(gb, ref, mask=None):
+    sel = slice(None) if mask is None else mask
+    assert np.array_equal(gb["prim"][sel], ref["prim"][sel]), "primary-hit primitive ids must match bit-exactly"
+    assert np.array_equal(gb["position"].reshape(-1, 3)[sel].view(np.uint32), ref["position"][sel].view(np.uint32))
+    assert np.array_equal((gb["geometric_normal"] & 0xFFFFFF)[sel], ref["geometric_normal"][sel])
+    assert np.array_equal((gb["shading_normal"] & 0xFFFFFF)[sel], ref["shading_normal"][sel])
+    mat = gb["material"].copy()
+    mat[:, 0] &= 0xFF
+    assert np.array_equal(mat[sel], ref["material"][sel])
+
+
+@pytest.mark.parametrize("variant,spp", [("c2", 2), ("c3", 1)])
+def test_cornell_1080p_is_bit_identical_to_the_reference(b2pt, gpu_ctx, tmp_path, variant, spp):
+    """BASELINE.json configs[1] (and the shipped RIS default) on every pixel of the 1920x1080 frame, 8 bounces."""
+    ref = run_oracle("ref", variant, "cornell_pbr_16x9", 1920, 1080, spp, 8, tmp_path)
+    gb, fb = render_cuda(b2pt, gpu_ctx, variant, "cornell_pbr_16x9", 1920, 1080, spp, 8)
+    assert_gbuffer_equal(gb, ref)
+    assert (rel_error(fb, ref["framebuffer"]) > REL_TOL).sum() == 0
+    assert pixels_not_bit_identical(fb, ref["framebuffer"]) == 0
+
+
+# ---- the synthetic 10M-triangle scene (tools/make_synthetic_scene.py, seeded) --------------------------------------------------
+@pytest.fixture(scope="module")
+def big_scene(built):
+    sys.path.insert(0, str(ROOT))
+    import bench
+    w = dict(bench.WORKLOADS["c4s"])
+    return dict(scene=str(bench.scene_file(w)), envmap=str(bench.envmap_file(w)))
+
+
+def test_c3_10m_triangles_window_is_bit_identical(b2pt, gpu_ctx, tmp_path, big_scene):
+    """BASELINE.json configs[2]: 10M triangles, RIS 4+1 over 100k emissive triangles, 1080p, 8 bounces; 128x128 centre window."""
+    window = [896, 476, 1024, 604]
+    ref = run_oracle("ref", "c3", big_scene["scene"], 1920, 1080, 1, 8, tmp_path, extra=["--window", *map(str, window)])
+    gb, fb = render_cuda(b2pt, gpu_ctx, "c3", big_scene["scene"], 1920, 1080, 1, 8)
+    m = window_mask(1920, 1080, window)
+    assert_gbuffer_equal(gb, ref, m)
+    assert pixels_not_bit_identical(fb[m], ref["framebuffer"][m]) == 0
+
+
+def test_c4_10m_triangles_window_interior(b2pt, gpu_ctx, tmp_path, big_scene):
+    """BASELINE.json configs[3]: 10M triangles, ReSTIR DI fused spatiotemporal reuse + 2k HDR envmap alias table, 2 frames; 256x256
+    window, compared on its interior (40-pixel margin = two frames of reuse radius). The reference reads an uninitialised
+    BSDFIncidentLightInfo on sheen-lobe candidates: a handful of pixels per 100k follow its stack garbage."""
+    window = [832, 412, 1088, 668]
+    ref = run_oracle("ref", "c4", big_scene["scene"], 1920, 1080, 2, 8, tmp_path, extra=["--window", *map(str, window), "--envmap", big_scene["envmap"]])
+    gb, fb = render_cuda(b2pt, gpu_ctx, "c4", big_scene["scene"], 1920, 1080, 2, 8, envmap=big_scene["envmap"])
+    assert_gbuffer_equal(gb, ref, window_mask(1920, 1080, window))
+    m = window_mask(1920, 1080, window, margin=40)
+    differing = pixels_not_bit_identical(fb[m], ref["framebuffer"][m])
+    assert differing <= 8, f"{differing} of {m.sum()} interior pixels differ from the reference"
+    assert (rel_error(fb[m], ref["framebuffer"][m]) > REL_TOL).mean() <= 2e-3
+
+
+def test_c5_4k_window_interior(b2pt, gpu_ctx, tmp_path, big_scene):
+    """BASELINE.json configs[4]: the same scene at 3840x2160, ReSTIR DI fused + envmap, first frame; 192x192 window, 24-pixel margin."""
+    import bench
+    scene = str(bench.scene_file(dict(bench.WORKLOADS["c5"])))
+    window = [1824, 984, 2016, 1176]
+    ref = run_oracle("ref", "c4", scene, 3840, 2160, 1, 8, tmp_path, extra=["--window", *map(str, window), "--envmap", big_scene["envmap"]])
+    gb, fb = render_cuda(b2pt, gpu_ctx, "c4", scene, 3840, 2160, 1, 8, envmap=big_scene["envmap"])
+    assert_gbuffer_equal(gb, ref, window_mask(3840, 2160, window))
+    m = window_mask(3840, 2160, window, margin=24)
+    differing = pixels_not_bit_identical(fb[m], ref["framebuffer"][m])
+    assert differing <= 4, f"{differing} of {m.sum()} interior pixels differ from the reference"
+
+
+# ---- moving camera: temporal reprojection + the previous-frame G-buffer ---------------------------------------------------
+@pytest.mark.parametrize("fused", [1, 0])
+def test_moving_camera_restir_di(b2pt, gpu_ctx, tmp_path, fused):
+    """prev_camera != current_camera: find_temporal_neighbor_index reprojects the shading point with the previous camera's
+    view-projection, searches up to 8 neighbours and reads the previous frame's G-buffer (UtilsTemporal.h:33-96). Three frames of
+    the Cornell box with the camera translated a little every frame; the oracle binary is ref_extras_c4 (same harness, --cameras)."""
+    import b2scene
+    scene = b2scene.read_scene(str(DATA / "cornell_pbr_16x9.b2scene"))
+    cameras = [moved_camera(scene["camera"], (0.06 * f, 0.02 * f, -0.04 * f)) for f in range(3)]
+    camera_file = tmp_path / "cameras.bin"
+    np.concatenate(cameras).astype(np.float32).tofile(camera_file)
+    width, height = 320, 180
+    try:
+        ref = run_oracle("extras", "c4", "cornell_pbr_16x9", width, height, 3, 4, tmp_path, extra=["--cameras", str(camera_file)] + ([] if fused else ["--no-fused"]))
+    except subprocess.CalledProcessError as e:
+        pytest.skip(f"the reference itself crashes on this configuration (uninitialised reads, DESIGN.md section 3): {e}")
+    gb, fb = render_cuda(b2pt, gpu_ctx, "c4", "cornell_pbr_16x9", width, height, 3, 4, fused=fused, cameras=cameras)
+    assert_gbuffer_equal(gb, ref)
+    rel = rel_error(fb, ref["framebuffer"])
+    assert (rel > REL_TOL).mean() <= 2e-3, f"{(rel > REL_TOL).sum()} of {rel.size} pixels beyond {REL_TOL}"
+    assert pixels_not_bit_identical(fb, ref["framebuffer"]) <= max(2, rel.size // 1000)
+
+
+def test_division_selftest_binary(built):
+    """b2_div3_exact (three IEEE divisions through one refined reciprocal, b2_math.h) == __fdiv_rn bit for bit on ~1.2e9 operand
+    triples of eight families (tools/div_selftest.cu)."""
+    exe = ROOT / "tools" / "div_selftest"
+    if not exe.exists():
+        pytest.skip("tools/div_selftest not built")
+    out = subprocess.run([str(exe), "4096"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and '"mismatches": 0' in out.stdout, out.stdout[-2000:]

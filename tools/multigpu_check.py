@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Run under torchrun with N ranks (one per GPU): renders a frame partitioned across the ranks (interleaved 16-row bands,
-ReSTIR DI reservoir exchange, framebuffer all-gather) and checks on every rank that the gathered frame is BIT-IDENTICAL to
+"""Run under torchrun with N ranks (one per GPU): renders a frame partitioned across the ranks (interleaved row bands,
+ReSTIR DI reservoir halo exchange, framebuffer all-gather -- NCCL from C) and checks on every rank that the gathered frame is BIT-IDENTICAL to
 the same frame rendered by that rank alone -- results must not depend on the number of GPUs.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multigpu_check.py --variant c4
@@ -61,9 +61,12 @@ def main():
     part.set_partition(rank, world, torch, dist)
     gather = part.make_gather(torch, dist)
     part.render(a.spp, sync=False)
-    gather_ms = gather()
+    gather()
+    part.synchronize()
+    gather_ms = part.last_render_ms()
     got = part.framebuffer()
     exchanges = part.exchange_count
+    info = part.partition_info()
     part.close()
 
     same = bool(np.array_equal(ref.view(np.uint32), got.view(np.uint32)))
@@ -72,7 +75,7 @@ def main():
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps(dict(multigpu_check=a.variant, world=world, width=a.width, height=a.height, spp=a.spp, fused=a.fused, bit_identical_on_all_ranks=bool(flags.item()),
-                              rank0_mismatching_pixels=mismatching, reservoir_exchanges=exchanges, gather_ms=gather_ms)))
+                              rank0_mismatching_pixels=mismatching, reservoir_exchanges=exchanges, render_plus_gather_ms=gather_ms, partition=info)))
     ctx.close()
     dist.destroy_process_group()
     sys.exit(0 if flags.item() else 1)
