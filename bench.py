@@ -365,6 +365,7 @@ def main():
     if world > 1:
         r.set_partition(rank, world, torch, dist)
     info = r.scene_info()
+    partition_text = r.partition_description() if world > 1 else "single GPU"
 
     fb_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
     fb_np = fb_host.numpy()
@@ -538,7 +539,7 @@ def main():
                     higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
                     config=workload_config(w),
                     impl_detail=dict(flavour="precise (bit-identical to the reference CPURenderer, tests/)" if precise else "fast (--use_fast_math A/B build)",
-                                     partition=r.partition_description() if world > 1 else "single GPU",
+                                     partition=partition_text,
                                      l2_policy="every step re-renders from reset: G-buffer + framebuffer + reservoirs (> 126 MB) are rewritten between timed iterations; the scene (0.72 GB BVH) exceeds L2"),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit="Mpaths/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps),

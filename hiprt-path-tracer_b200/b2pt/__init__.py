@@ -176,6 +176,15 @@ class Communicator:
             self.handle = C.c_void_p()
 
 
+def read_hdr(path, flip_y=True):
+    """b2pt_image_read_hdr: the library's Radiance .hdr decoder (host only) -> (height, width, 4) float32."""
+    w, h = C.c_int(), C.c_int()
+    check(lib().b2pt_image_read_hdr(str(path).encode(), int(flip_y), None, C.byref(w), C.byref(h)))
+    out = np.empty((h.value, w.value, 4), np.float32)
+    check(lib().b2pt_image_read_hdr(str(path).encode(), int(flip_y), out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(w), C.byref(h)))
+    return out
+
+
 def partition_rows(height, rank, world, band_rows, halo=0):
     """b2pt_partition_rows (host logic of the C layer): rows within `halo` of rank's bands."""
     rows = (C.c_int * height)()
@@ -228,6 +237,18 @@ class Renderer:
 
     def set_envmap_file(self, path):
         check(lib().b2pt_renderer_set_envmap_file(self.handle, str(path).encode()))
+
+    def set_envmap_hdr_file(self, path):
+        check(lib().b2pt_renderer_set_envmap_hdr_file(self.handle, str(path).encode()))
+
+    def set_envmap_matrices(self, envmap_to_world, world_to_envmap):
+        a = np.ascontiguousarray(envmap_to_world, np.float32).reshape(9)
+        b = np.ascontiguousarray(world_to_envmap, np.float32).reshape(9)
+        check(lib().b2pt_renderer_set_envmap_matrices(self.handle, a.ctypes.data_as(C.POINTER(C.c_float)), b.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def update_materials(self, materials):
+        m = np.ascontiguousarray(materials, np.float32)
+        check(lib().b2pt_renderer_update_materials(self.handle, m.ctypes.data_as(C.POINTER(C.c_float)), len(m)))
 
     def set_envmap(self, rgba):
         if rgba is None:

@@ -335,3 +335,101 @@ bool b2_envmap_blob_read(const char* path, std::vector<float>& rgba, int& width,
     height = dims[1];
     return ok;
 }
+
+/* Radiance RGBE (.hdr) reader, written from the format description (Ward, "Real Pixels", Graphics Gems II; the file header of
+ * radiance/src/common/color.c): text header up to an empty line with FORMAT=32-bit_rle_rgbe, a resolution line "-Y h +X w", then
+ * scanlines, each either flat (4 bytes per pixel) or "new RLE" (2, 2, width hi, width lo, then the four channels run-length coded one
+ * after the other). A pixel (r, g, b, e) decodes to (r, g, b) * 2^(e - 136), e = 0 to black -- what stb_image's loader, which the
+ * reference calls (Image32Bit::read_image_hdr, src/Image/Image.cpp:389-417), computes; alpha = 1. flip_y: last scanline first. */
+bool b2_hdr_read(const char* path, bool flip_y, std::vector<float>& rgba, int& width, int& height, std::string& error)
+{
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { error = std::string("cannot open ") + path; return false; }
+    auto fail = [&](const char* what) { error = std::string(what) + ": " + path; std::fclose(f); return false; };
+    char line[1024];
+    if (!std::fgets(line, sizeof(line), f) || (std::strncmp(line, "#?RADIANCE", 10) != 0 && std::strncmp(line, "#?RGBE", 6) != 0))
+        return fail("not a Radiance .hdr file");
+    bool format_ok = false;
+    while (true)
+    {
+        if (!std::fgets(line, sizeof(line), f))
+            return fail("truncated .hdr header");
+        if (line[0] == '\n' || (line[0] == '\r' && line[1] == '\n'))
+            break;
+        if (std::strncmp(line, "FORMAT=32-bit_rle_rgbe", 22) == 0)
+            format_ok = true;
+    }
+    if (!format_ok)
+        return fail("unsupported .hdr pixel format");
+    if (!std::fgets(line, sizeof(line), f) || std::sscanf(line, "-Y %d +X %d", &height, &width) != 2 || width <= 0 || height <= 0 || width > 65535 || height > 65535)
+        return fail("unsupported .hdr resolution line");
+
+    rgba.assign((size_t)width * height * 4, 0.0f);
+    std::vector<unsigned char> scan((size_t)width * 4);
+    auto decode = [&](const unsigned char* p, float* out) {
+        if (p[3] != 0)
+        {
+            const float scale = std::ldexp(1.0f, (int)p[3] - 136);
+            out[0] = p[0] * scale;
+            out[1] = p[1] * scale;
+            out[2] = p[2] * scale;
+        }
+        else
+            out[0] = out[1] = out[2] = 0.0f;
+        out[3] = 1.0f;
+    };
+    for (int y = 0; y < height; y++)
+    {
+        unsigned char head[4];
+        if (std::fread(head, 1, 4, f) != 4)
+            return fail("truncated .hdr pixel data");
+        const bool rle = width >= 8 && width < 32768 && head[0] == 2 && head[1] == 2 && (head[2] & 0x80) == 0;
+        if (rle)
+        {
+            if (((int)head[2] << 8 | head[3]) != width)
+                return fail("corrupt .hdr scanline");
+            for (int c = 0; c < 4; c++)
+            {
+                int x = 0;
+                while (x < width)
+                {
+                    int count = std::fgetc(f);
+                    if (count == EOF)
+                        return fail("truncated .hdr pixel data");
+                    if (count > 128)
+                    {
+                        count -= 128;
+                        const int value = std::fgetc(f);
+                        if (value == EOF || count == 0 || x + count > width)
+                            return fail("corrupt .hdr run");
+                        for (int i = 0; i < count; i++)
+                            scan[(size_t)(x++) * 4 + c] = (unsigned char)value;
+                    }
+                    else
+                    {
+                        if (count == 0 || x + count > width)
+                            return fail("corrupt .hdr run");
+                        for (int i = 0; i < count; i++)
+                        {
+                            const int value = std::fgetc(f);
+                            if (value == EOF)
+                                return fail("truncated .hdr pixel data");
+                            scan[(size_t)(x++) * 4 + c] = (unsigned char)value;
+                        }
+                    }
+                }
+            }
+        }
+        else
+        {
+            std::memcpy(scan.data(), head, 4);
+            if (width > 1 && std::fread(scan.data() + 4, 4, (size_t)width - 1, f) != (size_t)width - 1)
+                return fail("truncated .hdr pixel data");
+        }
+        float* row = rgba.data() + (size_t)(flip_y ? height - 1 - y : y) * width * 4;
+        for (int x = 0; x < width; x++)
+            decode(scan.data() + (size_t)x * 4, row + (size_t)x * 4);
+    }
+    std::fclose(f);
+    return true;
+}

@@ -98,4 +98,6 @@ bool b2_envmap_blob_read(const char* path, std::vector<float>& rgba, int& width,
  * (dispersive media, > 2^26 - 1 materials, invalid indices). */
 bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bvh = true);
 
+bool b2_hdr_read(const char* path, bool flip_y, std::vector<float>& rgba, int& width, int& height, std::string& error);
+
 #endif

@@ -221,7 +221,7 @@ int resolve_kernels(b2pt_renderer* r)
 /* Forgets the current scene: after this no device pointer of the render data refers to scene memory, so a failed
  * upload leaves the renderer in the "no scene set" state (render / reupload return an error) instead of pointing at
  * freed allocations. */
-void invalidate_scene(b2pt_renderer* r)
+void invalidate_scene(b2pt_renderer* r, bool keep_bvh = false)
 {
     unpin_scene(r);
     r->has_scene = false;
@@ -233,7 +233,7 @@ void invalidate_scene(b2pt_renderer* r)
     rd.GPU_BVH = nullptr;
     rd.light_GPU_BVH = nullptr;
     free_all(r, r->scene_allocs);
-    if (r->bvh)
+    if (r->bvh && !keep_bvh)
     {
         b2pt_bvh_destroy(r->ctx, r->bvh);
         r->bvh = nullptr;
@@ -271,9 +271,11 @@ int update_partition_rows(b2pt_renderer* r)
     return B2PT_OK;
 }
 
-int upload_scene(b2pt_renderer* r)
+/* keep_bvh: the geometry did not change (update_all_materials): every scene array is re-derived and re-uploaded, the wide BVH stays */
+int upload_scene(b2pt_renderer* r, bool keep_bvh = false)
 {
-    invalidate_scene(r);
+    keep_bvh = keep_bvh && r->bvh != nullptr;
+    invalidate_scene(r, keep_bvh);
     B2HostScene& s = r->scene;
     std::string error;
     if (!b2_host_scene_prepare(s, error, /* build_bvh = */ false))
@@ -343,7 +345,8 @@ int upload_scene(b2pt_renderer* r)
     B2_TRY(upload(r, r->scene_allocs, m.coat_sheen_index, &d.coat_sheen_index));
     B2_TRY(upload(r, r->scene_allocs, m.specular_transmission_index, &d.specular_transmission_index));
 
-    B2_TRY(b2pt_bvh_build(r->ctx, s.blob.indices.data(), (int)s.blob.n_triangles(), s.blob.positions.data(), (int)s.blob.n_vertices(), 0, nullptr, &r->bvh));
+    if (!keep_bvh)
+        B2_TRY(b2pt_bvh_build(r->ctx, s.blob.indices.data(), (int)s.blob.n_triangles(), s.blob.positions.data(), (int)s.blob.n_vertices(), 0, nullptr, &r->bvh));
     rd.GPU_BVH = b2pt_bvh_device_handle(r->bvh);
     rd.light_GPU_BVH = nullptr;
 
@@ -512,6 +515,35 @@ int b2pt_renderer_set_scene_arrays(b2pt_renderer* r, const float* positions, con
     )
 }
 
+/* GPURenderer::update_all_materials (GPURenderer.cpp:1022-1040): new values for every material of the current scene. Everything
+ * derived from materials is rebuilt the way set_scene builds it (packed SoA, opacity flags, emissive triangle list, power alias
+ * table) and re-uploaded; the geometry and its BVH stay. */
+int b2pt_renderer_update_materials(b2pt_renderer* r, const float* materials, int material_count)
+{
+    if (!r || !materials || !r->has_scene) { b2_set_error("b2pt_renderer_update_materials: no scene / null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    if ((size_t)material_count != r->scene.blob.n_materials())
+    {
+        b2_set_error("b2pt_renderer_update_materials: the scene has %zu materials, %d given", r->scene.blob.n_materials(), material_count);
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    B2_TRY(b2pt_ctx_make_current(r->ctx));
+    B2_GUARDED(
+    B2_TRY(b2pt_stream_synchronize(r->ctx, r->stream));
+    r->scene.blob.materials.assign(materials, materials + (size_t)material_count * B2MAT_FLOAT_COUNT);
+    return upload_scene(r, /* keep_bvh = */ true);
+    )
+}
+
+/* RendererEnvmap::do_animation / update_renderer (RendererEnvmap.cpp:129-181): the two 3x3 rotations between envmap and world space,
+ * row-major as in WorldSettings (the reference host computes them with glm::orientate3 and its inverse and hands them over). */
+int b2pt_renderer_set_envmap_matrices(b2pt_renderer* r, const float* envmap_to_world9, const float* world_to_envmap9)
+{
+    if (!r || !envmap_to_world9 || !world_to_envmap9) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    std::memcpy(r->loop.rd.world_settings.envmap_to_world_matrix, envmap_to_world9, 36);
+    std::memcpy(r->loop.rd.world_settings.world_to_envmap_matrix, world_to_envmap9, 36);
+    return B2PT_OK;
+}
+
 /* Re-sends every scene array (geometry, per-triangle data, material SoA, alias table, wide-BVH blob) from the host
  * copies to their existing device allocations, asynchronously on the renderer's stream: the per-step host->device
  * traffic of the end-to-end measurement (what GPURenderer::set_scene hands to the device layer, BVH build excluded). */
@@ -623,6 +655,41 @@ int b2pt_renderer_set_envmap_file(b2pt_renderer* r, const char* envmap_blob_path
         return B2PT_ERR_IO;
     }
     return b2pt_renderer_set_envmap(r, rgba.data(), width, height);
+    )
+}
+
+int b2pt_renderer_set_envmap_hdr_file(b2pt_renderer* r, const char* hdr_path)
+{
+    if (!r || !hdr_path) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_GUARDED(
+    std::vector<float> rgba;
+    int width = 0, height = 0;
+    std::string error;
+    if (!b2_hdr_read(hdr_path, /* flip_y = */ true, rgba, width, height, error))
+    {
+        b2_set_error("%s", error.c_str());
+        return B2PT_ERR_IO;
+    }
+    return b2pt_renderer_set_envmap(r, rgba.data(), width, height);
+    )
+}
+
+/* host-only helper behind b2pt_renderer_set_envmap_hdr_file, exported so that the decoder can be checked without a device:
+ * out_rgba == null only reports the size; otherwise it receives width * height * 4 floats */
+int b2pt_image_read_hdr(const char* hdr_path, int flip_y, float* out_rgba, int* out_width, int* out_height)
+{
+    if (!hdr_path || !out_width || !out_height) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    B2_GUARDED(
+    std::vector<float> rgba;
+    std::string error;
+    if (!b2_hdr_read(hdr_path, flip_y != 0, rgba, *out_width, *out_height, error))
+    {
+        b2_set_error("%s", error.c_str());
+        return B2PT_ERR_IO;
+    }
+    if (out_rgba)
+        std::memcpy(out_rgba, rgba.data(), rgba.size() * sizeof(float));
+    return B2PT_OK;
     )
 }
 

@@ -222,9 +222,20 @@ int b2pt_renderer_set_scene_arrays(b2pt_renderer* renderer, const float* positio
 /* Host -> device re-send of every scene array + the BVH blob on the renderer's stream (GPURenderer::set_scene's upload
  * half, src/Renderer/GPURenderer.cpp:769-939, without the host BVH build). out_bytes: bytes copied. */
 int b2pt_renderer_reupload_scene(b2pt_renderer* renderer, uint64_t* out_bytes);
+/* GPURenderer::update_all_materials (src/Renderer/GPURenderer.cpp:1022-1040): new parameter records (B2MAT_FLOAT_COUNT floats each,
+ * include/b2pt_scene_blob.h) for every material of the current scene; packed SoA, opacity, emissive list and power alias table are
+ * rebuilt and re-uploaded, geometry and BVH stay. */
+int b2pt_renderer_update_materials(b2pt_renderer* renderer, const float* materials, int material_count);
 int b2pt_renderer_set_luts_file(b2pt_renderer* renderer, const char* lut_blob_path);
 /* RGBA fp32 texels, row 0 first (what Image32Bit holds after read_image_hdr(path, 4, flipY=true)) */
 int b2pt_renderer_set_envmap(b2pt_renderer* renderer, const float* rgba_texels, int width, int height);
+/* Radiance .hdr (RGBE) file, decoded like Image32Bit::read_image_hdr(path, 4, flipY = true) (src/Image/Image.cpp, stb_image) */
+int b2pt_renderer_set_envmap_hdr_file(b2pt_renderer* renderer, const char* hdr_path);
+/* the decoder alone (host only): out_rgba == null reports the size, else it receives width * height * 4 floats */
+int b2pt_image_read_hdr(const char* hdr_path, int flip_y, float* out_rgba, int* out_width, int* out_height);
+/* Envmap rotation (RendererEnvmap::do_animation, src/Renderer/RendererEnvmap.cpp:129-181): the row-major 3x3 envmap->world and
+ * world->envmap matrices of WorldSettings, as the reference host computes them (glm::orientate3 and its inverse). */
+int b2pt_renderer_set_envmap_matrices(b2pt_renderer* renderer, const float* envmap_to_world9, const float* world_to_envmap9);
 /* same, from a "B2ENVMP1" blob (int32 width, height, then width*height*4 floats): the container tests and bench use */
 int b2pt_renderer_set_envmap_file(b2pt_renderer* renderer, const char* envmap_blob_path);
 /* Host copy of the render data; edit settings (nb_bounces, restir_di_settings, ...) before rendering. */

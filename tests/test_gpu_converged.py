@@ -1,0 +1,66 @@
+"""Converged-image gate (BASELINE.json north_star: "converged images must agree within a stated RMSE/FLIP threshold").
+Images of 128 / 64 samples per pixel from the CUDA path against the reference CPU path (oracle/_ref) at the same seeds, compared
+with the reference's OWN metrics: its tone mapper, its FLIP (thirdparties/nvidia-FLIP through Utils::compute_image_weighted_median_FLIP)
+and its RMSE, all compiled from /root/reference into oracle/_ref/ref_tools (oracle/ref_tools.cpp).
+Stated thresholds: mean FLIP <= 0.02 and relative RMSE of the HDR image <= 0.03 for the fast-math flavour; the precise flavour is
+bit-identical, i.e. FLIP = 0 exactly. For scale, two renders of the same frame with DIFFERENT seeds sit at a FLIP of ~0.1."""
+import json
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import DATA, REF_DIR, ROOT, run_oracle
+
+pytestmark = pytest.mark.gpu
+FLIP_MAX, REL_RMSE_MAX = 0.02, 0.03
+
+
+def flip(tmp_path, a, b, width, height, samples, tag):
+    exe = REF_DIR / "ref_tools"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/ref_tools not built")
+    pa, pb = tmp_path / f"{tag}_a.bin", tmp_path / f"{tag}_b.bin"
+    np.asarray(a, np.float32).tofile(pa)
+    np.asarray(b, np.float32).tofile(pb)
+    out = subprocess.run([str(exe), "flip", str(pa), str(pb), str(width), str(height), str(samples)], check=True, capture_output=True, text=True)
+    return json.loads([l for l in out.stdout.splitlines() if l.startswith('{"tool"')][-1])
+
+
+def render(b2pt, ctx, variant, scene, width, height, samples, bounces, precise, envmap=None, seed=None):
+    r = b2pt.Renderer(ctx, width, height, variant, precise=precise)
+    r.set_scene_file(DATA / f"{scene}.b2scene")
+    r.set_luts_file(DATA / "brdf_luts.b2luts")
+    r.set(nb_bounces=bounces)
+    if variant.startswith("c4"):
+        r.set(restir_di_do_fused_spatiotemporal=1)
+    if envmap:
+        r.set_envmap_file(ROOT / envmap)
+    if seed is not None:
+        r.set_host_seed(seed)
+    r.render(samples)
+    fb = r.framebuffer().copy()
+    r.close()
+    return fb
+
+
+@pytest.mark.parametrize("variant,scene,width,height,samples,bounces,envmap", [("c2", "cornell_pbr_16x9", 320, 180, 128, 8, None),
+                                                                                ("c4", "synthetic_20k", 192, 108, 64, 4, "data/sky_128x64.b2env")])
+def test_converged_image_agrees_with_the_reference(b2pt, gpu_ctx, tmp_path, variant, scene, width, height, samples, bounces, envmap):
+    extra = ["--envmap", envmap] if envmap else []
+    ref = run_oracle("ref", variant, scene, width, height, samples, bounces, tmp_path, extra=extra)["framebuffer"]
+    precise = render(b2pt, gpu_ctx, variant, scene, width, height, samples, bounces, True, envmap)
+    fast = render(b2pt, gpu_ctx, variant, scene, width, height, samples, bounces, False, envmap)
+    other_seed = render(b2pt, gpu_ctx, variant, scene, width, height, samples, bounces, True, envmap, seed=7)
+
+    # the reference marks NaN samples with 1e30 "pink" pixels (display_NaNs); both sides produce the same ones -- they are not image content
+    sane = lambda img: np.where(np.asarray(img, np.float32) > 1e20, 0.0, img).astype(np.float32)
+    m_precise = flip(tmp_path, sane(ref), sane(precise), width, height, samples, "precise")
+    m_fast = flip(tmp_path, sane(ref), sane(fast), width, height, samples, "fast")
+    m_noise = flip(tmp_path, sane(ref), sane(other_seed), width, height, samples, "noise")
+    print(json.dumps(dict(variant=variant, precise=m_precise, fast=m_fast, different_seed=m_noise)))
+
+    assert m_precise["mean_flip"] <= 1e-4 and m_precise["rel_rmse_hdr"] <= 1e-3, m_precise
+    assert m_fast["mean_flip"] <= FLIP_MAX and m_fast["rel_rmse_hdr"] <= REL_RMSE_MAX, m_fast
+    # the gate has teeth: an independent render of the same frame is an order of magnitude further away than the fast flavour
+    assert m_noise["mean_flip"] > 2 * m_fast["mean_flip"]

@@ -137,3 +137,96 @@ def test_division_selftest_binary(built):
         pytest.skip("tools/div_selftest not built")
     out = subprocess.run([str(exe), "4096"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and '"mismatches": 0' in out.stdout, out.stdout[-2000:]
+
+
+# ---- host-mirror features of SURVEY 8f rank 4: envmap rotation, .hdr envmaps, material updates ---------------------------------
+def rotation_matrices(rx, ry, rz):
+    """A rotation about x, y, z (radians) and its inverse as float32 3x3 (the reference host builds them with glm::orientate3 /
+    glm::inverse and stores them in WorldSettings; both sides of this test get the same 18 floats)."""
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    mx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    my = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    mz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    m = (mz @ my @ mx).astype(np.float32)
+    return m, np.linalg.inv(m.astype(np.float64)).astype(np.float32)
+
+
+@pytest.mark.parametrize("variant,scene", [("c3", "cornell_pbr_16x9"), ("c4", "synthetic_20k")])
+def test_rotated_envmap(b2pt, gpu_ctx, tmp_path, variant, scene):
+    """world_to_envmap / envmap_to_world != identity (RendererEnvmap::do_animation): envmap lookup, alias-table sampling and the
+    ReSTIR DI envmap candidates all go through the two matrices."""
+    e2w, w2e = rotation_matrices(0.4, 1.1, -0.3)
+    matrices = tmp_path / "matrices.bin"
+    np.concatenate([e2w.ravel(), w2e.ravel()]).astype(np.float32).tofile(matrices)
+    width, height, spp = 192, 108, 3
+    ref = run_oracle("extras", variant, scene, width, height, spp, 4, tmp_path, extra=["--envmap", "data/sky_128x64.b2env", "--envmap-matrices", str(matrices)])
+    r = b2pt.Renderer(gpu_ctx, width, height, variant, precise=True)
+    r.set_scene_file(DATA / f"{scene}.b2scene")
+    r.set_luts_file(DATA / "brdf_luts.b2luts")
+    r.set(nb_bounces=4)
+    if variant == "c4":
+        r.set(restir_di_do_fused_spatiotemporal=1)
+    r.set_envmap_file(DATA / "sky_128x64.b2env")
+    r.set_envmap_matrices(e2w, w2e)
+    r.render(spp)
+    fb = r.framebuffer().reshape(-1, 3)
+    unrotated_differs = None
+    r.close()
+    rel = rel_error(fb, ref["framebuffer"])
+    assert (rel > REL_TOL).mean() <= 2e-3, f"{(rel > REL_TOL).sum()} of {rel.size} pixels beyond {REL_TOL}"
+    assert pixels_not_bit_identical(fb, ref["framebuffer"]) <= max(2, rel.size // 1000)
+
+
+def test_hdr_envmap_file_equals_the_decoded_blob(b2pt, gpu_ctx):
+    """b2pt_renderer_set_envmap_hdr_file (Radiance .hdr -> RGBE9995 + alias table) == set_envmap with the pixels the reference's
+    loader decodes from the same file (the decoder itself is checked against the reference's on CPU, tests/test_host_tools.py)."""
+    frames = []
+    for use_file in (True, False):
+        r = b2pt.Renderer(gpu_ctx, 160, 90, "c3", precise=True)
+        r.set_scene_file(DATA / "cornell_pbr_16x9.b2scene")
+        r.set_luts_file(DATA / "brdf_luts.b2luts")
+        r.set(nb_bounces=3)
+        if use_file:
+            r.set_envmap_hdr_file(DATA / "sky_64x32.hdr")
+        else:
+            r.set_envmap(b2pt.read_hdr(DATA / "sky_64x32.hdr"))
+        r.render(2)
+        frames.append(r.framebuffer().copy())
+        r.close()
+    assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32)) and frames[0].mean() > 0
+
+
+def test_update_materials_equals_a_fresh_scene(b2pt, gpu_ctx):
+    """GPURenderer::update_all_materials: new material records on the loaded scene (packed SoA, opacity, emissive list and power
+    alias table rebuilt, BVH kept) render exactly like a renderer that was given the edited scene from the start."""
+    import b2scene
+    scene = b2scene.read_scene(str(DATA / "cornell_pbr_16x9.b2scene"))
+    edited = dict(scene)
+    mats = np.array(scene["materials"], np.float32).copy()
+    mats[:, 3:6] = mats[:, 3:6][:, ::-1]          # permute the base colour channels of every material
+    emissive = np.flatnonzero(mats[:, 0:3].sum(axis=1) > 0)
+    mats[emissive, 0:3] *= 0.5                      # and halve the emission (changes the power alias table)
+    edited["materials"] = mats
+
+    def render(setup):
+        r = b2pt.Renderer(gpu_ctx, 160, 90, "c2", precise=True)
+        r.set_luts_file(DATA / "brdf_luts.b2luts")
+        r.set(nb_bounces=4)
+        setup(r)
+        r.render(2)
+        fb = r.framebuffer().copy()
+        r.close()
+        return fb
+
+    def updated(r):
+        r.set_scene(scene)
+        r.render(1)
+        r.update_materials(mats)
+        r.reset()
+        r.set_host_seed(42)
+
+    a = render(updated)
+    b = render(lambda r: r.set_scene(edited))
+    c = render(lambda r: r.set_scene(scene))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert not np.array_equal(a.view(np.uint32), c.view(np.uint32))
