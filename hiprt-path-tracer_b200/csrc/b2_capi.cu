@@ -67,9 +67,11 @@ struct b2pt_bvh
     bool host_pinned = false; /* page-locked on the first re-upload */
 };
 
-/* device descriptor -> depth of the tree, so a launch can size the traversal stack (b2pt_kernel_launch only sees the render data) */
+/* device descriptor -> depth and size of the tree, so a launch can size the traversal stack and pick the MegaKernel form
+ * (b2pt_kernel_launch only sees the render data) */
 static std::mutex g_bvh_depth_mutex;
 static std::unordered_map<const void*, int> g_bvh_depth;
+static std::unordered_map<const void*, uint64_t> g_bvh_nodes;
 
 /* kernel units (objects of b2_kernels.cu) register here from their static initialisers */
 static std::vector<B2KernelUnit>& kernel_units()
@@ -382,6 +384,7 @@ int b2pt_bvh_build(b2pt_ctx* ctx, const int* triangle_indices, int triangle_coun
     {
         std::lock_guard<std::mutex> lock(g_bvh_depth_mutex);
         g_bvh_depth[bvh->descriptor] = bvh->stats.max_depth;
+        g_bvh_nodes[bvh->descriptor] = bvh->stats.node_count;
     }
     *out_bvh = bvh;
     return B2PT_OK;
@@ -432,6 +435,7 @@ int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh)
     {
         std::lock_guard<std::mutex> lock(g_bvh_depth_mutex);
         g_bvh_depth.erase(bvh->descriptor);
+        g_bvh_nodes.erase(bvh->descriptor);
     }
     if (bvh->host_pinned)
     {
@@ -554,18 +558,28 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
     return B2PT_ERR_NO_VARIANT;
 }
 
-/* Form of the MegaKernel: 2 = "phased" (default: persistent warps, bounce cut at its rays, block-pooled traversal; the
- * fastest form on B200 for both the L2-resident Cornell box and the 10M-triangle scene, profiles/), 1 = "persistent"
- * (persistent warps, rays traced in place), 0 = "tiles" (one thread per pixel). B2PT_MEGAKERNEL=phased|persistent|tiles
- * forces one (A/B measurements, tests); it is read at every launch so a test can switch between them. */
-static int megakernel_form()
+/* Form of the MegaKernel (all four render bit-identical frames, tests/test_gpu_parity.py):
+ *   3 = "wavefront": path state parked in HBM between stages, all rays of a bounce in one queue drained at 32 warps / SM, shading
+ *       kernels over paths sorted by material (b2_wavefront.h). The fastest form once the scene no longer fits the L2: on the
+ *       10M-triangle workloads 1.7x (RIS) to 2.6x (ReSTIR DI + envmap) the phased form (profiles/r02_results.md).
+ *   2 = "phased": persistent 512-thread blocks, bounce cut at its rays, block-pooled traversal; the fastest form on L2-resident
+ *       scenes (Cornell: 12.0 ms against 17.9 ms per 1080p sample), where the wavefront's state traffic is not paid back.
+ *   1 = "persistent" (persistent warps, rays traced in place), 0 = "tiles" (one thread per pixel): kept for A/B runs and tests.
+ * Default: wavefront when the BVH has at least B2_WAVEFRONT_MIN_NODES nodes, phased below. B2PT_MEGAKERNEL=wavefront|phased|
+ * persistent|tiles forces one; it is read at every launch so a test can switch between them. */
+#define B2_WAVEFRONT_MIN_NODES 32768u
+static int megakernel_form(uint64_t bvh_nodes)
 {
     const char* e = std::getenv("B2PT_MEGAKERNEL");
     if (e && !std::strcmp(e, "tiles"))
         return 0;
     if (e && !std::strcmp(e, "persistent"))
         return 1;
-    return 2;
+    if (e && !std::strcmp(e, "phased"))
+        return 2;
+    if (e && !std::strcmp(e, "wavefront"))
+        return 3;
+    return bvh_nodes >= B2_WAVEFRONT_MIN_NODES ? 3 : 2;
 }
 
 int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank, int world, void** args, b2pt_stream stream)
@@ -615,9 +629,9 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
         geom.directional_masks_ull = *reinterpret_cast<void**>(args[2]);
         geom.directional_radius = *reinterpret_cast<void**>(args[3]);
     }
-    geom.persistent = megakernel_form();
     geom.pool_rays = (rd->world_settings.ambient_light_type == 2 && rd->world_settings.envmap_intensity > 0.0f) ? 5 : 3;
     geom.stack_entries = B2_STACK_ENTRIES;
+    uint64_t bvh_nodes = 0;
     {
         /* a traversal pushes at most one entry per level: depth + 1 entries are enough for this tree */
         std::lock_guard<std::mutex> lock(g_bvh_depth_mutex);
@@ -631,8 +645,10 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
                 return B2PT_ERR_UNSUPPORTED_SCENE;
             }
             geom.stack_entries = std::max(4, std::min(B2_STACK_ENTRIES, it->second + 1));
+            bvh_nodes = g_bvh_nodes[rd->GPU_BVH];
         }
     }
+    geom.persistent = megakernel_form(bvh_nodes);
     B2_CUDA(cudaEventRecord(kernel->start, s));
     B2_CUDA(kernel->entry->launch(rd, &geom, s));
     B2_CUDA(cudaEventRecord(kernel->stop, s));

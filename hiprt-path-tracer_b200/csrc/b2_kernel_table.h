@@ -22,7 +22,7 @@ struct B2LaunchGeom
     const void* presampling_parameters; /* ReSTIR_DI_LightsPresampling only: host pointer to its LightPresamplingParameters argument */
     void* directional_masks_ull; /* ReSTIR_Directional_Reuse_Compute only: its two output buffers (device pointers) */
     void* directional_radius;
-    int persistent; /* MegaKernel only: 0 = one thread per pixel, 1 = persistent warps, 2 = persistent + phased (pooled rays) */
+    int persistent; /* MegaKernel only: 0 = one thread per pixel, 1 = persistent warps, 2 = persistent + phased (pooled rays), 3 = wavefront */
 };
 
 struct B2KernelEntry

@@ -589,6 +589,8 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
         b2_flush_counters(local_counters);
 }
 
+#include "b2_wavefront.h"
+
 /* ReSTIR_DI_LightsPresampling: one thread per presampled light (kernels/ReSTIR/DI/LightsPresampling.h:78-110); arguments in the
  * reference's order (LightPresamplingParameters, HIPRTRenderData) */
 template <class V>
@@ -646,6 +648,8 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
     if (rows == 0)
         return cudaSuccess;
     const int tiles_x = (g.width + B2_TILE_W - 1) / B2_TILE_W;
+    if (PASS == B2_PASS_MEGAKERNEL && g.persistent == 3)
+        return launch_wavefront<V>(rd, g, rows, stream);
     if (PASS == B2_PASS_MEGAKERNEL && g.persistent)
     {
         /* per instantiation and per device: resident blocks per SM, SM count, and a ring of work counters (a launch

@@ -1,0 +1,522 @@
+/*
+ * b2_wavefront.h -- the MegaKernel pass as a WAVEFRONT of small kernels (included by b2_kernels.cu inside its namespaces).
+ *
+ * Same per-pixel code as the other forms (megakernel_begin / megakernel_stage1 / megakernel_stage2 / megakernel_end of
+ * b2_pathtrace.h, i.e. the reference's Megakernel.h:22-144 cut at its rays) -- what changes is where a path lives between its
+ * rays: in the phased form a path stays in the registers of one thread of a persistent 512-thread block for its whole life,
+ * which caps the SM at 16 warps (ncu, profiles/r02_ncu_precise.md: issue slots 17 % busy, shading at 6.5 of 32 lanes because the
+ * lanes of a warp hold 32 different materials, traversal waiting on dependent node fetches with 16 warps to hide them). Here the
+ * path state is parked in HBM between stages (B200: 180 GB, 7 TB/s; ~0.7 KB per path) and every stage gets the launch shape it
+ * wants:
+ *   wf_trace   : ALL rays of the frame's current bounce in one queue, drained by persistent 64-register warps (32 warps / SM,
+ *                traversal stack in shared memory) with the same converged step loop + dynamic refill as the block pool
+ *   wf_stage1/2: one thread per live path, paths SORTED BY THE MATERIAL they are about to shade (counting sort on the material
+ *                index of the main hit), so that the lanes of a warp run the same lobes of the principled BSDF
+ * Paths never move between threads mid-stage, RNG streams and arithmetic are per path: frames are bit-identical to the other
+ * forms (tests/test_gpu_parity.py runs all of them against the same fixtures and against each other).
+ *
+ * Per launch (one sample of every owned pixel): wf_begin, then nb_bounces + 2 rounds of
+ *   wf_trace(A) -> wf_sort_count -> wf_sort_scan -> wf_sort_scatter -> wf_stage1 -> [wf_trace(B): RIS variants] -> wf_stage2
+ * all on the caller's stream, sized by device-side counters (no host round trip; a kernel whose list is empty returns at once).
+ */
+#ifndef B2_WAVEFRONT_H
+#define B2_WAVEFRONT_H
+
+#define B2_WF_RAYS 5           /* ray slots per path: main, deferred X, deferred Y, envmap light, envmap BSDF (slot 0 doubles as the sequential ray) */
+#define B2_WF_STAGE_THREADS 128
+#define B2_WF_TRACE_THREADS 256
+#define B2_WF_TRACE_MIN_BLOCKS 4
+#define B2_WF_SORT_BUCKETS 1024 /* material index & 1023; the last bucket also takes paths whose main ray missed */
+
+enum { WF_C_ALIVE = 0, WF_C_MID = 1, WF_C_NEXT = 2, WF_C_RAYS = 3, WF_C_CURSOR = 4, WF_C_COUNT = 8 };
+
+template <class V>
+struct alignas(16) WfPath
+{
+    PathState s;
+    BouncePhase<V> ph;
+    unsigned int have; /* rays of this path in flight: bits 0..4 = slots of trace A, bit 8 = the sequential ray (slot 0) of trace B */
+};
+
+struct WfBuffers
+{
+    unsigned char* paths;   /* n_paths records of WfPath<V> */
+    float4* slot_a;         /* n_paths * B2_WF_RAYS: ray (origin, t_max) -> hit (t, u, v, prim) */
+    float4* slot_b;         /* ray (direction, skip | any-hit flag) -> hit (ng, 0) */
+    int* ray_list;          /* slots to trace in the next wf_trace */
+    int* list[3];           /* path ids: live paths (two, ping-pong) and the material-sorted copy */
+    unsigned int* keys;     /* sort bucket per entry of the live list */
+    unsigned int* counters; /* WF_C_* */
+    unsigned int* buckets;  /* 2 * B2_WF_SORT_BUCKETS: histogram, then running offsets */
+    int n_paths;
+};
+
+__device__ __forceinline__ void wf_path_pixel(int path, const B2LaunchGeom& g, uint32_t& x, uint32_t& y)
+{
+    x = (uint32_t)(path % g.width);
+    y = b2_global_row((uint32_t)(path / g.width), g);
+}
+
+/* warp-aggregated append of `value` to list[counter++] by the lanes with `take` set; every lane of the warp must call it */
+__device__ __forceinline__ void wf_append(int* list, unsigned int* counter, bool take, int value)
+{
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int takers = __ballot_sync(0xFFFFFFFFu, take);
+    if (takers == 0u)
+        return;
+    unsigned int base = 0;
+    if (lane == (unsigned int)(__ffs(takers) - 1))
+        base = atomicAdd(counter, (unsigned int)__popc(takers));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(takers) - 1);
+    if (take)
+        list[base + __popc(takers & ((1u << lane) - 1u))] = value;
+}
+
+/* drops the thread's ray k into its slot and the trace list; returns the have-bit */
+__device__ __forceinline__ unsigned int wf_deposit(const Ctx& ctx, const WfBuffers& b, int path, int k, const RayRequest& ray, bool thread_active)
+{
+    const bool have = thread_active && ray.kind != B2_RAY_NONE && ctx.bvh.node_count != 0;
+    const int slot = path * B2_WF_RAYS + k;
+    if (have)
+    {
+        b.slot_a[slot] = make_float4(ray.origin.x, ray.origin.y, ray.origin.z, ray.t_max);
+        b.slot_b[slot] = make_float4(ray.direction.x, ray.direction.y, ray.direction.z, __int_as_float((ray.skip_prim << 1) | (ray.kind == B2_RAY_ANY_HIT ? 1 : 0)));
+    }
+    wf_append(b.ray_list, b.counters + WF_C_RAYS, have, slot);
+    return have ? (1u << k) : 0u;
+}
+
+__device__ __forceinline__ void wf_result(const WfBuffers& b, int path, int k, bool have, B2Hit& out)
+{
+    out.t = -1.0f;
+    out.u = out.v = 0.0f;
+    out.prim = -1;
+    out.ng = v3(0.0f);
+    if (have)
+    {
+        const float4 a = b.slot_a[path * B2_WF_RAYS + k], c = b.slot_b[path * B2_WF_RAYS + k];
+        out.t = a.x;
+        out.u = a.y;
+        out.v = a.z;
+        out.prim = __float_as_int(a.w);
+        out.ng = v3(c.x, c.y, c.z);
+    }
+}
+
+/* Megakernel.h:33-79 for every owned pixel: primary-miss pixels are finished here, hit pixels become live paths */
+template <class V>
+__global__ void __launch_bounds__(B2_WF_STAGE_THREADS) wf_begin(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b)
+{
+    extern __shared__ __align__(16) unsigned char wf_smem[];
+    b2_block_constants_init(rd);
+    Ctx ctx;
+    b2_make_ctx(ctx, rd, reinterpret_cast<uint64_t*>(wf_smem), nullptr, g_faults, B2_WF_STAGE_THREADS);
+    const int path = blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = false;
+    if (path < b.n_paths)
+    {
+        uint32_t x, y;
+        wf_path_pixel(path, geom, x, y);
+        const int res_x = rd.render_settings.render_resolution.x, res_y = rd.render_settings.render_resolution.y;
+        if (x < (uint32_t)res_x && y < (uint32_t)res_y)
+        {
+            const uint32_t pixel_index = x + y * (uint32_t)res_x;
+            if (rd.aux_buffers.pixel_active[pixel_index])
+            {
+                if (rd.g_buffer.first_hit_prim_index[pixel_index] == -1)
+                    megakernel_primary_miss<V>(ctx, x, y, pixel_index);
+                else
+                {
+                    WfPath<V>* record = reinterpret_cast<WfPath<V>*>(b.paths) + path;
+                    PathState s;
+                    alive = megakernel_begin<V>(ctx, x, y, s);
+                    if (alive)
+                    {
+                        record->s = s;
+                        record->ph.reset();
+                        record->have = 0u;
+                    }
+                }
+            }
+        }
+    }
+    wf_append(b.list[0], b.counters + WF_C_ALIVE, alive, path);
+}
+
+/* sort bucket of every live path = the material it shades next: the material of the main ray's hit (bounce > 0: slot 0 holds the
+ * traced result by now) or of the G-buffer's primary hit (bounce 0) */
+template <class V>
+__global__ void __launch_bounds__(256) wf_sort_count(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b, int list_in)
+{
+    __shared__ unsigned int hist[B2_WF_SORT_BUCKETS];
+    for (int i = threadIdx.x; i < B2_WF_SORT_BUCKETS; i += blockDim.x)
+        hist[i] = 0u;
+    __syncthreads();
+    const unsigned int count = b.counters[WF_C_ALIVE];
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        const int path = b.list[list_in][i];
+        const WfPath<V>* record = reinterpret_cast<const WfPath<V>*>(b.paths) + path;
+        int prim;
+        if (record->have & 1u)
+            prim = __float_as_int(b.slot_a[path * B2_WF_RAYS].w);
+        else
+            prim = record->s.hit.primitive_index;
+        const unsigned int key = prim >= 0 ? ((unsigned int)rd.buffers.material_indices[prim] % (B2_WF_SORT_BUCKETS - 1)) : (B2_WF_SORT_BUCKETS - 1);
+        b.keys[i] = key;
+        atomicAdd(&hist[key], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B2_WF_SORT_BUCKETS; i += blockDim.x)
+        if (hist[i])
+            atomicAdd(&b.buckets[i], hist[i]);
+}
+
+/* one block: exclusive prefix of the histogram into the running offsets; also resets what the next stage appends to */
+__global__ void __launch_bounds__(B2_WF_SORT_BUCKETS) wf_sort_scan(const WfBuffers b)
+{
+    __shared__ unsigned int scan[B2_WF_SORT_BUCKETS];
+    const unsigned int mine = b.buckets[threadIdx.x];
+    scan[threadIdx.x] = mine;
+    __syncthreads();
+    for (int offset = 1; offset < B2_WF_SORT_BUCKETS; offset <<= 1)
+    {
+        const unsigned int add = threadIdx.x >= (unsigned int)offset ? scan[threadIdx.x - offset] : 0u;
+        __syncthreads();
+        scan[threadIdx.x] += add;
+        __syncthreads();
+    }
+    b.buckets[B2_WF_SORT_BUCKETS + threadIdx.x] = scan[threadIdx.x] - mine;
+    b.buckets[threadIdx.x] = 0u; /* histogram cleared for the next round */
+    if (threadIdx.x == 0)
+    {
+        /* trace A is over: stage 1 starts with empty lists */
+        b.counters[WF_C_MID] = 0u;
+        b.counters[WF_C_RAYS] = 0u;
+        b.counters[WF_C_CURSOR] = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) wf_sort_scatter(const WfBuffers b, int list_in, int list_out)
+{
+    const unsigned int count = b.counters[WF_C_ALIVE];
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    {
+        const unsigned int position = atomicAdd(&b.buckets[B2_WF_SORT_BUCKETS + b.keys[i]], 1u);
+        b.list[list_out][position] = b.list[list_in][i];
+    }
+}
+
+/* between trace B and stage 2 / at the end of a round: one thread moves the counters on */
+__global__ void wf_advance(const WfBuffers b, int after_stage)
+{
+    if (after_stage == 1)
+    {
+        /* trace B is over: stage 2 appends the next round's rays and live paths */
+        b.counters[WF_C_RAYS] = 0u;
+        b.counters[WF_C_CURSOR] = 0u;
+        b.counters[WF_C_NEXT] = 0u;
+    }
+    else
+        b.counters[WF_C_ALIVE] = b.counters[WF_C_NEXT];
+}
+
+/* All rays of the queue, drained by persistent warps: a lane whose ray finished takes the next one while the others keep
+ * stepping (the block pool's loop, fed from HBM instead of shared memory). */
+template <bool COUNTERS>
+__global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) wf_trace(const B2BvhDevice* __restrict__ bvh_descriptor, const WfBuffers b, int stack_entries)
+{
+    extern __shared__ __align__(16) unsigned char wf_smem[];
+    B2BvhDevice bvh;
+    bvh.nodes = nullptr;
+    bvh.tris = nullptr;
+    bvh.node_count = bvh.tri_count = 0;
+    if (bvh_descriptor != nullptr)
+        bvh = *bvh_descriptor;
+    uint64_t* stack = reinterpret_cast<uint64_t*>(wf_smem) + threadIdx.x;
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int lanes_below = (1u << lane) - 1u;
+    const int count = (int)b.counters[WF_C_RAYS];
+    B2TraversalCounters local_counters;
+    local_counters.rays = local_counters.nodes = local_counters.tris = 0;
+
+    B2Traversal t;
+    bool busy = false;
+    bool drained = false; /* warp-uniform */
+    int slot = 0;
+    while (true)
+    {
+        const unsigned int idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (idle != 0u && !drained && ((int)__popc(idle) >= 8 || idle == 0xFFFFFFFFu))
+        {
+            const int wanted = __popc(idle);
+            int base = 0;
+            if (lane == 0)
+                base = (int)atomicAdd(b.counters + WF_C_CURSOR, (unsigned int)wanted);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (!busy)
+            {
+                const int i = base + __popc(idle & lanes_below);
+                if (i < count)
+                {
+                    slot = b.ray_list[i];
+                    const float4 a = b.slot_a[slot], c = b.slot_b[slot];
+                    const int packed = __float_as_int(c.w);
+                    b2_traverse_begin(t, (packed & 1) != 0, v3(a.x, a.y, a.z), v3(c.x, c.y, c.z), a.w, packed >> 1, stack);
+                    busy = true;
+                }
+            }
+            drained = base + wanted >= count;
+        }
+        if (!__any_sync(0xFFFFFFFFu, busy))
+        {
+            if (drained)
+                break;
+            continue;
+        }
+        if (busy)
+        {
+            if (!b2_traverse_step(t, bvh, B2_WF_TRACE_THREADS, g_faults, stack_entries))
+            {
+                b.slot_a[slot] = make_float4(t.best.t, t.best.u, t.best.v, __int_as_float(t.best.prim));
+                b.slot_b[slot] = make_float4(t.best.ng.x, t.best.ng.y, t.best.ng.z, 0.0f);
+                if (COUNTERS)
+                {
+                    local_counters.rays += 1;
+                    local_counters.nodes += t.n_nodes;
+                    local_counters.tris += t.n_tris;
+                }
+                busy = false;
+            }
+        }
+    }
+    if (COUNTERS)
+        b2_flush_counters(local_counters);
+}
+
+/* stage 1 of every live path, in material order: resolve the previous vertex's NEE, take the main hit, begin this vertex's NEE */
+template <class V>
+__global__ void __launch_bounds__(B2_WF_STAGE_THREADS) wf_stage1(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b, int list_in, int list_out)
+{
+    extern __shared__ __align__(16) unsigned char wf_smem[];
+    b2_block_constants_init(rd);
+    B2TraversalCounters local_counters;
+    local_counters.rays = local_counters.nodes = local_counters.tris = 0;
+    Ctx ctx;
+    b2_make_ctx(ctx, rd, reinterpret_cast<uint64_t*>(wf_smem), V::COUNTERS ? &local_counters : nullptr, g_faults, B2_WF_STAGE_THREADS);
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int count = b.counters[WF_C_ALIVE];
+    if (blockIdx.x * blockDim.x >= count)
+        return; /* block-uniform */
+    const bool active = i < count;
+    const int path = active ? b.list[list_in][i] : 0;
+    bool alive = false;
+    unsigned int have_b = 0u;
+    if (active)
+    {
+        WfPath<V>* record = reinterpret_cast<WfPath<V>*>(b.paths) + path;
+        WfPath<V> p = *record;
+        B2Hit results[B2_WF_RAYS];
+#pragma unroll
+        for (int k = 0; k < B2_WF_RAYS; k++)
+            wf_result(b, path, k, (p.have >> k) & 1u, results[k]);
+        RayRequest sequential;
+        request_none(sequential);
+        alive = megakernel_stage1<V>(ctx, p.s, p.ph, p.s.payload.bounce > 0 ? &results[0] : nullptr, results[1], results[2], results[3], results[4], sequential);
+        if (!alive)
+        {
+            megakernel_end(ctx, p.s);
+            request_none(sequential);
+        }
+        p.have = 0u;
+        if (alive)
+        {
+            /* the sequential ray takes slot 0 (the main ray's result has been consumed) */
+            if (Nee<V>::HAS_SEQUENTIAL_RAY && sequential.kind != B2_RAY_NONE && ctx.bvh.node_count != 0)
+            {
+                const int slot = path * B2_WF_RAYS;
+                b.slot_a[slot] = make_float4(sequential.origin.x, sequential.origin.y, sequential.origin.z, sequential.t_max);
+                b.slot_b[slot] = make_float4(sequential.direction.x, sequential.direction.y, sequential.direction.z,
+                                             __int_as_float((sequential.skip_prim << 1) | (sequential.kind == B2_RAY_ANY_HIT ? 1 : 0)));
+                have_b = 1u;
+                p.have = 1u << 8;
+            }
+            *record = p;
+        }
+    }
+    if (Nee<V>::HAS_SEQUENTIAL_RAY)
+        wf_append(b.ray_list, b.counters + WF_C_RAYS, have_b != 0u, path * B2_WF_RAYS);
+    wf_append(b.list[list_out], b.counters + WF_C_MID, alive, path);
+    if (V::COUNTERS)
+        b2_flush_counters(local_counters);
+}
+
+/* stage 2: rest of the NEE sampling, envmap NEE, next direction; ends with the rays of the next trace A */
+template <class V>
+__global__ void __launch_bounds__(B2_WF_STAGE_THREADS) wf_stage2(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b, int list_in, int list_out)
+{
+    extern __shared__ __align__(16) unsigned char wf_smem[];
+    b2_block_constants_init(rd);
+    B2TraversalCounters local_counters;
+    local_counters.rays = local_counters.nodes = local_counters.tris = 0;
+    Ctx ctx;
+    b2_make_ctx(ctx, rd, reinterpret_cast<uint64_t*>(wf_smem), V::COUNTERS ? &local_counters : nullptr, g_faults, B2_WF_STAGE_THREADS);
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int count = b.counters[WF_C_MID];
+    if (blockIdx.x * blockDim.x >= count)
+        return; /* block-uniform */
+    const bool active = i < count;
+    const int path = active ? b.list[list_in][i] : 0;
+    bool alive = false;
+    RayRequest rays[B2_WF_RAYS];
+#pragma unroll
+    for (int k = 0; k < B2_WF_RAYS; k++)
+        request_none(rays[k]);
+    WfPath<V>* record = reinterpret_cast<WfPath<V>*>(b.paths) + path;
+    if (active)
+    {
+        WfPath<V> p = *record;
+        B2Hit sequential_result;
+        wf_result(b, path, 0, (p.have >> 8) & 1u, sequential_result);
+        alive = megakernel_stage2<V>(ctx, p.s, p.ph, sequential_result, rays[0], rays[1], rays[2], rays[3], rays[4]);
+        if (!alive)
+        {
+            megakernel_end(ctx, p.s);
+#pragma unroll
+            for (int k = 0; k < B2_WF_RAYS; k++)
+                request_none(rays[k]);
+        }
+        if (!Nee<V>::HAS_DEFERRED_Y)
+            request_none(rays[2]);
+        if (alive)
+        {
+            p.have = 0u; /* the bits are set below, after the deposits */
+            *record = p;
+        }
+    }
+    unsigned int have = 0u;
+#pragma unroll
+    for (int k = 0; k < B2_WF_RAYS; k++)
+        if (k < geom.pool_rays)
+            have |= wf_deposit(ctx, b, path, k, rays[k], active && alive);
+    if (active && alive)
+        record->have = have;
+    wf_append(b.list[list_out], b.counters + WF_C_NEXT, alive, path);
+    if (V::COUNTERS)
+        b2_flush_counters(local_counters);
+}
+
+/* host side: scratch buffers per device (grown on demand, kept for the life of the library) and the launch sequence */
+struct WfScratch
+{
+    void* base = nullptr;
+    size_t bytes = 0;
+    unsigned int* counters = nullptr;
+    unsigned int* buckets = nullptr;
+};
+
+template <class V>
+cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, int rows, cudaStream_t stream)
+{
+    static WfScratch scratch[B2_MAX_DEVICES];
+    static std::mutex scratch_mutex;
+    static int sm_count[B2_MAX_DEVICES] = {};
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess)
+        return e;
+    if (device < 0 || device >= B2_MAX_DEVICES)
+        return cudaErrorInvalidDevice;
+
+    const size_t n_paths = (size_t)rows * g.width;
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t paths_bytes = align(n_paths * sizeof(WfPath<V>));
+    const size_t slots_bytes = align(n_paths * B2_WF_RAYS * sizeof(float4));
+    const size_t ray_list_bytes = align(n_paths * B2_WF_RAYS * sizeof(int));
+    const size_t list_bytes = align(n_paths * sizeof(int));
+    const size_t total = paths_bytes + 2 * slots_bytes + ray_list_bytes + 4 * list_bytes;
+    WfScratch& sc = scratch[device];
+    {
+        std::lock_guard<std::mutex> lock(scratch_mutex);
+        if (!sm_count[device])
+        {
+            e = cudaDeviceGetAttribute(&sm_count[device], cudaDevAttrMultiProcessorCount, device);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(wf_trace<V::COUNTERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_STACK_ENTRIES * B2_WF_TRACE_THREADS * 8);
+            if (e != cudaSuccess)
+                return e;
+        }
+        if (!sc.counters)
+        {
+            e = cudaMalloc((void**)&sc.counters, WF_C_COUNT * sizeof(unsigned int));
+            if (e == cudaSuccess) e = cudaMalloc((void**)&sc.buckets, 2 * B2_WF_SORT_BUCKETS * sizeof(unsigned int));
+            if (e != cudaSuccess)
+                return e;
+        }
+        if (sc.bytes < total)
+        {
+            /* the scratch of the previous size may still be in use by work in flight on any stream of this device */
+            e = cudaDeviceSynchronize();
+            if (e != cudaSuccess)
+                return e;
+            cudaFree(sc.base);
+            sc.base = nullptr;
+            sc.bytes = 0;
+            e = cudaMalloc(&sc.base, total);
+            if (e != cudaSuccess)
+                return e;
+            sc.bytes = total;
+        }
+    }
+    WfBuffers b;
+    unsigned char* p = static_cast<unsigned char*>(sc.base);
+    b.paths = p; p += paths_bytes;
+    b.slot_a = reinterpret_cast<float4*>(p); p += slots_bytes;
+    b.slot_b = reinterpret_cast<float4*>(p); p += slots_bytes;
+    b.ray_list = reinterpret_cast<int*>(p); p += ray_list_bytes;
+    for (int i = 0; i < 3; i++)
+    {
+        b.list[i] = reinterpret_cast<int*>(p);
+        p += list_bytes;
+    }
+    b.keys = reinterpret_cast<unsigned int*>(p);
+    b.counters = sc.counters;
+    b.buckets = sc.buckets;
+    b.n_paths = (int)n_paths;
+
+    e = cudaMemsetAsync(sc.counters, 0, WF_C_COUNT * sizeof(unsigned int), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc.buckets, 0, 2 * B2_WF_SORT_BUCKETS * sizeof(unsigned int), stream);
+    if (e != cudaSuccess)
+        return e;
+
+    const int stage_blocks = (int)((n_paths + B2_WF_STAGE_THREADS - 1) / B2_WF_STAGE_THREADS);
+    const int sort_blocks = sm_count[device] * 4;
+    const int trace_blocks = sm_count[device] * B2_WF_TRACE_MIN_BLOCKS;
+    const size_t stage_smem = (size_t)g.stack_entries * B2_WF_STAGE_THREADS * 8;
+    const size_t trace_smem = (size_t)g.stack_entries * B2_WF_TRACE_THREADS * 8;
+    const B2BvhDevice* bvh = reinterpret_cast<const B2BvhDevice*>(rd->GPU_BVH);
+
+    wf_begin<V><<<stage_blocks, B2_WF_STAGE_THREADS, stage_smem, stream>>>(*rd, g, b);
+    int nb_bounces = rd->render_settings.nb_bounces;
+    if (nb_bounces < 0)
+        nb_bounces = 0;
+    /* lists: [0] live paths of the round -> sorted into [2] -> stage-1 survivors appended to [1] -> stage-2 survivors appended to
+     * [0] again (its old content has been consumed by the scatter before stage 1 started) */
+    const int cur = 0, other = 1;
+    for (int round = 0; round < nb_bounces + 2; round++)
+    {
+        if (round > 0)
+            wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, b, g.stack_entries);
+        wf_sort_count<V><<<sort_blocks, 256, 0, stream>>>(*rd, g, b, cur);
+        wf_sort_scan<<<1, B2_WF_SORT_BUCKETS, 0, stream>>>(b);
+        wf_sort_scatter<<<sort_blocks, 256, 0, stream>>>(b, cur, 2);
+        wf_stage1<V><<<stage_blocks, B2_WF_STAGE_THREADS, stage_smem, stream>>>(*rd, g, b, 2, other); /* survivors -> list[other] */
+        if (Nee<V>::HAS_SEQUENTIAL_RAY)
+            wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, b, g.stack_entries);
+        wf_advance<<<1, 1, 0, stream>>>(b, 1);
+        wf_stage2<V><<<stage_blocks, B2_WF_STAGE_THREADS, stage_smem, stream>>>(*rd, g, b, other, cur); /* survivors -> list[cur] */
+        wf_advance<<<1, 1, 0, stream>>>(b, 2);
+    }
+    return cudaGetLastError();
+}
+
+#endif

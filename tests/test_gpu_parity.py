@@ -73,6 +73,27 @@ def test_cuda_fast_flavour_agrees_statistically(b2pt, gpu_ctx, name):
     assert abs(fb.reshape(-1, 3).mean() - ref.mean()) <= 0.01 * abs(ref.mean()) + 1e-6
 
 
+@pytest.mark.parametrize("name", ["c2_128x72", "c3_syn_96x54"])
+def test_scene_derived_inputs_match_the_reference_dump(b2pt, gpu_ctx, name):
+    """what the host derives from a scene before the first launch -- packed materials (33 words each), triangle
+    areas, the emissive triangle list and the power alias table -- against the arrays the reference's own host code produced
+    (dumped by oracle/_ref into the fixture), bit for bit."""
+    g, meta = load_golden(name)
+    r = make_renderer(b2pt, gpu_ctx, meta, precise=True)
+    n_materials = g["packed_materials"].size // 33
+    d = r.derived(n_materials)
+    r.close()
+    ours = d["packed_materials"].copy()
+    theirs = g["packed_materials"].reshape(n_materials, 33).copy()
+    ours[:, 0] &= 0xFF      # struct padding bytes after the flags byte are indeterminate in the reference
+    theirs[:, 0] &= 0xFF
+    assert np.array_equal(ours, theirs)
+    assert np.array_equal(d["triangle_areas"].view(np.uint32), g["triangle_areas"].view(np.uint32))
+    assert np.array_equal(d["emissive_triangles"], g["emissive_prims"])
+    assert np.array_equal(d["alias_alias"], g["power_alias"])
+    assert np.array_equal(d["alias_probas"].view(np.uint32), g["power_probas"].view(np.uint32))
+
+
 def test_c1_512_against_reference_oracle_on_host(b2pt, gpu_ctx, tmp_path):
     """BASELINE.json configs[0] at full size: Cornell 512x512, 1 spp, 3 bounces, Lambertian + uniform one-light NEE."""
     ref = run_oracle("ref", "c1", "cornell_pbr_1x1", 512, 512, 1, 3, tmp_path)
@@ -144,10 +165,10 @@ def megakernel_form(monkeypatch):
     return choose
 
 
-@pytest.mark.parametrize("form", ["persistent", "tiles"])
+@pytest.mark.parametrize("form", ["phased", "wavefront", "persistent", "tiles"])
 @pytest.mark.parametrize("name", ["c1_128x72", "c2_128x72", "c3_syn_96x54", "c4_synenv_96x54_fused"])
 def test_other_megakernel_forms_match_golden(b2pt, gpu_ctx, megakernel_form, name, form):
-    """The fixtures above run through the default (phased) MegaKernel; the other two forms must meet the same bars."""
+    """The fixtures above run through the default form of the MegaKernel; every form must meet the same bars."""
     megakernel_form(form)
     g, meta = load_golden(name)
     r = make_renderer(b2pt, gpu_ctx, meta, precise=True)
@@ -166,7 +187,7 @@ def test_schedule_independence_at_full_size(b2pt, gpu_ctx, megakernel_form, vari
     persistent warps with regeneration, phased with block-pooled rays) must not change a single bit of the frame -- every
     pixel owns its RNG stream -- and no traversal may trip a guard."""
     frames = {}
-    for form in ("phased", "persistent", "tiles"):
+    for form in ("phased", "wavefront", "persistent", "tiles"):
         megakernel_form(form)
         r = b2pt.Renderer(gpu_ctx, width, height, variant, precise=True)
         r.set_scene_file(DATA / "cornell_pbr_16x9.b2scene")
@@ -179,5 +200,6 @@ def test_schedule_independence_at_full_size(b2pt, gpu_ctx, megakernel_form, vari
         r.close()
     assert gpu_ctx.faults() == dict(traversal_guard_trips=0, boundary_guard_trips=0, stack_overflows=0)
     assert np.array_equal(frames["phased"].view(np.uint32), frames["tiles"].view(np.uint32))
+    assert np.array_equal(frames["wavefront"].view(np.uint32), frames["tiles"].view(np.uint32))
     assert np.array_equal(frames["persistent"].view(np.uint32), frames["tiles"].view(np.uint32))
     assert np.isfinite(frames["phased"]).all() and frames["phased"].mean() > 0
