@@ -401,12 +401,12 @@ def main():
     barrier()
     t0 = time.perf_counter()
     dev_ms = 0.0
-    launches_before = sum(v["launches"] for v in r.pass_times().values())
+    launches_before = ctx.cuda_launches()
     for _ in range(a.steps):
         dev_ms += step(False)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    launches = sum(v["launches"] for v in r.pass_times().values()) - launches_before
+    launches = ctx.cuda_launches() - launches_before   # CUDA kernels of the passes (the NCCL pack / unpack kernels of N > 1 are extra)
     clocks = sampler.stop() if rank == 0 else None
     # the renderer's own CUDA events bracket every step on its stream; the wall clock around the barrier pair is an upper bound
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")

@@ -139,6 +139,11 @@ class Context:
         check(lib().b2pt_counters_read(self.handle, C.byref(c)))
         return dict(rays=c.rays, nodes=c.nodes, triangles=c.triangles)
 
+    def cuda_launches(self):
+        n = C.c_uint64()
+        check(lib().b2pt_cuda_launch_count(self.handle, C.byref(n)))
+        return n.value
+
     def faults(self, reset=True):
         f = Faults()
         check(lib().b2pt_faults_read(self.handle, C.byref(f), int(reset)))

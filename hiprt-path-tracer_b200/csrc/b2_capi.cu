@@ -715,6 +715,17 @@ int b2pt_counters_read(b2pt_ctx* ctx, b2pt_counters_t* out)
     return B2PT_OK;
 }
 
+/* CUDA kernels launched by this library's path-tracing passes so far (all contexts of the process) */
+int b2pt_cuda_launch_count(b2pt_ctx*, uint64_t* out_count)
+{
+    if (!out_count) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    uint64_t n = 0;
+    for (const B2KernelUnit& unit : kernel_units())
+        n += unit.launches_read();
+    *out_count = n;
+    return B2PT_OK;
+}
+
 int b2pt_faults_read(b2pt_ctx* ctx, b2pt_faults_t* out, int reset)
 {
     B2_SELECT_DEVICE(ctx);

@@ -47,6 +47,7 @@ struct B2KernelUnit
     cudaError_t (*counters_reset)();
     cudaError_t (*counters_read)(unsigned long long out[3]);
     cudaError_t (*faults_read)(unsigned int out[B2_FAULT_COUNT], int reset);
+    unsigned long long (*launches_read)();
 };
 void b2_register_kernel_unit(const B2KernelUnit* unit);
 

@@ -17,6 +17,7 @@
 #include "b2_kernels_body.h"
 
 #include <atomic>
+#include <map>
 #include <mutex>
 
 #if defined(B2_FLAVOUR_PRECISE)
@@ -50,6 +51,8 @@ namespace B2_NS
 {
 static __device__ unsigned long long g_counters[3];
 static __device__ unsigned int g_faults[B2_FAULT_COUNT];
+/* CUDA kernels this object launched (bench.py: gpu_launches) */
+static std::atomic<unsigned long long> g_cuda_launches{ 0 };
 
 /* Pixel rows are partitioned across GPUs in interleaved bands of B2_BAND_ROWS rows (band b belongs to rank b % world);
  * a launch covers the bands of one rank. `local_row` counts the rows of this rank's bands, top to bottom. */
@@ -626,6 +629,7 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
         if (!g.directional_masks_ull || !g.directional_radius)
             return cudaErrorInvalidValue;
         const int tx = (g.width + B2_TILE_W - 1) / B2_TILE_W, ty = (g.height + B2_TILE_H - 1) / B2_TILE_H;
+        g_cuda_launches += 1;
         directional_reuse_kernel<<<tx * ty, B2_BLOCK_THREADS, 0, stream>>>(*rd, nullptr, (unsigned long long*)g.directional_masks_ull, (uint8_t*)g.directional_radius, tx);
         return cudaGetLastError();
     }
@@ -639,6 +643,7 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
             const int count = params.number_of_subsets * params.subset_size;
             if (count <= 0)
                 return cudaSuccess;
+            g_cuda_launches += 1;
             lights_presampling_kernel<V><<<(count + 127) / 128, 128, 0, stream>>>(params, *rd);
             return cudaGetLastError();
         }
@@ -650,6 +655,14 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
     const int tiles_x = (g.width + B2_TILE_W - 1) / B2_TILE_W;
     if (PASS == B2_PASS_MEGAKERNEL && g.persistent == 3)
         return launch_wavefront<V>(rd, g, rows, stream);
+    if constexpr (V::DIRECT == B2_LSS_RESTIR_DI)
+    {
+        /* the ray-delimited ReSTIR DI passes follow the MegaKernel's form: frame-wide phases + the global ray queue on big scenes */
+        if (PASS == B2_PASS_RESTIR_DI_INITIAL_CANDIDATES && g.persistent == 3)
+            return launch_wavefront_pass<WfInitialCandidates<V>, V>(rd, g, rows, stream);
+        if (PASS == B2_PASS_RESTIR_DI_SPATIOTEMPORAL && g.persistent == 3 && restir_di_spatiotemporal_supported<V>(*rd))
+            return launch_wavefront_pass<WfSpatiotemporalReuse<V>, V>(rd, g, rows, stream);
+    }
     if (PASS == B2_PASS_MEGAKERNEL && g.persistent)
     {
         /* per instantiation and per device: resident blocks per SM, SM count, and a ring of work counters (a launch
@@ -685,6 +698,7 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
         if (e != cudaSuccess)
             return e;
         const unsigned int total_tiles = (unsigned int)tiles_x * (unsigned int)((rows + 3) / 4);
+        g_cuda_launches += 1;
         if (g.persistent == 2)
             megakernel_phased<V><<<pd.sm_count * pd.blocks_per_sm[1], B2_MK_THREADS, B2_PH_SMEM_BYTES_FOR(g.stack_entries, g.pool_rays), stream>>>(*rd, g, tiles_x, total_tiles, counter);
         else
@@ -692,6 +706,7 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
         return cudaGetLastError();
     }
     const int tiles_y = (rows + B2_TILE_H - 1) / B2_TILE_H;
+    g_cuda_launches += 1;
     pass_kernel<V, PASS><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x);
     return cudaGetLastError();
 }
@@ -774,6 +789,8 @@ static cudaError_t unit_faults_read(unsigned int out[B2_FAULT_COUNT], int reset)
     return cudaMemcpyToSymbol(g_faults, zero, sizeof(zero));
 }
 
+static unsigned long long unit_launches_read() { return g_cuda_launches.load(); }
+
 struct Registrar
 {
     Registrar()
@@ -788,6 +805,7 @@ struct Registrar
         u.counters_reset = &unit_counters_reset;
         u.counters_read = &unit_counters_read;
         u.faults_read = &unit_faults_read;
+        u.launches_read = &unit_launches_read;
         b2_register_kernel_unit(&u);
     }
 };

@@ -336,12 +336,13 @@ struct PairwiseMis
 {
     float mc;
 
-    template <class V>
-    B2_HD float weight(const Ctx& ctx, int reservoir_being_resampled_M, float reservoir_being_resampled_target_function, int center_pixel_reservoir_M,
-                       float center_pixel_reservoir_target_function, const DiSample& center_pixel_reservoir_sample, float target_function_at_center, int neighbor_pixel_index,
-                       bool neighbor_from_previous_frame, int valid_neighbors_count, int valid_neighbors_M_sum, bool update_mc, bool resampling_canonical, bool guard_zero_confidence, Rng& rng)
+    /* the weight of resampling one neighbour and the running canonical weight mc, given the target function of the CENTER pixel's
+     * canonical sample evaluated at that neighbour's surface (with visibility: ReSTIR_DI_BiasCorrectionUseVisibility); only read
+     * when update_mc */
+    B2_HD float weight_given(const b2pt_render_data& rd, int reservoir_being_resampled_M, float reservoir_being_resampled_target_function, int center_pixel_reservoir_M,
+                             float center_pixel_reservoir_target_function, float target_function_at_center, float target_function_center_sample_at_neighbor,
+                             int valid_neighbors_count, int valid_neighbors_M_sum, bool update_mc, bool resampling_canonical, bool guard_zero_confidence)
     {
-        const b2pt_render_data& rd = *ctx.rd;
         if (resampling_canonical)
             return mc == 0.0f ? 1.0f : mc;
 
@@ -359,9 +360,6 @@ struct PairwiseMis
 
         if (update_mc)
         {
-            DiSurface neighbor_pixel_surface = get_pixel_surface<V>(rd, neighbor_pixel_index, neighbor_from_previous_frame, rng);
-            float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, center_pixel_reservoir_sample, neighbor_pixel_surface);
-
             float nume_mc = target_function_center_sample_at_center / valid_neighbor_division_term * center_reservoir_M;
             float denom_mc = target_function_center_sample_at_neighbor * neighbors_confidence_sum + target_function_center_sample_at_center / valid_neighbor_division_term * center_reservoir_M;
 
@@ -380,6 +378,23 @@ struct PairwiseMis
                 mc += nume_mc / denom_mc / valid_neighbor_division_term * confidence_weights_multiplier;
         }
         return mi / valid_neighbor_division_term;
+    }
+
+    template <class V>
+    B2_HD float weight(const Ctx& ctx, int reservoir_being_resampled_M, float reservoir_being_resampled_target_function, int center_pixel_reservoir_M,
+                       float center_pixel_reservoir_target_function, const DiSample& center_pixel_reservoir_sample, float target_function_at_center, int neighbor_pixel_index,
+                       bool neighbor_from_previous_frame, int valid_neighbors_count, int valid_neighbors_M_sum, bool update_mc, bool resampling_canonical, bool guard_zero_confidence, Rng& rng)
+    {
+        const b2pt_render_data& rd = *ctx.rd;
+        float target_function_center_sample_at_neighbor = 0.0f;
+        if (!resampling_canonical && update_mc)
+        {
+            DiSurface neighbor_pixel_surface = get_pixel_surface<V>(rd, neighbor_pixel_index, neighbor_from_previous_frame, rng);
+            target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, center_pixel_reservoir_sample, neighbor_pixel_surface);
+        }
+        return weight_given(rd, reservoir_being_resampled_M, reservoir_being_resampled_target_function, center_pixel_reservoir_M, center_pixel_reservoir_target_function,
+                            target_function_at_center, target_function_center_sample_at_neighbor, valid_neighbors_count, valid_neighbors_M_sum, update_mc, resampling_canonical,
+                            guard_zero_confidence);
     }
 };
 
@@ -617,10 +632,81 @@ B2_HD DiSurface surface_from_hit(const HitInfo& hit, const Payload& payload, V3 
 }
 
 template <class V>
-B2_HD DiReservoir sample_initial_candidates(const Ctx& ctx, Payload& payload, const HitInfo& hit, V3 view_direction, Rng& rng, int pixel_x, int pixel_y)
+B2_HD bool restir_pass_prologue(const b2pt_render_data& rd, uint32_t x, uint32_t y, uint32_t& pixel_index)
+{
+    const b2pt_int2 res = rd.render_settings.render_resolution;
+    if (x >= (uint32_t)res.x || y >= (uint32_t)res.y)
+        return false;
+    pixel_index = x + y * res.x;
+    return true;
+}
+
+/* ---- InitialCandidates cut at its rays -------------------------------------------------------------------------------------
+ * The pass traces two rays per pixel, and what follows each depends on its result: the closest hit along BSDF candidate 0 (it
+ * becomes a reservoir candidate) and the visibility of the reservoir's final sample (ReSTIR_DI_DoVisibilityReuse). The per-pixel
+ * code is therefore three phases with a ray request between them:
+ *     phase A: light candidates, BSDF candidate 0 sampled            -> closest-hit ray
+ *     phase B: BSDF candidate 0 resampled, reservoir.end()           -> shadow ray towards the reservoir's sample
+ *     phase C: visibility reuse, store
+ * restir_di_initial_candidates_pixel below runs A, trace, B, trace, C for one pixel (the form the host port, the one-thread-per-pixel
+ * kernel and the goldens go through); the wavefront kernels of b2_kernels.cu run each phase over the whole frame and trace the
+ * frame's rays together (b2_wavefront.h). Same operations and RNG draws in the same order either way. */
+struct DiInitialState
+{
+    DiReservoir reservoir;
+    Rng rng;
+    V3 bsdf_sampled_direction;
+    float bsdf_sample_pdf_solid_angle;
+    int sampled_lobe_info;
+    int nb_light_candidates, nb_bsdf_candidates;
+    float envmap_candidate_probability;
+    int active;        /* 0: the pixel takes no part in the pass (nothing is stored) */
+    int pending_final; /* phase B requested the visibility ray */
+};
+
+/* what the three phases share: the pixel's primary hit rebuilt from the G-buffer (InitialCandidates.h:430-470) */
+template <class V>
+B2_HD void di_initial_surface(const b2pt_render_data& rd, uint32_t pixel_index, Rng& rng, HitInfo& hit, Payload& payload, V3& view_direction)
+{
+    hit = hit_info_defaults();
+    hit.geometric_normal = unpack_normal_oct24(rd.g_buffer.geometric_normals[pixel_index]);
+    hit.shading_normal = unpack_normal_oct24(rd.g_buffer.shading_normals[pixel_index]);
+    hit.inter_point = load_v3(rd.g_buffer.primary_hit_position, pixel_index);
+    hit.primitive_index = rd.g_buffer.first_hit_prim_index[pixel_index];
+
+    payload.init();
+    payload.material = unpack_material(load_packed_material(rd.g_buffer.materials, pixel_index));
+    reconstruct_first_hit<V>(payload.volume_state, payload.material, rd.buffers.material_indices, hit.primitive_index, rng);
+
+    V3 cam = v3(rd.current_camera.position.x, rd.current_camera.position.y, rd.current_camera.position.z);
+    view_direction = normalize(cam - hit.inter_point);
+}
+
+template <class V>
+B2_HD void restir_di_initial_phase_a(const Ctx& ctx, uint32_t x, uint32_t y, DiInitialState& st, RayRequest& candidate_ray)
 {
     const b2pt_render_data& rd = *ctx.rd;
     const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    request_none(candidate_ray);
+    st.active = 0;
+    st.pending_final = 0;
+    if (rd.buffers.emissive_triangles_count == 0 && rd.world_settings.ambient_light_type != 2)
+        return;
+    uint32_t pixel_index;
+    if (!restir_pass_prologue<V>(rd, x, y, pixel_index))
+        return;
+
+    Rng rng = make_rng(pixel_seed(rd, pixel_index));
+    if (!rd.aux_buffers.pixel_active[pixel_index] || rd.g_buffer.first_hit_prim_index[pixel_index] == -1)
+        return;
+    st.active = 1;
+
+    HitInfo hit;
+    Payload payload;
+    V3 view_direction;
+    di_initial_surface<V>(rd, pixel_index, rng, hit, payload, view_direction);
+
+    /* sample_initial_candidates (InitialCandidates.h:150-426) */
     int initial_nb_light_cand = di.initial_candidates.number_of_initial_light_candidates;
     int initial_nb_bsdf_cand = di.initial_candidates.number_of_initial_bsdf_candidates;
     const bool low_res = do_render_low_resolution(rd.render_settings);
@@ -634,6 +720,9 @@ B2_HD DiReservoir sample_initial_candidates(const Ctx& ctx, Payload& payload, co
         else
             envmap_candidate_probability = di.initial_candidates.envmap_candidate_probability;
     }
+    st.nb_light_candidates = nb_light_candidates;
+    st.nb_bsdf_candidates = nb_bsdf_candidates;
+    st.envmap_candidate_probability = envmap_candidate_probability;
 
     DiReservoir reservoir;
     reservoir.init();
@@ -649,7 +738,7 @@ B2_HD DiReservoir sample_initial_candidates(const Ctx& ctx, Payload& payload, co
 
         /* ReSTIR_DI_DoLightPresampling (a -D macro in the reference, InitialCandidates.h:192-211) is a launch-time switch here */
         DiSample light_sample = ctx.light_presampling
-                                    ? use_presampled_light_candidate(rd, pixel_x, pixel_y, hit.inter_point, hit.shading_normal, sample_radiance, sample_cosine_term, light_pdf_area_measure, rng)
+                                    ? use_presampled_light_candidate(rd, (int)x, (int)y, hit.inter_point, hit.shading_normal, sample_radiance, sample_cosine_term, light_pdf_area_measure, rng)
                                     : sample_fresh_light_candidate<V>(ctx, envmap_candidate_probability, hit, sample_radiance, sample_cosine_term, light_pdf_area_measure, rng);
         to_light_direction = di_light_sample_direction(rd, light_sample, hit.inter_point, distance_to_light);
 
@@ -691,8 +780,132 @@ B2_HD DiReservoir sample_initial_candidates(const Ctx& ctx, Payload& payload, co
         reservoir.add_one_candidate(light_sample, candidate_weight, rng);
     }
 
-    /* ---- BSDF candidates ---- */
-    for (int i = 0; i < nb_bsdf_candidates; i++)
+    /* ---- BSDF candidate 0: the sampling half ---- */
+    st.bsdf_sample_pdf_solid_angle = 0.0f;
+    st.bsdf_sampled_direction = v3(0.0f);
+    st.sampled_lobe_info = B2_LOBE_NO_INFO;
+    if (nb_bsdf_candidates > 0)
+    {
+        BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, v3(0.0f), &st.sampled_lobe_info, &payload.volume_state, false, &payload.material, 0,
+                                     payload.accumulated_roughness);
+        (void)bsdf_sample<V>(rd, bctx, st.bsdf_sampled_direction, st.bsdf_sample_pdf_solid_angle, rng);
+        if (st.bsdf_sample_pdf_solid_angle > 0.0f)
+            request_closest(candidate_ray, hit.inter_point, st.bsdf_sampled_direction, hit.primitive_index);
+    }
+    st.reservoir = reservoir;
+    st.rng = rng;
+}
+
+/* one BSDF candidate, given the closest hit along its direction (InitialCandidates.h:296-420) */
+template <class V>
+B2_HD void di_initial_bsdf_candidate_finish(const Ctx& ctx, const Payload& payload, const HitInfo& hit, V3 view_direction, V3 bsdf_sampled_direction, float bsdf_sample_pdf_solid_angle,
+                                            int sampled_lobe_info, bool hit_found, const LightRayHit& light_hit, int nb_light_candidates, int nb_bsdf_candidates,
+                                            float envmap_candidate_probability, DiReservoir& reservoir, Rng& rng)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    if (hit_found && !is_black(light_hit.emission))
+    {
+        DiSurface surface = surface_from_hit(hit, payload, view_direction);
+        DiSample bsdf_RIS_sample = di_sample_defaults();
+        bsdf_RIS_sample.emissive_triangle_index = light_hit.prim;
+        bsdf_RIS_sample.point_on_light_source = hit.inter_point + bsdf_sampled_direction * light_hit.distance;
+        bsdf_RIS_sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+        bsdf_RIS_sample.or_flags(sampled_lobe_info);
+        bsdf_RIS_sample.target_function = di_target_function<V, false>(ctx, bsdf_RIS_sample, surface);
+
+        float light_pdf_solid_angle = 0.0f;
+        bool refraction_sampled = dot(bsdf_sampled_direction, hit.shading_normal) < 0.0f;
+        if (!refraction_sampled)
+            light_pdf_solid_angle = pdf_of_emissive_triangle_hit_solid_angle<V>(rd, light_hit, bsdf_sampled_direction);
+
+        float target_function = bsdf_RIS_sample.target_function;
+        if (bsdf_sample_pdf_solid_angle <= 0.0f || !check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, target_function / light_pdf_solid_angle / bsdf_sample_pdf_solid_angle))
+            return;
+
+        light_pdf_solid_angle *= (1.0f - envmap_candidate_probability);
+        float mis_weight = balance_heuristic(bsdf_sample_pdf_solid_angle, (float)nb_bsdf_candidates, light_pdf_solid_angle, (float)nb_light_candidates);
+
+        float bsdf_sample_pdf_area_measure = bsdf_sample_pdf_solid_angle;
+        bsdf_sample_pdf_area_measure /= (light_hit.distance * light_hit.distance);
+        bsdf_sample_pdf_area_measure *= cosine_term_at_light_source(light_hit.geometric_normal, -bsdf_sampled_direction);
+
+        float candidate_weight = mis_weight * target_function / bsdf_sample_pdf_area_measure;
+        reservoir.add_one_candidate(bsdf_RIS_sample, candidate_weight, rng);
+    }
+    else if (!hit_found && rd.world_settings.ambient_light_type == 2)
+    {
+        if (dot(hit.shading_normal, bsdf_sampled_direction) > 0.0f)
+        {
+            float envmap_pdf;
+            (void)envmap_eval<V>(rd.world_settings, bsdf_sampled_direction, envmap_pdf);
+
+            DiSurface surface = surface_from_hit(hit, payload, view_direction);
+            DiSample bsdf_RIS_sample = di_sample_defaults();
+            bsdf_RIS_sample.emissive_triangle_index = -1;
+            bsdf_RIS_sample.point_on_light_source = mat3_mul_vec(rd.world_settings.world_to_envmap_matrix, bsdf_sampled_direction);
+            bsdf_RIS_sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+            bsdf_RIS_sample.or_flags(B2_DI_FLAGS_ENVMAP_SAMPLE);
+            bsdf_RIS_sample.or_flags(sampled_lobe_info);
+            bsdf_RIS_sample.target_function = di_target_function<V, false>(ctx, bsdf_RIS_sample, surface);
+
+            float target_function = bsdf_RIS_sample.target_function;
+            if (bsdf_sample_pdf_solid_angle <= 0.0f || !check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, target_function / bsdf_sample_pdf_solid_angle))
+                return;
+
+            envmap_pdf *= envmap_candidate_probability;
+            float mis_weight = balance_heuristic(bsdf_sample_pdf_solid_angle, (float)nb_bsdf_candidates, envmap_pdf, (float)nb_light_candidates);
+            float candidate_weight = mis_weight * target_function / bsdf_sample_pdf_solid_angle;
+            reservoir.add_one_candidate(bsdf_RIS_sample, candidate_weight, rng);
+        }
+    }
+}
+
+/* the shadow ray of the visibility-reuse test (ReSTIR/Utils.h:25-65), or none when the test would not trace */
+B2_HD bool di_visibility_test_request(const b2pt_render_data& rd, const DiReservoir& reservoir, V3 shading_point, int last_primitive_hit_index, RayRequest& ray)
+{
+    request_none(ray);
+    if (reservoir.UCW <= 0.0f && reservoir.weight_sum <= 0.0f)
+        return false;
+    else if (reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED)
+        return false;
+    float distance_to_light;
+    V3 sample_direction = di_light_sample_direction(rd, reservoir.sample, shading_point, distance_to_light);
+    request_shadow(ray, shading_point, sample_direction, distance_to_light, last_primitive_hit_index);
+    return true;
+}
+B2_HD void di_visibility_test_apply(DiReservoir& reservoir, bool occluded)
+{
+    if (occluded)
+        reservoir.UCW = -1.0f;
+    else
+        reservoir.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+}
+
+template <class V>
+B2_HD void restir_di_initial_phase_b(const Ctx& ctx, uint32_t x, uint32_t y, DiInitialState& st, const B2Hit& candidate_hit, RayRequest& visibility_ray)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    request_none(visibility_ray);
+    if (!st.active)
+        return;
+    const uint32_t pixel_index = x + y * (uint32_t)rd.render_settings.render_resolution.x;
+    HitInfo hit;
+    Payload payload;
+    V3 view_direction;
+    Rng surface_rng = make_rng(pixel_seed(rd, pixel_index)); /* reconstruct_first_hit's draw (dispersive glass only) already happened in phase A */
+    di_initial_surface<V>(rd, pixel_index, surface_rng, hit, payload, view_direction);
+
+    DiReservoir reservoir = st.reservoir;
+    Rng rng = st.rng;
+    if (st.nb_bsdf_candidates > 0 && st.bsdf_sample_pdf_solid_angle > 0.0f)
+    {
+        LightRayHit light_hit;
+        bool hit_found = light_ray_hit_from(rd, candidate_hit, 1.0e35f, light_hit);
+        di_initial_bsdf_candidate_finish<V>(ctx, payload, hit, view_direction, st.bsdf_sampled_direction, st.bsdf_sample_pdf_solid_angle, st.sampled_lobe_info, hit_found, light_hit,
+                                            st.nb_light_candidates, st.nb_bsdf_candidates, st.envmap_candidate_probability, reservoir, rng);
+    }
+    /* BSDF candidates beyond the first (not the default): traced in place, one after the other */
+    for (int i = 1; i < st.nb_bsdf_candidates; i++)
     {
         float bsdf_sample_pdf_solid_angle = 0.0f;
         V3 bsdf_sampled_direction;
@@ -700,115 +913,57 @@ B2_HD DiReservoir sample_initial_candidates(const Ctx& ctx, Payload& payload, co
         BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, v3(0.0f), &sampled_lobe_info, &payload.volume_state, false, &payload.material, 0,
                                      payload.accumulated_roughness);
         (void)bsdf_sample<V>(rd, bctx, bsdf_sampled_direction, bsdf_sample_pdf_solid_angle, rng);
-
         if (bsdf_sample_pdf_solid_angle > 0.0f)
         {
             LightRayHit light_hit;
             bool hit_found = bsdf_light_sample_ray(ctx, hit.inter_point, bsdf_sampled_direction, 1.0e35f, light_hit, hit.primitive_index);
-            if (hit_found && !is_black(light_hit.emission))
-            {
-                DiSurface surface = surface_from_hit(hit, payload, view_direction);
-                DiSample bsdf_RIS_sample = di_sample_defaults();
-                bsdf_RIS_sample.emissive_triangle_index = light_hit.prim;
-                bsdf_RIS_sample.point_on_light_source = hit.inter_point + bsdf_sampled_direction * light_hit.distance;
-                bsdf_RIS_sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
-                bsdf_RIS_sample.or_flags(sampled_lobe_info);
-                bsdf_RIS_sample.target_function = di_target_function<V, false>(ctx, bsdf_RIS_sample, surface);
-
-                float light_pdf_solid_angle = 0.0f;
-                bool refraction_sampled = dot(bsdf_sampled_direction, hit.shading_normal) < 0.0f;
-                if (!refraction_sampled)
-                    light_pdf_solid_angle = pdf_of_emissive_triangle_hit_solid_angle<V>(rd, light_hit, bsdf_sampled_direction);
-
-                float target_function = bsdf_RIS_sample.target_function;
-                if (bsdf_sample_pdf_solid_angle <= 0.0f || !check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, target_function / light_pdf_solid_angle / bsdf_sample_pdf_solid_angle))
-                    continue;
-
-                light_pdf_solid_angle *= (1.0f - envmap_candidate_probability);
-                float mis_weight = balance_heuristic(bsdf_sample_pdf_solid_angle, (float)nb_bsdf_candidates, light_pdf_solid_angle, (float)nb_light_candidates);
-
-                float bsdf_sample_pdf_area_measure = bsdf_sample_pdf_solid_angle;
-                bsdf_sample_pdf_area_measure /= (light_hit.distance * light_hit.distance);
-                bsdf_sample_pdf_area_measure *= cosine_term_at_light_source(light_hit.geometric_normal, -bsdf_sampled_direction);
-
-                float candidate_weight = mis_weight * target_function / bsdf_sample_pdf_area_measure;
-                reservoir.add_one_candidate(bsdf_RIS_sample, candidate_weight, rng);
-            }
-            else if (!hit_found && rd.world_settings.ambient_light_type == 2)
-            {
-                if (dot(hit.shading_normal, bsdf_sampled_direction) > 0.0f)
-                {
-                    float envmap_pdf;
-                    (void)envmap_eval<V>(rd.world_settings, bsdf_sampled_direction, envmap_pdf);
-
-                    DiSurface surface = surface_from_hit(hit, payload, view_direction);
-                    DiSample bsdf_RIS_sample = di_sample_defaults();
-                    bsdf_RIS_sample.emissive_triangle_index = -1;
-                    bsdf_RIS_sample.point_on_light_source = mat3_mul_vec(rd.world_settings.world_to_envmap_matrix, bsdf_sampled_direction);
-                    bsdf_RIS_sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
-                    bsdf_RIS_sample.or_flags(B2_DI_FLAGS_ENVMAP_SAMPLE);
-                    bsdf_RIS_sample.or_flags(sampled_lobe_info);
-                    bsdf_RIS_sample.target_function = di_target_function<V, false>(ctx, bsdf_RIS_sample, surface);
-
-                    float target_function = bsdf_RIS_sample.target_function;
-                    if (bsdf_sample_pdf_solid_angle <= 0.0f || !check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, target_function / bsdf_sample_pdf_solid_angle))
-                        continue;
-
-                    envmap_pdf *= envmap_candidate_probability;
-                    float mis_weight = balance_heuristic(bsdf_sample_pdf_solid_angle, (float)nb_bsdf_candidates, envmap_pdf, (float)nb_light_candidates);
-                    float candidate_weight = mis_weight * target_function / bsdf_sample_pdf_solid_angle;
-                    reservoir.add_one_candidate(bsdf_RIS_sample, candidate_weight, rng);
-                }
-            }
+            di_initial_bsdf_candidate_finish<V>(ctx, payload, hit, view_direction, bsdf_sampled_direction, bsdf_sample_pdf_solid_angle, sampled_lobe_info, hit_found, light_hit,
+                                                st.nb_light_candidates, st.nb_bsdf_candidates, st.envmap_candidate_probability, reservoir, rng);
         }
     }
-
     reservoir.end();
     reservoir.M = 1;
-    return reservoir;
+
+    st.reservoir = reservoir;
+    st.rng = rng;
+    st.pending_final = di_visibility_test_request(rd, reservoir, hit.inter_point, hit.primitive_index, visibility_ray) ? 1 : 0;
 }
 
 template <class V>
-B2_HD bool restir_pass_prologue(const b2pt_render_data& rd, uint32_t x, uint32_t y, uint32_t& pixel_index)
+B2_HD void restir_di_initial_phase_c(const Ctx& ctx, uint32_t x, uint32_t y, DiInitialState& st, const B2Hit& visibility_hit)
 {
-    const b2pt_int2 res = rd.render_settings.render_resolution;
-    if (x >= (uint32_t)res.x || y >= (uint32_t)res.y)
-        return false;
-    pixel_index = x + y * res.x;
-    return true;
+    const b2pt_render_data& rd = *ctx.rd;
+    if (!st.active)
+        return;
+    const uint32_t pixel_index = x + y * (uint32_t)rd.render_settings.render_resolution.x;
+    if (st.pending_final)
+        di_visibility_test_apply(st.reservoir, visibility_hit.prim >= 0);
+    di_store(rd, rd.render_settings.restir_di_settings.initial_candidates.output_reservoirs, (int)pixel_index, st.reservoir);
+}
+
+/* a requested ray traced on the spot (the per-pixel form of the passes) */
+B2_HD B2Hit di_trace_request(const Ctx& ctx, const RayRequest& ray)
+{
+    B2Hit none;
+    none.t = -1.0f;
+    none.u = none.v = 0.0f;
+    none.prim = -1;
+    none.ng = v3(0.0f);
+    if (ray.kind == B2_RAY_NONE)
+        return none;
+    return b2_trace(ctx, ray.kind == B2_RAY_ANY_HIT, ray.origin, ray.direction, ray.t_max, ray.skip_prim);
 }
 
 template <class V>
 B2_HD void restir_di_initial_candidates_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
 {
-    const b2pt_render_data& rd = *ctx.rd;
-    if (rd.buffers.emissive_triangles_count == 0 && rd.world_settings.ambient_light_type != 2)
-        return;
-    uint32_t pixel_index;
-    if (!restir_pass_prologue<V>(rd, x, y, pixel_index))
-        return;
-
-    Rng rng = make_rng(pixel_seed(rd, pixel_index));
-    if (!rd.aux_buffers.pixel_active[pixel_index] || rd.g_buffer.first_hit_prim_index[pixel_index] == -1)
-        return;
-
-    HitInfo hit = hit_info_defaults();
-    hit.geometric_normal = unpack_normal_oct24(rd.g_buffer.geometric_normals[pixel_index]);
-    hit.shading_normal = unpack_normal_oct24(rd.g_buffer.shading_normals[pixel_index]);
-    hit.inter_point = load_v3(rd.g_buffer.primary_hit_position, pixel_index);
-    hit.primitive_index = rd.g_buffer.first_hit_prim_index[pixel_index];
-
-    Payload payload;
-    payload.init();
-    payload.material = unpack_material(load_packed_material(rd.g_buffer.materials, pixel_index));
-    reconstruct_first_hit<V>(payload.volume_state, payload.material, rd.buffers.material_indices, hit.primitive_index, rng);
-
-    V3 cam = v3(rd.current_camera.position.x, rd.current_camera.position.y, rd.current_camera.position.z);
-    V3 view_direction = normalize(cam - hit.inter_point);
-    DiReservoir initial_candidates_reservoir = sample_initial_candidates<V>(ctx, payload, hit, view_direction, rng, (int)x, (int)y);
-
-    di_visibility_test_kill_reservoir(ctx, initial_candidates_reservoir, hit.inter_point, hit.primitive_index);
-    di_store(rd, rd.render_settings.restir_di_settings.initial_candidates.output_reservoirs, (int)pixel_index, initial_candidates_reservoir);
+    DiInitialState st;
+    RayRequest ray;
+    restir_di_initial_phase_a<V>(ctx, x, y, st, ray);
+    B2Hit result = di_trace_request(ctx, ray);
+    restir_di_initial_phase_b<V>(ctx, x, y, st, result, ray);
+    result = di_trace_request(ctx, ray);
+    restir_di_initial_phase_c<V>(ctx, x, y, st, result);
 }
 
 /* ---------------------------------------------------------------------------------------------------------- */
@@ -1007,16 +1162,78 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
 
 /* ---------------------------------------------------------------------------------------------------------- */
 /* fused spatiotemporal reuse (FusedSpatiotemporalReuse.h) */
+/* ---- the fused spatiotemporal pass cut at its rays ------------------------------------------------------------------------------
+ * Up to 8 shadow rays per pixel decide target functions that are otherwise fully determined: the temporal neighbour's sample seen
+ * from the center pixel, and the center pixel's canonical sample seen from the temporal and from every spatial neighbour (the
+ * pairwise-MIS canonical weight, ReSTIR_DI_BiasCorrectionUseVisibility). They do not depend on one another, so:
+ *     phase A: neighbours found, every target function evaluated AS IF VISIBLE              -> up to 8 shadow rays
+ *     phase B: occluded values zeroed, MIS weights, the reservoirs combined (RNG draws in the reference's order),
+ *              normalisation                                                                -> the visibility-reuse shadow ray
+ *     phase C: visibility reuse, M cap, store
+ * restir_di_spatiotemporal_pixel below = A, trace, B, trace, C for one pixel; the wavefront kernels run each phase frame-wide. */
+#define B2_ST_MAX_ENTRIES 8 /* temporal neighbour + up to 6 spatial neighbours + the center pixel; more neighbours: the caller uses the in-place form */
+enum { B2_ST_TEMPORAL = 1, B2_ST_CANONICAL = 2 };
+struct DiStEntry
+{
+    int neighbor_pixel_index;
+    float target_function_at_center;            /* as if visible */
+    float target_function_canonical_at_neighbor; /* as if visible */
+    int kind;
+};
+struct DiSpatiotemporalState
+{
+    Rng rng;
+    int active, pending_final;
+    int entry_count;
+    int valid_neighbors_count, valid_neighbors_M_sum;
+    int update_mc;
+    DiStEntry entries[B2_ST_MAX_ENTRIES];
+    DiReservoir out; /* between phases B and C */
+};
+/* ray slots of phase A: [2 k] = center-side ray of entry k (temporal entry only), [2 k + 1] = its canonical-at-neighbour ray */
+#define B2_ST_RAYS (2 * B2_ST_MAX_ENTRIES)
+
+/* di_target_function<V, true> split at its shadow ray */
 template <class V>
-B2_HD void restir_di_spatiotemporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+B2_HD float di_target_function_deferred(const Ctx& ctx, const DiSample& sample, DiSurface& surface, RayRequest& ray)
+{
+    request_none(ray);
+    const b2pt_render_data& rd = *ctx.rd;
+    if (sample.emissive_triangle_index == -1 && !sample.is_envmap_sample())
+        return 0.0f;
+    float distance_to_light;
+    V3 sample_direction = di_light_sample_direction(rd, sample, surface.shading_point, distance_to_light);
+    float target_function = di_target_function<V, false>(ctx, sample, surface);
+    if (target_function == 0.0f)
+        return 0.0f;
+    request_shadow(ray, surface.shading_point, sample_direction, distance_to_light, surface.primitive_index);
+    return target_function;
+}
+
+template <class V>
+B2_HD bool restir_di_spatiotemporal_supported(const b2pt_render_data& rd)
+{
+    const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    int most_neighbors = b2_max(di.common_spatial_pass.reuse_neighbor_count, di.common_spatial_pass.do_disocclusion_reuse_boost ? di.common_spatial_pass.disocclusion_reuse_count : 0);
+    return most_neighbors + 2 <= B2_ST_MAX_ENTRIES;
+}
+
+template <class V>
+B2_HD void restir_di_spatiotemporal_phase_a(const Ctx& ctx, uint32_t x, uint32_t y, DiSpatiotemporalState& st, RayRequest (&rays)[B2_ST_RAYS])
 {
     const b2pt_render_data& rd = *ctx.rd;
     const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    for (int k = 0; k < B2_ST_RAYS; k++)
+        request_none(rays[k]);
+    st.active = 0;
+    st.pending_final = 0;
+    st.entry_count = 0;
     uint32_t center_pixel_index;
     if (!restir_pass_prologue<V>(rd, x, y, center_pixel_index))
         return;
     if (!rd.aux_buffers.pixel_active[center_pixel_index] || rd.g_buffer.first_hit_prim_index[center_pixel_index] == -1)
         return;
+    st.active = 1;
 
     unsigned int seed = rd.render_settings.freeze_random ? wang_hash(center_pixel_index + 1) : wang_hash(((center_pixel_index + 1) * (rd.render_settings.sample_number + 1)) ^ rd.random_number);
     Rng rng = make_rng(seed);
@@ -1039,14 +1256,9 @@ B2_HD void restir_di_spatiotemporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y
     temporal_neighbor_reservoir.init();
     Int3 temporal = find_temporal_neighbor_index<V>(rd, load_v3(rd.g_buffer.primary_hit_position, center_pixel_index), center_pixel_surface.shading_normal, (int)center_pixel_index, rng);
     if (!(temporal.x == -1 || rd.render_settings.freeze_random))
-    {
         temporal_neighbor_reservoir = di_load(rd, di.temporal_pass.input_reservoirs, temporal.x);
-        if (temporal_neighbor_reservoir.M != 0)
-        {
-            /* the surface is only consumed by bias-correction modes other than pairwise MIS; its RNG side effect
-             * (wavelength draw for dispersive glass) cannot occur because dispersive scenes are refused */
-        }
-    }
+    /* (the temporal neighbour's surface is only consumed by bias-correction modes other than pairwise MIS; its RNG side effect -- the
+     * wavelength draw for dispersive glass -- cannot occur because dispersive scenes are refused) */
     if ((temporal.x == -1 || temporal_neighbor_reservoir.M <= 1) && di.common_spatial_pass.do_disocclusion_reuse_boost)
         local.reuse_neighbor_count = di.common_spatial_pass.disocclusion_reuse_count;
 
@@ -1062,28 +1274,31 @@ B2_HD void restir_di_spatiotemporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y
         valid_neighbors_count++;
         valid_neighbors_M_sum += temporal_neighbor_reservoir.M;
     }
+    st.valid_neighbors_count = valid_neighbors_count;
+    st.valid_neighbors_M_sum = valid_neighbors_M_sum;
 
-    DiReservoir out;
-    out.init();
     DiReservoir initial_candidates_reservoir = di_load(rd, di.initial_candidates.output_reservoirs, (int)center_pixel_index);
-    PairwiseMis mis;
-    mis.mc = 0.0f;
     const bool update_mc = initial_candidates_reservoir.M > 0 && initial_candidates_reservoir.UCW > 0.0f;
+    st.update_mc = update_mc ? 1 : 0;
 
-    if (temporal.x != -1)
+    /* the canonical sample seen from a neighbour's surface (pairwise MIS, update_mc), as if visible */
+    auto canonical_at = [&](int neighbor_pixel_index, RayRequest& ray) {
+        if (!update_mc)
+            return 0.0f;
+        DiSurface neighbor_pixel_surface = get_pixel_surface<V>(rd, neighbor_pixel_index, prev_gbuffer, rng);
+        return di_target_function_deferred<V>(ctx, initial_candidates_reservoir.sample, neighbor_pixel_surface, ray);
+    };
+
+    if (temporal.x != -1 && temporal_neighbor_reservoir.M > 0)
     {
-        if (temporal_neighbor_reservoir.M > 0)
-        {
-            float target_function_at_center = 0.0f;
-            if (temporal_neighbor_reservoir.UCW > 0.0f)
-                target_function_at_center = di_target_function<V, true>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface);
-
-            float w = mis.weight<V>(ctx, temporal_neighbor_reservoir.M, temporal_neighbor_reservoir.sample.target_function, initial_candidates_reservoir.M,
-                                    initial_candidates_reservoir.sample.target_function, initial_candidates_reservoir.sample, target_function_at_center, temporal.x, prev_gbuffer,
-                                    valid_neighbors_count, valid_neighbors_M_sum, update_mc, false, false, rng);
-            if (out.combine_with(temporal_neighbor_reservoir, w, target_function_at_center, 1.0f, rng))
-                out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
-        }
+        DiStEntry& e = st.entries[st.entry_count];
+        e.neighbor_pixel_index = temporal.x;
+        e.kind = B2_ST_TEMPORAL;
+        e.target_function_at_center = 0.0f;
+        if (temporal_neighbor_reservoir.UCW > 0.0f)
+            e.target_function_at_center = di_target_function_deferred<V>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface, rays[2 * st.entry_count]);
+        e.target_function_canonical_at_neighbor = canonical_at(temporal.x, rays[2 * st.entry_count + 1]);
+        st.entry_count++;
     }
 
     const void* spatial_input_reservoir_buffer = di.spatial_pass.input_reservoirs;
@@ -1113,45 +1328,121 @@ B2_HD void restir_di_spatiotemporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y
             if (!check_neighbor_similarity_heuristics(rd, neighbor_pixel_index, (int)center_pixel_index, center_pixel_surface.shading_point, normal_for_rejection_heuristic(rd, center_pixel_surface), prev_gbuffer))
                 continue;
 
-        DiReservoir neighbor_reservoir;
-        if (spatial_neighbor_index == reused_neighbors_count)
-            neighbor_reservoir = initial_candidates_reservoir;
-        else
-            neighbor_reservoir = di_load(rd, spatial_input_reservoir_buffer, neighbor_pixel_index);
+        const bool canonical = spatial_neighbor_index == reused_neighbors_count;
+        DiReservoir neighbor_reservoir = canonical ? initial_candidates_reservoir : di_load(rd, spatial_input_reservoir_buffer, neighbor_pixel_index);
 
-        float target_function_at_center = 0.0f;
-        bool do_neighbor_target_function_visibility = do_include_spatial_visibility_term(rd, local, spatial_neighbor_index);
+        DiStEntry& e = st.entries[st.entry_count];
+        e.neighbor_pixel_index = neighbor_pixel_index;
+        e.kind = canonical ? B2_ST_CANONICAL : 0;
+        e.target_function_at_center = 0.0f;
         if (neighbor_reservoir.UCW > 0.0f)
         {
-            if (spatial_neighbor_index == reused_neighbors_count)
-                target_function_at_center = neighbor_reservoir.sample.target_function;
+            if (canonical)
+                e.target_function_at_center = neighbor_reservoir.sample.target_function;
             else
-                target_function_at_center = di_target_function<V, false>(ctx, neighbor_reservoir.sample, center_pixel_surface);
+                e.target_function_at_center = di_target_function<V, false>(ctx, neighbor_reservoir.sample, center_pixel_surface);
         }
+        e.target_function_canonical_at_neighbor = canonical ? 0.0f : canonical_at(neighbor_pixel_index, rays[2 * st.entry_count + 1]);
+        st.entry_count++;
+    }
+    st.rng = rng;
+}
 
-        float mis_weight = mis.weight<V>(ctx, neighbor_reservoir.M, neighbor_reservoir.sample.target_function, initial_candidates_reservoir.M, initial_candidates_reservoir.sample.target_function,
-                                         initial_candidates_reservoir.sample, target_function_at_center, neighbor_pixel_index, prev_gbuffer, valid_neighbors_count, valid_neighbors_M_sum, update_mc,
-                                         spatial_neighbor_index == reused_neighbors_count, false, rng);
+template <class V>
+B2_HD void restir_di_spatiotemporal_phase_b(const Ctx& ctx, uint32_t x, uint32_t y, DiSpatiotemporalState& st, const B2Hit (&results)[B2_ST_RAYS], RayRequest& visibility_ray)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    request_none(visibility_ray);
+    if (!st.active)
+        return;
+    const int center_pixel_index = (int)(x + y * (uint32_t)rd.render_settings.render_resolution.x);
+    Rng rng = st.rng;
+    DiReservoir initial_candidates_reservoir = di_load(rd, di.initial_candidates.output_reservoirs, center_pixel_index);
+    const bool update_mc = st.update_mc != 0;
 
-        if (out.combine_with(neighbor_reservoir, mis_weight, target_function_at_center, 1.0f, rng))
+    DiReservoir out;
+    out.init();
+    PairwiseMis mis;
+    mis.mc = 0.0f;
+    for (int k = 0; k < st.entry_count; k++)
+    {
+        const DiStEntry& e = st.entries[k];
+        /* an occluded ray zeroes its target function (target_function *= visible ? 1 : 0); unrequested rays come back as misses */
+        float target_function_at_center = e.target_function_at_center;
+        if (results[2 * k].prim >= 0)
+            target_function_at_center *= 0.0f;
+        float target_function_canonical_at_neighbor = e.target_function_canonical_at_neighbor;
+        if (results[2 * k + 1].prim >= 0)
+            target_function_canonical_at_neighbor *= 0.0f;
+
+        if (e.kind == B2_ST_TEMPORAL)
         {
-            if (do_neighbor_target_function_visibility)
+            DiReservoir temporal_neighbor_reservoir = di_load(rd, di.temporal_pass.input_reservoirs, e.neighbor_pixel_index);
+            float w = mis.weight_given(rd, temporal_neighbor_reservoir.M, temporal_neighbor_reservoir.sample.target_function, initial_candidates_reservoir.M,
+                                       initial_candidates_reservoir.sample.target_function, target_function_at_center, target_function_canonical_at_neighbor, st.valid_neighbors_count,
+                                       st.valid_neighbors_M_sum, update_mc, false, false);
+            if (out.combine_with(temporal_neighbor_reservoir, w, target_function_at_center, 1.0f, rng))
                 out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
-            else if (spatial_neighbor_index == reused_neighbors_count)
-                out.sample.or_flags((int)(neighbor_reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED));
-            else
-                out.sample.flags &= ~(uint32_t)B2_DI_FLAGS_UNOCCLUDED;
+        }
+        else
+        {
+            const bool canonical = e.kind == B2_ST_CANONICAL;
+            DiReservoir neighbor_reservoir = canonical ? initial_candidates_reservoir : di_load(rd, di.spatial_pass.input_reservoirs, e.neighbor_pixel_index);
+            float mis_weight = mis.weight_given(rd, neighbor_reservoir.M, neighbor_reservoir.sample.target_function, initial_candidates_reservoir.M,
+                                                initial_candidates_reservoir.sample.target_function, target_function_at_center, target_function_canonical_at_neighbor,
+                                                st.valid_neighbors_count, st.valid_neighbors_M_sum, update_mc, canonical, false);
+            if (out.combine_with(neighbor_reservoir, mis_weight, target_function_at_center, 1.0f, rng))
+            {
+                /* ReSTIR_DI_SpatialTargetFunctionVisibility = FALSE: do_include_spatial_visibility_term is false for every neighbour */
+                if (canonical)
+                    out.sample.or_flags((int)(neighbor_reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED));
+                else
+                    out.sample.flags &= ~(uint32_t)B2_DI_FLAGS_UNOCCLUDED;
+            }
         }
     }
 
     out.end_with_normalization(1.0f, 1.0f);
 
+    st.out = out;
+    st.rng = rng;
     if (di.common_temporal_pass.do_temporal_reuse_pass || di.common_spatial_pass.number_of_passes - 1 != di.common_spatial_pass.spatial_pass_index)
-        di_visibility_test_kill_reservoir(ctx, out, center_pixel_surface.shading_point, center_pixel_surface.primitive_index);
+        st.pending_final = di_visibility_test_request(rd, out, load_v3(rd.g_buffer.primary_hit_position, center_pixel_index), rd.g_buffer.first_hit_prim_index[center_pixel_index],
+                                                      visibility_ray)
+                               ? 1
+                               : 0;
+}
 
+template <class V>
+B2_HD void restir_di_spatiotemporal_phase_c(const Ctx& ctx, uint32_t x, uint32_t y, DiSpatiotemporalState& st, const B2Hit& visibility_hit)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    if (!st.active)
+        return;
+    const int center_pixel_index = (int)(x + y * (uint32_t)rd.render_settings.render_resolution.x);
+    DiReservoir out = st.out;
+    if (st.pending_final)
+        di_visibility_test_apply(out, visibility_hit.prim >= 0);
     if (di.m_cap > 0)
         out.M = b2_min(out.M, di.m_cap);
-    di_store(rd, di.spatial_pass.output_reservoirs, (int)center_pixel_index, out);
+    di_store(rd, di.spatial_pass.output_reservoirs, center_pixel_index, out);
+}
+
+template <class V>
+B2_HD void restir_di_spatiotemporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    DiSpatiotemporalState st;
+    RayRequest rays[B2_ST_RAYS];
+    B2Hit results[B2_ST_RAYS];
+    restir_di_spatiotemporal_phase_a<V>(ctx, x, y, st, rays);
+    for (int k = 0; k < B2_ST_RAYS; k++)
+        results[k] = di_trace_request(ctx, rays[k]);
+    RayRequest visibility_ray;
+    restir_di_spatiotemporal_phase_b<V>(ctx, x, y, st, results, visibility_ray);
+    B2Hit visibility_hit = di_trace_request(ctx, visibility_ray);
+    restir_di_spatiotemporal_phase_c<V>(ctx, x, y, st, visibility_hit);
 }
 
 template <class V>

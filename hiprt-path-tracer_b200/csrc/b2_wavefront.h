@@ -406,7 +406,208 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS) wf_stage2(const __grid_co
         b2_flush_counters(local_counters);
 }
 
-/* host side: scratch buffers per device (grown on demand, kept for the life of the library) and the launch sequence */
+/* ---- the ReSTIR DI passes whose per-pixel code is cut at its rays (b2_restir_di.h: InitialCandidates, fused spatiotemporal reuse) ----
+ * phase A over every owned pixel -> wf_trace -> phase B -> wf_trace -> phase C. One thread per pixel in 8x8 tiles like pass_kernel
+ * (the neighbour gathers of a reuse pass stay local); a pixel's state between phases (40 - 200 B) is parked in HBM. */
+template <class V>
+struct WfInitialCandidates
+{
+    typedef DiInitialState State;
+    static constexpr int RAYS = 1;
+    static __device__ __forceinline__ void phase_a(const Ctx& ctx, uint32_t x, uint32_t y, State& st, RayRequest (&rays)[RAYS]) { restir_di_initial_phase_a<V>(ctx, x, y, st, rays[0]); }
+    static __device__ __forceinline__ void phase_b(const Ctx& ctx, uint32_t x, uint32_t y, State& st, const B2Hit (&results)[RAYS], RayRequest& final_ray)
+    {
+        restir_di_initial_phase_b<V>(ctx, x, y, st, results[0], final_ray);
+    }
+    static __device__ __forceinline__ void phase_c(const Ctx& ctx, uint32_t x, uint32_t y, State& st, const B2Hit& final_hit) { restir_di_initial_phase_c<V>(ctx, x, y, st, final_hit); }
+};
+
+template <class V>
+struct WfSpatiotemporalReuse
+{
+    typedef DiSpatiotemporalState State;
+    /* slot k < 8: the canonical-sample ray of entry k; slot 8: the center-side ray of the temporal entry (always entry 0) */
+    static constexpr int RAYS = B2_ST_MAX_ENTRIES + 1;
+    static __device__ __forceinline__ void phase_a(const Ctx& ctx, uint32_t x, uint32_t y, State& st, RayRequest (&rays)[RAYS])
+    {
+        RayRequest all[B2_ST_RAYS];
+        restir_di_spatiotemporal_phase_a<V>(ctx, x, y, st, all);
+#pragma unroll
+        for (int k = 0; k < B2_ST_MAX_ENTRIES; k++)
+            rays[k] = all[2 * k + 1];
+        rays[B2_ST_MAX_ENTRIES] = all[0];
+    }
+    static __device__ __forceinline__ void phase_b(const Ctx& ctx, uint32_t x, uint32_t y, State& st, const B2Hit (&results)[RAYS], RayRequest& final_ray)
+    {
+        B2Hit all[B2_ST_RAYS];
+#pragma unroll
+        for (int k = 0; k < B2_ST_MAX_ENTRIES; k++)
+        {
+            all[2 * k + 1] = results[k];
+            all[2 * k] = results[k];
+            all[2 * k].prim = -1; /* no center-side ray but entry 0's */
+        }
+        all[0] = results[B2_ST_MAX_ENTRIES];
+        restir_di_spatiotemporal_phase_b<V>(ctx, x, y, st, all, final_ray);
+    }
+    static __device__ __forceinline__ void phase_c(const Ctx& ctx, uint32_t x, uint32_t y, State& st, const B2Hit& final_hit) { restir_di_spatiotemporal_phase_c<V>(ctx, x, y, st, final_hit); }
+};
+
+struct WfPassBuffers
+{
+    unsigned char* states;
+    float4* slot_a;
+    float4* slot_b;
+    int* ray_list;
+    unsigned int* counters;
+    unsigned int* have; /* per pixel: bit k = ray k of phase A is in flight; bit 31 = the final ray */
+};
+
+/* pixel of a thread in 8x8 tiles over the launch's rows; slot = its index among the launch's pixels, -1 outside */
+__device__ __forceinline__ int wf_tile_pixel(const B2LaunchGeom& g, int tiles_x, int rows, uint32_t& x, uint32_t& y)
+{
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    x = tile_x * B2_TILE_W + (threadIdx.x & 7);
+    const int local_row = tile_y * B2_TILE_H + (threadIdx.x >> 3);
+    y = b2_global_row((uint32_t)local_row, g);
+    if (x >= (uint32_t)g.width || local_row >= rows)
+        return -1;
+    return local_row * g.width + (int)x;
+}
+
+template <class P, class V>
+__global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_a(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x, int rows, const WfPassBuffers b)
+{
+    __shared__ uint64_t stacks[B2_STACK_ENTRIES * B2_BLOCK_THREADS];
+    b2_block_constants_init(rd);
+    B2TraversalCounters local_counters;
+    local_counters.rays = local_counters.nodes = local_counters.tris = 0;
+    Ctx ctx;
+    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults);
+    ctx.light_presampling = geom.light_presampling != 0;
+    uint32_t x, y;
+    const int slot = wf_tile_pixel(geom, tiles_x, rows, x, y);
+    RayRequest rays[P::RAYS];
+#pragma unroll
+    for (int k = 0; k < P::RAYS; k++)
+        request_none(rays[k]);
+    typename P::State st;
+    st.active = 0;
+    if (slot >= 0)
+    {
+        P::phase_a(ctx, x, y, st, rays);
+        reinterpret_cast<typename P::State*>(b.states)[slot] = st;
+    }
+    unsigned int have = 0u;
+#pragma unroll
+    for (int k = 0; k < P::RAYS; k++)
+    {
+        const bool take = slot >= 0 && st.active && rays[k].kind != B2_RAY_NONE && ctx.bvh.node_count != 0;
+        const int ray_slot = slot * P::RAYS + k;
+        if (take)
+        {
+            b.slot_a[ray_slot] = make_float4(rays[k].origin.x, rays[k].origin.y, rays[k].origin.z, rays[k].t_max);
+            b.slot_b[ray_slot] = make_float4(rays[k].direction.x, rays[k].direction.y, rays[k].direction.z,
+                                             __int_as_float((rays[k].skip_prim << 1) | (rays[k].kind == B2_RAY_ANY_HIT ? 1 : 0)));
+            have |= 1u << k;
+        }
+        wf_append(b.ray_list, b.counters + WF_C_RAYS, take, ray_slot);
+    }
+    if (slot >= 0)
+        b.have[slot] = have;
+    if (V::COUNTERS)
+        b2_flush_counters(local_counters);
+}
+
+template <class P, class V>
+__global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_b(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x, int rows, const WfPassBuffers b)
+{
+    __shared__ uint64_t stacks[B2_STACK_ENTRIES * B2_BLOCK_THREADS];
+    b2_block_constants_init(rd);
+    B2TraversalCounters local_counters;
+    local_counters.rays = local_counters.nodes = local_counters.tris = 0;
+    Ctx ctx;
+    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults);
+    ctx.light_presampling = geom.light_presampling != 0;
+    uint32_t x, y;
+    const int slot = wf_tile_pixel(geom, tiles_x, rows, x, y);
+    RayRequest final_ray;
+    request_none(final_ray);
+    bool active = false;
+    if (slot >= 0)
+    {
+        typename P::State st = reinterpret_cast<const typename P::State*>(b.states)[slot];
+        active = st.active != 0;
+        if (active)
+        {
+            const unsigned int have = b.have[slot];
+            B2Hit results[P::RAYS];
+#pragma unroll
+            for (int k = 0; k < P::RAYS; k++)
+            {
+                results[k].t = -1.0f;
+                results[k].u = results[k].v = 0.0f;
+                results[k].prim = -1;
+                results[k].ng = v3(0.0f);
+                if ((have >> k) & 1u)
+                {
+                    const float4 ra = b.slot_a[slot * P::RAYS + k], rb = b.slot_b[slot * P::RAYS + k];
+                    results[k].t = ra.x;
+                    results[k].u = ra.y;
+                    results[k].v = ra.z;
+                    results[k].prim = __float_as_int(ra.w);
+                    results[k].ng = v3(rb.x, rb.y, rb.z);
+                }
+            }
+            P::phase_b(ctx, x, y, st, results, final_ray);
+            reinterpret_cast<typename P::State*>(b.states)[slot] = st;
+        }
+    }
+    const bool take = active && final_ray.kind != B2_RAY_NONE && ctx.bvh.node_count != 0;
+    const int ray_slot = slot * P::RAYS;
+    if (take)
+    {
+        b.slot_a[ray_slot] = make_float4(final_ray.origin.x, final_ray.origin.y, final_ray.origin.z, final_ray.t_max);
+        b.slot_b[ray_slot] = make_float4(final_ray.direction.x, final_ray.direction.y, final_ray.direction.z,
+                                         __int_as_float((final_ray.skip_prim << 1) | (final_ray.kind == B2_RAY_ANY_HIT ? 1 : 0)));
+    }
+    wf_append(b.ray_list, b.counters + WF_C_RAYS, take, ray_slot);
+    if (slot >= 0)
+        b.have[slot] = take ? (1u << 31) : 0u;
+    if (V::COUNTERS)
+        b2_flush_counters(local_counters);
+}
+
+template <class P, class V>
+__global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_c(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x, int rows, const WfPassBuffers b)
+{
+    Ctx ctx;
+    b2_make_ctx(ctx, rd, nullptr, nullptr, g_faults);
+    uint32_t x, y;
+    const int slot = wf_tile_pixel(geom, tiles_x, rows, x, y);
+    if (slot < 0)
+        return;
+    typename P::State st = reinterpret_cast<const typename P::State*>(b.states)[slot];
+    if (!st.active)
+        return;
+    B2Hit final_hit;
+    final_hit.t = -1.0f;
+    final_hit.u = final_hit.v = 0.0f;
+    final_hit.prim = -1;
+    final_hit.ng = v3(0.0f);
+    if (b.have[slot] >> 31)
+        final_hit.prim = __float_as_int(b.slot_a[slot * P::RAYS].w);
+    P::phase_c(ctx, x, y, st, final_hit);
+}
+
+__global__ void wf_reset_rays(unsigned int* counters)
+{
+    counters[WF_C_RAYS] = 0u;
+    counters[WF_C_CURSOR] = 0u;
+}
+
+/* host side: scratch buffers per (device, stream) -- launches on different streams never share state --, grown on demand and kept
+ * for the life of the library, and the launch sequences */
 struct WfScratch
 {
     void* base = nullptr;
@@ -415,58 +616,115 @@ struct WfScratch
     unsigned int* buckets = nullptr;
 };
 
-template <class V>
-cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, int rows, cudaStream_t stream)
+static cudaError_t wf_scratch_get(cudaStream_t stream, size_t total, WfScratch& out, int& out_sm_count)
 {
-    static WfScratch scratch[B2_MAX_DEVICES];
-    static std::mutex scratch_mutex;
+    static std::map<std::pair<int, cudaStream_t>, WfScratch> scratch;
     static int sm_count[B2_MAX_DEVICES] = {};
+    static std::mutex scratch_mutex;
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess)
         return e;
     if (device < 0 || device >= B2_MAX_DEVICES)
         return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(scratch_mutex);
+    if (!sm_count[device])
+    {
+        e = cudaDeviceGetAttribute(&sm_count[device], cudaDevAttrMultiProcessorCount, device);
+        if (e != cudaSuccess)
+            return e;
+    }
+    out_sm_count = sm_count[device];
+    WfScratch& sc = scratch[std::make_pair(device, stream)];
+    if (!sc.counters)
+    {
+        e = cudaMalloc((void**)&sc.counters, WF_C_COUNT * sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&sc.buckets, 2 * B2_WF_SORT_BUCKETS * sizeof(unsigned int));
+        if (e != cudaSuccess)
+            return e;
+    }
+    if (sc.bytes < total)
+    {
+        /* work of this stream may still be using the smaller buffer */
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess)
+            return e;
+        cudaFree(sc.base);
+        sc.base = nullptr;
+        sc.bytes = 0;
+        e = cudaMalloc(&sc.base, total);
+        if (e != cudaSuccess)
+            return e;
+        sc.bytes = total;
+    }
+    out = sc;
+    return cudaSuccess;
+}
 
+template <class P, class V>
+cudaError_t launch_wavefront_pass(const b2pt_render_data* rd, const B2LaunchGeom& g, int rows, cudaStream_t stream)
+{
+    const size_t n_pixels = (size_t)rows * g.width;
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t states_bytes = align(n_pixels * sizeof(typename P::State));
+    const size_t slots_bytes = align(n_pixels * P::RAYS * sizeof(float4));
+    const size_t ray_list_bytes = align(n_pixels * P::RAYS * sizeof(int));
+    const size_t have_bytes = align(n_pixels * sizeof(unsigned int));
+    WfScratch sc;
+    int sms = 0;
+    cudaError_t e = wf_scratch_get(stream, states_bytes + 2 * slots_bytes + ray_list_bytes + have_bytes, sc, sms);
+    if (e != cudaSuccess)
+        return e;
+    WfPassBuffers b;
+    unsigned char* p = static_cast<unsigned char*>(sc.base);
+    b.states = p; p += states_bytes;
+    b.slot_a = reinterpret_cast<float4*>(p); p += slots_bytes;
+    b.slot_b = reinterpret_cast<float4*>(p); p += slots_bytes;
+    b.ray_list = reinterpret_cast<int*>(p); p += ray_list_bytes;
+    b.have = reinterpret_cast<unsigned int*>(p);
+    b.counters = sc.counters;
+    WfBuffers tb; /* what wf_trace looks at */
+    tb.paths = nullptr;
+    tb.slot_a = b.slot_a;
+    tb.slot_b = b.slot_b;
+    tb.ray_list = b.ray_list;
+    tb.list[0] = tb.list[1] = tb.list[2] = nullptr;
+    tb.keys = nullptr;
+    tb.counters = sc.counters;
+    tb.buckets = sc.buckets;
+    tb.n_paths = (int)n_pixels;
+
+    e = cudaMemsetAsync(sc.counters, 0, WF_C_COUNT * sizeof(unsigned int), stream);
+    if (e != cudaSuccess)
+        return e;
+    const int tiles_x = (g.width + B2_TILE_W - 1) / B2_TILE_W, tiles_y = (rows + B2_TILE_H - 1) / B2_TILE_H;
+    const int trace_blocks = sms * B2_WF_TRACE_MIN_BLOCKS;
+    const size_t trace_smem = (size_t)g.stack_entries * B2_WF_TRACE_THREADS * 8;
+    const B2BvhDevice* bvh = reinterpret_cast<const B2BvhDevice*>(rd->GPU_BVH);
+    g_cuda_launches += 6;
+    wf_pass_a<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
+    wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, tb, g.stack_entries);
+    wf_reset_rays<<<1, 1, 0, stream>>>(sc.counters);
+    wf_pass_b<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
+    wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, tb, g.stack_entries);
+    wf_pass_c<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
+    return cudaGetLastError();
+}
+
+template <class V>
+cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, int rows, cudaStream_t stream)
+{
     const size_t n_paths = (size_t)rows * g.width;
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t paths_bytes = align(n_paths * sizeof(WfPath<V>));
     const size_t slots_bytes = align(n_paths * B2_WF_RAYS * sizeof(float4));
     const size_t ray_list_bytes = align(n_paths * B2_WF_RAYS * sizeof(int));
     const size_t list_bytes = align(n_paths * sizeof(int));
-    const size_t total = paths_bytes + 2 * slots_bytes + ray_list_bytes + 4 * list_bytes;
-    WfScratch& sc = scratch[device];
-    {
-        std::lock_guard<std::mutex> lock(scratch_mutex);
-        if (!sm_count[device])
-        {
-            e = cudaDeviceGetAttribute(&sm_count[device], cudaDevAttrMultiProcessorCount, device);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(wf_trace<V::COUNTERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_STACK_ENTRIES * B2_WF_TRACE_THREADS * 8);
-            if (e != cudaSuccess)
-                return e;
-        }
-        if (!sc.counters)
-        {
-            e = cudaMalloc((void**)&sc.counters, WF_C_COUNT * sizeof(unsigned int));
-            if (e == cudaSuccess) e = cudaMalloc((void**)&sc.buckets, 2 * B2_WF_SORT_BUCKETS * sizeof(unsigned int));
-            if (e != cudaSuccess)
-                return e;
-        }
-        if (sc.bytes < total)
-        {
-            /* the scratch of the previous size may still be in use by work in flight on any stream of this device */
-            e = cudaDeviceSynchronize();
-            if (e != cudaSuccess)
-                return e;
-            cudaFree(sc.base);
-            sc.base = nullptr;
-            sc.bytes = 0;
-            e = cudaMalloc(&sc.base, total);
-            if (e != cudaSuccess)
-                return e;
-            sc.bytes = total;
-        }
-    }
+    WfScratch sc;
+    int sms = 0;
+    cudaError_t e = wf_scratch_get(stream, paths_bytes + 2 * slots_bytes + ray_list_bytes + 4 * list_bytes, sc, sms);
+    if (e != cudaSuccess)
+        return e;
     WfBuffers b;
     unsigned char* p = static_cast<unsigned char*>(sc.base);
     b.paths = p; p += paths_bytes;
@@ -489,8 +747,8 @@ cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, 
         return e;
 
     const int stage_blocks = (int)((n_paths + B2_WF_STAGE_THREADS - 1) / B2_WF_STAGE_THREADS);
-    const int sort_blocks = sm_count[device] * 4;
-    const int trace_blocks = sm_count[device] * B2_WF_TRACE_MIN_BLOCKS;
+    const int sort_blocks = sms * 4;
+    const int trace_blocks = sms * B2_WF_TRACE_MIN_BLOCKS;
     const size_t stage_smem = (size_t)g.stack_entries * B2_WF_STAGE_THREADS * 8;
     const size_t trace_smem = (size_t)g.stack_entries * B2_WF_TRACE_THREADS * 8;
     const B2BvhDevice* bvh = reinterpret_cast<const B2BvhDevice*>(rd->GPU_BVH);
@@ -499,6 +757,7 @@ cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, 
     int nb_bounces = rd->render_settings.nb_bounces;
     if (nb_bounces < 0)
         nb_bounces = 0;
+    g_cuda_launches += 1 + (unsigned long long)(nb_bounces + 2) * (7 + (Nee<V>::HAS_SEQUENTIAL_RAY ? 1 : 0)) + (unsigned long long)(nb_bounces + 1);
     /* lists: [0] live paths of the round -> sorted into [2] -> stage-1 survivors appended to [1] -> stage-2 survivors appended to
      * [0] again (its old content has been consumed by the scatter before stage 1 started) */
     const int cur = 0, other = 1;

@@ -179,6 +179,8 @@ typedef struct
     uint32_t stack_overflows;
 } b2pt_faults_t;
 int b2pt_faults_read(b2pt_ctx* ctx, b2pt_faults_t* out, int reset);
+/* CUDA kernels launched so far by the passes of this library (a MegaKernel pass in its wavefront form is ~80 kernels) */
+int b2pt_cuda_launch_count(b2pt_ctx* ctx, uint64_t* out_count);
 int b2pt_counters_reset(b2pt_ctx* ctx);
 int b2pt_counters_read(b2pt_ctx* ctx, b2pt_counters_t* out);
 
