@@ -104,7 +104,7 @@ __device__ __forceinline__ void b2_flush_counters(const B2TraversalCounters& loc
 /* resident 64-thread blocks per SM the per-pixel pass kernels are compiled for (register cap 65536 / (64 * N)): their private
  * traversals are latency-bound, so occupancy is worth a few spills (measured: profiles/r02_results.md) */
 #ifndef B2_PASS_MIN_BLOCKS
-#define B2_PASS_MIN_BLOCKS 6
+#define B2_PASS_MIN_BLOCKS 8
 #endif
 template <class V, int PASS>
 __global__ void __launch_bounds__(B2_BLOCK_THREADS, B2_PASS_MIN_BLOCKS) pass_kernel(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x)

@@ -24,6 +24,12 @@
 
 #define B2_WF_RAYS 5           /* ray slots per path: main, deferred X, deferred Y, envmap light, envmap BSDF (slot 0 doubles as the sequential ray) */
 #define B2_WF_STAGE_THREADS 128
+#ifndef B2_WF_STAGE1_MIN_BLOCKS
+#define B2_WF_STAGE1_MIN_BLOCKS 3 /* resident 128-thread blocks per SM the shading kernels are compiled for (65536 / (128 N) registers) */
+#endif
+#ifndef B2_WF_STAGE2_MIN_BLOCKS
+#define B2_WF_STAGE2_MIN_BLOCKS 3
+#endif
 #define B2_WF_TRACE_THREADS 256
 #define B2_WF_TRACE_MIN_BLOCKS 4
 #define B2_WF_SORT_BUCKETS 1024 /* material index & 1023; the last bucket also takes paths whose main ray missed */
@@ -199,10 +205,30 @@ __global__ void __launch_bounds__(B2_WF_SORT_BUCKETS) wf_sort_scan(const WfBuffe
 
 __global__ void __launch_bounds__(256) wf_sort_scatter(const WfBuffers b, int list_in, int list_out)
 {
+    /* A block owns a contiguous chunk of the list: it counts its keys in shared memory, reserves one range per non-empty bucket
+     * with ONE global atomic, and places its entries with shared-memory atomics -- a frame has tens of materials, so per-entry
+     * global atomics on the bucket cursors serialise (measured: 0.38 ms per round, profiles/r02_launches_c4s.md). */
+    __shared__ unsigned int local[B2_WF_SORT_BUCKETS];
     const unsigned int count = b.counters[WF_C_ALIVE];
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    const unsigned int chunk = (count + gridDim.x - 1) / gridDim.x;
+    const unsigned int begin = blockIdx.x * chunk, end = min(begin + chunk, count);
+    if (begin >= end)
+        return;
+    for (int i = threadIdx.x; i < B2_WF_SORT_BUCKETS; i += blockDim.x)
+        local[i] = 0u;
+    __syncthreads();
+    for (unsigned int i = begin + threadIdx.x; i < end; i += blockDim.x)
+        atomicAdd(&local[b.keys[i]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < B2_WF_SORT_BUCKETS; i += blockDim.x)
     {
-        const unsigned int position = atomicAdd(&b.buckets[B2_WF_SORT_BUCKETS + b.keys[i]], 1u);
+        const unsigned int n = local[i];
+        local[i] = n ? atomicAdd(&b.buckets[B2_WF_SORT_BUCKETS + i], n) : 0u; /* first position of this block's range in bucket i */
+    }
+    __syncthreads();
+    for (unsigned int i = begin + threadIdx.x; i < end; i += blockDim.x)
+    {
+        const unsigned int position = atomicAdd(&local[b.keys[i]], 1u);
         b.list[list_out][position] = b.list[list_in][i];
     }
 }
@@ -296,7 +322,7 @@ __global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) w
 
 /* stage 1 of every live path, in material order: resolve the previous vertex's NEE, take the main hit, begin this vertex's NEE */
 template <class V>
-__global__ void __launch_bounds__(B2_WF_STAGE_THREADS) wf_stage1(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b, int list_in, int list_out)
+__global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE1_MIN_BLOCKS) wf_stage1(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b, int list_in, int list_out)
 {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     b2_block_constants_init(rd);
@@ -353,7 +379,7 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS) wf_stage1(const __grid_co
 
 /* stage 2: rest of the NEE sampling, envmap NEE, next direction; ends with the rays of the next trace A */
 template <class V>
-__global__ void __launch_bounds__(B2_WF_STAGE_THREADS) wf_stage2(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b, int list_in, int list_out)
+__global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE2_MIN_BLOCKS) wf_stage2(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b, int list_in, int list_out)
 {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     b2_block_constants_init(rd);

@@ -16,6 +16,13 @@
  *   int32   material_indices[n_triangles]
  *   uint8   has_normals[n_vertices]            (padded with zeros to a multiple of 4 bytes)
  *   float   materials[n_materials][B2MAT_FLOAT_COUNT]
+ *   -- optional, only when the scene has textures (what the reference's Scene holds after ThreadFunctions::load_scene_texture,
+ *      src/Threads/ThreadFunctions.cpp:33-133) --
+ *   char    "B2TEXTR1"
+ *   uint32  n_textures
+ *   { uint32 width, height, channels; uint8 texels[height][width][channels] (row 0 first, as stb_image returns them, padded to 4 B) } x n_textures
+ *   int32   texture_indices[n_materials][B2TEX_SLOT_COUNT]   (index into the textures, B2TEX_NONE, or B2TEX_CONSTANT_EMISSIVE)
+ *   uint8   base_color_texture_opaque[n_materials]            (Scene::material_has_opaque_base_color_texture; 1 without texture)
  */
 #ifndef B2PT_SCENE_BLOB_H
 #define B2PT_SCENE_BLOB_H
@@ -60,6 +67,22 @@ enum B2MatField : int
     B2MAT_FLOAT_COUNT
 };
 
+/* texture slots of a material, in the order of CPUMaterial's *_texture_index members (MaterialCPU.h:313-328) */
+enum B2TexSlot : int
+{
+    B2TEX_normal_map, B2TEX_emission, B2TEX_base_color, B2TEX_roughness_metallic, B2TEX_roughness, B2TEX_metallic, B2TEX_anisotropic,
+    B2TEX_specular, B2TEX_coat, B2TEX_sheen, B2TEX_specular_transmission,
+    B2TEX_SLOT_COUNT
+};
+#define B2TEX_NONE 65535              /* MaterialConstants::NO_TEXTURE */
+#define B2TEX_CONSTANT_EMISSIVE 65534 /* MaterialConstants::CONSTANT_EMISSIVE_TEXTURE */
+
+struct B2SceneTexture
+{
+    uint32_t width = 0, height = 0, channels = 0;
+    std::vector<uint8_t> texels;
+};
+
 struct B2SceneCamera
 {
     /* Row-major 4x4 matrices, right-multiplied by column points; same meaning as the reference's
@@ -91,6 +114,12 @@ struct B2Scene
     std::vector<int32_t> material_indices; /* n_triangles */
     std::vector<uint8_t> has_normals;    /* n_vertices */
     std::vector<float> materials;        /* n_materials * B2MAT_FLOAT_COUNT */
+    std::vector<B2SceneTexture> textures;           /* optional */
+    std::vector<int32_t> texture_indices;           /* n_materials * B2TEX_SLOT_COUNT, or empty (no textures) */
+    std::vector<uint8_t> base_color_texture_opaque; /* n_materials, or empty */
+
+    int texture_index(size_t material, int slot) const { return texture_indices.empty() ? B2TEX_NONE : texture_indices[material * B2TEX_SLOT_COUNT + slot]; }
+    bool base_color_opaque(size_t material) const { return base_color_texture_opaque.empty() ? true : base_color_texture_opaque[material] != 0; }
 
     size_t n_vertices() const { return has_normals.size(); }
     size_t n_triangles() const { return material_indices.size(); }
@@ -151,10 +180,56 @@ inline std::string b2scene_read(const char* path, B2Scene& out)
     if (pad)
         std::fseek(f, (long)pad, SEEK_CUR);
     rd(out.materials.data(), out.materials.size() * 4);
+    out.textures.clear();
+    out.texture_indices.clear();
+    out.base_color_texture_opaque.clear();
+    char tag[8];
+    if (ok && std::fread(tag, 1, 8, f) == 8 && std::memcmp(tag, "B2TEXTR1", 8) == 0)
+    {
+        long here = std::ftell(f);
+        std::fseek(f, 0, SEEK_END);
+        const unsigned long long file_bytes = (unsigned long long)std::ftell(f);
+        std::fseek(f, here, SEEK_SET);
+        uint32_t n_textures = 0;
+        rd(&n_textures, 4);
+        if (ok && 12ull * n_textures > file_bytes)
+            ok = false;
+        for (uint32_t t = 0; ok && t < n_textures; t++)
+        {
+            B2SceneTexture tex;
+            uint32_t dims[3] = { 0, 0, 0 };
+            rd(dims, 12);
+            const unsigned long long bytes = (unsigned long long)dims[0] * dims[1] * dims[2];
+            if (!ok || dims[2] < 1 || dims[2] > 4 || bytes > file_bytes)
+            {
+                ok = false;
+                break;
+            }
+            tex.width = dims[0];
+            tex.height = dims[1];
+            tex.channels = dims[2];
+            tex.texels.resize((size_t)bytes);
+            rd(tex.texels.data(), tex.texels.size());
+            const long pad = (long)((4 - (bytes & 3)) & 3);
+            if (pad)
+                std::fseek(f, pad, SEEK_CUR);
+            out.textures.push_back(std::move(tex));
+        }
+        if (ok)
+        {
+            out.texture_indices.resize((size_t)h.n_materials * B2TEX_SLOT_COUNT);
+            out.base_color_texture_opaque.resize(h.n_materials);
+            rd(out.texture_indices.data(), out.texture_indices.size() * 4);
+            rd(out.base_color_texture_opaque.data(), out.base_color_texture_opaque.size());
+            for (int32_t idx : out.texture_indices)
+                if (!(idx == B2TEX_NONE || idx == B2TEX_CONSTANT_EMISSIVE || (idx >= 0 && (size_t)idx < out.textures.size())))
+                    ok = false;
+        }
+    }
     std::fclose(f);
 
     if (!ok)
-        return std::string("truncated scene blob: ") + path;
+        return std::string("truncated or corrupt scene blob: ") + path;
     return "";
 }
 
@@ -181,6 +256,21 @@ inline std::string b2scene_write(const char* path, const B2Scene& s)
     const char zeros[4] = { 0, 0, 0, 0 };
     std::fwrite(zeros, 1, (4 - (s.n_vertices() & 3)) & 3, f);
     std::fwrite(s.materials.data(), 4, s.materials.size(), f);
+    if (!s.textures.empty())
+    {
+        std::fwrite("B2TEXTR1", 1, 8, f);
+        const uint32_t n_textures = (uint32_t)s.textures.size();
+        std::fwrite(&n_textures, 4, 1, f);
+        for (const B2SceneTexture& t : s.textures)
+        {
+            const uint32_t dims[3] = { t.width, t.height, t.channels };
+            std::fwrite(dims, 4, 3, f);
+            std::fwrite(t.texels.data(), 1, t.texels.size(), f);
+            std::fwrite(zeros, 1, (4 - (t.texels.size() & 3)) & 3, f);
+        }
+        std::fwrite(s.texture_indices.data(), 4, s.texture_indices.size(), f);
+        std::fwrite(s.base_color_texture_opaque.data(), 1, s.base_color_texture_opaque.size(), f);
+    }
     std::fclose(f);
     return "";
 }

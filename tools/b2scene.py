@@ -61,7 +61,13 @@ def camera_block(inverse_view, inverse_projection, view_projection, position, ve
             + struct.pack("<f", vertical_fov))
 
 
-def write_scene(path, camera_bytes, positions, normals, texcoords, indices, material_indices, has_normals, materials):
+TEX_SLOTS = ["normal_map", "emission", "base_color", "roughness_metallic", "roughness", "metallic", "anisotropic", "specular", "coat", "sheen", "specular_transmission"]
+TEX_NONE, TEX_CONSTANT_EMISSIVE = 65535, 65534
+
+
+def write_scene(path, camera_bytes, positions, normals, texcoords, indices, material_indices, has_normals, materials, textures=None, texture_indices=None,
+                base_color_texture_opaque=None):
+    """textures: list of uint8 arrays (height, width, channels), row 0 first; texture_indices: (n_materials, 11) int32 (TEX_SLOTS order)."""
     positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
     normals = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
     texcoords = np.ascontiguousarray(texcoords, np.float32).reshape(-1, 2)
@@ -80,6 +86,24 @@ def write_scene(path, camera_bytes, positions, normals, texcoords, indices, mate
             f.write(a.tobytes())
         f.write(b"\0" * ((4 - (nv & 3)) & 3))
         f.write(materials.tobytes())
+        if textures:
+            texture_indices = np.ascontiguousarray(texture_indices, np.int32).reshape(nm, len(TEX_SLOTS))
+            if base_color_texture_opaque is None:
+                base_color_texture_opaque = np.ones(nm, np.uint8)
+                for m in range(nm):
+                    idx = texture_indices[m, TEX_SLOTS.index("base_color")]
+                    if idx < len(textures) and textures[idx].shape[2] == 4:
+                        base_color_texture_opaque[m] = 1 if (textures[idx][..., 3] == 255).all() else 0   # Image8Bit::is_fully_opaque
+            f.write(b"B2TEXTR1")
+            f.write(struct.pack("<I", len(textures)))
+            for tex in textures:
+                tex = np.ascontiguousarray(tex, np.uint8)
+                hgt, wid, ch = tex.shape
+                f.write(struct.pack("<3I", wid, hgt, ch))
+                f.write(tex.tobytes())
+                f.write(b"\0" * ((4 - (tex.size & 3)) & 3))
+            f.write(texture_indices.tobytes())
+            f.write(np.ascontiguousarray(base_color_texture_opaque, np.uint8).tobytes())
 
 
 def read_scene(path):
@@ -109,6 +133,19 @@ def read_scene(path):
     )
     off += (4 - (nv & 3)) & 3
     out["materials"] = take(np.float32, nm * nf, (nm, nf))
+    if buf[off:off + 8] == b"B2TEXTR1":
+        off += 8
+        (n_tex,) = struct.unpack_from("<I", buf, off)
+        off += 4
+        textures = []
+        for _ in range(n_tex):
+            wid, hgt, ch = struct.unpack_from("<3I", buf, off)
+            off += 12
+            textures.append(take(np.uint8, wid * hgt * ch, (hgt, wid, ch)))
+            off += (4 - ((wid * hgt * ch) & 3)) & 3
+        out["textures"] = textures
+        out["texture_indices"] = take(np.int32, nm * len(TEX_SLOTS), (nm, len(TEX_SLOTS)))
+        out["base_color_texture_opaque"] = take(np.uint8, nm, (nm,))
     return out
 
 
