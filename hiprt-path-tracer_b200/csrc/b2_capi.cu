@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -325,6 +326,64 @@ int b2pt_lut_destroy(b2pt_ctx* ctx, void* handle)
 {
     B2_SELECT_DEVICE(ctx);
     if (handle) B2_CUDA(cudaFree(handle));
+    return B2PT_OK;
+}
+
+/* Material textures. Replaces the std::vector<OrochiTexture> of the reference's scene + the array of texture objects it uploads
+ * (GPURenderer::set_scene, GPURenderer.cpp:905-939): one allocation = [descriptors][sRGB decode table][texels...]. */
+int b2pt_textures_create(b2pt_ctx* ctx, const uint8_t* const* texels, const int* widths, const int* heights, const int* channels, int count, void** out_array)
+{
+    B2_SELECT_DEVICE(ctx);
+    if (!ctx || !out_array || count < 0 || (count > 0 && (!texels || !widths || !heights || !channels)))
+    {
+        b2_set_error("b2pt_textures_create: invalid argument");
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    *out_array = nullptr;
+    if (count == 0)
+        return B2PT_OK;
+    struct Descriptor { const uint8_t* texels; int width, height, channels; const float* srgb_to_linear; };
+    static_assert(sizeof(Descriptor) == 32, "b2pt_texture layout (b2_material.h)");
+    size_t offset = ((size_t)count * sizeof(Descriptor) + 255) & ~(size_t)255;
+    const size_t table_offset = offset;
+    offset += 256 * sizeof(float);
+    std::vector<size_t> texel_offsets((size_t)count);
+    for (int i = 0; i < count; i++)
+    {
+        if (!texels[i] || widths[i] <= 0 || heights[i] <= 0 || channels[i] < 1 || channels[i] > 4)
+        {
+            b2_set_error("b2pt_textures_create: texture %d is %dx%d with %d channels", i, widths[i], heights[i], channels[i]);
+            return B2PT_ERR_INVALID_ARGUMENT;
+        }
+        texel_offsets[i] = offset;
+        offset += ((size_t)widths[i] * heights[i] * channels[i] + 255) & ~(size_t)255;
+    }
+    char* block = nullptr;
+    B2_CUDA(cudaMalloc((void**)&block, offset));
+    std::vector<Descriptor> descriptors((size_t)count);
+    for (int i = 0; i < count; i++)
+    {
+        descriptors[i].texels = reinterpret_cast<const uint8_t*>(block + texel_offsets[i]);
+        descriptors[i].width = widths[i];
+        descriptors[i].height = heights[i];
+        descriptors[i].channels = channels[i];
+        descriptors[i].srgb_to_linear = reinterpret_cast<const float*>(block + table_offset);
+        B2_CUDA(cudaMemcpy(block + texel_offsets[i], texels[i], (size_t)widths[i] * heights[i] * channels[i], cudaMemcpyHostToDevice));
+    }
+    /* sample_texture_rgba's sRGB decode, intrin_pow(texel / 255, 2.2) (Texture.h:62-65): the host C library's powf on the 256 texel values */
+    float table[256];
+    for (int v = 0; v < 256; v++)
+        table[v] = powf((float)v / 255.0f, 2.2f);
+    B2_CUDA(cudaMemcpy(block + table_offset, table, sizeof(table), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(block, descriptors.data(), descriptors.size() * sizeof(Descriptor), cudaMemcpyHostToDevice));
+    *out_array = block;
+    return B2PT_OK;
+}
+
+int b2pt_textures_destroy(b2pt_ctx* ctx, void* array)
+{
+    B2_SELECT_DEVICE(ctx);
+    if (array) B2_CUDA(cudaFree(array));
     return B2PT_OK;
 }
 

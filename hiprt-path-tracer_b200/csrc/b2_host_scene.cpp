@@ -81,7 +81,7 @@ SafeMaterial make_safe(const float* rec)
 inline Rgb rgb_at(const SafeMaterial& m, int i) { return rgb(m.f[i], m.f[i + 1], m.f[i + 2]); }
 
 /* CPUMaterial::pack_to_GPU, MaterialCPU.h:31-120 */
-B2PackedTexturedMaterial pack_to_gpu(const SafeMaterial& m)
+B2PackedTexturedMaterial pack_to_gpu(const SafeMaterial& m, const int* tex /* B2TEX_SLOT_COUNT indices, or null */)
 {
     B2PackedTexturedMaterial out;
     Mat u = mat_defaults();
@@ -145,15 +145,16 @@ B2PackedTexturedMaterial pack_to_gpu(const SafeMaterial& m)
     for (int i = 0; i < 27; i++)
         out.effective[i] = p.w[i];
 
-    /* texture indices: every slot NO_TEXTURE. The reference's setters for the anisotropic index write into the
-     * roughness/metallic word (MaterialPacked.h:717), which leaves the anisotropic half of word 3 at 0. */
-    const uint32_t none = 0xFFFFu;
-    out.texture_indices[0] = none | (none << 16); /* normal map | emission */
-    out.texture_indices[1] = none | (none << 16); /* base colour | roughness-metallic */
-    out.texture_indices[2] = none | (none << 16); /* roughness (then anisotropic, same slot) | metallic */
-    out.texture_indices[3] = none << 16;          /* (anisotropic: never written) | specular */
-    out.texture_indices[4] = none | (none << 16); /* coat | sheen */
-    out.texture_indices[5] = none;                /* specular transmission */
+    /* texture indices, with the reference's setters (MaterialPacked.h:725-735, in CPUMaterial::pack_to_GPU's order): the anisotropic
+     * index is written into the ROUGHNESS slot of the roughness/metallic word (:731), after the roughness index, so it replaces it;
+     * the anisotropic half of the anisotropic/specular word is never written and stays 0 */
+    auto idx = [&](int slot) -> uint32_t { return tex ? (uint32_t)tex[slot] & 0xFFFFu : 0xFFFFu; };
+    out.texture_indices[0] = idx(B2TEX_normal_map) | (idx(B2TEX_emission) << 16);
+    out.texture_indices[1] = idx(B2TEX_base_color) | (idx(B2TEX_roughness_metallic) << 16);
+    out.texture_indices[2] = idx(B2TEX_anisotropic) | (idx(B2TEX_metallic) << 16);
+    out.texture_indices[3] = idx(B2TEX_specular) << 16;
+    out.texture_indices[4] = idx(B2TEX_coat) | (idx(B2TEX_sheen) << 16);
+    out.texture_indices[5] = idx(B2TEX_specular_transmission);
     return out;
 }
 } // namespace
@@ -197,8 +198,15 @@ bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bv
             error = "dispersive media are not supported by the B200 path yet (SURVEY section 8: out of the configured scope)";
             return false;
         }
-        scene.packed_materials[i] = pack_to_gpu(safe[i]);
-        scene.material_opaque[i] = safe[i].f[B2MAT_alpha_opacity] == 1.0f;
+        scene.packed_materials[i] = pack_to_gpu(safe[i], blob.texture_indices.empty() ? nullptr : &blob.texture_indices[i * B2TEX_SLOT_COUNT]);
+        /* CPURenderer.cpp:312: opaque = fully opaque base colour texture (or none) and alpha_opacity == 1 */
+        scene.material_opaque[i] = blob.base_color_opaque(i) && safe[i].f[B2MAT_alpha_opacity] == 1.0f;
+        if (!scene.material_opaque[i])
+        {
+            error = "alpha-tested materials are not supported by the B200 path: the reference draws the test's random numbers in the order its CPU octree meets "
+                    "candidate triangles, which another acceleration structure cannot reproduce (alpha_opacity < 1 or a base colour texture with alpha)";
+            return false;
+        }
     }
 
     /* AoS -> SoA */
@@ -247,9 +255,16 @@ bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bv
     /* triangle areas (ThreadFunctions.cpp:221-243) and the emissive list (:136-194) */
     scene.triangle_areas.resize(n_tri);
     scene.emissive_triangles.clear();
-    std::vector<uint8_t> mat_emissive(n_mat);
+    scene.emissive_triangles_and_textures.clear();
+    /* ThreadFunctions.cpp:136-194: a mesh is emissive when its material emits or has a (non-constant) emission texture; triangles
+     * with an emission texture are not importance sampled: they are left out of the sampled list but kept in the second one */
+    std::vector<uint8_t> mat_emissive(n_mat), mat_emission_textured(n_mat);
     for (size_t i = 0; i < n_mat; i++)
-        mat_emissive[i] = !b2_is_zero(safe[i].f[B2MAT_emission_r]) || !b2_is_zero(safe[i].f[B2MAT_emission_g]) || !b2_is_zero(safe[i].f[B2MAT_emission_b]);
+    {
+        const int emission_texture = blob.texture_index(i, B2TEX_emission);
+        mat_emission_textured[i] = emission_texture != B2TEX_NONE && emission_texture != B2TEX_CONSTANT_EMISSIVE;
+        mat_emissive[i] = !b2_is_zero(safe[i].f[B2MAT_emission_r]) || !b2_is_zero(safe[i].f[B2MAT_emission_g]) || !b2_is_zero(safe[i].f[B2MAT_emission_b]) || mat_emission_textured[i];
+    }
     auto vertex = [&](int idx) { return v3(blob.positions[3 * (size_t)idx], blob.positions[3 * (size_t)idx + 1], blob.positions[3 * (size_t)idx + 2]); };
     for (size_t t = 0; t < n_tri; t++)
     {
@@ -257,7 +272,11 @@ bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bv
         V3 normal = cross(B - A, C - A);
         scene.triangle_areas[t] = length(normal) * 0.5f;
         if (mat_emissive[blob.material_indices[t]])
-            scene.emissive_triangles.push_back((int)t);
+        {
+            if (!mat_emission_textured[blob.material_indices[t]])
+                scene.emissive_triangles.push_back((int)t);
+            scene.emissive_triangles_and_textures.push_back((int)t);
+        }
     }
 
     /* power-proportional alias table (CPURenderer.cpp:420-465): built for every scene, used by the POWER variants */

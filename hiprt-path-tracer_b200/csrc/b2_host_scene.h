@@ -71,6 +71,7 @@ struct B2HostScene
     std::vector<uint8_t> material_opaque;
     std::vector<float> triangle_areas;
     std::vector<int> emissive_triangles;
+    std::vector<int> emissive_triangles_and_textures; /* + triangles whose material has an emission texture (not importance sampled) */
     std::vector<float> power_alias_probas;
     std::vector<int> power_alias_alias;
     float power_sum = 0.0f;

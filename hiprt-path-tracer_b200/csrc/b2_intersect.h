@@ -7,7 +7,10 @@
  *   evaluate_bsdf_light_sample_ray  :544-643   closest hit returning the emission of what was hit
  * plus NestedDielectricsInteriorStack (NestedDielectrics.h:64-255), RayVolumeState (RayVolumeState.h:13-80),
  * RayPayload (RayPayload.h:22-92) and fix_backfacing_normals (Intersect.h:142-176).
- * Untextured, opaque materials only (alpha testing / normal maps / emissive textures are SURVEY section 8f rank 3).
+ * Textured materials (8-bit textures, sRGB decode, normal maps, emissive textures: Texture.h, Material.h, Intersect.h:77-134) included;
+ * alpha-TESTED materials are refused at scene upload: the reference's CPU path draws the alpha test's random numbers in the order its
+ * octree meets candidate triangles (BVH.h:153-176 calls the filter for every triangle of every visited leaf), which no other
+ * acceleration structure reproduces.
  */
 #ifndef B2_INTERSECT_H
 #define B2_INTERSECT_H
@@ -289,18 +292,53 @@ B2_HD void fix_backfacing_normals(HitInfo& hit, V3 view_direction)
     }
 }
 
-/* get_shading_normal without normal maps (Intersect.h:114-134): smooth normal when the first vertex has one */
-B2_HD V3 shading_normal_at(const b2pt_render_data& rd, V3 geometric_normal, int i0, int i1, int i2, float u, float v)
+/* local_to_world_frame (ONB.h): T * v.x + B * v.y + N * v.z */
+B2_HD V3 b2_local_to_world_frame(V3 T, V3 B, V3 N, V3 v) { return normalize(v.x * T + v.y * B + v.z * N); }
+
+/* normal_mapping (Intersect.h:77-112) */
+B2_HD V3 normal_mapping(const b2pt_render_data& rd, int normal_map_texture_index, int i0, int i1, int i2, V2 interpolated_texcoords, V3 surface_normal)
+{
+    const b2pt_float2 tA = rd.buffers.texcoords[i0], tB = rd.buffers.texcoords[i1], tC = rd.buffers.texcoords[i2];
+    V2 delta_P1P0 = v2(tB.x, tB.y) - v2(tA.x, tA.y);
+    V2 delta_P2P0 = v2(tC.x, tC.y) - v2(tA.x, tA.y);
+    V3 P0 = load_v3(rd.buffers.vertices_positions, i0), P1 = load_v3(rd.buffers.vertices_positions, i1), P2 = load_v3(rd.buffers.vertices_positions, i2);
+    V3 edge_P0P1 = P1 - P0;
+    V3 edge_P0P2 = P2 - P0;
+
+    const float det_bias = 1.0e-6f;
+    float det = delta_P1P0.x * delta_P2P0.y - delta_P1P0.y * delta_P2P0.x + det_bias;
+    float det_inverse = 1.0f / det;
+    V3 T = (edge_P0P1 * delta_P2P0.y - edge_P0P2 * delta_P1P0.y) * det_inverse;
+    V3 B = (edge_P0P2 * delta_P1P0.x - edge_P0P1 * delta_P2P0.x) * det_inverse;
+    if (length2(T) < 1.0e-6f || length2(B) < 1.0e-6f)
+        return surface_normal;
+
+    float rgba[4];
+    sample_texture_rgba(rd.buffers.material_textures, normal_map_texture_index, false, interpolated_texcoords, rgba);
+    V3 normal_tangent_space = normalize(v3(rgba[0] - 0.5f, rgba[1] - 0.5f, rgba[2] - 0.5f));
+    return b2_local_to_world_frame(normalize(T), normalize(B), surface_normal, normal_tangent_space);
+}
+
+/* get_shading_normal (Intersect.h:114-134): smooth normal when the first vertex has one, then the material's normal map */
+B2_HD V3 shading_normal_at(const b2pt_render_data& rd, V3 geometric_normal, int i0, int i1, int i2, float u, float v, int primitive_index, V2 interpolated_texcoords)
 {
     if (!rd.render_settings.do_normal_mapping)
         return geometric_normal;
+    V3 surface_normal = geometric_normal;
     if (rd.buffers.has_vertex_normals[i0])
     {
         /* uv_interpolate: A * (1 - u - v) + B * u + C * v  (Texture.h) */
         V3 nA = load_v3(rd.buffers.vertex_normals, i0), nB = load_v3(rd.buffers.vertex_normals, i1), nC = load_v3(rd.buffers.vertex_normals, i2);
-        return normalize(nB * u + nC * v + nA * (1.0f - u - v));
+        surface_normal = normalize(nB * u + nC * v + nA * (1.0f - u - v));
     }
-    return geometric_normal;
+    if (rd.buffers.material_textures != nullptr)
+    {
+        const int material_index = rd.buffers.material_indices[primitive_index];
+        const int normal_map_texture_index = (int)(rd.buffers.materials_buffer.normal_map_emission_index[material_index] & 0xFFFFu);
+        if (normal_map_texture_index != B2_NO_TEXTURE)
+            surface_normal = normal_mapping(rd, normal_map_texture_index, i0, i1, i2, interpolated_texcoords, surface_normal);
+    }
+    return surface_normal;
 }
 
 /* sample_wavelength_uniformly (Dispersion.h:16-17,469-474): integer constants, so (830 - 360) is an int */
@@ -353,11 +391,15 @@ B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload&
         /* hiprtHit::normal is already normalize(cross(e1, e2)) in the CPU path (Triangle.h:53) and
          * trace_main_path_ray normalises it once more (Intersect.h:235) */
         out_hit.geometric_normal = normalize(normalize(hit.ng));
-        out_hit.shading_normal = shading_normal_at(rd, out_hit.geometric_normal, i0, i1, i2, hit.u, hit.v);
+        out_hit.shading_normal = shading_normal_at(rd, out_hit.geometric_normal, i0, i1, i2, hit.u, hit.v, hit.prim, out_hit.texcoords);
         out_hit.t = hit.t;
 
         const int material_index = rd.buffers.material_indices[hit.prim];
-        payload.material = load_scene_material(rd.buffers.materials_buffer, material_index, rd.bsdfs_data.white_furnace_mode != 0);
+        /* scenes without a single texture keep the shorter untextured gather (same values: every texture index is NO_TEXTURE) */
+        if (rd.buffers.material_textures != nullptr)
+            payload.material = load_scene_material_textured(rd.buffers.materials_buffer, rd.buffers.material_textures, material_index, out_hit.texcoords, rd.bsdfs_data.white_furnace_mode != 0);
+        else
+            payload.material = load_scene_material(rd.buffers.materials_buffer, material_index, rd.bsdfs_data.white_furnace_mode != 0);
 
         skipping_volume_boundary = payload.volume_state.interior_stack.push(
             payload.volume_state.incident_mat_index, payload.volume_state.outgoing_mat_index, payload.volume_state.inside_material,
@@ -419,9 +461,30 @@ B2_HD bool light_ray_hit_from(const b2pt_render_data& rd, const B2Hit& hit, floa
     const int i1 = rd.buffers.triangles_indices[hit.prim * 3 + 1];
     const int i2 = rd.buffers.triangles_indices[hit.prim * 3 + 2];
     const int material_index = rd.buffers.material_indices[hit.prim];
+    V2 interpolated_texcoords;
+    {
+        const b2pt_float2 tA = rd.buffers.texcoords[i0], tB = rd.buffers.texcoords[i1], tC = rd.buffers.texcoords[i2];
+        interpolated_texcoords = v2(tB.x, tB.y) * hit.u + v2(tC.x, tC.y) * hit.v + v2(tA.x, tA.y) * (1.0f - hit.u - hit.v);
+    }
     out.emission = load_rgb(rd.buffers.materials_buffer.emission, material_index);
+    if (rd.buffers.material_textures != nullptr)
+    {
+        /* Intersect.h:620-623: any emission texture index but NO_TEXTURE reads the texture (get_material_property returns black for
+         * the CONSTANT_EMISSIVE marker) */
+        const int emission_texture_index = (int)(rd.buffers.materials_buffer.normal_map_emission_index[material_index] >> 16);
+        if (emission_texture_index != B2_NO_TEXTURE)
+        {
+            out.emission = rgb(0.0f);
+            if (emission_texture_index != B2_CONSTANT_EMISSIVE_TEXTURE)
+            {
+                float rgba[4];
+                sample_texture_rgba(rd.buffers.material_textures, emission_texture_index, false, interpolated_texcoords, rgba);
+                out.emission = rgb(rgba[0], rgba[1], rgba[2]);
+            }
+        }
+    }
     out.geometric_normal = normalize(normalize(hit.ng));
-    out.shading_normal = shading_normal_at(rd, out.geometric_normal, i0, i1, i2, hit.u, hit.v);
+    out.shading_normal = shading_normal_at(rd, out.geometric_normal, i0, i1, i2, hit.u, hit.v, hit.prim, interpolated_texcoords);
     out.prim = hit.prim;
     out.material_index = material_index;
     out.distance = hit.t;

@@ -443,6 +443,265 @@ B2_HD Mat load_scene_material(const b2pt_materials_soa& s, int i, bool white_fur
     return m;
 }
 
+/* ---- material textures --------------------------------------------------------------------------------------------------------
+ * What RenderBuffers::material_textures points to on this device layer: an array of these descriptors (the reference's array of
+ * oroTextureObject_t on its GPU path, of Image8Bit on its CPU path). 8-bit texels, 1 or 4 channels, row 0 first; the descriptor is
+ * what b2pt_texture_create returns. */
+struct b2pt_texture
+{
+    const uint8_t* texels;
+    int width, height, channels;
+    /* 255^2.2-style decode of the 256 possible texel values, computed ON THE HOST with the C library's powf (sample_texture_rgba's
+     * `intrin_pow(rgba, 2.2f)`, Texture.h:62-65, is powf in the reference's host build) so that the device needs no pow at all */
+    const float* srgb_to_linear;
+};
+
+/* Image8Bit::sample_rgba32f (src/Image/Image.cpp:161-195): nearest texel, repeat addressing, v flipped; channels beyond the
+ * image's keep ColorRGBA32F's defaults (0, 0, 0, 1). Then sample_texture_rgba's sRGB decode of ALL four channels. */
+B2_HD void sample_texture_rgba(const void* textures, int texture_index, bool is_srgb, V2 uv, float (&rgba)[4])
+{
+    const b2pt_texture& t = reinterpret_cast<const b2pt_texture*>(textures)[texture_index];
+    float u = uv.x;
+    if (u != 1.0f)
+        u -= (float)(int)uv.x;
+    float v = uv.y;
+    if (v != 1.0f)
+        v -= (float)(int)uv.y;
+    u = u < 0.0f ? 1.0f + u : u;
+    v = v < 0.0f ? 1.0f + v : v;
+    v = 1.0f - v;
+    int x = (int)(u * (float)(t.width - 1));
+    int y = (int)(v * (float)(t.height - 1));
+    rgba[0] = rgba[1] = rgba[2] = 0.0f;
+    rgba[3] = 1.0f;
+    const uint8_t* texel = t.texels + ((size_t)x + (size_t)y * (size_t)t.width) * (size_t)t.channels;
+    for (int c = 0; c < t.channels; c++)
+        rgba[c] = (float)texel[c] / 255.0f;
+    if (is_srgb)
+    {
+        /* intrin_pow(rgba, 2.2f): on texel channels a table lookup; on defaulted channels pow(0) = 0 and pow(1) = 1 */
+        for (int c = 0; c < t.channels; c++)
+            rgba[c] = t.srgb_to_linear[texel[c]];
+    }
+}
+
+/* texture indices of a material: the six packed words of DevicePackedTexturedMaterialSoA and the reference's getters
+ * (MaterialPacked.h:713-723) -- including get_anisotropic_texture_index reading the ROUGHNESS slot of the roughness/metallic word */
+struct MatTextureIndices
+{
+    int normal_map, emission, base_color, roughness_metallic, roughness, metallic, anisotropic, specular, coat, sheen, specular_transmission;
+};
+B2_HD MatTextureIndices load_texture_indices(const b2pt_materials_soa& s, int i)
+{
+    MatTextureIndices t;
+    const uint32_t w0 = s.normal_map_emission_index[i], w1 = s.base_color_roughness_metallic_index[i], w2 = s.roughness_and_metallic_index[i];
+    const uint32_t w3 = s.anisotropic_specular_index[i], w4 = s.coat_sheen_index[i], w5 = s.specular_transmission_index[i];
+    t.normal_map = (int)(w0 & 0xFFFFu);
+    t.emission = (int)(w0 >> 16);
+    t.base_color = (int)(w1 & 0xFFFFu);
+    t.roughness_metallic = (int)(w1 >> 16);
+    t.roughness = (int)(w2 & 0xFFFFu);
+    t.metallic = (int)(w2 >> 16);
+    t.anisotropic = (int)(w2 & 0xFFFFu);
+    t.specular = (int)(w3 >> 16);
+    t.coat = (int)(w4 & 0xFFFFu);
+    t.sheen = (int)(w4 >> 16);
+    t.specular_transmission = (int)(w5 & 0xFFFFu);
+    return t;
+}
+
+#define B2_CONSTANT_EMISSIVE_TEXTURE 65534
+
+/* get_material_property<float> (Material.h:213-221): the red channel, 0 without texture */
+B2_HD float material_property_float(const void* textures, V2 texcoords, int texture_index)
+{
+    if (texture_index == B2_NO_TEXTURE || texture_index == B2_CONSTANT_EMISSIVE_TEXTURE)
+        return 0.0f;
+    float rgba[4];
+    sample_texture_rgba(textures, texture_index, false, texcoords, rgba);
+    return rgba[0];
+}
+
+/*
+ * Scene SoA + textures -> working material: get_intersection_material (Material.h:60-150) over read_partial_material
+ * (MaterialPackedSoA.h:381-551) and DevicePackedTexturedMaterial::unpack (MaterialPacked.h:541-668). A parameter that has a texture
+ * is skipped by read_partial_material (its packed word stays 0) and replaced by the texel afterwards; a lobe's secondary parameters
+ * are loaded when the lobe weight is > 0 OR the weight has a texture.
+ */
+B2_HD Mat load_scene_material_textured(const b2pt_materials_soa& s, const void* textures, int i, V2 texcoords, bool white_furnace)
+{
+    const MatTextureIndices tx = load_texture_indices(s, i);
+    Mat m = mat_defaults();
+    uint32_t flags = s.flags[i];
+
+    bool packed_emissive_texture_used = (flags >> B2_FLAG_EMISSIVE_TEXTURE_USED) & 1u;
+    if (!packed_emissive_texture_used)
+        m.emission = rgb(s.emission[i].r, s.emission[i].g, s.emission[i].b);
+
+    uint32_t bcr = s.base_color_roughness[i];
+    if (tx.base_color == B2_NO_TEXTURE)
+        m.base_color = unpack_rgb24(bcr);
+    /* roughness: skipped by read_partial_material when a roughness / roughness-metallic texture exists (the packed 0 is unpacked) */
+    m.roughness = (tx.roughness == B2_NO_TEXTURE && tx.roughness_metallic == B2_NO_TEXTURE) ? unpack_hi8(bcr) : 0.0f;
+    m.oren_nayar_sigma = s.oren_nayar_sigma[i];
+
+    uint32_t mf90 = s.metallic_F90_and_metallic[i];
+    m.metallic = unpack_hi8(mf90);
+    uint32_t aniso = s.anisotropy_and_rotation_and_second_roughness[i];
+    uint32_t mf82 = s.metallic_F82_packed_and_diffuse_transmission[i];
+    if (m.metallic > 0.0f || tx.metallic != B2_NO_TEXTURE || tx.roughness_metallic != B2_NO_TEXTURE)
+    {
+        m.metallic_F90_falloff_exponent = s.metallic_F90_falloff_exponent[i];
+        m.metallic_F82 = unpack_rgb24(mf82);
+        m.metallic_F90 = unpack_rgb24(mf90);
+        m.second_roughness_weight = unpack_f8(aniso, 2);
+        m.second_roughness = unpack_f8(aniso, 3);
+        m.do_metallic_energy_compensation = (flags >> B2_FLAG_METALLIC_ENERGY_COMPENSATION) & 1u;
+    }
+    m.anisotropy = tx.anisotropic == B2_NO_TEXTURE ? unpack_f8(aniso, 0) : 0.0f;
+    m.anisotropy_rotation = unpack_f8(aniso, 1);
+
+    uint32_t spec = s.specular_and_darkening_and_coat_roughness[i];
+    m.specular = unpack_f8(spec, 0);
+    if (m.specular > 0.0f || tx.specular != B2_NO_TEXTURE)
+    {
+        uint32_t sct = s.specular_color_and_tint_factor[i];
+        m.specular_tint = unpack_hi8(sct);
+        m.specular_color = unpack_rgb24(sct);
+        m.specular_darkening = unpack_f8(spec, 1);
+        m.do_specular_energy_compensation = (flags >> B2_FLAG_SPECULAR_ENERGY_COMPENSATION) & 1u;
+    }
+
+    uint32_t coat_w = s.coat_and_medium_absorption[i];
+    m.coat = unpack_hi8(coat_w);
+    if (m.coat > 0.0f || tx.coat != B2_NO_TEXTURE)
+    {
+        uint32_t crd = s.coat_roughening_darkening_anisotropy_and_rotation[i];
+        m.coat_medium_absorption = unpack_rgb24(coat_w);
+        m.coat_medium_thickness = s.coat_medium_thickness[i];
+        m.coat_roughness = unpack_f8(spec, 2);
+        m.coat_roughening = unpack_f8(crd, 0);
+        m.coat_darkening = unpack_f8(crd, 1);
+        m.coat_anisotropy = unpack_f8(crd, 2);
+        m.coat_anisotropy_rotation = unpack_f8(crd, 3);
+        m.coat_ior = s.coat_ior[i];
+        m.do_coat_energy_compensation = (flags >> B2_FLAG_COAT_ENERGY_COMPENSATION) & 1u;
+    }
+
+    uint32_t sheen_w = s.sheen_and_color[i];
+    uint32_t srtd = s.sheen_roughness_transmission_dispersion_thin_film[i];
+    m.sheen = unpack_hi8(sheen_w);
+    if (m.sheen > 0.0f || tx.sheen != B2_NO_TEXTURE)
+    {
+        m.sheen_roughness = unpack_f8(srtd, 0);
+        m.sheen_color = unpack_rgb24(sheen_w);
+    }
+
+    m.ior = s.ior[i];
+    m.diffuse_transmission = unpack_hi8(mf82);
+    m.specular_transmission = unpack_f8(srtd, 1);
+    if (m.specular_transmission > 0.0f || tx.specular_transmission != B2_NO_TEXTURE)
+    {
+        m.dispersion_scale = unpack_f8(srtd, 2);
+        m.dispersion_abbe_number = s.dispersion_abbe_number[i];
+        m.thin_walled = (flags >> B2_FLAG_THIN_WALLED) & 1u;
+        m.do_glass_energy_compensation = (flags >> B2_FLAG_GLASS_ENERGY_COMPENSATION) & 1u;
+    }
+    if (m.specular_transmission > 0.0f || m.diffuse_transmission > 0.0f || tx.specular_transmission != B2_NO_TEXTURE)
+    {
+        m.absorption_at_distance = s.absorption_at_distance[i];
+        m.absorption_color = unpack_rgb24(s.absorption_color_packed[i]);
+    }
+
+    uint32_t ahp = s.alpha_thin_film_hue_dielectric_priority[i];
+    m.thin_film = unpack_f8(srtd, 3);
+    if (m.thin_film > 0.0f)
+    {
+        m.thin_film_ior = s.thin_film_ior[i];
+        m.thin_film_thickness = s.thin_film_thickness[i];
+        m.thin_film_kappa_3 = s.thin_film_kappa_3[i];
+        m.thin_film_hue_shift_degrees = unpack_f8(ahp, 1);
+        m.thin_film_base_ior_override = s.thin_film_base_ior_override[i] != 0.0f ? 1.0f : 0.0f;
+        m.thin_film_do_ior_override = (flags >> B2_FLAG_THIN_FILM_DO_IOR_OVERRIDE) & 1u;
+    }
+    m.alpha_opacity = unpack_f8(ahp, 0);
+    m.dielectric_priority = (uint8_t)((ahp >> 16) & 0xFFu);
+
+    /* ---- get_intersection_material (Material.h:60-150) ---- */
+    if (white_furnace)
+        m.base_color = rgb(1.0f);
+    else if (tx.base_color != B2_NO_TEXTURE)
+    {
+        float rgba[4];
+        sample_texture_rgba(textures, tx.base_color, true, texcoords, rgba);
+        m.base_color = rgb(rgba[0], rgba[1], rgba[2]);
+    }
+
+    /* get_metallic_roughness: (roughness, metallic) */
+    float tex_roughness, tex_metallic;
+    if (tx.roughness_metallic != B2_NO_TEXTURE)
+    {
+        float rgba[4];
+        sample_texture_rgba(textures, tx.roughness_metallic, false, texcoords, rgba);
+        tex_roughness = rgba[1];
+        tex_metallic = rgba[2];
+        m.roughness = tex_roughness;
+        m.metallic = tex_metallic;
+    }
+    else
+    {
+        tex_roughness = material_property_float(textures, texcoords, tx.roughness);
+        tex_metallic = material_property_float(textures, texcoords, tx.metallic);
+        if (tx.roughness != B2_NO_TEXTURE)
+            m.roughness = tex_roughness;
+        if (tx.metallic != B2_NO_TEXTURE)
+            m.metallic = tex_metallic;
+        tex_roughness = m.roughness;
+    }
+
+    if (tx.anisotropic != B2_NO_TEXTURE)
+        m.anisotropy = material_property_float(textures, texcoords, tx.anisotropic);
+    if (tx.specular != B2_NO_TEXTURE)
+        m.specular = material_property_float(textures, texcoords, tx.specular);
+    float coat = material_property_float(textures, texcoords, tx.coat);
+    if (tx.coat != B2_NO_TEXTURE)
+        m.coat = coat;
+    else
+        coat = m.coat;
+    if (tx.sheen != B2_NO_TEXTURE)
+        m.sheen = material_property_float(textures, texcoords, tx.sheen);
+    if (tx.specular_transmission != B2_NO_TEXTURE)
+        m.specular_transmission = material_property_float(textures, texcoords, tx.specular_transmission);
+
+    Rgb emission = m.emission;
+    if (!(tx.emission == B2_NO_TEXTURE || tx.emission == B2_CONSTANT_EMISSIVE_TEXTURE))
+    {
+        float rgba[4];
+        sample_texture_rgba(textures, tx.emission, false, texcoords, rgba);
+        emission = rgb(rgba[0], rgba[1], rgba[2]);
+    }
+    m.emissive_texture_used = tx.emission != B2_NO_TEXTURE;
+    m.emission = emission;
+
+    /* coat roughening of the base layer(s), Material.h:127-147: from the roughness READ ABOVE (texture or parameter) */
+    if (coat > 0.0f && m.coat_roughening > 0.0f)
+    {
+        float base_roughness = tex_roughness;
+        float coat_roughness = m.coat_roughness;
+        float target = b2_pow_1_4(b2_min(1.0f, b2_pow_4(base_roughness) + 2.0f * b2_pow_4(coat_roughness)));
+        float roughened = b2_lerp(base_roughness, target, coat);
+        m.roughness = b2_lerp(base_roughness, roughened, m.coat_roughening);
+        if (m.second_roughness_weight > 0.0f)
+        {
+            float second = m.second_roughness;
+            float target2 = b2_pow_1_4(b2_min(1.0f, b2_pow_4(second) + 2.0f * b2_pow_4(coat_roughness)));
+            float roughened2 = b2_lerp(second, target2, coat);
+            m.second_roughness = b2_lerp(second, roughened2, m.coat_roughening);
+        }
+    }
+    return m;
+}
+
 /* MaterialUtils (HostDeviceCommon/Material/MaterialUtils.h:16-178) */
 B2_HD void material_alphas(float roughness, float anisotropy, float& alpha_x, float& alpha_y)
 {

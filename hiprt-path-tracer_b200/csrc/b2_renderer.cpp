@@ -82,6 +82,7 @@ struct b2pt_renderer
     bool scene_pin_attempted = false; /* the host copies are page-locked on the first b2pt_renderer_reupload_scene */
     std::vector<Upload> scene_uploads; /* (device, host, bytes) of every scene array, for b2pt_renderer_reupload_scene */
     b2pt_bvh* bvh = nullptr;
+    void* textures = nullptr; /* b2pt_textures_create: the descriptor array RenderBuffers::material_textures points to */
     b2pt_kernel* kernels[B2_PASS_COUNT] = {};
     double pass_ms[B2_PASS_COUNT] = {};
     uint64_t pass_launches[B2_PASS_COUNT] = {};
@@ -303,12 +304,31 @@ int upload_scene(b2pt_renderer* r, bool keep_bvh = false)
     b.vertex_normals = reinterpret_cast<b2pt_float3*>(d_nrm);
     b.texcoords = reinterpret_cast<b2pt_float2*>(d_uv);
     b.emissive_triangles_count = (int)s.emissive_triangles.size();
-    b.emissive_triangles_primitive_indices_and_emissive_textures = b.emissive_triangles_primitive_indices;
+    B2_TRY(upload(r, r->scene_allocs, s.emissive_triangles_and_textures, &b.emissive_triangles_primitive_indices_and_emissive_textures));
     B2_TRY(upload(r, r->scene_allocs, s.power_alias_alias, &b.emissives_power_alias_table.alias_table_alias));
     B2_TRY(upload(r, r->scene_allocs, s.power_alias_probas, &b.emissives_power_alias_table.alias_table_probas));
     b.emissives_power_alias_table.sum_elements = s.power_sum;
     b.emissives_power_alias_table.size = (unsigned)s.emissive_triangles.size();
     b.material_textures = nullptr;
+    if (r->textures)
+    {
+        b2pt_textures_destroy(r->ctx, r->textures);
+        r->textures = nullptr;
+    }
+    if (!s.blob.textures.empty())
+    {
+        std::vector<const uint8_t*> texels;
+        std::vector<int> widths, heights, channels;
+        for (const B2SceneTexture& t : s.blob.textures)
+        {
+            texels.push_back(t.texels.data());
+            widths.push_back((int)t.width);
+            heights.push_back((int)t.height);
+            channels.push_back((int)t.channels);
+        }
+        B2_TRY(b2pt_textures_create(r->ctx, texels.data(), widths.data(), heights.data(), channels.data(), (int)texels.size(), &r->textures));
+        b.material_textures = r->textures;
+    }
 
     B2MaterialSoAHost& m = s.materials;
     b2pt_materials_soa& d = b.materials_buffer;
@@ -464,6 +484,7 @@ int b2pt_renderer_destroy(b2pt_renderer* r)
     for (void* h : r->lut_handles)
         b2pt_lut_destroy(r->ctx, h);
     if (r->bvh) b2pt_bvh_destroy(r->ctx, r->bvh);
+    if (r->textures) b2pt_textures_destroy(r->ctx, r->textures);
     b2pt_event_destroy(r->ctx, r->ev_start);
     b2pt_event_destroy(r->ctx, r->ev_stop);
     b2pt_stream_destroy(r->ctx, r->stream);

@@ -107,6 +107,12 @@ int b2pt_stream_launch_host_func(b2pt_ctx* ctx, b2pt_stream stream, b2pt_host_fn
  * handle (a device pointer to a b2pt_lut descriptor) goes into the BRDFsData fields of HIPRTRenderData. */
 int b2pt_lut_create(b2pt_ctx* ctx, const float* texels, int width, int height, int depth, int channels, void** out_handle);
 int b2pt_lut_destroy(b2pt_ctx* ctx, void* handle);
+/* Material textures. Replaces the scene's OrochiTexture objects and the array of texture objects RenderBuffers::material_textures
+ * points to (src/HIPRT-Orochi/OrochiTexture.h, src/Renderer/GPURenderer.cpp:905-939). texels[i]: 8-bit, widths[i] x heights[i] x
+ * channels[i] (1..4), row 0 first, as Image8Bit::read_image returns them. *out_array goes into RenderBuffers::material_textures;
+ * material texture indices index it. Sampling is the reference CPU path's (nearest texel, repeat addressing, Image.cpp:161-195). */
+int b2pt_textures_create(b2pt_ctx* ctx, const uint8_t* const* texels, const int* widths, const int* heights, const int* channels, int count, void** out_array);
+int b2pt_textures_destroy(b2pt_ctx* ctx, void* array);
 
 /* Geometry / BVH. Replaces HIPRTGeometry::upload_triangle_indices / upload_vertices_positions / build_bvh
  * (src/HIPRT-Orochi/HIPRTScene.h:37-72,87-150). The BVH is built on the HOST (binned SAH -> compressed 8-wide) and

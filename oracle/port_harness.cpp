@@ -292,7 +292,15 @@ int main(int argc, char** argv)
     rd.buffers.material_opaque = scene.material_opaque.data();
     rd.buffers.emissive_triangles_count = (int)scene.emissive_triangles.size();
     rd.buffers.emissive_triangles_primitive_indices = scene.emissive_triangles.data();
-    rd.buffers.emissive_triangles_primitive_indices_and_emissive_textures = scene.emissive_triangles.data();
+    rd.buffers.emissive_triangles_primitive_indices_and_emissive_textures = scene.emissive_triangles_and_textures.data();
+    /* material textures: host-side descriptors of the product's device format (b2_material.h), sRGB table from the same powf */
+    std::vector<b2pt_texture> texture_descriptors;
+    std::vector<float> srgb_to_linear(256);
+    for (int v = 0; v < 256; v++)
+        srgb_to_linear[v] = powf((float)v / 255.0f, 2.2f);
+    for (const B2SceneTexture& t : scene.blob.textures)
+        texture_descriptors.push_back(b2pt_texture{ t.texels.data(), (int)t.width, (int)t.height, (int)t.channels, srgb_to_linear.data() });
+    rd.buffers.material_textures = texture_descriptors.empty() ? nullptr : texture_descriptors.data();
     rd.buffers.emissives_power_alias_table.alias_table_alias = scene.power_alias_alias.data();
     rd.buffers.emissives_power_alias_table.alias_table_probas = scene.power_alias_probas.data();
     rd.buffers.emissives_power_alias_table.sum_elements = scene.power_sum;

@@ -22,6 +22,12 @@ REF_DIR = ROOT / "oracle" / "_ref"
 PORT_EXE = ROOT / "oracle" / "_port" / "port_render"
 
 
+# Fixtures on which the REFERENCE reads uninitialised memory often enough to matter: principled_bsdf_sample does not write
+# incident_light_info when it picks the sheen lobe (Principled.h:1875-1884), so a ReSTIR DI BSDF candidate's flags are stack garbage
+# (DESIGN.md section 3). The textured Cornell box has a sheen TEXTURE on a large wall: 17 of 5184 pixels follow the garbage.
+UNINITIALISED_READ_PIXELS = {"c4_texenv_96x54_fused": 20}
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 

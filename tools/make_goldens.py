@@ -37,11 +37,21 @@ CASES = [
     # mask) and the spatial neighbour sampling restricted to the allowed directions
     ("c4_syn_96x54_directional_fused", "c4", "synthetic_20k", 96, 54, 3, 4, ["--directional-reuse"]),
     ("c4_syn_96x54_directional_split", "c4", "synthetic_20k", 96, 54, 2, 4, ["--directional-reuse", "--no-fused"]),
+    # textured Cornell box (tools/make_textured_scene.py): sRGB base colour, normal map, packed roughness/metallic, single-channel
+    # parameter maps, emission texture + constant-emission marker. Rendered by oracle/_ref/ref_extras_* (the harness binds the blob's
+    # textures as the reference's Image8Bit scene textures only under -DB2_REF_EXTRAS, so that ref_render_* stays what made the other
+    # fixtures). ReSTIR DI needs the envmap here: without one the reference dereferences a null envmap through its uninitialised
+    # sampled_lobe_info on sheen-lobe samples and segfaults.
+    ("c2_tex_96x54", "c2", "cornell_textured_16x9", 96, 54, 2, 4, []),
+    ("c3_tex_96x54", "c3", "cornell_textured_16x9", 96, 54, 2, 4, []),
+    ("c4_texenv_96x54_fused", "c4", "cornell_textured_16x9", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
 ]
+EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
 
 
 def run_case(name, variant, scene, w, h, spp, bounces, extra):
-    exe = ROOT / "oracle" / "_ref" / f"ref_render_{variant}"
+    binary = "extras" if scene in EXTRAS_SCENES else "render"
+    exe = ROOT / "oracle" / "_ref" / f"ref_{binary}_{variant}"
     if not exe.exists():
         print(f"skip {name}: {exe} not built")
         return
@@ -61,7 +71,7 @@ def run_case(name, variant, scene, w, h, spp, bounces, extra):
             gbuffer_material=mat, framebuffer=load("framebuffer", np.float32),
             packed_materials=load("packed_materials", np.uint32), triangle_areas=load("triangle_areas", np.float32),
             emissive_prims=load("emissive_prims", np.int32), power_alias=load("power_alias", np.int32), power_probas=load("power_probas", np.float32),
-            meta=np.frombuffer(json.dumps(dict(meta, name=name, scene=scene, extra=extra)).encode(), np.uint8))
+            meta=np.frombuffer(json.dumps(dict(meta, name=name, scene=scene, extra=extra, oracle_binary=binary)).encode(), np.uint8))
         np.savez_compressed(GOLD / f"{name}.npz", **arrays)
         print(f"wrote {name}.npz ({(GOLD / (name + '.npz')).stat().st_size} bytes)")
 
