@@ -455,6 +455,13 @@ def main():
     r.render(spp)
     c = ctx.counters_read()
     r.set_counters(False)
+    # per-kernel times of the wavefront sequences (scenes beyond L2): CUDA events between the kernels of one more render
+    r.reset()
+    r.set_host_seed(42)
+    ctx.wavefront_profile(True)
+    r.render(spp)
+    wf = ctx.wavefront_profile_read()
+    ctx.wavefront_profile(False)
     # whole-job ray / node / triangle counts: every rank counted its own pixels
     c_all = torch.tensor([c["rays"], c["nodes"], c["triangles"]], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -482,10 +489,29 @@ def main():
                         peak_source=which, algorithmic_bytes_per_launch=algo_bytes, launch_ms=mk_ms,
                         note=("10M-triangle scene: 0.72 GB of nodes + triangles, random-sector HBM/L2 gathers (dependent node fetches) bind" if w["scene"].startswith("synthetic:")
                               else "Cornell (BVH+triangles < 1 MB) is L2-resident: issue rate, not HBM, binds; see DESIGN.md"))
+        if wf["trace"]["groups"] > 0:
+            # Wavefront form: the MegaKernel pass is ~80 kernels; the dominant one is named from the live per-kernel times. wf_trace
+            # (all rays of a bounce from one HBM queue) is the HBM-bound one: algorithmic bytes = node + triangle fetches of the
+            # MegaKernel's rays + 64 B ray in / 64 B hit out + 4 B queue entry per ray.
+            kernels_ms = {k: v["ms"] / spp for k, v in wf.items() if v["groups"]}
+            trace_bytes = trav_bytes + mk_rays * (64 + 64 + 4)
+            trace_ms = wf["trace"]["ms"] / spp            # all wf_trace launches of one MegaKernel pass (one sample)
+            trace_launches = wf["trace"]["groups"] / spp
+            achieved = trace_bytes / (trace_ms * 1e-3) / 1e9
+            dominant = max(("trace", "stage1", "stage2"), key=lambda k: wf[k]["ms"])
+            roofline = dict(bound="hbm", kernel="wf_trace", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, peak_source=which,
+                            algorithmic_bytes_per_launch=trace_bytes / trace_launches, launch_ms=trace_ms / trace_launches, launches_per_sample=trace_launches,
+                            dominant_kernel_by_time={"trace": "wf_trace", "stage1": "wf_stage1", "stage2": "wf_stage2"}[dominant],
+                            kernels_ms_per_sample=kernels_ms,
+                            megakernel_pass=dict(achieved=algo_bytes / (mk_ms * 1e-3) / 1e9, algorithmic_bytes=algo_bytes, ms=mk_ms),
+                            note="wavefront form (scene beyond L2): per-kernel CUDA-event times measured live; wf_trace = dependent 80-B node fetches over a 0.72 GB BVH "
+                                 "(random 32-B sectors); the shading stages park ~1 KB of path state per path in HBM between rays (not algorithmic bytes)")
         # dram__bytes_read.sum + dram__bytes_write.sum of one MegaKernel launch from the committed `ncu --set full` capture
         traffic_file = ROOT / "profiles" / "ncu_traffic.json"
         if traffic_file.exists():
             key = {"c5": "c4s"}.get(name, name) + ("" if precise else "_fast")
+            if roofline["kernel"] == "wf_trace":
+                key += "_wf_trace"
             roofline["traffic"] = json.loads(traffic_file.read_text()).get(key, {}).get("dram_bytes_per_launch")
         total_pass_ms = sum(pass_ms.values())
         extra = dict(pass_ms_per_step=pass_ms, mrays_per_s=rays_all / (total_pass_ms * 1e-3) / 1e6 if total_pass_ms else None,

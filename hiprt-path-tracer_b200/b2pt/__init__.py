@@ -144,6 +144,20 @@ class Context:
         check(lib().b2pt_cuda_launch_count(self.handle, C.byref(n)))
         return n.value
 
+    WF_KINDS = ("trace", "stage1", "stage2", "sort", "begin", "advance", "pass_a", "pass_b", "pass_c", "trace_pass")  # B2PT_WF_KIND_NAMES
+
+    def wavefront_profile(self, enabled):
+        """Per-kernel CUDA-event timing of the wavefront launch sequences on / off (resets the totals)."""
+        check(lib().b2pt_wavefront_profile(self.handle, int(enabled)))
+
+    def wavefront_profile_read(self):
+        """{kind: dict(ms=..., groups=...)} accumulated since wavefront_profile(True)."""
+        n = len(self.WF_KINDS)
+        ms = (C.c_double * n)()
+        groups = (C.c_uint64 * n)()
+        check(lib().b2pt_wavefront_profile_read(self.handle, ms, groups, n))
+        return {k: dict(ms=ms[i], groups=int(groups[i])) for i, k in enumerate(self.WF_KINDS)}
+
     def faults(self, reset=True):
         f = Faults()
         check(lib().b2pt_faults_read(self.handle, C.byref(f), int(reset)))

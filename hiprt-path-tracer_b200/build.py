@@ -99,7 +99,7 @@ def compile_unit(unit, feats, log_dir):
 def build(force=False, jobs=None, verbose=True):
     OBJ.mkdir(exist_ok=True)
     digest = source_digest()
-    stamp = OBJ / "digest.txt"
+    stamp = OUT.with_suffix(".so.digest")  # next to the library: build/ (objects, logs) does not travel to the GPU box (.gpurunignore)
     if not force and OUT.exists() and stamp.exists() and stamp.read_text() == digest:
         if verbose:
             print(f"{OUT} is up to date")

@@ -80,6 +80,58 @@ static std::vector<B2KernelUnit>& kernel_units()
     static std::vector<B2KernelUnit> units;
     return units;
 }
+/* ---- per-kernel timing of the wavefront sequences (b2_kernel_table.h) ---- */
+namespace
+{
+struct WfProfiler
+{
+    std::mutex mutex;
+    bool enabled = false;
+    std::vector<cudaEvent_t> events; /* pool, grown on demand, reused after every read */
+    std::vector<int> kinds;          /* kinds[i] = what was launched after events[i] (B2_WF_K_END closes a sequence) */
+    double ms[B2_WF_K_COUNT] = {};
+    unsigned long long marks[B2_WF_K_COUNT] = {};
+};
+WfProfiler& wf_profiler()
+{
+    static WfProfiler p;
+    return p;
+}
+/* folds the recorded marks into the totals; the caller has synchronised the device */
+void wf_profiler_fold(WfProfiler& p)
+{
+    for (size_t i = 0; i + 1 < p.kinds.size(); i++)
+    {
+        if (p.kinds[i] == B2_WF_K_END)
+            continue;
+        float elapsed = 0.0f;
+        if (cudaEventElapsedTime(&elapsed, p.events[i], p.events[i + 1]) == cudaSuccess)
+        {
+            p.ms[p.kinds[i]] += elapsed;
+            p.marks[p.kinds[i]] += 1;
+        }
+    }
+    p.kinds.clear();
+}
+} // namespace
+
+bool b2_wfprof_enabled() { return wf_profiler().enabled; }
+
+void b2_wfprof_mark(cudaStream_t stream, int kind)
+{
+    WfProfiler& p = wf_profiler();
+    std::lock_guard<std::mutex> lock(p.mutex);
+    if (p.kinds.size() >= p.events.size())
+    {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess)
+            return;
+        p.events.push_back(e);
+    }
+    if (cudaEventRecord(p.events[p.kinds.size()], stream) == cudaSuccess)
+        p.kinds.push_back(kind);
+}
+
 void b2_register_kernel_unit(const B2KernelUnit* unit) { kernel_units().push_back(*unit); }
 
 struct b2pt_kernel
@@ -770,6 +822,38 @@ int b2pt_counters_read(b2pt_ctx* ctx, b2pt_counters_t* out)
         out->rays += a[0];
         out->nodes += a[1];
         out->triangles += a[2];
+    }
+    return B2PT_OK;
+}
+
+int b2pt_wavefront_profile(b2pt_ctx* ctx, int enabled)
+{
+    B2_SELECT_DEVICE(ctx);
+    WfProfiler& p = wf_profiler();
+    B2_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(p.mutex);
+    p.enabled = enabled != 0;
+    p.kinds.clear();
+    for (int k = 0; k < B2_WF_K_COUNT; k++)
+    {
+        p.ms[k] = 0.0;
+        p.marks[k] = 0;
+    }
+    return B2PT_OK;
+}
+
+int b2pt_wavefront_profile_read(b2pt_ctx* ctx, double* out_ms, uint64_t* out_launch_groups, int kinds)
+{
+    B2_SELECT_DEVICE(ctx);
+    if (!out_ms || !out_launch_groups || kinds < 0) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    WfProfiler& p = wf_profiler();
+    B2_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(p.mutex);
+    wf_profiler_fold(p);
+    for (int k = 0; k < kinds; k++)
+    {
+        out_ms[k] = k < B2_WF_K_COUNT ? p.ms[k] : 0.0;
+        out_launch_groups[k] = k < B2_WF_K_COUNT ? p.marks[k] : 0;
     }
     return B2PT_OK;
 }

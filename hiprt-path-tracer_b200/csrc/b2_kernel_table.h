@@ -51,4 +51,11 @@ struct B2KernelUnit
 };
 void b2_register_kernel_unit(const B2KernelUnit* unit);
 
+/* Per-kernel timing of the wavefront launch sequences (b2_wavefront.h), off by default. When b2pt_wavefront_profile is on, every
+ * kernel of a sequence is preceded by a CUDA event on the launching stream tagged with the kernel's kind; the time between two
+ * consecutive events is attributed to the first one's kind (b2_capi.cu). */
+enum B2WfKind { B2_WF_K_TRACE = 0, B2_WF_K_STAGE1, B2_WF_K_STAGE2, B2_WF_K_SORT, B2_WF_K_BEGIN, B2_WF_K_ADVANCE, B2_WF_K_PASS_A, B2_WF_K_PASS_B, B2_WF_K_PASS_C, B2_WF_K_TRACE_PASS, B2_WF_K_END, B2_WF_K_COUNT = B2_WF_K_END };
+bool b2_wfprof_enabled();
+void b2_wfprof_mark(cudaStream_t stream, int kind);
+
 #endif

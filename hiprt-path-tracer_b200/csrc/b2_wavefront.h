@@ -109,6 +109,76 @@ __device__ __forceinline__ void wf_result(const WfBuffers& b, int path, int k, b
     }
 }
 
+
+/* ---- a warp moves the records of its 32 paths between HBM and the threads' private copies in full 128-byte lines -------------
+ * A thread copying its own ~0.6 KB record touches one 32-byte sector per lane and instruction (ncu on the 10M-triangle scene,
+ * profiles/r02_ncu_wavefront.md: 134 load + 161 store sectors per path and stage, `lg_throttle` the second stall reason, 24 GB
+ * through L2 in a 5.8 ms launch). Here 8 lanes fetch 128 contiguous bytes of ONE record, the warp 4 records per instruction, and
+ * the 16-byte pieces change hands through a padded shared-memory tile (32 records x 128 B per warp). */
+#define B2_WF_COPY_TILE_UINT4 (32 * 9) /* per warp: 32 records x (8 + 1 pad) uint4 */
+#define B2_WF_COPY_SMEM_BYTES ((B2_WF_STAGE_THREADS / 32) * B2_WF_COPY_TILE_UINT4 * 16)
+
+template <int BYTES>
+__device__ __forceinline__ void wf_records_load(uint4* __restrict__ mine, const unsigned char* __restrict__ records, int path, bool active, uint4* __restrict__ tile)
+{
+    static_assert(BYTES % 16 == 0, "records are whole uint4s");
+    constexpr int PIECES = BYTES / 16;
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int actives = __ballot_sync(0xFFFFFFFFu, active);
+#pragma unroll
+    for (int chunk = 0; chunk * 8 < PIECES; chunk++)
+    {
+#pragma unroll
+        for (int it = 0; it < 8; it++)
+        {
+            const int owner = it * 4 + (int)(lane >> 3), part = chunk * 8 + (int)(lane & 7u);
+            const int owner_path = __shfl_sync(0xFFFFFFFFu, path, owner);
+            if (((actives >> owner) & 1u) && part < PIECES)
+                tile[owner * 9 + (lane & 7u)] = __ldcs(reinterpret_cast<const uint4*>(records + (size_t)owner_path * BYTES) + part);
+        }
+        __syncwarp();
+        if (active)
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (chunk * 8 + j < PIECES)
+                    mine[chunk * 8 + j] = tile[lane * 9 + j];
+        }
+        __syncwarp();
+    }
+}
+
+template <int BYTES>
+__device__ __forceinline__ void wf_records_store(const uint4* __restrict__ mine, unsigned char* __restrict__ records, int path, bool write, uint4* __restrict__ tile)
+{
+    constexpr int PIECES = BYTES / 16;
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int writers = __ballot_sync(0xFFFFFFFFu, write);
+    if (writers == 0u)
+        return;
+#pragma unroll
+    for (int chunk = 0; chunk * 8 < PIECES; chunk++)
+    {
+        if (write)
+        {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (chunk * 8 + j < PIECES)
+                    tile[lane * 9 + j] = mine[chunk * 8 + j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; it++)
+        {
+            const int owner = it * 4 + (int)(lane >> 3), part = chunk * 8 + (int)(lane & 7u);
+            const int owner_path = __shfl_sync(0xFFFFFFFFu, path, owner);
+            if (((writers >> owner) & 1u) && part < PIECES)
+                __stcs(reinterpret_cast<uint4*>(records + (size_t)owner_path * BYTES) + part, tile[owner * 9 + (lane & 7u)]);
+        }
+        __syncwarp();
+    }
+}
+
 /* Megakernel.h:33-79 for every owned pixel: primary-miss pixels are finished here, hit pixels become live paths */
 template <class V>
 __global__ void __launch_bounds__(B2_WF_STAGE_THREADS) wf_begin(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b)
@@ -338,10 +408,11 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE1_MIN_BLOCKS) 
     const int path = active ? b.list[list_in][i] : 0;
     bool alive = false;
     unsigned int have_b = 0u;
+    uint4* tile = reinterpret_cast<uint4*>(wf_smem + (size_t)geom.stack_entries * B2_WF_STAGE_THREADS * 8) + (threadIdx.x >> 5) * B2_WF_COPY_TILE_UINT4;
+    WfPath<V> p;
+    wf_records_load<(int)sizeof(WfPath<V>)>(reinterpret_cast<uint4*>(&p), b.paths, path, active, tile);
     if (active)
     {
-        WfPath<V>* record = reinterpret_cast<WfPath<V>*>(b.paths) + path;
-        WfPath<V> p = *record;
         B2Hit results[B2_WF_RAYS];
 #pragma unroll
         for (int k = 0; k < B2_WF_RAYS; k++)
@@ -367,9 +438,9 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE1_MIN_BLOCKS) 
                 have_b = 1u;
                 p.have = 1u << 8;
             }
-            *record = p;
         }
     }
+    wf_records_store<(int)sizeof(WfPath<V>)>(reinterpret_cast<const uint4*>(&p), b.paths, path, alive, tile);
     if (Nee<V>::HAS_SEQUENTIAL_RAY)
         wf_append(b.ray_list, b.counters + WF_C_RAYS, have_b != 0u, path * B2_WF_RAYS);
     wf_append(b.list[list_out], b.counters + WF_C_MID, alive, path);
@@ -398,10 +469,11 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE2_MIN_BLOCKS) 
 #pragma unroll
     for (int k = 0; k < B2_WF_RAYS; k++)
         request_none(rays[k]);
-    WfPath<V>* record = reinterpret_cast<WfPath<V>*>(b.paths) + path;
+    uint4* tile = reinterpret_cast<uint4*>(wf_smem + (size_t)geom.stack_entries * B2_WF_STAGE_THREADS * 8) + (threadIdx.x >> 5) * B2_WF_COPY_TILE_UINT4;
+    WfPath<V> p;
+    wf_records_load<(int)sizeof(WfPath<V>)>(reinterpret_cast<uint4*>(&p), b.paths, path, active, tile);
     if (active)
     {
-        WfPath<V> p = *record;
         B2Hit sequential_result;
         wf_result(b, path, 0, (p.have >> 8) & 1u, sequential_result);
         alive = megakernel_stage2<V>(ctx, p.s, p.ph, sequential_result, rays[0], rays[1], rays[2], rays[3], rays[4]);
@@ -414,19 +486,14 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE2_MIN_BLOCKS) 
         }
         if (!Nee<V>::HAS_DEFERRED_Y)
             request_none(rays[2]);
-        if (alive)
-        {
-            p.have = 0u; /* the bits are set below, after the deposits */
-            *record = p;
-        }
     }
     unsigned int have = 0u;
 #pragma unroll
     for (int k = 0; k < B2_WF_RAYS; k++)
         if (k < geom.pool_rays)
             have |= wf_deposit(ctx, b, path, k, rays[k], active && alive);
-    if (active && alive)
-        record->have = have;
+    p.have = have;
+    wf_records_store<(int)sizeof(WfPath<V>)>(reinterpret_cast<const uint4*>(&p), b.paths, path, active && alive, tile);
     wf_append(b.list[list_out], b.counters + WF_C_NEXT, alive, path);
     if (V::COUNTERS)
         b2_flush_counters(local_counters);
@@ -728,12 +795,20 @@ cudaError_t launch_wavefront_pass(const b2pt_render_data* rd, const B2LaunchGeom
     const size_t trace_smem = (size_t)g.stack_entries * B2_WF_TRACE_THREADS * 8;
     const B2BvhDevice* bvh = reinterpret_cast<const B2BvhDevice*>(rd->GPU_BVH);
     g_cuda_launches += 6;
+    const bool prof = b2_wfprof_enabled();
+    if (prof) b2_wfprof_mark(stream, B2_WF_K_PASS_A);
     wf_pass_a<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
+    if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE_PASS);
     wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, tb, g.stack_entries);
+    if (prof) b2_wfprof_mark(stream, B2_WF_K_ADVANCE);
     wf_reset_rays<<<1, 1, 0, stream>>>(sc.counters);
+    if (prof) b2_wfprof_mark(stream, B2_WF_K_PASS_B);
     wf_pass_b<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
+    if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE_PASS);
     wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, tb, g.stack_entries);
+    if (prof) b2_wfprof_mark(stream, B2_WF_K_PASS_C);
     wf_pass_c<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
+    if (prof) b2_wfprof_mark(stream, B2_WF_K_END);
     return cudaGetLastError();
 }
 
@@ -775,11 +850,21 @@ cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, 
     const int stage_blocks = (int)((n_paths + B2_WF_STAGE_THREADS - 1) / B2_WF_STAGE_THREADS);
     const int sort_blocks = sms * 4;
     const int trace_blocks = sms * B2_WF_TRACE_MIN_BLOCKS;
-    const size_t stage_smem = (size_t)g.stack_entries * B2_WF_STAGE_THREADS * 8;
+    const size_t begin_smem = (size_t)g.stack_entries * B2_WF_STAGE_THREADS * 8;
+    const size_t stage_smem = begin_smem + B2_WF_COPY_SMEM_BYTES; /* traversal stacks, then the record-copy tiles of the block's warps */
     const size_t trace_smem = (size_t)g.stack_entries * B2_WF_TRACE_THREADS * 8;
     const B2BvhDevice* bvh = reinterpret_cast<const B2BvhDevice*>(rd->GPU_BVH);
+    if (stage_smem > 48 * 1024)
+    {
+        e = cudaFuncSetAttribute(wf_stage1<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wf_stage2<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem);
+        if (e != cudaSuccess)
+            return e;
+    }
 
-    wf_begin<V><<<stage_blocks, B2_WF_STAGE_THREADS, stage_smem, stream>>>(*rd, g, b);
+    const bool prof = b2_wfprof_enabled();
+    if (prof) b2_wfprof_mark(stream, B2_WF_K_BEGIN);
+    wf_begin<V><<<stage_blocks, B2_WF_STAGE_THREADS, begin_smem, stream>>>(*rd, g, b);
     int nb_bounces = rd->render_settings.nb_bounces;
     if (nb_bounces < 0)
         nb_bounces = 0;
@@ -790,17 +875,29 @@ cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, 
     for (int round = 0; round < nb_bounces + 2; round++)
     {
         if (round > 0)
+        {
+            if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE);
             wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, b, g.stack_entries);
+        }
+        if (prof) b2_wfprof_mark(stream, B2_WF_K_SORT);
         wf_sort_count<V><<<sort_blocks, 256, 0, stream>>>(*rd, g, b, cur);
         wf_sort_scan<<<1, B2_WF_SORT_BUCKETS, 0, stream>>>(b);
         wf_sort_scatter<<<sort_blocks, 256, 0, stream>>>(b, cur, 2);
+        if (prof) b2_wfprof_mark(stream, B2_WF_K_STAGE1);
         wf_stage1<V><<<stage_blocks, B2_WF_STAGE_THREADS, stage_smem, stream>>>(*rd, g, b, 2, other); /* survivors -> list[other] */
         if (Nee<V>::HAS_SEQUENTIAL_RAY)
+        {
+            if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE);
             wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, b, g.stack_entries);
+        }
+        if (prof) b2_wfprof_mark(stream, B2_WF_K_ADVANCE);
         wf_advance<<<1, 1, 0, stream>>>(b, 1);
+        if (prof) b2_wfprof_mark(stream, B2_WF_K_STAGE2);
         wf_stage2<V><<<stage_blocks, B2_WF_STAGE_THREADS, stage_smem, stream>>>(*rd, g, b, other, cur); /* survivors -> list[cur] */
+        if (prof) b2_wfprof_mark(stream, B2_WF_K_ADVANCE);
         wf_advance<<<1, 1, 0, stream>>>(b, 2);
     }
+    if (prof) b2_wfprof_mark(stream, B2_WF_K_END);
     return cudaGetLastError();
 }
 

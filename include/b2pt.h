@@ -187,6 +187,13 @@ typedef struct
 int b2pt_faults_read(b2pt_ctx* ctx, b2pt_faults_t* out, int reset);
 /* CUDA kernels launched so far by the passes of this library (a MegaKernel pass in its wavefront form is ~80 kernels) */
 int b2pt_cuda_launch_count(b2pt_ctx* ctx, uint64_t* out_count);
+/* Per-kernel CUDA-event timing of the wavefront launch sequences (MegaKernel and ReSTIR DI passes on scenes beyond L2), for
+ * bench.py's roofline: kinds in the order of B2PT_WF_KIND_NAMES; out_launch_groups[k] = timed intervals of kind k (the three sort
+ * kernels of a round count as one). Off by default (an event record per kernel when on). */
+#define B2PT_WF_KIND_NAMES "trace,stage1,stage2,sort,begin,advance,pass_a,pass_b,pass_c,trace_pass"
+#define B2PT_WF_KIND_COUNT 10
+int b2pt_wavefront_profile(b2pt_ctx* ctx, int enabled);
+int b2pt_wavefront_profile_read(b2pt_ctx* ctx, double* out_ms, uint64_t* out_launch_groups, int kinds);
 int b2pt_counters_reset(b2pt_ctx* ctx);
 int b2pt_counters_read(b2pt_ctx* ctx, b2pt_counters_t* out);
 
