@@ -236,18 +236,22 @@ B2_HD void b2_traverse_begin(B2Traversal& t, bool any_hit, V3 org, V3 dir, float
     t.n_nodes = t.n_tris = 0;
 }
 
-/* One step: at most one node (its 8 quantised child boxes) and the triangles of its hit leaf slots, then a pop if the
- * current group is exhausted. Returns false when the traversal is over (t.best holds the result). */
-B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_stride, unsigned int* faults, int stack_entries = B2_STACK_ENTRIES)
+/* One step = node part, triangle part, pop part, in this order (b2_traverse_step). The three parts are separate functions so that a
+ * kernel can run them as warp-wide phases (wf_trace: lanes that found leaf triangles wait until enough lanes have some).
+ *
+ * Node part: at most one node (its 8 quantised child boxes); the triangles of its hit leaf slots come back in tri_base / tri_bits.
+ * Returns false when the step guard tripped (the traversal is abandoned). */
+B2_HD bool b2_traverse_node(B2Traversal& t, const B2BvhDevice& bvh, int stack_stride, unsigned int* faults, int stack_entries, uint32_t& tri_base, uint32_t& tri_bits)
 {
     const V3 org = t.org, dir = t.dir;
     const uint32_t oct_inv = t.oct_inv;
+    tri_base = 0;
+    tri_bits = 0;
     if (++t.guard > B2_TRAVERSAL_GUARD)
     {
         b2_report_fault(faults, B2_FAULT_TRAVERSAL_GUARD);
         return false;
     }
-    uint32_t tri_base = 0, tri_bits = 0;
 
     if (t.group_bits > 0x00FFFFFFu)
     {
@@ -335,7 +339,13 @@ B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_st
     {
         t.group_bits = 0;
     }
+    return true;
+}
 
+/* Triangle part: the exact tests of the leaf triangles found by the node part. Returns true when an any-hit ray is done. */
+B2_HD bool b2_traverse_triangles(B2Traversal& t, const B2BvhDevice& bvh, uint32_t tri_base, uint32_t tri_bits)
+{
+    const V3 org = t.org, dir = t.dir;
     while (tri_bits != 0)
     {
         const uint32_t k = b2_bfind(tri_bits);
@@ -361,7 +371,7 @@ B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_st
             if (th < t.t_max)
             {
                 t.best.t = th; t.best.u = u; t.best.v = v; t.best.prim = prim; t.best.ng = cross(e1, e2);
-                return false;
+                return true;
             }
         }
         else if (th < t.t_far)
@@ -372,7 +382,12 @@ B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_st
             t.t_far = th;
         }
     }
+    return false;
+}
 
+/* Pop part: when the current group is exhausted, the next one comes off the stack. Returns false when the traversal is over. */
+B2_HD bool b2_traverse_pop(B2Traversal& t, int stack_stride, int stack_entries)
+{
     if (t.group_bits <= 0x00FFFFFFu)
     {
         if (t.sp == 0)
@@ -389,6 +404,17 @@ B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_st
             t.group_bits = 0;
     }
     return true;
+}
+
+/* Returns false when the traversal is over (t.best holds the result). */
+B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_stride, unsigned int* faults, int stack_entries = B2_STACK_ENTRIES)
+{
+    uint32_t tri_base, tri_bits;
+    if (!b2_traverse_node(t, bvh, stack_stride, faults, stack_entries, tri_base, tri_bits))
+        return false;
+    if (b2_traverse_triangles(t, bvh, tri_base, tri_bits))
+        return false;
+    return b2_traverse_pop(t, stack_stride, stack_entries);
 }
 
 B2_HD B2Hit b2_traverse_rt(const bool ANY_HIT, const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int stack_stride,

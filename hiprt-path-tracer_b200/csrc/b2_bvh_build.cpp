@@ -4,7 +4,8 @@
  * Replaces `HIPRTGeometry::build_bvh` (/root/reference/src/HIPRT-Orochi/HIPRTScene.h:87-150), which hands the
  * mesh to HIPRT's GPU LBVH/PLOC/SBVH builders. Per the north star the B200 build does this on the host:
  *   1. binned-SAH binary BVH over triangle boxes (64 bins; leaves of <= 2 triangles, 1 on scenes of a million triangles and more), subtrees built in parallel;
- *   2. collapse to 8-wide nodes by repeatedly opening the child with the largest surface area;
+ *   2. collapse to 8-wide nodes: a child whose whole subtree fits into the free slots is dissolved into them, otherwise the child
+ *      with the largest surface area is opened;
  *   3. octant-ordered slot assignment, 8-bit quantisation of child boxes on a power-of-two grid anchored at the
  *      node's min corner (floor / ceil, i.e. conservative), breadth-first emission so inner children are contiguous.
  * Every input triangle is kept (degenerate ones included: the reference tests them too and they can never be hit).
@@ -49,6 +50,9 @@ constexpr int kBins = 64;
  * B200 (profiles/r01_ncu_megakernel_history.md): 10M triangles 3 / 2 / 1 per leaf = 25.2 / 27.3 / 28.9 Mpaths/s (nodes per
  * ray 24.2 / 24.7 / 25.6, triangles per ray 9.9 / 7.8 / 5.9); Cornell (8k triangles) 342.9 / 344.2 / 328.1. */
 constexpr size_t kSmallLeafTriangleCount = 1u << 20;
+#ifndef B2_COLLAPSE_FILL
+#define B2_COLLAPSE_FILL 0 /* measured on the 10M-triangle scene: 3.03 M -> 2.0 M nodes but the same node visits per ray (the visits are upper-level nodes the ray grazes) and the same wf_trace time; off because a different tree resolves equal-t ties differently (frame checksum moved in the 8th digit) */
+#endif
 
 struct Builder
 {
@@ -221,6 +225,12 @@ bool b2_build_cw8(const int* indices, size_t n_tri, const float* positions, size
     builder.build(root, 0, (int)n_tri, 0);
     const std::vector<Bin2Node>& b2 = builder.nodes;
 
+    /* leaves below every binary node (children are allocated after their parent, so a reverse sweep sees them first) */
+    const int n_bin = builder.next_node.load();
+    std::vector<int> leaf_count((size_t)n_bin);
+    for (int i = n_bin - 1; i >= 0; i--)
+        leaf_count[i] = b2[i].left < 0 ? 1 : leaf_count[b2[i].left] + leaf_count[b2[i].right];
+
     /* ---- collapse to 8-wide + emit ---- */
     struct Pending { int bin_node; uint32_t wide_index; int depth; };
     std::deque<Pending> queue;
@@ -249,14 +259,26 @@ bool b2_build_cw8(const int* indices, size_t n_tri, const float* positions, size
             kids[n_kids++] = top.right;
             while (n_kids < 8)
             {
+                /* First choice: an inner child whose WHOLE subtree fits into the free slots (it disappears as a node: its leaves
+                 * become slots of this one). Opening by area alone leaves the bottom of the tree full of 2- and 3-child nodes
+                 * (10M triangles: 3.03 M nodes = 4.3 children per node); each of them costs a ray a dependent 80-byte fetch and
+                 * the same 8-slot slab test as a full node. Otherwise: the child with the largest surface area. */
                 int pick = -1;
                 float pick_area = -1.0f;
+                bool pick_fits = false;
                 for (int i = 0; i < n_kids; i++)
-                    if (b2[kids[i]].left >= 0 && b2[kids[i]].box.half_area() > pick_area)
+                {
+                    if (b2[kids[i]].left < 0)
+                        continue;
+                    const bool fits = B2_COLLAPSE_FILL && leaf_count[kids[i]] - 1 <= 8 - n_kids;
+                    const float area = b2[kids[i]].box.half_area();
+                    if ((fits && !pick_fits) || (fits == pick_fits && area > pick_area))
                     {
                         pick = i;
-                        pick_area = b2[kids[i]].box.half_area();
+                        pick_area = area;
+                        pick_fits = fits;
                     }
+                }
                 if (pick < 0)
                     break;
                 int opened = kids[pick];

@@ -32,6 +32,9 @@
 #endif
 #define B2_WF_TRACE_THREADS 256
 #define B2_WF_TRACE_MIN_BLOCKS 4
+#ifndef B2_WF_TRI_LANES
+#define B2_WF_TRI_LANES 8 /* lanes of a warp that must hold untested leaf triangles before the warp runs a triangle phase */
+#endif
 #define B2_WF_SORT_BUCKETS 1024 /* material index & 1023; the last bucket also takes paths whose main ray missed */
 
 enum { WF_C_ALIVE = 0, WF_C_MID = 1, WF_C_NEXT = 2, WF_C_RAYS = 3, WF_C_CURSOR = 4, WF_C_COUNT = 8 };
@@ -42,6 +45,15 @@ struct alignas(16) WfPath
     PathState s;
     BouncePhase<V> ph;
     unsigned int have; /* rays of this path in flight: bits 0..4 = slots of trace A, bit 8 = the sequential ray (slot 0) of trace B */
+};
+
+/* the 16-byte pieces of a record that lie wholly inside the unpacked material of its payload */
+template <class V>
+struct WfMaterialPieces
+{
+    static constexpr int BEGIN_BYTE = (int)(offsetof(WfPath<V>, s) + offsetof(PathState, payload) + offsetof(Payload, material));
+    static constexpr int BEGIN = (BEGIN_BYTE + 15) / 16;
+    static constexpr int END = (BEGIN_BYTE + (int)sizeof(Mat)) / 16;
 };
 
 struct WfBuffers
@@ -118,7 +130,9 @@ __device__ __forceinline__ void wf_result(const WfBuffers& b, int path, int k, b
 #define B2_WF_COPY_TILE_UINT4 (32 * 9) /* per warp: 32 records x (8 + 1 pad) uint4 */
 #define B2_WF_COPY_SMEM_BYTES ((B2_WF_STAGE_THREADS / 32) * B2_WF_COPY_TILE_UINT4 * 16)
 
-template <int BYTES>
+/* pieces [SKIP_BEGIN, SKIP_END) of a record are left alone: the unpacked material (224 of 624 bytes) is dead between stage 2 and the
+ * next stage 1, which gathers the material of the new hit */
+template <int BYTES, int SKIP_BEGIN = 0, int SKIP_END = 0>
 __device__ __forceinline__ void wf_records_load(uint4* __restrict__ mine, const unsigned char* __restrict__ records, int path, bool active, uint4* __restrict__ tile)
 {
     static_assert(BYTES % 16 == 0, "records are whole uint4s");
@@ -128,12 +142,14 @@ __device__ __forceinline__ void wf_records_load(uint4* __restrict__ mine, const 
 #pragma unroll
     for (int chunk = 0; chunk * 8 < PIECES; chunk++)
     {
+        if (chunk * 8 >= SKIP_BEGIN && chunk * 8 + 8 <= SKIP_END)
+            continue; /* compile-time: the loop is unrolled */
 #pragma unroll
         for (int it = 0; it < 8; it++)
         {
             const int owner = it * 4 + (int)(lane >> 3), part = chunk * 8 + (int)(lane & 7u);
             const int owner_path = __shfl_sync(0xFFFFFFFFu, path, owner);
-            if (((actives >> owner) & 1u) && part < PIECES)
+            if (((actives >> owner) & 1u) && part < PIECES && !(part >= SKIP_BEGIN && part < SKIP_END))
                 tile[owner * 9 + (lane & 7u)] = __ldcs(reinterpret_cast<const uint4*>(records + (size_t)owner_path * BYTES) + part);
         }
         __syncwarp();
@@ -141,14 +157,14 @@ __device__ __forceinline__ void wf_records_load(uint4* __restrict__ mine, const 
         {
 #pragma unroll
             for (int j = 0; j < 8; j++)
-                if (chunk * 8 + j < PIECES)
+                if (chunk * 8 + j < PIECES && !(chunk * 8 + j >= SKIP_BEGIN && chunk * 8 + j < SKIP_END))
                     mine[chunk * 8 + j] = tile[lane * 9 + j];
         }
         __syncwarp();
     }
 }
 
-template <int BYTES>
+template <int BYTES, int SKIP_BEGIN = 0, int SKIP_END = 0>
 __device__ __forceinline__ void wf_records_store(const uint4* __restrict__ mine, unsigned char* __restrict__ records, int path, bool write, uint4* __restrict__ tile)
 {
     constexpr int PIECES = BYTES / 16;
@@ -159,11 +175,13 @@ __device__ __forceinline__ void wf_records_store(const uint4* __restrict__ mine,
 #pragma unroll
     for (int chunk = 0; chunk * 8 < PIECES; chunk++)
     {
+        if (chunk * 8 >= SKIP_BEGIN && chunk * 8 + 8 <= SKIP_END)
+            continue;
         if (write)
         {
 #pragma unroll
             for (int j = 0; j < 8; j++)
-                if (chunk * 8 + j < PIECES)
+                if (chunk * 8 + j < PIECES && !(chunk * 8 + j >= SKIP_BEGIN && chunk * 8 + j < SKIP_END))
                     tile[lane * 9 + j] = mine[chunk * 8 + j];
         }
         __syncwarp();
@@ -172,7 +190,7 @@ __device__ __forceinline__ void wf_records_store(const uint4* __restrict__ mine,
         {
             const int owner = it * 4 + (int)(lane >> 3), part = chunk * 8 + (int)(lane & 7u);
             const int owner_path = __shfl_sync(0xFFFFFFFFu, path, owner);
-            if (((writers >> owner) & 1u) && part < PIECES)
+            if (((writers >> owner) & 1u) && part < PIECES && !(part >= SKIP_BEGIN && part < SKIP_END))
                 __stcs(reinterpret_cast<uint4*>(records + (size_t)owner_path * BYTES) + part, tile[owner * 9 + (lane & 7u)]);
         }
         __syncwarp();
@@ -340,6 +358,8 @@ __global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) w
     bool busy = false;
     bool drained = false; /* warp-uniform */
     int slot = 0;
+    /* leaf triangles found by the lane's last node step, waiting for the warp's next triangle phase */
+    uint32_t tri_base = 0, tri_bits = 0;
     while (true)
     {
         const unsigned int idle = __ballot_sync(0xFFFFFFFFu, !busy);
@@ -359,6 +379,7 @@ __global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) w
                     const float4 a = b.slot_a[slot], c = b.slot_b[slot];
                     const int packed = __float_as_int(c.w);
                     b2_traverse_begin(t, (packed & 1) != 0, v3(a.x, a.y, a.z), v3(c.x, c.y, c.z), a.w, packed >> 1, stack);
+                    tri_bits = 0;
                     busy = true;
                 }
             }
@@ -370,20 +391,44 @@ __global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) w
                 break;
             continue;
         }
-        if (busy)
+        /* node phase: every lane without pending triangles takes its next node (or pops). The per-ray order node -> triangles ->
+         * pop of b2_traverse_step is kept: a lane with pending triangles just waits, so results and counters do not change. */
+        bool finished = false;
+        if (busy && tri_bits == 0u)
         {
-            if (!b2_traverse_step(t, bvh, B2_WF_TRACE_THREADS, g_faults, stack_entries))
+            if (!b2_traverse_node(t, bvh, B2_WF_TRACE_THREADS, g_faults, stack_entries, tri_base, tri_bits))
+                finished = true;
+            else if (tri_bits == 0u)
+                finished = !b2_traverse_pop(t, B2_WF_TRACE_THREADS, stack_entries);
+        }
+        /* triangle phase: the exact tests run with 2 - 3 lanes when every lane does them right after its node (ncu, profiles/r02_ncu_
+         * wavefront_before.md: 17 of 32 lanes per instruction over the kernel); here they wait until B2_WF_TRI_LANES lanes have
+         * some, or until no lane of the warp can take a node */
+        const unsigned int pending = __ballot_sync(0xFFFFFFFFu, busy && !finished && tri_bits != 0u);
+        if (pending != 0u)
+        {
+            const unsigned int runnable = __ballot_sync(0xFFFFFFFFu, busy && !finished && tri_bits == 0u);
+            if ((int)__popc(pending) >= B2_WF_TRI_LANES || runnable == 0u)
             {
-                b.slot_a[slot] = make_float4(t.best.t, t.best.u, t.best.v, __int_as_float(t.best.prim));
-                b.slot_b[slot] = make_float4(t.best.ng.x, t.best.ng.y, t.best.ng.z, 0.0f);
-                if (COUNTERS)
+                if (busy && !finished && tri_bits != 0u)
                 {
-                    local_counters.rays += 1;
-                    local_counters.nodes += t.n_nodes;
-                    local_counters.tris += t.n_tris;
+                    const bool any_hit_done = b2_traverse_triangles(t, bvh, tri_base, tri_bits);
+                    tri_bits = 0u;
+                    finished = any_hit_done || !b2_traverse_pop(t, B2_WF_TRACE_THREADS, stack_entries);
                 }
-                busy = false;
             }
+        }
+        if (finished)
+        {
+            b.slot_a[slot] = make_float4(t.best.t, t.best.u, t.best.v, __int_as_float(t.best.prim));
+            b.slot_b[slot] = make_float4(t.best.ng.x, t.best.ng.y, t.best.ng.z, 0.0f);
+            if (COUNTERS)
+            {
+                local_counters.rays += 1;
+                local_counters.nodes += t.n_nodes;
+                local_counters.tris += t.n_tris;
+            }
+            busy = false;
         }
     }
     if (COUNTERS)
@@ -392,7 +437,7 @@ __global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) w
 
 /* stage 1 of every live path, in material order: resolve the previous vertex's NEE, take the main hit, begin this vertex's NEE */
 template <class V>
-__global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE1_MIN_BLOCKS) wf_stage1(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b, int list_in, int list_out)
+__global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE1_MIN_BLOCKS) wf_stage1(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, const WfBuffers b, int list_in, int list_out, int first_round)
 {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     b2_block_constants_init(rd);
@@ -410,7 +455,12 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE1_MIN_BLOCKS) 
     unsigned int have_b = 0u;
     uint4* tile = reinterpret_cast<uint4*>(wf_smem + (size_t)geom.stack_entries * B2_WF_STAGE_THREADS * 8) + (threadIdx.x >> 5) * B2_WF_COPY_TILE_UINT4;
     WfPath<V> p;
-    wf_records_load<(int)sizeof(WfPath<V>)>(reinterpret_cast<uint4*>(&p), b.paths, path, active, tile);
+    /* round 0 shades the primary hit with the material wf_begin unpacked from the G-buffer; every later round gathers the material of
+     * the main ray's hit (trace_main_path_ray), so what the record holds there is dead */
+    if (first_round)
+        wf_records_load<(int)sizeof(WfPath<V>)>(reinterpret_cast<uint4*>(&p), b.paths, path, active, tile);
+    else
+        wf_records_load<(int)sizeof(WfPath<V>), WfMaterialPieces<V>::BEGIN, WfMaterialPieces<V>::END>(reinterpret_cast<uint4*>(&p), b.paths, path, active, tile);
     if (active)
     {
         B2Hit results[B2_WF_RAYS];
@@ -493,7 +543,7 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE2_MIN_BLOCKS) 
         if (k < geom.pool_rays)
             have |= wf_deposit(ctx, b, path, k, rays[k], active && alive);
     p.have = have;
-    wf_records_store<(int)sizeof(WfPath<V>)>(reinterpret_cast<const uint4*>(&p), b.paths, path, active && alive, tile);
+    wf_records_store<(int)sizeof(WfPath<V>), WfMaterialPieces<V>::BEGIN, WfMaterialPieces<V>::END>(reinterpret_cast<const uint4*>(&p), b.paths, path, active && alive, tile);
     wf_append(b.list[list_out], b.counters + WF_C_NEXT, alive, path);
     if (V::COUNTERS)
         b2_flush_counters(local_counters);
@@ -884,7 +934,7 @@ cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, 
         wf_sort_scan<<<1, B2_WF_SORT_BUCKETS, 0, stream>>>(b);
         wf_sort_scatter<<<sort_blocks, 256, 0, stream>>>(b, cur, 2);
         if (prof) b2_wfprof_mark(stream, B2_WF_K_STAGE1);
-        wf_stage1<V><<<stage_blocks, B2_WF_STAGE_THREADS, stage_smem, stream>>>(*rd, g, b, 2, other); /* survivors -> list[other] */
+        wf_stage1<V><<<stage_blocks, B2_WF_STAGE_THREADS, stage_smem, stream>>>(*rd, g, b, 2, other, round == 0); /* survivors -> list[other] */
         if (Nee<V>::HAS_SEQUENTIAL_RAY)
         {
             if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE);

@@ -53,7 +53,19 @@ def main():
             after = r.pass_times()
             pass_ms = {k: (after[k]["ms"] - before.get(k, dict(ms=0.0))["ms"]) / a.spp for k in after}
             step_ms = min(ms[1:]) / a.spp
-            out[f"{name}_{flavour}"] = dict(ms_per_sample=step_ms, mpaths=w["width"] * w["height"] / step_ms / 1e3, pass_ms_per_sample=pass_ms,
+            # per-kernel times of the wavefront sequences (libraries older than b2pt_wavefront_profile: skipped)
+            wf_ms = None
+            try:
+                r.set_profile_passes(False)
+                r.reset()
+                r.set_host_seed(42)
+                ctx.wavefront_profile(True)
+                r.render(a.spp)
+                wf_ms = {k: round(v["ms"] / a.spp, 3) for k, v in ctx.wavefront_profile_read().items() if v["groups"]}
+                ctx.wavefront_profile(False)
+            except AttributeError:
+                pass
+            out[f"{name}_{flavour}"] = dict(ms_per_sample=step_ms, mpaths=w["width"] * w["height"] / step_ms / 1e3, pass_ms_per_sample=pass_ms, wavefront_kernel_ms_per_sample=wf_ms,
                                             checksum=float(r.framebuffer().astype("float64").sum()))
             r.close()
     print(json.dumps(out))
