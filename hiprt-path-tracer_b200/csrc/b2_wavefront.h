@@ -443,8 +443,13 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE1_MIN_BLOCKS) 
     b2_block_constants_init(rd);
     B2TraversalCounters local_counters;
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
+    /* The stages trace nothing themselves except in rare cases (a main hit that is a skipped nested-dielectric boundary, RIS with more
+     * than one BSDF candidate): those traversals keep their stack in LOCAL memory, so that the block's shared memory is the copy tile
+     * alone and the L1 -- which these kernels need for their 1.1 - 1.3 KB stack frames -- keeps the rest of the 256 KB */
+    uint64_t local_stack[B2_STACK_ENTRIES];
     Ctx ctx;
-    b2_make_ctx(ctx, rd, reinterpret_cast<uint64_t*>(wf_smem), V::COUNTERS ? &local_counters : nullptr, g_faults, B2_WF_STAGE_THREADS);
+    b2_make_ctx(ctx, rd, local_stack, V::COUNTERS ? &local_counters : nullptr, g_faults, 1);
+    ctx.stack = local_stack;
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int count = b.counters[WF_C_ALIVE];
     if (blockIdx.x * blockDim.x >= count)
@@ -453,7 +458,7 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE1_MIN_BLOCKS) 
     const int path = active ? b.list[list_in][i] : 0;
     bool alive = false;
     unsigned int have_b = 0u;
-    uint4* tile = reinterpret_cast<uint4*>(wf_smem + (size_t)geom.stack_entries * B2_WF_STAGE_THREADS * 8) + (threadIdx.x >> 5) * B2_WF_COPY_TILE_UINT4;
+    uint4* tile = reinterpret_cast<uint4*>(wf_smem) + (threadIdx.x >> 5) * B2_WF_COPY_TILE_UINT4;
     WfPath<V> p;
     /* round 0 shades the primary hit with the material wf_begin unpacked from the G-buffer; every later round gathers the material of
      * the main ray's hit (trace_main_path_ray), so what the record holds there is dead */
@@ -506,8 +511,10 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE2_MIN_BLOCKS) 
     b2_block_constants_init(rd);
     B2TraversalCounters local_counters;
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
+    uint64_t local_stack[B2_STACK_ENTRIES];
     Ctx ctx;
-    b2_make_ctx(ctx, rd, reinterpret_cast<uint64_t*>(wf_smem), V::COUNTERS ? &local_counters : nullptr, g_faults, B2_WF_STAGE_THREADS);
+    b2_make_ctx(ctx, rd, local_stack, V::COUNTERS ? &local_counters : nullptr, g_faults, 1);
+    ctx.stack = local_stack;
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int count = b.counters[WF_C_MID];
     if (blockIdx.x * blockDim.x >= count)
@@ -519,7 +526,7 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE2_MIN_BLOCKS) 
 #pragma unroll
     for (int k = 0; k < B2_WF_RAYS; k++)
         request_none(rays[k]);
-    uint4* tile = reinterpret_cast<uint4*>(wf_smem + (size_t)geom.stack_entries * B2_WF_STAGE_THREADS * 8) + (threadIdx.x >> 5) * B2_WF_COPY_TILE_UINT4;
+    uint4* tile = reinterpret_cast<uint4*>(wf_smem) + (threadIdx.x >> 5) * B2_WF_COPY_TILE_UINT4;
     WfPath<V> p;
     wf_records_load<(int)sizeof(WfPath<V>)>(reinterpret_cast<uint4*>(&p), b.paths, path, active, tile);
     if (active)
@@ -901,7 +908,7 @@ cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, 
     const int sort_blocks = sms * 4;
     const int trace_blocks = sms * B2_WF_TRACE_MIN_BLOCKS;
     const size_t begin_smem = (size_t)g.stack_entries * B2_WF_STAGE_THREADS * 8;
-    const size_t stage_smem = begin_smem + B2_WF_COPY_SMEM_BYTES; /* traversal stacks, then the record-copy tiles of the block's warps */
+    const size_t stage_smem = B2_WF_COPY_SMEM_BYTES; /* the record-copy tiles of the block's warps */
     const size_t trace_smem = (size_t)g.stack_entries * B2_WF_TRACE_THREADS * 8;
     const B2BvhDevice* bvh = reinterpret_cast<const B2BvhDevice*>(rd->GPU_BVH);
     if (stage_smem > 48 * 1024)
