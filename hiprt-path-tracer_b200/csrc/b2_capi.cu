@@ -142,6 +142,7 @@ struct b2pt_kernel
     bool timed = false;
     uint64_t launches = 0;
     int light_presampling = 0; /* ReSTIR_DI_DoLightPresampling the kernel was asked for */
+    int precise = 1;           /* codegen flavour of the unit the entry comes from */
 };
 
 int b2_ctx_device(b2pt_ctx* ctx) { return ctx ? ctx->device : 0; }
@@ -656,6 +657,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
                 k->ctx = ctx;
                 k->entry = &e;
                 k->light_presampling = light_presampling;
+                k->precise = unit.precise;
                 B2_CUDA(cudaEventCreate(&k->start));
                 B2_CUDA(cudaEventCreate(&k->stop));
                 *out_kernel = k;
@@ -670,16 +672,17 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
 }
 
 /* Form of the MegaKernel (all four render bit-identical frames, tests/test_gpu_parity.py):
- *   3 = "wavefront": path state parked in HBM between stages, all rays of a bounce in one queue drained at 32 warps / SM, shading
- *       kernels over paths sorted by material (b2_wavefront.h). The fastest form once the scene no longer fits the L2: on the
- *       10M-triangle workloads 1.7x (RIS) to 2.6x (ReSTIR DI + envmap) the phased form (profiles/r02_results.md).
- *   2 = "phased": persistent 512-thread blocks, bounce cut at its rays, block-pooled traversal; the fastest form on L2-resident
- *       scenes (Cornell: 12.0 ms against 17.9 ms per 1080p sample), where the wavefront's state traffic is not paid back.
+ *   3 = "wavefront": path records parked in HBM between stages and moved by the warp in full lines, all rays of a bounce in one
+ *       queue drained at 32 warps / SM, shading kernels over paths sorted by material (b2_wavefront.h). The fastest form of the
+ *       PRECISE flavour everywhere (10M triangles: 2.3x - 3.1x the phased form; Cornell 1080p: 7.5 ms against 12.2 ms per sample,
+ *       profiles/r02_results.md) and of the fast flavour once the scene no longer fits the L2.
+ *   2 = "phased": persistent 512-thread blocks, bounce cut at its rays, block-pooled traversal; the fastest form of the FAST flavour
+ *       on L2-resident scenes (Cornell: 5.6 ms against 6.0 ms), where its 1.3 KB stack frames cost least.
  *   1 = "persistent" (persistent warps, rays traced in place), 0 = "tiles" (one thread per pixel): kept for A/B runs and tests.
- * Default: wavefront when the BVH has at least B2_WAVEFRONT_MIN_NODES nodes, phased below. B2PT_MEGAKERNEL=wavefront|phased|
- * persistent|tiles forces one; it is read at every launch so a test can switch between them. */
+ * Default: wavefront for the precise flavour and for any BVH of at least B2_WAVEFRONT_MIN_NODES nodes, phased otherwise.
+ * B2PT_MEGAKERNEL=wavefront|phased|persistent|tiles forces one; it is read at every launch so a test can switch between them. */
 #define B2_WAVEFRONT_MIN_NODES 32768u
-static int megakernel_form(uint64_t bvh_nodes)
+static int megakernel_form(uint64_t bvh_nodes, bool precise)
 {
     const char* e = std::getenv("B2PT_MEGAKERNEL");
     if (e && !std::strcmp(e, "tiles"))
@@ -690,7 +693,7 @@ static int megakernel_form(uint64_t bvh_nodes)
         return 2;
     if (e && !std::strcmp(e, "wavefront"))
         return 3;
-    return bvh_nodes >= B2_WAVEFRONT_MIN_NODES ? 3 : 2;
+    return (precise || bvh_nodes >= B2_WAVEFRONT_MIN_NODES) ? 3 : 2;
 }
 
 int b2pt_kernel_launch_rows(b2pt_kernel* kernel, int width, int height, int rank, int world, void** args, b2pt_stream stream)
@@ -759,7 +762,7 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
             bvh_nodes = g_bvh_nodes[rd->GPU_BVH];
         }
     }
-    geom.persistent = megakernel_form(bvh_nodes);
+    geom.persistent = megakernel_form(bvh_nodes, kernel->precise != 0);
     B2_CUDA(cudaEventRecord(kernel->start, s));
     B2_CUDA(kernel->entry->launch(rd, &geom, s));
     B2_CUDA(cudaEventRecord(kernel->stop, s));

@@ -30,8 +30,12 @@
 #ifndef B2_WF_STAGE2_MIN_BLOCKS
 #define B2_WF_STAGE2_MIN_BLOCKS 3
 #endif
+#ifndef B2_WF_TRACE_THREADS
 #define B2_WF_TRACE_THREADS 256
-#define B2_WF_TRACE_MIN_BLOCKS 4
+#endif
+#ifndef B2_WF_TRACE_MIN_BLOCKS
+#define B2_WF_TRACE_MIN_BLOCKS 4 /* 64 registers, 32 warps / SM */
+#endif
 #ifndef B2_WF_TRI_LANES
 #define B2_WF_TRI_LANES 8 /* lanes of a warp that must hold untested leaf triangles before the warp runs a triangle phase */
 #endif

@@ -157,7 +157,7 @@ def test_traversal_selftest_binary(built):
     assert out.returncode == 0 and "SELFTEST OK" in out.stdout, out.stdout[-2000:]
 
 
-# ---- the three forms of the MegaKernel (B2PT_MEGAKERNEL: phased = default, persistent, tiles) ------------------------------
+# ---- the four forms of the MegaKernel (B2PT_MEGAKERNEL: wavefront = default of the precise flavour, phased, persistent, tiles) ----
 @pytest.fixture
 def megakernel_form(monkeypatch):
     def choose(form):
