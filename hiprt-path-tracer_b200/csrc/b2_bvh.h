@@ -189,6 +189,96 @@ __device__ __forceinline__ B2NodeRaw b2_load_node(const B2Node* nodes, uint32_t 
 /* The traversal as explicit state + one step, so that a kernel can interleave the steps of many rays in one converged
  * loop (b2_kernels.cu: a lane that finishes its ray fetches the next one from the block's pool while the other lanes
  * keep stepping). b2_traverse_rt below = begin; while (step); -- the same operations in the same order as before. */
+/* ---- alpha testing inside the traversal (the reference's any-hit filter, src/Device/functions/FilterFunction.h:47-74) --------------
+ * A candidate hit on a material that is not fully opaque is accepted with probability alpha_opacity x base-colour-texture alpha.
+ * The reference draws that random number from the PATH's generator, once per candidate in the order its acceleration structure
+ * meets them -- an order its own two back-ends (CPU octree, HIPRT) do not share, so a path's later draws already differ between
+ * them. Here every RAY owns a small generator seeded from the bits of its origin and direction: which candidates are accepted
+ * is a per-ray matter and the path's own stream is not touched. Scenes that use it are therefore held to the converged-image bar
+ * (tests/test_gpu_converged.py), not to the per-pixel one; scenes without a non-opaque material never enter this code. */
+struct b2pt_texture
+{
+    const uint8_t* texels;
+    int width, height, channels;
+    /* decode of the 256 possible texel values, computed ON THE HOST with the C library's powf (sample_texture_rgba's
+     * `intrin_pow(rgba, 2.2f)`, Texture.h:62-65, is powf in the reference's host build) so that the device needs no pow at all */
+    const float* srgb_to_linear;
+};
+struct B2AlphaTest
+{
+    const int* material_indices;            /* per triangle */
+    const unsigned char* material_opaque;   /* per material: 1 = never filtered */
+    const int* triangle_indices;
+    const float* texcoords;                 /* 2 floats per vertex */
+    const uint32_t* alpha_words;            /* materials_buffer.alpha_thin_film_hue_dielectric_priority: byte 0 = alpha_opacity */
+    const uint32_t* base_color_words;       /* materials_buffer.base_color_roughness_metallic_index: low 16 bits = base colour texture */
+    const b2pt_texture* textures;
+    int enabled;                            /* the kernel was asked for alpha testing and the render settings allow it */
+    int bounce_limit;                       /* rays of a vertex at bounce >= this are not filtered (alpha_testing_indirect_bounce) */
+};
+B2_HD uint32_t b2_alpha_seed(V3 org, V3 dir)
+{
+    uint32_t h = b2_float_as_uint(org.x) * 0x9E3779B1u ^ b2_float_as_uint(org.y) * 0x85EBCA77u ^ b2_float_as_uint(org.z) * 0xC2B2AE3Du;
+    h ^= b2_float_as_uint(dir.x) * 0x27D4EB2Fu ^ b2_float_as_uint(dir.y) * 0x165667B1u ^ b2_float_as_uint(dir.z) * 0xD3A2646Cu;
+    h = (h ^ 61u) ^ (h >> 16); /* wang_hash */
+    h *= 9u;
+    h ^= h >> 4;
+    h *= 0x27D4EB2Du;
+    h ^= h >> 15;
+    return h ? h : 0x9E3779B9u; /* xorshift must not start at 0 */
+}
+/* Which of the reference's trace functions a ray stands for. Its CPU path -- the parity oracle -- does not treat them alike:
+ * trace_main_path_ray goes through the filter alone (Intersect.h:200-257), while evaluate_shadow_ray_occluded and
+ * evaluate_bsdf_light_sample_ray (Intersect.h:295-322, 587-640) re-trace from every accepted hit whose base-colour TEXTURE alpha is
+ * below 1, i.e. for next-event rays a texel with any transparency never blocks. The same CPU path leaves FilterFunctionPayload::bounce
+ * at its default 0 (intersect_scene_cpu, Intersect.h:180-194), so alpha_testing_indirect_bounce only switches the test on or off. */
+enum { B2_ALPHA_RAY_NONE = 0, B2_ALPHA_RAY_MAIN = 1, B2_ALPHA_RAY_NEE = 2 };
+
+/* true = the hit stands (FilterFunction.h returns false for it) */
+B2_HD bool b2_alpha_test_accept(const B2AlphaTest& a, int prim, float u, float v, uint32_t& rng_state, bool nee_ray)
+{
+    const int material_index = a.material_indices[prim];
+    if (a.material_opaque[material_index])
+        return true;
+    float base_color_alpha = 1.0f;
+    const uint32_t texture_index = a.base_color_words[material_index] & 0xFFFFu;
+    if (texture_index != 0xFFFFu && a.textures != nullptr)
+    {
+        /* get_hit_base_color_alpha (Material.h:24-37): uv_interpolate, then the alpha channel of sample_texture_rgba(is_srgb = true)
+         * (Image8Bit::sample_rgba32f, Image.cpp:161-195: nearest texel, repeat, v flipped; the sRGB decode is applied to alpha too) */
+        const int i0 = a.triangle_indices[prim * 3 + 0], i1 = a.triangle_indices[prim * 3 + 1], i2 = a.triangle_indices[prim * 3 + 2];
+        const float w = 1.0f - u - v;
+        const float tu = a.texcoords[2 * i1] * u + a.texcoords[2 * i2] * v + a.texcoords[2 * i0] * w;
+        const float tv = a.texcoords[2 * i1 + 1] * u + a.texcoords[2 * i2 + 1] * v + a.texcoords[2 * i0 + 1] * w;
+        const b2pt_texture& t = a.textures[texture_index];
+        if (t.channels == 4)
+        {
+            float fu = tu, fv = tv;
+            if (fu != 1.0f)
+                fu -= (float)(int)tu;
+            if (fv != 1.0f)
+                fv -= (float)(int)tv;
+            fu = fu < 0.0f ? 1.0f + fu : fu;
+            fv = fv < 0.0f ? 1.0f + fv : fv;
+            fv = 1.0f - fv;
+            const int x = (int)(fu * (float)(t.width - 1)), y = (int)(fv * (float)(t.height - 1));
+            base_color_alpha = t.srgb_to_linear[t.texels[((size_t)x + (size_t)y * (size_t)t.width) * 4 + 3]];
+        }
+    }
+    if (nee_ray && base_color_alpha < 1.0f)
+        return false;
+    const float alpha_opacity = (float)(a.alpha_words[material_index] & 0xFFu) * 0.00392156862745098039f;
+    const float composited_alpha = alpha_opacity * base_color_alpha;
+    uint32_t x = rng_state;
+    x ^= x << 13;
+    x ^= x >> 17;
+    x ^= x << 5;
+    rng_state = x;
+    float draw = (float)x / 4294967296.0f;
+    draw = draw < 1.0f - 1.0e-7f ? draw : 1.0f - 1.0e-7f;
+    return draw < composited_alpha;
+}
+
 struct B2Traversal
 {
     V3 org, dir;
@@ -203,10 +293,14 @@ struct B2Traversal
     uint32_t group_base, group_bits;
     unsigned int guard;
     unsigned int n_nodes, n_tris;
+    uint32_t alpha_rng; /* 0 = this ray's candidate hits are not alpha-tested */
+    bool alpha_nee;     /* B2_ALPHA_RAY_NEE */
 };
 
-B2_HD void b2_traverse_begin(B2Traversal& t, bool any_hit, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack)
+B2_HD void b2_traverse_begin(B2Traversal& t, bool any_hit, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int alpha_ray = B2_ALPHA_RAY_NONE)
 {
+    t.alpha_rng = alpha_ray != B2_ALPHA_RAY_NONE ? b2_alpha_seed(org, dir) : 0u;
+    t.alpha_nee = alpha_ray == B2_ALPHA_RAY_NEE;
     t.org = org;
     t.dir = dir;
     t.any_hit = any_hit;
@@ -356,7 +450,7 @@ B2_HD bool b2_traverse_node(B2Traversal& t, const B2BvhDevice& bvh, int stack_st
 }
 
 /* Triangle part: the exact tests of the leaf triangles found by the node part. Returns true when an any-hit ray is done. */
-B2_HD bool b2_traverse_triangles(B2Traversal& t, const B2BvhDevice& bvh, uint32_t tri_base, uint32_t tri_bits)
+B2_HD bool b2_traverse_triangles(B2Traversal& t, const B2BvhDevice& bvh, uint32_t tri_base, uint32_t tri_bits, const B2AlphaTest* alpha = nullptr)
 {
     const V3 org = t.org, dir = t.dir;
     while (tri_bits != 0)
@@ -379,6 +473,8 @@ B2_HD bool b2_traverse_triangles(B2Traversal& t, const B2BvhDevice& bvh, uint32_
         float th, u, v;
         if (!b2_intersect_triangle(org, dir, a, e1, e2, th, u, v))
             continue;
+        if (alpha != nullptr && t.alpha_rng != 0u && !b2_alpha_test_accept(*alpha, prim, u, v, t.alpha_rng, t.alpha_nee))
+            continue; /* the ray passes through (FilterFunction.h:66-73) */
         if (t.any_hit)
         {
             if (th < t.t_max)
@@ -420,24 +516,24 @@ B2_HD bool b2_traverse_pop(B2Traversal& t, int stack_stride, int stack_entries)
 }
 
 /* Returns false when the traversal is over (t.best holds the result). */
-B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_stride, unsigned int* faults, int stack_entries = B2_STACK_ENTRIES)
+B2_HD bool b2_traverse_step(B2Traversal& t, const B2BvhDevice& bvh, int stack_stride, unsigned int* faults, int stack_entries = B2_STACK_ENTRIES, const B2AlphaTest* alpha = nullptr)
 {
     uint32_t tri_base, tri_bits;
     if (!b2_traverse_node(t, bvh, stack_stride, faults, stack_entries, tri_base, tri_bits))
         return false;
-    if (b2_traverse_triangles(t, bvh, tri_base, tri_bits))
+    if (b2_traverse_triangles(t, bvh, tri_base, tri_bits, alpha))
         return false;
     return b2_traverse_pop(t, stack_stride, stack_entries);
 }
 
 B2_HD B2Hit b2_traverse_rt(const bool ANY_HIT, const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int skip_prim, uint64_t* stack, int stack_stride,
-                           B2TraversalCounters* counters, unsigned int* faults)
+                           B2TraversalCounters* counters, unsigned int* faults, const B2AlphaTest* alpha = nullptr, int alpha_ray = B2_ALPHA_RAY_NONE)
 {
     B2Traversal t;
-    b2_traverse_begin(t, ANY_HIT, org, dir, t_max, skip_prim, stack);
+    b2_traverse_begin(t, ANY_HIT, org, dir, t_max, skip_prim, stack, alpha != nullptr ? alpha_ray : B2_ALPHA_RAY_NONE);
     if (bvh.node_count != 0)
     {
-        while (b2_traverse_step(t, bvh, stack_stride, faults))
+        while (b2_traverse_step(t, bvh, stack_stride, faults, B2_STACK_ENTRIES, alpha))
         {
         }
         if (counters) { counters->rays += 1; counters->nodes += t.n_nodes; counters->tris += t.n_tris; }
@@ -460,14 +556,14 @@ B2_HD B2Hit b2_traverse(const B2BvhDevice& bvh, V3 org, V3 dir, float t_max, int
  * Members are passed by value so the caller's context stays in registers. */
 static __device__ __noinline__ B2Hit b2_traverse_shared(bool any_hit, const B2Node* nodes, const B2Tri* tris, uint32_t node_count, float ox, float oy, float oz, float dx,
                                                         float dy, float dz, float t_max, int skip_prim, uint64_t* stack, int stack_stride,
-                                                        B2TraversalCounters* counters, unsigned int* faults)
+                                                        B2TraversalCounters* counters, unsigned int* faults, const B2AlphaTest* alpha, int alpha_ray)
 {
     B2BvhDevice bvh;
     bvh.nodes = nodes;
     bvh.tris = tris;
     bvh.node_count = node_count;
     bvh.tri_count = 0;
-    return b2_traverse_rt(any_hit, bvh, v3(ox, oy, oz), v3(dx, dy, dz), t_max, skip_prim, stack, stack_stride, counters, faults);
+    return b2_traverse_rt(any_hit, bvh, v3(ox, oy, oz), v3(dx, dy, dz), t_max, skip_prim, stack, stack_stride, counters, faults, alpha, alpha_ray);
 }
 #endif
 

@@ -143,6 +143,7 @@ struct b2pt_kernel
     uint64_t launches = 0;
     int light_presampling = 0; /* ReSTIR_DI_DoLightPresampling the kernel was asked for */
     int precise = 1;           /* codegen flavour of the unit the entry comes from */
+    int alpha_test = 0;        /* B2PT_ALPHA_TEST: candidate hits on non-opaque materials go through the alpha test */
 };
 
 int b2_ctx_device(b2pt_ctx* ctx) { return ctx ? ctx->device : 0; }
@@ -609,7 +610,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
         return B2PT_ERR_NO_VARIANT;
     }
     /* reference defaults */
-    int bsdf = 0, direct = 4, base = 1, later = 3, envmap = 2, precise = 1, counters = 0, light_presampling = 0;
+    int bsdf = 0, direct = 4, base = 1, later = 3, envmap = 2, precise = 1, counters = 0, light_presampling = 0, alpha_test = 0;
     for (int i = 0; i < option_count; i++)
     {
         const char* n = options[i].name;
@@ -622,6 +623,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
         else if (!std::strcmp(n, "EnvmapSamplingStrategy")) envmap = v;
         else if (!std::strcmp(n, "ReSTIR_DI_DoLightPresampling")) light_presampling = v != 0; /* launch-time switch of the same kernels */
         else if (!std::strcmp(n, "B2PT_PRECISE")) precise = v;
+        else if (!std::strcmp(n, "B2PT_ALPHA_TEST")) alpha_test = v != 0; /* launch-time switch of the same kernels */
         else if (!std::strcmp(n, "B2PT_COUNTERS")) counters = v;
         else
         {
@@ -658,6 +660,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
                 k->entry = &e;
                 k->light_presampling = light_presampling;
                 k->precise = unit.precise;
+                k->alpha_test = alpha_test;
                 B2_CUDA(cudaEventCreate(&k->start));
                 B2_CUDA(cudaEventCreate(&k->stop));
                 *out_kernel = k;
@@ -729,6 +732,7 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
     geom.row_map = device_rows;
     geom.row_count = device_rows ? n_rows : 0;
     geom.light_presampling = kernel->light_presampling;
+    geom.alpha_test = kernel->alpha_test;
     geom.presampling_parameters = presampling_pass ? args[0] : nullptr;
     geom.directional_masks_ull = nullptr;
     geom.directional_radius = nullptr;
@@ -763,6 +767,8 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
         }
     }
     geom.persistent = megakernel_form(bvh_nodes, kernel->precise != 0);
+    if (kernel->alpha_test && (geom.persistent == 1 || geom.persistent == 2))
+        geom.persistent = 3; /* the block-pooled forms queue rays without the alpha-test bit: alpha-tested scenes take the wavefront form */
     B2_CUDA(cudaEventRecord(kernel->start, s));
     B2_CUDA(kernel->entry->launch(rd, &geom, s));
     B2_CUDA(cudaEventRecord(kernel->stop, s));

@@ -188,6 +188,7 @@ bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bv
         }
 
     std::vector<SafeMaterial> safe(n_mat);
+    scene.has_alpha_tested_materials = false;
     scene.packed_materials.resize(n_mat);
     scene.material_opaque.resize(n_mat);
     for (size_t i = 0; i < n_mat; i++)
@@ -202,11 +203,7 @@ bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bv
         /* CPURenderer.cpp:312: opaque = fully opaque base colour texture (or none) and alpha_opacity == 1 */
         scene.material_opaque[i] = blob.base_color_opaque(i) && safe[i].f[B2MAT_alpha_opacity] == 1.0f;
         if (!scene.material_opaque[i])
-        {
-            error = "alpha-tested materials are not supported by the B200 path: the reference draws the test's random numbers in the order its CPU octree meets "
-                    "candidate triangles, which another acceleration structure cannot reproduce (alpha_opacity < 1 or a base colour texture with alpha)";
-            return false;
-        }
+            scene.has_alpha_tested_materials = true; /* the kernels are then asked for the alpha test (B2PT_ALPHA_TEST) */
     }
 
     /* AoS -> SoA */

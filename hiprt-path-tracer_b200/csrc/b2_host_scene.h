@@ -69,6 +69,7 @@ struct B2HostScene
     std::vector<B2PackedTexturedMaterial> packed_materials;
     B2MaterialSoAHost materials;
     std::vector<uint8_t> material_opaque;
+    bool has_alpha_tested_materials = false; /* some material_opaque entry is 0 */
     std::vector<float> triangle_areas;
     std::vector<int> emissive_triangles;
     std::vector<int> emissive_triangles_and_textures; /* + triangles whose material has an emission texture (not importance sampled) */

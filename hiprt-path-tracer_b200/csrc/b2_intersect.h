@@ -7,10 +7,10 @@
  *   evaluate_bsdf_light_sample_ray  :544-643   closest hit returning the emission of what was hit
  * plus NestedDielectricsInteriorStack (NestedDielectrics.h:64-255), RayVolumeState (RayVolumeState.h:13-80),
  * RayPayload (RayPayload.h:22-92) and fix_backfacing_normals (Intersect.h:142-176).
- * Textured materials (8-bit textures, sRGB decode, normal maps, emissive textures: Texture.h, Material.h, Intersect.h:77-134) included;
- * alpha-TESTED materials are refused at scene upload: the reference's CPU path draws the alpha test's random numbers in the order its
- * octree meets candidate triangles (BVH.h:153-176 calls the filter for every triangle of every visited leaf), which no other
- * acceleration structure reproduces.
+ * Textured materials (8-bit textures, sRGB decode, normal maps, emissive textures: Texture.h, Material.h, Intersect.h:77-134) included.
+ * Alpha-tested materials: the any-hit filter's test (FilterFunction.h:47-74) runs inside the traversal (b2_bvh.h) with a per-ray
+ * generator -- statistically equivalent to the reference, not bit-exact: the reference draws from the path's generator in the order its
+ * own acceleration structure meets candidate triangles (BVH.h:153-176 calls the filter for every triangle of every visited leaf).
  */
 #ifndef B2_INTERSECT_H
 #define B2_INTERSECT_H
@@ -245,15 +245,78 @@ struct Ctx
     B2TraversalCounters* counters; /* null unless the instrumented variant runs */
     unsigned int* faults;          /* B2_FAULT_COUNT words (device global / host array) or null */
     bool light_presampling;        /* ReSTIR_DI_DoLightPresampling: initial candidates come from the presampled light buffer */
+    bool alpha_test;               /* the kernel was asked for alpha testing (B2PT_ALPHA_TEST: the scene has materials that are not fully opaque) */
+#if defined(B2_ALPHA_TEST_GATED_BY_BOUNCE)
+    mutable int ray_bounce;        /* bounce of the vertex whose rays are being traced in place (FilterFunctionPayload::bounce): set by the pass / bounce code */
+#endif
 };
+#if defined(B2_ALPHA_TEST_GATED_BY_BOUNCE)
+#define B2_SET_RAY_BOUNCE(ctx, bounce) ((ctx).ray_bounce = (bounce))
+#define B2_RAY_BOUNCE(ctx) ((ctx).ray_bounce)
+#else
+#define B2_SET_RAY_BOUNCE(ctx, bounce) ((void)0)
+#define B2_RAY_BOUNCE(ctx) 0
+#endif
+
+/* the B2AlphaTest of a render data (RenderBuffers arrays + the two render settings of FilterFunction.h:47-53) */
+B2_HD B2AlphaTest b2_alpha_test_of(const b2pt_render_data& rd, bool kernel_wants_it)
+{
+    B2AlphaTest a;
+    a.material_indices = rd.buffers.material_indices;
+    a.material_opaque = rd.buffers.material_opaque;
+    a.triangle_indices = rd.buffers.triangles_indices;
+    a.texcoords = reinterpret_cast<const float*>(rd.buffers.texcoords);
+    a.alpha_words = rd.buffers.materials_buffer.alpha_thin_film_hue_dielectric_priority;
+    a.base_color_words = rd.buffers.materials_buffer.base_color_roughness_metallic_index;
+    a.textures = reinterpret_cast<const b2pt_texture*>(rd.buffers.material_textures);
+    a.bounce_limit = rd.render_settings.alpha_testing_indirect_bounce;
+    a.enabled = kernel_wants_it && rd.render_settings.do_alpha_testing && a.bounce_limit > 0 && a.material_opaque != nullptr;
+    return a;
+}
+/* Does a ray of a vertex at `bounce` get its candidate hits alpha-tested? The reference's CPU path (the oracle) never hands the bounce
+ * to its filter -- FilterFunctionPayload::bounce stays 0 (b2_bvh.h) -- so the limit only switches the test on or off; `bounce` is
+ * what its GPU path would compare (kept in the interface, B2_ALPHA_TEST_GATED_BY_BOUNCE selects that behaviour at build time). */
+B2_HD bool b2_alpha_tested_at(const B2AlphaTest& a, int bounce)
+{
+#if defined(B2_ALPHA_TEST_GATED_BY_BOUNCE)
+    return a.enabled && bounce < a.bounce_limit;
+#else
+    (void)bounce;
+    return a.enabled != 0;
+#endif
+}
+
+/* are the queued rays of a vertex at `bounce` alpha-tested? (the wavefront forms decide when they queue a ray) */
+B2_HD bool b2_ctx_alpha_tested_at(const Ctx& ctx, int bounce)
+{
+    if (!ctx.alpha_test)
+        return false;
+    return b2_alpha_tested_at(b2_alpha_test_of(*ctx.rd, true), bounce);
+}
 
 /* HIPRTRenderSettings::do_render_low_resolution, RenderSettings.h */
 /* every ray of the per-pixel code goes through here: on the device one shared out-of-line traversal (b2_bvh.h) */
-B2_HD B2Hit b2_trace(const Ctx& ctx, bool any_hit, V3 origin, V3 direction, float t_max, int skip_prim)
+B2_HD B2Hit b2_trace(const Ctx& ctx, bool any_hit, V3 origin, V3 direction, float t_max, int skip_prim, bool main_path_ray = false)
 {
+    const int alpha_ray = main_path_ray ? B2_ALPHA_RAY_MAIN : B2_ALPHA_RAY_NEE;
+    if (ctx.alpha_test)
+    {
+        /* the rare path (scenes with alpha-tested materials): the filter's inputs are gathered from the render data here, so that the
+         * context every kernel carries stays one flag */
+        const B2AlphaTest alpha = b2_alpha_test_of(*ctx.rd, true);
+        if (b2_alpha_tested_at(alpha, B2_RAY_BOUNCE(ctx)))
+        {
+#if defined(__CUDA_ARCH__) && !defined(B2_INLINE_TRAVERSAL)
+            return b2_traverse_shared(any_hit, ctx.bvh.nodes, ctx.bvh.tris, ctx.bvh.node_count, origin.x, origin.y, origin.z, direction.x, direction.y, direction.z, t_max,
+                                      skip_prim, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults, &alpha, alpha_ray);
+#else
+            return b2_traverse_rt(any_hit, ctx.bvh, origin, direction, t_max, skip_prim, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults, &alpha, alpha_ray);
+#endif
+        }
+    }
 #if defined(__CUDA_ARCH__) && !defined(B2_INLINE_TRAVERSAL)
     return b2_traverse_shared(any_hit, ctx.bvh.nodes, ctx.bvh.tris, ctx.bvh.node_count, origin.x, origin.y, origin.z, direction.x, direction.y, direction.z, t_max,
-                              skip_prim, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults);
+                              skip_prim, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults, nullptr, B2_ALPHA_RAY_NONE);
 #else
     return b2_traverse_rt(any_hit, ctx.bvh, origin, direction, t_max, skip_prim, ctx.stack, ctx.stack_stride, ctx.counters, ctx.faults);
 #endif
@@ -374,7 +437,7 @@ B2_HD bool trace_main_path_ray(const Ctx& ctx, V3 origin, V3 direction, Payload&
         if (first != nullptr && boundary_skips == 1)
             hit = *first;
         else
-            hit = b2_trace(ctx, false, origin, direction, 3.0e38f, last_hit_primitive_index);
+            hit = b2_trace(ctx, false, origin, direction, 3.0e38f, last_hit_primitive_index, /* main_path_ray = */ true);
         if (hit.prim < 0)
             return false;
 

@@ -65,7 +65,8 @@ __device__ __forceinline__ uint32_t b2_global_row(uint32_t local_row, const B2La
     return (band_local * (uint32_t)g.world + (uint32_t)g.rank) * band_rows + local_row % band_rows;
 }
 
-__device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd, uint64_t* stacks, B2TraversalCounters* counters, unsigned int* faults, int threads = B2_BLOCK_THREADS)
+__device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd, uint64_t* stacks, B2TraversalCounters* counters, unsigned int* faults, int threads = B2_BLOCK_THREADS,
+                                            bool alpha_test = false)
 {
     ctx.rd = &rd;
     if (rd.GPU_BVH != nullptr)
@@ -81,6 +82,8 @@ __device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd
     ctx.counters = counters;
     ctx.faults = faults;
     ctx.light_presampling = false;
+    ctx.alpha_test = alpha_test; /* kernels that were asked for alpha testing (B2PT_ALPHA_TEST) */
+    B2_SET_RAY_BOUNCE(ctx, 0);
 }
 
 __device__ __forceinline__ void b2_flush_counters(const B2TraversalCounters& local_counters)
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS, B2_PASS_MIN_BLOCKS) pass_ker
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
 
     Ctx ctx;
-    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults);
+    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
     ctx.light_presampling = geom.light_presampling != 0;
 
     b2_run_pass_pixel<V>(PASS, ctx, x, y);
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(B2_MKP_THREADS, B2_MKP_MIN_BLOCKS) megakernel_
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
 
     Ctx ctx;
-    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_MKP_THREADS);
+    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_MKP_THREADS, geom.alpha_test != 0);
 
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lanes_below = (1u << lane) - 1u;
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
     B2TraversalCounters* counters = V::COUNTERS ? &local_counters : nullptr;
 
     Ctx ctx;
-    b2_make_ctx(ctx, rd, stacks, counters, g_faults, B2_MK_THREADS);
+    b2_make_ctx(ctx, rd, stacks, counters, g_faults, B2_MK_THREADS, geom.alpha_test != 0);
 
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lanes_below = (1u << lane) - 1u;

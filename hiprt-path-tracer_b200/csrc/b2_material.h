@@ -12,6 +12,7 @@
 #define B2_MATERIAL_H
 
 #include "b2_math.h"
+#include "b2_bvh.h"
 #include "b2pt_render_data.h"
 
 #define B2_NO_TEXTURE 65535
@@ -447,14 +448,7 @@ B2_HD Mat load_scene_material(const b2pt_materials_soa& s, int i, bool white_fur
  * What RenderBuffers::material_textures points to on this device layer: an array of these descriptors (the reference's array of
  * oroTextureObject_t on its GPU path, of Image8Bit on its CPU path). 8-bit texels, 1 or 4 channels, row 0 first; the descriptor is
  * what b2pt_texture_create returns. */
-struct b2pt_texture
-{
-    const uint8_t* texels;
-    int width, height, channels;
-    /* 255^2.2-style decode of the 256 possible texel values, computed ON THE HOST with the C library's powf (sample_texture_rgba's
-     * `intrin_pow(rgba, 2.2f)`, Texture.h:62-65, is powf in the reference's host build) so that the device needs no pow at all */
-    const float* srgb_to_linear;
-};
+/* struct b2pt_texture: b2_bvh.h (the traversal samples the base-colour alpha for the alpha test) */
 
 /* Image8Bit::sample_rgba32f (src/Image/Image.cpp:161-195): nearest texel, repeat addressing, v flipped; channels beyond the
  * image's keep ColorRGBA32F's defaults (0, 0, 0, 1). Then sample_texture_rgba's sRGB decode of ALL four channels. */

@@ -44,6 +44,7 @@ struct RayRequest
     float t_max; /* as passed to the traversal: shadow rays carry (distance - 1e-4), closest-hit rays 3e38 */
     int skip_prim;
     int kind;
+    int main_path; /* 1: the path's main ray (trace_main_path_ray); 0: a next-event ray -- the alpha test tells them apart (b2_bvh.h) */
 };
 
 B2_HD void request_none(RayRequest& r) { r.kind = B2_RAY_NONE; }
@@ -55,9 +56,11 @@ B2_HD void request_shadow(RayRequest& r, V3 origin, V3 direction, float distance
     r.t_max = distance - 1.0e-4f;
     r.skip_prim = skip_prim;
     r.kind = B2_RAY_ANY_HIT;
+    r.main_path = 0;
 }
-B2_HD void request_closest(RayRequest& r, V3 origin, V3 direction, int skip_prim)
+B2_HD void request_closest(RayRequest& r, V3 origin, V3 direction, int skip_prim, bool main_path_ray = false)
 {
+    r.main_path = main_path_ray ? 1 : 0;
     /* bsdf_light_sample_ray, b2_intersect.h */
     r.origin = origin;
     r.direction = direction;

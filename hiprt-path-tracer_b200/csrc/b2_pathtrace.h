@@ -567,6 +567,7 @@ B2_HD bool megakernel_bounce(const Ctx& ctx, PathState& s)
         return false;
     if (payload.next_ray_state == B2_RAY_MISSED)
         return false;
+    B2_SET_RAY_BOUNCE(ctx, bounce); /* every ray of this iteration is traced with FilterFunctionPayload::bounce = bounce (Megakernel.h:81-131) */
 
     if (bounce > 0)
         s.intersection_found = trace_main_path_ray<V>(ctx, s.ray_origin, s.ray_direction, payload, hit, hit.primitive_index, s.rng);
@@ -682,6 +683,7 @@ B2_HD bool megakernel_stage1(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, c
 
     const int bounce = payload.bounce;
     ph.nee_on = false;
+    B2_SET_RAY_BOUNCE(ctx, bounce);
     if (bounce > 0)
         s.intersection_found = trace_main_path_ray<V>(ctx, s.ray_origin, s.ray_direction, payload, hit, hit.primitive_index, s.rng, main_hit);
 
@@ -714,6 +716,7 @@ B2_HD bool megakernel_stage2(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, c
     request_none(deferred_y);
     request_none(env_light_ray);
     request_none(env_bsdf_ray);
+    B2_SET_RAY_BOUNCE(ctx, payload.bounce);
     if (ph.nee_on)
     {
         ph.nee.finish_sampling(ctx, payload, hit, -s.ray_direction, s.rng, s.x, s.y, sequential_result, deferred_x, deferred_y);
@@ -731,7 +734,7 @@ B2_HD bool megakernel_stage2(const Ctx& ctx, PathState& s, BouncePhase<V>& ph, c
         valid_indirect_bounce = payload.bounce < s.nb_bounces + 1;
     }
     if (valid_indirect_bounce)
-        request_closest(main_ray, s.ray_origin, s.ray_direction, hit.primitive_index);
+        request_closest(main_ray, s.ray_origin, s.ray_direction, hit.primitive_index, /* main_path_ray = */ true);
     else
         ph.ending = true;
     return valid_indirect_bounce || ph.pending;

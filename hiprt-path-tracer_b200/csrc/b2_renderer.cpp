@@ -68,6 +68,7 @@ struct b2pt_renderer
     int precise = 1;
     int counters = 0;
     bool kernels_stale = true;
+    bool alpha_test = false; /* the current scene has materials that are not fully opaque: kernels are asked for B2PT_ALPHA_TEST */
     bool profile_passes = false;
 
     B2FrameLoop loop;
@@ -211,7 +212,7 @@ int resolve_kernels(b2pt_renderer* r)
         b2pt_option opts[] = {
             { "BSDFOverride", v->bsdf }, { "DirectLightSamplingStrategy", v->direct }, { "DirectLightSamplingBaseStrategy", v->base },
             { "ReSTIR_DI_LaterBouncesSamplingStrategy", v->later }, { "ReSTIR_DI_DoLightPresampling", v->presampling ? 1 : 0 },
-            { "B2PT_PRECISE", r->precise }, { "B2PT_COUNTERS", r->counters },
+            { "B2PT_PRECISE", r->precise }, { "B2PT_COUNTERS", r->counters }, { "B2PT_ALPHA_TEST", r->alpha_test ? 1 : 0 },
         };
         B2_TRY(b2pt_kernel_get(r->ctx, entry, opts, (int)(sizeof(opts) / sizeof(opts[0])), &r->kernels[pass]));
     }
@@ -283,6 +284,11 @@ int upload_scene(b2pt_renderer* r, bool keep_bvh = false)
     {
         b2_set_error("scene rejected: %s", error.c_str());
         return B2PT_ERR_UNSUPPORTED_SCENE;
+    }
+    if (r->alpha_test != s.has_alpha_tested_materials)
+    {
+        r->alpha_test = s.has_alpha_tested_materials;
+        r->kernels_stale = true;
     }
 
     b2pt_render_data& rd = r->loop.rd;

@@ -94,15 +94,23 @@ __device__ __forceinline__ void wf_append(int* list, unsigned int* counter, bool
         list[base + __popc(takers & ((1u << lane) - 1u))] = value;
 }
 
-/* drops the thread's ray k into its slot and the trace list; returns the have-bit */
-__device__ __forceinline__ unsigned int wf_deposit(const Ctx& ctx, const WfBuffers& b, int path, int k, const RayRequest& ray, bool thread_active)
+/* fourth word of a queued ray: (skip primitive << 3) | (B2_ALPHA_RAY_* << 1) | any-hit */
+__device__ __forceinline__ float wf_ray_word(const RayRequest& ray, bool alpha_tested)
+{
+    const int alpha_ray = !alpha_tested ? B2_ALPHA_RAY_NONE : (ray.main_path ? B2_ALPHA_RAY_MAIN : B2_ALPHA_RAY_NEE);
+    return __int_as_float((ray.skip_prim << 3) | (alpha_ray << 1) | (ray.kind == B2_RAY_ANY_HIT ? 1 : 0));
+}
+
+/* drops the thread's ray k into its slot and the trace list; returns the have-bit. `bounce` = bounce of the vertex the ray belongs
+ * to (FilterFunctionPayload::bounce of the reference's trace call) */
+__device__ __forceinline__ unsigned int wf_deposit(const Ctx& ctx, const WfBuffers& b, int path, int k, const RayRequest& ray, bool thread_active, int bounce)
 {
     const bool have = thread_active && ray.kind != B2_RAY_NONE && ctx.bvh.node_count != 0;
     const int slot = path * B2_WF_RAYS + k;
     if (have)
     {
         b.slot_a[slot] = make_float4(ray.origin.x, ray.origin.y, ray.origin.z, ray.t_max);
-        b.slot_b[slot] = make_float4(ray.direction.x, ray.direction.y, ray.direction.z, __int_as_float((ray.skip_prim << 1) | (ray.kind == B2_RAY_ANY_HIT ? 1 : 0)));
+        b.slot_b[slot] = make_float4(ray.direction.x, ray.direction.y, ray.direction.z, wf_ray_word(ray, b2_ctx_alpha_tested_at(ctx, bounce)));
     }
     wf_append(b.ray_list, b.counters + WF_C_RAYS, have, slot);
     return have ? (1u << k) : 0u;
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS) wf_begin(const __grid_con
     extern __shared__ __align__(16) unsigned char wf_smem[];
     b2_block_constants_init(rd);
     Ctx ctx;
-    b2_make_ctx(ctx, rd, reinterpret_cast<uint64_t*>(wf_smem), nullptr, g_faults, B2_WF_STAGE_THREADS);
+    b2_make_ctx(ctx, rd, reinterpret_cast<uint64_t*>(wf_smem), nullptr, g_faults, B2_WF_STAGE_THREADS, geom.alpha_test != 0);
     const int path = blockIdx.x * blockDim.x + threadIdx.x;
     bool alive = false;
     if (path < b.n_paths)
@@ -342,7 +350,8 @@ __global__ void wf_advance(const WfBuffers b, int after_stage)
 /* All rays of the queue, drained by persistent warps: a lane whose ray finished takes the next one while the others keep
  * stepping (the block pool's loop, fed from HBM instead of shared memory). */
 template <bool COUNTERS>
-__global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) wf_trace(const B2BvhDevice* __restrict__ bvh_descriptor, const WfBuffers b, int stack_entries)
+__global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) wf_trace(const B2BvhDevice* __restrict__ bvh_descriptor, const WfBuffers b, int stack_entries,
+                                                                                        const __grid_constant__ B2AlphaTest alpha)
 {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     B2BvhDevice bvh;
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) w
                     slot = b.ray_list[i];
                     const float4 a = b.slot_a[slot], c = b.slot_b[slot];
                     const int packed = __float_as_int(c.w);
-                    b2_traverse_begin(t, (packed & 1) != 0, v3(a.x, a.y, a.z), v3(c.x, c.y, c.z), a.w, packed >> 1, stack);
+                    b2_traverse_begin(t, (packed & 1) != 0, v3(a.x, a.y, a.z), v3(c.x, c.y, c.z), a.w, packed >> 3, stack, (packed >> 1) & 3);
                     tri_bits = 0;
                     busy = true;
                 }
@@ -416,7 +425,7 @@ __global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) w
             {
                 if (busy && !finished && tri_bits != 0u)
                 {
-                    const bool any_hit_done = b2_traverse_triangles(t, bvh, tri_base, tri_bits);
+                    const bool any_hit_done = b2_traverse_triangles(t, bvh, tri_base, tri_bits, alpha.enabled ? &alpha : nullptr);
                     tri_bits = 0u;
                     finished = any_hit_done || !b2_traverse_pop(t, B2_WF_TRACE_THREADS, stack_entries);
                 }
@@ -452,7 +461,7 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE1_MIN_BLOCKS) 
      * alone and the L1 -- which these kernels need for their 1.1 - 1.3 KB stack frames -- keeps the rest of the 256 KB */
     uint64_t local_stack[B2_STACK_ENTRIES];
     Ctx ctx;
-    b2_make_ctx(ctx, rd, local_stack, V::COUNTERS ? &local_counters : nullptr, g_faults, 1);
+    b2_make_ctx(ctx, rd, local_stack, V::COUNTERS ? &local_counters : nullptr, g_faults, 1, geom.alpha_test != 0);
     ctx.stack = local_stack;
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int count = b.counters[WF_C_ALIVE];
@@ -493,7 +502,7 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE1_MIN_BLOCKS) 
                 const int slot = path * B2_WF_RAYS;
                 b.slot_a[slot] = make_float4(sequential.origin.x, sequential.origin.y, sequential.origin.z, sequential.t_max);
                 b.slot_b[slot] = make_float4(sequential.direction.x, sequential.direction.y, sequential.direction.z,
-                                             __int_as_float((sequential.skip_prim << 1) | (sequential.kind == B2_RAY_ANY_HIT ? 1 : 0)));
+                                             wf_ray_word(sequential, b2_ctx_alpha_tested_at(ctx, p.s.payload.bounce)));
                 have_b = 1u;
                 p.have = 1u << 8;
             }
@@ -517,7 +526,7 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE2_MIN_BLOCKS) 
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
     uint64_t local_stack[B2_STACK_ENTRIES];
     Ctx ctx;
-    b2_make_ctx(ctx, rd, local_stack, V::COUNTERS ? &local_counters : nullptr, g_faults, 1);
+    b2_make_ctx(ctx, rd, local_stack, V::COUNTERS ? &local_counters : nullptr, g_faults, 1, geom.alpha_test != 0);
     ctx.stack = local_stack;
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int count = b.counters[WF_C_MID];
@@ -552,7 +561,7 @@ __global__ void __launch_bounds__(B2_WF_STAGE_THREADS, B2_WF_STAGE2_MIN_BLOCKS) 
 #pragma unroll
     for (int k = 0; k < B2_WF_RAYS; k++)
         if (k < geom.pool_rays)
-            have |= wf_deposit(ctx, b, path, k, rays[k], active && alive);
+            have |= wf_deposit(ctx, b, path, k, rays[k], active && alive, k == 0 ? p.s.payload.bounce : p.ph.pending_bounce);
     p.have = have;
     wf_records_store<(int)sizeof(WfPath<V>), WfMaterialPieces<V>::BEGIN, WfMaterialPieces<V>::END>(reinterpret_cast<const uint4*>(&p), b.paths, path, active && alive, tile);
     wf_append(b.list[list_out], b.counters + WF_C_NEXT, alive, path);
@@ -637,7 +646,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_a(const __grid_const
     B2TraversalCounters local_counters;
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
     Ctx ctx;
-    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults);
+    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
     ctx.light_presampling = geom.light_presampling != 0;
     uint32_t x, y;
     const int slot = wf_tile_pixel(geom, tiles_x, rows, x, y);
@@ -661,8 +670,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_a(const __grid_const
         if (take)
         {
             b.slot_a[ray_slot] = make_float4(rays[k].origin.x, rays[k].origin.y, rays[k].origin.z, rays[k].t_max);
-            b.slot_b[ray_slot] = make_float4(rays[k].direction.x, rays[k].direction.y, rays[k].direction.z,
-                                             __int_as_float((rays[k].skip_prim << 1) | (rays[k].kind == B2_RAY_ANY_HIT ? 1 : 0)));
+            b.slot_b[ray_slot] = make_float4(rays[k].direction.x, rays[k].direction.y, rays[k].direction.z, wf_ray_word(rays[k], b2_ctx_alpha_tested_at(ctx, 0)));
             have |= 1u << k;
         }
         wf_append(b.ray_list, b.counters + WF_C_RAYS, take, ray_slot);
@@ -681,7 +689,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_b(const __grid_const
     B2TraversalCounters local_counters;
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
     Ctx ctx;
-    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults);
+    b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
     ctx.light_presampling = geom.light_presampling != 0;
     uint32_t x, y;
     const int slot = wf_tile_pixel(geom, tiles_x, rows, x, y);
@@ -722,8 +730,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_b(const __grid_const
     if (take)
     {
         b.slot_a[ray_slot] = make_float4(final_ray.origin.x, final_ray.origin.y, final_ray.origin.z, final_ray.t_max);
-        b.slot_b[ray_slot] = make_float4(final_ray.direction.x, final_ray.direction.y, final_ray.direction.z,
-                                         __int_as_float((final_ray.skip_prim << 1) | (final_ray.kind == B2_RAY_ANY_HIT ? 1 : 0)));
+        b.slot_b[ray_slot] = make_float4(final_ray.direction.x, final_ray.direction.y, final_ray.direction.z, wf_ray_word(final_ray, b2_ctx_alpha_tested_at(ctx, 0)));
     }
     wf_append(b.ray_list, b.counters + WF_C_RAYS, take, ray_slot);
     if (slot >= 0)
@@ -736,7 +743,7 @@ template <class P, class V>
 __global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_c(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, int tiles_x, int rows, const WfPassBuffers b)
 {
     Ctx ctx;
-    b2_make_ctx(ctx, rd, nullptr, nullptr, g_faults);
+    b2_make_ctx(ctx, rd, nullptr, nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
     uint32_t x, y;
     const int slot = wf_tile_pixel(geom, tiles_x, rows, x, y);
     if (slot < 0)
@@ -855,18 +862,19 @@ cudaError_t launch_wavefront_pass(const b2pt_render_data* rd, const B2LaunchGeom
     const int trace_blocks = sms * B2_WF_TRACE_MIN_BLOCKS;
     const size_t trace_smem = (size_t)g.stack_entries * B2_WF_TRACE_THREADS * 8;
     const B2BvhDevice* bvh = reinterpret_cast<const B2BvhDevice*>(rd->GPU_BVH);
+    const B2AlphaTest alpha = b2_alpha_test_of(*rd, g.alpha_test != 0);
     g_cuda_launches += 6;
     const bool prof = b2_wfprof_enabled();
     if (prof) b2_wfprof_mark(stream, B2_WF_K_PASS_A);
     wf_pass_a<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE_PASS);
-    wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, tb, g.stack_entries);
+    wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, tb, g.stack_entries, alpha);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_ADVANCE);
     wf_reset_rays<<<1, 1, 0, stream>>>(sc.counters);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_PASS_B);
     wf_pass_b<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE_PASS);
-    wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, tb, g.stack_entries);
+    wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, tb, g.stack_entries, alpha);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_PASS_C);
     wf_pass_c<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_END);
@@ -915,6 +923,7 @@ cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, 
     const size_t stage_smem = B2_WF_COPY_SMEM_BYTES; /* the record-copy tiles of the block's warps */
     const size_t trace_smem = (size_t)g.stack_entries * B2_WF_TRACE_THREADS * 8;
     const B2BvhDevice* bvh = reinterpret_cast<const B2BvhDevice*>(rd->GPU_BVH);
+    const B2AlphaTest alpha = b2_alpha_test_of(*rd, g.alpha_test != 0);
     if (stage_smem > 48 * 1024)
     {
         e = cudaFuncSetAttribute(wf_stage1<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem);
@@ -938,7 +947,7 @@ cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, 
         if (round > 0)
         {
             if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE);
-            wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, b, g.stack_entries);
+            wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, b, g.stack_entries, alpha);
         }
         if (prof) b2_wfprof_mark(stream, B2_WF_K_SORT);
         wf_sort_count<V><<<sort_blocks, 256, 0, stream>>>(*rd, g, b, cur);
@@ -949,7 +958,7 @@ cudaError_t launch_wavefront(const b2pt_render_data* rd, const B2LaunchGeom& g, 
         if (Nee<V>::HAS_SEQUENTIAL_RAY)
         {
             if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE);
-            wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, b, g.stack_entries);
+            wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, b, g.stack_entries, alpha);
         }
         if (prof) b2_wfprof_mark(stream, B2_WF_K_ADVANCE);
         wf_advance<<<1, 1, 0, stream>>>(b, 1);

@@ -149,7 +149,12 @@ int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
  * listed take the reference's defaults. Two extra options select the codegen flavour:
  *   {"B2PT_PRECISE", 1}  (default) IEEE fp32 without FMA contraction: the flavour parity is asserted on;
  *   {"B2PT_PRECISE", 0}  FMA contraction + fast intrinsics.
- *   {"B2PT_COUNTERS", 1} traversal-step counters (rays / nodes / triangles) accumulated into b2pt_counters_read. */
+ *   {"B2PT_COUNTERS", 1} traversal-step counters (rays / nodes / triangles) accumulated into b2pt_counters_read.
+ * and {"B2PT_ALPHA_TEST", 1} asks for the any-hit filter's alpha test (src/Device/functions/FilterFunction.h:47-74: a hit on a
+ * material that is not fully opaque is accepted with probability alpha_opacity x base-colour-texture alpha, subject to
+ * render_settings.do_alpha_testing / alpha_testing_indirect_bounce). A host sets it when its scene has such a material
+ * (RenderBuffers::material_opaque holds a 0); scenes without one keep the shorter traversal. The random numbers of the test come
+ * from a per-ray generator, not from the path's (see csrc/b2_bvh.h): images agree with the reference's statistically. */
 typedef struct
 {
     const char* name;

@@ -107,6 +107,8 @@ struct LutStore
 static unsigned int g_port_faults[B2_FAULT_COUNT] = { 0, 0, 0 };
 static unsigned long long g_port_counters[3] = { 0, 0, 0 }; /* rays, nodes, triangles: traversal steps per ray of the CW8 BVH */
 
+static bool g_scene_has_alpha_tested_materials = false; /* = what the renderer passes as B2PT_ALPHA_TEST */
+
 template <class V>
 static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice& bvh, const Args& a)
 {
@@ -123,6 +125,8 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
         ctx.counters = &local;
         ctx.faults = g_port_faults;
         ctx.light_presampling = a.variant == "c4p";
+        ctx.alpha_test = g_scene_has_alpha_tested_materials;
+        B2_SET_RAY_BOUNCE(ctx, 0);
 #pragma omp for schedule(dynamic)
         for (int y = a.win_y0; y < a.win_y1; y++)
             for (int x = a.win_x0; x < a.win_x1; x++)
@@ -252,6 +256,7 @@ int main(int argc, char** argv)
     if (err.empty() && !b2_host_scene_prepare(scene, err) && err.empty())
         err = "scene preparation failed";
     if (!err.empty()) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    g_scene_has_alpha_tested_materials = scene.has_alpha_tested_materials;
 
     LutStore luts;
     if (!luts.load(a.luts.c_str())) { std::fprintf(stderr, "cannot read LUT blob %s\n", a.luts.c_str()); return 1; }

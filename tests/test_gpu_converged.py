@@ -69,3 +69,18 @@ def test_converged_image_agrees_with_the_reference(b2pt, gpu_ctx, tmp_path, vari
     assert m_fast["mean_flip"] <= FLIP_MAX and m_fast["rel_rmse_hdr"] <= REL_RMSE_MAX, m_fast
     # the gate has teeth: an independent render of the same frame is an order of magnitude further away than the fast flavour
     assert m_noise["mean_flip"] > 2 * m_fast["mean_flip"]
+
+
+@pytest.mark.parametrize("variant", ["c2", "c3"])
+def test_alpha_tested_scene_converges_to_the_reference(b2pt, gpu_ctx, tmp_path, variant):
+    """Alpha-tested materials: statistical bar (see tests/test_oracle.py): the CUDA image must be as close to the reference's as two CUDA
+    renders with different seeds are to each other, by the reference's own FLIP."""
+    w, h, spp, bounces = 160, 90, 512, 4
+    ref = run_oracle("extras", variant, "cornell_alpha_16x9", w, h, spp, bounces, tmp_path)["framebuffer"]
+    cuda = render(b2pt, gpu_ctx, variant, "cornell_alpha_16x9", w, h, spp, bounces, True)
+    other = render(b2pt, gpu_ctx, variant, "cornell_alpha_16x9", w, h, spp, bounces, True, seed=7)
+    m_ref = flip(tmp_path, ref, cuda, w, h, spp, "alpha_ref")
+    m_noise = flip(tmp_path, cuda, other, w, h, spp, "alpha_noise")
+    print(json.dumps(dict(variant=variant, against_reference=m_ref, different_seed=m_noise)))
+    assert m_ref["mean_flip"] <= 1.25 * m_noise["mean_flip"] + 0.003, (m_ref, m_noise)
+    assert abs(m_ref["mean_a"] - m_ref["mean_b"]) <= 0.02 * m_ref["mean_a"], m_ref

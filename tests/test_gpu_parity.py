@@ -161,7 +161,10 @@ def test_traversal_selftest_binary(built):
 @pytest.fixture
 def megakernel_form(monkeypatch):
     def choose(form):
-        monkeypatch.setenv("B2PT_MEGAKERNEL", form)
+        if form is None:
+            monkeypatch.delenv("B2PT_MEGAKERNEL", raising=False)  # the library's own choice
+        else:
+            monkeypatch.setenv("B2PT_MEGAKERNEL", form)
     return choose
 
 
@@ -203,3 +206,33 @@ def test_schedule_independence_at_full_size(b2pt, gpu_ctx, megakernel_form, vari
     assert np.array_equal(frames["wavefront"].view(np.uint32), frames["tiles"].view(np.uint32))
     assert np.array_equal(frames["persistent"].view(np.uint32), frames["tiles"].view(np.uint32))
     assert np.isfinite(frames["phased"]).all() and frames["phased"].mean() > 0
+
+
+# ---- alpha-tested materials (FilterFunction.h:47-74) ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant,envmap", [("c2", None), ("c3", None), ("c4", "data/sky_128x64.b2env")])
+def test_alpha_tested_scene_cuda_equals_the_host_port_bit_for_bit(b2pt, gpu_ctx, megakernel_form, tmp_path, variant, envmap):
+    """The alpha test's random numbers come from a per-ray generator seeded by the ray itself (csrc/b2_bvh.h), so they cannot match the
+    reference per pixel (tests/test_oracle.py holds the port to the reference statistically) -- but they do not depend on how rays
+    are scheduled either: the CUDA path in its default (wavefront) form and with one thread per pixel must both reproduce the host
+    build of the same headers bit for bit."""
+    from conftest import ROOT
+    w, h, spp, bounces = 96, 54, 3, 4
+    extra = ("--envmap", envmap) if envmap else ()
+    port = run_oracle("port", variant, "cornell_alpha_16x9", w, h, spp, bounces, tmp_path, extra=extra)
+    for form in (None, "tiles"):
+        megakernel_form(form)
+        r = b2pt.Renderer(gpu_ctx, w, h, variant, precise=True)
+        r.set_scene_file(DATA / "cornell_alpha_16x9.b2scene")
+        r.set_luts_file(DATA / "brdf_luts.b2luts")
+        r.set(nb_bounces=bounces)
+        if variant.startswith("c4"):
+            r.set(restir_di_do_fused_spatiotemporal=1)
+        if envmap:
+            r.set_envmap_file(ROOT / envmap)
+        r.render(1)
+        prim = r.gbuffer()["prim"]
+        r.render(spp - 1)
+        fb = r.framebuffer().copy()
+        r.close()
+        assert np.array_equal(prim, port["prim"]), f"form {form}: primary hits (alpha-tested camera rays) differ from the host port"
+        assert pixels_not_bit_identical(fb, port["framebuffer"]) == 0, f"form {form}: frame differs from the host port"

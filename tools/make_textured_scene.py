@@ -34,7 +34,7 @@ def textures(rng, n=48):
     return [np.clip(t * 255.0, 0, 255).astype(np.uint8) for t in out]
 
 
-def main(src, dst):
+def main(src, dst, alpha=False):
     rng = np.random.default_rng(0xB200)
     s = b2scene.read_scene(src)
     pos = s["positions"]
@@ -55,11 +55,24 @@ def main(src, dst):
     mats[6, M["emission_r"]:M["emission_r"] + 3] = (0.25, 0.2, 0.05)
     idx[7, slot["specular_transmission"]] = 8
     idx[8, slot["base_color"]] = 0
+    tex = textures(rng)
+    if alpha:
+        # alpha-tested variant (data/cornell_alpha_16x9.b2scene): a base colour texture whose alpha channel has holes (a lattice), and two
+        # materials with alpha_opacity < 1 -- every branch of the reference's any-hit filter (FilterFunction.h:47-74)
+        n = 48
+        yy, xx = np.mgrid[0:n, 0:n].astype(np.float32) / n
+        holes = (((np.floor(xx * 8) + np.floor(yy * 8)) % 2) > 0).astype(np.float32)
+        lattice = np.stack([0.8 - 0.5 * xx, 0.35 + 0.5 * yy, 0.3 + 0.4 * holes, 0.15 + 0.85 * holes], -1)
+        tex.append(np.clip(lattice * 255.0, 0, 255).astype(np.uint8))                                    # 10 base colour with alpha holes
+        idx[1, slot["base_color"]] = 10
+        idx[8, slot["base_color"]] = 10
+        mats[2, M["alpha_opacity"]] = 0.5
+        mats[5, M["alpha_opacity"]] = 0.25
     cam = s["camera"]
     camera = b2scene.camera_block(cam["inverse_view"], cam["inverse_projection"], cam["view_projection"], cam["position"], cam["vertical_fov"])
-    b2scene.write_scene(dst, camera, pos, s["normals"], uv, s["indices"], s["material_indices"], s["has_normals"], mats, textures=textures(rng), texture_indices=idx)
+    b2scene.write_scene(dst, camera, pos, s["normals"], uv, s["indices"], s["material_indices"], s["has_normals"], mats, textures=tex, texture_indices=idx)
     print(f"wrote {dst}")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], alpha="--alpha" in sys.argv[3:])
