@@ -194,11 +194,6 @@ bool b2_host_scene_prepare(B2HostScene& scene, std::string& error, bool build_bv
     for (size_t i = 0; i < n_mat; i++)
     {
         safe[i] = make_safe(blob.material(i));
-        if (safe[i].f[B2MAT_dispersion_scale] > 0.0f)
-        {
-            error = "dispersive media are not supported by the B200 path yet (SURVEY section 8: out of the configured scope)";
-            return false;
-        }
         scene.packed_materials[i] = pack_to_gpu(safe[i], blob.texture_indices.empty() ? nullptr : &blob.texture_indices[i * B2TEX_SLOT_COUNT]);
         /* CPURenderer.cpp:312: opaque = fully opaque base colour texture (or none) and alpha_opacity == 1 */
         scene.material_opaque[i] = blob.base_color_opaque(i) && safe[i].f[B2MAT_alpha_opacity] == 1.0f;

@@ -11,6 +11,7 @@
  * Alpha-tested materials: the any-hit filter's test (FilterFunction.h:47-74) runs inside the traversal (b2_bvh.h) with a per-ray
  * generator -- statistically equivalent to the reference, not bit-exact: the reference draws from the path's generator in the order its
  * own acceleration structure meets candidate triangles (BVH.h:153-176 calls the filter for every triangle of every visited leaf).
+ * Spectral dispersion (Intersect.h:259-267, Dispersion.h) included.
  */
 #ifndef B2_INTERSECT_H
 #define B2_INTERSECT_H

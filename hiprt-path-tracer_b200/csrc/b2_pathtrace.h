@@ -275,13 +275,13 @@ B2_HD bool do_russian_roulette(const b2pt_render_settings& s, int bounce, Rgb& r
     return true;
 }
 
-/* PathTracing.h:44-62; dispersive media are refused at scene upload, so get_dispersion_ray_color() == 1 */
+/* PathTracing.h:44-62 */
 B2_HD Rgb update_ray_throughput(const b2pt_render_data& rd, Payload& payload, const HitInfo& hit, Rgb current_throughput, Rgb bsdf_color, V3 bounce_direction, float bsdf_pdf_value, Rng& rng)
 {
     Rgb throughput_attenuation = bsdf_color * fabsf(dot(bounce_direction, hit.shading_normal)) / bsdf_pdf_value;
     if (!do_russian_roulette(rd.render_settings, payload.bounce, current_throughput, throughput_attenuation, rng))
         return rgb(0.0f);
-    current_throughput *= rgb(1.0f);
+    current_throughput *= get_dispersion_ray_color(payload.volume_state.sampled_wavelength, payload.material.dispersion_scale);
     current_throughput *= throughput_attenuation;
     current_throughput = rgb_max(current_throughput, rgb(1.0e-5f, 1.0e-5f, 1.0e-5f));
     payload.next_ray_state = B2_RAY_BOUNCE;

@@ -55,6 +55,9 @@ B2_HD V3 lut_fetch_2d(const void* handle, float u_in, float v_in)
     v = 1.0f - v;
     int x = (int)(u * (float)(lut->width - 1));
     int y = (int)(v * (float)(lut->height - 1));
+    /* a NaN or astronomically large coordinate (the reference then reads out of bounds, and crashes on its CPU path) lands on an edge texel */
+    x = x < 0 ? 0 : (x > lut->width - 1 ? lut->width - 1 : x);
+    y = y < 0 ? 0 : (y > lut->height - 1 ? lut->height - 1 : y);
     const float* t = lut->texels + (size_t)(x + y * lut->width) * lut->channels;
     V3 r = v3(t[0], 0.0f, 0.0f);
     if (lut->channels >= 3)
@@ -78,6 +81,9 @@ B2_HD float lut_fetch_3d(const void* handle, float u_in, float v_in, float w_in)
     int x = (int)(u * (float)(lut->width - 1));
     int y = (int)(v * (float)(lut->height - 1));
     int z = (int)(w * (float)(lut->depth - 1));
+    x = x < 0 ? 0 : (x > lut->width - 1 ? lut->width - 1 : x);
+    y = y < 0 ? 0 : (y > lut->height - 1 ? lut->height - 1 : y);
+    z = z < 0 ? 0 : (z > lut->depth - 1 ? lut->depth - 1 : z);
     return lut->texels[((size_t)z * lut->height * lut->width + (size_t)(x + y * lut->width)) * lut->channels];
 }
 
@@ -867,6 +873,57 @@ B2_HD V3 sheen_ltc_sample(const b2pt_render_data& rd, const Mat& material, V3 lo
 }
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Spectral dispersion of the glass lobe (Dispersion.h:433-522, WavelengthToRGBMethod = WAVELENGTH_TO_RGB_FIT)
+ * ------------------------------------------------------------------------------------------------------------ */
+/* compute_dispersion_ior (Dispersion.h:485-499): the IOR at `wavelength` of a medium whose base IOR is measured at 587.6 nm */
+B2_HD float compute_dispersion_ior(float dispersion_abbe_number, float dispersion_scale, float base_IOR, float wavelength)
+{
+    if (dispersion_scale == 0.0f)
+        return base_IOR;
+    float abbe_number = dispersion_abbe_number / dispersion_scale;
+    float B = (base_IOR - 1.0f) / (abbe_number * 0.00000191038851931481f);
+    float A = base_IOR - B / (334777.96f);
+    return A + B / (wavelength * wavelength);
+}
+
+/* wavelength_to_RGB_fit (Dispersion.h:433-458). The reference writes `exp` in the red and blue terms: unqualified, i.e. the double
+ * function with the rest of the expression carried in double (b2_math.h "wide evaluation"); `expf` / `logf` stay float. */
+B2_HD Rgb wavelength_to_RGB_fit(float wavelength)
+{
+    Rgb RGB;
+    if (wavelength < 463.0f)
+    {
+        RGB.r = (float)((b2w)-1.2776028240727566e-01f / ((b2w)1.0f + b2w_exp((wavelength - 4.2680623367293401e+02f) / 8.2197460736637176e+00f)) +
+                        (b2w)-1.3925673552505122e-11f * b2w_exp((wavelength - 45.0f) / 1.8175459086411596e+01f));
+        RGB.r += 1.2898689750552100e-01f;
+    }
+    else if (wavelength > 553.0f)
+    {
+        RGB.r = (float)((b2w)(1.7963649137825513e+01f * (1.0f / 2.6577826611702449e+01f)) *
+                        b2w_exp(-0.5f * b2_square((wavelength - 6.0625724092824566e+02f) * (1.0f / 2.6577826611702449e+01f))));
+        RGB.r += 2.5574660155104657e-03f;
+    }
+    else
+        RGB.r = 0.0f;
+    RGB.g = 3.4962267376163049e+02f * b2f_exp_rounded(-0.5f * b2_square((wavelength - 5.4209217455705152e+02f) / -2.9598170255834638e+01f));
+    RGB.g /= wavelength;
+    RGB.b = (float)b2w_exp(3.2987659944421112e+03f + (-2.0975839709372405e+05f / wavelength) - 4.6368268395094020e+02f * b2f_log_rounded(wavelength));
+    return RGB * 10.0f;
+}
+
+/* get_dispersion_ray_color (Dispersion.h:512-522): the colour filter of the sampled wavelength, applied once per path (a negative
+ * wavelength = not applied yet; it is made positive here) */
+B2_HD Rgb get_dispersion_ray_color(float& wavelength, float dispersion_scale)
+{
+    if (dispersion_scale == 0.0f)
+        return rgb(1.0f);
+    if (wavelength >= 0.0f)
+        return rgb(1.0f);
+    wavelength *= -1.0f;
+    return wavelength_to_RGB_fit(wavelength);
+}
+
+/* ------------------------------------------------------------------------------------------------------------
  * Lobes (Principled.h:49-881)
  * ------------------------------------------------------------------------------------------------------------ */
 B2_HD float medium_ior(const b2pt_render_data& rd, int material_index)
@@ -995,9 +1052,11 @@ B2_HD GlassSetup principled_glass_setup(const b2pt_render_data& rd, const BsdfCt
         return g;
 
     g.reflecting = NoL * NoV > 0;
-    /* dispersion_scale == 0 for every accepted scene: compute_dispersion_ior returns the base IOR (Dispersion.h:487-488) */
     g.eta_i = medium_ior(rd, ctx.volume_state->incident_mat_index);
     g.eta_t = medium_ior(rd, ctx.volume_state->outgoing_mat_index);
+    /* Principled.h:377-380, 578-581 */
+    g.eta_i = compute_dispersion_ior(m.dispersion_abbe_number, m.dispersion_scale, g.eta_i, fabsf(ctx.volume_state->sampled_wavelength));
+    g.eta_t = compute_dispersion_ior(m.dispersion_abbe_number, m.dispersion_scale, g.eta_t, fabsf(ctx.volume_state->sampled_wavelength));
     g.relative_eta = g.eta_t / g.eta_i;
     if (fabsf(g.relative_eta - 1.0f) < 1.0e-5f)
         g.relative_eta = 1.0f + 1.0e-5f;
@@ -1126,6 +1185,9 @@ B2_HD_NOINLINE V3 principled_glass_sample(const b2pt_render_data& rd, BsdfCtx& c
     VolumeState& vs = *ctx.volume_state;
     float eta_i = medium_ior(rd, vs.incident_mat_index);
     float eta_t = medium_ior(rd, vs.outgoing_mat_index);
+    /* Principled.h:731-734 */
+    eta_i = compute_dispersion_ior(m.dispersion_abbe_number, m.dispersion_scale, eta_i, fabsf(vs.sampled_wavelength));
+    eta_t = compute_dispersion_ior(m.dispersion_abbe_number, m.dispersion_scale, eta_t, fabsf(vs.sampled_wavelength));
     float relative_eta = eta_t / eta_i;
     if (fabsf(relative_eta - 1.0f) < 1.0e-5f)
         relative_eta = 1.0f + 1.0e-5f;

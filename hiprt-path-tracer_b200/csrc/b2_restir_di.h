@@ -1179,6 +1179,7 @@ struct DiStEntry
     float target_function_at_center;            /* as if visible */
     float target_function_canonical_at_neighbor; /* as if visible */
     int kind;
+    float combine_draw; /* the random number of the entry's combine_with, drawn in phase A at the reference's stream position */
 };
 struct DiSpatiotemporalState
 {
@@ -1257,8 +1258,11 @@ B2_HD void restir_di_spatiotemporal_phase_a(const Ctx& ctx, uint32_t x, uint32_t
     Int3 temporal = find_temporal_neighbor_index<V>(rd, load_v3(rd.g_buffer.primary_hit_position, center_pixel_index), center_pixel_surface.shading_normal, (int)center_pixel_index, rng);
     if (!(temporal.x == -1 || rd.render_settings.freeze_random))
         temporal_neighbor_reservoir = di_load(rd, di.temporal_pass.input_reservoirs, temporal.x);
-    /* (the temporal neighbour's surface is only consumed by bias-correction modes other than pairwise MIS; its RNG side effect -- the
-     * wavelength draw for dispersive glass -- cannot occur because dispersive scenes are refused) */
+    /* load_spatiotemporal_neighbor_data rebuilds the temporal neighbour's surface here (:97), which draws a wavelength when that pixel shows
+     * dispersive glass. Pairwise MIS never reads that surface (its weight function rebuilds its own, SpatiotemporalMISWeight.h:183): only
+     * the draw is kept. */
+    if (!(temporal.x == -1 || rd.render_settings.freeze_random) && temporal_neighbor_reservoir.M != 0)
+        (void)get_pixel_surface<V>(rd, temporal.x, prev_gbuffer, rng);
     if ((temporal.x == -1 || temporal_neighbor_reservoir.M <= 1) && di.common_spatial_pass.do_disocclusion_reuse_boost)
         local.reuse_neighbor_count = di.common_spatial_pass.disocclusion_reuse_count;
 
@@ -1281,7 +1285,7 @@ B2_HD void restir_di_spatiotemporal_phase_a(const Ctx& ctx, uint32_t x, uint32_t
     const bool update_mc = initial_candidates_reservoir.M > 0 && initial_candidates_reservoir.UCW > 0.0f;
     st.update_mc = update_mc ? 1 : 0;
 
-    /* the canonical sample seen from a neighbour's surface (pairwise MIS, update_mc), as if visible */
+    /* the canonical sample seen from a neighbour's surface (pairwise MIS, update_mc; SpatiotemporalMISWeight.h:181-191), as if visible */
     auto canonical_at = [&](int neighbor_pixel_index, RayRequest& ray) {
         if (!update_mc)
             return 0.0f;
@@ -1298,6 +1302,8 @@ B2_HD void restir_di_spatiotemporal_phase_a(const Ctx& ctx, uint32_t x, uint32_t
         if (temporal_neighbor_reservoir.UCW > 0.0f)
             e.target_function_at_center = di_target_function_deferred<V>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface, rays[2 * st.entry_count]);
         e.target_function_canonical_at_neighbor = canonical_at(temporal.x, rays[2 * st.entry_count + 1]);
+        /* :281 combine_with draws only for a reservoir with UCW > 0 */
+        e.combine_draw = temporal_neighbor_reservoir.UCW > 0.0f ? rng.next_float() : 0.0f;
         st.entry_count++;
     }
 
@@ -1342,7 +1348,11 @@ B2_HD void restir_di_spatiotemporal_phase_a(const Ctx& ctx, uint32_t x, uint32_t
             else
                 e.target_function_at_center = di_target_function<V, false>(ctx, neighbor_reservoir.sample, center_pixel_surface);
         }
+        /* :397 the neighbour's surface is rebuilt for every entry, the centre pixel's own included (a wavelength draw on dispersive glass;
+         * pairwise MIS does not read it), then the weight function rebuilds it once more for the canonical sample, then :444 combine_with draws */
+        (void)get_pixel_surface<V>(rd, neighbor_pixel_index, prev_gbuffer, rng);
         e.target_function_canonical_at_neighbor = canonical ? 0.0f : canonical_at(neighbor_pixel_index, rays[2 * st.entry_count + 1]);
+        e.combine_draw = neighbor_reservoir.UCW > 0.0f ? rng.next_float() : 0.0f;
         st.entry_count++;
     }
     st.rng = rng;
@@ -1382,7 +1392,7 @@ B2_HD void restir_di_spatiotemporal_phase_b(const Ctx& ctx, uint32_t x, uint32_t
             float w = mis.weight_given(rd, temporal_neighbor_reservoir.M, temporal_neighbor_reservoir.sample.target_function, initial_candidates_reservoir.M,
                                        initial_candidates_reservoir.sample.target_function, target_function_at_center, target_function_canonical_at_neighbor, st.valid_neighbors_count,
                                        st.valid_neighbors_M_sum, update_mc, false, false);
-            if (out.combine_with(temporal_neighbor_reservoir, w, target_function_at_center, 1.0f, rng))
+            if (out.combine_with_drawn(temporal_neighbor_reservoir, w, target_function_at_center, 1.0f, e.combine_draw))
                 out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
         }
         else
@@ -1392,7 +1402,7 @@ B2_HD void restir_di_spatiotemporal_phase_b(const Ctx& ctx, uint32_t x, uint32_t
             float mis_weight = mis.weight_given(rd, neighbor_reservoir.M, neighbor_reservoir.sample.target_function, initial_candidates_reservoir.M,
                                                 initial_candidates_reservoir.sample.target_function, target_function_at_center, target_function_canonical_at_neighbor,
                                                 st.valid_neighbors_count, st.valid_neighbors_M_sum, update_mc, canonical, false);
-            if (out.combine_with(neighbor_reservoir, mis_weight, target_function_at_center, 1.0f, rng))
+            if (out.combine_with_drawn(neighbor_reservoir, mis_weight, target_function_at_center, 1.0f, e.combine_draw))
             {
                 /* ReSTIR_DI_SpatialTargetFunctionVisibility = FALSE: do_include_spatial_visibility_term is false for every neighbour */
                 if (canonical)

@@ -90,6 +90,27 @@ struct DiReservoir
         return false;
     }
 
+    /* combine_with with its random number drawn beforehand (callers draw it exactly when other.UCW > 0, at the stream position of
+     * the reference's draw) */
+    B2_HD bool combine_with_drawn(const DiReservoir& other, float mis_weight, float target_function, float jacobian_determinant, float draw)
+    {
+        if (other.UCW <= 0.0f)
+        {
+            M += other.M;
+            return false;
+        }
+        float reservoir_sample_weight = mis_weight * target_function * other.UCW * jacobian_determinant;
+        M += other.M;
+        weight_sum += reservoir_sample_weight;
+        if (draw < reservoir_sample_weight / weight_sum)
+        {
+            sample = other.sample;
+            sample.target_function = target_function;
+            return true;
+        }
+        return false;
+    }
+
     B2_HD void end()
     {
         if (weight_sum == 0.0f)

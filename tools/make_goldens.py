@@ -45,6 +45,11 @@ CASES = [
     ("c2_tex_96x54", "c2", "cornell_textured_16x9", 96, 54, 2, 4, []),
     ("c3_tex_96x54", "c3", "cornell_textured_16x9", 96, 54, 2, 4, []),
     ("c4_texenv_96x54_fused", "c4", "cornell_textured_16x9", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
+    # spectral dispersion (tools/make_dispersion_scene.py): wavelength sampling, wavelength-dependent IOR in the glass lobe, the
+    # wavelength's colour filter on the throughput; in the fused ReSTIR DI pass also the wavelength draws of every surface rebuild
+    ("c2_disp_96x54", "c2", "cornell_dispersion_16x9", 96, 54, 3, 6, []),
+    ("c3_disp_96x54", "c3", "cornell_dispersion_16x9", 96, 54, 3, 6, []),
+    ("c4_disp_96x54_fused", "c4", "cornell_dispersion_16x9", 96, 54, 3, 6, []),
 ]
 EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
 
