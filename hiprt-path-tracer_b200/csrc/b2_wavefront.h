@@ -139,6 +139,9 @@ __device__ __forceinline__ void wf_result(const WfBuffers& b, int path, int k, b
  * profiles/r02_ncu_wavefront.md: 134 load + 161 store sectors per path and stage, `lg_throttle` the second stall reason, 24 GB
  * through L2 in a 5.8 ms launch). Here 8 lanes fetch 128 contiguous bytes of ONE record, the warp 4 records per instruction, and
  * the 16-byte pieces change hands through a padded shared-memory tile (32 records x 128 B per warp). */
+#ifndef B2_WF_SORT_ENDING_APART
+#define B2_WF_SORT_ENDING_APART 1
+#endif
 #define B2_WF_COPY_TILE_UINT4 (32 * 9) /* per warp: 32 records x (8 + 1 pad) uint4 */
 #define B2_WF_COPY_SMEM_BYTES ((B2_WF_STAGE_THREADS / 32) * B2_WF_COPY_TILE_UINT4 * 16)
 
@@ -268,7 +271,13 @@ __global__ void __launch_bounds__(256) wf_sort_count(const __grid_constant__ b2p
             prim = __float_as_int(b.slot_a[path * B2_WF_RAYS].w);
         else
             prim = record->s.hit.primitive_index;
-        const unsigned int key = prim >= 0 ? ((unsigned int)rd.buffers.material_indices[prim] % (B2_WF_SORT_BUCKETS - 1)) : (B2_WF_SORT_BUCKETS - 1);
+        /* paths that only come back to collect their last vertex's NEE (no main ray: they end in stage 1 after a few instructions)
+         * and paths whose main ray left the scene get buckets of their own, so that they do not idle lanes of shading warps */
+        unsigned int key;
+        if (B2_WF_SORT_ENDING_APART && record->ph.ending)
+            key = B2_WF_SORT_BUCKETS - 2;
+        else
+            key = prim >= 0 ? ((unsigned int)rd.buffers.material_indices[prim] % (B2_WF_SORT_BUCKETS - 2)) : (B2_WF_SORT_BUCKETS - 1);
         b.keys[i] = key;
         atomicAdd(&hist[key], 1u);
     }
