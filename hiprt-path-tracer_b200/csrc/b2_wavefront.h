@@ -633,18 +633,75 @@ struct WfPassBuffers
     int* ray_list;
     unsigned int* counters;
     unsigned int* have; /* per pixel: bit k = ray k of phase A is in flight; bit 31 = the final ray */
+    const int* pixel_list; /* the launch's pixels (slots) sorted by the material of their primary hit; thread i works on pixel_list[i] */
+    int n_pixels;
 };
 
-/* pixel of a thread in 8x8 tiles over the launch's rows; slot = its index among the launch's pixels, -1 outside */
-__device__ __forceinline__ int wf_tile_pixel(const B2LaunchGeom& g, int tiles_x, int rows, uint32_t& x, uint32_t& y)
+/* Pixel of a thread. The phases of a pass run over the launch's pixels SORTED BY THE MATERIAL OF THEIR PRIMARY HIT (pixels without a
+ * hit last): like the paths of the MegaKernel's shading stages, the lanes of a warp then evaluate the same lobes of the principled BSDF
+ * (the stages lose 20 % when their paths come in pixel order instead, profiles/r02_results.md). slot = the pixel's index among the
+ * launch's pixels (row-major over the launch's rows), -1 for a thread beyond the list. */
+__device__ __forceinline__ int wf_list_pixel(const B2LaunchGeom& g, const WfPassBuffers& b, uint32_t& x, uint32_t& y)
 {
-    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
-    x = tile_x * B2_TILE_W + (threadIdx.x & 7);
-    const int local_row = tile_y * B2_TILE_H + (threadIdx.x >> 3);
-    y = b2_global_row((uint32_t)local_row, g);
-    if (x >= (uint32_t)g.width || local_row >= rows)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    x = y = 0;
+    if (i >= b.n_pixels)
         return -1;
-    return local_row * g.width + (int)x;
+    const int slot = b.pixel_list[i];
+    x = (uint32_t)(slot % g.width);
+    y = b2_global_row((uint32_t)(slot / g.width), g);
+    return slot;
+}
+
+/* counting sort of the launch's pixels on the material of their primary hit (same three steps as the path sort above) */
+__global__ void __launch_bounds__(256) wf_pixel_sort_count(const __grid_constant__ b2pt_render_data rd, const B2LaunchGeom geom, unsigned int* __restrict__ keys, unsigned int* __restrict__ buckets, int n_pixels)
+{
+    __shared__ unsigned int hist[B2_WF_SORT_BUCKETS];
+    for (int i = threadIdx.x; i < B2_WF_SORT_BUCKETS; i += blockDim.x)
+        hist[i] = 0u;
+    __syncthreads();
+    const int res_x = rd.render_settings.render_resolution.x, res_y = rd.render_settings.render_resolution.y;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_pixels; slot += gridDim.x * blockDim.x)
+    {
+        const uint32_t x = (uint32_t)(slot % geom.width), y = b2_global_row((uint32_t)(slot / geom.width), geom);
+        unsigned int key = B2_WF_SORT_BUCKETS - 1;
+        if (x < (uint32_t)res_x && y < (uint32_t)res_y)
+        {
+            const int prim = rd.g_buffer.first_hit_prim_index[x + y * (uint32_t)res_x];
+            if (prim >= 0)
+                key = (unsigned int)rd.buffers.material_indices[prim] % (B2_WF_SORT_BUCKETS - 2);
+        }
+        keys[slot] = key;
+        atomicAdd(&hist[key], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B2_WF_SORT_BUCKETS; i += blockDim.x)
+        if (hist[i])
+            atomicAdd(&buckets[i], hist[i]);
+}
+
+__global__ void __launch_bounds__(256) wf_pixel_sort_scatter(const unsigned int* __restrict__ keys, unsigned int* __restrict__ buckets, int* __restrict__ pixel_list, int n_pixels)
+{
+    __shared__ unsigned int local[B2_WF_SORT_BUCKETS];
+    const unsigned int count = (unsigned int)n_pixels;
+    const unsigned int chunk = (count + gridDim.x - 1) / gridDim.x;
+    const unsigned int begin = blockIdx.x * chunk, end = min(begin + chunk, count);
+    if (begin >= end)
+        return;
+    for (int i = threadIdx.x; i < B2_WF_SORT_BUCKETS; i += blockDim.x)
+        local[i] = 0u;
+    __syncthreads();
+    for (unsigned int i = begin + threadIdx.x; i < end; i += blockDim.x)
+        atomicAdd(&local[keys[i]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < B2_WF_SORT_BUCKETS; i += blockDim.x)
+    {
+        const unsigned int n = local[i];
+        local[i] = n ? atomicAdd(&buckets[B2_WF_SORT_BUCKETS + i], n) : 0u;
+    }
+    __syncthreads();
+    for (unsigned int i = begin + threadIdx.x; i < end; i += blockDim.x)
+        pixel_list[atomicAdd(&local[keys[i]], 1u)] = (int)i;
 }
 
 template <class P, class V>
@@ -658,7 +715,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_a(const __grid_const
     b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
     ctx.light_presampling = geom.light_presampling != 0;
     uint32_t x, y;
-    const int slot = wf_tile_pixel(geom, tiles_x, rows, x, y);
+    const int slot = wf_list_pixel(geom, b, x, y);
     RayRequest rays[P::RAYS];
 #pragma unroll
     for (int k = 0; k < P::RAYS; k++)
@@ -701,7 +758,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_b(const __grid_const
     b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
     ctx.light_presampling = geom.light_presampling != 0;
     uint32_t x, y;
-    const int slot = wf_tile_pixel(geom, tiles_x, rows, x, y);
+    const int slot = wf_list_pixel(geom, b, x, y);
     RayRequest final_ray;
     request_none(final_ray);
     bool active = false;
@@ -754,7 +811,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_c(const __grid_const
     Ctx ctx;
     b2_make_ctx(ctx, rd, nullptr, nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
     uint32_t x, y;
-    const int slot = wf_tile_pixel(geom, tiles_x, rows, x, y);
+    const int slot = wf_list_pixel(geom, b, x, y);
     if (slot < 0)
         return;
     typename P::State st = reinterpret_cast<const typename P::State*>(b.states)[slot];
@@ -840,9 +897,10 @@ cudaError_t launch_wavefront_pass(const b2pt_render_data* rd, const B2LaunchGeom
     const size_t slots_bytes = align(n_pixels * P::RAYS * sizeof(float4));
     const size_t ray_list_bytes = align(n_pixels * P::RAYS * sizeof(int));
     const size_t have_bytes = align(n_pixels * sizeof(unsigned int));
+    const size_t list_bytes = align(n_pixels * sizeof(int));
     WfScratch sc;
     int sms = 0;
-    cudaError_t e = wf_scratch_get(stream, states_bytes + 2 * slots_bytes + ray_list_bytes + have_bytes, sc, sms);
+    cudaError_t e = wf_scratch_get(stream, states_bytes + 2 * slots_bytes + ray_list_bytes + have_bytes + 2 * list_bytes, sc, sms);
     if (e != cudaSuccess)
         return e;
     WfPassBuffers b;
@@ -851,7 +909,11 @@ cudaError_t launch_wavefront_pass(const b2pt_render_data* rd, const B2LaunchGeom
     b.slot_a = reinterpret_cast<float4*>(p); p += slots_bytes;
     b.slot_b = reinterpret_cast<float4*>(p); p += slots_bytes;
     b.ray_list = reinterpret_cast<int*>(p); p += ray_list_bytes;
-    b.have = reinterpret_cast<unsigned int*>(p);
+    b.have = reinterpret_cast<unsigned int*>(p); p += have_bytes;
+    int* pixel_list = reinterpret_cast<int*>(p); p += list_bytes;
+    unsigned int* pixel_keys = reinterpret_cast<unsigned int*>(p);
+    b.pixel_list = pixel_list;
+    b.n_pixels = (int)n_pixels;
     b.counters = sc.counters;
     WfBuffers tb; /* what wf_trace looks at */
     tb.paths = nullptr;
@@ -865,27 +927,34 @@ cudaError_t launch_wavefront_pass(const b2pt_render_data* rd, const B2LaunchGeom
     tb.n_paths = (int)n_pixels;
 
     e = cudaMemsetAsync(sc.counters, 0, WF_C_COUNT * sizeof(unsigned int), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc.buckets, 0, 2 * B2_WF_SORT_BUCKETS * sizeof(unsigned int), stream);
     if (e != cudaSuccess)
         return e;
-    const int tiles_x = (g.width + B2_TILE_W - 1) / B2_TILE_W, tiles_y = (rows + B2_TILE_H - 1) / B2_TILE_H;
+    const int tiles_x = (g.width + B2_TILE_W - 1) / B2_TILE_W;
+    const int pass_blocks = (int)((n_pixels + B2_BLOCK_THREADS - 1) / B2_BLOCK_THREADS);
+    const int sort_blocks = sms * 4;
     const int trace_blocks = sms * B2_WF_TRACE_MIN_BLOCKS;
     const size_t trace_smem = (size_t)g.stack_entries * B2_WF_TRACE_THREADS * 8;
     const B2BvhDevice* bvh = reinterpret_cast<const B2BvhDevice*>(rd->GPU_BVH);
     const B2AlphaTest alpha = b2_alpha_test_of(*rd, g.alpha_test != 0);
-    g_cuda_launches += 6;
+    g_cuda_launches += 9;
     const bool prof = b2_wfprof_enabled();
+    if (prof) b2_wfprof_mark(stream, B2_WF_K_SORT);
+    wf_pixel_sort_count<<<sort_blocks, 256, 0, stream>>>(*rd, g, pixel_keys, sc.buckets, (int)n_pixels);
+    wf_sort_scan<<<1, B2_WF_SORT_BUCKETS, 0, stream>>>(tb);
+    wf_pixel_sort_scatter<<<sort_blocks, 256, 0, stream>>>(pixel_keys, sc.buckets, pixel_list, (int)n_pixels);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_PASS_A);
-    wf_pass_a<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
+    wf_pass_a<P, V><<<pass_blocks, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE_PASS);
     wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, tb, g.stack_entries, alpha);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_ADVANCE);
     wf_reset_rays<<<1, 1, 0, stream>>>(sc.counters);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_PASS_B);
-    wf_pass_b<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
+    wf_pass_b<P, V><<<pass_blocks, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_TRACE_PASS);
     wf_trace<V::COUNTERS><<<trace_blocks, B2_WF_TRACE_THREADS, trace_smem, stream>>>(bvh, tb, g.stack_entries, alpha);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_PASS_C);
-    wf_pass_c<P, V><<<tiles_x * tiles_y, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
+    wf_pass_c<P, V><<<pass_blocks, B2_BLOCK_THREADS, 0, stream>>>(*rd, g, tiles_x, rows, b);
     if (prof) b2_wfprof_mark(stream, B2_WF_K_END);
     return cudaGetLastError();
 }
