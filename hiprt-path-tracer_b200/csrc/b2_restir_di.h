@@ -752,10 +752,14 @@ B2_HD void restir_di_initial_phase_a(const Ctx& ctx, uint32_t x, uint32_t y, DiI
             int incident_light_info = B2_LOBE_NO_INFO; /* uninitialised in the reference (InitialCandidates.h:226) */
             BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, to_light_direction, &incident_light_info, &payload.volume_state, false, &payload.material,
                                          payload.bounce, payload.accumulated_roughness);
-            (void)bsdf_eval<V>(rd, bctx, bsdf_pdf_solid_angle);
+            const Rgb candidate_bsdf_color = bsdf_eval<V>(rd, bctx, bsdf_pdf_solid_angle);
 
             DiSurface surface = surface_from_hit(hit, payload, view_direction);
-            float target_function = di_target_function<V, false>(ctx, light_sample, surface);
+            /* same surface, same direction (di_light_sample_direction both times), lobe info NO_INFO (a fresh or presampled light candidate
+             * carries no lobe bits), bounce 0, accumulated roughness 0 at the primary hit: the target function's own evaluation
+             * would return candidate_bsdf_color again */
+            const bool same_context = payload.bounce == 0 && payload.accumulated_roughness == 0.0f && light_sample.lobe_info() == B2_LOBE_NO_INFO;
+            float target_function = di_target_function<V, false>(ctx, light_sample, surface, same_context ? &candidate_bsdf_color : nullptr);
             if (bsdf_pdf_solid_angle <= 0.0f || !check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, target_function / light_pdf_area_measure / bsdf_pdf_solid_angle))
                 target_function = 0.0f;
             else

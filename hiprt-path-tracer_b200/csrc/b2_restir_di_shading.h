@@ -249,8 +249,11 @@ B2_HD Rgb di_light_sample_emission(const b2pt_render_data& rd, const DiSample& s
 }
 
 /* ReSTIR_DI_evaluate_target_function<withVisibility>, DI/TargetFunction.h:48-98 */
+/* known_bsdf_color: the value bsdf_eval returns for exactly this context (same surface, direction, lobe info NO_INFO, bounce 0,
+ * accumulated roughness 0, no regularisation), when the caller has just computed it: the evaluation is a pure function of its
+ * inputs, so the initial-candidates loop does not run it twice per candidate as the reference does (InitialCandidates.h:226-240) */
 template <class V, bool WITH_VISIBILITY>
-B2_HD float di_target_function(const Ctx& ctx, const DiSample& sample, DiSurface& surface)
+B2_HD float di_target_function(const Ctx& ctx, const DiSample& sample, DiSurface& surface, const Rgb* known_bsdf_color = nullptr)
 {
     const b2pt_render_data& rd = *ctx.rd;
     if (sample.emissive_triangle_index == -1 && !sample.is_envmap_sample())
@@ -267,7 +270,7 @@ B2_HD float di_target_function(const Ctx& ctx, const DiSample& sample, DiSurface
     int incident_light_info = sample.lobe_info();
     BsdfCtx bctx = make_bsdf_ctx(surface.view_direction, surface.shading_normal, surface.geometric_normal, sample_direction, &incident_light_info, &surface.ray_volume_state, false,
                                  &surface.material, 0, 0.0f);
-    Rgb bsdf_color = bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
+    Rgb bsdf_color = known_bsdf_color != nullptr ? *known_bsdf_color : bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
     Rgb sample_emission = di_light_sample_emission<V>(rd, sample, sample_direction);
 
     float geometry_term = 1.0f;

@@ -91,6 +91,7 @@ B2_HD void ris_light_candidate(const Ctx& ctx, Payload& payload, const HitInfo& 
     const b2pt_render_data& rd = *ctx.rd;
     float target_function = 0.0f;
     float candidate_weight = 0.0f;
+    Rgb candidate_bsdf_color = rgb(0.0f);
     LightSample light_sample = sample_one_emissive_triangle<V>(rd, rng);
 
     if (light_sample.area_measure_pdf > 0.0f)
@@ -112,6 +113,7 @@ B2_HD void ris_light_candidate(const Ctx& ctx, Payload& payload, const HitInfo& 
                 BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, to_light_direction, &incident_light_info, &payload.volume_state, false,
                                              &payload.material, payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
                 Rgb bsdf_color = bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
+                candidate_bsdf_color = bsdf_color;
                 Rgb light_contribution = bsdf_color * light_sample.emission * cosine_at_evaluated_point;
                 contributes_enough = check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, light_contribution / bsdf_pdf_value / light_sample.area_measure_pdf);
                 if (!contributes_enough)
@@ -130,6 +132,8 @@ B2_HD void ris_light_candidate(const Ctx& ctx, Payload& payload, const HitInfo& 
     light_RIS_sample.point_on_light_source = light_sample.point_on_light;
     light_RIS_sample.target_function = target_function;
     light_RIS_sample.emission = light_sample.emission;
+    /* kept for ris_shade_survivor: a light candidate can only be selected with a weight > 0, i.e. after this evaluation */
+    light_RIS_sample.bsdf_sample_contribution = candidate_bsdf_color;
     reservoir.add_one_candidate(light_RIS_sample, candidate_weight, rng);
 }
 
@@ -227,10 +231,11 @@ B2_HD Rgb ris_shade_survivor(const Ctx& ctx, Payload& payload, const HitInfo& hi
         }
         else
         {
-            int incident_light_info = B2_LOBE_NO_INFO;
-            BsdfCtx bctx = make_bsdf_ctx(view_direction, hit.shading_normal, hit.geometric_normal, shadow_ray_direction_normalized, &incident_light_info, &payload.volume_state, false,
-                                         &payload.material, payload.bounce, payload.accumulated_roughness, B2_REGULARIZATION_MIS);
-            bsdf_color = bsdf_eval<V>(rd, bctx, bsdf_pdf_value);
+            /* RIS.h:56-63 evaluates the BSDF of the surviving light sample here: same surface, same direction (both normalise
+             * point_on_light - inter_point the same way), same lobe info / bounce / roughness / regularisation as the evaluation the
+             * candidate went through when it was weighed (ris_light_candidate), which is a pure function of those: its value was kept */
+            (void)bsdf_pdf_value;
+            bsdf_color = sample.bsdf_sample_contribution;
             cosine_at_evaluated_point = fabsf(dot(hit.shading_normal, shadow_ray_direction_normalized));
         }
         final_color = bsdf_color * reservoir.UCW * sample.emission * cosine_at_evaluated_point;

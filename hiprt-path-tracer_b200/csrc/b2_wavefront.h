@@ -36,6 +36,9 @@
 #ifndef B2_WF_TRACE_MIN_BLOCKS
 #define B2_WF_TRACE_MIN_BLOCKS 4 /* 64 registers, 32 warps / SM */
 #endif
+#ifndef B2_WF_REFILL_LANES
+#define B2_WF_REFILL_LANES 8 /* idle lanes of a warp that trigger a refill from the queue */
+#endif
 #ifndef B2_WF_TRI_LANES
 #define B2_WF_TRI_LANES 8 /* lanes of a warp that must hold untested leaf triangles before the warp runs a triangle phase */
 #endif
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(B2_WF_TRACE_THREADS, B2_WF_TRACE_MIN_BLOCKS) w
     while (true)
     {
         const unsigned int idle = __ballot_sync(0xFFFFFFFFu, !busy);
-        if (idle != 0u && !drained && ((int)__popc(idle) >= 8 || idle == 0xFFFFFFFFu))
+        if (idle != 0u && !drained && ((int)__popc(idle) >= B2_WF_REFILL_LANES || idle == 0xFFFFFFFFu))
         {
             const int wanted = __popc(idle);
             int base = 0;
