@@ -897,6 +897,34 @@ int b2pt_renderer_render(b2pt_renderer* r, int samples)
 }
 
 /* Multi-GPU partition of the frame: interleaved row bands, scene replicated. */
+/* Band height of a partition: interleaved bands of `preferred` rows leave the ranks with unequal shares whenever the number of bands
+ * is not a multiple of the number of ranks (2160 rows in 32-row bands over 8 GPUs: 9 bands = 288 rows on four ranks, 8 = 256 on the
+ * others, and a step takes as long as its slowest rank). The height between `minimum` and `preferred` whose busiest rank owns the
+ * fewest rows is taken (2160 rows, 8 GPUs: 30-row bands, 270 rows everywhere); ties go to the taller band (fewer halo rows). */
+static int balanced_band_rows(int height, int world, int preferred, int minimum)
+{
+    if (world <= 1)
+        return preferred;
+    int best = preferred, best_rows = height + 1;
+    for (int band = preferred; band >= minimum; band--)
+    {
+        int worst = 0;
+        for (int rank = 0; rank < world; rank++)
+        {
+            int rows = 0;
+            for (int b = rank; b * band < height; b += world)
+                rows += std::min(band, height - b * band);
+            worst = std::max(worst, rows);
+        }
+        if (worst < best_rows)
+        {
+            best_rows = worst;
+            best = band;
+        }
+    }
+    return best;
+}
+
 int b2pt_renderer_set_partition(b2pt_renderer* r, int rank, int world, b2pt_comm* comm, int dynamic_camera)
 {
     if (!r || world < 1 || rank < 0 || rank >= world) { b2_set_error("b2pt_renderer_set_partition: invalid argument"); return B2PT_ERR_INVALID_ARGUMENT; }
@@ -911,7 +939,7 @@ int b2pt_renderer_set_partition(b2pt_renderer* r, int rank, int world, b2pt_comm
     r->world = world;
     r->comm = comm;
     r->dynamic_camera = dynamic_camera != 0;
-    r->band_rows = r->loop.restir_di ? 32 : B2PT_BAND_ROWS;
+    r->band_rows = balanced_band_rows(r->height, world, r->loop.restir_di ? 32 : B2PT_BAND_ROWS, r->loop.restir_di ? 24 : 8);
     if (r->d_camera_rows)
     {
         b2pt_free(r->ctx, r->d_camera_rows);
