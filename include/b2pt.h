@@ -269,7 +269,8 @@ int b2pt_renderer_reset(b2pt_renderer* renderer);
 /* Renders `samples` samples of every pixel (all passes), asynchronously on the renderer's stream. */
 int b2pt_renderer_render(b2pt_renderer* renderer, int samples);
 /* Multi-GPU (BASELINE.json north_star; the reference itself is single-GPU): this renderer renders only the pixel rows of its
- * interleaved bands (band b -> rank b % world; 16-row bands, 32-row bands for the ReSTIR DI variants); scene, BVH and LUTs are
+ * interleaved bands (band b -> rank b % world; bands of at most 16 rows, at most 32 for the ReSTIR DI variants, the exact height chosen so that
+ * every rank owns the same number of rows -- b2pt_renderer_partition_info reports it); scene, BVH and LUTs are
  * replicated by giving every rank the same scene. Without ReSTIR DI no pass reads another pixel. With ReSTIR DI the reuse passes
  * read reservoirs and G-buffer entries up to reuse_radius + neighbor_search_radius pixels away: CameraRays also covers those
  * halo rows (deterministic, so neighbours' G-buffer entries are recomputed instead of exchanged) and the reservoir rows of the
