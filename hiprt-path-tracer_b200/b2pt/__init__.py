@@ -70,6 +70,7 @@ SETTINGS_OFFSETS = {
     "restir_di_reuse_neighbor_count": (_RS + 160 + 24 + 20, "i"),
     "restir_di_use_adaptive_directional_spatial_reuse": (_RS + 160 + 24 + 49, "B"),
     "restir_di_m_cap": (_RS + 160 + 180, "i"),
+    "restir_di_use_confidence_weights": (_RS + 160 + 184, "B"),
     "restir_di_do_fused_spatiotemporal": (_RS + 160 + 272, "B"),
     "current_camera_do_jittering": (2328 + 216, "B"),
     "ambient_light_type": (2088 + 0, "i"),

@@ -144,6 +144,7 @@ struct b2pt_kernel
     int light_presampling = 0; /* ReSTIR_DI_DoLightPresampling the kernel was asked for */
     int precise = 1;           /* codegen flavour of the unit the entry comes from */
     int alpha_test = 0;        /* B2PT_ALPHA_TEST: candidate hits on non-opaque materials go through the alpha test */
+    int bias_correction = 4;   /* ReSTIR_DI_BiasCorrectionWeights */
 };
 
 int b2_ctx_device(b2pt_ctx* ctx) { return ctx ? ctx->device : 0; }
@@ -610,7 +611,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
         return B2PT_ERR_NO_VARIANT;
     }
     /* reference defaults */
-    int bsdf = 0, direct = 4, base = 1, later = 3, envmap = 2, precise = 1, counters = 0, light_presampling = 0, alpha_test = 0;
+    int bsdf = 0, direct = 4, base = 1, later = 3, envmap = 2, precise = 1, counters = 0, light_presampling = 0, alpha_test = 0, bias_correction = 4;
     for (int i = 0; i < option_count; i++)
     {
         const char* n = options[i].name;
@@ -624,6 +625,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
         else if (!std::strcmp(n, "ReSTIR_DI_DoLightPresampling")) light_presampling = v != 0; /* launch-time switch of the same kernels */
         else if (!std::strcmp(n, "B2PT_PRECISE")) precise = v;
         else if (!std::strcmp(n, "B2PT_ALPHA_TEST")) alpha_test = v != 0; /* launch-time switch of the same kernels */
+        else if (!std::strcmp(n, "ReSTIR_DI_BiasCorrectionWeights")) bias_correction = v; /* launch-time switch of the reuse passes */
         else if (!std::strcmp(n, "B2PT_COUNTERS")) counters = v;
         else
         {
@@ -645,6 +647,19 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
             }
         }
     }
+    /* ReSTIR_DI_BiasCorrectionWeights (ReSTIRDIOptions.h:9-16): 1/Z, MIS-like, generalised balance heuristic, pairwise MIS (the default)
+     * and defensive pairwise MIS are built for the temporal and spatial reuse passes; the fused spatiotemporal pass is built for
+     * pairwise MIS only; 1/M does not compile in the reference itself (SpatialReuse.h:237 calls its normalisation with 6 of 7 arguments)
+     * and the two ratio heuristics are not built */
+    {
+        const bool built = bias_correction >= 1 && bias_correction <= 5;
+        const bool reuse_pass = pass == B2_PASS_RESTIR_DI_TEMPORAL || pass == B2_PASS_RESTIR_DI_SPATIAL || pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL;
+        if (reuse_pass && (!built || (pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL && bias_correction != 4)))
+        {
+            b2_set_error("no precompiled variant of %s with ReSTIR_DI_BiasCorrectionWeights=%d", entry_name, bias_correction);
+            return B2PT_ERR_NO_VARIANT;
+        }
+    }
     for (const B2KernelUnit& unit : kernel_units())
     {
         if ((unit.precise != 0) != (precise != 0))
@@ -661,6 +676,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
                 k->light_presampling = light_presampling;
                 k->precise = unit.precise;
                 k->alpha_test = alpha_test;
+                k->bias_correction = bias_correction;
                 B2_CUDA(cudaEventCreate(&k->start));
                 B2_CUDA(cudaEventCreate(&k->stop));
                 *out_kernel = k;
@@ -733,6 +749,7 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
     geom.row_count = device_rows ? n_rows : 0;
     geom.light_presampling = kernel->light_presampling;
     geom.alpha_test = kernel->alpha_test;
+    geom.bias_correction = kernel->bias_correction;
     geom.presampling_parameters = presampling_pass ? args[0] : nullptr;
     geom.directional_masks_ull = nullptr;
     geom.directional_radius = nullptr;

@@ -83,6 +83,7 @@ __device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd
     ctx.faults = faults;
     ctx.light_presampling = false;
     ctx.alpha_test = alpha_test; /* kernels that were asked for alpha testing (B2PT_ALPHA_TEST) */
+    ctx.bias_correction = 4;     /* RESTIR_DI_BIAS_CORRECTION_PAIRWISE_MIS; the pixel kernels of the reuse passes take the launch's */
     B2_SET_RAY_BOUNCE(ctx, 0);
 }
 
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS, B2_PASS_MIN_BLOCKS) pass_ker
     Ctx ctx;
     b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
     ctx.light_presampling = geom.light_presampling != 0;
+    ctx.bias_correction = geom.bias_correction;
 
     b2_run_pass_pixel<V>(PASS, ctx, x, y);
 

@@ -156,13 +156,19 @@ void free_all(b2pt_renderer* r, std::vector<void*>& owner)
     owner.clear();
 }
 
-struct VariantKey { const char* name; int bsdf, direct, base, later; bool restir; bool presampling; };
+struct VariantKey { const char* name; int bsdf, direct, base, later; bool restir; bool presampling; int bias_correction; };
 const VariantKey kVariants[] = {
-    { "c1", 1, 1, 0, 3, false, false },
-    { "c2", 0, 3, 1, 3, false, false },
-    { "c3", 0, 4, 1, 3, false, false },
-    { "c4", 0, 5, 1, 3, true, false },
-    { "c4p", 0, 5, 1, 3, true, true }, /* c4 with ReSTIR_DI_DoLightPresampling */
+    { "c1", 1, 1, 0, 3, false, false, 4 },
+    { "c2", 0, 3, 1, 3, false, false, 4 },
+    { "c3", 0, 4, 1, 3, false, false, 4 },
+    { "c4", 0, 5, 1, 3, true, false, 4 },
+    { "c4p", 0, 5, 1, 3, true, true, 4 }, /* c4 with ReSTIR_DI_DoLightPresampling */
+    /* c4 with another ReSTIR_DI_BiasCorrectionWeights (ReSTIRDIOptions.h:9-16): 1/Z, MIS-like, generalised balance heuristic, defensive
+     * pairwise MIS. Temporal + spatial passes only: restir_di_do_fused_spatiotemporal must be 0 */
+    { "c4b1", 0, 5, 1, 3, true, false, 1 },
+    { "c4b2", 0, 5, 1, 3, true, false, 2 },
+    { "c4b3", 0, 5, 1, 3, true, false, 3 },
+    { "c4b5", 0, 5, 1, 3, true, false, 5 },
 };
 
 const VariantKey* find_variant(const std::string& name)
@@ -213,7 +219,12 @@ int resolve_kernels(b2pt_renderer* r)
             { "BSDFOverride", v->bsdf }, { "DirectLightSamplingStrategy", v->direct }, { "DirectLightSamplingBaseStrategy", v->base },
             { "ReSTIR_DI_LaterBouncesSamplingStrategy", v->later }, { "ReSTIR_DI_DoLightPresampling", v->presampling ? 1 : 0 },
             { "B2PT_PRECISE", r->precise }, { "B2PT_COUNTERS", r->counters }, { "B2PT_ALPHA_TEST", r->alpha_test ? 1 : 0 },
+            { "ReSTIR_DI_BiasCorrectionWeights", v->bias_correction },
         };
+        /* a variant with another bias correction has no fused pass (b2pt_kernel_get would answer NO_VARIANT): the frame loop does not
+         * launch it as long as restir_di_do_fused_spatiotemporal is 0, and says so otherwise */
+        if (pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL && v->bias_correction != 4)
+            continue;
         B2_TRY(b2pt_kernel_get(r->ctx, entry, opts, (int)(sizeof(opts) / sizeof(opts[0])), &r->kernels[pass]));
     }
     r->kernels_stale = false;

@@ -36,6 +36,9 @@ B2_HD bool restir_gi_coalesced_spatial_reuse(const b2pt_render_data& rd)
     return gi[offset] != 0;
 }
 
+/* ReSTIR_DI_BiasCorrectionWeights (HostDeviceCommon/KernelOptions/ReSTIRDIOptions.h:9-16) */
+enum { B2_BIAS_1_OVER_M = 0, B2_BIAS_1_OVER_Z = 1, B2_BIAS_MIS_LIKE = 2, B2_BIAS_MIS_GBH = 3, B2_BIAS_PAIRWISE_MIS = 4, B2_BIAS_PAIRWISE_MIS_DEFENSIVE = 5 };
+
 struct SpatialLocal
 {
     unsigned int rng_seed;
@@ -341,8 +344,43 @@ struct PairwiseMis
      * when update_mc */
     B2_HD float weight_given(const b2pt_render_data& rd, int reservoir_being_resampled_M, float reservoir_being_resampled_target_function, int center_pixel_reservoir_M,
                              float center_pixel_reservoir_target_function, float target_function_at_center, float target_function_center_sample_at_neighbor,
-                             int valid_neighbors_count, int valid_neighbors_M_sum, bool update_mc, bool resampling_canonical, bool guard_zero_confidence)
+                             int valid_neighbors_count, int valid_neighbors_M_sum, bool update_mc, bool resampling_canonical, bool guard_zero_confidence, bool defensive = false)
     {
+        if (defensive)
+        {
+            /* RESTIR_DI_BIAS_CORRECTION_PAIRWISE_MIS_DEFENSIVE, SpatialMISWeight.h:236-368: the canonical sample keeps a share of its own */
+            const bool confidence = rd.render_settings.restir_di_settings.use_confidence_weights != 0;
+            if (resampling_canonical)
+            {
+                if (mc == 0.0f)
+                    return 1.0f;
+                if (confidence)
+                    return mc + (float)center_pixel_reservoir_M / (float)(center_pixel_reservoir_M + valid_neighbors_M_sum);
+                return (1.0f + mc) / ((float)valid_neighbors_count + 1.0f);
+            }
+            float target_function_at_neighbor = reservoir_being_resampled_target_function;
+            float reservoir_resampled_M = confidence ? (float)reservoir_being_resampled_M : 1.0f;
+            float center_reservoir_M = confidence ? (float)center_pixel_reservoir_M : 1.0f;
+            float neighbors_confidence_sum = confidence ? (float)valid_neighbors_M_sum : 1.0f;
+            float valid_neighbor_division_term = confidence ? 1.0f : (float)valid_neighbors_count;
+            float nume = target_function_at_neighbor * reservoir_resampled_M;
+            float denom = target_function_at_neighbor * neighbors_confidence_sum + target_function_at_center / valid_neighbor_division_term * center_reservoir_M;
+            float mi = denom == 0.0f ? 0.0f : (nume / denom);
+            if (confidence)
+                mi *= neighbors_confidence_sum / (neighbors_confidence_sum + center_reservoir_M);
+            if (update_mc)
+            {
+                float target_function_center_sample_at_center = center_pixel_reservoir_target_function;
+                float nume_mc = target_function_center_sample_at_center / valid_neighbor_division_term * center_reservoir_M;
+                float denom_mc = target_function_center_sample_at_neighbor * neighbors_confidence_sum + target_function_center_sample_at_center / valid_neighbor_division_term * center_reservoir_M;
+                float confidence_multiplier = 1.0f;
+                if (confidence)
+                    confidence_multiplier = reservoir_resampled_M / (center_reservoir_M + neighbors_confidence_sum);
+                if (denom_mc != 0.0f)
+                    mc += nume_mc / denom_mc * confidence_multiplier;
+            }
+            return confidence ? mi : mi / ((float)valid_neighbors_count + 1.0f);
+        }
         if (resampling_canonical)
             return mc == 0.0f ? 1.0f : mc;
 
@@ -383,7 +421,8 @@ struct PairwiseMis
     template <class V>
     B2_HD float weight(const Ctx& ctx, int reservoir_being_resampled_M, float reservoir_being_resampled_target_function, int center_pixel_reservoir_M,
                        float center_pixel_reservoir_target_function, const DiSample& center_pixel_reservoir_sample, float target_function_at_center, int neighbor_pixel_index,
-                       bool neighbor_from_previous_frame, int valid_neighbors_count, int valid_neighbors_M_sum, bool update_mc, bool resampling_canonical, bool guard_zero_confidence, Rng& rng)
+                       bool neighbor_from_previous_frame, int valid_neighbors_count, int valid_neighbors_M_sum, bool update_mc, bool resampling_canonical, bool guard_zero_confidence, Rng& rng,
+                       bool defensive = false)
     {
         const b2pt_render_data& rd = *ctx.rd;
         float target_function_center_sample_at_neighbor = 0.0f;
@@ -394,7 +433,7 @@ struct PairwiseMis
         }
         return weight_given(rd, reservoir_being_resampled_M, reservoir_being_resampled_target_function, center_pixel_reservoir_M, center_pixel_reservoir_target_function,
                             target_function_at_center, target_function_center_sample_at_neighbor, valid_neighbors_count, valid_neighbors_M_sum, update_mc, resampling_canonical,
-                            guard_zero_confidence);
+                            guard_zero_confidence, defensive);
     }
 };
 
@@ -1019,43 +1058,139 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
         return;
     }
 
-    /* pairwise MIS, TemporalMISWeight.h:163-254 */
+    /* ReSTIR_DI_BiasCorrectionWeights: how the two reservoirs are weighted against each other (TemporalMISWeight.h) and how the result is
+     * normalised (TemporalNormalizationWeight.h); a -D macro in the reference, a launch-time switch here */
+    const int bias = ctx.bias_correction;
+    const bool use_confidence_weights = di.use_confidence_weights != 0;
+    int selected_neighbor = 0; /* TEMPORAL_NEIGHBOR_ID = 0, INITIAL_CANDIDATES_ID = 1 */
     float mc = 0.0f;
+
+    /* generalised balance heuristic (TemporalMISWeight.h:93-160). As in the reference, BOTH target functions are evaluated on the
+     * temporal neighbour's surface (:129 passes temporal_neighbor_surface where the centre pixel's is meant) */
+    auto gbh_weight = [&](const DiSample& sample, int current_neighbor_index) {
+        float target_function_at_temporal_neighbor = 0.0f;
+        if (temporal_neighbor_reservoir.M != 0)
+            target_function_at_temporal_neighbor = di_target_function<V, true>(ctx, sample, temporal_neighbor_surface);
+        if (current_neighbor_index == 0 && target_function_at_temporal_neighbor == 0.0f)
+            return 0.0f;
+        float target_function_at_center = di_target_function<V, true>(ctx, sample, temporal_neighbor_surface);
+        int temporal_M = temporal_neighbor_reservoir.M;
+        int center_reservoir_M = initial_candidates_reservoir.M;
+        if (!use_confidence_weights)
+        {
+            temporal_M = 1;
+            center_reservoir_M = 1;
+        }
+        float nume = current_neighbor_index == 0 ? target_function_at_temporal_neighbor * temporal_M : target_function_at_center * center_reservoir_M;
+        float denom = target_function_at_temporal_neighbor * temporal_M + target_function_at_center * center_reservoir_M;
+        return denom == 0.0f ? 0.0f : nume / denom;
+    };
+
     if (temporal_neighbor_reservoir.M > 0)
     {
         float target_function_at_center = 0.0f;
         if (temporal_neighbor_reservoir.UCW > 0.0f)
             target_function_at_center = di_target_function<V, true>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface);
 
-        float target_function_at_neighbor = temporal_neighbor_reservoir.sample.target_function;
-        bool use_confidence_weights = di.use_confidence_weights != 0;
-        float temporal_neighbor_M = use_confidence_weights ? (float)temporal_neighbor_reservoir.M : 1.0f;
-        float center_reservoir_M = use_confidence_weights ? (float)initial_candidates_reservoir.M : 1.0f;
-        float neighbors_confidence_sum = use_confidence_weights ? (float)temporal_neighbor_reservoir.M : 1.0f;
+        float temporal_neighbor_resampling_mis_weight;
+        if (bias == B2_BIAS_1_OVER_Z)
+            temporal_neighbor_resampling_mis_weight = (float)temporal_neighbor_reservoir.M;
+        else if (bias == B2_BIAS_MIS_LIKE)
+            temporal_neighbor_resampling_mis_weight = use_confidence_weights ? (float)temporal_neighbor_reservoir.M : 1.0f;
+        else if (bias == B2_BIAS_MIS_GBH)
+            temporal_neighbor_resampling_mis_weight = gbh_weight(temporal_neighbor_reservoir.sample, 0);
+        else
+        {
+            /* pairwise MIS (TemporalMISWeight.h:163-254) and its defensive form (:256-365) */
+            const bool defensive = bias == B2_BIAS_PAIRWISE_MIS_DEFENSIVE;
+            float target_function_at_neighbor = temporal_neighbor_reservoir.sample.target_function;
+            float temporal_neighbor_M = use_confidence_weights ? (float)temporal_neighbor_reservoir.M : 1.0f;
+            float center_reservoir_M = use_confidence_weights ? (float)initial_candidates_reservoir.M : 1.0f;
+            float neighbors_confidence_sum = use_confidence_weights ? (float)temporal_neighbor_reservoir.M : 1.0f;
 
-        float nume = target_function_at_neighbor * temporal_neighbor_M;
-        float denom = target_function_at_neighbor * neighbors_confidence_sum + target_function_at_center * center_reservoir_M;
-        float mi = denom == 0.0f ? 0.0f : (nume / denom);
+            float nume = target_function_at_neighbor * temporal_neighbor_M;
+            float denom = target_function_at_neighbor * neighbors_confidence_sum + target_function_at_center * center_reservoir_M;
+            float mi = denom == 0.0f ? 0.0f : (nume / denom);
+            if (defensive && use_confidence_weights)
+                mi *= neighbors_confidence_sum / (neighbors_confidence_sum + center_reservoir_M);
 
-        float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, initial_candidates_reservoir.sample, temporal_neighbor_surface);
-        float target_function_center_sample_at_center = initial_candidates_reservoir.sample.target_function;
-        float nume_mc = target_function_center_sample_at_center * center_reservoir_M;
-        float denom_mc = target_function_center_sample_at_neighbor * neighbors_confidence_sum + target_function_center_sample_at_center * center_reservoir_M;
-        float confidence_multiplier = 1.0f;
-        if (use_confidence_weights)
-            confidence_multiplier = temporal_neighbor_M / neighbors_confidence_sum;
-        if (denom_mc != 0.0f)
-            mc += nume_mc / denom_mc * confidence_multiplier;
+            float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, initial_candidates_reservoir.sample, temporal_neighbor_surface);
+            float target_function_center_sample_at_center = initial_candidates_reservoir.sample.target_function;
+            float nume_mc = target_function_center_sample_at_center * center_reservoir_M;
+            float denom_mc = target_function_center_sample_at_neighbor * neighbors_confidence_sum + target_function_center_sample_at_center * center_reservoir_M;
+            float confidence_multiplier = 1.0f;
+            if (use_confidence_weights)
+                confidence_multiplier = defensive ? neighbors_confidence_sum / (neighbors_confidence_sum + center_reservoir_M) : temporal_neighbor_M / neighbors_confidence_sum;
+            if (denom_mc != 0.0f)
+                mc += nume_mc / denom_mc * confidence_multiplier;
 
-        if (out.combine_with(temporal_neighbor_reservoir, mi, target_function_at_center, 1.0f, rng))
+            temporal_neighbor_resampling_mis_weight = (defensive && !use_confidence_weights) ? mi * 0.5f : mi;
+        }
+
+        if (out.combine_with(temporal_neighbor_reservoir, temporal_neighbor_resampling_mis_weight, target_function_at_center, 1.0f, rng))
+        {
+            selected_neighbor = 0;
             out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+        }
     }
 
-    float initial_candidates_mis_weight = mc == 0.0f ? 1.0f : mc;
+    float initial_candidates_mis_weight;
+    if (bias == B2_BIAS_1_OVER_Z)
+        initial_candidates_mis_weight = (float)initial_candidates_reservoir.M;
+    else if (bias == B2_BIAS_MIS_LIKE)
+        initial_candidates_mis_weight = use_confidence_weights ? (float)initial_candidates_reservoir.M : 1.0f;
+    else if (bias == B2_BIAS_MIS_GBH)
+        initial_candidates_mis_weight = gbh_weight(initial_candidates_reservoir.sample, 1);
+    else if (bias == B2_BIAS_PAIRWISE_MIS_DEFENSIVE)
+    {
+        if (mc == 0.0f)
+            initial_candidates_mis_weight = 1.0f;
+        else if (use_confidence_weights)
+            initial_candidates_mis_weight = mc + (float)initial_candidates_reservoir.M / (float)(initial_candidates_reservoir.M + temporal_neighbor_reservoir.M);
+        else
+            initial_candidates_mis_weight = (1.0f + mc) * 0.5f;
+    }
+    else
+        initial_candidates_mis_weight = mc == 0.0f ? 1.0f : mc;
     if (out.combine_with(initial_candidates_reservoir, initial_candidates_mis_weight, initial_candidates_reservoir.sample.target_function, 1.0f, rng))
+    {
+        selected_neighbor = 1;
         out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+    }
 
-    out.end_with_normalization(1.0f, 1.0f);
+    /* TemporalNormalizationWeight.h: 1/Z counts the confidence of the reservoirs that could have produced the chosen sample, MIS-like
+     * weighs the chosen one against both; the others put everything into the resampling weights */
+    float normalization_numerator = 1.0f, normalization_denominator = 1.0f;
+    if ((bias == B2_BIAS_1_OVER_Z || bias == B2_BIAS_MIS_LIKE) && !(out.weight_sum <= 0.0f))
+    {
+        float center_pixel_target_function = di_target_function<V, true>(ctx, out.sample, center_pixel_surface);
+        float temporal_neighbor_target_function = 0.0f;
+        if (bias == B2_BIAS_1_OVER_Z)
+        {
+            normalization_denominator = 0.0f;
+            normalization_denominator += (float)((center_pixel_target_function > 0.0f) * initial_candidates_reservoir.M);
+            if (temporal_neighbor_reservoir.M > 0)
+            {
+                temporal_neighbor_target_function = di_target_function<V, true>(ctx, out.sample, temporal_neighbor_surface);
+                normalization_denominator += (float)((temporal_neighbor_target_function > 0.0f) * temporal_neighbor_reservoir.M);
+            }
+        }
+        else
+        {
+            if (temporal_neighbor_reservoir.M > 0)
+                temporal_neighbor_target_function = di_target_function<V, true>(ctx, out.sample, temporal_neighbor_surface);
+            normalization_numerator = selected_neighbor == 1 ? center_pixel_target_function : temporal_neighbor_target_function;
+            int initial_candidates_M = initial_candidates_reservoir.M, temporal_neighbor_M = temporal_neighbor_reservoir.M;
+            if (!use_confidence_weights)
+            {
+                initial_candidates_M = 1;
+                temporal_neighbor_M = 1;
+            }
+            normalization_denominator = center_pixel_target_function * initial_candidates_M + temporal_neighbor_target_function * temporal_neighbor_M;
+        }
+    }
+
+    out.end_with_normalization(normalization_numerator, normalization_denominator);
     if (di.m_cap > 0)
         out.M = b2_min(out.M, di.m_cap);
     di_store(rd, di.temporal_pass.output_reservoirs, (int)center_pixel_index, out);
@@ -1104,6 +1239,45 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
     PairwiseMis mis;
     mis.mc = 0.0f;
     Rng spatial_neighbors_rng = make_rng(local.rng_seed);
+    const int bias = ctx.bias_correction;
+    const bool use_confidence_weights = di.use_confidence_weights != 0;
+    int selected_neighbor = 0;
+
+    /* The families that walk over ALL neighbours again -- the generalised balance heuristic for every resampled neighbour, 1/Z and
+     * MIS-like for the normalisation -- regenerate the neighbour positions by re-seeding the kernel's MAIN generator with the
+     * spatial-neighbours seed (SpatialMISWeight.h:66-67, SpatialNormalizationWeight.h:88,158); the balance heuristic's restore of
+     * the old seed sits behind its return statements (:113-118) and never runs, so whatever the kernel draws next -- the reservoir's
+     * combine_with -- comes from the re-seeded stream. Mirrored as written. `evaluate(j, neighbour pixel, its surface)` is called
+     * for every neighbour that passes the similarity heuristics. */
+    auto for_all_neighbors = [&](auto&& evaluate) {
+        rng = make_rng(local.rng_seed);
+        for (int j = 0; j < local.reuse_neighbor_count + 1; j++)
+        {
+            int neighbor_index_j = get_spatial_neighbor_pixel_index(rd, local, j, (int)x, (int)y, rng);
+            if (neighbor_index_j == -1)
+                continue;
+            if (!check_neighbor_similarity_heuristics(rd, neighbor_index_j, (int)center_pixel_index, center_pixel_surface.shading_point, normal_for_rejection_heuristic(rd, center_pixel_surface), false))
+                continue;
+            DiSurface neighbor_surface = get_pixel_surface<V>(rd, neighbor_index_j, false, rng);
+            evaluate(j, neighbor_index_j, neighbor_surface);
+        }
+    };
+    /* SpatialMISWeight.h:46-117 */
+    auto gbh_weight = [&](float reservoir_being_resampled_UCW, const DiSample& reservoir_being_resampled_sample, int current_neighbor_index) {
+        if (reservoir_being_resampled_UCW <= 0.0f)
+            return 1.0f;
+        float nume = 0.0f, denom = 0.0f;
+        for_all_neighbors([&](int j, int neighbor_index_j, DiSurface& neighbor_surface) {
+            float target_function_at_j = di_target_function<V, true>(ctx, reservoir_being_resampled_sample, neighbor_surface);
+            int M = 1;
+            if (use_confidence_weights)
+                M = di_load(rd, input_reservoir_buffer, neighbor_index_j).M;
+            denom += target_function_at_j * M;
+            if (j == current_neighbor_index)
+                nume = target_function_at_j * M;
+        });
+        return denom == 0.0f ? 0.0f : nume / denom;
+    };
 
     int reused_neighbors_count = local.reuse_neighbor_count;
     int start_index = 0;
@@ -1137,13 +1311,25 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
                 target_function_at_center = di_target_function<V, false>(ctx, neighbor_reservoir.sample, center_pixel_surface);
         }
 
-        bool update_mc = center_pixel_reservoir.M > 0 && center_pixel_reservoir.UCW > 0.0f;
-        float mis_weight = mis.weight<V>(ctx, neighbor_reservoir.M, neighbor_reservoir.sample.target_function, center_pixel_reservoir.M, center_pixel_reservoir.sample.target_function,
-                                         center_pixel_reservoir.sample, target_function_at_center, neighbor_pixel_index, false, valid_neighbors_count, valid_neighbors_M_sum, update_mc,
-                                         neighbor_index == reused_neighbors_count, true, rng);
+        /* ReSTIR_DI_BiasCorrectionWeights (SpatialMISWeight.h): a -D macro in the reference, a launch-time switch here */
+        float mis_weight;
+        if (bias == B2_BIAS_1_OVER_Z)
+            mis_weight = (float)neighbor_reservoir.M;
+        else if (bias == B2_BIAS_MIS_LIKE)
+            mis_weight = use_confidence_weights ? (float)neighbor_reservoir.M : 1.0f;
+        else if (bias == B2_BIAS_MIS_GBH)
+            mis_weight = gbh_weight(neighbor_reservoir.UCW, neighbor_reservoir.sample, neighbor_index);
+        else
+        {
+            bool update_mc = center_pixel_reservoir.M > 0 && center_pixel_reservoir.UCW > 0.0f;
+            mis_weight = mis.weight<V>(ctx, neighbor_reservoir.M, neighbor_reservoir.sample.target_function, center_pixel_reservoir.M, center_pixel_reservoir.sample.target_function,
+                                       center_pixel_reservoir.sample, target_function_at_center, neighbor_pixel_index, false, valid_neighbors_count, valid_neighbors_M_sum, update_mc,
+                                       neighbor_index == reused_neighbors_count, true, rng, bias == B2_BIAS_PAIRWISE_MIS_DEFENSIVE);
+        }
 
         if (out.combine_with(neighbor_reservoir, mis_weight, target_function_at_center, 1.0f, rng))
         {
+            selected_neighbor = neighbor_index;
             if (do_neighbor_target_function_visibility)
                 out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
             else if (neighbor_index == reused_neighbors_count)
@@ -1153,10 +1339,37 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
         }
     }
 
-    out.end_with_normalization(1.0f, 1.0f);
+    /* SpatialNormalizationWeight.h: 1/Z divides by the confidence of the neighbours that could have produced the chosen sample (:64-131),
+     * MIS-like weighs the chosen neighbour against all of them (:133-198); the others put everything into the resampling weights */
+    float normalization_numerator = 1.0f, normalization_denominator = 1.0f;
+    if ((bias == B2_BIAS_1_OVER_Z || bias == B2_BIAS_MIS_LIKE) && !(out.weight_sum <= 0.0f))
+    {
+        const DiSample final_reservoir_sample = out.sample;
+        normalization_denominator = 0.0f;
+        normalization_numerator = bias == B2_BIAS_1_OVER_Z ? 1.0f : 0.0f;
+        for_all_neighbors([&](int j, int neighbor_index_j, DiSurface& neighbor_surface) {
+            float target_function_at_neighbor = di_target_function<V, true>(ctx, final_reservoir_sample, neighbor_surface);
+            if (target_function_at_neighbor > 0.0f)
+            {
+                if (bias == B2_BIAS_1_OVER_Z)
+                    normalization_denominator += (float)di_load(rd, input_reservoir_buffer, neighbor_index_j).M;
+                else
+                {
+                    int M = 1;
+                    if (use_confidence_weights)
+                        M = di_load(rd, input_reservoir_buffer, neighbor_index_j).M;
+                    if (j == selected_neighbor)
+                        normalization_numerator = target_function_at_neighbor;
+                    normalization_denominator += target_function_at_neighbor * M;
+                }
+            }
+        });
+    }
+    out.end_with_normalization(normalization_numerator, normalization_denominator);
 
+    /* the visibility-reuse test at the end of the pass exists for 1/Z, pairwise MIS and its defensive form only (SpatialReuse.h:264-275) */
     bool not_last_spatial_pass = di.common_spatial_pass.number_of_passes - 1 != di.common_spatial_pass.spatial_pass_index;
-    if (di.common_temporal_pass.do_temporal_reuse_pass || not_last_spatial_pass)
+    if (bias != B2_BIAS_MIS_LIKE && bias != B2_BIAS_MIS_GBH && (di.common_temporal_pass.do_temporal_reuse_pass || not_last_spatial_pass))
         di_visibility_test_kill_reservoir(ctx, out, center_pixel_surface.shading_point, center_pixel_surface.primitive_index);
 
     if (di.m_cap > 0)

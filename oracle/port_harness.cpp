@@ -28,7 +28,7 @@ struct Args
     int width = 512, height = 512, spp = 1, bounces = 3;
     int win_x0 = 0, win_y0 = 0, win_x1 = -1, win_y1 = -1;
     int threads = 0;
-    bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false, kat = false;
+    bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false, kat = false, confidence_weights = true;
     int spatial_passes = 1;
     unsigned int seed = 42;
 };
@@ -57,6 +57,7 @@ static Args parse_args(int argc, char** argv)
         else if (k == "--dump-per-sample") a.dump_per_sample = true;
         else if (k == "--no-jitter") a.no_jitter = true;
         else if (k == "--kat") a.kat = true; /* function-level known-answer dump instead of a render (see run_bsdf_kat) */
+        else if (k == "--no-confidence-weights") a.confidence_weights = false;
         else if (k == "--directional-reuse") a.directional_reuse = true; /* use_adaptive_directional_spatial_reuse + the prepass */
         else { std::fprintf(stderr, "unknown argument %s\n", k.c_str()); std::exit(2); }
     }
@@ -107,6 +108,9 @@ struct LutStore
 static unsigned int g_port_faults[B2_FAULT_COUNT] = { 0, 0, 0 };
 static unsigned long long g_port_counters[3] = { 0, 0, 0 }; /* rays, nodes, triangles: traversal steps per ray of the CW8 BVH */
 
+/* "c4b<N>" = c4 with ReSTIR_DI_BiasCorrectionWeights = N (the renderer's variant table, csrc/b2_renderer.cpp) */
+static int bias_correction_of(const std::string& variant) { return variant.rfind("c4b", 0) == 0 ? std::atoi(variant.c_str() + 3) : 4; }
+static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant.rfind("c4b", 0) == 0; }
 static bool g_scene_has_alpha_tested_materials = false; /* = what the renderer passes as B2PT_ALPHA_TEST */
 
 template <class V>
@@ -125,6 +129,7 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
         ctx.counters = &local;
         ctx.faults = g_port_faults;
         ctx.light_presampling = a.variant == "c4p";
+        ctx.bias_correction = bias_correction_of(a.variant);
         ctx.alpha_test = g_scene_has_alpha_tested_materials;
         B2_SET_RAY_BOUNCE(ctx, 0);
 #pragma omp for schedule(dynamic)
@@ -272,6 +277,7 @@ int main(int argc, char** argv)
     rd.render_settings.restir_di_settings.do_fused_spatiotemporal = a.fused;
     rd.render_settings.restir_di_settings.common_spatial_pass.use_adaptive_directional_spatial_reuse = a.directional_reuse ? 1 : 0;
     rd.render_settings.restir_di_settings.common_spatial_pass.number_of_passes = a.spatial_passes;
+    rd.render_settings.restir_di_settings.use_confidence_weights = a.confidence_weights ? 1 : 0;
 
     /* camera */
     std::memcpy(loop.camera.inverse_view, scene.blob.camera.inverse_view, 64);
@@ -432,7 +438,7 @@ int main(int argc, char** argv)
         return 0;
     }
 #endif
-    loop.restir_di = a.variant == "c4" || a.variant == "c4p";
+    loop.restir_di = is_c4(a.variant);
     loop.restir_di_presampling = a.variant == "c4p";
     std::vector<unsigned long long> directional_masks((size_t)a.width * a.height, 0ull);
     std::vector<uint8_t> directional_radius((size_t)a.width * a.height, 0);
@@ -483,7 +489,7 @@ int main(int argc, char** argv)
             for (int index = 0; index < params.number_of_subsets * params.subset_size; index++)
                 restir_di_presample_light<B2VariantC4>(rd, params, (uint32_t)index);
         }
-        else if (a.variant == "c4" || a.variant == "c4p") run_pass<B2VariantC4>(pass, rd, bvh, a);
+        else if (is_c4(a.variant)) run_pass<B2VariantC4>(pass, rd, bvh, a);
 #endif
         else { std::fprintf(stderr, "unknown variant %s\n", a.variant.c_str()); std::exit(2); }
         if (a.dump_per_sample && !a.dump.empty() && pass != B2_PASS_CAMERA_RAYS && pass != B2_PASS_MEGAKERNEL)

@@ -28,6 +28,10 @@ def make_renderer(b2pt, ctx, meta, precise=True):
         r.set(restir_di_do_fused_spatiotemporal=0 if "--no-fused" in meta.get("extra", []) else 1)
     if "--directional-reuse" in meta.get("extra", []):
         r.set(restir_di_use_adaptive_directional_spatial_reuse=1)
+    if "--no-confidence-weights" in meta.get("extra", []):
+        r.set(restir_di_use_confidence_weights=0)
+    if "--spatial-passes" in meta.get("extra", []):
+        r.set(restir_di_number_of_passes=int(meta["extra"][meta["extra"].index("--spatial-passes") + 1]))
     if envmap_of(meta):
         r.set_envmap_file(envmap_of(meta))
     return r

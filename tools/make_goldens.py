@@ -50,6 +50,14 @@ CASES = [
     ("c2_disp_96x54", "c2", "cornell_dispersion_16x9", 96, 54, 3, 6, []),
     ("c3_disp_96x54", "c3", "cornell_dispersion_16x9", 96, 54, 3, 6, []),
     ("c4_disp_96x54_fused", "c4", "cornell_dispersion_16x9", 96, 54, 3, 6, []),
+    # ReSTIR_DI_BiasCorrectionWeights other than pairwise MIS (variants "c4b<N>": 1 = 1/Z, 2 = MIS-like, 3 = generalised balance
+    # heuristic, 5 = defensive pairwise MIS), temporal + spatial passes, with and without confidence weights, one and two spatial passes
+    ("c4b1_96x54_split", "c4b1", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused"]),
+    ("c4b2_synenv_96x54_split", "c4b2", "synthetic_20k", 96, 54, 3, 4, ["--no-fused", "--envmap", "data/sky_128x64.b2env"]),
+    ("c4b3_96x54_split_noconf", "c4b3", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused", "--no-confidence-weights"]),
+    ("c4b3_syn_96x54_split", "c4b3", "synthetic_20k", 96, 54, 2, 4, ["--no-fused"]),
+    ("c4b5_96x54_split2", "c4b5", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused", "--spatial-passes", "2"]),
+    ("c4b5_syn_96x54_split_noconf", "c4b5", "synthetic_20k", 96, 54, 2, 4, ["--no-fused", "--no-confidence-weights"]),
 ]
 EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
 
