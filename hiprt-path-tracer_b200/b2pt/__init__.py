@@ -68,6 +68,7 @@ SETTINGS_OFFSETS = {
     "restir_di_number_of_passes": (_RS + 160 + 24 + 8, "i"),
     "restir_di_reuse_radius": (_RS + 160 + 24 + 12, "i"),
     "restir_di_reuse_neighbor_count": (_RS + 160 + 24 + 20, "i"),
+    "restir_di_disocclusion_reuse_count": (_RS + 160 + 24 + 28, "i"),
     "restir_di_use_adaptive_directional_spatial_reuse": (_RS + 160 + 24 + 49, "B"),
     "restir_di_m_cap": (_RS + 160 + 180, "i"),
     "restir_di_use_confidence_weights": (_RS + 160 + 184, "B"),

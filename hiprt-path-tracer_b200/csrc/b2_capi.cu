@@ -647,14 +647,13 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
             }
         }
     }
-    /* ReSTIR_DI_BiasCorrectionWeights (ReSTIRDIOptions.h:9-16): 1/Z, MIS-like, generalised balance heuristic, pairwise MIS (the default)
-     * and defensive pairwise MIS are built for the temporal and spatial reuse passes; the fused spatiotemporal pass is built for
-     * pairwise MIS only; 1/M does not compile in the reference itself (SpatialReuse.h:237 calls its normalisation with 6 of 7 arguments)
-     * and the two ratio heuristics are not built */
+    /* ReSTIR_DI_BiasCorrectionWeights (ReSTIRDIOptions.h:9-16): 1/Z, MIS-like, generalised balance heuristic, pairwise MIS (the default),
+     * defensive pairwise MIS and the symmetric / asymmetric ratio heuristics are built for the temporal, spatial and fused spatiotemporal
+     * reuse passes; 1/M does not compile in the reference itself (SpatialReuse.h:237 calls its normalisation with 6 of 7 arguments) */
     {
-        const bool built = bias_correction >= 1 && bias_correction <= 5;
+        const bool built = bias_correction >= 1 && bias_correction <= 7;
         const bool reuse_pass = pass == B2_PASS_RESTIR_DI_TEMPORAL || pass == B2_PASS_RESTIR_DI_SPATIAL || pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL;
-        if (reuse_pass && (!built || (pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL && bias_correction != 4)))
+        if (reuse_pass && !built)
         {
             b2_set_error("no precompiled variant of %s with ReSTIR_DI_BiasCorrectionWeights=%d", entry_name, bias_correction);
             return B2PT_ERR_NO_VARIANT;

@@ -665,7 +665,8 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
         /* the ray-delimited ReSTIR DI passes follow the MegaKernel's form: frame-wide phases + the global ray queue on big scenes */
         if (PASS == B2_PASS_RESTIR_DI_INITIAL_CANDIDATES && g.persistent == 3)
             return launch_wavefront_pass<WfInitialCandidates<V>, V>(rd, g, rows, stream);
-        if (PASS == B2_PASS_RESTIR_DI_SPATIOTEMPORAL && g.persistent == 3 && restir_di_spatiotemporal_supported<V>(*rd))
+        /* (pairwise MIS with at most 6 neighbours; anything else runs the pass in one piece, restir_di_spatiotemporal_inplace_pixel) */
+        if (PASS == B2_PASS_RESTIR_DI_SPATIOTEMPORAL && g.persistent == 3 && g.bias_correction == 4 && restir_di_spatiotemporal_supported<V>(*rd))
             return launch_wavefront_pass<WfSpatiotemporalReuse<V>, V>(rd, g, rows, stream);
     }
     if (PASS == B2_PASS_MEGAKERNEL && g.persistent)

@@ -164,11 +164,13 @@ const VariantKey kVariants[] = {
     { "c4", 0, 5, 1, 3, true, false, 4 },
     { "c4p", 0, 5, 1, 3, true, true, 4 }, /* c4 with ReSTIR_DI_DoLightPresampling */
     /* c4 with another ReSTIR_DI_BiasCorrectionWeights (ReSTIRDIOptions.h:9-16): 1/Z, MIS-like, generalised balance heuristic, defensive
-     * pairwise MIS. Temporal + spatial passes only: restir_di_do_fused_spatiotemporal must be 0 */
+     * pairwise MIS, symmetric and asymmetric ratio */
     { "c4b1", 0, 5, 1, 3, true, false, 1 },
     { "c4b2", 0, 5, 1, 3, true, false, 2 },
     { "c4b3", 0, 5, 1, 3, true, false, 3 },
     { "c4b5", 0, 5, 1, 3, true, false, 5 },
+    { "c4b6", 0, 5, 1, 3, true, false, 6 }, /* symmetric ratio */
+    { "c4b7", 0, 5, 1, 3, true, false, 7 }, /* asymmetric ratio */
 };
 
 const VariantKey* find_variant(const std::string& name)
@@ -221,10 +223,6 @@ int resolve_kernels(b2pt_renderer* r)
             { "B2PT_PRECISE", r->precise }, { "B2PT_COUNTERS", r->counters }, { "B2PT_ALPHA_TEST", r->alpha_test ? 1 : 0 },
             { "ReSTIR_DI_BiasCorrectionWeights", v->bias_correction },
         };
-        /* a variant with another bias correction has no fused pass (b2pt_kernel_get would answer NO_VARIANT): the frame loop does not
-         * launch it as long as restir_di_do_fused_spatiotemporal is 0, and says so otherwise */
-        if (pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL && v->bias_correction != 4)
-            continue;
         B2_TRY(b2pt_kernel_get(r->ctx, entry, opts, (int)(sizeof(opts) / sizeof(opts[0])), &r->kernels[pass]));
     }
     r->kernels_stale = false;

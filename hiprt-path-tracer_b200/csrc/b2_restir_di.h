@@ -37,7 +37,26 @@ B2_HD bool restir_gi_coalesced_spatial_reuse(const b2pt_render_data& rd)
 }
 
 /* ReSTIR_DI_BiasCorrectionWeights (HostDeviceCommon/KernelOptions/ReSTIRDIOptions.h:9-16) */
-enum { B2_BIAS_1_OVER_M = 0, B2_BIAS_1_OVER_Z = 1, B2_BIAS_MIS_LIKE = 2, B2_BIAS_MIS_GBH = 3, B2_BIAS_PAIRWISE_MIS = 4, B2_BIAS_PAIRWISE_MIS_DEFENSIVE = 5 };
+enum { B2_BIAS_1_OVER_M = 0, B2_BIAS_1_OVER_Z = 1, B2_BIAS_MIS_LIKE = 2, B2_BIAS_MIS_GBH = 3, B2_BIAS_PAIRWISE_MIS = 4, B2_BIAS_PAIRWISE_MIS_DEFENSIVE = 5,
+       B2_BIAS_SYMMETRIC_RATIO = 6, B2_BIAS_ASYMMETRIC_RATIO = 7 };
+
+/* MISWeightsCommon.h:49-64: min(a / b, b / a) ^ beta, 0 when either target function is */
+B2_HD float ratio_mis_difference_function(float target_function_at_center, float target_function_from_i, float exponent)
+{
+    if (target_function_at_center == 0.0f || target_function_from_i == 0.0f)
+        return 0.0f;
+    float ratio = b2_min(target_function_at_center / target_function_from_i, target_function_from_i / target_function_at_center);
+    if (exponent == 2.0f)
+        return ratio * ratio;
+    if (exponent == 3.0f)
+        return ratio * ratio * ratio;
+    if (exponent == 4.0f)
+    {
+        float ratio2 = ratio * ratio;
+        return ratio2 * ratio2;
+    }
+    return b2f_pow(ratio, exponent);
+}
 
 struct SpatialLocal
 {
@@ -1099,6 +1118,45 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
             temporal_neighbor_resampling_mis_weight = use_confidence_weights ? (float)temporal_neighbor_reservoir.M : 1.0f;
         else if (bias == B2_BIAS_MIS_GBH)
             temporal_neighbor_resampling_mis_weight = gbh_weight(temporal_neighbor_reservoir.sample, 0);
+        else if (bias == B2_BIAS_SYMMETRIC_RATIO || bias == B2_BIAS_ASYMMETRIC_RATIO)
+        {
+            /* symmetric ratio (TemporalMISWeight.h:367-462) and asymmetric ratio (:464-595); no guard on the divisions, as there */
+            const bool asymmetric = bias == B2_BIAS_ASYMMETRIC_RATIO;
+            const float beta = di.symmetric_ratio_mis_weights_beta_exponent;
+            float target_function_neighbor_sample_at_neighbor = temporal_neighbor_reservoir.sample.target_function;
+            float temporal_neighbor_M = use_confidence_weights ? (float)temporal_neighbor_reservoir.M : 1.0f;
+            float center_reservoir_M = use_confidence_weights ? (float)initial_candidates_reservoir.M : 1.0f;
+            float neighbors_confidence_sum = use_confidence_weights ? temporal_neighbor_M : 1.0f;
+
+            float difference_function = ratio_mis_difference_function(target_function_at_center, target_function_neighbor_sample_at_neighbor, beta);
+            float nume_mi = difference_function * temporal_neighbor_M;
+            float denom_mi = center_reservoir_M + neighbors_confidence_sum * difference_function;
+            if (asymmetric && !(target_function_at_center <= target_function_neighbor_sample_at_neighbor))
+                denom_mi = center_reservoir_M + neighbors_confidence_sum;
+            float mi = nume_mi / denom_mi;
+
+            float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, initial_candidates_reservoir.sample, temporal_neighbor_surface);
+            float target_function_center_sample_at_center = initial_candidates_reservoir.sample.target_function;
+            float difference_function_mc = ratio_mis_difference_function(target_function_center_sample_at_neighbor, target_function_center_sample_at_center, beta);
+            if (asymmetric)
+            {
+                float nume_mc = difference_function_mc * temporal_neighbor_M;
+                float denom_mc = center_reservoir_M + neighbors_confidence_sum * difference_function_mc;
+                if (!(target_function_center_sample_at_center <= target_function_center_sample_at_neighbor))
+                    denom_mc = center_reservoir_M + neighbors_confidence_sum;
+                mc += nume_mc / denom_mc;
+            }
+            else
+            {
+                float nume_mc = center_reservoir_M;
+                float denom_mc = center_reservoir_M + neighbors_confidence_sum * difference_function_mc;
+                float confidence_weights_multiplier = 1.0f;
+                if (use_confidence_weights)
+                    confidence_weights_multiplier = neighbors_confidence_sum == 0.0f ? 0.0f : temporal_neighbor_M / neighbors_confidence_sum;
+                mc += confidence_weights_multiplier * nume_mc / denom_mc;
+            }
+            temporal_neighbor_resampling_mis_weight = mi;
+        }
         else
         {
             /* pairwise MIS (TemporalMISWeight.h:163-254) and its defensive form (:256-365) */
@@ -1150,6 +1208,8 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
         else
             initial_candidates_mis_weight = (1.0f + mc) * 0.5f;
     }
+    else if (bias == B2_BIAS_ASYMMETRIC_RATIO)
+        initial_candidates_mis_weight = mc == 0.0f ? 1.0f : 1.0f - mc;
     else
         initial_candidates_mis_weight = mc == 0.0f ? 1.0f : mc;
     if (out.combine_with(initial_candidates_reservoir, initial_candidates_mis_weight, initial_candidates_reservoir.sample.target_function, 1.0f, rng))
@@ -1319,6 +1379,56 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
             mis_weight = use_confidence_weights ? (float)neighbor_reservoir.M : 1.0f;
         else if (bias == B2_BIAS_MIS_GBH)
             mis_weight = gbh_weight(neighbor_reservoir.UCW, neighbor_reservoir.sample, neighbor_index);
+        else if (bias == B2_BIAS_SYMMETRIC_RATIO || bias == B2_BIAS_ASYMMETRIC_RATIO)
+        {
+            /* symmetric ratio (SpatialMISWeight.h:370-475) and asymmetric ratio (:477-599); mis.mc is the canonical sample's running weight */
+            const bool asymmetric = bias == B2_BIAS_ASYMMETRIC_RATIO;
+            const float beta = di.symmetric_ratio_mis_weights_beta_exponent;
+            bool update_mc = center_pixel_reservoir.M > 0 && center_pixel_reservoir.UCW > 0.0f;
+            if (neighbor_index == reused_neighbors_count)
+                mis_weight = mis.mc == 0.0f ? 1.0f : (asymmetric ? 1.0f - mis.mc : mis.mc);
+            else
+            {
+                float target_function_neighbor_sample_at_neighbor = neighbor_reservoir.sample.target_function;
+                float target_function_center_sample_at_center = center_pixel_reservoir.sample.target_function;
+                float reservoir_resampled_M = use_confidence_weights ? (float)neighbor_reservoir.M : 1.0f;
+                float center_reservoir_M = use_confidence_weights ? (float)center_pixel_reservoir.M : 1.0f;
+                float neighbors_confidence_sum = use_confidence_weights ? (float)valid_neighbors_M_sum : (float)valid_neighbors_count;
+
+                float difference_function = ratio_mis_difference_function(target_function_at_center, target_function_neighbor_sample_at_neighbor, beta);
+                float nume_mi = difference_function * reservoir_resampled_M;
+                float denom_mi = center_reservoir_M + neighbors_confidence_sum * difference_function;
+                if (asymmetric && !(target_function_at_center <= target_function_neighbor_sample_at_neighbor))
+                    denom_mi = center_reservoir_M + neighbors_confidence_sum;
+                mis_weight = nume_mi / denom_mi;
+
+                if (update_mc)
+                {
+                    DiSurface neighbor_pixel_surface = get_pixel_surface<V>(rd, neighbor_pixel_index, false, rng);
+                    float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, center_pixel_reservoir.sample, neighbor_pixel_surface);
+                    float difference_function_mc = ratio_mis_difference_function(target_function_center_sample_at_neighbor, target_function_center_sample_at_center, beta);
+                    if (asymmetric)
+                    {
+                        float nume_mc = difference_function_mc * reservoir_resampled_M;
+                        float denom_mc = center_reservoir_M + neighbors_confidence_sum * difference_function_mc;
+                        if (!(target_function_center_sample_at_center <= target_function_center_sample_at_neighbor))
+                            denom_mc = center_reservoir_M + neighbors_confidence_sum;
+                        mis.mc += nume_mc / denom_mc;
+                    }
+                    else
+                    {
+                        float nume_mc = center_reservoir_M;
+                        float denom_mc = center_reservoir_M + neighbors_confidence_sum * difference_function_mc;
+                        float confidence_weights_multiplier;
+                        if (use_confidence_weights)
+                            confidence_weights_multiplier = neighbors_confidence_sum == 0.0f ? 0.0f : reservoir_resampled_M / neighbors_confidence_sum;
+                        else
+                            confidence_weights_multiplier = 1.0f / (float)valid_neighbors_count;
+                        mis.mc += confidence_weights_multiplier * nume_mc / denom_mc;
+                    }
+                }
+            }
+        }
         else
         {
             bool update_mc = center_pixel_reservoir.M > 0 && center_pixel_reservoir.UCW > 0.0f;
@@ -1657,9 +1767,286 @@ B2_HD void restir_di_spatiotemporal_phase_c(const Ctx& ctx, uint32_t x, uint32_t
     di_store(rd, di.spatial_pass.output_reservoirs, center_pixel_index, out);
 }
 
+/* ---- the fused pass in one piece -------------------------------------------------------------------------------------------------
+ * FusedSpatiotemporalReuse.h:169-563 followed top to bottom, rays traced where they occur. Takes any number of neighbours and every
+ * ReSTIR_DI_BiasCorrectionWeights but 1/M; the phase-cut form above is the fast path of the default (pairwise MIS, <= 6 neighbours).
+ * What the reference does here and is mirrored as written:
+ *   - the weight / normalisation functions that walk over all neighbours again (generalised balance heuristic, 1/Z, MIS-like:
+ *     SpatiotemporalMISWeight.h:78-121, SpatiotemporalNormalizationWeight.h:98-131,170-215) draw the neighbour positions from the
+ *     kernel's main generator where it stands, not from the spatial-neighbours seed: they visit OTHER pixels than the ones resampled;
+ *   - temporal_neighbor_surface stays default-constructed (zero normals: every target function on it is 0) when there is no temporal
+ *     neighbour or its reservoir is empty (:73-104);
+ *   - the asymmetric-ratio weights of this pass are a copy of the symmetric ones (SpatiotemporalMISWeight.h:449-555), and both rebuild
+ *     the neighbour's surface from the CURRENT G-buffer (:389) where pairwise MIS takes the previous frame's when asked to (:183). */
+template <class V>
+B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;
+    uint32_t center_pixel_index;
+    if (!restir_pass_prologue<V>(rd, x, y, center_pixel_index))
+        return;
+    if (!rd.aux_buffers.pixel_active[center_pixel_index] || rd.g_buffer.first_hit_prim_index[center_pixel_index] == -1)
+        return;
+
+    unsigned int seed = rd.render_settings.freeze_random ? wang_hash(center_pixel_index + 1) : wang_hash(((center_pixel_index + 1) * (rd.render_settings.sample_number + 1)) ^ rd.random_number);
+    Rng rng = make_rng(seed);
+    SpatialLocal local = spatial_local_from(rd);
+    local.rng_seed = rng.next_u32();
+
+    if (di.common_temporal_pass.temporal_buffer_clear_requested)
+    {
+        DiReservoir empty;
+        empty.init();
+        di_store(rd, di.temporal_pass.input_reservoirs, (int)center_pixel_index, empty);
+    }
+
+    DiSurface center_pixel_surface = get_pixel_surface<V>(rd, (int)center_pixel_index, false, rng);
+    const bool prev_gbuffer = use_prev_frame_g_buffer<V>(rd.render_settings);
+    const int bias = ctx.bias_correction;
+    const bool use_confidence_weights = di.use_confidence_weights != 0;
+
+    /* load_spatiotemporal_neighbor_data (:73-104) */
+    DiReservoir temporal_neighbor_reservoir;
+    temporal_neighbor_reservoir.init();
+    DiSurface temporal_neighbor_surface;
+    temporal_neighbor_surface.material = unpack_material(PackedMat{});
+    temporal_neighbor_surface.ray_volume_state.init();
+    temporal_neighbor_surface.primitive_index = -1;
+    temporal_neighbor_surface.view_direction = temporal_neighbor_surface.shading_normal = temporal_neighbor_surface.geometric_normal = temporal_neighbor_surface.shading_point = v3(0.0f, 0.0f, 0.0f);
+    Int3 temporal = find_temporal_neighbor_index<V>(rd, load_v3(rd.g_buffer.primary_hit_position, center_pixel_index), center_pixel_surface.shading_normal, (int)center_pixel_index, rng);
+    if (!(temporal.x == -1 || rd.render_settings.freeze_random))
+    {
+        temporal_neighbor_reservoir = di_load(rd, di.temporal_pass.input_reservoirs, temporal.x);
+        if (temporal_neighbor_reservoir.M != 0)
+            temporal_neighbor_surface = get_pixel_surface<V>(rd, temporal.x, prev_gbuffer, rng);
+    }
+    if ((temporal.x == -1 || temporal_neighbor_reservoir.M <= 1) && di.common_spatial_pass.do_disocclusion_reuse_boost)
+        local.reuse_neighbor_count = di.common_spatial_pass.disocclusion_reuse_count;
+
+    setup_adaptive_directional_spatial_reuse(rd, local, center_pixel_index, rng);
+
+    int selected_neighbor = 0;
+    int neighbor_heuristics_cache = 0;
+    int valid_neighbors_count = 0;
+    int valid_neighbors_M_sum = 0;
+    count_valid_neighbors(rd, local, center_pixel_surface, (int)center_pixel_index, temporal.y, temporal.z, prev_gbuffer, di.spatial_pass.input_reservoirs, valid_neighbors_count,
+                          valid_neighbors_M_sum, neighbor_heuristics_cache);
+    if (temporal.x != -1 && temporal_neighbor_reservoir.M > 0)
+    {
+        valid_neighbors_count++;
+        valid_neighbors_M_sum += temporal_neighbor_reservoir.M;
+    }
+
+    DiReservoir out;
+    out.init();
+    DiReservoir initial_candidates_reservoir = di_load(rd, di.initial_candidates.output_reservoirs, (int)center_pixel_index);
+    const bool update_mc = initial_candidates_reservoir.M > 0 && initial_candidates_reservoir.UCW > 0.0f;
+    PairwiseMis mis;
+    mis.mc = 0.0f;
+
+    /* the "all neighbours again" walk of the balance heuristic and of the 1/Z / MIS-like normalisations; `evaluate(j, M of neighbour j,
+     * its surface)` for every neighbour that is inside the viewport and similar enough, the centre pixel (j = neighbour count) last */
+    auto for_all_spatial_neighbors = [&](bool surfaces_from_previous_frame, auto&& evaluate) {
+        for (int j = 0; j < local.reuse_neighbor_count + 1; j++)
+        {
+            int neighbor_index_j = (int)center_pixel_index;
+            if (j != local.reuse_neighbor_count)
+            {
+                neighbor_index_j = get_spatial_neighbor_pixel_index(rd, local, j, temporal.y, temporal.z, rng);
+                if (neighbor_index_j == -1)
+                    continue;
+                if (!check_neighbor_similarity_heuristics(rd, neighbor_index_j, (int)center_pixel_index, center_pixel_surface.shading_point, normal_for_rejection_heuristic(rd, center_pixel_surface), prev_gbuffer))
+                    continue;
+            }
+            DiSurface neighbor_surface = center_pixel_surface;
+            if (j != local.reuse_neighbor_count)
+                neighbor_surface = get_pixel_surface<V>(rd, neighbor_index_j, surfaces_from_previous_frame, rng);
+            int M = j == local.reuse_neighbor_count ? initial_candidates_reservoir.M : di_load(rd, di.spatial_pass.input_reservoirs, neighbor_index_j).M;
+            evaluate(j, M, neighbor_surface);
+        }
+    };
+    /* SpatiotemporalMISWeight.h:59-137; current_neighbor: 0 = the temporal neighbour, j + 1 = spatial neighbour j */
+    auto gbh_weight = [&](float reservoir_being_resampled_UCW, const DiSample& reservoir_being_resampled_sample, int current_neighbor) {
+        if (reservoir_being_resampled_UCW <= 0.0f)
+            return 1.0f;
+        float nume = 0.0f, denom = 0.0f;
+        for_all_spatial_neighbors(prev_gbuffer, [&](int j, int M_j, DiSurface& neighbor_surface) {
+            float target_function_at_j = di_target_function<V, true>(ctx, reservoir_being_resampled_sample, neighbor_surface);
+            int M = use_confidence_weights ? M_j : 1;
+            denom += target_function_at_j * M;
+            if (j + 1 == current_neighbor)
+                nume = target_function_at_j * M;
+        });
+        float target_function_at_temporal_neighbor = di_target_function<V, true>(ctx, reservoir_being_resampled_sample, temporal_neighbor_surface);
+        int M = use_confidence_weights ? temporal_neighbor_reservoir.M : 1;
+        denom += target_function_at_temporal_neighbor * M;
+        if (current_neighbor == 0)
+            nume = target_function_at_temporal_neighbor * M;
+        return denom == 0.0f ? 0.0f : nume / denom;
+    };
+    /* one resampling weight: `resampled` seen from the centre pixel has target_function_at_center */
+    auto resampling_weight = [&](const DiReservoir& resampled, float target_function_at_center, int neighbor_pixel_index, int current_neighbor, bool canonical) {
+        if (bias == B2_BIAS_1_OVER_Z)
+            return (float)resampled.M;
+        if (bias == B2_BIAS_MIS_LIKE)
+            return use_confidence_weights ? (float)resampled.M : 1.0f;
+        if (bias == B2_BIAS_MIS_GBH)
+            return gbh_weight(resampled.UCW, resampled.sample, current_neighbor);
+        if (bias == B2_BIAS_SYMMETRIC_RATIO || bias == B2_BIAS_ASYMMETRIC_RATIO)
+        {
+            /* SpatiotemporalMISWeight.h:341-447 (= :449-555) */
+            if (canonical)
+                return mis.mc == 0.0f ? 1.0f : mis.mc;
+            const float beta = di.symmetric_ratio_mis_weights_beta_exponent;
+            float target_function_neighbor_sample_at_neighbor = resampled.sample.target_function;
+            float target_function_center_sample_at_center = initial_candidates_reservoir.sample.target_function;
+            float reservoir_resampled_M = use_confidence_weights ? (float)resampled.M : 1.0f;
+            float center_reservoir_M = use_confidence_weights ? (float)initial_candidates_reservoir.M : 1.0f;
+            float neighbors_confidence_sum = use_confidence_weights ? (float)valid_neighbors_M_sum : (float)valid_neighbors_count;
+            float difference_function = ratio_mis_difference_function(target_function_at_center, target_function_neighbor_sample_at_neighbor, beta);
+            float nume_mi = difference_function * reservoir_resampled_M;
+            float denom_mi = center_reservoir_M + neighbors_confidence_sum * difference_function;
+            float mi = nume_mi / denom_mi;
+            if (update_mc)
+            {
+                DiSurface neighbor_pixel_surface = get_pixel_surface<V>(rd, neighbor_pixel_index, false, rng);
+                float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, initial_candidates_reservoir.sample, neighbor_pixel_surface);
+                float nume_mc = center_reservoir_M;
+                float denom_mc = center_reservoir_M + neighbors_confidence_sum * ratio_mis_difference_function(target_function_center_sample_at_neighbor, target_function_center_sample_at_center, beta);
+                float confidence_weights_multiplier;
+                if (use_confidence_weights)
+                    confidence_weights_multiplier = neighbors_confidence_sum == 0.0f ? 0.0f : reservoir_resampled_M / neighbors_confidence_sum;
+                else
+                    confidence_weights_multiplier = 1.0f / (float)valid_neighbors_count;
+                mis.mc += confidence_weights_multiplier * nume_mc / denom_mc;
+            }
+            return mi;
+        }
+        return mis.weight<V>(ctx, resampled.M, resampled.sample.target_function, initial_candidates_reservoir.M, initial_candidates_reservoir.sample.target_function,
+                             initial_candidates_reservoir.sample, target_function_at_center, neighbor_pixel_index, prev_gbuffer, valid_neighbors_count, valid_neighbors_M_sum, update_mc,
+                             canonical, false, rng, bias == B2_BIAS_PAIRWISE_MIS_DEFENSIVE);
+    };
+
+    if (temporal.x != -1 && temporal_neighbor_reservoir.M > 0)
+    {
+        float target_function_at_center = 0.0f;
+        if (temporal_neighbor_reservoir.UCW > 0.0f)
+            target_function_at_center = di_target_function<V, true>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface);
+        float w = resampling_weight(temporal_neighbor_reservoir, target_function_at_center, temporal.x, 0, false);
+        if (out.combine_with(temporal_neighbor_reservoir, w, target_function_at_center, 1.0f, rng))
+        {
+            selected_neighbor = 0;
+            out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+        }
+    }
+
+    Rng spatial_neighbors_rng = make_rng(local.rng_seed);
+    int reused_neighbors_count = local.reuse_neighbor_count;
+    int start_index = 0;
+    if (valid_neighbors_M_sum == 0)
+        start_index = reused_neighbors_count;
+    for (int spatial_neighbor_index = start_index; spatial_neighbor_index < reused_neighbors_count + 1; spatial_neighbor_index++)
+    {
+        if (spatial_neighbor_index < reused_neighbors_count && reused_neighbors_count <= 32)
+            if ((neighbor_heuristics_cache & (1 << spatial_neighbor_index)) == 0)
+            {
+                spatial_neighbor_advance_rng(rd, spatial_neighbors_rng);
+                continue;
+            }
+
+        int neighbor_pixel_index = -1;
+        if (spatial_neighbor_index == reused_neighbors_count)
+            neighbor_pixel_index = (int)center_pixel_index;
+        else
+            neighbor_pixel_index = get_spatial_neighbor_pixel_index(rd, local, spatial_neighbor_index, temporal.y, temporal.z, spatial_neighbors_rng);
+        if (neighbor_pixel_index == -1)
+            continue;
+
+        if (spatial_neighbor_index < reused_neighbors_count && reused_neighbors_count > 32)
+            if (!check_neighbor_similarity_heuristics(rd, neighbor_pixel_index, (int)center_pixel_index, center_pixel_surface.shading_point, normal_for_rejection_heuristic(rd, center_pixel_surface), prev_gbuffer))
+                continue;
+
+        const bool canonical = spatial_neighbor_index == reused_neighbors_count;
+        DiReservoir neighbor_reservoir = canonical ? initial_candidates_reservoir : di_load(rd, di.spatial_pass.input_reservoirs, neighbor_pixel_index);
+
+        /* ReSTIR_DI_SpatialTargetFunctionVisibility = FALSE: do_include_spatial_visibility_term_or_not is false for every neighbour */
+        float target_function_at_center = 0.0f;
+        if (neighbor_reservoir.UCW > 0.0f)
+        {
+            if (canonical)
+                target_function_at_center = neighbor_reservoir.sample.target_function;
+            else
+                target_function_at_center = di_target_function<V, false>(ctx, neighbor_reservoir.sample, center_pixel_surface);
+        }
+        (void)get_pixel_surface<V>(rd, neighbor_pixel_index, prev_gbuffer, rng); /* :397, read by ReSTIR GI only; its wavelength draw stays */
+
+        float mis_weight = resampling_weight(neighbor_reservoir, target_function_at_center, neighbor_pixel_index, spatial_neighbor_index + 1, canonical);
+        if (out.combine_with(neighbor_reservoir, mis_weight, target_function_at_center, 1.0f, rng))
+        {
+            selected_neighbor = spatial_neighbor_index + 1;
+            if (canonical)
+                out.sample.or_flags((int)(neighbor_reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED));
+            else
+                out.sample.flags &= ~(uint32_t)B2_DI_FLAGS_UNOCCLUDED;
+        }
+    }
+
+    /* SpatiotemporalNormalizationWeight.h: 1/Z (:84-147), MIS-like (:149-229); MIS-like rebuilds the surfaces from the current G-buffer (:189) */
+    float normalization_numerator = 1.0f, normalization_denominator = 1.0f;
+    if ((bias == B2_BIAS_1_OVER_Z || bias == B2_BIAS_MIS_LIKE) && !(out.weight_sum <= 0.0f))
+    {
+        const DiSample final_reservoir_sample = out.sample;
+        normalization_denominator = 0.0f;
+        normalization_numerator = bias == B2_BIAS_1_OVER_Z ? 1.0f : 0.0f;
+        for_all_spatial_neighbors(bias == B2_BIAS_1_OVER_Z ? prev_gbuffer : false, [&](int j, int M_j, DiSurface& neighbor_surface) {
+            float target_function_at_neighbor = di_target_function<V, true>(ctx, final_reservoir_sample, neighbor_surface);
+            if (target_function_at_neighbor > 0.0f)
+            {
+                if (bias == B2_BIAS_1_OVER_Z)
+                    normalization_denominator += (float)M_j;
+                else
+                {
+                    int M = use_confidence_weights ? M_j : 1;
+                    if (j + 1 == selected_neighbor)
+                        normalization_numerator += target_function_at_neighbor;
+                    normalization_denominator += target_function_at_neighbor * M;
+                }
+            }
+        });
+        float target_function_at_temporal_neighbor = di_target_function<V, true>(ctx, final_reservoir_sample, temporal_neighbor_surface);
+        if (bias == B2_BIAS_1_OVER_Z)
+        {
+            if (target_function_at_temporal_neighbor > 0.0f)
+                normalization_denominator += (float)temporal_neighbor_reservoir.M;
+        }
+        else
+        {
+            if (selected_neighbor == 0)
+                normalization_numerator += target_function_at_temporal_neighbor;
+            int temporal_M = use_confidence_weights ? temporal_neighbor_reservoir.M : 1;
+            normalization_denominator += target_function_at_temporal_neighbor * temporal_M;
+        }
+    }
+    out.end_with_normalization(normalization_numerator, normalization_denominator);
+
+    if (bias != B2_BIAS_MIS_LIKE && bias != B2_BIAS_MIS_GBH &&
+        (di.common_temporal_pass.do_temporal_reuse_pass || di.common_spatial_pass.number_of_passes - 1 != di.common_spatial_pass.spatial_pass_index))
+        di_visibility_test_kill_reservoir(ctx, out, center_pixel_surface.shading_point, center_pixel_surface.primitive_index);
+
+    if (di.m_cap > 0)
+        out.M = b2_min(out.M, di.m_cap);
+    di_store(rd, di.spatial_pass.output_reservoirs, (int)center_pixel_index, out);
+}
+
 template <class V>
 B2_HD void restir_di_spatiotemporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
 {
+    if (ctx.bias_correction != B2_BIAS_PAIRWISE_MIS || !restir_di_spatiotemporal_supported<V>(*ctx.rd))
+    {
+        restir_di_spatiotemporal_inplace_pixel<V>(ctx, x, y);
+        return;
+    }
     DiSpatiotemporalState st;
     RayRequest rays[B2_ST_RAYS];
     B2Hit results[B2_ST_RAYS];

@@ -155,9 +155,10 @@ int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
  * render_settings.do_alpha_testing / alpha_testing_indirect_bounce). A host sets it when its scene has such a material
  * (RenderBuffers::material_opaque holds a 0); scenes without one keep the shorter traversal. The random numbers of the test come
  * from a per-ray generator, not from the path's (see csrc/b2_bvh.h): images agree with the reference's statistically.
- * {"ReSTIR_DI_BiasCorrectionWeights", N} (ReSTIRDIOptions.h:9-16,120): "ReSTIR_DI_TemporalReuse" and "ReSTIR_DI_SpatialReuse" are
- * served for N = 1 (1/Z), 2 (MIS-like), 3 (generalised balance heuristic), 4 (pairwise MIS, the default) and 5 (defensive pairwise
- * MIS); "ReSTIR_DI_SpatiotemporalReuse" for 4 only. Anything else answers B2PT_ERR_NO_VARIANT. */
+ * {"ReSTIR_DI_BiasCorrectionWeights", N} (ReSTIRDIOptions.h:9-16,120): "ReSTIR_DI_TemporalReuse", "ReSTIR_DI_SpatialReuse" and
+ * "ReSTIR_DI_SpatiotemporalReuse" are served for N = 1 (1/Z), 2 (MIS-like), 3 (generalised balance heuristic), 4 (pairwise MIS, the
+ * default), 5 (defensive pairwise MIS), 6 (symmetric ratio) and 7 (asymmetric ratio); 0 (1/M, which the reference itself does not
+ * compile) answers B2PT_ERR_NO_VARIANT. */
 typedef struct
 {
     const char* name;
@@ -234,8 +235,8 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
  * (2) headless renderer (host mirror of GPURenderer, CPURenderer pass order)
  * ------------------------------------------------------------------------------------------------------------ */
 
-/* variant: "c1" | "c2" | "c3" | "c4" | "c4p" (= c4 + ReSTIR DI light presampling) | "c4b1" "c4b2" "c4b3" "c4b5" (= c4 with
- * ReSTIR_DI_BiasCorrectionWeights 1 / 2 / 3 / 5: temporal + spatial passes, restir_di_do_fused_spatiotemporal must be 0)
+/* variant: "c1" | "c2" | "c3" | "c4" | "c4p" (= c4 + ReSTIR DI light presampling) | "c4b1" "c4b2" "c4b3" "c4b5" "c4b6" "c4b7" (= c4 with
+ * ReSTIR_DI_BiasCorrectionWeights 1 / 2 / 3 / 5 / 6 / 7)
  * (see b2_kernels_body.h); precise: 1 = parity flavour, 0 = fast flavour */
 int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* variant, int precise, b2pt_renderer** out_renderer);
 int b2pt_renderer_destroy(b2pt_renderer* renderer);

@@ -29,7 +29,7 @@ struct Args
     int win_x0 = 0, win_y0 = 0, win_x1 = -1, win_y1 = -1;
     int threads = 0;
     bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false, kat = false, confidence_weights = true;
-    int spatial_passes = 1;
+    int spatial_passes = 1, neighbors = -1;
     unsigned int seed = 42;
 };
 
@@ -57,6 +57,7 @@ static Args parse_args(int argc, char** argv)
         else if (k == "--dump-per-sample") a.dump_per_sample = true;
         else if (k == "--no-jitter") a.no_jitter = true;
         else if (k == "--kat") a.kat = true; /* function-level known-answer dump instead of a render (see run_bsdf_kat) */
+        else if (k == "--neighbors") a.neighbors = std::atoi(next());
         else if (k == "--no-confidence-weights") a.confidence_weights = false;
         else if (k == "--directional-reuse") a.directional_reuse = true; /* use_adaptive_directional_spatial_reuse + the prepass */
         else { std::fprintf(stderr, "unknown argument %s\n", k.c_str()); std::exit(2); }
@@ -278,6 +279,11 @@ int main(int argc, char** argv)
     rd.render_settings.restir_di_settings.common_spatial_pass.use_adaptive_directional_spatial_reuse = a.directional_reuse ? 1 : 0;
     rd.render_settings.restir_di_settings.common_spatial_pass.number_of_passes = a.spatial_passes;
     rd.render_settings.restir_di_settings.use_confidence_weights = a.confidence_weights ? 1 : 0;
+    if (a.neighbors >= 0)
+    {
+        rd.render_settings.restir_di_settings.common_spatial_pass.reuse_neighbor_count = a.neighbors;
+        rd.render_settings.restir_di_settings.common_spatial_pass.disocclusion_reuse_count = a.neighbors;
+    }
 
     /* camera */
     std::memcpy(loop.camera.inverse_view, scene.blob.camera.inverse_view, 64);

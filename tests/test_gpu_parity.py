@@ -30,6 +30,9 @@ def make_renderer(b2pt, ctx, meta, precise=True):
         r.set(restir_di_use_adaptive_directional_spatial_reuse=1)
     if "--no-confidence-weights" in meta.get("extra", []):
         r.set(restir_di_use_confidence_weights=0)
+    if "--neighbors" in meta.get("extra", []):
+        n = int(meta["extra"][meta["extra"].index("--neighbors") + 1])
+        r.set(restir_di_reuse_neighbor_count=n, restir_di_disocclusion_reuse_count=n)
     if "--spatial-passes" in meta.get("extra", []):
         r.set(restir_di_number_of_passes=int(meta["extra"][meta["extra"].index("--spatial-passes") + 1]))
     if envmap_of(meta):

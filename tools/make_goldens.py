@@ -51,13 +51,27 @@ CASES = [
     ("c3_disp_96x54", "c3", "cornell_dispersion_16x9", 96, 54, 3, 6, []),
     ("c4_disp_96x54_fused", "c4", "cornell_dispersion_16x9", 96, 54, 3, 6, []),
     # ReSTIR_DI_BiasCorrectionWeights other than pairwise MIS (variants "c4b<N>": 1 = 1/Z, 2 = MIS-like, 3 = generalised balance
-    # heuristic, 5 = defensive pairwise MIS), temporal + spatial passes, with and without confidence weights, one and two spatial passes
+    # heuristic, 5 = defensive pairwise MIS, 6 / 7 below), temporal + spatial passes, with and without confidence weights, one and two spatial passes
     ("c4b1_96x54_split", "c4b1", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused"]),
     ("c4b2_synenv_96x54_split", "c4b2", "synthetic_20k", 96, 54, 3, 4, ["--no-fused", "--envmap", "data/sky_128x64.b2env"]),
     ("c4b3_96x54_split_noconf", "c4b3", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused", "--no-confidence-weights"]),
     ("c4b3_syn_96x54_split", "c4b3", "synthetic_20k", 96, 54, 2, 4, ["--no-fused"]),
     ("c4b5_96x54_split2", "c4b5", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused", "--spatial-passes", "2"]),
     ("c4b5_syn_96x54_split_noconf", "c4b5", "synthetic_20k", 96, 54, 2, 4, ["--no-fused", "--no-confidence-weights"]),
+    # 6 = symmetric ratio, 7 = asymmetric ratio
+    ("c4b6_96x54_split", "c4b6", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused"]),
+    ("c4b6_synenv_96x54_split_noconf", "c4b6", "synthetic_20k", 96, 54, 2, 4, ["--no-fused", "--no-confidence-weights", "--envmap", "data/sky_128x64.b2env"]),
+    ("c4b7_96x54_split2_noconf", "c4b7", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused", "--no-confidence-weights", "--spatial-passes", "2"]),
+    ("c4b7_syn_96x54_split", "c4b7", "synthetic_20k", 96, 54, 2, 4, ["--no-fused"]),
+    # the fused spatiotemporal pass with those weights, and with more neighbours than its phase-cut form holds (both run the pass in
+    # one piece, restir_di_spatiotemporal_inplace_pixel)
+    ("c4b1_96x54_fused", "c4b1", "cornell_pbr_16x9", 96, 54, 3, 4, []),
+    ("c4b2_synenv_96x54_fused", "c4b2", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
+    ("c4b3_96x54_fused_noconf", "c4b3", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-confidence-weights"]),
+    ("c4b5_syn_96x54_directional_fused", "c4b5", "synthetic_20k", 96, 54, 3, 4, ["--directional-reuse"]),
+    ("c4b6_96x54_fused", "c4b6", "cornell_pbr_16x9", 96, 54, 3, 4, []),
+    ("c4_96x54_fused_9neighbors", "c4", "cornell_pbr_16x9", 96, 54, 3, 4, ["--neighbors", "9"]),
+    ("c4b1_synenv_96x54_fused_12neighbors", "c4b1", "synthetic_20k", 96, 54, 2, 4, ["--neighbors", "12", "--envmap", "data/sky_128x64.b2env"]),
 ]
 EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
 
