@@ -145,6 +145,7 @@ struct b2pt_kernel
     int precise = 1;           /* codegen flavour of the unit the entry comes from */
     int alpha_test = 0;        /* B2PT_ALPHA_TEST: candidate hits on non-opaque materials go through the alpha test */
     int bias_correction = 4;   /* ReSTIR_DI_BiasCorrectionWeights */
+    int restir_options = 4 | 8; /* B2_DI_OPT_* bits: the four ReSTIR DI visibility macros, at the reference's defaults */
 };
 
 int b2_ctx_device(b2pt_ctx* ctx) { return ctx ? ctx->device : 0; }
@@ -578,9 +579,7 @@ static const MacroDefault kFixedMacros[] = {
     { "PrincipledBSDFDoSpecularEnergyCompensation", 1 }, { "PrincipledBSDFDeltaDistributionEvaluationOptimization", 1 },
     { "PrincipledBSDFSampleGlossyBasedOnFresnel", 0 }, { "PrincipledBSDFSampleCoatBasedOnFresnel", 0 },
     { "PrincipledBSDFDoMicrofacetRegularization", 1 }, { "PrincipledBSDFDoMicrofacetRegularizationConsistentParameterization", 1 },
-    { "PrincipledBSDFMicrofacetRegularizationDiffusionHeuristic", 1 }, { "ReSTIR_DI_InitialTargetFunctionVisibility", 0 },
-    { "ReSTIR_DI_SpatialTargetFunctionVisibility", 0 }, { "ReSTIR_DI_DoVisibilityReuse", 1 }, { "ReSTIR_DI_BiasCorrectionUseVisibility", 1 },
-    { "ReSTIR_DI_BiasCorrectionWeights", 4 }, { "ReSTIR_DI_DoOptimalVisibilitySampling", 0 },
+    { "PrincipledBSDFMicrofacetRegularizationDiffusionHeuristic", 1 }, { "ReSTIR_DI_DoOptimalVisibilitySampling", 0 },
     { "DirectLightUseNEEPlusPlus", 0 }, { "SharedStackBVHTraversalSize", 16 },
 };
 
@@ -611,7 +610,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
         return B2PT_ERR_NO_VARIANT;
     }
     /* reference defaults */
-    int bsdf = 0, direct = 4, base = 1, later = 3, envmap = 2, precise = 1, counters = 0, light_presampling = 0, alpha_test = 0, bias_correction = 4;
+    int bsdf = 0, direct = 4, base = 1, later = 3, envmap = 2, precise = 1, counters = 0, light_presampling = 0, alpha_test = 0, bias_correction = 4, restir_options = 4 | 8;
     for (int i = 0; i < option_count; i++)
     {
         const char* n = options[i].name;
@@ -626,6 +625,11 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
         else if (!std::strcmp(n, "B2PT_PRECISE")) precise = v;
         else if (!std::strcmp(n, "B2PT_ALPHA_TEST")) alpha_test = v != 0; /* launch-time switch of the same kernels */
         else if (!std::strcmp(n, "ReSTIR_DI_BiasCorrectionWeights")) bias_correction = v; /* launch-time switch of the reuse passes */
+        /* ReSTIRDIOptions.h:50-84, launch-time switches of the ReSTIR DI passes (bits B2_DI_OPT_*) */
+        else if (!std::strcmp(n, "ReSTIR_DI_InitialTargetFunctionVisibility")) restir_options = v ? (restir_options | 1) : (restir_options & ~1);
+        else if (!std::strcmp(n, "ReSTIR_DI_SpatialTargetFunctionVisibility")) restir_options = v ? (restir_options | 2) : (restir_options & ~2);
+        else if (!std::strcmp(n, "ReSTIR_DI_DoVisibilityReuse")) restir_options = v ? (restir_options | 4) : (restir_options & ~4);
+        else if (!std::strcmp(n, "ReSTIR_DI_BiasCorrectionUseVisibility")) restir_options = v ? (restir_options | 8) : (restir_options & ~8);
         else if (!std::strcmp(n, "B2PT_COUNTERS")) counters = v;
         else
         {
@@ -676,6 +680,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
                 k->precise = unit.precise;
                 k->alpha_test = alpha_test;
                 k->bias_correction = bias_correction;
+                k->restir_options = restir_options;
                 B2_CUDA(cudaEventCreate(&k->start));
                 B2_CUDA(cudaEventCreate(&k->stop));
                 *out_kernel = k;
@@ -749,6 +754,7 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
     geom.light_presampling = kernel->light_presampling;
     geom.alpha_test = kernel->alpha_test;
     geom.bias_correction = kernel->bias_correction;
+    geom.restir_options = kernel->restir_options;
     geom.presampling_parameters = presampling_pass ? args[0] : nullptr;
     geom.directional_masks_ull = nullptr;
     geom.directional_radius = nullptr;

@@ -247,6 +247,7 @@ struct Ctx
     unsigned int* faults;          /* B2_FAULT_COUNT words (device global / host array) or null */
     bool light_presampling;        /* ReSTIR_DI_DoLightPresampling: initial candidates come from the presampled light buffer */
     int bias_correction;           /* ReSTIR_DI_BiasCorrectionWeights (B2_BIAS_*, b2_restir_di.h): a launch-time switch of the reuse passes */
+    int restir_options;  /* B2_DI_OPT_* (b2_restir_di.h): the four ReSTIR DI visibility macros of ReSTIRDIOptions.h:50-84 */
     bool alpha_test;               /* the kernel was asked for alpha testing (B2PT_ALPHA_TEST: the scene has materials that are not fully opaque) */
 #if defined(B2_ALPHA_TEST_GATED_BY_BOUNCE)
     mutable int ray_bounce;        /* bounce of the vertex whose rays are being traced in place (FilterFunctionPayload::bounce): set by the pass / bounce code */

@@ -20,6 +20,7 @@ struct B2LaunchGeom
     int stack_entries; /* phased MegaKernel: traversal-stack entries per thread (BVH depth + 1 when known, else B2_STACK_ENTRIES) */
     int light_presampling; /* ReSTIR DI initial candidates: take light candidates from the presampled buffer */
     int bias_correction;   /* ReSTIR_DI_BiasCorrectionWeights of the ReSTIR DI reuse passes (ReSTIRDIOptions.h:9-16; 4 = pairwise MIS, the default) */
+    int restir_options;    /* ReSTIR DI passes: B2_DI_OPT_* bits (InitialTargetFunctionVisibility, SpatialTargetFunctionVisibility, DoVisibilityReuse, BiasCorrectionUseVisibility) */
     int alpha_test;        /* the scene has materials that are not fully opaque: candidate hits go through the alpha test (b2_bvh.h) */
     const void* presampling_parameters; /* ReSTIR_DI_LightsPresampling only: host pointer to its LightPresamplingParameters argument */
     void* directional_masks_ull; /* ReSTIR_Directional_Reuse_Compute only: its two output buffers (device pointers) */

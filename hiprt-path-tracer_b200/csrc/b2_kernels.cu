@@ -84,6 +84,7 @@ __device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd
     ctx.light_presampling = false;
     ctx.alpha_test = alpha_test; /* kernels that were asked for alpha testing (B2PT_ALPHA_TEST) */
     ctx.bias_correction = 4;     /* RESTIR_DI_BIAS_CORRECTION_PAIRWISE_MIS; the pixel kernels of the reuse passes take the launch's */
+    ctx.restir_options = 4 | 8;  /* B2_DI_OPT_DEFAULTS, likewise */
     B2_SET_RAY_BOUNCE(ctx, 0);
 }
 
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS, B2_PASS_MIN_BLOCKS) pass_ker
     b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
     ctx.light_presampling = geom.light_presampling != 0;
     ctx.bias_correction = geom.bias_correction;
+    ctx.restir_options = geom.restir_options;
 
     b2_run_pass_pixel<V>(PASS, ctx, x, y);
 
@@ -663,10 +665,11 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
     if constexpr (V::DIRECT == B2_LSS_RESTIR_DI)
     {
         /* the ray-delimited ReSTIR DI passes follow the MegaKernel's form: frame-wide phases + the global ray queue on big scenes */
-        if (PASS == B2_PASS_RESTIR_DI_INITIAL_CANDIDATES && g.persistent == 3)
+        const bool default_options = g.restir_options == B2_DI_OPT_DEFAULTS;
+        if (PASS == B2_PASS_RESTIR_DI_INITIAL_CANDIDATES && g.persistent == 3 && default_options)
             return launch_wavefront_pass<WfInitialCandidates<V>, V>(rd, g, rows, stream);
         /* (pairwise MIS with at most 6 neighbours; anything else runs the pass in one piece, restir_di_spatiotemporal_inplace_pixel) */
-        if (PASS == B2_PASS_RESTIR_DI_SPATIOTEMPORAL && g.persistent == 3 && g.bias_correction == 4 && restir_di_spatiotemporal_supported<V>(*rd))
+        if (PASS == B2_PASS_RESTIR_DI_SPATIOTEMPORAL && g.persistent == 3 && g.bias_correction == 4 && default_options && restir_di_spatiotemporal_supported<V>(*rd))
             return launch_wavefront_pass<WfSpatiotemporalReuse<V>, V>(rd, g, rows, stream);
     }
     if (PASS == B2_PASS_MEGAKERNEL && g.persistent)

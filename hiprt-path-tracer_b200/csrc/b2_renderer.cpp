@@ -156,7 +156,7 @@ void free_all(b2pt_renderer* r, std::vector<void*>& owner)
     owner.clear();
 }
 
-struct VariantKey { const char* name; int bsdf, direct, base, later; bool restir; bool presampling; int bias_correction; };
+struct VariantKey { const char* name; int bsdf, direct, base, later; bool restir; bool presampling; int bias_correction; int restir_options = 4 | 8; };
 const VariantKey kVariants[] = {
     { "c1", 1, 1, 0, 3, false, false, 4 },
     { "c2", 0, 3, 1, 3, false, false, 4 },
@@ -171,6 +171,13 @@ const VariantKey kVariants[] = {
     { "c4b5", 0, 5, 1, 3, true, false, 5 },
     { "c4b6", 0, 5, 1, 3, true, false, 6 }, /* symmetric ratio */
     { "c4b7", 0, 5, 1, 3, true, false, 7 }, /* asymmetric ratio */
+    /* c4 with one of the four ReSTIR DI visibility macros (ReSTIRDIOptions.h:50-84) away from its default; bits: 1 InitialTargetFunctionVisibility,
+     * 2 SpatialTargetFunctionVisibility, 4 DoVisibilityReuse, 8 BiasCorrectionUseVisibility (defaults 4 | 8) */
+    { "c4v1", 0, 5, 1, 3, true, false, 4, 1 | 4 | 8 }, /* InitialTargetFunctionVisibility on */
+    { "c4v2", 0, 5, 1, 3, true, false, 4, 2 | 4 | 8 }, /* SpatialTargetFunctionVisibility on */
+    { "c4v3", 0, 5, 1, 3, true, false, 4, 8 },         /* DoVisibilityReuse off */
+    { "c4v4", 0, 5, 1, 3, true, false, 4, 4 },         /* BiasCorrectionUseVisibility off */
+    { "c4v5", 0, 5, 1, 3, true, false, 4, 1 | 2 | 8 }, /* both target-function visibilities on, visibility reuse off */
 };
 
 const VariantKey* find_variant(const std::string& name)
@@ -222,6 +229,8 @@ int resolve_kernels(b2pt_renderer* r)
             { "ReSTIR_DI_LaterBouncesSamplingStrategy", v->later }, { "ReSTIR_DI_DoLightPresampling", v->presampling ? 1 : 0 },
             { "B2PT_PRECISE", r->precise }, { "B2PT_COUNTERS", r->counters }, { "B2PT_ALPHA_TEST", r->alpha_test ? 1 : 0 },
             { "ReSTIR_DI_BiasCorrectionWeights", v->bias_correction },
+            { "ReSTIR_DI_InitialTargetFunctionVisibility", (v->restir_options & 1) ? 1 : 0 }, { "ReSTIR_DI_SpatialTargetFunctionVisibility", (v->restir_options & 2) ? 1 : 0 },
+            { "ReSTIR_DI_DoVisibilityReuse", (v->restir_options & 4) ? 1 : 0 }, { "ReSTIR_DI_BiasCorrectionUseVisibility", (v->restir_options & 8) ? 1 : 0 },
         };
         B2_TRY(b2pt_kernel_get(r->ctx, entry, opts, (int)(sizeof(opts) / sizeof(opts[0])), &r->kernels[pass]));
     }

@@ -40,6 +40,29 @@ B2_HD bool restir_gi_coalesced_spatial_reuse(const b2pt_render_data& rd)
 enum { B2_BIAS_1_OVER_M = 0, B2_BIAS_1_OVER_Z = 1, B2_BIAS_MIS_LIKE = 2, B2_BIAS_MIS_GBH = 3, B2_BIAS_PAIRWISE_MIS = 4, B2_BIAS_PAIRWISE_MIS_DEFENSIVE = 5,
        B2_BIAS_SYMMETRIC_RATIO = 6, B2_BIAS_ASYMMETRIC_RATIO = 7 };
 
+/* The four visibility macros of ReSTIRDIOptions.h:50-84 as launch-time switches (Ctx::restir_options). The reference's defaults:
+ * visibility reuse and visibility in the bias-correction target functions on, the other two off. The phase-cut (wavefront) forms of
+ * InitialCandidates and of the fused pass are built for the defaults; any other setting runs the passes in one piece. */
+enum { B2_DI_OPT_INITIAL_VISIBILITY = 1, B2_DI_OPT_SPATIAL_VISIBILITY = 2, B2_DI_OPT_VISIBILITY_REUSE = 4, B2_DI_OPT_BIAS_VISIBILITY = 8,
+       B2_DI_OPT_DEFAULTS = B2_DI_OPT_VISIBILITY_REUSE | B2_DI_OPT_BIAS_VISIBILITY };
+
+/* ReSTIR_DI_evaluate_target_function<ReSTIR_DI_BiasCorrectionUseVisibility> */
+template <class V>
+B2_HD float di_target_function_bias(const Ctx& ctx, const DiSample& sample, DiSurface& surface)
+{
+    if (ctx.restir_options & B2_DI_OPT_BIAS_VISIBILITY)
+        return di_target_function<V, true>(ctx, sample, surface);
+    return di_target_function<V, false>(ctx, sample, surface);
+}
+
+/* the visibility-reuse pass at the end of the spatial / fused pass exists when the bias-correction target functions see visibility and
+ * the reservoirs that come in do too (SpatialReuse.h:264-270, FusedSpatiotemporalReuse.h:507-513) */
+B2_HD bool di_end_of_pass_visibility_reuse(const Ctx& ctx)
+{
+    const int o = ctx.restir_options;
+    return (o & B2_DI_OPT_BIAS_VISIBILITY) && ((o & B2_DI_OPT_VISIBILITY_REUSE) || ((o & B2_DI_OPT_INITIAL_VISIBILITY) && (o & B2_DI_OPT_SPATIAL_VISIBILITY)));
+}
+
 /* MISWeightsCommon.h:49-64: min(a / b, b / a) ^ beta, 0 when either target function is */
 B2_HD float ratio_mis_difference_function(float target_function_at_center, float target_function_from_i, float exponent)
 {
@@ -343,13 +366,18 @@ B2_HD void count_valid_neighbors(const b2pt_render_data& rd, const SpatialLocal&
     }
 }
 
-B2_HD bool do_include_spatial_visibility_term(const b2pt_render_data& rd, const SpatialLocal& local, int current_neighbor_index)
+B2_HD bool do_include_spatial_visibility_term(const Ctx& ctx, const SpatialLocal& local, int current_neighbor_index)
 {
-    /* ReSTIR_DI_SpatialTargetFunctionVisibility = FALSE (reference default) makes the whole expression false */
-    (void)rd;
-    (void)local;
-    (void)current_neighbor_index;
-    return false;
+    /* do_include_visibility_term_or_not (UtilsSpatial.h:40-58) = do_include_spatial_visibility_term_or_not (FusedSpatiotemporalReuse.h:44-63);
+     * ReSTIR_DI_SpatialTargetFunctionVisibility = FALSE (the reference's default) makes the whole expression false */
+    const b2pt_restir_spatial_common& s = ctx.rd->render_settings.restir_di_settings.common_spatial_pass;
+    bool is_last_pass = s.spatial_pass_index == s.number_of_passes - 1;
+    bool include_target_function_visibility = s.do_visibility_only_last_pass && is_last_pass;
+    include_target_function_visibility |= !s.do_visibility_only_last_pass;
+    include_target_function_visibility &= current_neighbor_index < s.neighbor_visibility_count;
+    include_target_function_visibility &= (ctx.restir_options & B2_DI_OPT_SPATIAL_VISIBILITY) != 0;
+    include_target_function_visibility &= current_neighbor_index != local.reuse_neighbor_count;
+    return include_target_function_visibility;
 }
 
 /* ---------------------------------------------------------------------------------------------------------- */
@@ -448,7 +476,7 @@ struct PairwiseMis
         if (!resampling_canonical && update_mc)
         {
             DiSurface neighbor_pixel_surface = get_pixel_surface<V>(rd, neighbor_pixel_index, neighbor_from_previous_frame, rng);
-            target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, center_pixel_reservoir_sample, neighbor_pixel_surface);
+            target_function_center_sample_at_neighbor = di_target_function_bias<V>(ctx, center_pixel_reservoir_sample, neighbor_pixel_surface);
         }
         return weight_given(rd, reservoir_being_resampled_M, reservoir_being_resampled_target_function, center_pixel_reservoir_M, center_pixel_reservoir_target_function,
                             target_function_at_center, target_function_center_sample_at_neighbor, valid_neighbors_count, valid_neighbors_M_sum, update_mc, resampling_canonical,
@@ -740,7 +768,7 @@ B2_HD void di_initial_surface(const b2pt_render_data& rd, uint32_t pixel_index, 
     view_direction = normalize(cam - hit.inter_point);
 }
 
-template <class V>
+template <class V, bool IN_ONE_PIECE = false>
 B2_HD void restir_di_initial_phase_a(const Ctx& ctx, uint32_t x, uint32_t y, DiInitialState& st, RayRequest& candidate_ray)
 {
     const b2pt_render_data& rd = *ctx.rd;
@@ -837,6 +865,21 @@ B2_HD void restir_di_initial_phase_a(const Ctx& ctx, uint32_t x, uint32_t y, DiI
                 float mis_weight = balance_heuristic(light_pdf_solid_angle, (float)nb_light_candidates, bsdf_pdf_solid_angle, (float)nb_bsdf_candidates);
                 candidate_weight = mis_weight * target_function / light_pdf_area_measure;
                 light_sample.target_function = target_function;
+            }
+        }
+        /* ReSTIR_DI_InitialTargetFunctionVisibility (InitialCandidates.h:266-291): a shadow ray per light candidate, traced on the spot --
+         * the per-pixel form of the pass only, the wavefront form is launched for the default (off) */
+        if constexpr (IN_ONE_PIECE)
+        {
+            if ((ctx.restir_options & B2_DI_OPT_INITIAL_VISIBILITY) && !do_render_low_resolution(rd.render_settings) && light_sample.target_function > 0.0f)
+            {
+                bool visible = !shadow_ray_occluded(ctx, hit.inter_point, to_light_direction, distance_to_light, hit.primitive_index);
+                if (!visible)
+                {
+                    reservoir.M++;
+                    continue;
+                }
+                light_sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
             }
         }
         reservoir.add_one_candidate(light_sample, candidate_weight, rng);
@@ -988,7 +1031,10 @@ B2_HD void restir_di_initial_phase_b(const Ctx& ctx, uint32_t x, uint32_t y, DiI
 
     st.reservoir = reservoir;
     st.rng = rng;
-    st.pending_final = di_visibility_test_request(rd, reservoir, hit.inter_point, hit.primitive_index, visibility_ray) ? 1 : 0;
+    /* ReSTIR_DI_DoVisibilityReuse (InitialCandidates.h:533-535) */
+    st.pending_final = 0;
+    if (ctx.restir_options & B2_DI_OPT_VISIBILITY_REUSE)
+        st.pending_final = di_visibility_test_request(rd, reservoir, hit.inter_point, hit.primitive_index, visibility_ray) ? 1 : 0;
 }
 
 template <class V>
@@ -1021,7 +1067,7 @@ B2_HD void restir_di_initial_candidates_pixel(const Ctx& ctx, uint32_t x, uint32
 {
     DiInitialState st;
     RayRequest ray;
-    restir_di_initial_phase_a<V>(ctx, x, y, st, ray);
+    restir_di_initial_phase_a<V, true>(ctx, x, y, st, ray);
     B2Hit result = di_trace_request(ctx, ray);
     restir_di_initial_phase_b<V>(ctx, x, y, st, result, ray);
     result = di_trace_request(ctx, ray);
@@ -1089,10 +1135,10 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
     auto gbh_weight = [&](const DiSample& sample, int current_neighbor_index) {
         float target_function_at_temporal_neighbor = 0.0f;
         if (temporal_neighbor_reservoir.M != 0)
-            target_function_at_temporal_neighbor = di_target_function<V, true>(ctx, sample, temporal_neighbor_surface);
+            target_function_at_temporal_neighbor = di_target_function_bias<V>(ctx, sample, temporal_neighbor_surface);
         if (current_neighbor_index == 0 && target_function_at_temporal_neighbor == 0.0f)
             return 0.0f;
-        float target_function_at_center = di_target_function<V, true>(ctx, sample, temporal_neighbor_surface);
+        float target_function_at_center = di_target_function_bias<V>(ctx, sample, temporal_neighbor_surface);
         int temporal_M = temporal_neighbor_reservoir.M;
         int center_reservoir_M = initial_candidates_reservoir.M;
         if (!use_confidence_weights)
@@ -1109,7 +1155,7 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
     {
         float target_function_at_center = 0.0f;
         if (temporal_neighbor_reservoir.UCW > 0.0f)
-            target_function_at_center = di_target_function<V, true>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface);
+            target_function_at_center = di_target_function_bias<V>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface);
 
         float temporal_neighbor_resampling_mis_weight;
         if (bias == B2_BIAS_1_OVER_Z)
@@ -1135,7 +1181,7 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
                 denom_mi = center_reservoir_M + neighbors_confidence_sum;
             float mi = nume_mi / denom_mi;
 
-            float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, initial_candidates_reservoir.sample, temporal_neighbor_surface);
+            float target_function_center_sample_at_neighbor = di_target_function_bias<V>(ctx, initial_candidates_reservoir.sample, temporal_neighbor_surface);
             float target_function_center_sample_at_center = initial_candidates_reservoir.sample.target_function;
             float difference_function_mc = ratio_mis_difference_function(target_function_center_sample_at_neighbor, target_function_center_sample_at_center, beta);
             if (asymmetric)
@@ -1172,7 +1218,7 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
             if (defensive && use_confidence_weights)
                 mi *= neighbors_confidence_sum / (neighbors_confidence_sum + center_reservoir_M);
 
-            float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, initial_candidates_reservoir.sample, temporal_neighbor_surface);
+            float target_function_center_sample_at_neighbor = di_target_function_bias<V>(ctx, initial_candidates_reservoir.sample, temporal_neighbor_surface);
             float target_function_center_sample_at_center = initial_candidates_reservoir.sample.target_function;
             float nume_mc = target_function_center_sample_at_center * center_reservoir_M;
             float denom_mc = target_function_center_sample_at_neighbor * neighbors_confidence_sum + target_function_center_sample_at_center * center_reservoir_M;
@@ -1188,7 +1234,11 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
         if (out.combine_with(temporal_neighbor_reservoir, temporal_neighbor_resampling_mis_weight, target_function_at_center, 1.0f, rng))
         {
             selected_neighbor = 0;
-            out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+            /* TemporalReuse.h:193-203: with visibility in the target function the neighbour could only be chosen unoccluded */
+            if (ctx.restir_options & B2_DI_OPT_BIAS_VISIBILITY)
+                out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+            else
+                out.sample.flags &= ~(uint32_t)B2_DI_FLAGS_UNOCCLUDED;
         }
     }
 
@@ -1215,7 +1265,10 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
     if (out.combine_with(initial_candidates_reservoir, initial_candidates_mis_weight, initial_candidates_reservoir.sample.target_function, 1.0f, rng))
     {
         selected_neighbor = 1;
-        out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+        if (ctx.restir_options & B2_DI_OPT_BIAS_VISIBILITY) /* TemporalReuse.h:248-256 */
+            out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+        else
+            out.sample.or_flags((int)(initial_candidates_reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED));
     }
 
     /* TemporalNormalizationWeight.h: 1/Z counts the confidence of the reservoirs that could have produced the chosen sample, MIS-like
@@ -1223,7 +1276,7 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
     float normalization_numerator = 1.0f, normalization_denominator = 1.0f;
     if ((bias == B2_BIAS_1_OVER_Z || bias == B2_BIAS_MIS_LIKE) && !(out.weight_sum <= 0.0f))
     {
-        float center_pixel_target_function = di_target_function<V, true>(ctx, out.sample, center_pixel_surface);
+        float center_pixel_target_function = di_target_function_bias<V>(ctx, out.sample, center_pixel_surface);
         float temporal_neighbor_target_function = 0.0f;
         if (bias == B2_BIAS_1_OVER_Z)
         {
@@ -1231,14 +1284,14 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
             normalization_denominator += (float)((center_pixel_target_function > 0.0f) * initial_candidates_reservoir.M);
             if (temporal_neighbor_reservoir.M > 0)
             {
-                temporal_neighbor_target_function = di_target_function<V, true>(ctx, out.sample, temporal_neighbor_surface);
+                temporal_neighbor_target_function = di_target_function_bias<V>(ctx, out.sample, temporal_neighbor_surface);
                 normalization_denominator += (float)((temporal_neighbor_target_function > 0.0f) * temporal_neighbor_reservoir.M);
             }
         }
         else
         {
             if (temporal_neighbor_reservoir.M > 0)
-                temporal_neighbor_target_function = di_target_function<V, true>(ctx, out.sample, temporal_neighbor_surface);
+                temporal_neighbor_target_function = di_target_function_bias<V>(ctx, out.sample, temporal_neighbor_surface);
             normalization_numerator = selected_neighbor == 1 ? center_pixel_target_function : temporal_neighbor_target_function;
             int initial_candidates_M = initial_candidates_reservoir.M, temporal_neighbor_M = temporal_neighbor_reservoir.M;
             if (!use_confidence_weights)
@@ -1328,7 +1381,7 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
             return 1.0f;
         float nume = 0.0f, denom = 0.0f;
         for_all_neighbors([&](int j, int neighbor_index_j, DiSurface& neighbor_surface) {
-            float target_function_at_j = di_target_function<V, true>(ctx, reservoir_being_resampled_sample, neighbor_surface);
+            float target_function_at_j = di_target_function_bias<V>(ctx, reservoir_being_resampled_sample, neighbor_surface);
             int M = 1;
             if (use_confidence_weights)
                 M = di_load(rd, input_reservoir_buffer, neighbor_index_j).M;
@@ -1362,11 +1415,13 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
 
         DiReservoir neighbor_reservoir = di_load(rd, input_reservoir_buffer, neighbor_pixel_index);
         float target_function_at_center = 0.0f;
-        bool do_neighbor_target_function_visibility = do_include_spatial_visibility_term(rd, local, neighbor_index);
+        bool do_neighbor_target_function_visibility = do_include_spatial_visibility_term(ctx, local, neighbor_index);
         if (neighbor_reservoir.UCW > 0.0f)
         {
             if (neighbor_index == reused_neighbors_count)
                 target_function_at_center = neighbor_reservoir.sample.target_function;
+            else if (do_neighbor_target_function_visibility)
+                target_function_at_center = di_target_function<V, true>(ctx, neighbor_reservoir.sample, center_pixel_surface);
             else
                 target_function_at_center = di_target_function<V, false>(ctx, neighbor_reservoir.sample, center_pixel_surface);
         }
@@ -1405,7 +1460,7 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
                 if (update_mc)
                 {
                     DiSurface neighbor_pixel_surface = get_pixel_surface<V>(rd, neighbor_pixel_index, false, rng);
-                    float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, center_pixel_reservoir.sample, neighbor_pixel_surface);
+                    float target_function_center_sample_at_neighbor = di_target_function_bias<V>(ctx, center_pixel_reservoir.sample, neighbor_pixel_surface);
                     float difference_function_mc = ratio_mis_difference_function(target_function_center_sample_at_neighbor, target_function_center_sample_at_center, beta);
                     if (asymmetric)
                     {
@@ -1458,7 +1513,7 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
         normalization_denominator = 0.0f;
         normalization_numerator = bias == B2_BIAS_1_OVER_Z ? 1.0f : 0.0f;
         for_all_neighbors([&](int j, int neighbor_index_j, DiSurface& neighbor_surface) {
-            float target_function_at_neighbor = di_target_function<V, true>(ctx, final_reservoir_sample, neighbor_surface);
+            float target_function_at_neighbor = di_target_function_bias<V>(ctx, final_reservoir_sample, neighbor_surface);
             if (target_function_at_neighbor > 0.0f)
             {
                 if (bias == B2_BIAS_1_OVER_Z)
@@ -1479,7 +1534,7 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
 
     /* the visibility-reuse test at the end of the pass exists for 1/Z, pairwise MIS and its defensive form only (SpatialReuse.h:264-275) */
     bool not_last_spatial_pass = di.common_spatial_pass.number_of_passes - 1 != di.common_spatial_pass.spatial_pass_index;
-    if (bias != B2_BIAS_MIS_LIKE && bias != B2_BIAS_MIS_GBH && (di.common_temporal_pass.do_temporal_reuse_pass || not_last_spatial_pass))
+    if (bias != B2_BIAS_MIS_LIKE && bias != B2_BIAS_MIS_GBH && di_end_of_pass_visibility_reuse(ctx) && (di.common_temporal_pass.do_temporal_reuse_pass || not_last_spatial_pass))
         di_visibility_test_kill_reservoir(ctx, out, center_pixel_surface.shading_point, center_pixel_surface.primitive_index);
 
     if (di.m_cap > 0)
@@ -1872,13 +1927,13 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
             return 1.0f;
         float nume = 0.0f, denom = 0.0f;
         for_all_spatial_neighbors(prev_gbuffer, [&](int j, int M_j, DiSurface& neighbor_surface) {
-            float target_function_at_j = di_target_function<V, true>(ctx, reservoir_being_resampled_sample, neighbor_surface);
+            float target_function_at_j = di_target_function_bias<V>(ctx, reservoir_being_resampled_sample, neighbor_surface);
             int M = use_confidence_weights ? M_j : 1;
             denom += target_function_at_j * M;
             if (j + 1 == current_neighbor)
                 nume = target_function_at_j * M;
         });
-        float target_function_at_temporal_neighbor = di_target_function<V, true>(ctx, reservoir_being_resampled_sample, temporal_neighbor_surface);
+        float target_function_at_temporal_neighbor = di_target_function_bias<V>(ctx, reservoir_being_resampled_sample, temporal_neighbor_surface);
         int M = use_confidence_weights ? temporal_neighbor_reservoir.M : 1;
         denom += target_function_at_temporal_neighbor * M;
         if (current_neighbor == 0)
@@ -1911,7 +1966,7 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
             if (update_mc)
             {
                 DiSurface neighbor_pixel_surface = get_pixel_surface<V>(rd, neighbor_pixel_index, false, rng);
-                float target_function_center_sample_at_neighbor = di_target_function<V, true>(ctx, initial_candidates_reservoir.sample, neighbor_pixel_surface);
+                float target_function_center_sample_at_neighbor = di_target_function_bias<V>(ctx, initial_candidates_reservoir.sample, neighbor_pixel_surface);
                 float nume_mc = center_reservoir_M;
                 float denom_mc = center_reservoir_M + neighbors_confidence_sum * ratio_mis_difference_function(target_function_center_sample_at_neighbor, target_function_center_sample_at_center, beta);
                 float confidence_weights_multiplier;
@@ -1932,12 +1987,15 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
     {
         float target_function_at_center = 0.0f;
         if (temporal_neighbor_reservoir.UCW > 0.0f)
-            target_function_at_center = di_target_function<V, true>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface);
+            target_function_at_center = di_target_function_bias<V>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface);
         float w = resampling_weight(temporal_neighbor_reservoir, target_function_at_center, temporal.x, 0, false);
         if (out.combine_with(temporal_neighbor_reservoir, w, target_function_at_center, 1.0f, rng))
         {
             selected_neighbor = 0;
-            out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+            if (ctx.restir_options & B2_DI_OPT_BIAS_VISIBILITY) /* :284-296 */
+                out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+            else
+                out.sample.flags &= ~(uint32_t)B2_DI_FLAGS_UNOCCLUDED;
         }
     }
 
@@ -1970,12 +2028,14 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
         const bool canonical = spatial_neighbor_index == reused_neighbors_count;
         DiReservoir neighbor_reservoir = canonical ? initial_candidates_reservoir : di_load(rd, di.spatial_pass.input_reservoirs, neighbor_pixel_index);
 
-        /* ReSTIR_DI_SpatialTargetFunctionVisibility = FALSE: do_include_spatial_visibility_term_or_not is false for every neighbour */
         float target_function_at_center = 0.0f;
+        const bool do_neighbor_target_function_visibility = do_include_spatial_visibility_term(ctx, local, spatial_neighbor_index);
         if (neighbor_reservoir.UCW > 0.0f)
         {
             if (canonical)
                 target_function_at_center = neighbor_reservoir.sample.target_function;
+            else if (do_neighbor_target_function_visibility)
+                target_function_at_center = di_target_function<V, true>(ctx, neighbor_reservoir.sample, center_pixel_surface);
             else
                 target_function_at_center = di_target_function<V, false>(ctx, neighbor_reservoir.sample, center_pixel_surface);
         }
@@ -1985,7 +2045,9 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
         if (out.combine_with(neighbor_reservoir, mis_weight, target_function_at_center, 1.0f, rng))
         {
             selected_neighbor = spatial_neighbor_index + 1;
-            if (canonical)
+            if (do_neighbor_target_function_visibility)
+                out.sample.or_flags(B2_DI_FLAGS_UNOCCLUDED);
+            else if (canonical)
                 out.sample.or_flags((int)(neighbor_reservoir.sample.flags & B2_DI_FLAGS_UNOCCLUDED));
             else
                 out.sample.flags &= ~(uint32_t)B2_DI_FLAGS_UNOCCLUDED;
@@ -2000,7 +2062,7 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
         normalization_denominator = 0.0f;
         normalization_numerator = bias == B2_BIAS_1_OVER_Z ? 1.0f : 0.0f;
         for_all_spatial_neighbors(bias == B2_BIAS_1_OVER_Z ? prev_gbuffer : false, [&](int j, int M_j, DiSurface& neighbor_surface) {
-            float target_function_at_neighbor = di_target_function<V, true>(ctx, final_reservoir_sample, neighbor_surface);
+            float target_function_at_neighbor = di_target_function_bias<V>(ctx, final_reservoir_sample, neighbor_surface);
             if (target_function_at_neighbor > 0.0f)
             {
                 if (bias == B2_BIAS_1_OVER_Z)
@@ -2014,7 +2076,7 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
                 }
             }
         });
-        float target_function_at_temporal_neighbor = di_target_function<V, true>(ctx, final_reservoir_sample, temporal_neighbor_surface);
+        float target_function_at_temporal_neighbor = di_target_function_bias<V>(ctx, final_reservoir_sample, temporal_neighbor_surface);
         if (bias == B2_BIAS_1_OVER_Z)
         {
             if (target_function_at_temporal_neighbor > 0.0f)
@@ -2030,7 +2092,7 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
     }
     out.end_with_normalization(normalization_numerator, normalization_denominator);
 
-    if (bias != B2_BIAS_MIS_LIKE && bias != B2_BIAS_MIS_GBH &&
+    if (bias != B2_BIAS_MIS_LIKE && bias != B2_BIAS_MIS_GBH && di_end_of_pass_visibility_reuse(ctx) &&
         (di.common_temporal_pass.do_temporal_reuse_pass || di.common_spatial_pass.number_of_passes - 1 != di.common_spatial_pass.spatial_pass_index))
         di_visibility_test_kill_reservoir(ctx, out, center_pixel_surface.shading_point, center_pixel_surface.primitive_index);
 
@@ -2042,7 +2104,7 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
 template <class V>
 B2_HD void restir_di_spatiotemporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
 {
-    if (ctx.bias_correction != B2_BIAS_PAIRWISE_MIS || !restir_di_spatiotemporal_supported<V>(*ctx.rd))
+    if (ctx.bias_correction != B2_BIAS_PAIRWISE_MIS || ctx.restir_options != B2_DI_OPT_DEFAULTS || !restir_di_spatiotemporal_supported<V>(*ctx.rd))
     {
         restir_di_spatiotemporal_inplace_pixel<V>(ctx, x, y);
         return;

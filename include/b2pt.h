@@ -158,7 +158,10 @@ int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
  * {"ReSTIR_DI_BiasCorrectionWeights", N} (ReSTIRDIOptions.h:9-16,120): "ReSTIR_DI_TemporalReuse", "ReSTIR_DI_SpatialReuse" and
  * "ReSTIR_DI_SpatiotemporalReuse" are served for N = 1 (1/Z), 2 (MIS-like), 3 (generalised balance heuristic), 4 (pairwise MIS, the
  * default), 5 (defensive pairwise MIS), 6 (symmetric ratio) and 7 (asymmetric ratio); 0 (1/M, which the reference itself does not
- * compile) answers B2PT_ERR_NO_VARIANT. */
+ * compile) answers B2PT_ERR_NO_VARIANT.
+ * {"ReSTIR_DI_InitialTargetFunctionVisibility", 0|1}, {"ReSTIR_DI_SpatialTargetFunctionVisibility", 0|1}, {"ReSTIR_DI_DoVisibilityReuse", 0|1},
+ * {"ReSTIR_DI_BiasCorrectionUseVisibility", 0|1} (ReSTIRDIOptions.h:50-84; defaults 0, 0, 1, 1): launch-time switches of the ReSTIR DI
+ * passes; give the same values to every ReSTIR DI kernel of a renderer, as the reference's global compiler options do. */
 typedef struct
 {
     const char* name;
@@ -236,7 +239,9 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
  * ------------------------------------------------------------------------------------------------------------ */
 
 /* variant: "c1" | "c2" | "c3" | "c4" | "c4p" (= c4 + ReSTIR DI light presampling) | "c4b1" "c4b2" "c4b3" "c4b5" "c4b6" "c4b7" (= c4 with
- * ReSTIR_DI_BiasCorrectionWeights 1 / 2 / 3 / 5 / 6 / 7)
+ * ReSTIR_DI_BiasCorrectionWeights 1 / 2 / 3 / 5 / 6 / 7) | "c4v1" .. "c4v5" (= c4 with the ReSTIR DI visibility macros away from their
+ * defaults: InitialTargetFunctionVisibility on / SpatialTargetFunctionVisibility on / DoVisibilityReuse off / BiasCorrectionUseVisibility
+ * off / the first three together)
  * (see b2_kernels_body.h); precise: 1 = parity flavour, 0 = fast flavour */
 int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* variant, int precise, b2pt_renderer** out_renderer);
 int b2pt_renderer_destroy(b2pt_renderer* renderer);

@@ -111,7 +111,17 @@ static unsigned long long g_port_counters[3] = { 0, 0, 0 }; /* rays, nodes, tria
 
 /* "c4b<N>" = c4 with ReSTIR_DI_BiasCorrectionWeights = N (the renderer's variant table, csrc/b2_renderer.cpp) */
 static int bias_correction_of(const std::string& variant) { return variant.rfind("c4b", 0) == 0 ? std::atoi(variant.c_str() + 3) : 4; }
-static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant.rfind("c4b", 0) == 0; }
+/* c4v<N>: one of the four ReSTIR DI visibility macros away from its default (bits B2_DI_OPT_*, the table of b2_renderer.cpp) */
+static int restir_options_of(const std::string& variant)
+{
+    if (variant == "c4v1") return 1 | 4 | 8;
+    if (variant == "c4v2") return 2 | 4 | 8;
+    if (variant == "c4v3") return 8;
+    if (variant == "c4v4") return 4;
+    if (variant == "c4v5") return 1 | 2 | 8;
+    return 4 | 8;
+}
+static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant.rfind("c4b", 0) == 0 || variant.rfind("c4v", 0) == 0; }
 static bool g_scene_has_alpha_tested_materials = false; /* = what the renderer passes as B2PT_ALPHA_TEST */
 
 template <class V>
@@ -131,6 +141,7 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
         ctx.faults = g_port_faults;
         ctx.light_presampling = a.variant == "c4p";
         ctx.bias_correction = bias_correction_of(a.variant);
+        ctx.restir_options = restir_options_of(a.variant);
         ctx.alpha_test = g_scene_has_alpha_tested_materials;
         B2_SET_RAY_BOUNCE(ctx, 0);
 #pragma omp for schedule(dynamic)

@@ -77,7 +77,11 @@ def test_cuda_fast_flavour_agrees_statistically(b2pt, gpu_ctx, name):
     r.close()
     assert (gb["prim"] != g["gbuffer_prim"]).mean() < 1e-3
     ref = g["framebuffer"].reshape(-1, 3)
-    assert abs(fb.reshape(-1, 3).mean() - ref.mean()) <= 0.01 * abs(ref.mean()) + 1e-6
+    fb = fb.reshape(-1, 3)
+    # pixels painted with the reference's NaN marker (1e30 per sample, SanityCheck.h:99; mirrored in b2_pathtrace.h) stay out of the mean
+    marked = (fb.max(axis=1) >= 1e29) | (ref.max(axis=1) >= 1e29)
+    assert marked.mean() <= 2e-3
+    assert abs(fb[~marked].mean() - ref[~marked].mean()) <= 0.01 * abs(ref[~marked].mean()) + 1e-6
 
 
 @pytest.mark.parametrize("name", ["c2_128x72", "c3_syn_96x54"])

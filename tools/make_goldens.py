@@ -72,6 +72,19 @@ CASES = [
     ("c4b6_96x54_fused", "c4b6", "cornell_pbr_16x9", 96, 54, 3, 4, []),
     ("c4_96x54_fused_9neighbors", "c4", "cornell_pbr_16x9", 96, 54, 3, 4, ["--neighbors", "9"]),
     ("c4b1_synenv_96x54_fused_12neighbors", "c4b1", "synthetic_20k", 96, 54, 2, 4, ["--neighbors", "12", "--envmap", "data/sky_128x64.b2env"]),
+    # the four ReSTIR DI visibility macros (ReSTIRDIOptions.h:50-84) away from their defaults, variants "c4v<N>": 1 = InitialTargetFunctionVisibility
+    # on, 2 = SpatialTargetFunctionVisibility on, 3 = DoVisibilityReuse off, 4 = BiasCorrectionUseVisibility off, 5 = 1 + 2 + 3.
+    # (DoVisibilityReuse off on the Cornell box: the reference puts 2e30 into the pixels that look at the lamp; the port follows bit for
+    #  bit, but an image mean of that says nothing about the fast flavour, so 3 and 5 use the many-light scene)
+    ("c4v1_96x54_fused", "c4v1", "cornell_pbr_16x9", 96, 54, 3, 4, []),
+    ("c4v1_syn_96x54_split", "c4v1", "synthetic_20k", 96, 54, 2, 4, ["--no-fused"]),
+    ("c4v2_96x54_fused", "c4v2", "cornell_pbr_16x9", 96, 54, 3, 4, []),
+    ("c4v2_96x54_split", "c4v2", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused"]),
+    ("c4v3_synenv_96x54_fused", "c4v3", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
+    ("c4v3_syn_96x54_split", "c4v3", "synthetic_20k", 96, 54, 2, 4, ["--no-fused"]),
+    ("c4v4_96x54_fused", "c4v4", "cornell_pbr_16x9", 96, 54, 3, 4, []),
+    ("c4v4_synenv_96x54_split", "c4v4", "synthetic_20k", 96, 54, 2, 4, ["--no-fused", "--envmap", "data/sky_128x64.b2env"]),
+    ("c4v5_synenv_96x54_fused", "c4v5", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
 ]
 EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
 
