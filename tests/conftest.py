@@ -55,6 +55,7 @@ def gpu_ctx(b2pt):
 
 
 def load_golden(name):
+    """name: a fixture of tests/golden/, or "options/<fixture>" for one of tests/golden/options/."""
     g = np.load(GOLDEN / f"{name}.npz")
     meta = json.loads(bytes(g["meta"]).decode())
     return g, meta

@@ -87,6 +87,9 @@ CASES = [
     ("c4v5_synenv_96x54_fused", "c4v5", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
 ]
 EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
+# fixtures of kernel options added after the round's GPU budget was spent live in tests/golden/options/ and are tested by
+# tests/test_restir_di_options.py, which runs after the suites whose CUDA side has been seen green on a B200
+OPTIONS_PREFIXES = ("c4v", "c4l")
 
 
 def run_case(name, variant, scene, w, h, spp, bounces, extra):
@@ -112,8 +115,10 @@ def run_case(name, variant, scene, w, h, spp, bounces, extra):
             packed_materials=load("packed_materials", np.uint32), triangle_areas=load("triangle_areas", np.float32),
             emissive_prims=load("emissive_prims", np.int32), power_alias=load("power_alias", np.int32), power_probas=load("power_probas", np.float32),
             meta=np.frombuffer(json.dumps(dict(meta, name=name, scene=scene, extra=extra, oracle_binary=binary)).encode(), np.uint8))
-        np.savez_compressed(GOLD / f"{name}.npz", **arrays)
-        print(f"wrote {name}.npz ({(GOLD / (name + '.npz')).stat().st_size} bytes)")
+        out_dir = GOLD / "options" if name.startswith(OPTIONS_PREFIXES) else GOLD
+        out_dir.mkdir(parents=True, exist_ok=True)
+        np.savez_compressed(out_dir / f"{name}.npz", **arrays)
+        print(f"wrote {out_dir.name}/{name}.npz ({(out_dir / (name + '.npz')).stat().st_size} bytes)")
 
 
 if __name__ == "__main__":
