@@ -33,11 +33,12 @@ FEATURES = ["-DB2_HAVE_PRINCIPLED", "-DB2_HAVE_RIS", "-DB2_HAVE_RESTIR_DI"]
 PRECISE_FLAGS = os.environ.get("B2PT_PRECISE_FLAGS", "-fmad=false -prec-div=true -prec-sqrt=true -ftz=false").split()
 FAST_FLAGS = os.environ.get("B2PT_FAST_FLAGS", "--use_fast_math").split()
 # b2_kernels.cu is compiled once per (flavour, unit, counters): unit 1 = c1, 2 = c2, 3 = c3, 4 = c4 CameraRays + MegaKernel,
-# 5 = c4 ReSTIR DI passes. B2PT_ONLY_UNITS="2,3" / B2PT_NO_COUNTERS=1 / B2PT_ONLY_FLAVOUR=precise shorten experiment builds.
-ONLY_UNITS = [int(u) for u in os.environ.get("B2PT_ONLY_UNITS", "1,2,3,4,5").split(",")]
+# 5 = c4 ReSTIR DI passes, 6 / 7 / 8 = the c4 MegaKernel with ReSTIR_DI_LaterBouncesSamplingStrategy 0 / 1 / 2. B2PT_ONLY_UNITS="2,3" / B2PT_NO_COUNTERS=1 / B2PT_ONLY_FLAVOUR=precise shorten experiment builds.
+ONLY_UNITS = [int(u) for u in os.environ.get("B2PT_ONLY_UNITS", "1,2,3,4,5,6,7,8").split(",")]
 ONLY_FLAVOUR = os.environ.get("B2PT_ONLY_FLAVOUR", "")
 COUNTER_BUILDS = [0] if os.environ.get("B2PT_NO_COUNTERS") else [0, 1]
-UNIT_FEATURE = {1: None, 2: "-DB2_HAVE_PRINCIPLED", 3: "-DB2_HAVE_RIS", 4: "-DB2_HAVE_RESTIR_DI", 5: "-DB2_HAVE_RESTIR_DI"}
+UNIT_FEATURE = {1: None, 2: "-DB2_HAVE_PRINCIPLED", 3: "-DB2_HAVE_RIS", 4: "-DB2_HAVE_RESTIR_DI", 5: "-DB2_HAVE_RESTIR_DI",
+                6: "-DB2_HAVE_RESTIR_DI", 7: "-DB2_HAVE_RESTIR_DI", 8: "-DB2_HAVE_RESTIR_DI"}
 
 
 def kernel_units(feats):

@@ -670,7 +670,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
         for (int i = 0; i < unit.count; i++)
         {
             const B2KernelEntry& e = unit.entries[i];
-            bool later_matters = e.direct == 5; /* LSS_RESTIR_DI */
+            bool later_matters = e.direct == 5 && pass == B2_PASS_MEGAKERNEL; /* LSS_RESTIR_DI: ReSTIR_DI_LaterBouncesSamplingStrategy is read by the MegaKernel only */
             if (e.pass == pass && e.bsdf_override == bsdf && e.direct == direct && e.base == base && (!later_matters || e.later == later) && e.envmap == envmap && e.counters == (counters ? 1 : 0))
             {
                 b2pt_kernel* k = new b2pt_kernel();

@@ -744,6 +744,9 @@ struct Reg
     Reg<BSDF, DIRECT, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_CAMERA_RAYS>(),    \
     Reg<BSDF, DIRECT, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_MEGAKERNEL>()
 
+/* ReSTIR DI with another ReSTIR_DI_LaterBouncesSamplingStrategy: only the MegaKernel reads it (CameraRays and the ReSTIR DI passes are unit 4's and 5's) */
+#define B2_REG_LATER(BSDF, BASE, LATER, COUNTERS) Reg<BSDF, B2_LSS_RESTIR_DI, BASE, LATER, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_MEGAKERNEL>()
+
 #define B2_REG_RESTIR(BSDF, BASE, COUNTERS)                                                                                       \
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DI_PRESAMPLING>(),        \
     Reg<BSDF, B2_LSS_RESTIR_DI, BASE, B2_LATER_RIS, B2_ESS_ALIAS_TABLE, COUNTERS>::entry<B2_PASS_RESTIR_DIRECTIONAL_REUSE>(),     \
@@ -755,7 +758,7 @@ struct Reg
 /* This translation unit is compiled once per (flavour, B2_UNIT, B2_UNIT_COUNTERS) -- build.py -- so that the variants build in
  * parallel; every object registers its entries (and its own copy of the counter / fault words) with b2_capi.cu at load time. */
 #ifndef B2_UNIT
-#error "define B2_UNIT (1 = c1, 2 = c2, 3 = c3, 4 = c4 MegaKernel + CameraRays, 5 = c4 ReSTIR DI passes)"
+#error "define B2_UNIT (1 = c1, 2 = c2, 3 = c3, 4 = c4 MegaKernel + CameraRays, 5 = c4 ReSTIR DI passes, 6 / 7 / 8 = c4 MegaKernel with later bounces = one light / BSDF / MIS)"
 #endif
 #ifndef B2_UNIT_COUNTERS
 #define B2_UNIT_COUNTERS 0
@@ -775,6 +778,12 @@ static const B2KernelEntry* table(int* count)
         B2_REG_BASIC(B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_UC),
 #elif B2_UNIT == 5
         B2_REG_RESTIR(B2_BSDF_NONE, B2_BASE_POWER, B2_UC),
+#elif B2_UNIT == 6
+        B2_REG_LATER(B2_BSDF_NONE, B2_BASE_POWER, B2_LATER_ONE_LIGHT, B2_UC),
+#elif B2_UNIT == 7
+        B2_REG_LATER(B2_BSDF_NONE, B2_BASE_POWER, B2_LATER_BSDF, B2_UC),
+#elif B2_UNIT == 8
+        B2_REG_LATER(B2_BSDF_NONE, B2_BASE_POWER, B2_LATER_MIS, B2_UC),
 #else
 #error "unknown B2_UNIT"
 #endif

@@ -173,6 +173,10 @@ const VariantKey kVariants[] = {
     { "c4b7", 0, 5, 1, 3, true, false, 7 }, /* asymmetric ratio */
     /* c4 with one of the four ReSTIR DI visibility macros (ReSTIRDIOptions.h:50-84) away from its default; bits: 1 InitialTargetFunctionVisibility,
      * 2 SpatialTargetFunctionVisibility, 4 DoVisibilityReuse, 8 BiasCorrectionUseVisibility (defaults 4 | 8) */
+    /* c4 with ReSTIR_DI_LaterBouncesSamplingStrategy (ReSTIRDIOptions.h:18-21,140) = uniform one light / BSDF only / light + BSDF MIS */
+    { "c4l0", 0, 5, 1, 0, true, false, 4 },
+    { "c4l1", 0, 5, 1, 1, true, false, 4 },
+    { "c4l2", 0, 5, 1, 2, true, false, 4 },
     { "c4v1", 0, 5, 1, 3, true, false, 4, 1 | 4 | 8 }, /* InitialTargetFunctionVisibility on */
     { "c4v2", 0, 5, 1, 3, true, false, 4, 2 | 4 | 8 }, /* SpatialTargetFunctionVisibility on */
     { "c4v3", 0, 5, 1, 3, true, false, 4, 8 },         /* DoVisibilityReuse off */

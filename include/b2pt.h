@@ -146,7 +146,8 @@ int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
  * arguments, args = { &LightPresamplingParameters, &render_data } (ReSTIRDIRenderPass.cpp:441-444); kernels obtained with
  * {"ReSTIR_DI_DoLightPresampling", 1} draw their initial light candidates from render_data's presampled-light buffer.
  * Options are the reference's macro names with integer values, e.g. {"DirectLightSamplingStrategy", 3}; macros not
- * listed take the reference's defaults. Two extra options select the codegen flavour:
+ * listed take the reference's defaults. {"ReSTIR_DI_LaterBouncesSamplingStrategy", 0..3} selects among four precompiled ReSTIR DI
+ * MegaKernels (the other ReSTIR DI entries do not read it). Two extra options select the codegen flavour:
  *   {"B2PT_PRECISE", 1}  (default) IEEE fp32 without FMA contraction: the flavour parity is asserted on;
  *   {"B2PT_PRECISE", 0}  FMA contraction + fast intrinsics.
  *   {"B2PT_COUNTERS", 1} traversal-step counters (rays / nodes / triangles) accumulated into b2pt_counters_read.
@@ -241,7 +242,8 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
 /* variant: "c1" | "c2" | "c3" | "c4" | "c4p" (= c4 + ReSTIR DI light presampling) | "c4b1" "c4b2" "c4b3" "c4b5" "c4b6" "c4b7" (= c4 with
  * ReSTIR_DI_BiasCorrectionWeights 1 / 2 / 3 / 5 / 6 / 7) | "c4v1" .. "c4v5" (= c4 with the ReSTIR DI visibility macros away from their
  * defaults: InitialTargetFunctionVisibility on / SpatialTargetFunctionVisibility on / DoVisibilityReuse off / BiasCorrectionUseVisibility
- * off / the first three together)
+ * off / the first three together) | "c4l0" "c4l1" "c4l2" (= c4 with ReSTIR_DI_LaterBouncesSamplingStrategy 0 / 1 / 2: uniform one light /
+ * BSDF only / light + BSDF MIS at the bounces after the first)
  * (see b2_kernels_body.h); precise: 1 = parity flavour, 0 = fast flavour */
 int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* variant, int precise, b2pt_renderer** out_renderer);
 int b2pt_renderer_destroy(b2pt_renderer* renderer);

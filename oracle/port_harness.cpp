@@ -8,7 +8,8 @@
  * "CUDA codegen / libdevice rounding" differences from logic differences (port vs CUDA must agree to the last
  * transcendental ulp, port vs reference must agree within the parity tolerances).
  * The authoritative oracle is oracle/_ref (reference sources); this one is only as good as its agreement with it,
- * which tests/test_oracle_port.py checks.
+ * which tests/test_oracle.py checks (test_port_oracle_matches_golden and following).
+ * --staged runs the MegaKernel through the stage functions the GPU kernels use (see staged_megakernel_pixel below).
  */
 #include "b2_frame_loop.h"
 #include "b2_host_scene.h"
@@ -28,7 +29,7 @@ struct Args
     int width = 512, height = 512, spp = 1, bounces = 3;
     int win_x0 = 0, win_y0 = 0, win_x1 = -1, win_y1 = -1;
     int threads = 0;
-    bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false, kat = false, confidence_weights = true;
+    bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false, kat = false, confidence_weights = true, staged = false;
     int spatial_passes = 1, neighbors = -1;
     unsigned int seed = 42;
 };
@@ -58,6 +59,7 @@ static Args parse_args(int argc, char** argv)
         else if (k == "--no-jitter") a.no_jitter = true;
         else if (k == "--kat") a.kat = true; /* function-level known-answer dump instead of a render (see run_bsdf_kat) */
         else if (k == "--neighbors") a.neighbors = std::atoi(next());
+        else if (k == "--staged") a.staged = true; /* the MegaKernel through megakernel_stage1 / stage2, the way the GPU kernels run it */
         else if (k == "--no-confidence-weights") a.confidence_weights = false;
         else if (k == "--directional-reuse") a.directional_reuse = true; /* use_adaptive_directional_spatial_reuse + the prepass */
         else { std::fprintf(stderr, "unknown argument %s\n", k.c_str()); std::exit(2); }
@@ -121,8 +123,70 @@ static int restir_options_of(const std::string& variant)
     if (variant == "c4v5") return 1 | 2 | 8;
     return 4 | 8;
 }
-static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant.rfind("c4b", 0) == 0 || variant.rfind("c4v", 0) == 0; }
+static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant.rfind("c4b", 0) == 0 || variant.rfind("c4v", 0) == 0 || variant.rfind("c4l", 0) == 0; }
 static bool g_scene_has_alpha_tested_materials = false; /* = what the renderer passes as B2PT_ALPHA_TEST */
+
+/* The MegaKernel the way the phased and wavefront GPU kernels run it (b2_kernels.cu: megakernel_phased, b2_wavefront.h): one path
+ * carried through begin -> { trace A, stage 1, trace B, stage 2 } with the rays the stages request traced between them, instead of
+ * megakernel_bounce's straight-line code. Same protocol as the device loop: unrequested rays answer "miss", deferred Y only where the
+ * variant has it, the sequential ray only with RIS. */
+template <class V>
+static void staged_megakernel_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
+{
+    const b2pt_render_data& rd = *ctx.rd;
+    if (x >= (uint32_t)rd.render_settings.render_resolution.x || y >= (uint32_t)rd.render_settings.render_resolution.y)
+        return;
+    const uint32_t pixel_index = x + y * (uint32_t)rd.render_settings.render_resolution.x;
+    if (!rd.aux_buffers.pixel_active[pixel_index])
+        return;
+    if (rd.g_buffer.first_hit_prim_index[pixel_index] == -1)
+    {
+        megakernel_primary_miss<V>(ctx, x, y, pixel_index);
+        return;
+    }
+    auto trace = [&](const RayRequest& ray) {
+        B2Hit none;
+        none.t = -1.0f;
+        none.u = none.v = 0.0f;
+        none.prim = -1;
+        none.ng = v3(0.0f);
+        if (ray.kind == B2_RAY_NONE)
+            return none;
+        return b2_trace(ctx, ray.kind == B2_RAY_ANY_HIT, ray.origin, ray.direction, ray.t_max, ray.skip_prim, ray.main_path != 0);
+    };
+    PathState s;
+    BouncePhase<V> ph;
+    bool alive = megakernel_begin<V>(ctx, x, y, s);
+    ph.reset();
+    RayRequest rays[5];
+    for (int k = 0; k < 5; k++)
+        request_none(rays[k]);
+    while (alive)
+    {
+        B2Hit results[5];
+        for (int k = 0; k < 5; k++)
+            results[k] = trace(rays[k]);
+        RayRequest sequential;
+        request_none(sequential);
+        if (!megakernel_stage1<V>(ctx, s, ph, s.payload.bounce > 0 ? &results[0] : nullptr, results[1], results[2], results[3], results[4], sequential))
+        {
+            megakernel_end(ctx, s);
+            break;
+        }
+        RayRequest none;
+        request_none(none);
+        B2Hit sequential_result = trace(Nee<V>::HAS_SEQUENTIAL_RAY ? sequential : none);
+        for (int k = 0; k < 5; k++)
+            request_none(rays[k]);
+        if (!megakernel_stage2<V>(ctx, s, ph, sequential_result, rays[0], rays[1], rays[2], rays[3], rays[4]))
+        {
+            megakernel_end(ctx, s);
+            break;
+        }
+        if (!Nee<V>::HAS_DEFERRED_Y)
+            request_none(rays[2]);
+    }
+}
 
 template <class V>
 static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice& bvh, const Args& a)
@@ -147,7 +211,12 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
 #pragma omp for schedule(dynamic)
         for (int y = a.win_y0; y < a.win_y1; y++)
             for (int x = a.win_x0; x < a.win_x1; x++)
-                b2_run_pass_pixel<V>(pass, ctx, (uint32_t)x, (uint32_t)y);
+            {
+                if (pass == B2_PASS_MEGAKERNEL && a.staged)
+                    staged_megakernel_pixel<V>(ctx, (uint32_t)x, (uint32_t)y);
+                else
+                    b2_run_pass_pixel<V>(pass, ctx, (uint32_t)x, (uint32_t)y);
+            }
 #pragma omp critical
         {
             g_port_counters[0] += local.rays;
@@ -506,6 +575,10 @@ int main(int argc, char** argv)
             for (int index = 0; index < params.number_of_subsets * params.subset_size; index++)
                 restir_di_presample_light<B2VariantC4>(rd, params, (uint32_t)index);
         }
+        /* c4l<N>: ReSTIR_DI_LaterBouncesSamplingStrategy = N (ReSTIRDIOptions.h:18-21,140): only the MegaKernel differs */
+        else if (a.variant == "c4l0" && pass == B2_PASS_MEGAKERNEL) run_pass<B2Variant<B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_LATER_ONE_LIGHT>>(pass, rd, bvh, a);
+        else if (a.variant == "c4l1" && pass == B2_PASS_MEGAKERNEL) run_pass<B2Variant<B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_LATER_BSDF>>(pass, rd, bvh, a);
+        else if (a.variant == "c4l2" && pass == B2_PASS_MEGAKERNEL) run_pass<B2Variant<B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_LATER_MIS>>(pass, rd, bvh, a);
         else if (is_c4(a.variant)) run_pass<B2VariantC4>(pass, rd, bvh, a);
 #endif
         else { std::fprintf(stderr, "unknown variant %s\n", a.variant.c_str()); std::exit(2); }

@@ -41,6 +41,16 @@ def test_port_oracle_matches_golden(built, name, tmp_path):
     assert pixels_not_bit_identical(r["framebuffer"], g["framebuffer"]) == 0
 
 
+@pytest.mark.parametrize("name", [c for c in CASES if "/c4l" in c])
+def test_port_staged_megakernel_matches_golden(built, name, tmp_path):
+    """The later-bounces strategies change the MegaKernel: its stage machine (the form the GPU kernels run, port_harness.cpp --staged)
+    against the fixtures, on the host."""
+    g, meta = load_golden(name)
+    a = _args(meta)
+    r = run_oracle("port", a["variant"], a["scene"], a["width"], a["height"], a["spp"], a["bounces"], tmp_path, (*a["extra"], "--staged"))
+    assert pixels_not_bit_identical(r["framebuffer"], g["framebuffer"]) == 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_precise_matches_golden(b2pt, gpu_ctx, name):

@@ -85,6 +85,12 @@ CASES = [
     ("c4v4_96x54_fused", "c4v4", "cornell_pbr_16x9", 96, 54, 3, 4, []),
     ("c4v4_synenv_96x54_split", "c4v4", "synthetic_20k", 96, 54, 2, 4, ["--no-fused", "--envmap", "data/sky_128x64.b2env"]),
     ("c4v5_synenv_96x54_fused", "c4v5", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
+    # ReSTIR_DI_LaterBouncesSamplingStrategy (ReSTIRDIOptions.h:18-21,140), variants "c4l<N>": 0 = uniform one light, 1 = BSDF only,
+    # 2 = light + BSDF MIS at the bounces after the first (3 = RIS, the default, is c4)
+    ("c4l0_96x54_fused", "c4l0", "cornell_pbr_16x9", 96, 54, 3, 4, []),
+    ("c4l1_synenv_96x54_fused", "c4l1", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
+    ("c4l2_96x54_split", "c4l2", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused"]),
+    ("c4l2_synenv_96x54_fused", "c4l2", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
 ]
 EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
 # fixtures of kernel options added after the round's GPU budget was spent live in tests/golden/options/ and are tested by
