@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """A/B timing of one library build (B2PT_LIB=...) on bench.py's workloads: device ms per sample of the MegaKernel and of the whole
-step, for the flavours the library holds. Used to attribute the precise/fast gap to compiler flags (tools/gpu_flavours.sh)."""
+step, for the flavours the library holds. Used to attribute the precise/fast gap to compiler flags (tools/gpu_runs/gpu_flavours.sh)."""
 import argparse
 import json
 import sys

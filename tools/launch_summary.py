@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Per-kernel summary of an `ncu --metrics gpu__time_duration.sum,... --csv` launch list (tools/gpu_r02m.sh):
+"""Per-kernel summary of an `ncu --metrics gpu__time_duration.sum,... --csv` launch list (tools/gpu_runs/gpu_r02m.sh):
     python tools/launch_summary.py gpurun_out/r02m/launches_c4s.csv > profiles/r02_launches_c4s.md
 Times are cold-cache and serialised (ncu replays every kernel): the SHARE of each kernel is what compares with the live bench."""
 import collections
