@@ -25,7 +25,7 @@
 
 struct Args
 {
-    std::string scene, luts, envmap, dump, variant = "c1";
+    std::string scene, luts, envmap, dump, variant = "c1", cameras;
     int width = 512, height = 512, spp = 1, bounces = 3;
     int win_x0 = 0, win_y0 = 0, win_x1 = -1, win_y1 = -1;
     int threads = 0;
@@ -59,6 +59,7 @@ static Args parse_args(int argc, char** argv)
         else if (k == "--no-jitter") a.no_jitter = true;
         else if (k == "--kat") a.kat = true; /* function-level known-answer dump instead of a render (see run_bsdf_kat) */
         else if (k == "--neighbors") a.neighbors = std::atoi(next());
+        else if (k == "--cameras") a.cameras = next(); /* a moving camera: one B2SceneCamera (52 floats) per frame, as ref_extras_* takes it */
         else if (k == "--staged") a.staged = true; /* the MegaKernel through megakernel_stage1 / stage2, the way the GPU kernels run it */
         else if (k == "--no-confidence-weights") a.confidence_weights = false;
         else if (k == "--directional-reuse") a.directional_reuse = true; /* use_adaptive_directional_spatial_reuse + the prepass */
@@ -609,9 +610,29 @@ int main(int argc, char** argv)
         }
     };
 
+    std::vector<B2SceneCamera> camera_frames;
+    if (!a.cameras.empty())
+    {
+        FILE* f = std::fopen(a.cameras.c_str(), "rb");
+        if (!f) { std::fprintf(stderr, "cannot read camera file %s\n", a.cameras.c_str()); return 1; }
+        B2SceneCamera c;
+        while (std::fread(&c, sizeof(c), 1, f) == 1)
+            camera_frames.push_back(c);
+        std::fclose(f);
+    }
+
     auto start = std::chrono::high_resolution_clock::now();
     for (frame = 1; frame <= a.spp; frame++)
     {
+        if (!camera_frames.empty())
+        {
+            const B2SceneCamera& c = camera_frames[std::min<size_t>((size_t)(frame - 1), camera_frames.size() - 1)];
+            std::memcpy(loop.camera.inverse_view, c.inverse_view, 64);
+            std::memcpy(loop.camera.inverse_projection, c.inverse_projection, 64);
+            std::memcpy(loop.camera.view_projection, c.view_projection, 64);
+            loop.camera.position = b2pt_float3{ c.position[0], c.position[1], c.position[2] };
+            loop.camera.vertical_fov = c.vertical_fov;
+        }
         loop.render_one_sample(launch);
         if (a.dump_per_sample)
         {

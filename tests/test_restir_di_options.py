@@ -51,6 +51,16 @@ def test_port_staged_megakernel_matches_golden(built, name, tmp_path):
     assert pixels_not_bit_identical(r["framebuffer"], g["framebuffer"]) == 0
 
 
+@pytest.mark.parametrize("neighbors", [0, 6, 7, 40])
+def test_port_matches_reference_for_neighbour_counts(built, tmp_path, neighbors):
+    """The fused pass has two forms: cut at its rays for up to 6 neighbours (8 table entries with the temporal neighbour and the centre
+    pixel), in one piece beyond; 40 is past the 32-bit heuristics cache too (FusedSpatiotemporalReuse.h:329-366). Reference run live."""
+    extra = ("--neighbors", str(neighbors))
+    ref = run_oracle("ref", "c4", "cornell_pbr_16x9", 96, 54, 3, 4, tmp_path, extra)
+    port = run_oracle("port", "c4", "cornell_pbr_16x9", 96, 54, 3, 4, tmp_path, extra)
+    assert pixels_not_bit_identical(port["framebuffer"], ref["framebuffer"]) == 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_precise_matches_golden(b2pt, gpu_ctx, name):
