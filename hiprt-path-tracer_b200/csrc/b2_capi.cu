@@ -611,6 +611,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
     }
     /* reference defaults */
     int bsdf = 0, direct = 4, base = 1, later = 3, envmap = 2, precise = 1, counters = 0, light_presampling = 0, alpha_test = 0, bias_correction = 4, restir_options = 4 | 8;
+    int presampling_strategy = 1; /* ReSTIR_DI_LightPresamplingStrategy: LSS_BASE_POWER */
     for (int i = 0; i < option_count; i++)
     {
         const char* n = options[i].name;
@@ -622,6 +623,7 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
         else if (!std::strcmp(n, "ReSTIR_DI_LaterBouncesSamplingStrategy")) later = v;
         else if (!std::strcmp(n, "EnvmapSamplingStrategy")) envmap = v;
         else if (!std::strcmp(n, "ReSTIR_DI_DoLightPresampling")) light_presampling = v != 0; /* launch-time switch of the same kernels */
+        else if (!std::strcmp(n, "ReSTIR_DI_LightPresamplingStrategy")) presampling_strategy = v; /* 0 uniform, 1 power alias table: launch-time too */
         else if (!std::strcmp(n, "B2PT_PRECISE")) precise = v;
         else if (!std::strcmp(n, "B2PT_ALPHA_TEST")) alpha_test = v != 0; /* launch-time switch of the same kernels */
         else if (!std::strcmp(n, "ReSTIR_DI_BiasCorrectionWeights")) bias_correction = v; /* launch-time switch of the reuse passes */
@@ -654,6 +656,13 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
     /* ReSTIR_DI_BiasCorrectionWeights (ReSTIRDIOptions.h:9-16): 1/Z, MIS-like, generalised balance heuristic, pairwise MIS (the default),
      * defensive pairwise MIS and the symmetric / asymmetric ratio heuristics are built for the temporal, spatial and fused spatiotemporal
      * reuse passes; 1/M does not compile in the reference itself (SpatialReuse.h:237 calls its normalisation with 6 of 7 arguments) */
+    if (presampling_strategy != 0 && presampling_strategy != 1)
+    {
+        b2_set_error("no precompiled variant with ReSTIR_DI_LightPresamplingStrategy=%d (uniform = 0 and power = 1 are built)", presampling_strategy);
+        return B2PT_ERR_NO_VARIANT;
+    }
+    if (light_presampling && presampling_strategy == 0)
+        light_presampling = 2;
     {
         const bool built = bias_correction >= 1 && bias_correction <= 7;
         const bool reuse_pass = pass == B2_PASS_RESTIR_DI_TEMPORAL || pass == B2_PASS_RESTIR_DI_SPATIAL || pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL;

@@ -245,7 +245,8 @@ struct Ctx
     int stack_stride;              /* distance between this thread's consecutive slots */
     B2TraversalCounters* counters; /* null unless the instrumented variant runs */
     unsigned int* faults;          /* B2_FAULT_COUNT words (device global / host array) or null */
-    bool light_presampling;        /* ReSTIR_DI_DoLightPresampling: initial candidates come from the presampled light buffer */
+    int light_presampling;         /* ReSTIR_DI_DoLightPresampling: initial candidates come from the presampled light buffer (1: presampled with the
+                                    * power alias table, 2: uniformly -- ReSTIR_DI_LightPresamplingStrategy) */
     int bias_correction;           /* ReSTIR_DI_BiasCorrectionWeights (B2_BIAS_*, b2_restir_di.h): a launch-time switch of the reuse passes */
     int restir_options;  /* B2_DI_OPT_* (b2_restir_di.h): the four ReSTIR DI visibility macros of ReSTIRDIOptions.h:50-84 */
     bool alpha_test;               /* the kernel was asked for alpha testing (B2PT_ALPHA_TEST: the scene has materials that are not fully opaque) */

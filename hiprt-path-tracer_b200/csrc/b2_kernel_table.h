@@ -18,7 +18,7 @@ struct B2LaunchGeom
     int row_count;
     int pool_rays;      /* phased MegaKernel: ray-pool slots per thread (3; 5 when the world has an envmap: its two MIS shadow rays) */
     int stack_entries; /* phased MegaKernel: traversal-stack entries per thread (BVH depth + 1 when known, else B2_STACK_ENTRIES) */
-    int light_presampling; /* ReSTIR DI initial candidates: take light candidates from the presampled buffer */
+    int light_presampling; /* ReSTIR DI initial candidates: take light candidates from the presampled buffer (1; 2 = presampled uniformly, ReSTIR_DI_LightPresamplingStrategy) */
     int bias_correction;   /* ReSTIR_DI_BiasCorrectionWeights of the ReSTIR DI reuse passes (ReSTIRDIOptions.h:9-16; 4 = pairwise MIS, the default) */
     int restir_options;    /* ReSTIR DI passes: B2_DI_OPT_* bits (InitialTargetFunctionVisibility, SpatialTargetFunctionVisibility, DoVisibilityReuse, BiasCorrectionUseVisibility) */
     int alpha_test;        /* the scene has materials that are not fully opaque: candidate hits go through the alpha test (b2_bvh.h) */

@@ -81,7 +81,7 @@ __device__ __forceinline__ void b2_make_ctx(Ctx& ctx, const b2pt_render_data& rd
     ctx.stack_stride = threads;
     ctx.counters = counters;
     ctx.faults = faults;
-    ctx.light_presampling = false;
+    ctx.light_presampling = 0;
     ctx.alpha_test = alpha_test; /* kernels that were asked for alpha testing (B2PT_ALPHA_TEST) */
     ctx.bias_correction = 4;     /* RESTIR_DI_BIAS_CORRECTION_PAIRWISE_MIS; the pixel kernels of the reuse passes take the launch's */
     ctx.restir_options = 4 | 8;  /* B2_DI_OPT_DEFAULTS, likewise */
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS, B2_PASS_MIN_BLOCKS) pass_ker
 
     Ctx ctx;
     b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
-    ctx.light_presampling = geom.light_presampling != 0;
+    ctx.light_presampling = geom.light_presampling;
     ctx.bias_correction = geom.bias_correction;
     ctx.restir_options = geom.restir_options;
 
@@ -604,9 +604,9 @@ __global__ void __launch_bounds__(B2_MK_THREADS, B2_MK_MIN_BLOCKS) megakernel_ph
 /* ReSTIR_DI_LightsPresampling: one thread per presampled light (kernels/ReSTIR/DI/LightsPresampling.h:78-110); arguments in the
  * reference's order (LightPresamplingParameters, HIPRTRenderData) */
 template <class V>
-__global__ void __launch_bounds__(128) lights_presampling_kernel(const B2LightPresamplingParameters params, const __grid_constant__ b2pt_render_data rd)
+__global__ void __launch_bounds__(128) lights_presampling_kernel(const B2LightPresamplingParameters params, const __grid_constant__ b2pt_render_data rd, int uniform_strategy)
 {
-    restir_di_presample_light<V>(rd, params, blockIdx.x * blockDim.x + threadIdx.x);
+    restir_di_presample_light<V>(rd, params, blockIdx.x * blockDim.x + threadIdx.x, uniform_strategy != 0);
 }
 
 /* ReSTIR_Directional_Reuse_Compute: one thread per pixel, 8x8 tiles; arguments in the reference's order (render data, 32-bit masks
@@ -651,7 +651,7 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
             if (count <= 0)
                 return cudaSuccess;
             g_cuda_launches += 1;
-            lights_presampling_kernel<V><<<(count + 127) / 128, 128, 0, stream>>>(params, *rd);
+            lights_presampling_kernel<V><<<(count + 127) / 128, 128, 0, stream>>>(params, *rd, g.light_presampling == 2 ? 1 : 0);
             return cudaGetLastError();
         }
         return cudaErrorInvalidValue;

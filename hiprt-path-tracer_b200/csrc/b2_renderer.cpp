@@ -156,13 +156,14 @@ void free_all(b2pt_renderer* r, std::vector<void*>& owner)
     owner.clear();
 }
 
-struct VariantKey { const char* name; int bsdf, direct, base, later; bool restir; bool presampling; int bias_correction; int restir_options = 4 | 8; };
+struct VariantKey { const char* name; int bsdf, direct, base, later; bool restir; bool presampling; int bias_correction; int restir_options = 4 | 8; int presampling_strategy = 1; };
 const VariantKey kVariants[] = {
     { "c1", 1, 1, 0, 3, false, false, 4 },
     { "c2", 0, 3, 1, 3, false, false, 4 },
     { "c3", 0, 4, 1, 3, false, false, 4 },
     { "c4", 0, 5, 1, 3, true, false, 4 },
     { "c4p", 0, 5, 1, 3, true, true, 4 }, /* c4 with ReSTIR_DI_DoLightPresampling */
+    { "c4pu", 0, 5, 1, 3, true, true, 4, 4 | 8, 0 }, /* ... and ReSTIR_DI_LightPresamplingStrategy = LSS_BASE_UNIFORM */
     /* c4 with another ReSTIR_DI_BiasCorrectionWeights (ReSTIRDIOptions.h:9-16): 1/Z, MIS-like, generalised balance heuristic, defensive
      * pairwise MIS, symmetric and asymmetric ratio */
     { "c4b1", 0, 5, 1, 3, true, false, 1 },
@@ -232,7 +233,7 @@ int resolve_kernels(b2pt_renderer* r)
             { "BSDFOverride", v->bsdf }, { "DirectLightSamplingStrategy", v->direct }, { "DirectLightSamplingBaseStrategy", v->base },
             { "ReSTIR_DI_LaterBouncesSamplingStrategy", v->later }, { "ReSTIR_DI_DoLightPresampling", v->presampling ? 1 : 0 },
             { "B2PT_PRECISE", r->precise }, { "B2PT_COUNTERS", r->counters }, { "B2PT_ALPHA_TEST", r->alpha_test ? 1 : 0 },
-            { "ReSTIR_DI_BiasCorrectionWeights", v->bias_correction },
+            { "ReSTIR_DI_BiasCorrectionWeights", v->bias_correction }, { "ReSTIR_DI_LightPresamplingStrategy", v->presampling_strategy },
             { "ReSTIR_DI_InitialTargetFunctionVisibility", (v->restir_options & 1) ? 1 : 0 }, { "ReSTIR_DI_SpatialTargetFunctionVisibility", (v->restir_options & 2) ? 1 : 0 },
             { "ReSTIR_DI_DoVisibilityReuse", (v->restir_options & 4) ? 1 : 0 }, { "ReSTIR_DI_BiasCorrectionUseVisibility", (v->restir_options & 8) ? 1 : 0 },
         };

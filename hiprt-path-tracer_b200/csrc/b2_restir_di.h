@@ -575,8 +575,13 @@ struct B2LightPresamplingParameters
 static_assert(sizeof(B2LightPresamplingParameters) == 24, "LightPresamplingParameters is 24 bytes");
 
 /* One thread per presampled light: LightsPresampling.h:78-110 (presample_envmap :27-41, presample_emissive_triangle :43-64) */
+/* ReSTIR_DI_LightPresamplingStrategy (ReSTIRDIOptions.h:162) = LSS_BASE_UNIFORM: the variant with that base strategy, for the two
+ * places that read the macro (LightsPresampling.h:44, InitialCandidates.h:364) */
 template <class V>
-B2_HD void restir_di_presample_light(const b2pt_render_data& rd, const B2LightPresamplingParameters& params, uint32_t x)
+using B2UniformBase = B2Variant<V::BSDF_OVERRIDE, V::DIRECT, B2_BASE_UNIFORM, V::LATER, V::ENVMAP, V::COUNTERS>;
+
+template <class V>
+B2_HD void restir_di_presample_light(const b2pt_render_data& rd, const B2LightPresamplingParameters& params, uint32_t x, bool uniform_strategy = false)
 {
     if (rd.buffers.emissive_triangles_count == 0 && rd.world_settings.ambient_light_type != 2)
         return;
@@ -609,7 +614,7 @@ B2_HD void restir_di_presample_light(const b2pt_render_data& rd, const B2LightPr
     }
     else
     {
-        LightSample sample = sample_one_emissive_triangle<V>(rd, rng);
+        LightSample sample = uniform_strategy ? sample_one_emissive_triangle<B2UniformBase<V>>(rd, rng) : sample_one_emissive_triangle<V>(rd, rng);
         if (sample.area_measure_pdf > 0.0f)
         {
             light.px = sample.point_on_light.x; light.py = sample.point_on_light.y; light.pz = sample.point_on_light.z;
@@ -921,7 +926,8 @@ B2_HD void di_initial_bsdf_candidate_finish(const Ctx& ctx, const Payload& paylo
         float light_pdf_solid_angle = 0.0f;
         bool refraction_sampled = dot(bsdf_sampled_direction, hit.shading_normal) < 0.0f;
         if (!refraction_sampled)
-            light_pdf_solid_angle = pdf_of_emissive_triangle_hit_solid_angle<V>(rd, light_hit, bsdf_sampled_direction);
+            light_pdf_solid_angle = ctx.light_presampling == 2 ? pdf_of_emissive_triangle_hit_solid_angle<B2UniformBase<V>>(rd, light_hit, bsdf_sampled_direction)
+                                                               : pdf_of_emissive_triangle_hit_solid_angle<V>(rd, light_hit, bsdf_sampled_direction);
 
         float target_function = bsdf_RIS_sample.target_function;
         if (bsdf_sample_pdf_solid_angle <= 0.0f || !check_minimum_light_contribution(rd.render_settings.minimum_light_contribution, target_function / light_pdf_solid_angle / bsdf_sample_pdf_solid_angle))

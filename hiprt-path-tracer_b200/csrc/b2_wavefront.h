@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_a(const __grid_const
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
     Ctx ctx;
     b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
-    ctx.light_presampling = geom.light_presampling != 0;
+    ctx.light_presampling = geom.light_presampling;
     uint32_t x, y;
     const int slot = wf_list_pixel(geom, b, x, y);
     RayRequest rays[P::RAYS];
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(B2_BLOCK_THREADS) wf_pass_b(const __grid_const
     local_counters.rays = local_counters.nodes = local_counters.tris = 0;
     Ctx ctx;
     b2_make_ctx(ctx, rd, stacks, V::COUNTERS ? &local_counters : nullptr, g_faults, B2_BLOCK_THREADS, geom.alpha_test != 0);
-    ctx.light_presampling = geom.light_presampling != 0;
+    ctx.light_presampling = geom.light_presampling;
     uint32_t x, y;
     const int slot = wf_list_pixel(geom, b, x, y);
     RayRequest final_ray;

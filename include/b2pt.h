@@ -162,7 +162,9 @@ int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
  * compile) answers B2PT_ERR_NO_VARIANT.
  * {"ReSTIR_DI_InitialTargetFunctionVisibility", 0|1}, {"ReSTIR_DI_SpatialTargetFunctionVisibility", 0|1}, {"ReSTIR_DI_DoVisibilityReuse", 0|1},
  * {"ReSTIR_DI_BiasCorrectionUseVisibility", 0|1} (ReSTIRDIOptions.h:50-84; defaults 0, 0, 1, 1): launch-time switches of the ReSTIR DI
- * passes; give the same values to every ReSTIR DI kernel of a renderer, as the reference's global compiler options do. */
+ * passes; give the same values to every ReSTIR DI kernel of a renderer, as the reference's global compiler options do.
+ * {"ReSTIR_DI_LightPresamplingStrategy", 0|1} (:162; LSS_BASE_UNIFORM / LSS_BASE_POWER, the default): how "ReSTIR_DI_LightsPresampling" picks
+ * its emissive triangles, and the matching pdf in "ReSTIR_DI_InitialCandidates" -- launch-time as well. */
 typedef struct
 {
     const char* name;
@@ -239,7 +241,7 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
  * (2) headless renderer (host mirror of GPURenderer, CPURenderer pass order)
  * ------------------------------------------------------------------------------------------------------------ */
 
-/* variant: "c1" | "c2" | "c3" | "c4" | "c4p" (= c4 + ReSTIR DI light presampling) | "c4b1" "c4b2" "c4b3" "c4b5" "c4b6" "c4b7" (= c4 with
+/* variant: "c1" | "c2" | "c3" | "c4" | "c4p" (= c4 + ReSTIR DI light presampling) | "c4pu" (= c4p with uniform instead of power presampling) | "c4b1" "c4b2" "c4b3" "c4b5" "c4b6" "c4b7" (= c4 with
  * ReSTIR_DI_BiasCorrectionWeights 1 / 2 / 3 / 5 / 6 / 7) | "c4v1" .. "c4v5" (= c4 with the ReSTIR DI visibility macros away from their
  * defaults: InitialTargetFunctionVisibility on / SpatialTargetFunctionVisibility on / DoVisibilityReuse off / BiasCorrectionUseVisibility
  * off / the first three together) | "c4l0" "c4l1" "c4l2" (= c4 with ReSTIR_DI_LaterBouncesSamplingStrategy 0 / 1 / 2: uniform one light /

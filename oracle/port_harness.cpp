@@ -124,7 +124,7 @@ static int restir_options_of(const std::string& variant)
     if (variant == "c4v5") return 1 | 2 | 8;
     return 4 | 8;
 }
-static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant.rfind("c4b", 0) == 0 || variant.rfind("c4v", 0) == 0 || variant.rfind("c4l", 0) == 0; }
+static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant == "c4pu" || variant.rfind("c4b", 0) == 0 || variant.rfind("c4v", 0) == 0 || variant.rfind("c4l", 0) == 0; }
 static bool g_scene_has_alpha_tested_materials = false; /* = what the renderer passes as B2PT_ALPHA_TEST */
 
 /* The MegaKernel the way the phased and wavefront GPU kernels run it (b2_kernels.cu: megakernel_phased, b2_wavefront.h): one path
@@ -204,7 +204,7 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
         local.rays = local.nodes = local.tris = 0;
         ctx.counters = &local;
         ctx.faults = g_port_faults;
-        ctx.light_presampling = a.variant == "c4p";
+        ctx.light_presampling = a.variant == "c4p" ? 1 : a.variant == "c4pu" ? 2 : 0; /* c4pu: ReSTIR_DI_LightPresamplingStrategy = LSS_BASE_UNIFORM */
         ctx.bias_correction = bias_correction_of(a.variant);
         ctx.restir_options = restir_options_of(a.variant);
         ctx.alpha_test = g_scene_has_alpha_tested_materials;
@@ -526,7 +526,7 @@ int main(int argc, char** argv)
     }
 #endif
     loop.restir_di = is_c4(a.variant);
-    loop.restir_di_presampling = a.variant == "c4p";
+    loop.restir_di_presampling = a.variant == "c4p" || a.variant == "c4pu";
     std::vector<unsigned long long> directional_masks((size_t)a.width * a.height, 0ull);
     std::vector<uint8_t> directional_radius((size_t)a.width * a.height, 0);
     rd.render_settings.restir_di_settings.common_spatial_pass.per_pixel_spatial_reuse_directions_mask_ull = directional_masks.data();
@@ -574,7 +574,7 @@ int main(int argc, char** argv)
             params.envmap_sampling_probability = di.initial_candidates.envmap_candidate_probability;
 #pragma omp parallel for schedule(static)
             for (int index = 0; index < params.number_of_subsets * params.subset_size; index++)
-                restir_di_presample_light<B2VariantC4>(rd, params, (uint32_t)index);
+                restir_di_presample_light<B2VariantC4>(rd, params, (uint32_t)index, a.variant == "c4pu");
         }
         /* c4l<N>: ReSTIR_DI_LaterBouncesSamplingStrategy = N (ReSTIRDIOptions.h:18-21,140): only the MegaKernel differs */
         else if (a.variant == "c4l0" && pass == B2_PASS_MEGAKERNEL) run_pass<B2Variant<B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_LATER_ONE_LIGHT>>(pass, rd, bvh, a);
@@ -583,7 +583,8 @@ int main(int argc, char** argv)
         else if (is_c4(a.variant)) run_pass<B2VariantC4>(pass, rd, bvh, a);
 #endif
         else { std::fprintf(stderr, "unknown variant %s\n", a.variant.c_str()); std::exit(2); }
-        if (a.dump_per_sample && !a.dump.empty() && pass != B2_PASS_CAMERA_RAYS && pass != B2_PASS_MEGAKERNEL)
+        if (a.dump_per_sample && !a.dump.empty() &&
+            (pass == B2_PASS_RESTIR_DI_INITIAL_CANDIDATES || pass == B2_PASS_RESTIR_DI_TEMPORAL || pass == B2_PASS_RESTIR_DI_SPATIAL || pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL))
         {
             /* same files as oracle/ref_harness.cpp::dump_pass_reservoirs, transposed from the SoA planes to 36-byte records */
             const b2pt_restir_di_settings& di = rd.render_settings.restir_di_settings;

@@ -65,8 +65,8 @@ def run_oracle(kind, variant, scene, width, height, spp, bounces, tmp_path, extr
     """kind: 'ref' (reference sources compiled in place), 'extras' (the same harness + --cameras / --repeat, a separate binary)
     or 'port' (host build of the product headers). scene: a name under data/ or the path of a .b2scene blob."""
     prefix = str(tmp_path / f"{kind}_")
-    if kind in ("ref", "extras"):
-        exe = REF_DIR / f"ref_{'render' if kind == 'ref' else 'extras'}_{variant}"
+    if kind in ("ref", "extras", "zero"):  # zero: the extras harness with every automatic variable zero-initialised (oracle/Makefile)
+        exe = REF_DIR / f"ref_{ {'ref': 'render', 'extras': 'extras', 'zero': 'zero'}[kind] }_{variant}"
         cmd = [str(exe)]
     else:
         exe = PORT_EXE

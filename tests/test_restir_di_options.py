@@ -38,7 +38,8 @@ def test_port_oracle_matches_golden(built, name, tmp_path):
     assert np.array_equal(r["geometric_normal"], g["gbuffer_geometric_normal"])
     assert np.array_equal(r["shading_normal"], g["gbuffer_shading_normal"])
     assert np.array_equal(r["material"], g["gbuffer_material"])
-    assert pixels_not_bit_identical(r["framebuffer"], g["framebuffer"]) == 0
+    # light presampling: one pixel follows an uninitialised read of the reference (tests/test_oracle.py::test_port_matches_zero_initialised_reference)
+    assert pixels_not_bit_identical(r["framebuffer"], g["framebuffer"]) <= (1 if "/c4pu" in name else 0)
 
 
 @pytest.mark.parametrize("name", [c for c in CASES if "/c4l" in c])

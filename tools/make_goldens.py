@@ -91,11 +91,14 @@ CASES = [
     ("c4l1_synenv_96x54_fused", "c4l1", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
     ("c4l2_96x54_split", "c4l2", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused"]),
     ("c4l2_synenv_96x54_fused", "c4l2", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
+    # ReSTIR_DI_LightPresamplingStrategy = LSS_BASE_UNIFORM (variant "c4pu" = c4p with uniform presampling)
+    ("c4pu_synenv_96x54_fused", "c4pu", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
+    ("c4pu_96x54_split", "c4pu", "cornell_pbr_16x9", 96, 54, 2, 4, ["--no-fused"]),
 ]
 EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
 # fixtures of kernel options added after the round's GPU budget was spent live in tests/golden/options/ and are tested by
 # tests/test_restir_di_options.py, which runs after the suites whose CUDA side has been seen green on a B200
-OPTIONS_PREFIXES = ("c4v", "c4l")
+OPTIONS_PREFIXES = ("c4v", "c4l", "c4pu")
 
 
 def run_case(name, variant, scene, w, h, spp, bounces, extra):
