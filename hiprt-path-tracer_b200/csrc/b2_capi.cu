@@ -572,7 +572,7 @@ static const MacroDefault kFixedMacros[] = {
     { "DirectLightSamplingNEESampleCount", 1 }, { "DirectLightSamplingDeltaDistributionOptimization", 1 },
     { "DirectLightSamplingAllowBackfacingLights", 0 }, { "TrianglePointSamplingStrategy", 1 }, { "EnvmapSamplingDoBSDFMIS", 1 },
     { "EnvmapSamplingDoBilinearFiltering", 0 }, { "PathSamplingStrategy", 0 }, { "RISUseVisiblityTargetFunction", 0 },
-    { "NestedDielectricsStackSize", 4 }, { "UseSharedStackBVHTraversal", 1 }, { "KernelBlockWidthHeight", 8 },
+    { "NestedDielectricsStackSize", 4 }, { "UseSharedStackBVHTraversal", 1 }, { "KernelWorkgroupThreadCount", 64 },
     { "PrincipledBSDFDiffuseLobe", 0 }, { "PrincipledBSDFAnisotropicGGXSampleFunction", 0 }, { "PrincipledBSDFDoEnergyCompensation", 1 },
     { "PrincipledBSDFDoGlassEnergyCompensation", 1 }, { "PrincipledBSDFDoClearcoatEnergyCompensation", 1 },
     { "PrincipledBSDFDoMetallicEnergyCompensation", 1 }, { "PrincipledBSDFDoMetallicFresnelEnergyCompensation", 1 },
@@ -596,9 +596,55 @@ static int pass_of_entry_name(const char* name)
     return -1;
 }
 
-int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* options, int option_count, b2pt_kernel** out_kernel)
+/* The macro names b2pt_kernel_get understands: the ones it switches on (below) and the ones it only accepts at the reference's default.
+ * A binding of the reference's GPUKernel passes these and leaves the rest of GPUKernelCompilerOptions::ALL_MACROS_NAMES out, the way the
+ * reference passes a kernel only the macros its source reads (GPUKernel::parse_option_macros_used). */
+static const char* const kSwitchedMacros[] = {
+    "BSDFOverride", "DirectLightSamplingStrategy", "DirectLightSamplingBaseStrategy", "ReSTIR_DI_LaterBouncesSamplingStrategy", "EnvmapSamplingStrategy",
+    "ReSTIR_DI_DoLightPresampling", "ReSTIR_DI_LightPresamplingStrategy", "ReSTIR_DI_BiasCorrectionWeights", "ReSTIR_DI_InitialTargetFunctionVisibility",
+    "ReSTIR_DI_SpatialTargetFunctionVisibility", "ReSTIR_DI_DoVisibilityReuse", "ReSTIR_DI_BiasCorrectionUseVisibility",
+};
+
+int b2pt_kernel_option_names(const char* const** out_names, int* out_count)
 {
-    if (!ctx || !entry_name || !out_kernel || option_count < 0 || (option_count > 0 && !options))
+    if (!out_names || !out_count) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    static std::vector<const char*> names;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* n : kSwitchedMacros)
+            names.push_back(n);
+        for (const MacroDefault& m : kFixedMacros)
+            names.push_back(m.name);
+    });
+    *out_names = names.data();
+    *out_count = (int)names.size();
+    return B2PT_OK;
+}
+
+int b2pt_kernel_option_fixed_value(const char* name, int* out_value)
+{
+    if (!name || !out_value) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    for (const MacroDefault& m : kFixedMacros)
+        if (!std::strcmp(name, m.name))
+        {
+            *out_value = m.value;
+            return B2PT_OK;
+        }
+    b2_set_error("'%s' is not a macro served at one value only", name);
+    return B2PT_ERR_NO_VARIANT;
+}
+
+/* Entry name + macro values -> the precompiled entry and the launch-time switches. Host logic only: no context, no CUDA call. */
+struct B2ResolvedKernel
+{
+    const B2KernelEntry* entry = nullptr;
+    int unit_precise = 1;
+    int light_presampling = 0, alpha_test = 0, bias_correction = 4, restir_options = 4 | 8;
+};
+
+static int resolve_kernel(const char* entry_name, const b2pt_option* options, int option_count, B2ResolvedKernel& resolved)
+{
+    if (!entry_name || option_count < 0 || (option_count > 0 && !options))
     {
         b2_set_error("b2pt_kernel_get: invalid argument");
         return B2PT_ERR_INVALID_ARGUMENT;
@@ -682,17 +728,12 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
             bool later_matters = e.direct == 5 && pass == B2_PASS_MEGAKERNEL; /* LSS_RESTIR_DI: ReSTIR_DI_LaterBouncesSamplingStrategy is read by the MegaKernel only */
             if (e.pass == pass && e.bsdf_override == bsdf && e.direct == direct && e.base == base && (!later_matters || e.later == later) && e.envmap == envmap && e.counters == (counters ? 1 : 0))
             {
-                b2pt_kernel* k = new b2pt_kernel();
-                k->ctx = ctx;
-                k->entry = &e;
-                k->light_presampling = light_presampling;
-                k->precise = unit.precise;
-                k->alpha_test = alpha_test;
-                k->bias_correction = bias_correction;
-                k->restir_options = restir_options;
-                B2_CUDA(cudaEventCreate(&k->start));
-                B2_CUDA(cudaEventCreate(&k->stop));
-                *out_kernel = k;
+                resolved.entry = &e;
+                resolved.unit_precise = unit.precise;
+                resolved.light_presampling = light_presampling;
+                resolved.alpha_test = alpha_test;
+                resolved.bias_correction = bias_correction;
+                resolved.restir_options = restir_options;
                 return B2PT_OK;
             }
         }
@@ -701,6 +742,38 @@ int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* op
                  "ReSTIR_DI_LaterBouncesSamplingStrategy=%d EnvmapSamplingStrategy=%d precise=%d counters=%d",
                  entry_name, bsdf, direct, base, later, envmap, precise, counters);
     return B2PT_ERR_NO_VARIANT;
+}
+
+int b2pt_kernel_query(const char* entry_name, const b2pt_option* options, int option_count)
+{
+    B2ResolvedKernel resolved;
+    return resolve_kernel(entry_name, options, option_count, resolved);
+}
+
+int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* options, int option_count, b2pt_kernel** out_kernel)
+{
+    if (!ctx || !out_kernel)
+    {
+        b2_set_error("b2pt_kernel_get: invalid argument");
+        return B2PT_ERR_INVALID_ARGUMENT;
+    }
+    B2ResolvedKernel resolved;
+    int rc = resolve_kernel(entry_name, options, option_count, resolved);
+    if (rc != B2PT_OK)
+        return rc;
+    B2_SELECT_DEVICE(ctx);
+    b2pt_kernel* k = new b2pt_kernel();
+    k->ctx = ctx;
+    k->entry = resolved.entry;
+    k->light_presampling = resolved.light_presampling;
+    k->precise = resolved.unit_precise;
+    k->alpha_test = resolved.alpha_test;
+    k->bias_correction = resolved.bias_correction;
+    k->restir_options = resolved.restir_options;
+    B2_CUDA(cudaEventCreate(&k->start));
+    B2_CUDA(cudaEventCreate(&k->stop));
+    *out_kernel = k;
+    return B2PT_OK;
 }
 
 /* Form of the MegaKernel (all four render bit-identical frames, tests/test_gpu_parity.py):

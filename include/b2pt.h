@@ -172,6 +172,16 @@ typedef struct
 } b2pt_option;
 
 int b2pt_kernel_get(b2pt_ctx* ctx, const char* entry_name, const b2pt_option* options, int option_count, b2pt_kernel** out_kernel);
+/* Would b2pt_kernel_get find a variant? Same answer and same error text, without a context or a device: what a host asks before it
+ * offers a combination of options (and what the CPU tests walk the option surface with). */
+int b2pt_kernel_query(const char* entry_name, const b2pt_option* options, int option_count);
+/* The macro names b2pt_kernel_get understands (static storage). Stands in for GPUKernel::parse_option_macros_used -> GPUKernelCompiler::
+ * get_option_macros_used_by_kernel (src/Compiler/GPUKernel.cpp:176-180), which finds the macros a kernel reads by parsing its source: a
+ * binding passes these and leaves the other entries of GPUKernelCompilerOptions::ALL_MACROS_NAMES (ReGIR, ReSTIR GI, GMoN ...) out. */
+int b2pt_kernel_option_names(const char* const** out_names, int* out_count);
+/* For a macro that is served at one value only (the reference's default): that value; B2PT_ERR_NO_VARIANT for the switched ones. Lets a
+ * binding check at start-up that the defaults it was built against are the ones the kernels were built with (oracle/binding_check.cpp). */
+int b2pt_kernel_option_fixed_value(const char* name, int* out_value);
 /* args[0] must point to a host HIPRTRenderData / b2pt_render_data (2784 bytes, passed by value to the kernel).
  * block_x / block_y are accepted for interface compatibility; the B200 kernels choose their own thread->pixel map. */
 int b2pt_kernel_launch(b2pt_kernel* kernel, int block_x, int block_y, int width, int height, void** args, b2pt_stream stream);

@@ -17,6 +17,14 @@
 
 #include "b2pt.h"
 
+#ifdef B2_BOUNDARY_GPUKERNEL
+/* boundary_gpukernel_<variant>: the same program with every kernel held, "compiled" and launched as a reference GPUKernel object
+ * (src/Compiler/GPUKernel.h, bound to this library by hiprt-path-tracer_b200/binding/GPUKernel_b2pt.cpp) and the macros set through the
+ * reference's GPUKernelCompilerOptions, the way GPURenderer and its render passes do (GPURenderer.cpp:482-501,
+ * MegaKernelRenderPass.cpp:20-60, ReSTIRDIRenderPass.cpp:21-140) */
+#include "Compiler/GPUKernel.h"
+#endif
+
 #define CHECK(call)                                                                                     \
     do                                                                                                  \
     {                                                                                                   \
@@ -215,6 +223,48 @@ int main(int argc, char** argv)
     rd.light_GPU_BVH = nullptr;
     rd.cpu_only = decltype(rd.cpu_only)();
 
+#ifdef B2_BOUNDARY_GPUKERNEL
+    /* the renderer's global compiler options, shared with every kernel (GPURenderer::m_global_compiler_options); the values of this
+     * build's strategy macros are set the way the ImGui panels set them */
+    auto hiprt_orochi_ctx = std::make_shared<HIPRTOrochiCtx>();
+    hiprt_orochi_ctx->orochi_ctx = reinterpret_cast<oroCtx>(g_ctx); /* the binding's convention: the context slot carries the b2pt_ctx */
+    auto global_options = std::make_shared<GPUKernelCompilerOptions>();
+    global_options->set_macro_value(GPUKernelCompilerOptions::BSDF_OVERRIDE, (int)BSDFOverride);
+    global_options->set_macro_value(GPUKernelCompilerOptions::DIRECT_LIGHT_SAMPLING_STRATEGY, (int)DirectLightSamplingStrategy);
+    global_options->set_macro_value(GPUKernelCompilerOptions::DIRECT_LIGHT_SAMPLING_BASE_STRATEGY, (int)DirectLightSamplingBaseStrategy);
+    global_options->set_macro_value(GPUKernelCompilerOptions::RESTIR_DI_LATER_BOUNCES_SAMPLING_STRATEGY, (int)ReSTIR_DI_LaterBouncesSamplingStrategy);
+    global_options->set_macro_value(GPUKernelCompilerOptions::ENVMAP_SAMPLING_STRATEGY, (int)EnvmapSamplingStrategy);
+    global_options->set_macro_value(GPUKernelCompilerOptions::RESTIR_DI_BIAS_CORRECTION_WEIGHTS, (int)ReSTIR_DI_BiasCorrectionWeights);
+    global_options->set_macro_value(GPUKernelCompilerOptions::RESTIR_DI_DO_LIGHT_PRESAMPLING, (int)ReSTIR_DI_DoLightPresampling);
+    GPUKernel camera_rays_kernel(std::string(DEVICE_KERNELS_DIRECTORY) + "/CameraRays.h", "CameraRays");
+    GPUKernel megakernel_kernel(std::string(DEVICE_KERNELS_DIRECTORY) + "/Megakernel.h", "MegaKernel");
+    GPUKernel initial_candidates_kernel(std::string(DEVICE_KERNELS_DIRECTORY) + "/ReSTIR/DI/InitialCandidates.h", "ReSTIR_DI_InitialCandidates");
+    GPUKernel spatiotemporal_kernel(std::string(DEVICE_KERNELS_DIRECTORY) + "/ReSTIR/DI/FusedSpatiotemporalReuse.h", "ReSTIR_DI_SpatiotemporalReuse");
+    GPUKernel temporal_kernel(std::string(DEVICE_KERNELS_DIRECTORY) + "/ReSTIR/DI/TemporalReuse.h", "ReSTIR_DI_TemporalReuse");
+    GPUKernel spatial_kernel(std::string(DEVICE_KERNELS_DIRECTORY) + "/ReSTIR/DI/SpatialReuse.h", "ReSTIR_DI_SpatialReuse");
+    auto prepare_kernel = [&](GPUKernel& k) {
+        k.synchronize_options_with(global_options);
+        k.compile(hiprt_orochi_ctx, {}, /* use_cache */ true, /* silent */ false);
+        if (!k.has_been_compiled())
+            std::exit(1);
+    };
+    GPUKernel *camera_rays = &camera_rays_kernel, *megakernel = &megakernel_kernel, *initial_candidates = nullptr, *spatiotemporal = nullptr, *temporal = nullptr, *spatial = nullptr;
+    prepare_kernel(camera_rays_kernel);
+    prepare_kernel(megakernel_kernel);
+#if DirectLightSamplingStrategy == LSS_RESTIR_DI
+    initial_candidates = &initial_candidates_kernel;
+    spatiotemporal = &spatiotemporal_kernel;
+    temporal = &temporal_kernel;
+    spatial = &spatial_kernel;
+    prepare_kernel(initial_candidates_kernel);
+    prepare_kernel(spatiotemporal_kernel);
+    prepare_kernel(temporal_kernel);
+    prepare_kernel(spatial_kernel);
+#endif
+    Xorshift32Generator rng(args.seed);
+    void* launch_args[] = { &rd };
+    auto launch = [&](GPUKernel* k) { k->launch_asynchronous(8, 8, args.width, args.height, launch_args, reinterpret_cast<oroStream_t>(stream)); };
+#else
     /* kernels, by the reference's macro names (GPUKernelCompilerOptions.cpp:19-105) */
     b2pt_option options[] = {
         { "BSDFOverride", (int)BSDFOverride }, { "DirectLightSamplingStrategy", (int)DirectLightSamplingStrategy },
@@ -238,6 +288,7 @@ int main(int argc, char** argv)
     Xorshift32Generator rng(args.seed);
     void* launch_args[] = { &rd };
     auto launch = [&](b2pt_kernel* k) { CHECK(b2pt_kernel_launch(k, 8, 8, args.width, args.height, launch_args, stream)); };
+#endif
     bool odd_frame = false;
     for (int frame = 1; frame <= args.spp; frame++)
     {
@@ -299,6 +350,14 @@ int main(int argc, char** argv)
     double mean = 0.0;
     for (size_t i = 0; i < n * 3; i++)
         mean += device_framebuffer[i];
+#ifdef B2_BOUNDARY_GPUKERNEL
+    if (megakernel->compute_execution_time() <= 0.0f)
+    {
+        std::fprintf(stderr, "GPUKernel::compute_execution_time reports no time for a kernel that ran\n");
+        return 1;
+    }
+    std::printf("{\"through_gpukernel_class\": true, \"megakernel_last_ms\": %.4f}\n", megakernel->get_last_execution_time());
+#endif
     std::printf("{\"boundary_check\": true, \"render_data_bytes\": %zu, \"width\": %d, \"height\": %d, \"spp\": %d, \"pixels\": %zu, \"pixels_not_bit_identical\": %zu, "
                 "\"mean\": %.6g, \"direct_light_strategy\": %d}\n",
                 sizeof(HIPRTRenderData), args.width, args.height, args.spp, n, differing, mean / (n * 3), (int)DirectLightSamplingStrategy);
