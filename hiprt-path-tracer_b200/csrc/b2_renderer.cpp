@@ -178,6 +178,9 @@ const VariantKey kVariants[] = {
     { "c4l0", 0, 5, 1, 0, true, false, 4 },
     { "c4l1", 0, 5, 1, 1, true, false, 4 },
     { "c4l2", 0, 5, 1, 2, true, false, 4 },
+    /* several at once: balance heuristic + no bias-correction visibility + spatial visibility + MIS later; symmetric ratio + no visibility reuse + initial visibility + BSDF later */
+    { "c4x1", 0, 5, 1, 2, true, false, 3, 2 | 4 },
+    { "c4x2", 0, 5, 1, 1, true, false, 6, 1 | 8 },
     { "c4v1", 0, 5, 1, 3, true, false, 4, 1 | 4 | 8 }, /* InitialTargetFunctionVisibility on */
     { "c4v2", 0, 5, 1, 3, true, false, 4, 2 | 4 | 8 }, /* SpatialTargetFunctionVisibility on */
     { "c4v3", 0, 5, 1, 3, true, false, 4, 8 },         /* DoVisibilityReuse off */

@@ -255,7 +255,7 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
  * ReSTIR_DI_BiasCorrectionWeights 1 / 2 / 3 / 5 / 6 / 7) | "c4v1" .. "c4v5" (= c4 with the ReSTIR DI visibility macros away from their
  * defaults: InitialTargetFunctionVisibility on / SpatialTargetFunctionVisibility on / DoVisibilityReuse off / BiasCorrectionUseVisibility
  * off / the first three together) | "c4l0" "c4l1" "c4l2" (= c4 with ReSTIR_DI_LaterBouncesSamplingStrategy 0 / 1 / 2: uniform one light /
- * BSDF only / light + BSDF MIS at the bounces after the first)
+ * BSDF only / light + BSDF MIS at the bounces after the first) | "c4x1" "c4x2" (= two combinations of the above, see b2_renderer.cpp)
  * (see b2_kernels_body.h); precise: 1 = parity flavour, 0 = fast flavour */
 int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* variant, int precise, b2pt_renderer** out_renderer);
 int b2pt_renderer_destroy(b2pt_renderer* renderer);

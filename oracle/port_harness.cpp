@@ -113,7 +113,13 @@ static unsigned int g_port_faults[B2_FAULT_COUNT] = { 0, 0, 0 };
 static unsigned long long g_port_counters[3] = { 0, 0, 0 }; /* rays, nodes, triangles: traversal steps per ray of the CW8 BVH */
 
 /* "c4b<N>" = c4 with ReSTIR_DI_BiasCorrectionWeights = N (the renderer's variant table, csrc/b2_renderer.cpp) */
-static int bias_correction_of(const std::string& variant) { return variant.rfind("c4b", 0) == 0 ? std::atoi(variant.c_str() + 3) : 4; }
+/* c4x<N>: combinations (the table of b2_renderer.cpp / oracle/Makefile): c4x1 = weights 3, options 2 | 4, later MIS; c4x2 = weights 6, options 1 | 8, later BSDF */
+static int bias_correction_of(const std::string& variant)
+{
+    if (variant == "c4x1") return 3;
+    if (variant == "c4x2") return 6;
+    return variant.rfind("c4b", 0) == 0 ? std::atoi(variant.c_str() + 3) : 4;
+}
 /* c4v<N>: one of the four ReSTIR DI visibility macros away from its default (bits B2_DI_OPT_*, the table of b2_renderer.cpp) */
 static int restir_options_of(const std::string& variant)
 {
@@ -122,9 +128,11 @@ static int restir_options_of(const std::string& variant)
     if (variant == "c4v3") return 8;
     if (variant == "c4v4") return 4;
     if (variant == "c4v5") return 1 | 2 | 8;
+    if (variant == "c4x1") return 2 | 4;
+    if (variant == "c4x2") return 1 | 8;
     return 4 | 8;
 }
-static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant == "c4pu" || variant.rfind("c4b", 0) == 0 || variant.rfind("c4v", 0) == 0 || variant.rfind("c4l", 0) == 0; }
+static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant == "c4pu" || variant.rfind("c4b", 0) == 0 || variant.rfind("c4v", 0) == 0 || variant.rfind("c4l", 0) == 0 || variant.rfind("c4x", 0) == 0; }
 static bool g_scene_has_alpha_tested_materials = false; /* = what the renderer passes as B2PT_ALPHA_TEST */
 
 /* The MegaKernel the way the phased and wavefront GPU kernels run it (b2_kernels.cu: megakernel_phased, b2_wavefront.h): one path
@@ -578,8 +586,8 @@ int main(int argc, char** argv)
         }
         /* c4l<N>: ReSTIR_DI_LaterBouncesSamplingStrategy = N (ReSTIRDIOptions.h:18-21,140): only the MegaKernel differs */
         else if (a.variant == "c4l0" && pass == B2_PASS_MEGAKERNEL) run_pass<B2Variant<B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_LATER_ONE_LIGHT>>(pass, rd, bvh, a);
-        else if (a.variant == "c4l1" && pass == B2_PASS_MEGAKERNEL) run_pass<B2Variant<B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_LATER_BSDF>>(pass, rd, bvh, a);
-        else if (a.variant == "c4l2" && pass == B2_PASS_MEGAKERNEL) run_pass<B2Variant<B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_LATER_MIS>>(pass, rd, bvh, a);
+        else if ((a.variant == "c4l1" || a.variant == "c4x2") && pass == B2_PASS_MEGAKERNEL) run_pass<B2Variant<B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_LATER_BSDF>>(pass, rd, bvh, a);
+        else if ((a.variant == "c4l2" || a.variant == "c4x1") && pass == B2_PASS_MEGAKERNEL) run_pass<B2Variant<B2_BSDF_NONE, B2_LSS_RESTIR_DI, B2_BASE_POWER, B2_LATER_MIS>>(pass, rd, bvh, a);
         else if (is_c4(a.variant)) run_pass<B2VariantC4>(pass, rd, bvh, a);
 #endif
         else { std::fprintf(stderr, "unknown variant %s\n", a.variant.c_str()); std::exit(2); }

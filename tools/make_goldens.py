@@ -94,11 +94,18 @@ CASES = [
     # ReSTIR_DI_LightPresamplingStrategy = LSS_BASE_UNIFORM (variant "c4pu" = c4p with uniform presampling)
     ("c4pu_synenv_96x54_fused", "c4pu", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env"]),
     ("c4pu_96x54_split", "c4pu", "cornell_pbr_16x9", 96, 54, 2, 4, ["--no-fused"]),
+    # several options at once (they interact: which passes end with visibility reuse, which flags a sample keeps): "c4x1" = balance
+    # heuristic + no bias-correction visibility + spatial target-function visibility + MIS at later bounces; "c4x2" = symmetric ratio +
+    # no visibility reuse + initial target-function visibility + BSDF sampling at later bounces
+    ("c4x1_96x54_fused", "c4x1", "cornell_pbr_16x9", 96, 54, 3, 4, []),
+    ("c4x1_syn_96x54_split_directional", "c4x1", "synthetic_20k", 96, 54, 2, 4, ["--no-fused", "--no-confidence-weights", "--directional-reuse"]),
+    ("c4x2_synenv_96x54_fused_8neighbors", "c4x2", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env", "--neighbors", "8"]),
+    ("c4x2_syn_96x54_split2", "c4x2", "synthetic_20k", 96, 54, 2, 4, ["--no-fused", "--spatial-passes", "2"]),
 ]
 EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
 # fixtures of kernel options added after the round's GPU budget was spent live in tests/golden/options/ and are tested by
 # tests/test_restir_di_options.py, which runs after the suites whose CUDA side has been seen green on a B200
-OPTIONS_PREFIXES = ("c4v", "c4l", "c4pu")
+OPTIONS_PREFIXES = ("c4v", "c4l", "c4pu", "c4x")
 
 
 def run_case(name, variant, scene, w, h, spp, bounces, extra):
