@@ -296,6 +296,10 @@ class Renderer:
     def set_counters(self, enabled):
         check(lib().b2pt_renderer_set_counters(self.handle, int(enabled)))
 
+    def set_macro(self, name, value):
+        """GPUKernelCompilerOptions::set_macro_value + recompile: a kernel option on top of the variant's (b2pt_renderer_set_macro)."""
+        check(lib().b2pt_renderer_set_macro(self.handle, name.encode(), int(value)))
+
     def set_profile_passes(self, enabled):
         check(lib().b2pt_renderer_set_profile_passes(self.handle, int(enabled)))
 

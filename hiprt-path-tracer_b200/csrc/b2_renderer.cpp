@@ -68,6 +68,7 @@ struct b2pt_renderer
     int precise = 1;
     int counters = 0;
     bool kernels_stale = true;
+    std::vector<std::pair<std::string, int>> macros; /* b2pt_renderer_set_macro: kernel options on top of the variant's, in the order they were set */
     bool alpha_test = false; /* the current scene has materials that are not fully opaque: kernels are asked for B2PT_ALPHA_TEST */
     bool profile_passes = false;
 
@@ -240,7 +241,11 @@ int resolve_kernels(b2pt_renderer* r)
             { "ReSTIR_DI_InitialTargetFunctionVisibility", (v->restir_options & 1) ? 1 : 0 }, { "ReSTIR_DI_SpatialTargetFunctionVisibility", (v->restir_options & 2) ? 1 : 0 },
             { "ReSTIR_DI_DoVisibilityReuse", (v->restir_options & 4) ? 1 : 0 }, { "ReSTIR_DI_BiasCorrectionUseVisibility", (v->restir_options & 8) ? 1 : 0 },
         };
-        B2_TRY(b2pt_kernel_get(r->ctx, entry, opts, (int)(sizeof(opts) / sizeof(opts[0])), &r->kernels[pass]));
+        /* the variant's options first, then the ones set one by one (GPUKernelCompilerOptions::set_macro_value): a later entry wins */
+        std::vector<b2pt_option> all(opts, opts + sizeof(opts) / sizeof(opts[0]));
+        for (const auto& macro : r->macros)
+            all.push_back(b2pt_option{ macro.first.c_str(), macro.second });
+        B2_TRY(b2pt_kernel_get(r->ctx, entry, all.data(), (int)all.size(), &r->kernels[pass]));
     }
     r->kernels_stale = false;
     return B2PT_OK;
@@ -787,6 +792,46 @@ int b2pt_renderer_set_counters(b2pt_renderer* r, int enabled)
 {
     if (!r) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
     r->counters = enabled ? 1 : 0;
+    r->kernels_stale = true;
+    return B2PT_OK;
+}
+
+/* GPURenderer::get_global_compiler_options()->set_macro_value(name, value) + recompile_kernels() (GPURenderer.cpp:482-501): the kernels
+ * are looked up again before the next render. The macros that decide which passes and buffers a renderer has are its variant's and are
+ * refused here; whether the value is served is answered at once (b2pt_kernel_query on the MegaKernel and, for ReSTIR DI, its passes). */
+int b2pt_renderer_set_macro(b2pt_renderer* r, const char* name, int value)
+{
+    if (!r || !name) { b2_set_error("null argument"); return B2PT_ERR_INVALID_ARGUMENT; }
+    for (const char* fixed : { "BSDFOverride", "DirectLightSamplingStrategy", "DirectLightSamplingBaseStrategy", "ReSTIR_DI_DoLightPresampling", "B2PT_PRECISE", "B2PT_COUNTERS", "B2PT_ALPHA_TEST" })
+        if (!std::strcmp(name, fixed))
+        {
+            b2_set_error("b2pt_renderer_set_macro: %s belongs to the renderer's variant / flavour (b2pt_renderer_create, b2pt_renderer_set_counters)", name);
+            return B2PT_ERR_INVALID_ARGUMENT;
+        }
+    const VariantKey* v = find_variant(r->variant);
+    std::vector<std::pair<std::string, int>> macros = r->macros;
+    bool replaced = false;
+    for (auto& macro : macros)
+        if (macro.first == name)
+        {
+            macro.second = value;
+            replaced = true;
+        }
+    if (!replaced)
+        macros.emplace_back(name, value);
+    std::vector<b2pt_option> opts = { { "BSDFOverride", v->bsdf }, { "DirectLightSamplingStrategy", v->direct }, { "DirectLightSamplingBaseStrategy", v->base },
+                                      { "ReSTIR_DI_LaterBouncesSamplingStrategy", v->later } };
+    for (const auto& macro : macros)
+        opts.push_back(b2pt_option{ macro.first.c_str(), macro.second });
+    for (int pass = 0; pass < B2_PASS_COUNT; pass++)
+    {
+        const char* entry = entry_name_of_pass(pass);
+        bool restir_pass = pass != B2_PASS_CAMERA_RAYS && pass != B2_PASS_MEGAKERNEL;
+        if (!entry || (restir_pass && !v->restir) || (pass == B2_PASS_RESTIR_DI_PRESAMPLING && !v->presampling))
+            continue;
+        B2_TRY(b2pt_kernel_query(entry, opts.data(), (int)opts.size()));
+    }
+    r->macros = macros;
     r->kernels_stale = true;
     return B2PT_OK;
 }

@@ -287,6 +287,11 @@ int b2pt_renderer_set_envmap_file(b2pt_renderer* renderer, const char* envmap_bl
 b2pt_render_data* b2pt_renderer_render_data(b2pt_renderer* renderer);
 int b2pt_renderer_set_host_seed(b2pt_renderer* renderer, unsigned int seed);
 int b2pt_renderer_set_counters(b2pt_renderer* renderer, int enabled);
+/* GPURenderer::get_global_compiler_options()->set_macro_value(name, value) followed by recompile_kernels() (GPURenderer.cpp:482-501): a kernel
+ * option on top of the variant's -- any name of b2pt_kernel_option_names except the ones that define the variant (BSDFOverride,
+ * DirectLightSamplingStrategy, DirectLightSamplingBaseStrategy, ReSTIR_DI_DoLightPresampling). B2PT_ERR_NO_VARIANT, at once, for a value that
+ * is not served; the kernels are looked up again before the next render. */
+int b2pt_renderer_set_macro(b2pt_renderer* renderer, const char* name, int value);
 /* When enabled, every pass launch is followed by an event wait and its time is added to b2pt_renderer_pass_ms
  * (serialises host and device: for profiling runs only, never for the timed bench region). */
 int b2pt_renderer_set_profile_passes(b2pt_renderer* renderer, int enabled);

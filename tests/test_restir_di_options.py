@@ -104,3 +104,28 @@ def test_cuda_fast_flavour_agrees_statistically(b2pt, gpu_ctx, name):
     # clipped at 256 (above every direct view of an emitter in these scenes) so that no single path decides a statistical comparison
     a, b = np.minimum(fb[~marked], 256.0), np.minimum(ref[~marked], 256.0)
     assert abs(a.mean() - b.mean()) <= 0.01 * abs(b.mean()) + 1e-6
+
+
+@pytest.mark.gpu
+def test_macros_set_one_by_one_on_a_plain_c4_renderer(b2pt, gpu_ctx):
+    """b2pt_renderer_set_macro (= GPUKernelCompilerOptions::set_macro_value + recompile_kernels): a "c4" renderer taken to the options of the
+    c4x1 fixture one macro at a time renders that fixture; values that are not served are refused at once and change nothing."""
+    g, meta = load_golden("options/c4x1_96x54_fused")
+    r = b2pt.Renderer(gpu_ctx, meta["width"], meta["height"], "c4", precise=True)
+    from conftest import DATA
+
+    r.set_scene_file(DATA / f"{meta['scene']}.b2scene")
+    r.set_luts_file(DATA / "brdf_luts.b2luts")
+    r.set(nb_bounces=meta["bounces"], restir_di_do_fused_spatiotemporal=1)
+    r.set_macro("ReSTIR_DI_BiasCorrectionWeights", 3)
+    r.set_macro("ReSTIR_DI_BiasCorrectionUseVisibility", 0)
+    r.set_macro("ReSTIR_DI_SpatialTargetFunctionVisibility", 1)
+    r.set_macro("ReSTIR_DI_LaterBouncesSamplingStrategy", 2)
+    with pytest.raises(b2pt.B2ptError):
+        r.set_macro("ReSTIR_DI_BiasCorrectionWeights", 0)  # 1/M: not built (does not compile in the reference)
+    with pytest.raises(b2pt.B2ptError):
+        r.set_macro("DirectLightSamplingStrategy", 3)  # belongs to the variant
+    r.render(meta["spp"])
+    fb = r.framebuffer()
+    r.close()
+    assert pixels_not_bit_identical(fb, g["framebuffer"]) <= 2
