@@ -213,6 +213,29 @@ const char* entry_name_of_pass(int pass)
     }
 }
 
+/* the kernel options a variant stands for (what resolve_kernels passes, before the macros set one by one) */
+std::vector<b2pt_option> variant_options(const VariantKey* v, int precise, int counters, int alpha_test)
+{
+    return {
+        { "BSDFOverride", v->bsdf }, { "DirectLightSamplingStrategy", v->direct }, { "DirectLightSamplingBaseStrategy", v->base },
+        { "ReSTIR_DI_LaterBouncesSamplingStrategy", v->later }, { "ReSTIR_DI_DoLightPresampling", v->presampling ? 1 : 0 },
+        { "B2PT_PRECISE", precise }, { "B2PT_COUNTERS", counters }, { "B2PT_ALPHA_TEST", alpha_test },
+        { "ReSTIR_DI_BiasCorrectionWeights", v->bias_correction }, { "ReSTIR_DI_LightPresamplingStrategy", v->presampling_strategy },
+        { "ReSTIR_DI_InitialTargetFunctionVisibility", (v->restir_options & 1) ? 1 : 0 }, { "ReSTIR_DI_SpatialTargetFunctionVisibility", (v->restir_options & 2) ? 1 : 0 },
+        { "ReSTIR_DI_DoVisibilityReuse", (v->restir_options & 4) ? 1 : 0 }, { "ReSTIR_DI_BiasCorrectionUseVisibility", (v->restir_options & 8) ? 1 : 0 },
+    };
+}
+
+bool variant_has_pass(const VariantKey* v, int pass)
+{
+    if (!entry_name_of_pass(pass))
+        return false;
+    bool restir_pass = pass != B2_PASS_CAMERA_RAYS && pass != B2_PASS_MEGAKERNEL;
+    if (restir_pass && !v->restir)
+        return false;
+    return pass != B2_PASS_RESTIR_DI_PRESAMPLING || v->presampling;
+}
+
 int resolve_kernels(b2pt_renderer* r)
 {
     if (!r->kernels_stale)
@@ -225,24 +248,11 @@ int resolve_kernels(b2pt_renderer* r)
             b2pt_kernel_destroy(r->kernels[pass]);
             r->kernels[pass] = nullptr;
         }
+        if (!variant_has_pass(v, pass))
+            continue;
         const char* entry = entry_name_of_pass(pass);
-        if (!entry)
-            continue;
-        bool restir_pass = pass != B2_PASS_CAMERA_RAYS && pass != B2_PASS_MEGAKERNEL;
-        if (restir_pass && !v->restir)
-            continue;
-        if (pass == B2_PASS_RESTIR_DI_PRESAMPLING && !v->presampling)
-            continue;
-        b2pt_option opts[] = {
-            { "BSDFOverride", v->bsdf }, { "DirectLightSamplingStrategy", v->direct }, { "DirectLightSamplingBaseStrategy", v->base },
-            { "ReSTIR_DI_LaterBouncesSamplingStrategy", v->later }, { "ReSTIR_DI_DoLightPresampling", v->presampling ? 1 : 0 },
-            { "B2PT_PRECISE", r->precise }, { "B2PT_COUNTERS", r->counters }, { "B2PT_ALPHA_TEST", r->alpha_test ? 1 : 0 },
-            { "ReSTIR_DI_BiasCorrectionWeights", v->bias_correction }, { "ReSTIR_DI_LightPresamplingStrategy", v->presampling_strategy },
-            { "ReSTIR_DI_InitialTargetFunctionVisibility", (v->restir_options & 1) ? 1 : 0 }, { "ReSTIR_DI_SpatialTargetFunctionVisibility", (v->restir_options & 2) ? 1 : 0 },
-            { "ReSTIR_DI_DoVisibilityReuse", (v->restir_options & 4) ? 1 : 0 }, { "ReSTIR_DI_BiasCorrectionUseVisibility", (v->restir_options & 8) ? 1 : 0 },
-        };
         /* the variant's options first, then the ones set one by one (GPUKernelCompilerOptions::set_macro_value): a later entry wins */
-        std::vector<b2pt_option> all(opts, opts + sizeof(opts) / sizeof(opts[0]));
+        std::vector<b2pt_option> all = variant_options(v, r->precise, r->counters, r->alpha_test ? 1 : 0);
         for (const auto& macro : r->macros)
             all.push_back(b2pt_option{ macro.first.c_str(), macro.second });
         B2_TRY(b2pt_kernel_get(r->ctx, entry, all.data(), (int)all.size(), &r->kernels[pass]));
@@ -833,6 +843,29 @@ int b2pt_renderer_set_macro(b2pt_renderer* r, const char* name, int value)
     }
     r->macros = macros;
     r->kernels_stale = true;
+    return B2PT_OK;
+}
+
+/* Host-only views of the variant table: tests walk it without a device (every pass of every named variant must resolve in both flavours) */
+int b2pt_renderer_variant_count(void) { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
+
+const char* b2pt_renderer_variant_name(int index)
+{
+    return index >= 0 && index < b2pt_renderer_variant_count() ? kVariants[index].name : nullptr;
+}
+
+int b2pt_renderer_variant_query(const char* variant, int precise)
+{
+    const VariantKey* v = variant ? find_variant(variant) : nullptr;
+    if (!v) { b2_set_error("unknown variant '%s'", variant ? variant : "(null)"); return B2PT_ERR_NO_VARIANT; }
+    for (int counters = 0; counters < 2; counters++)
+        for (int pass = 0; pass < B2_PASS_COUNT; pass++)
+        {
+            if (!variant_has_pass(v, pass))
+                continue;
+            std::vector<b2pt_option> opts = variant_options(v, precise, counters, 0);
+            B2_TRY(b2pt_kernel_query(entry_name_of_pass(pass), opts.data(), (int)opts.size()));
+        }
     return B2PT_OK;
 }
 

@@ -292,6 +292,11 @@ int b2pt_renderer_set_counters(b2pt_renderer* renderer, int enabled);
  * DirectLightSamplingStrategy, DirectLightSamplingBaseStrategy, ReSTIR_DI_DoLightPresampling). B2PT_ERR_NO_VARIANT, at once, for a value that
  * is not served; the kernels are looked up again before the next render. */
 int b2pt_renderer_set_macro(b2pt_renderer* renderer, const char* name, int value);
+/* The variant names b2pt_renderer_create takes, and whether every kernel of one resolves (b2pt_kernel_query over its passes, with and
+ * without traversal counters) in a flavour. No device needed. */
+int b2pt_renderer_variant_count(void);
+const char* b2pt_renderer_variant_name(int index);
+int b2pt_renderer_variant_query(const char* variant, int precise);
 /* When enabled, every pass launch is followed by an event wait and its time is added to b2pt_renderer_pass_ms
  * (serialises host and device: for profiling runs only, never for the timed bench region). */
 int b2pt_renderer_set_profile_passes(b2pt_renderer* renderer, int enabled);

@@ -55,6 +55,19 @@ def test_kernel_query_needs_no_device(b2pt):
     assert lib.b2pt_kernel_option_fixed_value(b"DirectLightSamplingStrategy", C.byref(value)) != 0
 
 
+def test_every_named_variant_resolves_without_a_device(b2pt):
+    """The renderer's variant table (c1 ... c4x2): every pass of every variant must name a precompiled kernel, in both flavours, with and
+    without traversal counters -- walked on the host (b2pt_renderer_variant_query), so a slip in the table shows here and not on a GPU."""
+    lib = b2pt.load_library()
+    lib.b2pt_renderer_variant_name.restype = C.c_char_p
+    names = [lib.b2pt_renderer_variant_name(i).decode() for i in range(lib.b2pt_renderer_variant_count())]
+    assert {"c1", "c2", "c3", "c4", "c4p", "c4pu", "c4b1", "c4b7", "c4v5", "c4l0", "c4x2"} <= set(names)
+    for name in names:
+        for precise in (1, 0):
+            assert lib.b2pt_renderer_variant_query(name.encode(), precise) == 0, (name, precise, lib.b2pt_last_error_string())
+    assert lib.b2pt_renderer_variant_query(b"c9", 1) != 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant,scene,extra", [("c1", "cornell_pbr_16x9", []), ("c2", "cornell_pbr_16x9", []), ("c3", "synthetic_20k", []),
                                                   ("c4", "cornell_pbr_16x9", []), ("c4", "cornell_pbr_16x9", ["--no-fused"])])
