@@ -26,6 +26,10 @@
 struct Args
 {
     std::string scene, luts, envmap, dump, variant = "c1", cameras;
+    int debug_x = -1, debug_y = -1, debug_frame = -1; /* --debug-visibility X Y FRAME */
+    bool trace_ray = false;                           /* --trace-ray ox oy oz dx dy dz t_max skip_prim: one ray through the product's traversal */
+    float ray[7] = { 0, 0, 0, 0, 0, 1, 3.0e38f };
+    int ray_skip_prim = -1;
     int width = 512, height = 512, spp = 1, bounces = 3;
     int win_x0 = 0, win_y0 = 0, win_x1 = -1, win_y1 = -1;
     int threads = 0;
@@ -59,6 +63,8 @@ static Args parse_args(int argc, char** argv)
         else if (k == "--no-jitter") a.no_jitter = true;
         else if (k == "--kat") a.kat = true; /* function-level known-answer dump instead of a render (see run_bsdf_kat) */
         else if (k == "--neighbors") a.neighbors = std::atoi(next());
+        else if (k == "--trace-ray") { a.trace_ray = true; for (int j = 0; j < 7; j++) a.ray[j] = std::strtof(next(), nullptr); a.ray_skip_prim = std::atoi(next()); }
+        else if (k == "--debug-visibility") { a.debug_x = std::atoi(next()); a.debug_y = std::atoi(next()); a.debug_frame = std::atoi(next()); }
         else if (k == "--cameras") a.cameras = next(); /* a moving camera: one B2SceneCamera (52 floats) per frame, as ref_extras_* takes it */
         else if (k == "--staged") a.staged = true; /* the MegaKernel through megakernel_stage1 / stage2, the way the GPU kernels run it */
         else if (k == "--no-confidence-weights") a.confidence_weights = false;
@@ -525,6 +531,28 @@ int main(int argc, char** argv)
     bvh.tri_count = (uint32_t)scene.bvh.tris.size();
     rd.GPU_BVH = &bvh;
 
+    if (a.trace_ray)
+    {
+        /* the counterpart of oracle/ray_check.cpp: the product's closest-hit and any-hit traversals on one ray */
+        uint64_t stack[B2_STACK_ENTRIES];
+        Ctx ctx;
+        ctx.rd = &rd;
+        ctx.bvh = bvh;
+        ctx.stack = stack;
+        ctx.stack_stride = 1;
+        ctx.counters = nullptr;
+        ctx.faults = g_port_faults;
+        ctx.light_presampling = 0;
+        ctx.bias_correction = 4;
+        ctx.restir_options = 4 | 8;
+        ctx.alpha_test = false;
+        B2_SET_RAY_BOUNCE(ctx, 0);
+        V3 origin = v3(a.ray[0], a.ray[1], a.ray[2]), direction = v3(a.ray[3], a.ray[4], a.ray[5]);
+        B2Hit closest = b2_trace(ctx, false, origin, direction, 3.0e38f, a.ray_skip_prim);
+        B2Hit any = b2_trace(ctx, true, origin, direction, a.ray[6], a.ray_skip_prim);
+        std::printf("{\"trace_ray\": true, \"closest_prim\": %d, \"closest_t\": %.9g, \"occluded\": %s}\n", closest.prim, closest.t, any.prim >= 0 ? "true" : "false");
+        return 0;
+    }
 #ifdef B2_PORT_HAVE_C2
     if (a.kat)
     {
@@ -591,6 +619,30 @@ int main(int argc, char** argv)
         else if (is_c4(a.variant)) run_pass<B2VariantC4>(pass, rd, bvh, a);
 #endif
         else { std::fprintf(stderr, "unknown variant %s\n", a.variant.c_str()); std::exit(2); }
+        if (pass == B2_PASS_RESTIR_DI_INITIAL_CANDIDATES && frame == a.debug_frame && a.debug_x >= 0)
+        {
+            /* debugging aid: the visibility ray of one pixel's initial reservoir, traced through the BVH and by brute force over every triangle */
+            const size_t pixel = (size_t)a.debug_x + (size_t)a.debug_y * a.width;
+            const uint32_t* soa = reinterpret_cast<const uint32_t*>(rd.render_settings.restir_di_settings.initial_candidates.output_reservoirs);
+            auto word = [&](int plane) { return soa[(size_t)plane * n + pixel]; };
+            auto as_float = [](uint32_t w) { float f; std::memcpy(&f, &w, 4); return f; };
+            V3 point = v3(as_float(word(3)), as_float(word(4)), as_float(word(5)));
+            V3 origin = load_v3(rd.g_buffer.primary_hit_position, (uint32_t)pixel);
+            int skip = rd.g_buffer.first_hit_prim_index[pixel];
+            V3 d = point - origin;
+            float distance = length(d);
+            d = d / distance;
+            float t_max = distance - 1.0e-4f;
+            std::fprintf(stderr, "debug pixel (%d, %d) frame %d: M %u UCW %g triangle %d flags %u origin (%.9g %.9g %.9g) dir (%.9g %.9g %.9g) distance %.9g skip %d\n", a.debug_x, a.debug_y,
+                         frame, word(0), as_float(word(2)), (int)word(6), word(8) & 0xFF, origin.x, origin.y, origin.z, d.x, d.y, d.z, distance, skip);
+            for (uint32_t i = 0; i < bvh.tri_count; i++)
+            {
+                const B2Tri& tri = bvh.tris[i];
+                float t, u, v;
+                if (tri.prim != skip && b2_intersect_triangle(origin, d, v3(tri.ax, tri.ay, tri.az), v3(tri.e1x, tri.e1y, tri.e1z), v3(tri.e2x, tri.e2y, tri.e2z), t, u, v) && t < t_max + 1.0e-3f)
+                    std::fprintf(stderr, "  brute force: prim %d t %.9g (t_max %.9g) u %.9g v %.9g\n", tri.prim, t, t_max, u, v);
+            }
+        }
         if (a.dump_per_sample && !a.dump.empty() &&
             (pass == B2_PASS_RESTIR_DI_INITIAL_CANDIDATES || pass == B2_PASS_RESTIR_DI_TEMPORAL || pass == B2_PASS_RESTIR_DI_SPATIAL || pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL))
         {
