@@ -903,6 +903,14 @@ int b2pt_renderer_render(b2pt_renderer* r, int samples)
     if (!r->has_scene) { b2_set_error("b2pt_renderer_render: no scene set"); return B2PT_ERR_INVALID_ARGUMENT; }
     B2_TRY(b2pt_ctx_make_current(r->ctx));
     B2_TRY(resolve_kernels(r));
+    if (r->world > 1 && r->loop.restir_di && r->loop.rd.render_settings.enable_adaptive_sampling)
+    {
+        /* CameraRays renders the halo rows around a rank's bands too, and with adaptive sampling it reads the sample counts and the
+         * accumulated colours of those pixels (AdaptiveSampling.h:30-102), which only their owner keeps up to date: the G-buffers of
+         * the ranks would drift apart. Refused rather than rendered differently from one GPU. */
+        b2_set_error("b2pt_renderer_render: adaptive sampling is not served for ReSTIR DI on a partitioned frame");
+        return B2PT_ERR_UNSUPPORTED_SCENE;
+    }
     r->loop.camera.sensor_width = r->width;
     r->loop.camera.sensor_height = r->height;
 
