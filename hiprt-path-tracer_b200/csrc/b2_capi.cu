@@ -579,7 +579,7 @@ static const MacroDefault kFixedMacros[] = {
     { "PrincipledBSDFDoSpecularEnergyCompensation", 1 }, { "PrincipledBSDFDeltaDistributionEvaluationOptimization", 1 },
     { "PrincipledBSDFSampleGlossyBasedOnFresnel", 0 }, { "PrincipledBSDFSampleCoatBasedOnFresnel", 0 },
     { "PrincipledBSDFDoMicrofacetRegularization", 1 }, { "PrincipledBSDFDoMicrofacetRegularizationConsistentParameterization", 1 },
-    { "PrincipledBSDFMicrofacetRegularizationDiffusionHeuristic", 1 }, { "ReSTIR_DI_DoOptimalVisibilitySampling", 0 },
+    { "PrincipledBSDFMicrofacetRegularizationDiffusionHeuristic", 1 }, 
     { "DirectLightUseNEEPlusPlus", 0 }, { "SharedStackBVHTraversalSize", 16 },
 };
 
@@ -602,7 +602,7 @@ static int pass_of_entry_name(const char* name)
 static const char* const kSwitchedMacros[] = {
     "BSDFOverride", "DirectLightSamplingStrategy", "DirectLightSamplingBaseStrategy", "ReSTIR_DI_LaterBouncesSamplingStrategy", "EnvmapSamplingStrategy",
     "ReSTIR_DI_DoLightPresampling", "ReSTIR_DI_LightPresamplingStrategy", "ReSTIR_DI_BiasCorrectionWeights", "ReSTIR_DI_InitialTargetFunctionVisibility",
-    "ReSTIR_DI_SpatialTargetFunctionVisibility", "ReSTIR_DI_DoVisibilityReuse", "ReSTIR_DI_BiasCorrectionUseVisibility",
+    "ReSTIR_DI_SpatialTargetFunctionVisibility", "ReSTIR_DI_DoVisibilityReuse", "ReSTIR_DI_BiasCorrectionUseVisibility", "ReSTIR_DI_DoOptimalVisibilitySampling",
 };
 
 int b2pt_kernel_option_names(const char* const** out_names, int* out_count)
@@ -678,6 +678,7 @@ static int resolve_kernel(const char* entry_name, const b2pt_option* options, in
         else if (!std::strcmp(n, "ReSTIR_DI_SpatialTargetFunctionVisibility")) restir_options = v ? (restir_options | 2) : (restir_options & ~2);
         else if (!std::strcmp(n, "ReSTIR_DI_DoVisibilityReuse")) restir_options = v ? (restir_options | 4) : (restir_options & ~4);
         else if (!std::strcmp(n, "ReSTIR_DI_BiasCorrectionUseVisibility")) restir_options = v ? (restir_options | 8) : (restir_options & ~8);
+        else if (!std::strcmp(n, "ReSTIR_DI_DoOptimalVisibilitySampling")) restir_options = v ? (restir_options | 16) : (restir_options & ~16); /* spatial pass only */
         else if (!std::strcmp(n, "B2PT_COUNTERS")) counters = v;
         else
         {

@@ -665,7 +665,7 @@ cudaError_t launch_pass(const b2pt_render_data* rd, const B2LaunchGeom* geom, cu
     if constexpr (V::DIRECT == B2_LSS_RESTIR_DI)
     {
         /* the ray-delimited ReSTIR DI passes follow the MegaKernel's form: frame-wide phases + the global ray queue on big scenes */
-        const bool default_options = g.restir_options == B2_DI_OPT_DEFAULTS;
+        const bool default_options = (g.restir_options & B2_DI_OPT_PHASE_CUT_MASK) == B2_DI_OPT_DEFAULTS;
         if (PASS == B2_PASS_RESTIR_DI_INITIAL_CANDIDATES && g.persistent == 3 && default_options)
             return launch_wavefront_pass<WfInitialCandidates<V>, V>(rd, g, rows, stream);
         /* (pairwise MIS with at most 6 neighbours; anything else runs the pass in one piece, restir_di_spatiotemporal_inplace_pixel) */

@@ -182,6 +182,7 @@ const VariantKey kVariants[] = {
     /* several at once: balance heuristic + no bias-correction visibility + spatial visibility + MIS later; symmetric ratio + no visibility reuse + initial visibility + BSDF later */
     { "c4x1", 0, 5, 1, 2, true, false, 3, 2 | 4 },
     { "c4x2", 0, 5, 1, 1, true, false, 6, 1 | 8 },
+    { "c4o", 0, 5, 1, 3, true, false, 4, 4 | 8 | 16 }, /* ReSTIR_DI_DoOptimalVisibilitySampling (bit 16; read by the spatial pass: restir_di_do_fused_spatiotemporal = 0) */
     { "c4v1", 0, 5, 1, 3, true, false, 4, 1 | 4 | 8 }, /* InitialTargetFunctionVisibility on */
     { "c4v2", 0, 5, 1, 3, true, false, 4, 2 | 4 | 8 }, /* SpatialTargetFunctionVisibility on */
     { "c4v3", 0, 5, 1, 3, true, false, 4, 8 },         /* DoVisibilityReuse off */
@@ -223,6 +224,7 @@ std::vector<b2pt_option> variant_options(const VariantKey* v, int precise, int c
         { "ReSTIR_DI_BiasCorrectionWeights", v->bias_correction }, { "ReSTIR_DI_LightPresamplingStrategy", v->presampling_strategy },
         { "ReSTIR_DI_InitialTargetFunctionVisibility", (v->restir_options & 1) ? 1 : 0 }, { "ReSTIR_DI_SpatialTargetFunctionVisibility", (v->restir_options & 2) ? 1 : 0 },
         { "ReSTIR_DI_DoVisibilityReuse", (v->restir_options & 4) ? 1 : 0 }, { "ReSTIR_DI_BiasCorrectionUseVisibility", (v->restir_options & 8) ? 1 : 0 },
+        { "ReSTIR_DI_DoOptimalVisibilitySampling", (v->restir_options & 16) ? 1 : 0 },
     };
 }
 

@@ -44,7 +44,10 @@ enum { B2_BIAS_1_OVER_M = 0, B2_BIAS_1_OVER_Z = 1, B2_BIAS_MIS_LIKE = 2, B2_BIAS
  * visibility reuse and visibility in the bias-correction target functions on, the other two off. The phase-cut (wavefront) forms of
  * InitialCandidates and of the fused pass are built for the defaults; any other setting runs the passes in one piece. */
 enum { B2_DI_OPT_INITIAL_VISIBILITY = 1, B2_DI_OPT_SPATIAL_VISIBILITY = 2, B2_DI_OPT_VISIBILITY_REUSE = 4, B2_DI_OPT_BIAS_VISIBILITY = 8,
-       B2_DI_OPT_DEFAULTS = B2_DI_OPT_VISIBILITY_REUSE | B2_DI_OPT_BIAS_VISIBILITY };
+       B2_DI_OPT_DEFAULTS = B2_DI_OPT_VISIBILITY_REUSE | B2_DI_OPT_BIAS_VISIBILITY,
+       /* ReSTIR_DI_DoOptimalVisibilitySampling (ReSTIRDIOptions.h:176): read by the spatial pass only, so it does not take the other passes
+        * off their phase-cut forms (B2_DI_OPT_PHASE_CUT_MASK = the bits those forms depend on) */
+       B2_DI_OPT_OPTIMAL_VISIBILITY_SAMPLING = 16, B2_DI_OPT_PHASE_CUT_MASK = 15 };
 
 /* ReSTIR_DI_evaluate_target_function<ReSTIR_DI_BiasCorrectionUseVisibility> */
 template <class V>
@@ -1508,6 +1511,14 @@ B2_HD void restir_di_spatial_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
             else
                 out.sample.flags &= ~(uint32_t)B2_DI_FLAGS_UNOCCLUDED;
         }
+
+        /* ReSTIR_optimal_visibility_sampling (OptimalVisibilitySampling.h:17-46, called at SpatialReuse.h:225): once the last neighbour
+         * before the canonical sample has been resampled, what the neighbours produced is tested for visibility and thrown away if it is
+         * occluded, so that the canonical sample is not drowned by it. (The reference does not compile with the option on -- :34 names a
+         * member ReSTIRSurface does not have; the oracle builds it with -Dlast_hit_primitive_index=primitive_index, the member meant.) */
+        if ((ctx.restir_options & B2_DI_OPT_OPTIMAL_VISIBILITY_SAMPLING) && out.weight_sum > 0.0f && neighbor_index == reused_neighbors_count - 1)
+            if (di_visibility_test_kill_reservoir(ctx, out, center_pixel_surface.shading_point, center_pixel_surface.primitive_index))
+                out.weight_sum = 0.0f;
     }
 
     /* SpatialNormalizationWeight.h: 1/Z divides by the confidence of the neighbours that could have produced the chosen sample (:64-131),
@@ -2110,7 +2121,7 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
 template <class V>
 B2_HD void restir_di_spatiotemporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
 {
-    if (ctx.bias_correction != B2_BIAS_PAIRWISE_MIS || ctx.restir_options != B2_DI_OPT_DEFAULTS || !restir_di_spatiotemporal_supported<V>(*ctx.rd))
+    if (ctx.bias_correction != B2_BIAS_PAIRWISE_MIS || (ctx.restir_options & B2_DI_OPT_PHASE_CUT_MASK) != B2_DI_OPT_DEFAULTS || !restir_di_spatiotemporal_supported<V>(*ctx.rd))
     {
         restir_di_spatiotemporal_inplace_pixel<V>(ctx, x, y);
         return;

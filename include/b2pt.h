@@ -163,6 +163,7 @@ int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
  * {"ReSTIR_DI_InitialTargetFunctionVisibility", 0|1}, {"ReSTIR_DI_SpatialTargetFunctionVisibility", 0|1}, {"ReSTIR_DI_DoVisibilityReuse", 0|1},
  * {"ReSTIR_DI_BiasCorrectionUseVisibility", 0|1} (ReSTIRDIOptions.h:50-84; defaults 0, 0, 1, 1): launch-time switches of the ReSTIR DI
  * passes; give the same values to every ReSTIR DI kernel of a renderer, as the reference's global compiler options do.
+ * {"ReSTIR_DI_DoOptimalVisibilitySampling", 0|1} (:176): read by "ReSTIR_DI_SpatialReuse" (OptimalVisibilitySampling.h:17-46).
  * {"ReSTIR_DI_LightPresamplingStrategy", 0|1} (:162; LSS_BASE_UNIFORM / LSS_BASE_POWER, the default): how "ReSTIR_DI_LightsPresampling" picks
  * its emissive triangles, and the matching pdf in "ReSTIR_DI_InitialCandidates" -- launch-time as well. */
 typedef struct
@@ -255,7 +256,7 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
  * ReSTIR_DI_BiasCorrectionWeights 1 / 2 / 3 / 5 / 6 / 7) | "c4v1" .. "c4v5" (= c4 with the ReSTIR DI visibility macros away from their
  * defaults: InitialTargetFunctionVisibility on / SpatialTargetFunctionVisibility on / DoVisibilityReuse off / BiasCorrectionUseVisibility
  * off / the first three together) | "c4l0" "c4l1" "c4l2" (= c4 with ReSTIR_DI_LaterBouncesSamplingStrategy 0 / 1 / 2: uniform one light /
- * BSDF only / light + BSDF MIS at the bounces after the first) | "c4x1" "c4x2" (= two combinations of the above, see b2_renderer.cpp)
+ * BSDF only / light + BSDF MIS at the bounces after the first) | "c4o" (= c4 with ReSTIR_DI_DoOptimalVisibilitySampling) | "c4x1" "c4x2" (= two combinations of the above, see b2_renderer.cpp)
  * (see b2_kernels_body.h); precise: 1 = parity flavour, 0 = fast flavour */
 int b2pt_renderer_create(b2pt_ctx* ctx, int width, int height, const char* variant, int precise, b2pt_renderer** out_renderer);
 int b2pt_renderer_destroy(b2pt_renderer* renderer);

@@ -161,7 +161,7 @@ int main()
         {
             GPUKernelCompilerOptions o = c4.deep_copy();
             o.set_macro_value(GPUKernelCompilerOptions::RESTIR_DI_DO_OPTIMAL_VISIBILITY_SAMPLING, KERNEL_OPTION_TRUE);
-            expect(false, o, "ReSTIR_DI_SpatialReuse", "ReSTIR_DI_DoOptimalVisibilitySampling");
+            for (const char* e : restir_entries) expect(true, o, e, "ReSTIR_DI_DoOptimalVisibilitySampling");
             GPUKernelCompilerOptions regir;
             regir.set_macro_value(GPUKernelCompilerOptions::DIRECT_LIGHT_SAMPLING_BASE_STRATEGY, LSS_BASE_REGIR);
             expect(false, regir, "MegaKernel", "ReGIR base strategy");

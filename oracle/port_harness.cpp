@@ -134,11 +134,12 @@ static int restir_options_of(const std::string& variant)
     if (variant == "c4v3") return 8;
     if (variant == "c4v4") return 4;
     if (variant == "c4v5") return 1 | 2 | 8;
+    if (variant == "c4o") return 4 | 8 | 16; /* ReSTIR_DI_DoOptimalVisibilitySampling */
     if (variant == "c4x1") return 2 | 4;
     if (variant == "c4x2") return 1 | 8;
     return 4 | 8;
 }
-static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant == "c4pu" || variant.rfind("c4b", 0) == 0 || variant.rfind("c4v", 0) == 0 || variant.rfind("c4l", 0) == 0 || variant.rfind("c4x", 0) == 0; }
+static bool is_c4(const std::string& variant) { return variant == "c4" || variant == "c4p" || variant == "c4pu" || variant == "c4o" || variant.rfind("c4b", 0) == 0 || variant.rfind("c4v", 0) == 0 || variant.rfind("c4l", 0) == 0 || variant.rfind("c4x", 0) == 0; }
 static bool g_scene_has_alpha_tested_materials = false; /* = what the renderer passes as B2PT_ALPHA_TEST */
 
 /* The MegaKernel the way the phased and wavefront GPU kernels run it (b2_kernels.cu: megakernel_phased, b2_wavefront.h): one path

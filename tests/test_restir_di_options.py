@@ -1,6 +1,6 @@
 """ReSTIR DI kernel options beyond the bias-correction weights: the four visibility macros of ReSTIRDIOptions.h:50-84 (variants c4v<N>)
-the later-bounces sampling strategy (:140, variants c4l<N>), uniform light presampling (:162, c4pu) and combinations of them with the
-bias-correction weights (c4x<N>). Fixtures in tests/golden/options/ (tools/make_goldens.py, from the
+the later-bounces sampling strategy (:140, variants c4l<N>), uniform light presampling (:162, c4pu), optimal visibility sampling (:176, c4o) and combinations of them with
+the bias-correction weights (c4x<N>). Fixtures in tests/golden/options/ (tools/make_goldens.py, from the
 reference compiled with the macro: oracle/_ref/ref_render_<variant>).
  * CPU: oracle/_ref reproduces its fixtures; oracle/_port (host build of the product's headers) matches them bit for bit.
  * GPU: the CUDA precise flavour matches them bit for bit, the fast flavour statistically -- the bars of tests/test_gpu_parity.py.
@@ -51,6 +51,18 @@ def test_port_staged_megakernel_matches_golden(built, name, tmp_path):
     a = _args(meta)
     r = run_oracle("port", a["variant"], a["scene"], a["width"], a["height"], a["spp"], a["bounces"], tmp_path, (*a["extra"], "--staged"))
     assert pixels_not_bit_identical(r["framebuffer"], g["framebuffer"]) == 0
+
+
+@pytest.mark.parametrize("name", ["c4_96x54_fused", "c4_96x54_split", "c4_synenv_96x54_fused"])
+def test_member_rename_alone_changes_nothing(built, name, tmp_path):
+    """The optimal-visibility-sampling oracle (ref_render_c4o) is the reference built with -Dlast_hit_primitive_index=primitive_index, without
+    which that option does not compile (OptimalVisibilitySampling.h:34). ref_render_c4r is built with the rename ALONE: it must reproduce
+    the fixtures of the plain c4 build bit for bit, i.e. the rename only touches the one expression that did not compile."""
+    g, meta = load_golden(name)
+    a = _args(meta)
+    r = run_oracle("ref", "c4r", a["scene"], a["width"], a["height"], a["spp"], a["bounces"], tmp_path, a["extra"])
+    assert np.array_equal(r["prim"], g["gbuffer_prim"])
+    assert np.array_equal(r["framebuffer"].ravel().view(np.uint32), g["framebuffer"].view(np.uint32))
 
 
 @pytest.mark.parametrize("neighbors", [0, 6, 7, 40])

@@ -101,11 +101,16 @@ CASES = [
     ("c4x1_syn_96x54_split_directional", "c4x1", "synthetic_20k", 96, 54, 2, 4, ["--no-fused", "--no-confidence-weights", "--directional-reuse"]),
     ("c4x2_synenv_96x54_fused_8neighbors", "c4x2", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env", "--neighbors", "8"]),
     ("c4x2_syn_96x54_split2", "c4x2", "synthetic_20k", 96, 54, 2, 4, ["--no-fused", "--spatial-passes", "2"]),
+    # ReSTIR_DI_DoOptimalVisibilitySampling (variant "c4o"; the spatial pass reads it). The reference needs -Dlast_hit_primitive_index=
+    # primitive_index to compile with it (oracle/Makefile: c4o, and c4r = the rename alone, which reproduces c4's fixtures)
+    ("c4o_96x54_split", "c4o", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused"]),
+    ("c4o_synenv_96x54_split", "c4o", "synthetic_20k", 96, 54, 3, 4, ["--no-fused", "--envmap", "data/sky_128x64.b2env"]),
+    ("c4o_96x54_split2_3neighbors", "c4o", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused", "--spatial-passes", "2", "--neighbors", "3"]),
 ]
 EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
 # fixtures of kernel options added after the round's GPU budget was spent live in tests/golden/options/ and are tested by
 # tests/test_restir_di_options.py, which runs after the suites whose CUDA side has been seen green on a B200
-OPTIONS_PREFIXES = ("c4v", "c4l", "c4pu", "c4x")
+OPTIONS_PREFIXES = ("c4v", "c4l", "c4pu", "c4x", "c4o")
 
 
 def run_case(name, variant, scene, w, h, spp, bounces, extra):
