@@ -711,7 +711,8 @@ static int resolve_kernel(const char* entry_name, const b2pt_option* options, in
     if (light_presampling && presampling_strategy == 0)
         light_presampling = 2;
     {
-        const bool built = bias_correction >= 1 && bias_correction <= 7;
+        /* 1/M (0): the reference's spatial pass does not compile with it; its temporal and fused passes do, and are served */
+        const bool built = (bias_correction >= 1 && bias_correction <= 7) || (bias_correction == 0 && pass != B2_PASS_RESTIR_DI_SPATIAL);
         const bool reuse_pass = pass == B2_PASS_RESTIR_DI_TEMPORAL || pass == B2_PASS_RESTIR_DI_SPATIAL || pass == B2_PASS_RESTIR_DI_SPATIOTEMPORAL;
         if (reuse_pass && !built)
         {

@@ -167,6 +167,7 @@ const VariantKey kVariants[] = {
     { "c4pu", 0, 5, 1, 3, true, true, 4, 4 | 8, 0 }, /* ... and ReSTIR_DI_LightPresamplingStrategy = LSS_BASE_UNIFORM */
     /* c4 with another ReSTIR_DI_BiasCorrectionWeights (ReSTIRDIOptions.h:9-16): 1/Z, MIS-like, generalised balance heuristic, defensive
      * pairwise MIS, symmetric and asymmetric ratio */
+    { "c4b0", 0, 5, 1, 3, true, false, 0 }, /* 1/M: fused pass, or temporal reuse alone (restir_di_do_spatial_reuse_pass = 0) */
     { "c4b1", 0, 5, 1, 3, true, false, 1 },
     { "c4b2", 0, 5, 1, 3, true, false, 2 },
     { "c4b3", 0, 5, 1, 3, true, false, 3 },
@@ -235,6 +236,8 @@ bool variant_has_pass(const VariantKey* v, int pass)
     bool restir_pass = pass != B2_PASS_CAMERA_RAYS && pass != B2_PASS_MEGAKERNEL;
     if (restir_pass && !v->restir)
         return false;
+    if (pass == B2_PASS_RESTIR_DI_SPATIAL && v->bias_correction == 0)
+        return false; /* 1/M: no spatial reuse kernel (the reference's does not compile with these weights); fused or temporal-only reuse */
     return pass != B2_PASS_RESTIR_DI_PRESAMPLING || v->presampling;
 }
 

@@ -1167,7 +1167,7 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
             target_function_at_center = di_target_function_bias<V>(ctx, temporal_neighbor_reservoir.sample, center_pixel_surface);
 
         float temporal_neighbor_resampling_mis_weight;
-        if (bias == B2_BIAS_1_OVER_Z)
+        if (bias == B2_BIAS_1_OVER_Z || bias == B2_BIAS_1_OVER_M)
             temporal_neighbor_resampling_mis_weight = (float)temporal_neighbor_reservoir.M;
         else if (bias == B2_BIAS_MIS_LIKE)
             temporal_neighbor_resampling_mis_weight = use_confidence_weights ? (float)temporal_neighbor_reservoir.M : 1.0f;
@@ -1252,7 +1252,7 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
     }
 
     float initial_candidates_mis_weight;
-    if (bias == B2_BIAS_1_OVER_Z)
+    if (bias == B2_BIAS_1_OVER_Z || bias == B2_BIAS_1_OVER_M)
         initial_candidates_mis_weight = (float)initial_candidates_reservoir.M;
     else if (bias == B2_BIAS_MIS_LIKE)
         initial_candidates_mis_weight = use_confidence_weights ? (float)initial_candidates_reservoir.M : 1.0f;
@@ -1283,6 +1283,8 @@ B2_HD void restir_di_temporal_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
     /* TemporalNormalizationWeight.h: 1/Z counts the confidence of the reservoirs that could have produced the chosen sample, MIS-like
      * weighs the chosen one against both; the others put everything into the resampling weights */
     float normalization_numerator = 1.0f, normalization_denominator = 1.0f;
+    if (bias == B2_BIAS_1_OVER_M && !(out.weight_sum <= 0.0f))
+        normalization_denominator = (float)(initial_candidates_reservoir.M + temporal_neighbor_reservoir.M); /* TemporalNormalizationWeight.h:38-54: every sample counted, biased */
     if ((bias == B2_BIAS_1_OVER_Z || bias == B2_BIAS_MIS_LIKE) && !(out.weight_sum <= 0.0f))
     {
         float center_pixel_target_function = di_target_function_bias<V>(ctx, out.sample, center_pixel_surface);
@@ -1959,7 +1961,7 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
     };
     /* one resampling weight: `resampled` seen from the centre pixel has target_function_at_center */
     auto resampling_weight = [&](const DiReservoir& resampled, float target_function_at_center, int neighbor_pixel_index, int current_neighbor, bool canonical) {
-        if (bias == B2_BIAS_1_OVER_Z)
+        if (bias == B2_BIAS_1_OVER_Z || bias == B2_BIAS_1_OVER_M)
             return (float)resampled.M;
         if (bias == B2_BIAS_MIS_LIKE)
             return use_confidence_weights ? (float)resampled.M : 1.0f;
@@ -2073,6 +2075,13 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
 
     /* SpatiotemporalNormalizationWeight.h: 1/Z (:84-147), MIS-like (:149-229); MIS-like rebuilds the surfaces from the current G-buffer (:189) */
     float normalization_numerator = 1.0f, normalization_denominator = 1.0f;
+    if (bias == B2_BIAS_1_OVER_M && !(out.weight_sum <= 0.0f))
+    {
+        /* SpatiotemporalNormalizationWeight.h:19-77: the confidence of every neighbour that passes the heuristics, whatever it could have produced */
+        normalization_denominator = 0.0f;
+        for_all_spatial_neighbors(prev_gbuffer, [&](int, int M_j, DiSurface&) { normalization_denominator += (float)M_j; });
+        normalization_denominator += (float)temporal_neighbor_reservoir.M;
+    }
     if ((bias == B2_BIAS_1_OVER_Z || bias == B2_BIAS_MIS_LIKE) && !(out.weight_sum <= 0.0f))
     {
         const DiSample final_reservoir_sample = out.sample;
@@ -2109,7 +2118,7 @@ B2_HD void restir_di_spatiotemporal_inplace_pixel(const Ctx& ctx, uint32_t x, ui
     }
     out.end_with_normalization(normalization_numerator, normalization_denominator);
 
-    if (bias != B2_BIAS_MIS_LIKE && bias != B2_BIAS_MIS_GBH && di_end_of_pass_visibility_reuse(ctx) &&
+    if (bias != B2_BIAS_1_OVER_M && bias != B2_BIAS_MIS_LIKE && bias != B2_BIAS_MIS_GBH && di_end_of_pass_visibility_reuse(ctx) &&
         (di.common_temporal_pass.do_temporal_reuse_pass || di.common_spatial_pass.number_of_passes - 1 != di.common_spatial_pass.spatial_pass_index))
         di_visibility_test_kill_reservoir(ctx, out, center_pixel_surface.shading_point, center_pixel_surface.primitive_index);
 

@@ -158,8 +158,8 @@ int b2pt_bvh_destroy(b2pt_ctx* ctx, b2pt_bvh* bvh);
  * from a per-ray generator, not from the path's (see csrc/b2_bvh.h): images agree with the reference's statistically.
  * {"ReSTIR_DI_BiasCorrectionWeights", N} (ReSTIRDIOptions.h:9-16,120): "ReSTIR_DI_TemporalReuse", "ReSTIR_DI_SpatialReuse" and
  * "ReSTIR_DI_SpatiotemporalReuse" are served for N = 1 (1/Z), 2 (MIS-like), 3 (generalised balance heuristic), 4 (pairwise MIS, the
- * default), 5 (defensive pairwise MIS), 6 (symmetric ratio) and 7 (asymmetric ratio); 0 (1/M, which the reference itself does not
- * compile) answers B2PT_ERR_NO_VARIANT.
+ * default), 5 (defensive pairwise MIS), 6 (symmetric ratio) and 7 (asymmetric ratio); 0 (1/M) for the temporal and the fused pass --
+ * the reference's spatial pass does not compile with 1/M (SpatialReuse.h:237) and "ReSTIR_DI_SpatialReuse" answers B2PT_ERR_NO_VARIANT.
  * {"ReSTIR_DI_InitialTargetFunctionVisibility", 0|1}, {"ReSTIR_DI_SpatialTargetFunctionVisibility", 0|1}, {"ReSTIR_DI_DoVisibilityReuse", 0|1},
  * {"ReSTIR_DI_BiasCorrectionUseVisibility", 0|1} (ReSTIRDIOptions.h:50-84; defaults 0, 0, 1, 1): launch-time switches of the ReSTIR DI
  * passes; give the same values to every ReSTIR DI kernel of a renderer, as the reference's global compiler options do.
@@ -252,8 +252,8 @@ int b2pt_kernel_launch_partition(b2pt_kernel* kernel, int width, int height, int
  * (2) headless renderer (host mirror of GPURenderer, CPURenderer pass order)
  * ------------------------------------------------------------------------------------------------------------ */
 
-/* variant: "c1" | "c2" | "c3" | "c4" | "c4p" (= c4 + ReSTIR DI light presampling) | "c4pu" (= c4p with uniform instead of power presampling) | "c4b1" "c4b2" "c4b3" "c4b5" "c4b6" "c4b7" (= c4 with
- * ReSTIR_DI_BiasCorrectionWeights 1 / 2 / 3 / 5 / 6 / 7) | "c4v1" .. "c4v5" (= c4 with the ReSTIR DI visibility macros away from their
+/* variant: "c1" | "c2" | "c3" | "c4" | "c4p" (= c4 + ReSTIR DI light presampling) | "c4pu" (= c4p with uniform instead of power presampling) | "c4b0" "c4b1" "c4b2" "c4b3" "c4b5" "c4b6" "c4b7" (= c4 with
+ * ReSTIR_DI_BiasCorrectionWeights 0 / 1 / 2 / 3 / 5 / 6 / 7; c4b0 has no spatial reuse pass) | "c4v1" .. "c4v5" (= c4 with the ReSTIR DI visibility macros away from their
  * defaults: InitialTargetFunctionVisibility on / SpatialTargetFunctionVisibility on / DoVisibilityReuse off / BiasCorrectionUseVisibility
  * off / the first three together) | "c4l0" "c4l1" "c4l2" (= c4 with ReSTIR_DI_LaterBouncesSamplingStrategy 0 / 1 / 2: uniform one light /
  * BSDF only / light + BSDF MIS at the bounces after the first) | "c4o" (= c4 with ReSTIR_DI_DoOptimalVisibilitySampling) | "c4x1" "c4x2" (= two combinations of the above, see b2_renderer.cpp)

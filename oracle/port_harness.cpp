@@ -33,7 +33,7 @@ struct Args
     int width = 512, height = 512, spp = 1, bounces = 3;
     int win_x0 = 0, win_y0 = 0, win_x1 = -1, win_y1 = -1;
     int threads = 0;
-    bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false, kat = false, confidence_weights = true, staged = false;
+    bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false, kat = false, confidence_weights = true, staged = false, spatial_pass = true;
     int spatial_passes = 1, neighbors = -1;
     unsigned int seed = 42;
 };
@@ -68,6 +68,7 @@ static Args parse_args(int argc, char** argv)
         else if (k == "--cameras") a.cameras = next(); /* a moving camera: one B2SceneCamera (52 floats) per frame, as ref_extras_* takes it */
         else if (k == "--staged") a.staged = true; /* the MegaKernel through megakernel_stage1 / stage2, the way the GPU kernels run it */
         else if (k == "--no-confidence-weights") a.confidence_weights = false;
+        else if (k == "--no-spatial") a.spatial_pass = false;
         else if (k == "--directional-reuse") a.directional_reuse = true; /* use_adaptive_directional_spatial_reuse + the prepass */
         else { std::fprintf(stderr, "unknown argument %s\n", k.c_str()); std::exit(2); }
     }
@@ -375,6 +376,8 @@ int main(int argc, char** argv)
     rd.render_settings.restir_di_settings.common_spatial_pass.use_adaptive_directional_spatial_reuse = a.directional_reuse ? 1 : 0;
     rd.render_settings.restir_di_settings.common_spatial_pass.number_of_passes = a.spatial_passes;
     rd.render_settings.restir_di_settings.use_confidence_weights = a.confidence_weights ? 1 : 0;
+    if (!a.spatial_pass)
+        rd.render_settings.restir_di_settings.common_spatial_pass.do_spatial_reuse_pass = 0;
     if (a.neighbors >= 0)
     {
         rd.render_settings.restir_di_settings.common_spatial_pass.reuse_neighbor_count = a.neighbors;

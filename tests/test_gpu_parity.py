@@ -28,6 +28,8 @@ def make_renderer(b2pt, ctx, meta, precise=True):
         r.set(restir_di_do_fused_spatiotemporal=0 if "--no-fused" in meta.get("extra", []) else 1)
     if "--directional-reuse" in meta.get("extra", []):
         r.set(restir_di_use_adaptive_directional_spatial_reuse=1)
+    if "--no-spatial" in meta.get("extra", []):
+        r.set(restir_di_do_spatial_reuse_pass=0)
     if "--no-confidence-weights" in meta.get("extra", []):
         r.set(restir_di_use_confidence_weights=0)
     if "--neighbors" in meta.get("extra", []):

@@ -41,7 +41,8 @@ def test_kernel_query_needs_no_device(b2pt):
     assert query("MegaKernel") == 0
     assert query("MegaKernel", BSDFOverride=1, DirectLightSamplingStrategy=1, DirectLightSamplingBaseStrategy=0) == 0
     assert query("ReSTIR_DI_SpatiotemporalReuse", DirectLightSamplingStrategy=5, ReSTIR_DI_BiasCorrectionWeights=3) == 0
-    assert query("ReSTIR_DI_SpatiotemporalReuse", DirectLightSamplingStrategy=5, ReSTIR_DI_BiasCorrectionWeights=0) != 0
+    assert query("ReSTIR_DI_SpatiotemporalReuse", DirectLightSamplingStrategy=5, ReSTIR_DI_BiasCorrectionWeights=0) == 0
+    assert query("ReSTIR_DI_SpatialReuse", DirectLightSamplingStrategy=5, ReSTIR_DI_BiasCorrectionWeights=0) != 0  # 1/M: the reference's does not compile
     assert query("MegaKernel", DirectLightSamplingStrategy=5, ReSTIR_DI_LaterBouncesSamplingStrategy=1) == 0
     assert query("MegaKernel", NoSuchMacro=1) != 0
     assert query("NoSuchKernel") != 0

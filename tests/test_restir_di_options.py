@@ -134,7 +134,7 @@ def test_macros_set_one_by_one_on_a_plain_c4_renderer(b2pt, gpu_ctx):
     r.set_macro("ReSTIR_DI_SpatialTargetFunctionVisibility", 1)
     r.set_macro("ReSTIR_DI_LaterBouncesSamplingStrategy", 2)
     with pytest.raises(b2pt.B2ptError):
-        r.set_macro("ReSTIR_DI_BiasCorrectionWeights", 0)  # 1/M: not built (does not compile in the reference)
+        r.set_macro("ReSTIR_DI_BiasCorrectionWeights", 9)  # no such weights
     with pytest.raises(b2pt.B2ptError):
         r.set_macro("DirectLightSamplingStrategy", 3)  # belongs to the variant
     r.render(meta["spp"])

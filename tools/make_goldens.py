@@ -106,11 +106,17 @@ CASES = [
     ("c4o_96x54_split", "c4o", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused"]),
     ("c4o_synenv_96x54_split", "c4o", "synthetic_20k", 96, 54, 3, 4, ["--no-fused", "--envmap", "data/sky_128x64.b2env"]),
     ("c4o_96x54_split2_3neighbors", "c4o", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused", "--spatial-passes", "2", "--neighbors", "3"]),
+    # 1/M weights (variant "c4b0"): the reference's spatial reuse kernel does not compile with them (SpatialReuse.h:237), its fused and
+    # temporal kernels do -- ref_render_c4b0 is built without the spatial kernel and runs the fused pass or temporal reuse alone
+    ("c4b0_96x54_fused", "c4b0", "cornell_pbr_16x9", 96, 54, 3, 4, []),
+    ("c4b0_synenv_96x54_fused_8neighbors", "c4b0", "synthetic_20k", 96, 54, 3, 4, ["--envmap", "data/sky_128x64.b2env", "--neighbors", "8"]),
+    ("c4b0_96x54_temporal_only", "c4b0", "cornell_pbr_16x9", 96, 54, 3, 4, ["--no-fused", "--no-spatial"]),
+    ("c4b0_syn_96x54_temporal_only_noconf", "c4b0", "synthetic_20k", 96, 54, 3, 4, ["--no-fused", "--no-spatial", "--no-confidence-weights"]),
 ]
 EXTRAS_SCENES = {"cornell_textured_16x9"}  # cases rendered by ref_extras_* instead of ref_render_*
 # fixtures of kernel options added after the round's GPU budget was spent live in tests/golden/options/ and are tested by
 # tests/test_restir_di_options.py, which runs after the suites whose CUDA side has been seen green on a B200
-OPTIONS_PREFIXES = ("c4v", "c4l", "c4pu", "c4x", "c4o")
+OPTIONS_PREFIXES = ("c4v", "c4l", "c4pu", "c4x", "c4o", "c4b0")
 
 
 def run_case(name, variant, scene, w, h, spp, bounces, extra):
