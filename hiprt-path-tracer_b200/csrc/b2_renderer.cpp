@@ -918,6 +918,18 @@ int b2pt_renderer_render(b2pt_renderer* r, int samples)
     }
     r->loop.camera.sensor_width = r->width;
     r->loop.camera.sensor_height = r->height;
+    if (r->loop.restir_di)
+    {
+        /* With the fused pass on and the spatial pass off the reference's own pass order (CPURenderer.cpp:1018-1032) shades from the temporal
+         * pass's output buffer, which the fused path leaves null: its CPU renderer crashes there (tools/settings_fuzz.py), a GPU would
+         * fault. Refused instead. */
+        const b2pt_restir_di_settings& di = r->loop.rd.render_settings.restir_di_settings;
+        if (di.do_fused_spatiotemporal && !di.common_spatial_pass.do_spatial_reuse_pass)
+        {
+            b2_set_error("b2pt_renderer_render: restir_di_do_fused_spatiotemporal needs restir_di_do_spatial_reuse_pass (the reference shades from a null buffer otherwise)");
+            return B2PT_ERR_INVALID_ARGUMENT;
+        }
+    }
 
     int rc = B2PT_OK;
     auto launch = [&](B2Pass pass) {

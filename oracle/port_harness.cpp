@@ -35,6 +35,7 @@ struct Args
     int threads = 0;
     bool fused = true, dump_per_sample = false, no_jitter = false, directional_reuse = false, kat = false, confidence_weights = true, staged = false, spatial_pass = true;
     int spatial_passes = 1, neighbors = -1;
+    std::vector<std::string> pokes; /* --poke OFFSET:KIND:VALUE, as in ref_harness.cpp */
     unsigned int seed = 42;
 };
 
@@ -62,6 +63,7 @@ static Args parse_args(int argc, char** argv)
         else if (k == "--dump-per-sample") a.dump_per_sample = true;
         else if (k == "--no-jitter") a.no_jitter = true;
         else if (k == "--kat") a.kat = true; /* function-level known-answer dump instead of a render (see run_bsdf_kat) */
+        else if (k == "--poke") a.pokes.push_back(next());
         else if (k == "--neighbors") a.neighbors = std::atoi(next());
         else if (k == "--trace-ray") { a.trace_ray = true; for (int j = 0; j < 7; j++) a.ray[j] = std::strtof(next(), nullptr); a.ray_skip_prim = std::atoi(next()); }
         else if (k == "--debug-visibility") { a.debug_x = std::atoi(next()); a.debug_y = std::atoi(next()); a.debug_frame = std::atoi(next()); }
@@ -684,6 +686,19 @@ int main(int argc, char** argv)
         while (std::fread(&c, sizeof(c), 1, f) == 1)
             camera_frames.push_back(c);
         std::fclose(f);
+    }
+
+    for (const std::string& poke : a.pokes)
+    {
+        size_t offset = 0;
+        char kind = 0;
+        double value = 0.0;
+        if (std::sscanf(poke.c_str(), "%zu:%c:%lf", &offset, &kind, &value) != 3 || offset + 4 > sizeof(b2pt_render_data)) { std::fprintf(stderr, "bad --poke %s\n", poke.c_str()); return 2; }
+        char* base = reinterpret_cast<char*>(&rd) + offset;
+        if (kind == 'i') { int v = (int)value; std::memcpy(base, &v, 4); }
+        else if (kind == 'f') { float v = (float)value; std::memcpy(base, &v, 4); }
+        else if (kind == 'b') { unsigned char v = (unsigned char)value; std::memcpy(base, &v, 1); }
+        else { std::fprintf(stderr, "bad --poke kind %c\n", kind); return 2; }
     }
 
     auto start = std::chrono::high_resolution_clock::now();
