@@ -274,6 +274,7 @@ static void run_bsdf_kat(const b2pt_render_data& rd, const Args& a, int n_materi
             kat_directions((unsigned int)(m * per_material + k), normal, view, light, seed);
             Mat material = load_scene_material(rd.buffers.materials_buffer, m, rd.bsdfs_data.white_furnace_mode != 0);
             VolumeState volume_state;
+            volume_state.init(); /* = the reference's default-constructed RayVolumeState (the harness used to leave it unwritten) */
             Rng rng = make_rng(seed);
             {
                 int info = B2_LOBE_NO_INFO;
