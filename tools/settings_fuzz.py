@@ -97,10 +97,11 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--scene", default="synthetic_20k")
     ap.add_argument("--fields", type=int, default=8, help="settings changed per case")
+    ap.add_argument("--ref-exe", default="", help="path of a reference binary to use instead (e.g. a one-off zero-initialised build of another variant)")
     ap.add_argument("--reference", default="zero", choices=["zero", "render"], help="ref_zero_<variant> (ReSTIR DI variants) or the plain ref_render_<variant>")
     a = ap.parse_args()
     rng = random.Random(a.seed)
-    ref_exe = ROOT / "oracle" / "_ref" / f"ref_{a.reference}_{a.variant}"
+    ref_exe = Path(a.ref_exe) if a.ref_exe else ROOT / "oracle" / "_ref" / f"ref_{a.reference}_{a.variant}"
     port_exe = ROOT / "oracle" / "_port" / "port_render"
     if not ref_exe.exists() or not port_exe.exists():
         print(f"{ref_exe} or {port_exe} not built")
