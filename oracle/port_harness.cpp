@@ -149,6 +149,8 @@ static bool g_scene_has_alpha_tested_materials = false; /* = what the renderer p
  * carried through begin -> { trace A, stage 1, trace B, stage 2 } with the rays the stages request traced between them, instead of
  * megakernel_bounce's straight-line code. Same protocol as the device loop: unrequested rays answer "miss", deferred Y only where the
  * variant has it, the sequential ray only with RIS. */
+static int g_debug_rays_x = -1, g_debug_rays_y = -1; /* --staged --debug-visibility X Y FRAME: every ray of that pixel's path, with a brute-force check */
+
 template <class V>
 static void staged_megakernel_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
 {
@@ -171,7 +173,25 @@ static void staged_megakernel_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
         none.ng = v3(0.0f);
         if (ray.kind == B2_RAY_NONE)
             return none;
-        return b2_trace(ctx, ray.kind == B2_RAY_ANY_HIT, ray.origin, ray.direction, ray.t_max, ray.skip_prim, ray.main_path != 0);
+        B2Hit result = b2_trace(ctx, ray.kind == B2_RAY_ANY_HIT, ray.origin, ray.direction, ray.t_max, ray.skip_prim, ray.main_path != 0);
+        if ((int)x == g_debug_rays_x && (int)y == g_debug_rays_y)
+        {
+            int brute_prim = -1;
+            float brute_t = 3.0e38f;
+            for (uint32_t i = 0; i < ctx.bvh.tri_count; i++)
+            {
+                const B2Tri& tri = ctx.bvh.tris[i];
+                float t, u, v;
+                if (tri.prim != ray.skip_prim && b2_intersect_triangle(ray.origin, ray.direction, v3(tri.ax, tri.ay, tri.az), v3(tri.e1x, tri.e1y, tri.e1z), v3(tri.e2x, tri.e2y, tri.e2z), t, u, v) && t < brute_t)
+                {
+                    brute_t = t;
+                    brute_prim = tri.prim;
+                }
+            }
+            std::fprintf(stderr, "ray %s o %.9g %.9g %.9g d %.9g %.9g %.9g tmax %.9g skip %d -> prim %d t %.9g | brute force nearest prim %d t %.9g\n", ray.kind == B2_RAY_ANY_HIT ? "shadow " : "closest",
+                         ray.origin.x, ray.origin.y, ray.origin.z, ray.direction.x, ray.direction.y, ray.direction.z, ray.t_max, ray.skip_prim, result.prim, result.t, brute_prim, brute_t);
+        }
+        return result;
     };
     PathState s;
     BouncePhase<V> ph;
@@ -207,6 +227,9 @@ static void staged_megakernel_pixel(const Ctx& ctx, uint32_t x, uint32_t y)
     }
 }
 
+static int g_current_frame = 0;
+static bool frame_of_debug(const Args& a) { return a.debug_x >= 0 && g_current_frame == a.debug_frame; }
+
 template <class V>
 static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice& bvh, const Args& a)
 {
@@ -231,6 +254,11 @@ static void run_pass(B2Pass pass, const b2pt_render_data& rd, const B2BvhDevice&
         for (int y = a.win_y0; y < a.win_y1; y++)
             for (int x = a.win_x0; x < a.win_x1; x++)
             {
+                if (a.staged && frame_of_debug(a))
+                {
+                    g_debug_rays_x = a.debug_x;
+                    g_debug_rays_y = a.debug_y;
+                }
                 if (pass == B2_PASS_MEGAKERNEL && a.staged)
                     staged_megakernel_pixel<V>(ctx, (uint32_t)x, (uint32_t)y);
                 else
@@ -714,6 +742,7 @@ int main(int argc, char** argv)
             loop.camera.position = b2pt_float3{ c.position[0], c.position[1], c.position[2] };
             loop.camera.vertical_fov = c.vertical_fov;
         }
+        g_current_frame = frame;
         loop.render_one_sample(launch);
         if (a.dump_per_sample)
         {
